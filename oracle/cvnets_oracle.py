@@ -1,0 +1,351 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY. Not part of the product path.
+
+A CPU (fp32, plain PyTorch) restatement of the apple/ml-cvnets vision-backbone hot path that
+``BASELINE.json:north_star`` names: ConvLayer2d(+BN+SiLU), InvertedResidual, LinearSelfAttention,
+LinearAttnFFN, MobileViTBlockv2 and the MobileViTv2 classifier that assembles them.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this file.
+The product (``ml-cvnets_b200``) never does: it fails loudly when its CUDA library is missing.
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real reference from
+``/root/reference`` (possible only in the build container), runs the reference ``nn.Module``s on seeded
+inputs and commits their outputs/gradients under ``tests/golden/``; ``tests/test_oracle_golden.py``
+checks every function below against those fixtures (fp32, atol/rtol 1e-5 class).
+
+Every function is a *functional* restatement: parameters arrive in a flat ``dict`` keyed exactly like
+the reference ``state_dict``, so nothing here depends on the product's module
+classes.  All citations are relative to the reference checkout (``/root/reference``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+BN_EPS = 1e-5  # cvnets/layers/normalization/batch_norm.py:31-47 (nn.BatchNorm2d default eps)
+GN_EPS = 1e-5  # cvnets/layers/normalization/layer_norm.py:93-103 (nn.GroupNorm(1, C, eps=1e-5))
+
+
+# --------------------------------------------------------------------------------------------
+# configuration (cvnets/models/classification/config/mobilevit_v2.py:11-77, utils/math_utils.py:9-35)
+# --------------------------------------------------------------------------------------------
+def make_divisible(v, divisor: int = 8, min_value=None):
+    """utils/math_utils.py:9-30."""
+    if min_value is None:
+        min_value = divisor
+    new_v = max(min_value, int(v + divisor / 2) // divisor * divisor)
+    if new_v < 0.9 * v:
+        new_v += divisor
+    return new_v
+
+
+def mobilevit_v2_config(width_multiplier: float = 1.0) -> Dict:
+    """cvnets/models/classification/config/mobilevit_v2.py:11-77."""
+    wm = width_multiplier
+    layer_0_dim = max(16, min(64, 32 * wm))
+    layer_0_dim = int(make_divisible(layer_0_dim, divisor=8, min_value=16))
+    return {
+        "layer0": {"img_channels": 3, "out_channels": layer_0_dim},
+        "layer1": {"out_channels": int(make_divisible(64 * wm, divisor=16)), "expand_ratio": 2,
+                   "num_blocks": 1, "stride": 1, "block_type": "mv2"},
+        "layer2": {"out_channels": int(make_divisible(128 * wm, divisor=8)), "expand_ratio": 2,
+                   "num_blocks": 2, "stride": 2, "block_type": "mv2"},
+        "layer3": {"out_channels": int(make_divisible(256 * wm, divisor=8)),
+                   "attn_unit_dim": int(make_divisible(128 * wm, divisor=8)), "ffn_multiplier": 2,
+                   "attn_blocks": 2, "patch_h": 2, "patch_w": 2, "stride": 2, "mv_expand_ratio": 2,
+                   "block_type": "mobilevit"},
+        "layer4": {"out_channels": int(make_divisible(384 * wm, divisor=8)),
+                   "attn_unit_dim": int(make_divisible(192 * wm, divisor=8)), "ffn_multiplier": 2,
+                   "attn_blocks": 4, "patch_h": 2, "patch_w": 2, "stride": 2, "mv_expand_ratio": 2,
+                   "block_type": "mobilevit"},
+        "layer5": {"out_channels": int(make_divisible(512 * wm, divisor=8)),
+                   "attn_unit_dim": int(make_divisible(256 * wm, divisor=8)), "ffn_multiplier": 2,
+                   "attn_blocks": 3, "patch_h": 2, "patch_w": 2, "stride": 2, "mv_expand_ratio": 2,
+                   "block_type": "mobilevit"},
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# layers
+# --------------------------------------------------------------------------------------------
+def batch_norm(P: Params, pre: str, x: Tensor, training: bool, momentum: float = 0.1) -> Tensor:
+    """cvnets/layers/normalization/batch_norm.py:14-49 == nn.BatchNorm2d(eps=1e-5, momentum=0.1).
+
+    Training: batch mean / biased var normalise; running stats get the EMA with *unbiased* var and
+    ``num_batches_tracked += 1``.  ``P`` buffers are updated in place like the module.
+    """
+    rm, rv = P[pre + ".running_mean"], P[pre + ".running_var"]
+    if training and (pre + ".num_batches_tracked") in P:
+        P[pre + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, rm, rv, P[pre + ".weight"], P[pre + ".bias"], training, momentum, BN_EPS)
+
+
+def conv_layer_2d(P: Params, pre: str, x: Tensor, *, stride: int = 1, groups: int = 1, use_norm: bool = True,
+                  use_act: bool = True, training: bool = True, momentum: float = 0.1) -> Tensor:
+    """ConvLayer2d = Sequential(conv[, norm][, act]) (cvnets/layers/conv_layer.py:200-226,254-255).
+
+    Auto padding ``(k-1)//2`` (``:182-185``); norm = BatchNorm2d (``model.normalization.name=batch_norm``,
+    ``:138-144``); act = Swish == nn.SiLU (cvnets/layers/activation/swish.py:13-20).
+    """
+    w = P[pre + ".block.conv.weight"]
+    b = P.get(pre + ".block.conv.bias")
+    k = w.shape[-1]
+    x = F.conv2d(x, w, b, stride=stride, padding=(k - 1) // 2, groups=groups)
+    if use_norm:
+        x = batch_norm(P, pre + ".block.norm", x, training, momentum)
+    if use_act:
+        x = F.silu(x)
+    return x
+
+
+def layer_norm_2d(P: Params, pre: str, x: Tensor) -> Tensor:
+    """LayerNorm2D_NCHW == nn.GroupNorm(num_groups=1) (cvnets/layers/normalization/layer_norm.py:75-108):
+    statistics over all of (C, P, N) per sample, per-channel affine."""
+    return F.group_norm(x, 1, P[pre + ".weight"], P[pre + ".bias"], GN_EPS)
+
+
+def linear_self_attention(P: Params, pre: str, x: Tensor) -> Tensor:
+    """LinearSelfAttention._forward_self_attn (cvnets/layers/linear_attention.py:134-161).
+
+    x: [B, d, P, N].  qkv 1x1 (d -> 1+2d, bias) -> split [1, d, d] -> softmax over N (dim=-1) ->
+    ctx = sum_N(key * scores) -> relu(value) * ctx -> out_proj 1x1 (d -> d, bias).
+    """
+    d = x.shape[1]
+    qkv = F.conv2d(x, P[pre + ".qkv_proj.block.conv.weight"], P[pre + ".qkv_proj.block.conv.bias"])
+    query, key, value = torch.split(qkv, [1, d, d], dim=1)
+    context_scores = F.softmax(query, dim=-1)
+    context_vector = (key * context_scores).sum(dim=-1, keepdim=True)
+    out = F.relu(value) * context_vector.expand_as(value)
+    return F.conv2d(out, P[pre + ".out_proj.block.conv.weight"], P[pre + ".out_proj.block.conv.bias"])
+
+
+def linear_attn_ffn(P: Params, pre: str, x: Tensor) -> Tensor:
+    """LinearAttnFFN.forward, self-attention branch (cvnets/modules/transformer.py:248-264), dropout p=0.
+
+    x = x + LSA(GN1(x));  x = x + conv1x1(silu(conv1x1(GN1(x)))).  Child indices: pre_norm_attn.{0,1},
+    pre_norm_ffn.{0,1,3} (``:192-228``).
+    """
+    a = layer_norm_2d(P, pre + ".pre_norm_attn.0", x)
+    x = x + linear_self_attention(P, pre + ".pre_norm_attn.1", a)
+    f = layer_norm_2d(P, pre + ".pre_norm_ffn.0", x)
+    f = F.silu(F.conv2d(f, P[pre + ".pre_norm_ffn.1.block.conv.weight"], P[pre + ".pre_norm_ffn.1.block.conv.bias"]))
+    f = F.conv2d(f, P[pre + ".pre_norm_ffn.3.block.conv.weight"], P[pre + ".pre_norm_ffn.3.block.conv.bias"])
+    return x + f
+
+
+# --------------------------------------------------------------------------------------------
+# modules
+# --------------------------------------------------------------------------------------------
+def inverted_residual(P: Params, pre: str, x: Tensor, *, stride: int, training: bool = True,
+                      momentum: float = 0.1) -> Tensor:
+    """InvertedResidual (cvnets/modules/mobilenetv2.py:141-246): exp_1x1 (if present) -> conv_3x3 depthwise
+    (stride) -> red_1x1 (no act); residual iff stride==1 and Cin==Cout (``:227-235``)."""
+    y = x
+    if (pre + ".block.exp_1x1.block.conv.weight") in P:
+        y = conv_layer_2d(P, pre + ".block.exp_1x1", y, training=training, momentum=momentum)
+    hid = P[pre + ".block.conv_3x3.block.conv.weight"].shape[0]
+    y = conv_layer_2d(P, pre + ".block.conv_3x3", y, stride=stride, groups=hid, training=training, momentum=momentum)
+    y = conv_layer_2d(P, pre + ".block.red_1x1", y, use_act=False, training=training, momentum=momentum)
+    cout = P[pre + ".block.red_1x1.block.conv.weight"].shape[0]
+    if stride == 1 and x.shape[1] == cout:
+        y = x + y
+    return y
+
+
+def unfolding(fm: Tensor, ph: int = 2, pw: int = 2) -> Tuple[Tensor, Tuple[int, int]]:
+    """MobileViTBlockv2.unfolding_pytorch (cvnets/modules/mobilevit_block.py:526-540)."""
+    B, C, H, W = fm.shape
+    patches = F.unfold(fm, kernel_size=(ph, pw), stride=(ph, pw))
+    return patches.reshape(B, C, ph * pw, -1), (H, W)
+
+
+def folding(patches: Tensor, output_size: Tuple[int, int], ph: int = 2, pw: int = 2) -> Tensor:
+    """MobileViTBlockv2.folding_pytorch (cvnets/modules/mobilevit_block.py:542-555)."""
+    B, C, Pp, N = patches.shape
+    return F.fold(patches.reshape(B, C * Pp, N), output_size=output_size, kernel_size=(ph, pw), stride=(ph, pw))
+
+
+def mobilevit_block_v2(P: Params, pre: str, x: Tensor, *, n_attn_blocks: int, patch_h: int = 2, patch_w: int = 2,
+                       training: bool = True, momentum: float = 0.1) -> Tensor:
+    """MobileViTBlockv2.forward_spatial (cvnets/modules/mobilevit_block.py:605-626):
+    local_rep (dw3x3+BN+SiLU, 1x1) -> unfold -> n x LinearAttnFFN -> layer_norm_2d -> fold -> conv_proj 1x1 + BN.
+    Input H, W must be multiples of the patch (the bilinear ``resize_input_if_needed`` ``:595-603`` never fires
+    at 256x256 and is out of scope)."""
+    C = x.shape[1]
+    assert x.shape[2] % patch_h == 0 and x.shape[3] % patch_w == 0
+    fm = conv_layer_2d(P, pre + ".local_rep.0", x, groups=C, training=training, momentum=momentum)
+    fm = conv_layer_2d(P, pre + ".local_rep.1", fm, use_norm=False, use_act=False)
+    patches, out_size = unfolding(fm, patch_h, patch_w)
+    for i in range(n_attn_blocks):
+        patches = linear_attn_ffn(P, f"{pre}.global_rep.{i}", patches)
+    patches = layer_norm_2d(P, f"{pre}.global_rep.{n_attn_blocks}", patches)
+    fm = folding(patches, out_size, patch_h, patch_w)
+    return conv_layer_2d(P, pre + ".conv_proj", fm, use_act=False, training=training, momentum=momentum)
+
+
+# --------------------------------------------------------------------------------------------
+# model
+# --------------------------------------------------------------------------------------------
+def mobilevit_v2_layout(width_multiplier: float = 1.0) -> List[Tuple[str, str, Dict]]:
+    """Stage wiring of MobileViTv2.__init__/_make_layer (cvnets/models/classification/mobilevit_v2.py:25-226),
+    as a flat list of (kind, state_dict prefix, kwargs)."""
+    cfg = mobilevit_v2_config(width_multiplier)
+    out: List[Tuple[str, str, Dict]] = [("stem", "conv_1", {})]
+    for li in range(1, 6):
+        c = cfg[f"layer{li}"]
+        if c["block_type"] == "mv2":
+            for i in range(c["num_blocks"]):
+                out.append(("ir", f"layer_{li}.{i}", {"stride": c["stride"] if i == 0 else 1}))
+        else:
+            out.append(("ir", f"layer_{li}.0", {"stride": 2}))
+            out.append(("mvit", f"layer_{li}.1", {"n_attn_blocks": c["attn_blocks"]}))
+    return out
+
+
+def mobilevit_v2_forward(P: Params, x: Tensor, *, width_multiplier: float = 1.0, training: bool = True,
+                         momentum: float = 0.1, return_stages: bool = False):
+    """BaseImageEncoder.forward -> extract_features -> classifier
+    (cvnets/models/classification/base_image_encoder.py:261-301; mobilevit_v2.py:37-45,91-94)."""
+    stages = {}
+    for kind, pre, kw in mobilevit_v2_layout(width_multiplier):
+        if kind == "stem":
+            x = conv_layer_2d(P, pre, x, stride=2, training=training, momentum=momentum)
+        elif kind == "ir":
+            x = inverted_residual(P, pre, x, stride=kw["stride"], training=training, momentum=momentum)
+        else:
+            x = mobilevit_block_v2(P, pre, x, n_attn_blocks=kw["n_attn_blocks"], training=training, momentum=momentum)
+        stages[pre] = x
+    x = x.mean(dim=[-2, -1])  # GlobalPool(mean) cvnets/layers/global_pool.py:60-71
+    logits = F.linear(x, P["classifier.1.weight"], P["classifier.1.bias"])  # cvnets/layers/linear_layer.py:90
+    return (logits, stages) if return_stages else logits
+
+
+# --------------------------------------------------------------------------------------------
+# parameter construction (shape contract: SURVEY.md App. B) + deterministic seeding used by the golden files
+# --------------------------------------------------------------------------------------------
+def _conv_bn(P: Dict, pre: str, cin: int, cout: int, k: int, groups: int = 1, norm: bool = True, bias: bool = False):
+    P[pre + ".block.conv.weight"] = torch.empty(cout, cin // groups, k, k)
+    if bias:
+        P[pre + ".block.conv.bias"] = torch.empty(cout)
+    if norm:
+        P[pre + ".block.norm.weight"] = torch.empty(cout)
+        P[pre + ".block.norm.bias"] = torch.empty(cout)
+        P[pre + ".block.norm.running_mean"] = torch.empty(cout)
+        P[pre + ".block.norm.running_var"] = torch.empty(cout)
+        P[pre + ".block.norm.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+
+def inverted_residual_shapes(P: Dict, pre: str, cin: int, cout: int, expand_ratio: float = 2):
+    hid = make_divisible(int(round(cin * expand_ratio)), 8)  # mobilenetv2.py:176
+    if expand_ratio != 1:
+        _conv_bn(P, pre + ".block.exp_1x1", cin, hid, 1)
+    _conv_bn(P, pre + ".block.conv_3x3", hid, hid, 3, groups=hid)
+    _conv_bn(P, pre + ".block.red_1x1", hid, cout, 1)
+
+
+def _gn(P: Dict, pre: str, c: int):
+    P[pre + ".weight"] = torch.empty(c)
+    P[pre + ".bias"] = torch.empty(c)
+
+
+def linear_attn_ffn_shapes(P: Dict, pre: str, d: int, ffn: int):
+    _gn(P, pre + ".pre_norm_attn.0", d)
+    _conv_bn(P, pre + ".pre_norm_attn.1.qkv_proj", d, 1 + 2 * d, 1, norm=False, bias=True)
+    _conv_bn(P, pre + ".pre_norm_attn.1.out_proj", d, d, 1, norm=False, bias=True)
+    _gn(P, pre + ".pre_norm_ffn.0", d)
+    _conv_bn(P, pre + ".pre_norm_ffn.1", d, ffn, 1, norm=False, bias=True)
+    _conv_bn(P, pre + ".pre_norm_ffn.3", ffn, d, 1, norm=False, bias=True)
+
+
+def mobilevit_block_v2_shapes(P: Dict, pre: str, c: int, d: int, n_attn_blocks: int, ffn_multiplier: float = 2.0):
+    _conv_bn(P, pre + ".local_rep.0", c, c, 3, groups=c)
+    _conv_bn(P, pre + ".local_rep.1", c, d, 1, norm=False)
+    ffn = int((ffn_multiplier * d) // 16 * 16)  # mobilevit_block.py:475
+    for i in range(n_attn_blocks):
+        linear_attn_ffn_shapes(P, f"{pre}.global_rep.{i}", d, ffn)
+    _gn(P, f"{pre}.global_rep.{n_attn_blocks}", d)
+    _conv_bn(P, pre + ".conv_proj", d, c, 1)
+
+
+def mobilevit_v2_shapes(width_multiplier: float = 1.0, n_classes: int = 1000) -> Dict[str, Tensor]:
+    cfg = mobilevit_v2_config(width_multiplier)
+    P: Dict[str, Tensor] = {}
+    c = cfg["layer0"]["out_channels"]
+    _conv_bn(P, "conv_1", 3, c, 3)
+    for li in range(1, 6):
+        lc = cfg[f"layer{li}"]
+        co = lc["out_channels"]
+        if lc["block_type"] == "mv2":
+            for i in range(lc["num_blocks"]):
+                inverted_residual_shapes(P, f"layer_{li}.{i}", c, co, lc["expand_ratio"])
+                c = co
+        else:
+            inverted_residual_shapes(P, f"layer_{li}.0", c, co, lc["mv_expand_ratio"])
+            c = co
+            mobilevit_block_v2_shapes(P, f"layer_{li}.1", c, lc["attn_unit_dim"], lc["attn_blocks"], lc["ffn_multiplier"])
+    P["classifier.1.weight"] = torch.empty(n_classes, c)
+    P["classifier.1.bias"] = torch.empty(n_classes)
+    return P
+
+
+def seeded_fill_(P: Dict[str, Tensor], seed: int) -> Dict[str, Tensor]:
+    """Deterministic, reference-independent parameter values (CPU generator, sorted key order) so the golden
+    fixtures only need to store outputs.  Non-trivial BN/GN affine and running stats on purpose."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for k in sorted(P.keys()):
+        t = P[k]
+        if k.endswith("num_batches_tracked"):
+            t.zero_()
+        elif k.endswith("running_mean"):
+            t.copy_(0.1 * torch.randn(t.shape, generator=g))
+        elif k.endswith("running_var"):
+            t.copy_(1.0 + 0.2 * torch.rand(t.shape, generator=g))
+        elif t.dim() == 1 and k.endswith(".weight"):  # BN / GN gamma
+            t.copy_(1.0 + 0.2 * torch.randn(t.shape, generator=g))
+        elif t.dim() == 1:  # biases, beta
+            t.copy_(0.1 * torch.randn(t.shape, generator=g))
+        else:
+            fan_in = t[0].numel()
+            t.copy_(torch.randn(t.shape, generator=g) * (1.0 / math.sqrt(fan_in)))
+    return P
+
+
+def seeded_input(shape, seed: int) -> Tensor:
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(shape, generator=g)
+
+
+def clone_params(P: Params, requires_grad: bool = True, device=None, dtype=None) -> Params:
+    out = {}
+    for k, v in P.items():
+        v = v.detach().clone()
+        if device is not None:
+            v = v.to(device)
+        if v.is_floating_point():
+            if dtype is not None:
+                v = v.to(dtype)
+            is_buffer = k.endswith("running_mean") or k.endswith("running_var")
+            v.requires_grad_(requires_grad and not is_buffer)
+        out[k] = v
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# the training step the metric is quoted on: fwd + CE(label_smoothing=0.1) + bwd + AdamW
+# --------------------------------------------------------------------------------------------
+def training_step(P: Params, opt: Optional[torch.optim.Optimizer], x: Tensor, y: Tensor, width_multiplier: float = 1.0):
+    """One reference-style step: engine/training_engine.py:257-307 restated without AMP (CPU refuses AMP,
+    engine/utils.py:31-32).  Returns the loss value."""
+    logits = mobilevit_v2_forward(P, x, width_multiplier=width_multiplier, training=True)
+    loss = F.cross_entropy(logits, y, label_smoothing=0.1)  # loss_fn/classification/cross_entropy.py:19-95
+    if opt is not None:
+        opt.zero_grad(set_to_none=True)
+    loss.backward()
+    if opt is not None:
+        opt.step()
+    return float(loss.detach())

@@ -1,0 +1,132 @@
+"""Pin the oracle (oracle/cvnets_oracle.py) to the fixtures generated from the REAL reference
+(tests/golden/make_golden.py).  CPU only, fp32, tight tolerances."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cvnets_oracle as O
+
+TOL = dict(atol=2e-5, rtol=2e-4)
+
+
+@pytest.fixture(scope="module")
+def mods(golden_dir):
+    return torch.load(os.path.join(golden_dir, "modules_fp32.pt"), weights_only=False)
+
+
+def _run(fn, P, fx):
+    x = fx["x"].clone().requires_grad_(True)
+    y = fn(P, x)
+    y.backward(fx["gy"])
+    return x, y
+
+
+def _check(P, fx, x, y, prefix="m."):
+    torch.testing.assert_close(y, fx["y"], **TOL)
+    torch.testing.assert_close(x.grad, fx["gx"], **TOL)
+    for k, g in fx["grads"].items():
+        torch.testing.assert_close(P[prefix + k].grad, g, atol=5e-5, rtol=5e-4, msg=lambda m, k=k: f"{k}: {m}")
+    for k, b in fx["buffers"].items():
+        torch.testing.assert_close(P[prefix + k].detach(), b, **TOL, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_stem(mods):
+    fx = mods["stem"]
+    P = {}
+    O._conv_bn(P, "m", 3, 16, 3)
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.conv_layer_2d(P, "m", x, stride=2), P, fx)
+    _check(P, fx, x, y)
+
+
+@pytest.mark.parametrize("name", ["ir_s1_res", "ir_s2"])
+def test_inverted_residual(mods, name):
+    fx = mods[name]
+    c = fx["cfg"]
+    P = {}
+    O.inverted_residual_shapes(P, "m", c["cin"], c["cout"], c["expand_ratio"])
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.inverted_residual(P, "m", x, stride=c["stride"]), P, fx)
+    _check(P, fx, x, y)
+
+
+def test_linear_self_attention(mods):
+    fx = mods["lsa"]
+    P = {}
+    O._conv_bn(P, "m.qkv_proj", 16, 33, 1, norm=False, bias=True)
+    O._conv_bn(P, "m.out_proj", 16, 16, 1, norm=False, bias=True)
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.linear_self_attention(P, "m", x), P, fx)
+    _check(P, fx, x, y)
+
+
+def test_linear_attn_ffn(mods):
+    fx = mods["laffn"]
+    P = {}
+    O.linear_attn_ffn_shapes(P, "m", 16, 32)
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.linear_attn_ffn(P, "m", x), P, fx)
+    _check(P, fx, x, y)
+
+
+def test_mobilevit_block_v2(mods):
+    fx = mods["mvit_v2"]
+    c = fx["cfg"]
+    P = {}
+    O.mobilevit_block_v2_shapes(P, "m", c["c"], c["d"], c["n_attn_blocks"])
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.mobilevit_block_v2(P, "m", x, n_attn_blocks=c["n_attn_blocks"]), P, fx)
+    _check(P, fx, x, y)
+
+
+def test_unfold_index_map(mods):
+    """patches[b,c,p,n] = x[b,c,(n//n_w)*2 + p//2, (n%n_w)*2 + p%2]; fold is the inverse."""
+    fx = mods["unfold_probe"]
+    x = fx["x"]
+    patches, size = O.unfolding(x)
+    assert torch.equal(patches, fx["patches"])
+    B, C, H, W = x.shape
+    nw = W // 2
+    for p in range(4):
+        for n in range(patches.shape[-1]):
+            assert torch.equal(patches[:, :, p, n], x[:, :, (n // nw) * 2 + p // 2, (n % nw) * 2 + p % 2])
+    assert torch.equal(O.folding(patches, size), x)
+
+
+def test_state_dict_contract(golden_dir):
+    with open(os.path.join(golden_dir, "state_dict_contract.json")) as f:
+        contract = json.load(f)
+    for width, entries in contract.items():
+        P = O.mobilevit_v2_shapes(float(width))
+        assert list(P.keys()) == [e[0] for e in entries] or set(P.keys()) == {e[0] for e in entries}
+        for k, shape, dtype in entries:
+            assert list(P[k].shape) == shape, k
+    assert sum(v.numel() for k, v in O.mobilevit_v2_shapes(1.0).items()
+               if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))) == 4901841
+
+
+@pytest.mark.parametrize("width", ["1.0", "0.5"])
+def test_mobilevit_v2_model(golden_dir, width):
+    fx = torch.load(os.path.join(golden_dir, "mobilevit_v2_fp32.pt"), weights_only=False)[width]
+    P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(fx["width"]), fx["seed"]))
+    x = O.seeded_input((2, 3, fx["res"], fx["res"]), fx["x_seed"])
+    logits, stages = O.mobilevit_v2_forward(P, x, width_multiplier=fx["width"], return_stages=True)
+    loss = F.cross_entropy(logits, fx["labels"], label_smoothing=0.1)
+    loss.backward()
+    torch.testing.assert_close(logits, fx["logits"], atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(loss.detach(), fx["loss"], atol=1e-5, rtol=1e-5)
+    last = {"conv_1": "conv_1", "layer_1": "layer_1.0", "layer_2": "layer_2.1", "layer_3": "layer_3.1",
+            "layer_4": "layer_4.1", "layer_5": "layer_5.1"}
+    for name, pre in last.items():
+        v = stages[pre].detach()
+        assert abs(float(v.norm()) - fx["stage_norms"][name]) <= 1e-4 * fx["stage_norms"][name]
+        torch.testing.assert_close(v.flatten()[:: max(1, v.numel() // 512)][:512], fx["stage_sample"][name], atol=1e-4, rtol=1e-3)
+    for k, n in fx["grad_norms"].items():
+        assert abs(float(P[k].grad.norm()) - n) <= 2e-3 * n + 1e-6, (k, float(P[k].grad.norm()), n)
+    for k, g in fx["grad_small"].items():
+        torch.testing.assert_close(P[k].grad, g, atol=1e-4 * float(g.abs().max()) + 1e-7, rtol=2e-3, msg=lambda m, k=k: f"{k}: {m}")
+    for k, b in fx["buffers_after"].items():
+        torch.testing.assert_close(P[k].detach(), b, atol=1e-5, rtol=1e-4)
