@@ -1,0 +1,217 @@
+/*
+ * cvnets_b200.h -- C ABI of libcvnets_b200.so: the sm_100a kernels behind the apple/ml-cvnets vision-backbone hot path.
+ *
+ * The reference (apple/ml-cvnets) is pure Python and has NO native operator / FFI boundary; its hot
+ * path bottoms out in torch.nn.functional calls.  This header is therefore the boundary a maintainer would bind with
+ * ctypes/cffi/pybind from the reference's layers (INTEGRATION.md shows the stub).  Each entry point names the
+ * reference call site(s) it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - plain pointers + sizes only (no torch types); every pointer is a DEVICE pointer unless stated otherwise;
+ *  - activations are bf16, channels-last: a feature map [B,H,W,C] is the row-major matrix [M=B*H*W, C];
+ *  - parameters / statistics are fp32, batch statistics accumulators are fp64 (atomically accumulated, caller zeroes);
+ *  - every function enqueues work on `stream` and returns immediately: 0 on success, non-zero on error
+ *    (cvb_last_error() gives the message).  No host sync, no global state: CUDA-graph capturable, DDP safe.
+ *  - leading dimensions are in ELEMENTS and must be multiples of 8 (16-byte vector access).
+ */
+#ifndef CVNETS_B200_H_
+#define CVNETS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cvb_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define CVB_API __attribute__((visibility("default")))
+#else
+#define CVB_API
+#endif
+
+#define CVB_ABI_VERSION 3
+
+/* operand "load modes": the normalisation / activation of the PRODUCER layer is applied while the CONSUMER loads it
+ * (training-mode BatchNorm cannot be fused into its own conv: SURVEY.md section 7 "hard parts"). */
+enum {
+  CVB_A_RAW = 0,      /* x                                                                                   */
+  CVB_A_AFF = 1,      /* p0[c]*x + p1[c]                 BatchNorm apply (batch_norm.py:14-49)               */
+  CVB_A_AFF_SILU = 2, /* silu(p0[c]*x + p1[c])           BatchNorm + Swish (activation/swish.py:13-20)       */
+  CVB_A_SILU = 3,     /* silu(x)                                                                             */
+  CVB_A_GN = 4,       /* (x-mean[b])*rstd[b]*p0[c]+p1[c] GroupNorm(1,C) = layer_norm_2d (layer_norm.py:75-108) */
+  CVB_A_BNB = 5       /* p0[c]*x + p1[c]*x2 + p2[c]      BatchNorm backward dy from (dz, y)   */
+};
+
+/* epilogue modes of cvb_pw_gemm */
+enum {
+  CVB_E_STORE = 0,    /* out = acc + bias (+R)                                                               */
+  CVB_E_SILU = 1,     /* out = silu(acc + bias) (+R)                                                         */
+  CVB_E_SILU_BWD = 2, /* out = acc * silu'(e_p0[n]*Y + e_p1[n]);   col_sum += out, col_sq += out*Y           */
+  CVB_E_GN_BWD = 3    /* xh=(Y-mean[b])*rstd[b]; col_sum += acc, col_sq += acc*xh; out = acc*e_p0[n];
+                         samp_sum += out, samp_sq += out*xh   (GroupNorm backward, phase 1)                   */
+};
+
+CVB_API const char* cvb_last_error(void);
+CVB_API int cvb_abi_version(void);
+/* host-side query: number of SMs / compute capability of the current device */
+CVB_API int cvb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Pointwise (1x1) convolution / linear layer as a GEMM:  C[M,N] = epi( load(A)[M,K] * W[N,K]^T + bias )
+ * Replaces F.conv2d(k=1) in ConvLayer2d (cvnets/layers/conv_layer.py:200-226) for InvertedResidual exp_1x1/red_1x1
+ * (cvnets/modules/mobilenetv2.py:182-219), MobileViTBlockv2 local_rep[1]/conv_proj (cvnets/modules/mobilevit_block.py
+ * :380-412), LinearSelfAttention qkv_proj/out_proj (cvnets/layers/linear_attention.py:51-70), the LinearAttnFFN convs
+ * (cvnets/modules/transformer.py:206-226), F.linear of the classifier (cvnets/layers/linear_layer.py:90), and -- with
+ * pre-transposed weights -- their input-gradient GEMMs.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int M, N, K;
+  const void* A; int lda;   /* bf16 [M, lda] */
+  const void* A2; int lda2; /* bf16 [M, lda2], CVB_A_BNB only */
+  int a_mode;
+  const float* a_p0; const float* a_p1; const float* a_p2; /* per-K vectors, see load modes */
+  const float* row_mean; const float* row_rstd;            /* per-sample [M/rows_per_sample] (CVB_A_GN, CVB_E_GN_BWD) */
+  int rows_per_sample;
+  const void* W; int ldw;   /* bf16 [N, ldw], K contiguous */
+  const float* bias;        /* fp32 [N] or NULL */
+  int e_mode;
+  const void* Y; int ldy;   /* bf16 [M, ldy] auxiliary tensor of the epilogue (SILU_BWD / GN_BWD) */
+  const float* e_p0; const float* e_p1; /* per-N vectors (NULL => 1 / 0) */
+  const void* R; int ldr;   /* bf16 [M, ldr] residual added to the output, or NULL */
+  void* C; int ldc; int c_fp32; /* output bf16 (or fp32 if c_fp32) [M, ldc] */
+  double* col_sum; double* col_sq;   /* fp64 [N] accumulators or NULL (BatchNorm statistics of the stored output) */
+  double* samp_sum; double* samp_sq; /* fp64 [M/rows_per_sample] or NULL (GroupNorm statistics of the stored output) */
+} cvb_gemm_args;
+CVB_API int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream);
+
+/* Weight gradient of a pointwise conv / linear:  dW[N,K] += sum_m load(G)[m,n] * load(A)[m,k];  dbias[n] += sum_m load(G)[m,n]
+ * (autograd of F.conv2d / F.linear at the call sites above).  G modes: RAW or BNB; A modes: RAW/AFF/AFF_SILU/SILU/GN. */
+typedef struct {
+  int M, N, K;
+  const void* G; int ldg; const void* G2; int ldg2; int g_mode;
+  const float* g_p0; const float* g_p1; const float* g_p2; /* per-N */
+  const void* A; int lda; int a_mode;
+  const float* a_p0; const float* a_p1;                    /* per-K */
+  const float* row_mean; const float* row_rstd; int rows_per_sample;
+  float* dW; int lddw; /* fp32 [N, lddw], atomically accumulated: caller zeroes */
+  float* dbias;        /* fp32 [N] or NULL, atomically accumulated */
+} cvb_wgrad_args;
+CVB_API int cvb_pw_wgrad(const cvb_wgrad_args* args, cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Depthwise 3x3 convolution, pad 1, stride 1|2, NHWC (ConvLayer2d(groups=C): mobilenetv2.py:194-207,
+ * mobilevit_block.py:369-379).  The producer's BN(+SiLU) is applied on load (x_mode RAW/AFF/AFF_SILU); zero padding
+ * is applied AFTER that transform, as in the reference where padding acts on the activated tensor.
+ * Output: pre-BN y (bf16) + fp64 per-channel sum / sum of squares of the stored values.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, H, W, C, stride;
+  const void* X; int x_mode; const float* x_p0; const float* x_p1;
+  const float* Wt;  /* fp32 [9][C] (tap-major), values already rounded to bf16 (autocast semantics) */
+  void* Y;          /* bf16 [B,Ho,Wo,C] */
+  double* col_sum; double* col_sq;
+} cvb_dw_fwd_args;
+CVB_API int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream);
+
+/* Backward of the above, fused: dy = load(DZ[,Y2]) (RAW or BNB), dX = conv_transpose(dy) then through the producer's
+ * activation (x_mode AFF_SILU: dX *= silu'(p0*x+p1)), statistics col_sum += dX, col_sq += dX*x for the producer's BN
+ * backward, and dWt[9][C] += sum dy * load(X)(shifted). */
+typedef struct {
+  int B, H, W, C, stride;
+  const void* DZ; const void* Y2; int g_mode; const float* g_p0; const float* g_p1; const float* g_p2;
+  const void* X; int x_mode; const float* x_p0; const float* x_p1;
+  const float* Wt;
+  void* DX;         /* bf16 [B,H,W,C] */
+  double* col_sum; double* col_sq; /* may be NULL when x_mode == RAW */
+  float* dWt;       /* fp32 [9][C], atomically accumulated */
+} cvb_dw_bwd_args;
+CVB_API int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stem: the dense 3x3 stride-2 conv 3 -> C0 of MobileViTv2 (mobilevit_v2.py:37-45) runs as im2col + cvb_pw_gemm:
+ * A[(b,oh,ow), ci*9+u*3+v] = bf16(X[b,ci,2oh+u-1,2ow+v-1]) (zero padded; columns 27..31 are zero), fp32 image in with
+ * arbitrary element strides (NCHW or channels_last).  The 32-column bf16 patch matrix costs 64 B/pixel (the stem's
+ * output alone is 64 B/pixel at C0=32) and lets forward, BN statistics and dW reuse the GEMM kernels.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_stem_im2col(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A,
+                    cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * BatchNorm2d bookkeeping (cvnets/layers/normalization/batch_norm.py:14-49; math SURVEY App. A1)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* training: from fp64 sum / sumsq over `count` values per channel -> mean, rstd, scale=gamma*rstd, shift=beta-mean*scale;
+ * running_mean/var EMA (unbiased var) if running_mean != NULL; num_batches_tracked += 1 if not NULL. */
+CVB_API int cvb_bn_finalize(const double* sum, const double* sq, double count, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    float* mean, float* rstd, float* scale, float* shift, int C, cvb_stream_t stream);
+/* eval: scale/shift from running statistics */
+CVB_API int cvb_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                            float eps, float* mean, float* rstd, float* scale, float* shift, int C, cvb_stream_t stream);
+/* backward: from sum_dz, sum_dz_y -> dgamma, dbeta and the coefficients of dy = c1*dz + c2*y + c3.
+ * eval_mode != 0: statistics were constants: c1 = gamma*rstd, c2 = c3 = 0. */
+CVB_API int cvb_bn_bwd_finalize(const double* sum_dz, const double* sum_dzy, double count, const float* gamma, const float* mean,
+                        const float* rstd, int eval_mode, float* dgamma, float* dbeta, float* c1, float* c2, float* c3,
+                        int C, cvb_stream_t stream);
+/* out = act(scale*y + shift) (+ R): materialises a module output.  act: 0 none, 1 silu. */
+CVB_API int cvb_bn_apply(const void* Y, const float* scale, const float* shift, int act, const void* R, void* OUT, int64_t M, int C,
+                 cvb_stream_t stream);
+/* sum_dz[c] += dz, sum_dzy[c] += dz*y with dz = dout (act=0) or dout*silu'(scale*y+shift) (act=1); dz optionally stored */
+CVB_API int cvb_bn_bwd_reduce(const void* DOUT, const void* Y, const float* scale, const float* shift, int act, void* DZ /* bf16 out or NULL */,
+                      double* sum_dz, double* sum_dzy, int64_t M, int C, cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GroupNorm(1, C) == layer_norm_2d bookkeeping (cvnets/layers/normalization/layer_norm.py:75-108)
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_gn_finalize(const double* samp_sum, const double* samp_sq, double count, float eps, float* mean, float* rstd, int B,
+                    cvb_stream_t stream);
+/* per-sample sum / sumsq of a bf16 [B*rows, C] tensor (used when no producer epilogue could emit them) */
+CVB_API int cvb_gn_stats(const void* X, int ldx, int B, int rows_per_sample, int C, double* samp_sum, double* samp_sq, cvb_stream_t stream);
+/* phase 2 of GroupNorm backward: dx = rstd[b]*(g - m1[b] - xh*m2[b]) + dres, m1 = sg/count, m2 = sgx/count;
+ * optional col_sum[c] += dx (bias gradient of the layer that produced the residual stream). */
+CVB_API int cvb_gn_bwd_apply(const void* G, const void* X, const float* mean, const float* rstd, const double* sg, const double* sgx,
+                     double count, const void* DRES, void* DX, int B, int rows_per_sample, int C, double* col_sum,
+                     cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * LinearSelfAttention core between qkv_proj and out_proj (cvnets/layers/linear_attention.py:134-161),
+ * with unfold/fold (mobilevit_block.py:526-555) collapsed into indexing: the feature map stays [B,H,W,*] and the four
+ * pixel positions p of every 2x2 patch are the (row parity, column parity) sub-lattices.
+ * QKV: bf16 [B*H*W, ldq] with columns [0,d)=key, [d,2d)=value, 2d=query (ldq >= 2d+8, multiple of 8).
+ * fwd:  s = softmax over the N=(H/2)(W/2) patches of q;  ctx[c] = sum_n key*s;  O = relu(value)*ctx.
+ * Saves s (fp32 [B,4,N]) and ctx (fp32 [B,4,d]) for the backward.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_linattn_fwd(const void* QKV, int ldq, int B, int H, int W, int d, int patch, void* O, int ldo, float* S, float* CTX,
+                    cvb_stream_t stream);
+/* bwd: from dO -> dQKV (same layout as QKV; pad columns zeroed); dbias_qkv[2d+1 (+pad)] += column sums if not NULL */
+CVB_API int cvb_linattn_bwd(const void* QKV, int ldq, const void* DO, int ldo, const float* S, const float* CTX, int B, int H, int W,
+                    int d, int patch, void* DQKV, float* dbias, cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GlobalPool(mean) (cvnets/layers/global_pool.py:60-71) and small utilities
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_global_pool_fwd(const void* X, int B, int HW, int C, void* OUT, cvb_stream_t stream);  /* bf16 -> bf16 [B,C] */
+CVB_API int cvb_global_pool_bwd(const void* DOUT, int B, int HW, int C, void* DX, cvb_stream_t stream); /* broadcast / HW */
+/* fp32 [N] += column sums of a bf16 (or fp32) [M, ld] matrix */
+CVB_API int cvb_col_sum(const void* X, int x_fp32, int ld, int64_t M, int N, float* out, cvb_stream_t stream);
+
+/* Batched weight preparation: one launch converts every fp32 parameter the step needs into the kernel layouts.
+ * kind 0: dst[r*ldd + c] = bf16(src[perm(r)*cols + c])           (row-major [rows, cols] -> bf16 [rows, ldd], zero padded)
+ * kind 1: dst[c*ldd + r] = bf16(src[perm(r)*cols + c])           (transposed:          -> bf16 [cols, ldd])
+ * kind 2: dst_f32[c*rows + r] = float(bf16(src[r*cols + c]))     (depthwise / stem: [C, taps] -> fp32 [taps, C], bf16-rounded)
+ * kind 3: dst_f32[perm^-1 ...]: dst_f32[r] = src[perm(r)]        (fp32 vector gather, e.g. permuted bias; cols = 1)
+ * perm(r) = (r + rot) % rows for r < rows (rot = 1 moves the reference's leading query row of qkv_proj to the end). */
+typedef struct {
+  const float* src; void* dst; int rows, cols, ldd, dst_rows; int kind; int rot;
+} cvb_prep_desc;
+CVB_API int cvb_prep_weights(const cvb_prep_desc* descs_device, int n_desc, int max_elems, cvb_stream_t stream);
+
+/* fp32 gradient scatter-back for permuted layouts: dst[perm(r)*cols + c] = src[r*lds + c] (kind 0) or
+ * dst[c*?]..: kind 2 (tap-major [taps, C] -> [C, taps]).  Used for qkv / depthwise / stem weight gradients. */
+CVB_API int cvb_unprep_grad(const float* src, float* dst, int rows, int cols, int lds, int kind, int rot, cvb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVNETS_B200_H_ */

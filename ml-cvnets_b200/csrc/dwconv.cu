@@ -1,0 +1,407 @@
+// Depthwise 3x3 convolution (pad 1, stride 1|2), NHWC bf16, forward and fused backward (sm_100a).
+//
+// Pure HBM-bound stencils (9 MAC per element): the kernels stage a spatial tile x 64 channels (+halo) in shared memory
+// with the PRODUCER's BatchNorm(+SiLU) already applied (so every input element is transformed exactly once), use
+// 16-byte channel vectors everywhere, and emit the BatchNorm statistics of their own output in the epilogue.
+// The backward kernel fuses  dy = BN-backward(dz, y)  ->  dX (transposed stencil)  ->  activation backward of the
+// producer + its BN-backward statistics  and  dW (per-channel 9-tap reduction) into one pass over the tensors.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CB = 64;  // channels per CTA (8 x 16-byte chunks)
+constexpr int NT = 256;
+
+__device__ __forceinline__ uint32_t pix_off(int pix, int ch) { return static_cast<uint32_t>(pix * 128 + ((ch ^ (pix & 7)) << 4)); }
+
+__device__ __forceinline__ void load8_mode(int mode, const bf16* ptr, const float* p0, const float* p1, float* out) {
+  unpack8(ldg16(ptr), out);
+  if (mode == CVB_A_AFF) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = fmaf(p0[j], out[j], p1[j]);
+  } else if (mode == CVB_A_AFF_SILU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = silu_f(fmaf(p0[j], out[j], p1[j]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------- forward
+template <int XMODE>
+__global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int Ho, int Wo, int TH, int TW, int logTW, int tiles_w) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_cs[CB], s_cq[CB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = p.stride;
+  const int th_i = blockIdx.x / tiles_w, tw_i = blockIdx.x % tiles_w;
+  const int oh0 = th_i * TH, ow0 = tw_i * TW;
+  const int c0 = blockIdx.y * CB;
+  const int b = blockIdx.z;
+  const int IH = (TH - 1) * s + 3, IW = (TW - 1) * s + 3;
+  const int h_base = oh0 * s - 1, w_base = ow0 * s - 1;
+  const bf16* __restrict__ X = static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C;
+
+  if (tid < CB) { s_cs[tid] = 0.f; s_cq[tid] = 0.f; }
+
+  // phase 1: stage transformed input tile (+halo)
+  {
+    const int ch = lane & 7;
+    const int c = c0 + ch * 8;
+    const bool c_ok = c < p.C;
+    float p0[8], p1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p0[j] = (XMODE != CVB_A_RAW && c_ok) ? p.x_p0[c + j] : 1.f;
+      p1[j] = (XMODE != CVB_A_RAW && c_ok) ? p.x_p1[c + j] : 0.f;
+    }
+    for (int ih = warp; ih < IH; ih += NT / 32) {
+      const int h = h_base + ih;
+      const bool h_ok = (h >= 0) && (h < p.H);
+      for (int jw = lane >> 3; jw < IW; jw += 4) {
+        const int w = w_base + jw;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (h_ok && c_ok && w >= 0 && w < p.W) {
+          float f[8];
+          load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + c, p0, p1, f);
+          v = pack8(f);
+        }
+        *reinterpret_cast<uint4*>(smem + pix_off(ih * IW + jw, ch)) = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase 2: stencil
+  const int cgi = tid & 7, pt = tid >> 3;
+  const int c = c0 + cgi * 8;
+  const bool c_ok = c < p.C;
+  float wt[9][8];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wt[tp][j] = c_ok ? p.Wt[tp * p.C + c + j] : 0.f;
+  float cs[8], cq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+  bf16* __restrict__ Y = static_cast<bf16*>(p.Y) + (size_t)b * Ho * Wo * p.C;
+  for (int op = pt; op < TH * TW; op += NT / 8) {
+    const int oh = op >> logTW, ow = op & (TW - 1);
+    const int gh = oh0 + oh, gw = ow0 + ow;
+    if (gh < Ho && gw < Wo && c_ok) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          float xin[8];
+          unpack8(*reinterpret_cast<const uint4*>(smem + pix_off((oh * s + u) * IW + ow * s + v, cgi)), xin);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt[u * 3 + v][j], xin[j], acc[j]);
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = bf16_round(acc[j]);
+        cs[j] += acc[j];
+        cq[j] += acc[j] * acc[j];
+      }
+      stg16(Y + ((size_t)gh * Wo + gw) * p.C + c, pack8(acc));
+    }
+  }
+  if (p.col_sum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // reduce over the 4 pixel-threads of this warp that share the channel chunk (lane bits 3,4)
+      float a = cs[j], q = cq[j];
+      a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+      q += __shfl_xor_sync(0xffffffffu, q, 8); q += __shfl_xor_sync(0xffffffffu, q, 16);
+      if (lane < 8) { atomicAdd(&s_cs[cgi * 8 + j], a); atomicAdd(&s_cq[cgi * 8 + j], q); }
+    }
+    __syncthreads();
+    if (tid < CB && c0 + tid < p.C) {
+      atomicAdd(p.col_sum + c0 + tid, (double)s_cs[tid]);
+      atomicAdd(p.col_sq + c0 + tid, (double)s_cq[tid]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------ backward
+template <int GMODE, int XMODE>
+__global__ void __launch_bounds__(NT) dw_bwd_kernel(const cvb_dw_bwd_args p, int Ho, int Wo, int TH, int TW, int logTW, int tiles_w) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_cs[CB], s_cq[CB];
+  __shared__ float s_dw[9][CB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = p.stride;
+  const int th_i = blockIdx.x / tiles_w, tw_i = blockIdx.x % tiles_w;
+  const int oh0 = th_i * TH, ow0 = tw_i * TW;
+  const int c0 = blockIdx.y * CB;
+  const int go = (s == 1) ? 1 : 0;          // halo of the dy tile on the low side
+  const int GH = TH + (s == 1 ? 2 : 1), GW = TW + (s == 1 ? 2 : 1);
+  const int XH = s * TH + 3 - s, XW = s * TW + 3 - s;  // input tile + halo (origin -1)
+  uint8_t* sG = smem;
+  uint8_t* sX = smem + (size_t)GH * GW * 128;
+  const int ITH = s * TH, ITW = s * TW;     // owned input tile
+  const int logITW = logTW + (s == 2 ? 1 : 0);
+
+  const int cgi = tid & 7, pt = tid >> 3;
+  const int cc = c0 + cgi * 8;
+  const bool cc_ok = cc < p.C;
+
+  for (int i = tid; i < 9 * CB; i += NT) (&s_dw[0][0])[i] = 0.f;
+  if (tid < CB) { s_cs[tid] = 0.f; s_cq[tid] = 0.f; }
+
+  float accw[9][8];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accw[tp][j] = 0.f;
+  float cs[8], cq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+
+  // loader-role parameters (chunk = lane & 7)
+  const int lch = lane & 7;
+  const int lc = c0 + lch * 8;
+  const bool lc_ok = lc < p.C;
+
+  for (int b = blockIdx.z; b < p.B; b += gridDim.z) {
+    const bf16* __restrict__ DZ = static_cast<const bf16*>(p.DZ) + (size_t)b * Ho * Wo * p.C;
+    const bf16* __restrict__ Y2 = (GMODE == CVB_A_BNB) ? static_cast<const bf16*>(p.Y2) + (size_t)b * Ho * Wo * p.C : nullptr;
+    const bf16* __restrict__ X = static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C;
+    bf16* __restrict__ DX = static_cast<bf16*>(p.DX) + (size_t)b * p.H * p.W * p.C;
+    __syncthreads();  // previous iteration done with smem
+    // ---- stage dy tile (per-channel coefficients are scoped here to keep them out of the stencil's live range)
+    {
+    float g0[8], g1[8], g2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g0[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p0[lc + j] : 1.f;
+      g1[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p1[lc + j] : 0.f;
+      g2[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p2[lc + j] : 0.f;
+    }
+    for (int gi = warp; gi < GH; gi += NT / 32) {
+      const int oh = oh0 - go + gi;
+      const bool h_ok = oh >= 0 && oh < Ho;
+      for (int gj = lane >> 3; gj < GW; gj += 4) {
+        const int ow = ow0 - go + gj;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (h_ok && lc_ok && ow >= 0 && ow < Wo) {
+          float f[8];
+          const size_t off = ((size_t)oh * Wo + ow) * p.C + lc;
+          unpack8(ldg16(DZ + off), f);
+          if (GMODE == CVB_A_BNB) {
+            float y[8];
+            unpack8(ldg16(Y2 + off), y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
+          }
+          v = pack8(f);
+        }
+        *reinterpret_cast<uint4*>(sG + pix_off(gi * GW + gj, lch)) = v;
+      }
+    }
+    }
+    // ---- stage transformed input tile (+halo)
+    {
+      const int h_base = s * oh0 - 1, w_base = s * ow0 - 1;
+      float x0[8], x1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x0[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p0[lc + j] : 1.f;
+        x1[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p1[lc + j] : 0.f;
+      }
+      for (int ih = warp; ih < XH; ih += NT / 32) {
+        const int h = h_base + ih;
+        const bool h_ok = h >= 0 && h < p.H;
+        for (int jw = lane >> 3; jw < XW; jw += 4) {
+          const int w = w_base + jw;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (h_ok && lc_ok && w >= 0 && w < p.W) {
+            float f[8];
+            load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + lc, x0, x1, f);
+            v = pack8(f);
+          }
+          *reinterpret_cast<uint4*>(sX + pix_off(ih * XW + jw, lch)) = v;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- A: weight gradient partials  dW[u,v] += dy[oh,ow] * a[s*oh+u-1, s*ow+v-1]
+    for (int op = pt; op < TH * TW; op += NT / 8) {
+      const int oh = op >> logTW, ow = op & (TW - 1);
+      float dy[8];
+      unpack8(*reinterpret_cast<const uint4*>(sG + pix_off((oh + go) * GW + ow + go, cgi)), dy);
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+          float a[8];
+          unpack8(*reinterpret_cast<const uint4*>(sX + pix_off((s * oh + u) * XW + s * ow + v, cgi)), a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) accw[u * 3 + v][j] = fmaf(dy[j], a[j], accw[u * 3 + v][j]);
+        }
+    }
+    // ---- B: input gradient  da[h,w] = sum_{u,v} W[u,v] * dy[(h+1-u)/s, (w+1-v)/s]
+    {
+      float wt[9][8];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wt[tp][j] = cc_ok ? p.Wt[tp * p.C + cc + j] : 0.f;
+      for (int ip = pt; ip < ITH * ITW; ip += NT / 8) {
+        const int ih = ip >> logITW, iw = ip & (ITW - 1);
+        const int h = s * oh0 + ih, w = s * ow0 + iw;
+        if (h < p.H && w < p.W && cc_ok) {
+          float da[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) da[j] = 0.f;
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            int gi;
+            if (s == 1) gi = ih + 2 - u;
+            else { if (((ih + 1 - u) & 1) != 0) continue; gi = (ih + 1 - u) >> 1; }
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+              int gj;
+              if (s == 1) gj = iw + 2 - v;
+              else { if (((iw + 1 - v) & 1) != 0) continue; gj = (iw + 1 - v) >> 1; }
+              float dy[8];
+              unpack8(*reinterpret_cast<const uint4*>(sG + pix_off(gi * GW + gj, cgi)), dy);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) da[j] = fmaf(wt[u * 3 + v][j], dy[j], da[j]);
+            }
+          }
+          const size_t off = ((size_t)h * p.W + w) * p.C + cc;
+          if (XMODE != CVB_A_RAW) {
+            float xr[8];
+            unpack8(ldg16(static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C + off), xr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (XMODE == CVB_A_AFF_SILU) da[j] *= silu_grad_f(fmaf(p.x_p0[cc + j], xr[j], p.x_p1[cc + j]));
+              da[j] = bf16_round(da[j]);
+              cs[j] += da[j];
+              cq[j] += da[j] * xr[j];
+            }
+          }
+          stg16(DX + off, pack8(da));
+        }
+      }
+    }
+  }
+
+  // ---- reductions
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = accw[tp][j];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if (lane < 8) atomicAdd(&s_dw[tp][cgi * 8 + j], a);
+    }
+  if (p.col_sum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = cs[j], q = cq[j];
+      a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+      q += __shfl_xor_sync(0xffffffffu, q, 8); q += __shfl_xor_sync(0xffffffffu, q, 16);
+      if (lane < 8) { atomicAdd(&s_cs[cgi * 8 + j], a); atomicAdd(&s_cq[cgi * 8 + j], q); }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 9 * CB; i += NT) {
+    int tp = i / CB, c = i % CB;
+    if (c0 + c < p.C) atomicAdd(p.dWt + tp * p.C + c0 + c, s_dw[tp][c]);
+  }
+  if (p.col_sum && tid < CB && c0 + tid < p.C) {
+    atomicAdd(p.col_sum + c0 + tid, (double)s_cs[tid]);
+    atomicAdd(p.col_sq + c0 + tid, (double)s_cq[tid]);
+  }
+}
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+void pick_tile(int Ho, int Wo, int stride, int* TH, int* TW) {
+  int tw = 1 << ilog2(Wo); if (tw > 16) tw = 16;
+  int budget = (stride == 1 ? 128 : 64) / tw;
+  int th = 1 << ilog2(Ho); if (th > budget) th = budget; if (th < 1) th = 1;
+  *TH = th; *TW = tw;
+}
+
+}  // namespace
+
+extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
+  CVB_CHECK(args != nullptr, "cvb_dw_fwd: null args");
+  const cvb_dw_fwd_args& a = *args;
+  CVB_CHECK(a.B > 0 && a.H > 0 && a.W > 0 && a.C > 0 && a.C % 8 == 0, "cvb_dw_fwd: bad shape B=%d H=%d W=%d C=%d (C %% 8 == 0)", a.B, a.H, a.W, a.C);
+  CVB_CHECK(a.stride == 1 || a.stride == 2, "cvb_dw_fwd: stride must be 1 or 2");
+  CVB_CHECK(a.X && a.Wt && a.Y && cvb_aligned16(a.X) && cvb_aligned16(a.Y), "cvb_dw_fwd: null / misaligned operand");
+  CVB_CHECK(a.x_mode == CVB_A_RAW || ((a.x_mode == CVB_A_AFF || a.x_mode == CVB_A_AFF_SILU) && a.x_p0 && a.x_p1), "cvb_dw_fwd: bad x_mode %d", a.x_mode);
+  if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_dw_fwd: col_sq missing");
+  const int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
+  int TH, TW; pick_tile(Ho, Wo, a.stride, &TH, &TW);
+  const int tiles_h = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
+  const int IH = (TH - 1) * a.stride + 3, IW = (TW - 1) * a.stride + 3;
+  size_t smem = (size_t)IH * IW * 128;
+  dim3 grid(tiles_h * tiles_w, (a.C + CB - 1) / CB, a.B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CVB_DW_FWD(MODE)                                                                                                  \
+  {                                                                                                                      \
+    static bool attr = false;                                                                                            \
+    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; } \
+    dw_fwd_kernel<MODE><<<grid, NT, smem, st>>>(a, Ho, Wo, TH, TW, ilog2(TW), tiles_w);                                  \
+  }
+  if (a.x_mode == CVB_A_RAW) CVB_DW_FWD(CVB_A_RAW)
+  else if (a.x_mode == CVB_A_AFF) CVB_DW_FWD(CVB_A_AFF)
+  else CVB_DW_FWD(CVB_A_AFF_SILU)
+#undef CVB_DW_FWD
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
+  CVB_CHECK(args != nullptr, "cvb_dw_bwd: null args");
+  const cvb_dw_bwd_args& a = *args;
+  CVB_CHECK(a.B > 0 && a.H > 0 && a.W > 0 && a.C > 0 && a.C % 8 == 0, "cvb_dw_bwd: bad shape");
+  CVB_CHECK(a.stride == 1 || a.stride == 2, "cvb_dw_bwd: stride must be 1 or 2");
+  CVB_CHECK(a.DZ && a.X && a.Wt && a.DX && a.dWt, "cvb_dw_bwd: null operand");
+  CVB_CHECK(a.g_mode == CVB_A_RAW || (a.g_mode == CVB_A_BNB && a.Y2 && a.g_p0 && a.g_p1 && a.g_p2), "cvb_dw_bwd: bad g_mode %d", a.g_mode);
+  CVB_CHECK(a.x_mode == CVB_A_RAW || ((a.x_mode == CVB_A_AFF || a.x_mode == CVB_A_AFF_SILU) && a.x_p0 && a.x_p1), "cvb_dw_bwd: bad x_mode %d", a.x_mode);
+  if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_dw_bwd: col_sq missing");
+  if (a.stride == 2) CVB_CHECK(a.H % 2 == 0 && a.W % 2 == 0, "cvb_dw_bwd: stride 2 needs even H, W");
+  const int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
+  int TH, TW; pick_tile(Ho, Wo, a.stride, &TH, &TW);
+  const int s = a.stride;
+  const int tiles_h = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
+  const int GH = TH + (s == 1 ? 2 : 1), GW = TW + (s == 1 ? 2 : 1);
+  const int XH = s * TH + 3 - s, XW = s * TW + 3 - s;
+  size_t smem = ((size_t)GH * GW + (size_t)XH * XW) * 128;
+  const int cblocks = (a.C + CB - 1) / CB;
+  // batch loop inside the CTA keeps the number of dW atomics bounded: aim for ~8 CTAs per SM in flight
+  int per_img = tiles_h * tiles_w * cblocks;
+  int want = 8 * cvb_num_sms();
+  int gz = (want + per_img - 1) / per_img;
+  if (gz > a.B) gz = a.B;
+  if (gz < 1) gz = 1;
+  dim3 grid(tiles_h * tiles_w, cblocks, gz);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CVB_DW_BWD(GM, XM)                                                                                                \
+  {                                                                                                                      \
+    static bool attr = false;                                                                                            \
+    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; } \
+    dw_bwd_kernel<GM, XM><<<grid, NT, smem, st>>>(a, Ho, Wo, TH, TW, ilog2(TW), tiles_w);                                \
+  }
+  if (a.g_mode == CVB_A_RAW) {
+    if (a.x_mode == CVB_A_RAW) CVB_DW_BWD(CVB_A_RAW, CVB_A_RAW)
+    else if (a.x_mode == CVB_A_AFF) CVB_DW_BWD(CVB_A_RAW, CVB_A_AFF)
+    else CVB_DW_BWD(CVB_A_RAW, CVB_A_AFF_SILU)
+  } else {
+    if (a.x_mode == CVB_A_RAW) CVB_DW_BWD(CVB_A_BNB, CVB_A_RAW)
+    else if (a.x_mode == CVB_A_AFF) CVB_DW_BWD(CVB_A_BNB, CVB_A_AFF)
+    else CVB_DW_BWD(CVB_A_BNB, CVB_A_AFF_SILU)
+  }
+#undef CVB_DW_BWD
+  CVB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,523 @@
+// BatchNorm / GroupNorm bookkeeping, materialisation, reductions, pooling, stem im2col and weight preparation (sm_100a).
+// All tensor passes are 16-byte vectorised over the channel dimension of the [M, C] channels-last matrix; per-channel
+// reductions keep a fixed channel chunk per thread (threads = multiple of C/8), reduce in smem, then one fp64 atomic per
+// channel per CTA.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------- error / device plumbing
+static thread_local char g_err[512] = "";
+void cvb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* cvb_last_error(void) { return g_err; }
+extern "C" int cvb_abi_version(void) { return CVB_ABI_VERSION; }
+int cvb_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+extern "C" int cvb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  CVB_CUDA(cudaGetDevice(&dev));
+  if (sm_count) CVB_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) CVB_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) CVB_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return 0;
+}
+
+namespace {
+
+constexpr int NT = 256;
+
+// row-block geometry shared by the per-channel reduction kernels
+struct RowGeom { int cgs, rpp, nthreads, rows_per_cta, ctas; };
+RowGeom row_geom(int64_t M, int C) {
+  RowGeom g;
+  g.cgs = C / 8;
+  g.rpp = NT / g.cgs; if (g.rpp < 1) g.rpp = 1;
+  g.nthreads = g.cgs * g.rpp;
+  int64_t target_ctas = 6 * (int64_t)cvb_num_sms();
+  int64_t rows = (M + target_ctas - 1) / target_ctas;
+  int64_t minrows = (int64_t)g.rpp * 4;
+  if (rows < minrows) rows = minrows;
+  rows = (rows + g.rpp - 1) / g.rpp * g.rpp;
+  g.rows_per_cta = (int)rows;
+  g.ctas = (int)((M + rows - 1) / rows);
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------ tiny per-channel kernels
+__global__ void bn_finalize_kernel(const double* sum, const double* sq, double count, const float* gamma, const float* beta, float eps,
+                                   float momentum, float* rmean, float* rvar, int64_t* nbt, float* mean, float* rstd, float* scale,
+                                   float* shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double m = sum[c] / count;
+  double var = sq[c] / count - m * m;
+  if (var < 0) var = 0;
+  float r = (float)(1.0 / sqrt(var + (double)eps));
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean[c] = (float)m;
+  rstd[c] = r;
+  scale[c] = g * r;
+  shift[c] = b - (float)m * g * r;
+  if (rmean) {
+    double unbiased = count > 1 ? var * count / (count - 1) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, float* mean,
+                               float* rstd, float* scale, float* shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float r = rsqrtf(rvar[c] + eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean[c] = rmean[c];
+  rstd[c] = r;
+  scale[c] = g * r;
+  shift[c] = b - rmean[c] * g * r;
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* sdz, const double* sdzy, double count, const float* gamma, const float* mean,
+                                       const float* rstd, int eval_mode, float* dgamma, float* dbeta, float* c1, float* c2, float* c3,
+                                       int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double db = sdz[c];
+  double dg = (double)rstd[c] * (sdzy[c] - (double)mean[c] * sdz[c]);  // sum dz * xhat
+  float g = gamma ? gamma[c] : 1.f;
+  if (dgamma) dgamma[c] = (float)dg;
+  if (dbeta) dbeta[c] = (float)db;
+  float k1 = g * rstd[c];
+  if (eval_mode) { c1[c] = k1; c2[c] = 0.f; c3[c] = 0.f; return; }
+  // dy = g*rstd*(dz - db/n - xhat*dg/n),  xhat = (y-mean)*rstd
+  double k2 = -(double)k1 * (double)rstd[c] * dg / count;
+  double k3 = -(double)k1 * db / count - k2 * (double)mean[c];
+  c1[c] = k1; c2[c] = (float)k2; c3[c] = (float)k3;
+}
+
+__global__ void gn_finalize_kernel(const double* ssum, const double* ssq, double count, float eps, float* mean, float* rstd, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double m = ssum[b] / count;
+  double var = ssq[b] / count - m * m;
+  if (var < 0) var = 0;
+  mean[b] = (float)m;
+  rstd[b] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise: BN apply
+__global__ void __launch_bounds__(NT) bn_apply_kernel(const bf16* __restrict__ Y, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      int act, const bf16* __restrict__ R, bf16* __restrict__ OUT, int64_t nvec, int cgs) {
+  for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
+    int c = (int)(v % cgs) * 8;
+    float f[8];
+    unpack8(ldg16_stream(Y + v * 8), f);
+    float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+    float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+    float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(sc[j], f[j], sh[j]);
+      if (act) f[j] = silu_f(f[j]);
+    }
+    if (R) {
+      float r[8];
+      unpack8(ldg16_stream(R + v * 8), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    stg16(OUT + v * 8, pack8(f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ per-channel reductions
+// mode 0: BN backward reduce: dz = dout (act 0) or dout*silu'(sc*y+sh) (act 1); s0 += dz, s1 += dz*y; optional DZ store.
+__global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const bf16* __restrict__ DOUT, const bf16* __restrict__ Y, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, int act, bf16* __restrict__ DZ, double* s0, double* s1,
+                                                           int64_t M, int C, int cgs, int rpp, int rows_per_cta) {
+  extern __shared__ float sred[];  // [2][C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cg = tid % cgs, rr = tid / cgs;
+  const int c = cg * 8;
+  float sc[8], sh[8], a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = act ? scale[c + j] : 1.f; sh[j] = act ? shift[c + j] : 0.f; a0[j] = 0.f; a1[j] = 0.f; }
+  int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = r_begin + rows_per_cta;
+  if (r_end > M) r_end = M;
+  for (int64_t r = r_begin + rr; r < r_end; r += rpp) {
+    float d[8], y[8];
+    unpack8(ldg16_stream(DOUT + r * C + c), d);
+    unpack8(ldg16_stream(Y + r * C + c), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (act) d[j] = bf16_round(d[j] * silu_grad_f(fmaf(sc[j], y[j], sh[j])));
+      a0[j] += d[j];
+      a1[j] += d[j] * y[j];
+    }
+    if (DZ) stg16(DZ + r * C + c, pack8(d));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { atomicAdd(&sred[c + j], a0[j]); atomicAdd(&sred[C + c + j], a1[j]); }
+  __syncthreads();
+  for (int i = tid; i < C; i += blockDim.x) { atomicAdd(s0 + i, (double)sred[i]); atomicAdd(s1 + i, (double)sred[C + i]); }
+}
+
+// column sums of a bf16 / fp32 [M, ld] matrix into fp32
+__global__ void __launch_bounds__(NT) col_sum_kernel(const void* __restrict__ X, int x_fp32, int ld, int64_t M, int N, float* out, int rows_per_cta) {
+  // thread per column (strided), rows looped: N is small (<= 1024) and M small for the fp32 use (classifier)
+  int64_t r_begin = (int64_t)blockIdx.y * rows_per_cta, r_end = r_begin + rows_per_cta;
+  if (r_end > M) r_end = M;
+  int n = blockIdx.x * NT + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  if (x_fp32) {
+    const float* x = static_cast<const float*>(X);
+    for (int64_t r = r_begin; r < r_end; ++r) acc += x[r * ld + n];
+  } else {
+    const bf16* x = static_cast<const bf16*>(X);
+    for (int64_t r = r_begin; r < r_end; ++r) acc += __bfloat162float(x[r * ld + n]);
+  }
+  atomicAdd(out + n, acc);
+}
+
+// per-sample sum / sumsq
+__global__ void __launch_bounds__(NT) gn_stats_kernel(const bf16* __restrict__ X, int ldx, int rows_per_sample, int C, int chunks_per_sample,
+                                                      double* ssum, double* ssq) {
+  const int b = blockIdx.x / chunks_per_sample, chunk = blockIdx.x % chunks_per_sample;
+  const int cgs = C / 8;
+  const int64_t nvec = (int64_t)rows_per_sample * cgs;
+  const int64_t per = (nvec + chunks_per_sample - 1) / chunks_per_sample;
+  int64_t v0 = chunk * per, v1 = v0 + per;
+  if (v1 > nvec) v1 = nvec;
+  float s = 0.f, q = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += NT) {
+    int64_t r = v / cgs;
+    int c = (int)(v % cgs) * 8;
+    float f[8];
+    unpack8(ldg16_stream(X + ((int64_t)b * rows_per_sample + r) * ldx + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += f[j]; q += f[j] * f[j]; }
+  }
+  __shared__ float ws[2][NT / 32];
+  s = warp_sum(s); q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = s; ws[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < NT / 32; ++i) { ts += ws[0][i]; tq += ws[1][i]; }
+    atomicAdd(ssum + b, (double)ts);
+    atomicAdd(ssq + b, (double)tq);
+  }
+}
+
+// GroupNorm backward phase 2 (+ residual-stream gradient, + column sums of the result)
+__global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict__ G, const bf16* __restrict__ X, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const double* __restrict__ sg, const double* __restrict__ sgx,
+                                                          double count, const bf16* __restrict__ DRES, bf16* __restrict__ DX, int64_t M,
+                                                          int rows_per_sample, int C, double* col_sum, int cgs, int rpp, int rows_per_cta) {
+  extern __shared__ float sred[];  // [C]
+  const int tid = threadIdx.x;
+  if (col_sum) { for (int i = tid; i < C; i += blockDim.x) sred[i] = 0.f; __syncthreads(); }
+  const int cg = tid % cgs, rr = tid / cgs;
+  const int c = cg * 8;
+  float a0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = 0.f;
+  int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = r_begin + rows_per_cta;
+  if (r_end > M) r_end = M;
+  for (int64_t r = r_begin + rr; r < r_end; r += rpp) {
+    const int b = (int)(r / rows_per_sample);
+    const float mu = mean[b], rs = rstd[b];
+    const float m1 = (float)(sg[b] / count), m2 = (float)(sgx[b] / count);
+    float g[8], x[8];
+    unpack8(ldg16_stream(G + r * C + c), g);
+    unpack8(ldg16_stream(X + r * C + c), x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float xh = (x[j] - mu) * rs;
+      g[j] = rs * (g[j] - m1 - xh * m2);
+    }
+    if (DRES) {
+      float d[8];
+      unpack8(ldg16_stream(DRES + r * C + c), d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += d[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { g[j] = bf16_round(g[j]); a0[j] += g[j]; }
+    stg16(DX + r * C + c, pack8(g));
+  }
+  if (col_sum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sred[c + j], a0[j]);
+    __syncthreads();
+    for (int i = tid; i < C; i += blockDim.x) atomicAdd(col_sum + i, (double)sred[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ global average pool
+__global__ void __launch_bounds__(NT) pool_fwd_kernel(const bf16* __restrict__ X, int HW, int C, bf16* __restrict__ OUT) {
+  // grid: (C/8 chunks rounded to blocks of 32 lanes..., B); thread = (chunk, row group)
+  extern __shared__ float sred[];  // [C]
+  const int b = blockIdx.x;
+  const int cgs = C / 8;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cg = tid % cgs, rr = tid / cgs, rpp = blockDim.x / cgs;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  for (int r = rr; r < HW; r += rpp) {
+    float f[8];
+    unpack8(ldg16(X + ((int64_t)b * HW + r) * C + cg * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&sred[cg * 8 + j], a[j]);
+  __syncthreads();
+  for (int i = tid; i < C; i += blockDim.x) OUT[(int64_t)b * C + i] = __float2bfloat16_rn(sred[i] / (float)HW);
+}
+
+__global__ void __launch_bounds__(NT) pool_bwd_kernel(const bf16* __restrict__ DOUT, int HW, int C, bf16* __restrict__ DX, int64_t nvec) {
+  const int cgs = C / 8;
+  const float inv = 1.f / (float)HW;
+  for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
+    int64_t row = v / cgs;
+    int c = (int)(v % cgs) * 8;
+    int64_t b = row / HW;
+    float f[8];
+    unpack8(ldg16(DOUT + b * C + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+    stg16(DX + v * 8, pack8(f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stem im2col
+// A[(b,oh,ow), ci*9+u*3+v] = bf16(X[b,ci,2oh+u-1,2ow+v-1]) (zero padded), columns 27..31 = 0
+__global__ void __launch_bounds__(NT) stem_im2col_kernel(const float* __restrict__ X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H,
+                                                         int W, bf16* __restrict__ A) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)B * Ho * Wo * 4;  // 4 chunks of 8 columns per output pixel
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    const int ch = (int)(i & 3);
+    const int64_t pix = i >> 2;
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int b = (int)(pix / ((int64_t)Wo * Ho));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = ch * 8 + j;
+      float v = 0.f;
+      if (col < 27) {
+        const int ci = col / 9, u = (col % 9) / 3, vv = col % 3;
+        const int h = 2 * oh + u - 1, w = 2 * ow + vv - 1;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(X + b * sxn + ci * sxc + h * sxh + w * sxw);
+      }
+      f[j] = v;
+    }
+    stg16(A + i * 8, pack8(f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight preparation
+__device__ __forceinline__ int perm_row(int r, int rows, int rot) { return rot ? (r + rot) % rows : r; }
+
+__global__ void __launch_bounds__(NT) prep_weights_kernel(const cvb_prep_desc* __restrict__ descs) {
+  const cvb_prep_desc d = descs[blockIdx.y];
+  const int64_t total = (d.kind == 2) ? (int64_t)d.rows * d.cols : (d.kind == 3 ? (int64_t)d.dst_rows : (int64_t)d.dst_rows * d.ldd);
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    if (d.kind == 0) {
+      int r = (int)(i / d.ldd), c = (int)(i % d.ldd);
+      float v = (r < d.rows && c < d.cols) ? d.src[(int64_t)perm_row(r, d.rows, d.rot) * d.cols + c] : 0.f;
+      static_cast<bf16*>(d.dst)[i] = __float2bfloat16_rn(v);
+    } else if (d.kind == 1) {
+      int c = (int)(i / d.ldd), r = (int)(i % d.ldd);
+      float v = (r < d.rows && c < d.cols) ? d.src[(int64_t)perm_row(r, d.rows, d.rot) * d.cols + c] : 0.f;
+      static_cast<bf16*>(d.dst)[i] = __float2bfloat16_rn(v);
+    } else if (d.kind == 2) {
+      int tap = (int)(i / d.rows), ch = (int)(i % d.rows);
+      static_cast<float*>(d.dst)[i] = bf16_round(d.src[(int64_t)ch * d.cols + tap]);
+    } else {
+      int r = (int)i;
+      static_cast<float*>(d.dst)[i] = (r < d.rows) ? d.src[perm_row(r, d.rows, d.rot)] : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) unprep_grad_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int lds, int kind,
+                                                         int rot) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
+    if (kind == 0) {
+      int r = (int)(i / cols), c = (int)(i % cols);
+      dst[(int64_t)perm_row(r, rows, rot) * cols + c] = src[(int64_t)r * lds + c];
+    } else if (kind == 2) {  // src [taps=cols][C=rows] -> dst [C][taps]
+      int ch = (int)(i / cols), tap = (int)(i % cols);
+      dst[i] = src[(int64_t)tap * rows + ch];
+    } else {
+      dst[perm_row((int)i, rows, rot)] = src[i];
+    }
+  }
+}
+
+int grid_for(int64_t n_items) {
+  int64_t g = (n_items + NT - 1) / NT;
+  int64_t cap = 16 * (int64_t)cvb_num_sms();
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int cvb_bn_finalize(const double* sum, const double* sq, double count, const float* gamma, const float* beta, float eps, float momentum,
+                               float* running_mean, float* running_var, int64_t* nbt, float* mean, float* rstd, float* scale, float* shift, int C,
+                               cvb_stream_t stream) {
+  CVB_CHECK(sum && sq && mean && rstd && scale && shift && C > 0 && count > 0, "cvb_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sum, sq, count, gamma, beta, eps, momentum, running_mean,
+                                                                                     running_var, nbt, mean, rstd, scale, shift, C);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                                       float* mean, float* rstd, float* scale, float* shift, int C, cvb_stream_t stream) {
+  CVB_CHECK(running_mean && running_var && mean && rstd && scale && shift && C > 0, "cvb_bn_eval_scale_shift: bad arguments");
+  bn_eval_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, running_mean, running_var, eps, mean, rstd, scale, shift, C);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_bn_bwd_finalize(const double* sum_dz, const double* sum_dzy, double count, const float* gamma, const float* mean, const float* rstd,
+                                   int eval_mode, float* dgamma, float* dbeta, float* c1, float* c2, float* c3, int C, cvb_stream_t stream) {
+  CVB_CHECK(sum_dz && sum_dzy && mean && rstd && c1 && c2 && c3 && C > 0 && count > 0, "cvb_bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sum_dz, sum_dzy, count, gamma, mean, rstd, eval_mode, dgamma,
+                                                                                         dbeta, c1, c2, c3, C);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_bn_apply(const void* Y, const float* scale, const float* shift, int act, const void* R, void* OUT, int64_t M, int C,
+                            cvb_stream_t stream) {
+  CVB_CHECK(Y && scale && shift && OUT && M > 0 && C > 0 && C % 8 == 0, "cvb_bn_apply: bad arguments");
+  int64_t nvec = M * (C / 8);
+  bn_apply_kernel<<<grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(Y), scale, shift, act,
+                                                                               static_cast<const bf16*>(R), static_cast<bf16*>(OUT), nvec, C / 8);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_bn_bwd_reduce(const void* DOUT, const void* Y, const float* scale, const float* shift, int act, void* DZ, double* sum_dz,
+                                 double* sum_dzy, int64_t M, int C, cvb_stream_t stream) {
+  CVB_CHECK(DOUT && Y && sum_dz && sum_dzy && M > 0 && C > 0 && C % 8 == 0 && C <= 2048, "cvb_bn_bwd_reduce: bad arguments");
+  if (act) CVB_CHECK(scale && shift, "cvb_bn_bwd_reduce: act needs scale/shift");
+  RowGeom g = row_geom(M, C);
+  bn_bwd_reduce_kernel<<<g.ctas, g.nthreads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(DOUT), static_cast<const bf16*>(Y), scale, shift, act, static_cast<bf16*>(DZ), sum_dz, sum_dzy, M, C, g.cgs, g.rpp,
+      g.rows_per_cta);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_gn_finalize(const double* samp_sum, const double* samp_sq, double count, float eps, float* mean, float* rstd, int B,
+                               cvb_stream_t stream) {
+  CVB_CHECK(samp_sum && samp_sq && mean && rstd && B > 0 && count > 0, "cvb_gn_finalize: bad arguments");
+  gn_finalize_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(samp_sum, samp_sq, count, eps, mean, rstd, B);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_gn_stats(const void* X, int ldx, int B, int rows_per_sample, int C, double* samp_sum, double* samp_sq, cvb_stream_t stream) {
+  CVB_CHECK(X && samp_sum && samp_sq && B > 0 && rows_per_sample > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0, "cvb_gn_stats: bad arguments");
+  int64_t nvec = (int64_t)rows_per_sample * (C / 8);
+  int chunks = (int)((nvec + 4095) / 4096);
+  if (chunks < 1) chunks = 1;
+  gn_stats_kernel<<<B * chunks, NT, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(X), ldx, rows_per_sample, C, chunks, samp_sum,
+                                                                           samp_sq);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_gn_bwd_apply(const void* G, const void* X, const float* mean, const float* rstd, const double* sg, const double* sgx, double count,
+                                const void* DRES, void* DX, int B, int rows_per_sample, int C, double* col_sum, cvb_stream_t stream) {
+  CVB_CHECK(G && X && mean && rstd && sg && sgx && DX && B > 0 && rows_per_sample > 0 && C > 0 && C % 8 == 0 && C <= 2048,
+            "cvb_gn_bwd_apply: bad arguments");
+  int64_t M = (int64_t)B * rows_per_sample;
+  RowGeom g = row_geom(M, C);
+  gn_bwd_apply_kernel<<<g.ctas, g.nthreads, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(G), static_cast<const bf16*>(X), mean, rstd, sg, sgx, count, static_cast<const bf16*>(DRES), static_cast<bf16*>(DX), M,
+      rows_per_sample, C, col_sum, g.cgs, g.rpp, g.rows_per_cta);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_global_pool_fwd(const void* X, int B, int HW, int C, void* OUT, cvb_stream_t stream) {
+  CVB_CHECK(X && OUT && B > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 2048, "cvb_global_pool_fwd: bad arguments");
+  int cgs = C / 8;
+  int rpp = NT / cgs; if (rpp < 1) rpp = 1;
+  pool_fwd_kernel<<<B, cgs * rpp, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(X), HW, C, static_cast<bf16*>(OUT));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_global_pool_bwd(const void* DOUT, int B, int HW, int C, void* DX, cvb_stream_t stream) {
+  CVB_CHECK(DOUT && DX && B > 0 && HW > 0 && C > 0 && C % 8 == 0, "cvb_global_pool_bwd: bad arguments");
+  int64_t nvec = (int64_t)B * HW * (C / 8);
+  pool_bwd_kernel<<<grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(DOUT), HW, C, static_cast<bf16*>(DX), nvec);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_col_sum(const void* X, int x_fp32, int ld, int64_t M, int N, float* out, cvb_stream_t stream) {
+  CVB_CHECK(X && out && M > 0 && N > 0 && ld >= N, "cvb_col_sum: bad arguments");
+  int rows_per_cta = 256;
+  dim3 grid((N + NT - 1) / NT, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
+  col_sum_kernel<<<grid, NT, 0, static_cast<cudaStream_t>(stream)>>>(X, x_fp32, ld, M, N, out, rows_per_cta);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_stem_im2col(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A, cvb_stream_t stream) {
+  CVB_CHECK(X && A && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "cvb_stem_im2col: bad arguments (H, W must be even)");
+  int64_t total = (int64_t)B * (H / 2) * (W / 2) * 4;
+  stem_im2col_kernel<<<grid_for(total), NT, 0, static_cast<cudaStream_t>(stream)>>>(X, sxn, sxc, sxh, sxw, B, H, W, static_cast<bf16*>(A));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_prep_weights(const cvb_prep_desc* descs_device, int n_desc, int max_elems, cvb_stream_t stream) {
+  CVB_CHECK(descs_device && n_desc > 0 && max_elems > 0, "cvb_prep_weights: bad arguments");
+  int gx = (max_elems + NT * 4 - 1) / (NT * 4);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  dim3 grid(gx, n_desc);
+  prep_weights_kernel<<<grid, NT, 0, static_cast<cudaStream_t>(stream)>>>(descs_device);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_unprep_grad(const float* src, float* dst, int rows, int cols, int lds, int kind, int rot, cvb_stream_t stream) {
+  CVB_CHECK(src && dst && rows > 0 && cols > 0, "cvb_unprep_grad: bad arguments");
+  unprep_grad_kernel<<<grid_for((int64_t)rows * cols), NT, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, rows, cols, lds, kind, rot);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
