@@ -1,0 +1,307 @@
+"""torch.autograd.Functions of the hot-path modules: each forward/backward is a fixed sequence of C-ABI kernel launches.
+
+Design: activations are bf16 channels-last matrices [M=B*H*W, C]; a conv writes its PRE-BatchNorm
+output once together with fp64 per-channel sum / sum-of-squares; a tiny finalize kernel turns them into scale/shift; the
+CONSUMER applies scale/shift(+SiLU) while loading.  The pre-BN tensors are exactly what the backward needs, so nothing is
+stored twice.  Module boundaries materialise real tensors so every module stays a drop-in ``nn.Module``.
+
+Reference semantics restated per function; citations are relative to the reference checkout.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List
+
+import torch
+
+from . import ops
+from .ops import A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU, E_GN_BWD, E_SILU_BWD, E_STORE
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------------------ helpers
+def to_bf16_cl(x: torch.Tensor) -> torch.Tensor:
+    """bf16 + channels_last (a no-op between our own modules).  Dtype/layout glue, not compute."""
+    if x.dtype != BF16:
+        x = x.to(BF16)
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    return x
+
+
+def as_2d(x: torch.Tensor) -> torch.Tensor:
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B * H * W, C)
+
+
+def to_4d(y: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
+    return y.view(B, H, W, y.shape[1]).permute(0, 3, 1, 2)
+
+
+def bn_cfg(bn_module) -> SimpleNamespace:
+    """Reads nn.BatchNorm2d state at call time (momentum may be annealed: cvnets/layers/normalization_layers.py:91-100)."""
+    assert bn_module.momentum is not None, "cumulative-average BatchNorm (momentum=None) is not implemented"
+    return SimpleNamespace(running_mean=bn_module.running_mean, running_var=bn_module.running_var,
+                           nbt=bn_module.num_batches_tracked, momentum=float(bn_module.momentum), eps=float(bn_module.eps),
+                           batch_stats=bool(bn_module.training or bn_module.running_mean is None))
+
+
+def _bn_forward(stats, count, gamma, beta, c):
+    if c.batch_stats:
+        return ops.bn_finalize(stats, count, gamma, beta, c.eps, c.momentum, c.running_mean, c.running_var, c.nbt)
+    return ops.bn_eval_scale_shift(gamma, beta, c.running_mean, c.running_var, c.eps)
+
+
+def _zeros64(device, *sizes: int) -> List[torch.Tensor]:
+    """One memset for all fp64 [2, n] accumulators of a pass."""
+    buf = torch.zeros(2 * sum(sizes), device=device, dtype=torch.float64)
+    out, o = [], 0
+    for n in sizes:
+        out.append(buf[o:o + 2 * n].view(2, n))
+        o += 2 * n
+    return out
+
+
+# ==================================================================================================================
+# Stem: ConvLayer2d(3 -> C0, k3, s2) + BN + SiLU  (cvnets/models/classification/mobilevit_v2.py:37-45)
+# ==================================================================================================================
+class StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg, w, gamma, beta):
+        B, _, H, W = x.shape
+        C0 = w.shape[0]
+        Ho, Wo = H // 2, W // 2
+        M = B * Ho * Wo
+        xin = x if x.dtype == torch.float32 else x.float()
+        A0 = ops.stem_im2col(xin)
+        Ws = cfg.prep.get(cfg.i_w)
+        (st,) = _zeros64(x.device, C0)
+        y = ops.pw_gemm(A0, Ws, C0, col_stats=st if cfg.bn.batch_stats else None)
+        bn = _bn_forward(st, M, gamma, beta, cfg.bn)
+        out = ops.bn_apply(y, bn, act=True)
+        ctx.cfg, ctx.dims = cfg, (B, Ho, Wo, C0, M)
+        ctx.saved = (A0, y, bn)
+        ctx.save_for_backward(gamma)
+        return to_4d(out, B, Ho, Wo)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, Ho, Wo, C0, M = ctx.dims
+        A0, y, bn = ctx.saved
+        (gamma,) = ctx.saved_tensors
+        g2 = as_2d(to_bf16_cl(gout))
+        (sd,) = _zeros64(g2.device, C0)
+        dz = ops.bn_bwd_reduce(g2, y, sd, bn, act=True, store_dz=True)
+        dgb, coef = ops.bn_bwd_finalize(sd, M, gamma, bn, eval_mode=not cfg.bn.batch_stats)
+        dW = ops.pw_wgrad(dz, A0, C0, 32, g_mode=A_BNB, G2=y, g_p=coef)
+        dw = ops.unprep_grad(dW, C0, 27, 32, 0).view(C0, 3, 3, 3)
+        return None, None, dw, dgb[0], dgb[1]
+
+
+# ==================================================================================================================
+# InvertedResidual (cvnets/modules/mobilenetv2.py:141-246): exp_1x1 -> dw3x3(stride) -> red_1x1 (+x)
+# ==================================================================================================================
+class InvertedResidualFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg, w1, g1, b1, wd, g2, b2, w3, g3, b3):
+        B, Cin, H, W = x.shape
+        hid, cout, s = cfg.hid, cfg.cout, cfg.stride
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        M, M2 = B * H * W, B * Ho * Wo
+        x2 = as_2d(x)
+        P = cfg.prep
+        st1, st2, st3 = _zeros64(x.device, hid, hid, cout)
+        bs = cfg.bn[0].batch_stats
+        y1 = ops.pw_gemm(x2, P.get(cfg.i_w1), hid, col_stats=st1 if bs else None)
+        bn1 = _bn_forward(st1, M, g1, b1, cfg.bn[0])
+        y2 = ops.dw_fwd(y1, B, H, W, hid, s, P.get(cfg.i_wd), x_mode=A_AFF_SILU, x_p=(bn1[2], bn1[3]), col_stats=st2 if bs else None)
+        bn2 = _bn_forward(st2, M2, g2, b2, cfg.bn[1])
+        y3 = ops.pw_gemm(y2, P.get(cfg.i_w3), cout, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), col_stats=st3 if bs else None)
+        bn3 = _bn_forward(st3, M2, g3, b3, cfg.bn[2])
+        out = ops.bn_apply(y3, bn3, act=False, R=x2 if cfg.residual else None)
+        ctx.cfg, ctx.dims = cfg, (B, Cin, H, W, Ho, Wo)
+        ctx.saved = (x2, y1, bn1, y2, bn2, y3, bn3)
+        ctx.save_for_backward(g1, g2, g3)
+        return to_4d(out, B, Ho, Wo)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, Cin, H, W, Ho, Wo = ctx.dims
+        hid, cout, s = cfg.hid, cfg.cout, cfg.stride
+        M, M2 = B * H * W, B * Ho * Wo
+        x2, y1, bn1, y2, bn2, y3, bn3 = ctx.saved
+        g1, g2, g3 = ctx.saved_tensors
+        P = cfg.prep
+        ev = not cfg.bn[0].batch_stats
+        dout = as_2d(to_bf16_cl(gout))
+        sd3, sd2, sd1 = _zeros64(dout.device, cout, hid, hid)
+        # red_1x1 + BN3 (no activation): dz3 = dout
+        ops.bn_bwd_reduce(dout, y3, sd3)
+        dgb3, c3 = ops.bn_bwd_finalize(sd3, M2, g3, bn3, ev)
+        dz2 = ops.pw_gemm(dout, P.get(cfg.i_w3t), hid, K=cout, a_mode=A_BNB, A2=y3, a_p=c3, e_mode=E_SILU_BWD, Y=y2,
+                          e_p=(bn2[2], bn2[3]), col_stats=sd2)
+        dW3 = ops.pw_wgrad(dout, y2, cout, hid, g_mode=A_BNB, G2=y3, g_p=c3, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]))
+        # depthwise + BN2
+        dgb2, c2 = ops.bn_bwd_finalize(sd2, M2, g2, bn2, ev)
+        dz1, dWt = ops.dw_bwd(dz2, y1, B, H, W, hid, s, P.get(cfg.i_wd), g_mode=A_BNB, Y2=y2, g_p=c2, x_mode=A_AFF_SILU,
+                              x_p=(bn1[2], bn1[3]), col_stats=sd1)
+        dWd = ops.unprep_grad(dWt, hid, 9, hid, 2).view(hid, 1, 3, 3)
+        # exp_1x1 + BN1
+        dgb1, c1 = ops.bn_bwd_finalize(sd1, M, g1, bn1, ev)
+        dx = ops.pw_gemm(dz1, P.get(cfg.i_w1t), Cin, K=hid, a_mode=A_BNB, A2=y1, a_p=c1, R=dout if cfg.residual else None)
+        dW1 = ops.pw_wgrad(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1)
+        return (to_4d(dx, B, H, W), None, dW1.view(hid, Cin, 1, 1), dgb1[0], dgb1[1], dWd, dgb2[0], dgb2[1],
+                dW3.view(cout, hid, 1, 1), dgb3[0], dgb3[1])
+
+
+# ==================================================================================================================
+# MobileViTBlockv2 (cvnets/modules/mobilevit_block.py:605-626) with LinearAttnFFN (cvnets/modules/transformer.py:248-264)
+# and LinearSelfAttention (cvnets/layers/linear_attention.py:134-161); unfold/fold live in the attention kernel's indexing.
+# Parameter order: [wd0, g0, b0, wl] + n x [ga, ba, wqkv, bqkv, wo, bo, gf, bf, w1, b1, w2, b2] + [gL, bL, wp, gp, bp]
+# ==================================================================================================================
+class MobileViTBlockv2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        B, C, H, W = x.shape
+        d, ffn, n = cfg.d, cfg.ffn, cfg.n_blocks
+        HW = H * W
+        M = B * HW
+        P = cfg.prep
+        x2 = as_2d(x)
+        wd0, g0, b0, wl = params[:4]
+        gL, bL, wp, gp, bp = params[4 + 12 * n:]
+        bs = cfg.bn[0].batch_stats
+        st0, stp = _zeros64(x.device, C, C)
+        samp = _zeros64(x.device, *([B] * (2 * n + 1)))
+        gcount = HW * d
+        # local_rep: dw3x3 + BN + SiLU -> 1x1 (C -> d)
+        y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), col_stats=st0 if bs else None)
+        bn0 = _bn_forward(st0, M, g0, b0, cfg.bn[0])
+        X = ops.pw_gemm(y0, P.get(cfg.i_wl), d, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), samp_stats=samp[0], rows_per_sample=HW)
+        blocks = []
+        for i in range(n):
+            ga, ba, wqkv, bqkv, wo, bo, gf, bf, w1, b1, w2, b2 = params[4 + 12 * i: 16 + 12 * i]
+            ix = cfg.i_blk[i]
+            gnA = ops.gn_finalize(samp[2 * i], gcount, cfg.gn_eps)
+            qkv = ops.pw_gemm(X, P.get(ix.wqkv), 2 * d + 8, a_mode=A_GN, a_p=(ga, ba), row_stats=(gnA[0], gnA[1]), rows_per_sample=HW,
+                              bias=P.get(ix.bqkv))
+            O, S, CTX = ops.linattn_fwd(qkv, B, H, W, d)
+            X1 = ops.pw_gemm(O, P.get(ix.wo), d, bias=bo, R=X, samp_stats=samp[2 * i + 1], rows_per_sample=HW)
+            gnF = ops.gn_finalize(samp[2 * i + 1], gcount, cfg.gn_eps)
+            h = ops.pw_gemm(X1, P.get(ix.w1), ffn, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW, bias=b1)
+            X2 = ops.pw_gemm(h, P.get(ix.w2), d, a_mode=A_SILU, bias=b2, R=X1, samp_stats=samp[2 * i + 2], rows_per_sample=HW)
+            blocks.append((X, gnA, qkv, O, S, CTX, X1, gnF, h))
+            X = X2
+        gnL = ops.gn_finalize(samp[2 * n], gcount, cfg.gn_eps)
+        yp = ops.pw_gemm(X, P.get(cfg.i_wp), C, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]), rows_per_sample=HW,
+                         col_stats=stp if bs else None)
+        bnp = _bn_forward(stp, M, gp, bp, cfg.bn[1])
+        out = ops.bn_apply(yp, bnp, act=False)
+        ctx.cfg, ctx.dims = cfg, (B, C, H, W)
+        ctx.saved = (x2, y0, bn0, blocks, X, gnL, yp, bnp)
+        ctx.save_for_backward(*params)
+        return to_4d(out, B, H, W)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, C, H, W = ctx.dims
+        d, ffn, n = cfg.d, cfg.ffn, cfg.n_blocks
+        HW = H * W
+        M = B * HW
+        P = cfg.prep
+        params = ctx.saved_tensors
+        x2, y0, bn0, blocks, XL, gnL, yp, bnp = ctx.saved
+        wd0, g0, b0, wl = params[:4]
+        gL, bL, wp, gp, bp = params[4 + 12 * n:]
+        ev = not cfg.bn[0].batch_stats
+        dev = x2.device
+        gcount = HW * d
+        dout = as_2d(to_bf16_cl(gout))
+        sdp, sd0 = _zeros64(dev, C, C)
+        grads = [None] * len(params)
+        # ---- conv_proj (GN -> 1x1 -> BN, no act)
+        ops.bn_bwd_reduce(dout, yp, sdp)
+        dgbp, cp = ops.bn_bwd_finalize(sdp, M, gp, bnp, ev)
+        cs, ss = _zeros64(dev, d, B)
+        g = ops.pw_gemm(dout, P.get(cfg.i_wpt), d, K=C, a_mode=A_BNB, A2=yp, a_p=cp, e_mode=E_GN_BWD, Y=XL, e_p=(gL, None),
+                        row_stats=(gnL[0], gnL[1]), rows_per_sample=HW, col_stats=cs, samp_stats=ss)
+        dWp = ops.pw_wgrad(dout, XL, C, d, g_mode=A_BNB, G2=yp, g_p=cp, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]),
+                           rows_per_sample=HW)
+        base = 4 + 12 * n
+        grads[base + 0], grads[base + 1] = cs[1].float(), cs[0].float()  # dgamma = sum v*xhat, dbeta = sum v
+        grads[base + 2], grads[base + 3], grads[base + 4] = dWp.view(C, d, 1, 1), dgbp[0], dgbp[1]
+        (bsum,) = _zeros64(dev, d)  # only row 0 used: column sums of the residual-stream gradient
+        dX = ops.gn_bwd_apply(g, XL, gnL, ss, gcount, B, HW, DRES=None, col_sum=bsum[0] if n > 0 else None)
+        # ---- attention/FFN units, last to first
+        for i in reversed(range(n)):
+            X, gnA, qkv, O, S, CTX, X1, gnF, h = blocks[i]
+            ga, ba, wqkv, bqkv, wo, bo, gf, bf, w1, b1, w2, b2 = params[4 + 12 * i: 16 + 12 * i]
+            ix = cfg.i_blk[i]
+            o = 4 + 12 * i
+            # FFN: X2 = X1 + W2 silu(h) + b2 ; h = W1 GN(X1) + b1
+            grads[o + 11] = bsum[0].float()  # db2
+            grads[o + 10] = ops.pw_wgrad(dX, h, d, ffn, a_mode=A_SILU).view(d, ffn, 1, 1)
+            csh, csf, ssf, bsum1 = _zeros64(dev, ffn, d, B, d)
+            dh = ops.pw_gemm(dX, P.get(ix.w2t), ffn, K=d, e_mode=E_SILU_BWD, Y=h, col_stats=csh)
+            grads[o + 9] = csh[0].float()  # db1 = column sums of dh
+            grads[o + 8] = ops.pw_wgrad(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW).view(ffn, d, 1, 1)
+            gF = ops.pw_gemm(dh, P.get(ix.w1t), d, K=ffn, e_mode=E_GN_BWD, Y=X1, e_p=(gf, None), row_stats=(gnF[0], gnF[1]),
+                             rows_per_sample=HW, col_stats=csf, samp_stats=ssf)
+            grads[o + 6], grads[o + 7] = csf[1].float(), csf[0].float()
+            dX1 = ops.gn_bwd_apply(gF, X1, gnF, ssf, gcount, B, HW, DRES=dX, col_sum=bsum1[0])
+            # attention: X1 = X + Wo O + bo ; O = linattn(qkv) ; qkv = Wqkv GN(X) + bqkv
+            grads[o + 5] = bsum1[0].float()  # dbo
+            grads[o + 4] = ops.pw_wgrad(dX1, O, d, d).view(d, d, 1, 1)
+            dO = ops.pw_gemm(dX1, P.get(ix.wot), d, K=d)
+            dbq = torch.zeros(2 * d + 8, device=dev, dtype=torch.float32)
+            dqkv = ops.linattn_bwd(qkv, dO, S, CTX, B, H, W, d, dbias=dbq)
+            dWq = ops.pw_wgrad(dqkv, X, 2 * d + 8, d, a_mode=A_GN, a_p=(ga, ba), row_stats=(gnA[0], gnA[1]), rows_per_sample=HW)
+            grads[o + 2] = ops.unprep_grad(dWq, 2 * d + 1, d, d, 0, rot=1).view(2 * d + 1, d, 1, 1)
+            grads[o + 3] = ops.unprep_grad(dbq, 2 * d + 1, 1, 1, 3, rot=1)
+            csa, ssa, bsum = _zeros64(dev, d, B, d)
+            gA = ops.pw_gemm(dqkv, P.get(ix.wqkvt), d, K=2 * d + 8, e_mode=E_GN_BWD, Y=X, e_p=(ga, None), row_stats=(gnA[0], gnA[1]),
+                             rows_per_sample=HW, col_stats=csa, samp_stats=ssa)
+            grads[o + 0], grads[o + 1] = csa[1].float(), csa[0].float()
+            dX = ops.gn_bwd_apply(gA, X, gnA, ssa, gcount, B, HW, DRES=dX1, col_sum=bsum[0] if i > 0 else None)
+        # ---- local_rep: 1x1 (no bias / norm) <- SiLU <- BN0 <- dw3x3
+        grads[3] = ops.pw_wgrad(dX, y0, d, C, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3])).view(d, C, 1, 1)
+        dz0 = ops.pw_gemm(dX, P.get(cfg.i_wlt), C, K=d, e_mode=E_SILU_BWD, Y=y0, e_p=(bn0[2], bn0[3]), col_stats=sd0)
+        dgb0, c0 = ops.bn_bwd_finalize(sd0, M, g0, bn0, ev)
+        dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW)
+        grads[0] = ops.unprep_grad(dWt, C, 9, C, 2).view(C, 1, 3, 3)
+        grads[1], grads[2] = dgb0[0], dgb0[1]
+        return (to_4d(dx, B, H, W), None) + tuple(grads)
+
+
+# ==================================================================================================================
+# classifier head: GlobalPool(mean) + LinearLayer (cvnets/layers/global_pool.py:60-71, linear_layer.py:90)
+# ==================================================================================================================
+class PoolLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cfg, w, b):
+        B, C, H, W = x.shape
+        x2 = as_2d(x)
+        pooled = ops.global_pool_fwd(x2, B, H * W)
+        ncls = w.shape[0]
+        npad = (ncls + 7) // 8 * 8
+        logits = ops.pw_gemm(pooled, cfg.prep.get(cfg.i_w), npad, bias=cfg.prep.get(cfg.i_b))
+        ctx.cfg, ctx.dims = cfg, (B, C, H, W, ncls, npad)
+        ctx.saved = (pooled,)
+        return logits[:, :ncls]
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, C, H, W, ncls, npad = ctx.dims
+        (pooled,) = ctx.saved
+        g = torch.zeros((B, npad), device=pooled.device, dtype=BF16)
+        g[:, :ncls] = gout
+        db = torch.zeros(npad, device=pooled.device, dtype=torch.float32)
+        dW = ops.pw_wgrad(g, pooled, npad, C, dbias=db)
+        dp = ops.pw_gemm(g, cfg.prep.get(cfg.i_wt), C, K=npad)
+        dx = ops.global_pool_bwd(dp, B, H * W)
+        return to_4d(dx, B, H, W), None, dW[:ncls], db[:ncls]

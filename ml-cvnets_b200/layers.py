@@ -1,0 +1,220 @@
+"""Host-side mirror of ``cvnets.layers`` for the hot path: SAME class names, constructor signatures, child-module tree
+and ``state_dict`` keys as the reference, so published checkpoints load unchanged and the
+reference's isinstance/name based machinery (weight init, BN momentum annealing, weight-decay grouping, EMA deepcopy)
+keeps working.  Parameters are ordinary ``nn.Parameter``s inside ordinary ``nn.Conv2d`` / ``nn.BatchNorm2d`` /
+``nn.GroupNorm`` / ``nn.Linear`` children; only ``forward`` is ours and it runs hand-written sm_100a kernels.
+
+There is deliberately NO PyTorch fallback: a layer used outside a fused module raises unless its own kernel path exists.
+"""
+from __future__ import annotations
+
+import argparse
+from typing import Optional, Tuple, Union
+
+import torch
+from torch import Tensor, nn
+
+
+def _opt(opts, name: str, default):
+    return getattr(opts, name, default) if opts is not None else default
+
+
+class BaseLayer(nn.Module):
+    """cvnets/layers/base_layer.py:14-63."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__()
+
+    @classmethod
+    def add_arguments(cls, parser: argparse.ArgumentParser):
+        return parser
+
+
+class Identity(BaseLayer):
+    """cvnets/layers/identity.py."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x
+
+
+class Dropout(nn.Dropout):
+    """cvnets/layers/dropout.py:11-29.  The MobileViTv2 recipe has p = 0 everywhere (mobilevit_v2.py:105-122)."""
+
+    def __init__(self, p: Optional[float] = 0.5, inplace: Optional[bool] = False, *args, **kwargs) -> None:
+        super().__init__(p=p, inplace=inplace)
+
+
+class Swish(nn.SiLU):
+    """cvnets/layers/activation/swish.py:13-20."""
+
+    def __init__(self, inplace: Optional[bool] = False, *args, **kwargs) -> None:
+        super().__init__(inplace=inplace)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """cvnets/layers/normalization/batch_norm.py:14-49."""
+
+    def __init__(self, num_features: int, eps: Optional[float] = 1e-5, momentum: Optional[float] = 0.1,
+                 affine: Optional[bool] = True, track_running_stats: Optional[bool] = True, *args, **kwargs) -> None:
+        super().__init__(num_features=num_features, eps=eps, momentum=momentum, affine=affine,
+                         track_running_stats=track_running_stats)
+
+
+class LayerNorm2D_NCHW(nn.GroupNorm):
+    """cvnets/layers/normalization/layer_norm.py:75-108 (``layer_norm_2d``): GroupNorm with one group."""
+
+    def __init__(self, num_features: int, eps: Optional[float] = 1e-5, elementwise_affine: Optional[bool] = True,
+                 *args, **kwargs) -> None:
+        super().__init__(num_channels=num_features, eps=eps, affine=elementwise_affine, num_groups=1)
+        self.num_channels = num_features
+
+    def forward(self, x: Tensor) -> Tensor:  # only ever applied inside the fused MobileViTBlockv2 path
+        raise NotImplementedError("LayerNorm2D_NCHW runs fused inside MobileViTBlockv2 (no standalone kernel path)")
+
+    def __repr__(self):
+        return "{}(num_channels={}, eps={}, affine={})".format(self.__class__.__name__, self.num_channels, self.eps, self.affine)
+
+
+norm_layers_tuple = (nn.BatchNorm2d, nn.GroupNorm)
+
+
+def get_normalization_layer(opts, num_features: int, norm_type: Optional[str] = None, *args, **kwargs) -> nn.Module:
+    """cvnets/layers/normalization_layers.py: factory restricted to the norms on the hot path."""
+    norm_type = norm_type or _opt(opts, "model.normalization.name", "batch_norm")
+    momentum = _opt(opts, "model.normalization.momentum", 0.1)
+    if norm_type in ("batch_norm", "batch_norm_2d"):
+        return BatchNorm2d(num_features=num_features, momentum=momentum)
+    if norm_type in ("layer_norm_2d", "layer_norm_nchw"):
+        return LayerNorm2D_NCHW(num_features=num_features)
+    raise NotImplementedError(f"normalization '{norm_type}' is not on the B200 hot path (batch_norm, layer_norm_2d are)")
+
+
+def build_activation_layer(opts, *args, **kwargs) -> nn.Module:
+    name = _opt(opts, "model.activation.name", "swish")
+    if name in ("swish", "silu"):
+        return Swish()
+    raise NotImplementedError(f"activation '{name}' is not on the B200 hot path (swish is)")
+
+
+class Conv2d(nn.Conv2d):
+    """cvnets/layers/conv_layer.py:18-66."""
+
+
+class ConvLayer2d(BaseLayer):
+    """cvnets/layers/conv_layer.py:69-267,275-277: ``self.block = Sequential(conv[, norm][, act])`` with keys
+    ``block.conv``, ``block.norm``, ``block.act``; auto padding ``(k-1)//2 * dilation``; bias only on request."""
+
+    def __init__(self, opts, in_channels: int, out_channels: int, kernel_size: Union[int, Tuple[int, ...]],
+                 stride: Union[int, Tuple[int, ...]] = 1, dilation: Union[int, Tuple[int, ...]] = 1,
+                 padding: Optional[Union[int, Tuple[int, ...]]] = None, groups: int = 1, bias: bool = False,
+                 padding_mode: str = "zeros", use_norm: bool = True, use_act: bool = True,
+                 norm_layer: Optional[nn.Module] = None, act_layer: Optional[nn.Module] = None, *args, **kwargs) -> None:
+        super().__init__()
+        if norm_layer is None and use_norm:
+            norm_type = _opt(opts, "model.normalization.name", "batch_norm")
+            norm_layer = get_normalization_layer(opts=opts, num_features=out_channels, norm_type=norm_type)
+        if act_layer is None and use_act:
+            act_layer = build_activation_layer(opts)
+        if use_norm and isinstance(norm_layer, LayerNorm2D_NCHW):
+            bias = True
+        ks = (kernel_size,) * 2 if isinstance(kernel_size, int) else tuple(kernel_size)
+        st = (stride,) * 2 if isinstance(stride, int) else tuple(stride)
+        dl = (dilation,) * 2 if isinstance(dilation, int) else tuple(dilation)
+        if padding is None:
+            padding = tuple(int((ks[i] - 1) / 2) * dl[i] for i in range(2))
+        assert in_channels % groups == 0 and out_channels % groups == 0
+        block = nn.Sequential()
+        block.add_module("conv", Conv2d(in_channels, out_channels, ks, st, padding, dl, groups, bias, padding_mode))
+        self.norm_name = None
+        if use_norm:
+            block.add_module("norm", norm_layer)
+            self.norm_name = norm_layer.__class__.__name__
+        self.act_name = None
+        if use_act:
+            block.add_module("act", act_layer)
+            self.act_name = act_layer.__class__.__name__
+        self.block = block
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.stride, self.groups, self.kernel_size, self.bias, self.dilation = st, groups, ks, bias, dl
+        self._stem = None
+
+    def forward(self, x: Tensor) -> Tensor:
+        """Standalone use is supported for the MobileViT stem pattern (3 -> C0, 3x3, stride 2, BN, SiLU)."""
+        conv = self.block.conv
+        if (self.in_channels == 3 and self.kernel_size == (3, 3) and self.stride == (2, 2) and self.groups == 1
+                and self.dilation == (1, 1) and conv.bias is None and self.norm_name == "BatchNorm2d" and self.act_name is not None
+                and self.out_channels % 8 == 0):
+            from .modules import _stem_forward
+            return _stem_forward(self, x)
+        raise NotImplementedError(
+            "standalone ConvLayer2d.forward exists only for the MobileViT stem; other convs run fused inside "
+            "InvertedResidual / MobileViTBlockv2 (no PyTorch fallback by design)")
+
+    def __repr__(self):
+        s = self.block[0].__repr__()[:-1]
+        if self.norm_name is not None:
+            s += ", normalization={}".format(self.norm_name)
+        if self.act_name is not None:
+            s += ", activation={}".format(self.act_name)
+        return s + ")"
+
+
+class LinearLayer(BaseLayer):
+    """cvnets/layers/linear_layer.py:17-103."""
+
+    def __init__(self, in_features: int, out_features: int, bias: Optional[bool] = True, channel_first: Optional[bool] = False,
+                 *args, **kwargs) -> None:
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features)) if bias else None
+        self.in_features, self.out_features, self.channel_first = in_features, out_features, channel_first
+        self.reset_params()
+
+    def reset_params(self):
+        nn.init.xavier_uniform_(self.weight)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, 0)
+
+    def forward(self, x: Tensor) -> Tensor:
+        raise NotImplementedError("LinearLayer runs fused with GlobalPool in the classifier head (PoolLinearFn)")
+
+    def __repr__(self):
+        return "{}(in_features={}, out_features={}, bias={}, channel_first={})".format(
+            self.__class__.__name__, self.in_features, self.out_features, self.bias is not None, self.channel_first)
+
+
+class GlobalPool(BaseLayer):
+    """cvnets/layers/global_pool.py:16-83 (mean pooling only on the hot path)."""
+
+    def __init__(self, pool_type: Optional[str] = "mean", keep_dim: Optional[bool] = False, *args, **kwargs) -> None:
+        super().__init__()
+        if pool_type != "mean":
+            raise NotImplementedError("only mean pooling is on the B200 hot path")
+        self.pool_type, self.keep_dim = pool_type, keep_dim
+
+    def forward(self, x: Tensor) -> Tensor:
+        raise NotImplementedError("GlobalPool runs fused with the classifier LinearLayer (PoolLinearFn)")
+
+    def __repr__(self):
+        return "{}(type={})".format(self.__class__.__name__, self.pool_type)
+
+
+class LinearSelfAttention(BaseLayer):
+    """cvnets/layers/linear_attention.py:16-215.  Children ``qkv_proj`` (d -> 1+2d, bias) and ``out_proj`` (d -> d, bias);
+    the forward runs inside MobileViTBlockv2Fn (qkv GEMM -> fused softmax/context/relu kernel -> out_proj GEMM)."""
+
+    def __init__(self, opts, embed_dim: int, attn_dropout: Optional[float] = 0.0, bias: Optional[bool] = True, *args, **kwargs) -> None:
+        super().__init__()
+        self.qkv_proj = ConvLayer2d(opts=opts, in_channels=embed_dim, out_channels=1 + (2 * embed_dim), bias=bias, kernel_size=1,
+                                    use_norm=False, use_act=False)
+        self.attn_dropout = Dropout(p=attn_dropout)
+        self.out_proj = ConvLayer2d(opts=opts, in_channels=embed_dim, out_channels=embed_dim, bias=bias, kernel_size=1,
+                                    use_norm=False, use_act=False)
+        self.embed_dim = embed_dim
+
+    def forward(self, x: Tensor, x_prev: Optional[Tensor] = None, *args, **kwargs) -> Tensor:
+        raise NotImplementedError("LinearSelfAttention runs fused inside MobileViTBlockv2 (self-attention on [B,C,H,W]); "
+                                  "the cross-attention (video) path is out of scope (SURVEY.md App. A5)")
+
+    def __repr__(self):
+        return "{}(embed_dim={}, attn_dropout={})".format(self.__class__.__name__, self.embed_dim, self.attn_dropout.p)

@@ -1,0 +1,262 @@
+"""Host-side mirror of ``cvnets.modules`` for the hot path (drop-in ``nn.Module``s, see layers.py for the contract).
+
+``InvertedResidual`` (cvnets/modules/mobilenetv2.py:141-246), ``LinearAttnFFN`` (cvnets/modules/transformer.py:159-264)
+and ``MobileViTBlockv2`` (cvnets/modules/mobilevit_block.py:329-667): identical constructor signatures, child tree and
+``state_dict`` keys; ``forward`` dispatches to the autograd Functions in functional.py (hand-written sm_100a kernels).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import functional as Fn
+from .layers import ConvLayer2d, Dropout, LinearSelfAttention, get_normalization_layer
+from .ops import PreparedWeights as PW
+
+
+def make_divisible(v, divisor: int = 8, min_value=None):
+    """utils/math_utils.py:9-30."""
+    if min_value is None:
+        min_value = divisor
+    new_v = max(min_value, int(v + divisor / 2) // divisor * divisor)
+    if new_v < 0.9 * v:
+        new_v += divisor
+    return new_v
+
+
+def _require_cuda(x: Tensor, who: str):
+    if not x.is_cuda:
+        raise RuntimeError(f"{who}: ml-cvnets_b200 runs on CUDA (sm_100a) only and has no CPU fallback; got a {x.device} tensor")
+
+
+class BaseModule(nn.Module):
+    """cvnets/modules/base_module.py:12-22."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__()
+
+    def forward(self, x, *args, **kwargs):
+        raise NotImplementedError
+
+
+# -------------------------------------------------------------------------------------------------------------- stem
+def _stem_forward(layer: ConvLayer2d, x: Tensor) -> Tensor:
+    _require_cuda(x, "ConvLayer2d(stem)")
+    if layer._stem is None:
+        prep = PW()
+        cfg = SimpleNamespace(prep=prep, i_w=prep.add(layer.block.conv.weight, PW.KIND_ROWMAJOR, ldd=32))
+        layer._stem = cfg
+    cfg = layer._stem
+    cfg.bn = Fn.bn_cfg(layer.block.norm)
+    cfg.prep.prepare(force=layer.training)
+    return Fn.StemFn.apply(x, cfg, layer.block.conv.weight, layer.block.norm.weight, layer.block.norm.bias)
+
+
+# ---------------------------------------------------------------------------------------------------- InvertedResidual
+class InvertedResidual(BaseModule):
+    def __init__(self, opts, in_channels: int, out_channels: int, stride: int, expand_ratio: Union[int, float], dilation: int = 1,
+                 skip_connection: Optional[bool] = True, *args, **kwargs) -> None:
+        assert stride in [1, 2]
+        hidden_dim = make_divisible(int(round(in_channels * expand_ratio)), 8)
+        super().__init__()
+        block = nn.Sequential()
+        if expand_ratio != 1:
+            block.add_module("exp_1x1", ConvLayer2d(opts, in_channels=in_channels, out_channels=hidden_dim, kernel_size=1,
+                                                    use_act=True, use_norm=True))
+        block.add_module("conv_3x3", ConvLayer2d(opts, in_channels=hidden_dim, out_channels=hidden_dim, stride=stride, kernel_size=3,
+                                                 groups=hidden_dim, use_act=True, use_norm=True, dilation=dilation))
+        block.add_module("red_1x1", ConvLayer2d(opts, in_channels=hidden_dim, out_channels=out_channels, kernel_size=1,
+                                                use_act=False, use_norm=True))
+        self.block = block
+        self.in_channels, self.out_channels, self.exp, self.dilation, self.stride = in_channels, out_channels, expand_ratio, dilation, stride
+        self.hidden_dim = hidden_dim
+        self.use_res_connect = self.stride == 1 and in_channels == out_channels and skip_connection
+        self._cfg = None
+
+    def _build_cfg(self):
+        if self.exp == 1:
+            raise NotImplementedError("InvertedResidual with expand_ratio == 1 (no exp_1x1) is not on the MobileViT hot path")
+        if self.dilation != 1:
+            raise NotImplementedError("dilated depthwise conv (segmentation heads, SURVEY.md 8f row 4) is a 'next' row")
+        if self.in_channels % 8 or self.out_channels % 8 or self.hidden_dim % 8:
+            raise NotImplementedError("channel counts must be multiples of 8 (16-byte channel vectors)")
+        b = self.block
+        prep = PW()
+        cfg = SimpleNamespace(prep=prep, hid=self.hidden_dim, cout=self.out_channels, stride=self.stride, residual=self.use_res_connect)
+        cfg.i_w1 = prep.add(b.exp_1x1.block.conv.weight, PW.KIND_ROWMAJOR)
+        cfg.i_w1t = prep.add(b.exp_1x1.block.conv.weight, PW.KIND_TRANSPOSED)
+        cfg.i_wd = prep.add(b.conv_3x3.block.conv.weight, PW.KIND_TAPMAJOR_F32)
+        cfg.i_w3 = prep.add(b.red_1x1.block.conv.weight, PW.KIND_ROWMAJOR)
+        cfg.i_w3t = prep.add(b.red_1x1.block.conv.weight, PW.KIND_TRANSPOSED)
+        self._cfg = cfg
+
+    def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
+        _require_cuda(x, "InvertedResidual")
+        if self._cfg is None:
+            self._build_cfg()
+        cfg, b = self._cfg, self.block
+        cfg.bn = [Fn.bn_cfg(b.exp_1x1.block.norm), Fn.bn_cfg(b.conv_3x3.block.norm), Fn.bn_cfg(b.red_1x1.block.norm)]
+        cfg.prep.prepare(force=self.training)
+        return Fn.InvertedResidualFn.apply(
+            Fn.to_bf16_cl(x), cfg,
+            b.exp_1x1.block.conv.weight, b.exp_1x1.block.norm.weight, b.exp_1x1.block.norm.bias,
+            b.conv_3x3.block.conv.weight, b.conv_3x3.block.norm.weight, b.conv_3x3.block.norm.bias,
+            b.red_1x1.block.conv.weight, b.red_1x1.block.norm.weight, b.red_1x1.block.norm.bias)
+
+    def __repr__(self) -> str:
+        return "{}(in_channels={}, out_channels={}, stride={}, exp={}, dilation={}, skip_conn={})".format(
+            self.__class__.__name__, self.in_channels, self.out_channels, self.stride, self.exp, self.dilation, self.use_res_connect)
+
+
+# -------------------------------------------------------------------------------------------------------- LinearAttnFFN
+class LinearAttnFFN(BaseModule):
+    """Parameter container with the reference tree (pre_norm_attn.{0,1,2}, pre_norm_ffn.{0,1,2,3,4}); executed inside
+    MobileViTBlockv2Fn."""
+
+    def __init__(self, opts, embed_dim: int, ffn_latent_dim: int, attn_dropout: Optional[float] = 0.0, dropout: Optional[float] = 0.1,
+                 ffn_dropout: Optional[float] = 0.0, norm_layer: Optional[str] = "layer_norm_2d", *args, **kwargs) -> None:
+        super().__init__()
+        attn_unit = LinearSelfAttention(opts, embed_dim=embed_dim, attn_dropout=attn_dropout, bias=True)
+        self.pre_norm_attn = nn.Sequential(
+            get_normalization_layer(opts=opts, norm_type=norm_layer, num_features=embed_dim), attn_unit, Dropout(p=dropout))
+        self.pre_norm_ffn = nn.Sequential(
+            get_normalization_layer(opts=opts, norm_type=norm_layer, num_features=embed_dim),
+            ConvLayer2d(opts=opts, in_channels=embed_dim, out_channels=ffn_latent_dim, kernel_size=1, stride=1, bias=True,
+                        use_norm=False, use_act=True),
+            Dropout(p=ffn_dropout),
+            ConvLayer2d(opts=opts, in_channels=ffn_latent_dim, out_channels=embed_dim, kernel_size=1, stride=1, bias=True,
+                        use_norm=False, use_act=False),
+            Dropout(p=dropout))
+        self.embed_dim, self.ffn_dim, self.ffn_dropout, self.std_dropout = embed_dim, ffn_latent_dim, ffn_dropout, dropout
+        self.attn_fn_name, self.norm_name = attn_unit.__repr__(), norm_layer
+        self.attn_dropout_p = attn_dropout
+
+    def forward(self, x: Tensor, x_prev: Optional[Tensor] = None, *args, **kwargs) -> Tensor:
+        raise NotImplementedError("LinearAttnFFN runs fused inside MobileViTBlockv2 (no standalone kernel path)")
+
+    def __repr__(self) -> str:
+        return "{}(embed_dim={}, ffn_dim={}, dropout={}, ffn_dropout={}, attn_fn={}, norm_layer={})".format(
+            self.__class__.__name__, self.embed_dim, self.ffn_dim, self.std_dropout, self.ffn_dropout, self.attn_fn_name, self.norm_name)
+
+
+# ----------------------------------------------------------------------------------------------------- MobileViTBlockv2
+class MobileViTBlockv2(BaseModule):
+    def __init__(self, opts, in_channels: int, attn_unit_dim: int,
+                 ffn_multiplier: Optional[Union[Sequence[Union[int, float]], int, float]] = 2.0, n_attn_blocks: Optional[int] = 2,
+                 attn_dropout: Optional[float] = 0.0, dropout: Optional[float] = 0.0, ffn_dropout: Optional[float] = 0.0,
+                 patch_h: Optional[int] = 8, patch_w: Optional[int] = 8, conv_ksize: Optional[int] = 3, dilation: Optional[int] = 1,
+                 attn_norm_layer: Optional[str] = "layer_norm_2d", *args, **kwargs) -> None:
+        cnn_out_dim = attn_unit_dim
+        conv_3x3_in = ConvLayer2d(opts=opts, in_channels=in_channels, out_channels=in_channels, kernel_size=conv_ksize, stride=1,
+                                  use_norm=True, use_act=True, dilation=dilation, groups=in_channels)
+        conv_1x1_in = ConvLayer2d(opts=opts, in_channels=in_channels, out_channels=cnn_out_dim, kernel_size=1, stride=1,
+                                  use_norm=False, use_act=False)
+        super().__init__()
+        self.local_rep = nn.Sequential(conv_3x3_in, conv_1x1_in)
+        self.global_rep, attn_unit_dim = self._build_attn_layer(opts=opts, d_model=attn_unit_dim, ffn_mult=ffn_multiplier,
+                                                               n_layers=n_attn_blocks, attn_dropout=attn_dropout, dropout=dropout,
+                                                               ffn_dropout=ffn_dropout, attn_norm_layer=attn_norm_layer)
+        self.conv_proj = ConvLayer2d(opts=opts, in_channels=cnn_out_dim, out_channels=in_channels, kernel_size=1, stride=1,
+                                     use_norm=True, use_act=False)
+        self.patch_h, self.patch_w, self.patch_area = patch_h, patch_w, patch_w * patch_h
+        self.cnn_in_dim, self.cnn_out_dim, self.transformer_in_dim = in_channels, cnn_out_dim, attn_unit_dim
+        self.dropout, self.attn_dropout, self.ffn_dropout = dropout, attn_dropout, ffn_dropout
+        self.n_blocks, self.conv_ksize, self.dilation = n_attn_blocks, conv_ksize, dilation
+        self.attn_norm_layer = attn_norm_layer
+        self._cfg = None
+
+    def _build_attn_layer(self, opts, d_model: int, ffn_mult, n_layers: int, attn_dropout: float, dropout: float, ffn_dropout: float,
+                          attn_norm_layer: str, *args, **kwargs) -> Tuple[nn.Module, int]:
+        if isinstance(ffn_mult, Sequence) and len(ffn_mult) == 2:
+            ffn_dims = np.linspace(ffn_mult[0], ffn_mult[1], n_layers, dtype=float) * d_model
+        elif isinstance(ffn_mult, Sequence) and len(ffn_mult) == 1:
+            ffn_dims = [ffn_mult[0] * d_model] * n_layers
+        elif isinstance(ffn_mult, (int, float)):
+            ffn_dims = [ffn_mult * d_model] * n_layers
+        else:
+            raise NotImplementedError
+        ffn_dims = [int((d // 16) * 16) for d in ffn_dims]
+        global_rep = [LinearAttnFFN(opts=opts, embed_dim=d_model, ffn_latent_dim=ffn_dims[i], attn_dropout=attn_dropout, dropout=dropout,
+                                    ffn_dropout=ffn_dropout, norm_layer=attn_norm_layer) for i in range(n_layers)]
+        global_rep.append(get_normalization_layer(opts=opts, norm_type=attn_norm_layer, num_features=d_model))
+        return nn.Sequential(*global_rep), d_model
+
+    def _build_cfg(self):
+        C, d = self.cnn_in_dim, self.cnn_out_dim
+        if self.patch_h != 2 or self.patch_w != 2:
+            raise NotImplementedError("only 2x2 patches (every MobileViTv2 config) are implemented")
+        if self.conv_ksize != 3 or self.dilation != 1:
+            raise NotImplementedError("local_rep must be an undilated 3x3 depthwise conv")
+        if self.attn_norm_layer not in ("layer_norm_2d", "layer_norm_nchw"):
+            raise NotImplementedError("attn_norm_layer must be layer_norm_2d")
+        if self.dropout or self.attn_dropout or self.ffn_dropout:
+            raise NotImplementedError("dropout > 0 is not implemented (the MobileViTv2 recipes use 0)")
+        ffns = {blk.ffn_dim for blk in list(self.global_rep)[:-1]}
+        if len(ffns) != 1:
+            raise NotImplementedError("per-block FFN widths must be equal")
+        if C % 8 or d % 8:
+            raise NotImplementedError("channel counts must be multiples of 8")
+        prep = PW()
+        cfg = SimpleNamespace(prep=prep, d=d, ffn=ffns.pop(), n_blocks=self.n_blocks, gn_eps=float(self.global_rep[-1].eps))
+        cfg.i_wd0 = prep.add(self.local_rep[0].block.conv.weight, PW.KIND_TAPMAJOR_F32)
+        cfg.i_wl = prep.add(self.local_rep[1].block.conv.weight, PW.KIND_ROWMAJOR)
+        cfg.i_wlt = prep.add(self.local_rep[1].block.conv.weight, PW.KIND_TRANSPOSED)
+        cfg.i_blk = []
+        for i in range(self.n_blocks):
+            blk = self.global_rep[i]
+            attn = blk.pre_norm_attn[1]
+            ix = SimpleNamespace()
+            # qkv: reference row order [q, K(d), V(d)] -> kernel order [K, V, q, pad(7)]  (rot = 1)
+            ix.wqkv = prep.add(attn.qkv_proj.block.conv.weight, PW.KIND_ROWMAJOR, rot=1, dst_rows=2 * d + 8)
+            ix.wqkvt = prep.add(attn.qkv_proj.block.conv.weight, PW.KIND_TRANSPOSED, rot=1, ldd=2 * d + 8)
+            ix.bqkv = prep.add(attn.qkv_proj.block.conv.bias, PW.KIND_VECTOR_F32, rot=1, dst_rows=2 * d + 8)
+            ix.wo = prep.add(attn.out_proj.block.conv.weight, PW.KIND_ROWMAJOR)
+            ix.wot = prep.add(attn.out_proj.block.conv.weight, PW.KIND_TRANSPOSED)
+            ix.w1 = prep.add(blk.pre_norm_ffn[1].block.conv.weight, PW.KIND_ROWMAJOR)
+            ix.w1t = prep.add(blk.pre_norm_ffn[1].block.conv.weight, PW.KIND_TRANSPOSED)
+            ix.w2 = prep.add(blk.pre_norm_ffn[3].block.conv.weight, PW.KIND_ROWMAJOR)
+            ix.w2t = prep.add(blk.pre_norm_ffn[3].block.conv.weight, PW.KIND_TRANSPOSED)
+            cfg.i_blk.append(ix)
+        cfg.i_wp = prep.add(self.conv_proj.block.conv.weight, PW.KIND_ROWMAJOR)
+        cfg.i_wpt = prep.add(self.conv_proj.block.conv.weight, PW.KIND_TRANSPOSED)
+        self._cfg = cfg
+
+    def _params(self):
+        lr = self.local_rep
+        out = [lr[0].block.conv.weight, lr[0].block.norm.weight, lr[0].block.norm.bias, lr[1].block.conv.weight]
+        for i in range(self.n_blocks):
+            blk = self.global_rep[i]
+            attn = blk.pre_norm_attn[1]
+            out += [blk.pre_norm_attn[0].weight, blk.pre_norm_attn[0].bias,
+                    attn.qkv_proj.block.conv.weight, attn.qkv_proj.block.conv.bias,
+                    attn.out_proj.block.conv.weight, attn.out_proj.block.conv.bias,
+                    blk.pre_norm_ffn[0].weight, blk.pre_norm_ffn[0].bias,
+                    blk.pre_norm_ffn[1].block.conv.weight, blk.pre_norm_ffn[1].block.conv.bias,
+                    blk.pre_norm_ffn[3].block.conv.weight, blk.pre_norm_ffn[3].block.conv.bias]
+        gl = self.global_rep[self.n_blocks]
+        out += [gl.weight, gl.bias, self.conv_proj.block.conv.weight, self.conv_proj.block.norm.weight, self.conv_proj.block.norm.bias]
+        return out
+
+    def forward_spatial(self, x: Tensor, *args, **kwargs) -> Tensor:
+        _require_cuda(x, "MobileViTBlockv2")
+        if x.shape[2] % self.patch_h or x.shape[3] % self.patch_w:
+            raise NotImplementedError("H, W must be multiples of the patch size (the bilinear resize_input_if_needed path, "
+                                      "mobilevit_block.py:595-603, never fires at 256x256 and is out of scope)")
+        if self._cfg is None:
+            self._build_cfg()
+        cfg = self._cfg
+        cfg.bn = [Fn.bn_cfg(self.local_rep[0].block.norm), Fn.bn_cfg(self.conv_proj.block.norm)]
+        cfg.prep.prepare(force=self.training)
+        return Fn.MobileViTBlockv2Fn.apply(Fn.to_bf16_cl(x), cfg, *self._params())
+
+    def forward(self, x: Union[Tensor, Tuple[Tensor]], *args, **kwargs) -> Union[Tensor, Tuple[Tensor, Tensor]]:
+        if isinstance(x, Tuple) and len(x) == 2:
+            raise NotImplementedError("forward_temporal (video cross-attention, mobilevit_block.py:628-655) is out of scope")
+        elif isinstance(x, Tensor):
+            return self.forward_spatial(x)
+        else:
+            raise NotImplementedError

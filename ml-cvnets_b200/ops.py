@@ -1,0 +1,366 @@
+"""Thin Python wrappers over the C ABI (one function per kernel entry point).
+
+Tensors are torch CUDA tensors used purely as device memory (allocation through the caching allocator, current stream);
+every wrapper launches on ``torch.cuda.current_stream()`` and never synchronises.  2-D activation matrices are
+``[M, C]`` bf16 (channels-last feature maps viewed as matrices).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import (A_AFF, A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU, E_GN_BWD, E_SILU, E_SILU_BWD, E_STORE)  # noqa: F401
+
+Tensor = torch.Tensor
+launch_count = 0  # number of kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _lib():
+    return L.load()
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# --------------------------------------------------------------------------------------------------------------- GEMM
+def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: int = A_RAW, A2: Optional[Tensor] = None,
+            a_p: Sequence[Optional[Tensor]] = (None, None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,
+            rows_per_sample: int = 0, bias: Optional[Tensor] = None, e_mode: int = E_STORE, Y: Optional[Tensor] = None,
+            e_p: Sequence[Optional[Tensor]] = (None, None), R: Optional[Tensor] = None, out: Optional[Tensor] = None,
+            out_fp32: bool = False, col_stats: Optional[Tensor] = None, samp_stats: Optional[Tensor] = None) -> Tensor:
+    """C[M,N] = epi(load(A)[M,K] @ W[N,K]^T + bias).  ``col_stats``/``samp_stats``: fp64 [2, *] accumulators (pre-zeroed)."""
+    lib = _lib()
+    M = A.shape[0]
+    K = A.shape[1] if K is None else K
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    a = L.GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda = A.data_ptr(), A.stride(0)
+    if A2 is not None:
+        a.A2, a.lda2 = A2.data_ptr(), A2.stride(0)
+    a.a_mode = a_mode
+    a.a_p0, a.a_p1, a.a_p2 = _p(a_p[0]), _p(a_p[1]), _p(a_p[2] if len(a_p) > 2 else None)
+    if row_stats is not None:
+        a.row_mean, a.row_rstd = row_stats[0].data_ptr(), row_stats[1].data_ptr()
+    a.rows_per_sample = rows_per_sample
+    a.W, a.ldw = W.data_ptr(), W.stride(0)
+    a.bias = _p(bias)
+    a.e_mode = e_mode
+    if Y is not None:
+        a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
+    a.e_p0, a.e_p1 = _p(e_p[0]), _p(e_p[1])
+    if R is not None:
+        a.R, a.ldr = R.data_ptr(), R.stride(0)
+    a.C, a.ldc, a.c_fp32 = out.data_ptr(), out.stride(0), int(out.dtype == torch.float32)
+    if col_stats is not None:
+        a.col_sum, a.col_sq = col_stats[0].data_ptr(), col_stats[1].data_ptr()
+    if samp_stats is not None:
+        a.samp_sum, a.samp_sq = samp_stats[0].data_ptr(), samp_stats[1].data_ptr()
+    L.check(lib.cvb_pw_gemm(ctypes.byref(a), _stream()), "cvb_pw_gemm")
+    _count()
+    return out
+
+
+def pw_wgrad(G: Tensor, A: Tensor, N: int, K: int, *, g_mode: int = A_RAW, G2: Optional[Tensor] = None,
+             g_p: Sequence[Optional[Tensor]] = (None, None, None), a_mode: int = A_RAW,
+             a_p: Sequence[Optional[Tensor]] = (None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,
+             rows_per_sample: int = 0, dW: Optional[Tensor] = None, dbias: Optional[Tensor] = None) -> Tensor:
+    """dW[N,K] (fp32, zero-initialised here unless given) += load(G)^T @ load(A)."""
+    lib = _lib()
+    if dW is None:
+        dW = torch.zeros((N, K), device=G.device, dtype=torch.float32)
+    a = L.WgradArgs()
+    a.M, a.N, a.K = G.shape[0], N, K
+    a.G, a.ldg, a.g_mode = G.data_ptr(), G.stride(0), g_mode
+    if G2 is not None:
+        a.G2, a.ldg2 = G2.data_ptr(), G2.stride(0)
+    a.g_p0, a.g_p1, a.g_p2 = _p(g_p[0]), _p(g_p[1]), _p(g_p[2])
+    a.A, a.lda, a.a_mode = A.data_ptr(), A.stride(0), a_mode
+    a.a_p0, a.a_p1 = _p(a_p[0]), _p(a_p[1])
+    if row_stats is not None:
+        a.row_mean, a.row_rstd = row_stats[0].data_ptr(), row_stats[1].data_ptr()
+    a.rows_per_sample = rows_per_sample
+    a.dW, a.lddw = dW.data_ptr(), dW.stride(0)
+    a.dbias = _p(dbias)
+    L.check(lib.cvb_pw_wgrad(ctypes.byref(a), _stream()), "cvb_pw_wgrad")
+    _count()
+    return dW
+
+
+# ---------------------------------------------------------------------------------------------------------- depthwise
+def dw_fwd(X: Tensor, B: int, H: int, W: int, C: int, stride: int, Wt: Tensor, *, x_mode: int = A_RAW,
+           x_p: Sequence[Optional[Tensor]] = (None, None), col_stats: Optional[Tensor] = None) -> Tensor:
+    lib = _lib()
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    Y = torch.empty((B * Ho * Wo, C), device=X.device, dtype=torch.bfloat16)
+    a = L.DwFwdArgs()
+    a.B, a.H, a.W, a.C, a.stride = B, H, W, C, stride
+    a.X, a.x_mode, a.x_p0, a.x_p1 = X.data_ptr(), x_mode, _p(x_p[0]), _p(x_p[1])
+    a.Wt, a.Y = Wt.data_ptr(), Y.data_ptr()
+    if col_stats is not None:
+        a.col_sum, a.col_sq = col_stats[0].data_ptr(), col_stats[1].data_ptr()
+    L.check(lib.cvb_dw_fwd(ctypes.byref(a), _stream()), "cvb_dw_fwd")
+    _count()
+    return Y
+
+
+def dw_bwd(DZ: Tensor, X: Tensor, B: int, H: int, W: int, C: int, stride: int, Wt: Tensor, *, g_mode: int = A_RAW,
+           Y2: Optional[Tensor] = None, g_p: Sequence[Optional[Tensor]] = (None, None, None), x_mode: int = A_RAW,
+           x_p: Sequence[Optional[Tensor]] = (None, None), col_stats: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Returns (DX bf16 [B*H*W, C], dWt fp32 [9, C])."""
+    lib = _lib()
+    DX = torch.empty((B * H * W, C), device=X.device, dtype=torch.bfloat16)
+    dWt = torch.zeros((9, C), device=X.device, dtype=torch.float32)
+    a = L.DwBwdArgs()
+    a.B, a.H, a.W, a.C, a.stride = B, H, W, C, stride
+    a.DZ, a.Y2, a.g_mode = DZ.data_ptr(), _p(Y2), g_mode
+    a.g_p0, a.g_p1, a.g_p2 = _p(g_p[0]), _p(g_p[1]), _p(g_p[2])
+    a.X, a.x_mode, a.x_p0, a.x_p1 = X.data_ptr(), x_mode, _p(x_p[0]), _p(x_p[1])
+    a.Wt, a.DX, a.dWt = Wt.data_ptr(), DX.data_ptr(), dWt.data_ptr()
+    if col_stats is not None:
+        a.col_sum, a.col_sq = col_stats[0].data_ptr(), col_stats[1].data_ptr()
+    L.check(lib.cvb_dw_bwd(ctypes.byref(a), _stream()), "cvb_dw_bwd")
+    _count()
+    return DX, dWt
+
+
+def stem_im2col(x: Tensor) -> Tensor:
+    """fp32 image [B,3,H,W] (any strides) -> bf16 patch matrix [B*(H/2)*(W/2), 32]."""
+    lib = _lib()
+    B, C, H, W = x.shape
+    assert C == 3 and x.dtype == torch.float32
+    A = torch.empty((B * (H // 2) * (W // 2), 32), device=x.device, dtype=torch.bfloat16)
+    sn, sc, sh, sw = x.stride()
+    L.check(lib.cvb_stem_im2col(x.data_ptr(), sn, sc, sh, sw, B, H, W, A.data_ptr(), _stream()), "cvb_stem_im2col")
+    _count()
+    return A
+
+
+# ------------------------------------------------------------------------------------------------------------- BN / GN
+def bn_finalize(stats: Tensor, count: float, gamma: Tensor, beta: Tensor, eps: float, momentum: float,
+                running_mean: Optional[Tensor], running_var: Optional[Tensor], nbt: Optional[Tensor]) -> Tensor:
+    """stats: fp64 [2, C].  Returns fp32 [4, C] = (mean, rstd, scale, shift); updates the running buffers in place."""
+    lib = _lib()
+    C = stats.shape[1]
+    out = torch.empty((4, C), device=stats.device, dtype=torch.float32)
+    L.check(lib.cvb_bn_finalize(stats[0].data_ptr(), stats[1].data_ptr(), float(count), _p(gamma), _p(beta), eps, momentum,
+                                _p(running_mean), _p(running_var), _p(nbt), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                out[3].data_ptr(), C, _stream()), "cvb_bn_finalize")
+    _count()
+    return out
+
+
+def bn_eval_scale_shift(gamma: Tensor, beta: Tensor, running_mean: Tensor, running_var: Tensor, eps: float) -> Tensor:
+    lib = _lib()
+    C = running_mean.shape[0]
+    out = torch.empty((4, C), device=running_mean.device, dtype=torch.float32)
+    L.check(lib.cvb_bn_eval_scale_shift(_p(gamma), _p(beta), running_mean.data_ptr(), running_var.data_ptr(), eps, out[0].data_ptr(),
+                                        out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), C, _stream()), "cvb_bn_eval_scale_shift")
+    _count()
+    return out
+
+
+def bn_bwd_finalize(stats: Tensor, count: float, gamma: Tensor, bn: Tensor, eval_mode: bool = False) -> Tuple[Tensor, Tensor]:
+    """stats: fp64 [2, C] (sum dz, sum dz*y); bn: the [4, C] forward record.  Returns (dgb fp32 [2,C] = dgamma,dbeta; coef fp32 [3,C])."""
+    lib = _lib()
+    C = stats.shape[1]
+    dgb = torch.empty((2, C), device=stats.device, dtype=torch.float32)
+    coef = torch.empty((3, C), device=stats.device, dtype=torch.float32)
+    L.check(lib.cvb_bn_bwd_finalize(stats[0].data_ptr(), stats[1].data_ptr(), float(count), _p(gamma), bn[0].data_ptr(), bn[1].data_ptr(),
+                                    int(eval_mode), dgb[0].data_ptr(), dgb[1].data_ptr(), coef[0].data_ptr(), coef[1].data_ptr(),
+                                    coef[2].data_ptr(), C, _stream()), "cvb_bn_bwd_finalize")
+    _count()
+    return dgb, coef
+
+
+def bn_apply(Y: Tensor, bn: Tensor, act: bool, R: Optional[Tensor] = None) -> Tensor:
+    lib = _lib()
+    M, C = Y.shape
+    out = torch.empty_like(Y)
+    L.check(lib.cvb_bn_apply(Y.data_ptr(), bn[2].data_ptr(), bn[3].data_ptr(), int(act), _p(R), out.data_ptr(), M, C, _stream()), "cvb_bn_apply")
+    _count()
+    return out
+
+
+def bn_bwd_reduce(DOUT: Tensor, Y: Tensor, stats: Tensor, bn: Optional[Tensor] = None, act: bool = False, store_dz: bool = False):
+    lib = _lib()
+    M, C = Y.shape
+    DZ = torch.empty_like(Y) if store_dz else None
+    L.check(lib.cvb_bn_bwd_reduce(DOUT.data_ptr(), Y.data_ptr(), _p(bn[2]) if act else None, _p(bn[3]) if act else None, int(act), _p(DZ),
+                                  stats[0].data_ptr(), stats[1].data_ptr(), M, C, _stream()), "cvb_bn_bwd_reduce")
+    _count()
+    return DZ
+
+
+def gn_finalize(stats: Tensor, count: float, eps: float) -> Tensor:
+    """stats fp64 [2, B] -> fp32 [2, B] (mean, rstd)."""
+    lib = _lib()
+    B = stats.shape[1]
+    out = torch.empty((2, B), device=stats.device, dtype=torch.float32)
+    L.check(lib.cvb_gn_finalize(stats[0].data_ptr(), stats[1].data_ptr(), float(count), eps, out[0].data_ptr(), out[1].data_ptr(), B, _stream()),
+            "cvb_gn_finalize")
+    _count()
+    return out
+
+
+def gn_stats(X: Tensor, B: int, rows_per_sample: int, stats: Tensor):
+    lib = _lib()
+    L.check(lib.cvb_gn_stats(X.data_ptr(), X.stride(0), B, rows_per_sample, X.shape[1], stats[0].data_ptr(), stats[1].data_ptr(), _stream()),
+            "cvb_gn_stats")
+    _count()
+
+
+def gn_bwd_apply(G: Tensor, X: Tensor, gn: Tensor, sstats: Tensor, count: float, B: int, rows_per_sample: int,
+                 DRES: Optional[Tensor] = None, col_sum: Optional[Tensor] = None) -> Tensor:
+    lib = _lib()
+    DX = torch.empty_like(G)
+    L.check(lib.cvb_gn_bwd_apply(G.data_ptr(), X.data_ptr(), gn[0].data_ptr(), gn[1].data_ptr(), sstats[0].data_ptr(), sstats[1].data_ptr(),
+                                 float(count), _p(DRES), DX.data_ptr(), B, rows_per_sample, G.shape[1], _p(col_sum), _stream()), "cvb_gn_bwd_apply")
+    _count()
+    return DX
+
+
+# ---------------------------------------------------------------------------------------------------------- attention
+def linattn_fwd(QKV: Tensor, B: int, H: int, W: int, d: int):
+    lib = _lib()
+    M = QKV.shape[0]
+    N = (H // 2) * (W // 2)
+    O = torch.empty((M, d), device=QKV.device, dtype=torch.bfloat16)
+    S = torch.empty((B, 4, N), device=QKV.device, dtype=torch.float32)
+    CTX = torch.empty((B, 4, d), device=QKV.device, dtype=torch.float32)
+    L.check(lib.cvb_linattn_fwd(QKV.data_ptr(), QKV.stride(0), B, H, W, d, 2, O.data_ptr(), O.stride(0), S.data_ptr(), CTX.data_ptr(), _stream()),
+            "cvb_linattn_fwd")
+    _count()
+    return O, S, CTX
+
+
+def linattn_bwd(QKV: Tensor, DO: Tensor, S: Tensor, CTX: Tensor, B: int, H: int, W: int, d: int, dbias: Optional[Tensor] = None) -> Tensor:
+    lib = _lib()
+    DQKV = torch.empty_like(QKV)
+    L.check(lib.cvb_linattn_bwd(QKV.data_ptr(), QKV.stride(0), DO.data_ptr(), DO.stride(0), S.data_ptr(), CTX.data_ptr(), B, H, W, d, 2,
+                                DQKV.data_ptr(), _p(dbias), _stream()), "cvb_linattn_bwd")
+    _count()
+    return DQKV
+
+
+# --------------------------------------------------------------------------------------------------------------- misc
+def global_pool_fwd(X: Tensor, B: int, HW: int) -> Tensor:
+    lib = _lib()
+    C = X.shape[1]
+    out = torch.empty((B, C), device=X.device, dtype=torch.bfloat16)
+    L.check(lib.cvb_global_pool_fwd(X.data_ptr(), B, HW, C, out.data_ptr(), _stream()), "cvb_global_pool_fwd")
+    _count()
+    return out
+
+
+def global_pool_bwd(DOUT: Tensor, B: int, HW: int) -> Tensor:
+    lib = _lib()
+    C = DOUT.shape[1]
+    DX = torch.empty((B * HW, C), device=DOUT.device, dtype=torch.bfloat16)
+    L.check(lib.cvb_global_pool_bwd(DOUT.data_ptr(), B, HW, C, DX.data_ptr(), _stream()), "cvb_global_pool_bwd")
+    _count()
+    return DX
+
+
+def col_sum(X: Tensor, N: Optional[int] = None, out: Optional[Tensor] = None) -> Tensor:
+    lib = _lib()
+    N = X.shape[1] if N is None else N
+    if out is None:
+        out = torch.zeros((N,), device=X.device, dtype=torch.float32)
+    L.check(lib.cvb_col_sum(X.data_ptr(), int(X.dtype == torch.float32), X.stride(0), X.shape[0], N, out.data_ptr(), _stream()), "cvb_col_sum")
+    _count()
+    return out
+
+
+def unprep_grad(src: Tensor, rows: int, cols: int, lds: int, kind: int, rot: int = 0) -> Tensor:
+    lib = _lib()
+    dst = torch.empty((rows, cols) if kind != 3 else (rows,), device=src.device, dtype=torch.float32)
+    L.check(lib.cvb_unprep_grad(src.data_ptr(), dst.data_ptr(), rows, cols, lds, kind, rot, _stream()), "cvb_unprep_grad")
+    _count()
+    return dst
+
+
+class PreparedWeights:
+    """Kernel-layout copies of a module's fp32 parameters, refreshed by ONE batched launch (cvb_prep_weights).
+
+    The parameters stay ordinary ``nn.Parameter``s owned by PyTorch (state_dict / optimizer / DDP / EMA see nothing
+    new); these buffers are a cache keyed on the parameters' ``_version`` and storage address.
+    """
+
+    KIND_ROWMAJOR, KIND_TRANSPOSED, KIND_TAPMAJOR_F32, KIND_VECTOR_F32 = 0, 1, 2, 3
+
+    def __init__(self):
+        self._entries = []  # (param, dst, rows, cols, ldd, dst_rows, kind, rot)
+        self._table = None
+        self._key = None
+        self._versions = None
+        self._max_elems = 1
+
+    def add(self, param: Tensor, kind: int, *, rot: int = 0, ldd: Optional[int] = None, dst_rows: Optional[int] = None) -> int:
+        p2 = param.reshape(param.shape[0], -1) if param.dim() > 1 else param.reshape(-1, 1)
+        rows, cols = p2.shape
+        self._entries.append([param, None, rows, cols, ldd, dst_rows, kind, rot])
+        self._table = None
+        return len(self._entries) - 1
+
+    def _alloc(self, device):
+        for e in self._entries:
+            param, _, rows, cols, ldd, dst_rows, kind, rot = e
+            if kind == self.KIND_ROWMAJOR:
+                ldd = ldd or (cols + 7) // 8 * 8
+                dst_rows = dst_rows or rows
+                dst = torch.empty((dst_rows, ldd), device=device, dtype=torch.bfloat16)
+            elif kind == self.KIND_TRANSPOSED:
+                ldd = ldd or (rows + 7) // 8 * 8
+                dst_rows = dst_rows or cols
+                dst = torch.empty((dst_rows, ldd), device=device, dtype=torch.bfloat16)
+            elif kind == self.KIND_TAPMAJOR_F32:
+                ldd, dst_rows = rows, cols
+                dst = torch.empty((cols, rows), device=device, dtype=torch.float32)
+            else:
+                dst_rows = dst_rows or rows
+                ldd = 1
+                dst = torch.empty((dst_rows,), device=device, dtype=torch.float32)
+            e[1], e[4], e[5] = dst, ldd, dst_rows
+            self._max_elems = max(self._max_elems, dst.numel())
+
+    def get(self, idx: int) -> Tensor:
+        return self._entries[idx][1]
+
+    def prepare(self, force: bool = True):
+        """Refresh all kernel-layout copies.  ``force=False`` skips the launch when no parameter changed."""
+        if not self._entries:
+            return
+        device = self._entries[0][0].device
+        key = tuple(e[0].data_ptr() for e in self._entries) + (device,)
+        versions = tuple(e[0]._version for e in self._entries)
+        if self._table is None or key != self._key:
+            if self._entries[0][1] is None or self._entries[0][1].device != device:
+                self._alloc(device)
+            descs = (L.PrepDesc * len(self._entries))()
+            for i, (param, dst, rows, cols, ldd, dst_rows, kind, rot) in enumerate(self._entries):
+                assert param.dtype == torch.float32 and param.is_contiguous(), "parameters must be contiguous fp32"
+                descs[i] = L.PrepDesc(param.data_ptr(), dst.data_ptr(), rows, cols, ldd, dst_rows, kind, rot)
+            raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+            self._table = raw.to(device)
+            self._key = key
+            self._versions = None
+        if not force and versions == self._versions:
+            return
+        L.check(_lib().cvb_prep_weights(self._table.data_ptr(), len(self._entries), int(self._max_elems), _stream()), "cvb_prep_weights")
+        _count()
+        self._versions = versions

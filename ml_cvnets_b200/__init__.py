@@ -1,0 +1,7 @@
+"""Import alias: the product package lives in ``ml-cvnets_b200/`` (a directory name Python cannot import)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "ml-cvnets_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

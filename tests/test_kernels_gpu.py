@@ -1,0 +1,382 @@
+"""Kernel-level parity (-m gpu): every C-ABI entry point against a plain PyTorch fp32 restatement of the same op on the
+same (bf16-rounded) inputs.  Tolerances are bf16 output rounding (2^-8 relative) plus fp32 accumulation-order noise."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from ml_cvnets_b200 import ops as o
+    return o
+
+
+def rnd(*shape, scale=1.0, seed=None):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed if seed is not None else (hash(shape) % 100000))
+    return torch.randn(*shape, device="cuda", generator=g) * scale
+
+
+def bf(x):
+    return x.to(BF)
+
+
+def silu(z):
+    return z * torch.sigmoid(z)
+
+
+def dsilu(z):
+    s = torch.sigmoid(z)
+    return s * (1 + z * (1 - s))
+
+
+def load_ref(mode, x, p=(None, None, None), x2=None, row=None, rps=0):
+    """fp32 restatement of the operand load modes, including the bf16 rounding of the transformed operand."""
+    from ml_cvnets_b200.ops import A_AFF, A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU
+    x = x.float()
+    if mode == A_RAW:
+        return x
+    if mode == A_AFF:
+        y = x * p[0] + p[1]
+    elif mode == A_AFF_SILU:
+        y = silu(x * p[0] + p[1])
+    elif mode == A_SILU:
+        y = silu(x)
+    elif mode == A_GN:
+        mu = row[0].repeat_interleave(rps)[: x.shape[0], None]
+        rs = row[1].repeat_interleave(rps)[: x.shape[0], None]
+        y = (x - mu) * rs * p[0] + p[1]
+    elif mode == A_BNB:
+        y = p[0] * x + p[1] * x2.float() + p[2]
+    return y.to(BF).float()
+
+
+def close(a, b, rtol=1.5e-2, atol=None, what=""):
+    a, b = a.float(), b.float()
+    if atol is None:
+        atol = 1e-2 * float(b.abs().max()) + 1e-6
+    err = (a - b).abs()
+    bad = err > atol + rtol * b.abs()
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} mismatches, max abs err {float(err.max()):.4g}, ref max {float(b.abs().max()):.4g}"
+
+
+def close_stat(a, b, what="", rtol=2e-3):
+    a, b = a.double(), b.double()
+    scale = float(b.abs().max()) + 1e-12
+    err = float((a - b).abs().max())
+    assert err <= rtol * scale + 1e-6, f"{what}: max err {err:.4g} vs scale {scale:.4g}"
+
+
+# ------------------------------------------------------------------------------------------------------------- GEMM fwd
+@pytest.mark.parametrize("M,N,K", [(256, 64, 32), (300, 32, 64), (1000, 128, 128), (513, 264, 40), (130, 72, 264), (2048, 384, 192)])
+@pytest.mark.parametrize("a_mode", [0, 1, 2, 3, 4, 5])
+def test_pw_gemm_modes(ops, M, N, K, a_mode):
+    rps = 50
+    nb = (M + rps - 1) // rps
+    A, A2 = bf(rnd(M, K, seed=1)), bf(rnd(M, K, seed=2))
+    W = bf(rnd(N, K, scale=K ** -0.5, seed=3))
+    bias = rnd(N, seed=4)
+    p = (1 + 0.2 * rnd(K, seed=5), 0.3 * rnd(K, seed=6), 0.1 * rnd(K, seed=7))
+    row = (0.2 * rnd(nb, seed=8), 1 + 0.3 * rnd(nb, seed=9).abs())
+    R = bf(rnd(M, N, seed=10))
+    col = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    samp = torch.zeros(2, nb, device="cuda", dtype=torch.float64)
+    out = ops.pw_gemm(A, W, N, a_mode=a_mode, A2=A2 if a_mode == 5 else None, a_p=p, row_stats=row if a_mode == 4 else None,
+                      rows_per_sample=rps, bias=bias, R=R, col_stats=col, samp_stats=samp)
+    Ar = load_ref(a_mode, A, p, A2, row, rps)
+    ref = Ar @ W.float().t() + bias + R.float()
+    close(out, ref, what="out")
+    o = out.float()
+    close_stat(col[0], o.sum(0), "col_sum")
+    close_stat(col[1], (o * o).sum(0), "col_sq")
+    sid = torch.arange(M, device="cuda") // rps
+    ss = torch.zeros(nb, device="cuda").index_add_(0, sid, o.sum(1))
+    sq = torch.zeros(nb, device="cuda").index_add_(0, sid, (o * o).sum(1))
+    close_stat(samp[0], ss, "samp_sum")
+    close_stat(samp[1], sq, "samp_sq")
+
+
+def test_pw_gemm_silu_and_fp32_out(ops):
+    M, N, K = 384, 96, 64
+    A, W, bias = bf(rnd(M, K)), bf(rnd(N, K, scale=0.1)), rnd(N)
+    out = ops.pw_gemm(A, W, N, bias=bias, e_mode=ops.E_SILU)
+    close(out, silu(A.float() @ W.float().t() + bias), what="silu epilogue")
+    out32 = ops.pw_gemm(A, W, N, bias=bias, out_fp32=True)
+    assert out32.dtype == torch.float32
+    close(out32, A.float() @ W.float().t() + bias, rtol=1e-4, atol=1e-4, what="fp32 out")
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 64, 128), (700, 136, 72)])
+def test_pw_gemm_silu_bwd(ops, M, N, K):
+    A, W = bf(rnd(M, K, seed=11)), bf(rnd(N, K, scale=K ** -0.5, seed=12))
+    Y = bf(rnd(M, N, seed=13))
+    sc, sh = 1 + 0.2 * rnd(N, seed=14), 0.3 * rnd(N, seed=15)
+    col = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    out = ops.pw_gemm(A, W, N, e_mode=ops.E_SILU_BWD, Y=Y, e_p=(sc, sh), col_stats=col)
+    ref = (A.float() @ W.float().t()) * dsilu(sc * Y.float() + sh)
+    close(out, ref, what="silu_bwd")
+    o = out.float()
+    close_stat(col[0], o.sum(0), "sum dz")
+    close_stat(col[1], (o * Y.float()).sum(0), "sum dz*y")
+    # identity scale/shift when e_p is omitted
+    out2 = ops.pw_gemm(A, W, N, e_mode=ops.E_SILU_BWD, Y=Y)
+    close(out2, (A.float() @ W.float().t()) * dsilu(Y.float()), what="silu_bwd identity")
+
+
+@pytest.mark.parametrize("M,N,K,rps", [(512, 64, 136, 64), (768, 128, 256, 256), (160, 16, 40, 16)])
+def test_pw_gemm_gn_bwd(ops, M, N, K, rps):
+    nb = M // rps
+    A, W = bf(rnd(M, K, seed=21)), bf(rnd(N, K, scale=K ** -0.5, seed=22))
+    X = bf(rnd(M, N, seed=23))
+    gamma = 1 + 0.2 * rnd(N, seed=24)
+    row = (0.2 * rnd(nb, seed=25), 1 + 0.3 * rnd(nb, seed=26).abs())
+    col = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    samp = torch.zeros(2, nb, device="cuda", dtype=torch.float64)
+    out = ops.pw_gemm(A, W, N, e_mode=ops.E_GN_BWD, Y=X, e_p=(gamma, None), row_stats=row, rows_per_sample=rps, col_stats=col, samp_stats=samp)
+    v = A.float() @ W.float().t()
+    xh = (X.float() - row[0].repeat_interleave(rps)[:, None]) * row[1].repeat_interleave(rps)[:, None]
+    close(out, v * gamma, what="g")
+    close_stat(col[0], v.sum(0), "dbeta", rtol=5e-3)
+    close_stat(col[1], (v * xh).sum(0), "dgamma", rtol=5e-3)
+    o = out.float()
+    close_stat(samp[0], o.view(nb, -1).sum(1), "sum g", rtol=5e-3)
+    close_stat(samp[1], (o * xh).view(nb, -1).sum(1), "sum g*xh", rtol=5e-3)
+
+
+# ----------------------------------------------------------------------------------------------------------- GEMM wgrad
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 32), (4096, 128, 64), (777, 264, 40), (300, 72, 200)])
+@pytest.mark.parametrize("g_mode,a_mode", [(0, 0), (5, 0), (5, 2), (0, 3), (0, 4), (5, 4), (0, 1)])
+def test_pw_wgrad(ops, M, N, K, g_mode, a_mode):
+    rps = 100
+    nb = (M + rps - 1) // rps
+    G, G2, A = bf(rnd(M, N, seed=31)), bf(rnd(M, N, seed=32)), bf(rnd(M, K, seed=33))
+    gp = (1 + 0.2 * rnd(N, seed=34), 0.3 * rnd(N, seed=35), 0.1 * rnd(N, seed=36))
+    ap = (1 + 0.2 * rnd(K, seed=37), 0.3 * rnd(K, seed=38))
+    row = (0.2 * rnd(nb, seed=39), 1 + 0.3 * rnd(nb, seed=40).abs())
+    db = torch.zeros(N, device="cuda")
+    dW = ops.pw_wgrad(G, A, N, K, g_mode=g_mode, G2=G2 if g_mode == 5 else None, g_p=gp, a_mode=a_mode, a_p=ap,
+                      row_stats=row if a_mode == 4 else None, rows_per_sample=rps, dbias=db)
+    Gr = load_ref(g_mode, G, gp, G2)
+    Ar = load_ref(a_mode, A, ap + (None,), None, row, rps)
+    ref = Gr.t() @ Ar
+    close(dW, ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()) + 1e-5, what="dW")
+    close(db, Gr.sum(0), rtol=2e-3, atol=2e-3 * float(Gr.sum(0).abs().max()) + 1e-4, what="dbias")
+
+
+# ------------------------------------------------------------------------------------------------------------ depthwise
+def _dw_ref(x_nhwc, B, H, W, C, stride, w, mode, p):
+    xa = load_ref(mode, x_nhwc, p + (None,)).view(B, H, W, C).permute(0, 3, 1, 2)
+    return torch.nn.functional.conv2d(xa, w, None, stride=stride, padding=1, groups=C), xa
+
+
+@pytest.mark.parametrize("B,H,W,C,stride", [(2, 16, 16, 64, 1), (3, 20, 12, 32, 1), (2, 32, 32, 128, 2), (2, 8, 8, 72, 2), (1, 4, 4, 8, 1), (2, 36, 36, 64, 2)])
+@pytest.mark.parametrize("x_mode", [0, 1, 2])
+def test_dw_fwd(ops, B, H, W, C, stride, x_mode):
+    X = bf(rnd(B * H * W, C, seed=41))
+    w = bf(rnd(C, 1, 3, 3, scale=0.3, seed=42)).float()
+    p = (1 + 0.2 * rnd(C, seed=43), 0.3 * rnd(C, seed=44))
+    Wt = w.view(C, 9).t().contiguous()
+    col = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    Y = ops.dw_fwd(X, B, H, W, C, stride, Wt, x_mode=x_mode, x_p=p, col_stats=col)
+    ref, _ = _dw_ref(X, B, H, W, C, stride, w, x_mode, p)
+    ref2 = ref.permute(0, 2, 3, 1).reshape(-1, C)
+    close(Y, ref2, what="dw fwd")
+    o = Y.float()
+    close_stat(col[0], o.sum(0), "col_sum")
+    close_stat(col[1], (o * o).sum(0), "col_sq")
+
+
+@pytest.mark.parametrize("B,H,W,C,stride", [(2, 16, 16, 64, 1), (3, 20, 12, 32, 1), (2, 32, 32, 128, 2), (2, 8, 8, 72, 2), (5, 4, 4, 8, 1), (2, 36, 36, 64, 2)])
+@pytest.mark.parametrize("g_mode,x_mode", [(0, 0), (5, 2), (5, 0), (0, 2), (5, 1)])
+def test_dw_bwd(ops, B, H, W, C, stride, g_mode, x_mode):
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    X = bf(rnd(B * H * W, C, seed=51))
+    DZ, Y2 = bf(rnd(B * Ho * Wo, C, seed=52)), bf(rnd(B * Ho * Wo, C, seed=53))
+    w = bf(rnd(C, 1, 3, 3, scale=0.3, seed=54)).float()
+    gp = (1 + 0.2 * rnd(C, seed=55), 0.3 * rnd(C, seed=56), 0.1 * rnd(C, seed=57))
+    xp = (1 + 0.2 * rnd(C, seed=58), 0.3 * rnd(C, seed=59))
+    Wt = w.view(C, 9).t().contiguous()
+    col = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    DX, dWt = ops.dw_bwd(DZ, X, B, H, W, C, stride, Wt, g_mode=g_mode, Y2=Y2 if g_mode == 5 else None, g_p=gp, x_mode=x_mode, x_p=xp,
+                         col_stats=col if x_mode != 0 else None)
+    dy = load_ref(g_mode, DZ, gp, Y2).view(B, Ho, Wo, C).permute(0, 3, 1, 2)
+    xa = load_ref(x_mode, X, xp + (None,)).view(B, H, W, C).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wv = w.clone().requires_grad_(True)
+    y = torch.nn.functional.conv2d(xa, wv, None, stride=stride, padding=1, groups=C)
+    y.backward(dy)
+    da = xa.grad.permute(0, 2, 3, 1).reshape(-1, C)
+    if x_mode == 2:
+        da = da * dsilu(xp[0] * X.float() + xp[1])
+    close(DX, da, what="dX")
+    close(dWt, wv.grad.view(C, 9).t(), rtol=3e-3, atol=3e-3 * float(wv.grad.abs().max()) + 1e-5, what="dW")
+    if x_mode != 0:
+        o = DX.float()
+        close_stat(col[0], o.sum(0), "sum dz")
+        close_stat(col[1], (o * X.float()).sum(0), "sum dz*x")
+
+
+# ----------------------------------------------------------------------------------------------------------- BN / GN / misc
+def test_bn_finalize_and_bwd_finalize(ops):
+    C, M = 96, 5000
+    y = bf(rnd(M, C, seed=61) * 1.5 + 0.3).float()
+    stats = torch.stack([y.sum(0), (y * y).sum(0)]).double()
+    gamma, beta = 1 + 0.2 * rnd(C, seed=62), 0.1 * rnd(C, seed=63)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), device="cuda", dtype=torch.long)
+    bn = ops.bn_finalize(stats, M, gamma, beta, 1e-5, 0.1, rm, rv, nbt)
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    close(bn[0], mean, rtol=1e-4, atol=1e-5, what="mean")
+    close(bn[1], (var + 1e-5).rsqrt(), rtol=1e-4, atol=1e-5, what="rstd")
+    close(bn[2], gamma * (var + 1e-5).rsqrt(), rtol=1e-4, atol=1e-5, what="scale")
+    close(bn[3], beta - mean * gamma * (var + 1e-5).rsqrt(), rtol=1e-4, atol=1e-4, what="shift")
+    close(rm, 0.1 * mean, rtol=1e-4, atol=1e-5, what="running_mean")
+    close(rv, 0.9 + 0.1 * y.var(0, unbiased=True), rtol=1e-4, atol=1e-5, what="running_var")
+    assert int(nbt) == 1
+    # backward coefficients against autograd of batch_norm
+    yv = y.clone().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    out = torch.nn.functional.batch_norm(yv, None, None, g, b, True, 0.1, 1e-5)
+    dz = rnd(M, C, seed=64)
+    out.backward(dz)
+    sd = torch.stack([dz.sum(0), (dz * y).sum(0)]).double()
+    dgb, coef = ops.bn_bwd_finalize(sd, M, gamma, bn)
+    close(dgb[0], g.grad, rtol=2e-3, atol=2e-3 * float(g.grad.abs().max()), what="dgamma")
+    close(dgb[1], b.grad, rtol=2e-3, atol=2e-3 * float(b.grad.abs().max()), what="dbeta")
+    dy = coef[0] * dz + coef[1] * y + coef[2]
+    close(dy, yv.grad, rtol=2e-3, atol=2e-3 * float(yv.grad.abs().max()), what="dy")
+    ev = ops.bn_eval_scale_shift(gamma, beta, rm, rv, 1e-5)
+    close(ev[2], gamma * (rv + 1e-5).rsqrt(), rtol=1e-5, atol=1e-6, what="eval scale")
+
+
+@pytest.mark.parametrize("M,C", [(1000, 64), (333, 96), (4096, 768), (50, 8)])
+def test_bn_apply_and_bwd_reduce(ops, M, C):
+    Y, R, D = bf(rnd(M, C, seed=71)), bf(rnd(M, C, seed=72)), bf(rnd(M, C, seed=73))
+    bn = torch.stack([rnd(C), rnd(C).abs() + 0.5, 1 + 0.2 * rnd(C, seed=74), 0.3 * rnd(C, seed=75)])
+    close(ops.bn_apply(Y, bn, False, R), Y.float() * bn[2] + bn[3] + R.float(), what="bn_apply")
+    close(ops.bn_apply(Y, bn, True), silu(Y.float() * bn[2] + bn[3]), what="bn_apply silu")
+    st = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    assert ops.bn_bwd_reduce(D, Y, st) is None
+    close_stat(st[0], D.float().sum(0), "sum dz")
+    close_stat(st[1], (D.float() * Y.float()).sum(0), "sum dz*y")
+    st.zero_()
+    dz = ops.bn_bwd_reduce(D, Y, st, bn, act=True, store_dz=True)
+    ref = D.float() * dsilu(Y.float() * bn[2] + bn[3])
+    close(dz, ref, what="dz")
+    close_stat(st[0], dz.float().sum(0), "sum dz (act)")
+    close_stat(st[1], (dz.float() * Y.float()).sum(0), "sum dz*y (act)")
+
+
+@pytest.mark.parametrize("B,rps,C", [(4, 64, 128), (3, 100, 24), (8, 16, 256)])
+def test_gn_kernels(ops, B, rps, C):
+    M = B * rps
+    X, G, DR = bf(rnd(M, C, seed=81) + 0.5), bf(rnd(M, C, seed=82)), bf(rnd(M, C, seed=83))
+    st = torch.zeros(2, B, device="cuda", dtype=torch.float64)
+    ops.gn_stats(X, B, rps, st)
+    xf = X.float().view(B, -1)
+    close_stat(st[0], xf.sum(1), "gn sum")
+    close_stat(st[1], (xf * xf).sum(1), "gn sq")
+    gn = ops.gn_finalize(st, rps * C, 1e-5)
+    close(gn[0], xf.mean(1), rtol=1e-4, atol=1e-5, what="gn mean")
+    close(gn[1], (xf.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-4, atol=1e-5, what="gn rstd")
+    # backward phase 2 against autograd of group_norm (gamma folded into g by the caller)
+    xv = X.float().view(B, rps, C).permute(0, 2, 1).contiguous().requires_grad_(True)  # [B, C, rps]
+    out = torch.nn.functional.group_norm(xv, 1, None, None, 1e-5)
+    gg = G.float().view(B, rps, C).permute(0, 2, 1)
+    out.backward(gg)
+    xh = ((X.float().view(B, -1) - gn[0][:, None]) * gn[1][:, None]).view(M, C)
+    ss = torch.stack([G.float().view(B, -1).sum(1), (G.float() * xh).view(B, -1).sum(1)]).double()
+    cs = torch.zeros(C, device="cuda", dtype=torch.float64)
+    DX = ops.gn_bwd_apply(G, X, gn, ss, rps * C, B, rps, DRES=DR, col_sum=cs)
+    ref = xv.grad.permute(0, 2, 1).reshape(M, C) + DR.float()
+    close(DX, ref, what="gn dx")
+    close_stat(cs, DX.float().sum(0), "col sum of dx")
+
+
+@pytest.mark.parametrize("B,H,W,d", [(2, 8, 8, 16), (3, 16, 16, 128), (2, 8, 8, 192), (2, 4, 4, 256), (1, 32, 32, 128)])
+def test_linattn(ops, B, H, W, d):
+    ldq = 2 * d + 8
+    M = B * H * W
+    QKV = bf(rnd(M, ldq, seed=91))
+    DO = bf(rnd(M, d, seed=92))
+    O, S, CTX = ops.linattn_fwd(QKV, B, H, W, d)
+    # reference through the ORIGINAL formulation: unfold -> [B, c, 4, N]
+    q4 = QKV.float().view(B, H, W, ldq).permute(0, 3, 1, 2)
+
+    def unfold(t):
+        Bc, C = t.shape[:2]
+        return torch.nn.functional.unfold(t, kernel_size=2, stride=2).reshape(Bc, C, 4, -1)
+
+    def fold(p):
+        Bc, C, P, N = p.shape
+        return torch.nn.functional.fold(p.reshape(Bc, C * P, N), output_size=(H, W), kernel_size=2, stride=2)
+
+    k = unfold(q4[:, :d]).requires_grad_(True)
+    v = unfold(q4[:, d:2 * d]).requires_grad_(True)
+    q = unfold(q4[:, 2 * d:2 * d + 1]).requires_grad_(True)
+    s = torch.softmax(q, dim=-1)
+    ctx = (k * s).sum(-1, keepdim=True)
+    out = torch.relu(v) * ctx
+    ref_O = fold(out).permute(0, 2, 3, 1).reshape(M, d)
+    close(O, ref_O, what="O")
+    close(CTX, ctx.squeeze(-1).permute(0, 2, 1), rtol=2e-3, atol=1e-4, what="ctx")
+    close(S, s.squeeze(1), rtol=2e-3, atol=1e-5, what="scores")
+    dOu = unfold(DO.float().view(B, H, W, d).permute(0, 3, 1, 2))
+    out.backward(dOu)
+    db = torch.zeros(ldq, device="cuda")
+    DQKV = ops.linattn_bwd(QKV, DO, S, CTX, B, H, W, d, dbias=db)
+    ref = torch.zeros(M, ldq, device="cuda")
+    ref[:, :d] = fold(k.grad).permute(0, 2, 3, 1).reshape(M, d)
+    ref[:, d:2 * d] = fold(v.grad).permute(0, 2, 3, 1).reshape(M, d)
+    ref[:, 2 * d] = fold(q.grad).permute(0, 2, 3, 1).reshape(M)
+    close(DQKV[:, :2 * d], ref[:, :2 * d], what="dK,dV")
+    close(DQKV[:, 2 * d], ref[:, 2 * d], rtol=3e-2, atol=2e-2 * float(ref[:, 2 * d].abs().max()) + 1e-6, what="dq")
+    assert float(DQKV[:, 2 * d + 1:].float().abs().max()) == 0.0
+    close(db[:2 * d], DQKV[:, :2 * d].float().sum(0), rtol=2e-3, atol=2e-3 * float(db.abs().max()) + 1e-5, what="dbias")
+
+
+def test_pool_colsum_im2col_prep(ops):
+    B, HW, C = 5, 64, 96
+    X = bf(rnd(B * HW, C, seed=101))
+    p = ops.global_pool_fwd(X, B, HW)
+    close(p, X.float().view(B, HW, C).mean(1), what="pool fwd")
+    dx = ops.global_pool_bwd(p, B, HW)
+    close(dx, (p.float() / HW)[:, None, :].expand(B, HW, C).reshape(-1, C), what="pool bwd")
+    close(ops.col_sum(X), X.float().sum(0), rtol=2e-3, atol=1e-2, what="col_sum bf16")
+    Xf = rnd(77, 1000, seed=102)
+    close(ops.col_sum(Xf), Xf.sum(0), rtol=1e-4, atol=1e-4, what="col_sum fp32")
+    # stem im2col, NCHW and channels_last images
+    img = rnd(2, 3, 16, 20, seed=103)
+    for im in (img, img.contiguous(memory_format=torch.channels_last)):
+        A = ops.stem_im2col(im)
+        ref = torch.nn.functional.unfold(im.to(BF).float(), kernel_size=3, stride=2, padding=1)  # [B, 27, L]
+        ref = ref.permute(0, 2, 1).reshape(-1, 27)
+        close(A[:, :27], ref, rtol=0, atol=0, what="im2col")
+        assert float(A[:, 27:].float().abs().max()) == 0.0
+    # weight preparation
+    d = 16
+    w = torch.nn.Parameter(rnd(2 * d + 1, d, 1, 1, seed=104))
+    bvec = torch.nn.Parameter(rnd(2 * d + 1, seed=105))
+    wd = torch.nn.Parameter(rnd(24, 1, 3, 3, seed=106))
+    P = ops.PreparedWeights()
+    i0 = P.add(w, P.KIND_ROWMAJOR, rot=1, dst_rows=2 * d + 8)
+    i1 = P.add(w, P.KIND_TRANSPOSED, rot=1, ldd=2 * d + 8)
+    i2 = P.add(bvec, P.KIND_VECTOR_F32, rot=1, dst_rows=2 * d + 8)
+    i3 = P.add(wd, P.KIND_TAPMAJOR_F32)
+    P.prepare()
+    w2 = w.detach().view(2 * d + 1, d)
+    perm = torch.cat([w2[1:], w2[:1]])
+    assert torch.equal(P.get(i0)[: 2 * d + 1], perm.to(BF)) and float(P.get(i0)[2 * d + 1:].float().abs().max()) == 0
+    assert torch.equal(P.get(i1)[:, : 2 * d + 1], perm.t().to(BF)) and float(P.get(i1)[:, 2 * d + 1:].float().abs().max()) == 0
+    assert torch.equal(P.get(i2)[: 2 * d + 1], torch.cat([bvec.detach()[1:], bvec.detach()[:1]]))
+    assert torch.equal(P.get(i3), wd.detach().view(24, 9).t().to(BF).float())
+    g = rnd(2 * d + 8, d, seed=107)
+    back = ops.unprep_grad(g, 2 * d + 1, d, d, 0, rot=1)
+    assert torch.equal(back[1:], g[: 2 * d]) and torch.equal(back[0], g[2 * d])
+    gt = rnd(9, 24, seed=108)
+    assert torch.equal(ops.unprep_grad(gt, 24, 9, 24, 2), gt.t())
