@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of a MobileViTv2-1.0 bf16 256x256 training step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = forward + cross-entropy(label_smoothing 0.1) + backward (+ DDP gradient all-reduce over NCCL at N > 1) +
+GradScaler unscale + clip_grad_norm_(10) + AdamW step, per-GPU batch 128 (config/classification/imagenet/mobilevit_v2.yaml
+:9,15 of the reference), synthetic ImageNet-shaped tensors, random-init weights.
+
+Prints ONE JSON line (rank 0).  ``value`` = whole-job images/s with inputs resident in HBM; ``e2e`` = same metric with the
+step's images+labels copied from pinned host memory and the loss read back inside the timed region; ``roofline`` =
+algorithmic bytes of the pointwise-conv GEMM kernel family (the dominant kernel) / their CUDA-event time vs measured HBM
+peak; ``cpu_baseline`` = the oracle (CPU restatement of the reference path) timed on a bounded sample on the host cores.
+``--impl reference`` times that CPU path alone (the reference is pure Python/PyTorch; its nn.Module path == the oracle).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "images/sec training step, MobileViTv2-1.0 bf16 256x256"
+RES, NCLS = 256, 1000
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md 'clocks line')."""
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU (reference) arm
+def cpu_training_throughput(batch, steps, warmup, threads=None):
+    """The reference's own nn.Module path restated by the oracle (fp32: the reference refuses AMP on CPU,
+    engine/utils.py:31-32), all host threads, AdamW(lr 2e-3, wd 0.05).  Returns (img/s, ms/step, cores)."""
+    from oracle import cvnets_oracle as O
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(1.0), 0))
+    params = [v for k, v in P.items() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=2e-3, weight_decay=0.05)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 3, RES, RES, generator=g)
+    y = torch.randint(0, NCLS, (batch,), generator=g)
+    for _ in range(warmup):
+        O.training_step(P, opt, x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.training_step(P, opt, x, y)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch / dt, dt * 1e3, cores
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    ips, ms, cores = cpu_training_throughput(batch, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32 (reference refuses AMP on CPU)", "data": "synthetic",
+        "config": {"workload": "MobileViTv2-1.0 training step, 256x256, CPU nn.Module path (oracle port of the Python reference)",
+                   "batch_sample": batch, "note": "bounded sample of the per-GPU batch of 128"},
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": f"batch {batch}, fwd+bwd+AdamW, fp32"},
+        "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------- our arm
+class GemmTimer:
+    """CUDA-event timing of every cvb_pw_gemm launch (the dominant kernel family) inside the timed region."""
+
+    def __init__(self, ops):
+        self.ops, self.records, self.enabled = ops, [], False
+        self._orig = ops.pw_gemm
+
+    def install(self):
+        ops, timer = self.ops, self
+
+        def timed_pw_gemm(A, W, N, **kw):
+            if not timer.enabled:
+                return timer._orig(A, W, N, **kw)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = timer._orig(A, W, N, **kw)
+            e.record()
+            M, K = A.shape[0], kw.get("K") or A.shape[1]
+            # algorithmic bytes: input activation read once + output written once, bf16
+            timer.records.append((s, e, 2.0 * M * (K + N), 2.0 * M * K * N))
+            return out
+
+        ops.pw_gemm = timed_pw_gemm
+        import ml_cvnets_b200.functional as Fn
+        Fn.ops.pw_gemm = timed_pw_gemm
+
+    def summary(self):
+        ms = sum(s.elapsed_time(e) for s, e, _, _ in self.records)
+        byts = sum(b for _, _, b, _ in self.records)
+        flops = sum(f for _, _, _, f in self.records)
+        return ms, byts, flops, len(self.records)
+
+
+def run_ours(args, rank, world, local_rank):
+    import ml_cvnets_b200 as m
+    from ml_cvnets_b200 import ops
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0 + rank)
+    B = args.batch
+    model = m.MobileViTv2(m.default_opts(width_multiplier=1.0)).to(dev).train()
+    train_model = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        train_model = DDP(model, device_ids=[local_rank], output_device=local_rank, broadcast_buffers=True, gradient_as_bucket_view=True)
+    groups, _ = model.get_trainable_parameters(weight_decay=0.05, no_decay_bn_filter_bias=True)
+    opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999), fused=True)
+    scaler = torch.amp.GradScaler("cuda", enabled=True)  # the reference enables it even for bf16 (main_train.py:114)
+    params = [p for p in model.parameters()]
+
+    def step(x, y):
+        logits = train_model(x)
+        loss = F.cross_entropy(logits.float(), y, label_smoothing=0.1)
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        scaler.step(opt)
+        scaler.update()
+        return loss
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_dev = torch.randn(B, 3, RES, RES, device=dev, generator=gen)
+    y_dev = torch.randint(0, NCLS, (B,), device=dev, generator=gen)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    timer = GemmTimer(ops)
+    if not args.no_kernel_timing:
+        timer.install()
+    sampler = ClockSampler(local_rank)
+    # ---------------- timed region 1: inputs resident in HBM
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    timer.enabled = not args.no_kernel_timing
+    launches0 = ops.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, y_dev)
+    ev1.record()
+    sync_all()
+    timer.enabled = False
+    launches = ops.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    final_loss = float(loss.detach())
+
+    # ---------------- timed region 2: end to end (pinned host -> device every step, loss read back every step)
+    nbuf = 2
+    hx = [torch.randn(B, 3, RES, RES).pin_memory() for _ in range(nbuf)]
+    hy = [torch.randint(0, NCLS, (B,)).pin_memory() for _ in range(nbuf)]
+    dx = [torch.empty_like(x_dev) for _ in range(nbuf)]
+    dy = [torch.empty_like(y_dev) for _ in range(nbuf)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(nbuf)]
+    consumed = [torch.cuda.Event() for _ in range(nbuf)]
+    hloss = torch.zeros(1).pin_memory()
+
+    def prefetch(i):
+        b = i % nbuf
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            dx[b].copy_(hx[b], non_blocking=True)
+            dy[b].copy_(hy[b], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    e2e_steps = args.steps
+    for b in range(nbuf):
+        consumed[b].record()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    prefetch(0)
+    for i in range(e2e_steps):
+        b = i % nbuf
+        if i + 1 < e2e_steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[b])
+        loss = step(dx[b], dy[b])
+        consumed[b].record()
+        hloss.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+        _ = float(hloss[0])
+    e1.record()
+    sync_all()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+    e2e_value = world * B / (e2e_ms * 1e-3)
+    h2d = world * (hx[0].numel() * 4 + hy[0].numel() * 8)
+    d2h = world * 4
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    roof = None
+    if timer.records:
+        gms, gbytes, gflops, n = timer.summary()
+        per_step_ms = gms / args.steps
+        ach = gbytes / (gms * 1e-3) / 1e9
+        roof = {"kernel": "pw_gemm_kernel (all 1x1-conv / linear forward + input-gradient GEMMs)", "bound": "hbm", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None, "launches_per_step": n // args.steps,
+                "kernel_ms_per_step": per_step_ms, "share_of_step": per_step_ms / ms_step,
+                "algorithmic_bytes_per_step": gbytes / args.steps, "tflops": gflops / (gms * 1e-3) / 1e12}
+    cpu = None
+    if not args.no_cpu_baseline:
+        ips, cms, cores = cpu_training_throughput(args.cpu_batch, 1, 1)
+        cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
+               "sample": f"oracle fp32 training step, batch {args.cpu_batch} (of 128), 1 warm-up + 1 timed step ({cms:.0f} ms)"}
+    # whole-step roofline: SURVEY.md 8d algorithmic bytes: 190.8 MB / image
+    step_frac = (value / world) * 190.8e6 / 1e9 / peak
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "MobileViTv2-1.0 bf16 training step, synthetic ImageNet 256x256 (BASELINE.json configs[1])",
+                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "optimizer": "AdamW(fused) + GradScaler + clip_grad_norm 10",
+                   "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush"},
+        "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                  "ms_per_step": e2e_ms},
+        "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "step_roofline": {"algorithmic_mb_per_image": 190.8, "frac_of_hbm_peak": step_frac, "peak_gbs": peak},
+        "loss": final_loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (recipe: 128)")
+    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

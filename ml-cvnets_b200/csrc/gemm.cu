@@ -22,11 +22,6 @@ __device__ __forceinline__ uint32_t swz64(int row, int ch) {  // 64-byte rows, 4
   return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int AMODE>
-__device__ __forceinline__ int nvec_of() {
-  return (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
-}
-
 template <int WM, int AMODE>
 __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p) {
   constexpr int WARPS_M = BM / WM;
@@ -44,7 +39,7 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
   uint8_t* sB = smem + (TWO_A ? 2 : 1) * STAGES * A_STAGE;
   float* sP = reinterpret_cast<float*>(sB + STAGES * B_STAGE);
   __shared__ float s_col[2][128];
-  __shared__ float s_samp[2][128];
+  __shared__ double s_samp[2][128];  // fp64: cross-thread order must not change the GroupNorm statistics
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp / WARPS_N) * WM;
@@ -54,7 +49,7 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
   const int KT = (p.K + BK - 1) / BK;
   const int Kpad = KT * BK;
 
-  if (tid < 128) { s_col[0][tid] = 0.f; s_col[1][tid] = 0.f; s_samp[0][tid] = 0.f; s_samp[1][tid] = 0.f; }
+  if (tid < 128) { s_col[0][tid] = 0.f; s_col[1][tid] = 0.f; s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
   // per-K prologue parameters -> smem (zero padded so that the K tail transforms to finite values)
   if (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN || AMODE == CVB_A_BNB) {
     for (int k = tid; k < Kpad; k += NTHREADS) {
@@ -296,8 +291,8 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
       }
       if (cg == 0 && m < p.M) {
         int bi = m / rps - first_sample;
-        atomicAdd(&s_samp[0][bi], ssum);
-        atomicAdd(&s_samp[1][bi], ssq);
+        atomicAdd(&s_samp[0][bi], (double)ssum);
+        atomicAdd(&s_samp[1][bi], (double)ssq);
       }
     }
   }
@@ -317,8 +312,8 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
     int mlast = min(m0 + BM, p.M) - 1;
     int nsamp = mlast / rps - first_sample + 1;
     if (tid < nsamp) {
-      atomicAdd(p.samp_sum + first_sample + tid, (double)s_samp[0][tid]);
-      atomicAdd(p.samp_sq + first_sample + tid, (double)s_samp[1][tid]);
+      atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
+      atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
     }
   }
 }

@@ -36,7 +36,7 @@ __device__ float block_reduce_max(float v, float* ws) {
   return t;
 }
 
-// dynamic smem: s[N] | ctx[d]
+// dynamic smem: s[N] | ctx[d] | partials[ngrp][d]
 __global__ void __launch_bounds__(NT) linattn_fwd_kernel(const bf16* __restrict__ QKV, int ldq, int H, int W, int d, bf16* __restrict__ O, int ldo,
                                                          float* __restrict__ S, float* __restrict__ CTX) {
   extern __shared__ float sm[];
@@ -84,12 +84,20 @@ __global__ void __launch_bounds__(NT) linattn_fwd_kernel(const bf16* __restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = fmaf(k[j], sv, acc[j]);
   }
+  // deterministic cross-group reduction (fixed order): partials -> smem [ngrp][d] -> ordered sum
+  float* s_part = s_ctx + d;
   if (grp < ngrp) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&s_ctx[cg * 8 + j], acc[j]);
+    for (int j = 0; j < 8; ++j) s_part[grp * d + cg * 8 + j] = acc[j];
   }
   __syncthreads();
-  for (int i = tid; i < d; i += blockDim.x) CTX[((int64_t)b * 4 + p) * d + i] = s_ctx[i];
+  for (int i = tid; i < d; i += blockDim.x) {
+    float t = 0.f;
+    for (int gq = 0; gq < ngrp; ++gq) t += s_part[gq * d + i];
+    s_ctx[i] = t;
+    CTX[((int64_t)b * 4 + p) * d + i] = t;
+  }
+  __syncthreads();
   float ctx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) ctx[j] = s_ctx[cg * 8 + j];
@@ -214,7 +222,7 @@ extern "C" int cvb_linattn_fwd(const void* QKV, int ldq, int B, int H, int W, in
   CVB_CHECK(QKV && O && S && CTX && ldo % 8 == 0 && ldo >= d, "cvb_linattn_fwd: bad arguments");
   const int N = (H / 2) * (W / 2);
   const int nthreads = NT;  // a multiple of 32; threads beyond (d/8)*(NT/(d/8)) idle in the channel-grouped loops
-  size_t smem = (size_t)(N + d) * sizeof(float);
+  size_t smem = (size_t)(N + d + (size_t)(NT / (d / 8)) * d) * sizeof(float);
   CVB_CHECK(smem <= 200 * 1024, "cvb_linattn_fwd: N=%d too large", N);
   static bool attr = false;
   if (!attr) { CVB_CUDA(cudaFuncSetAttribute(linattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict
       for (int j = 0; j < 8; ++j) g[j] += d[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { g[j] = bf16_round(g[j]); a0[j] += g[j]; }
+    for (int j = 0; j < 8; ++j) a0[j] += g[j];  // column sums (bias gradients) from the unrounded fp32 values
     stg16(DX + r * C + c, pack8(g));
   }
   if (col_sum) {

@@ -295,7 +295,7 @@ def test_gn_kernels(ops, B, rps, C):
     DX = ops.gn_bwd_apply(G, X, gn, ss, rps * C, B, rps, DRES=DR, col_sum=cs)
     ref = xv.grad.permute(0, 2, 1).reshape(M, C) + DR.float()
     close(DX, ref, what="gn dx")
-    close_stat(cs, DX.float().sum(0), "col sum of dx")
+    close_stat(cs, ref.sum(0), "col sum of dx", rtol=5e-3)
 
 
 @pytest.mark.parametrize("B,H,W,d", [(2, 8, 8, 16), (3, 16, 16, 128), (2, 8, 8, 192), (2, 4, 4, 256), (1, 32, 32, 128)])
