@@ -35,23 +35,31 @@ __global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int
   const int th_i = blockIdx.x / tiles_w, tw_i = blockIdx.x % tiles_w;
   const int oh0 = th_i * TH, ow0 = tw_i * TW;
   const int c0 = blockIdx.y * CB;
-  const int b = blockIdx.z;
   const int IH = (TH - 1) * s + 3, IW = (TW - 1) * s + 3;
   const int h_base = oh0 * s - 1, w_base = ow0 * s - 1;
-  const bf16* __restrict__ X = static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C;
 
   if (tid < CB) { s_cs[tid] = 0.f; s_cq[tid] = 0.f; }
+  const int cgi = tid & 7, pt = tid >> 3;
+  const int c = c0 + cgi * 8;
+  const bool c_ok = c < p.C;
+  float cs[8], cq[8];  // BatchNorm statistics, accumulated over the batch loop and flushed once per CTA
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+
+  for (int b = blockIdx.z; b < p.B; b += gridDim.z) {
+  const bf16* __restrict__ X = static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C;
+  __syncthreads();  // previous image's stencil reads are done before the tile is overwritten
 
   // phase 1: stage transformed input tile (+halo)
   {
     const int ch = lane & 7;
-    const int c = c0 + ch * 8;
-    const bool c_ok = c < p.C;
+    const int lc = c0 + ch * 8;
+    const bool lc_ok = lc < p.C;
     float p0[8], p1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      p0[j] = (XMODE != CVB_A_RAW && c_ok) ? p.x_p0[c + j] : 1.f;
-      p1[j] = (XMODE != CVB_A_RAW && c_ok) ? p.x_p1[c + j] : 0.f;
+      p0[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p0[lc + j] : 1.f;
+      p1[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p1[lc + j] : 0.f;
     }
     for (int ih = warp; ih < IH; ih += NT / 32) {
       const int h = h_base + ih;
@@ -59,9 +67,9 @@ __global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int
       for (int jw = lane >> 3; jw < IW; jw += 4) {
         const int w = w_base + jw;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (h_ok && c_ok && w >= 0 && w < p.W) {
+        if (h_ok && lc_ok && w >= 0 && w < p.W) {
           float f[8];
-          load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + c, p0, p1, f);
+          load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + lc, p0, p1, f);
           v = pack8(f);
         }
         *reinterpret_cast<uint4*>(smem + pix_off(ih * IW + jw, ch)) = v;
@@ -71,17 +79,11 @@ __global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int
   __syncthreads();
 
   // phase 2: stencil
-  const int cgi = tid & 7, pt = tid >> 3;
-  const int c = c0 + cgi * 8;
-  const bool c_ok = c < p.C;
   float wt[9][8];
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
     for (int j = 0; j < 8; ++j) wt[tp][j] = c_ok ? p.Wt[tp * p.C + c + j] : 0.f;
-  float cs[8], cq[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
   bf16* __restrict__ Y = static_cast<bf16*>(p.Y) + (size_t)b * Ho * Wo * p.C;
   for (int op = pt; op < TH * TW; op += NT / 8) {
     const int oh = op >> logTW, ow = op & (TW - 1);
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int
       stg16(Y + ((size_t)gh * Wo + gw) * p.C + c, pack8(acc));
     }
   }
+  }  // batch loop
   if (p.col_sum) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -344,7 +347,12 @@ extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   const int tiles_h = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
   const int IH = (TH - 1) * a.stride + 3, IW = (TW - 1) * a.stride + 3;
   size_t smem = (size_t)IH * IW * 128;
-  dim3 grid(tiles_h * tiles_w, (a.C + CB - 1) / CB, a.B);
+  const int cblocks = (a.C + CB - 1) / CB;
+  int per_img = tiles_h * tiles_w * cblocks;
+  int gz = (16 * cvb_num_sms() + per_img - 1) / per_img;  // batch loop inside the CTA bounds the statistics atomics
+  if (gz > a.B) gz = a.B;
+  if (gz < 1) gz = 1;
+  dim3 grid(tiles_h * tiles_w, cblocks, gz);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CVB_DW_FWD(MODE)                                                                                                  \
   {                                                                                                                      \

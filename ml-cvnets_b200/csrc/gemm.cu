@@ -37,17 +37,20 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
   uint8_t* sA = smem;
   uint8_t* sA2 = smem + STAGES * A_STAGE;
   uint8_t* sB = smem + (TWO_A ? 2 : 1) * STAGES * A_STAGE;
-  float* sP = reinterpret_cast<float*>(sB + STAGES * B_STAGE);
+  constexpr int PIPE_BYTES = (TWO_A ? 2 : 1) * STAGES * A_STAGE + STAGES * B_STAGE;
+  constexpr int STAGE_C_BYTES = BM * LDC_S * 4;
+  // prologue parameters live behind BOTH the pipeline ring and the epilogue staging tile (which overlays the ring)
+  float* sP = reinterpret_cast<float*>(smem + (PIPE_BYTES > STAGE_C_BYTES ? PIPE_BYTES : STAGE_C_BYTES));
   __shared__ float s_col[2][128];
   __shared__ double s_samp[2][128];  // fp64: cross-thread order must not change the GroupNorm statistics
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp / WARPS_N) * WM;
   const int wn0 = (warp % WARPS_N) * 32;
-  const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * BN;
   const int KT = (p.K + BK - 1) / BK;
   const int Kpad = KT * BK;
+  const int m_tiles = (p.M + BM - 1) / BM;
 
   if (tid < 128) { s_col[0][tid] = 0.f; s_col[1][tid] = 0.f; s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
   // per-K prologue parameters -> smem (zero padded so that the K tail transforms to finite values)
@@ -64,6 +67,25 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
   const bf16* __restrict__ A2 = static_cast<const bf16*>(p.A2);
   const bf16* __restrict__ Wg = static_cast<const bf16*>(p.W);
 
+  // epilogue thread mapping (fixed per thread across tiles): 8 consecutive columns of one row
+  constexpr int CGS = BN / 8;
+  constexpr int ROWS_PER_PASS = NTHREADS / CGS;
+  const int cg = tid % CGS, r0 = tid / CGS;
+  const int nc = n0 + cg * 8;
+  const bool col_ok = nc < p.N;
+  const int emode = p.e_mode;
+  const bool want_col = p.col_sum != nullptr;
+  const bool want_samp = p.samp_sum != nullptr;
+  const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
+  const bf16* __restrict__ Yg = static_cast<const bf16*>(p.Y);
+  const bf16* __restrict__ Rg = static_cast<const bf16*>(p.R);
+  float cs[8], cq[8];  // per-column statistics, accumulated over all tiles of this CTA
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+
+  // persistent over M tiles: column statistics are flushed ONCE per CTA (not once per tile)
+  for (int mt = blockIdx.y; mt < m_tiles; mt += gridDim.y) {
+  const int m0 = mt * BM;
   auto load_stage = [&](int kt, int stage) {
     const int k0 = kt * BK;
 #pragma unroll
@@ -203,12 +225,6 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
     }
   __syncthreads();
 
-  constexpr int CGS = BN / 8;
-  constexpr int ROWS_PER_PASS = NTHREADS / CGS;
-  const int cg = tid % CGS, r0 = tid / CGS;
-  const int nc = n0 + cg * 8;
-  const bool col_ok = nc < p.N;
-  const int emode = p.e_mode;
   float bias8[8], ep0[8], ep1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -216,15 +232,7 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
     ep0[j] = (col_ok && p.e_p0) ? p.e_p0[nc + j] : 1.f;
     ep1[j] = (col_ok && p.e_p1) ? p.e_p1[nc + j] : 0.f;
   }
-  float cs[8], cq[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-  const bool want_col = p.col_sum != nullptr;
-  const bool want_samp = p.samp_sum != nullptr;
-  const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
   const int first_sample = m0 / rps;
-  const bf16* __restrict__ Yg = static_cast<const bf16*>(p.Y);
-  const bf16* __restrict__ Rg = static_cast<const bf16*>(p.R);
 
   for (int r = r0; r < BM; r += ROWS_PER_PASS) {
     const int m = m0 + r;
@@ -296,24 +304,38 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
       }
     }
   }
-  if (want_col) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_col[0][cg * 8 + j], cs[j]);
-      atomicAdd(&s_col[1][cg * 8 + j], cq[j]);
-    }
-  }
-  __syncthreads();
-  if (want_col && tid < BN && n0 + tid < p.N) {
-    atomicAdd(p.col_sum + n0 + tid, (double)s_col[0][tid]);
-    atomicAdd(p.col_sq + n0 + tid, (double)s_col[1][tid]);
-  }
+  __syncthreads();  // all reads of the staged tile are done (next tile's cp.async overwrites it); s_samp complete
   if (want_samp && tid < 128) {
     int mlast = min(m0 + BM, p.M) - 1;
     int nsamp = mlast / rps - first_sample + 1;
     if (tid < nsamp) {
       atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
       atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
+      s_samp[0][tid] = 0.0;
+      s_samp[1][tid] = 0.0;
+    }
+  }
+  }  // tile loop
+
+  if (want_col) {
+    // reduce over the lanes that share a column group (lane stride CGS), then one smem atomic per warp and column
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = cs[j], q = cq[j];
+#pragma unroll
+      for (int o = CGS; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (lane < CGS) {
+        atomicAdd(&s_col[0][cg * 8 + j], a);
+        atomicAdd(&s_col[1][cg * 8 + j], q);
+      }
+    }
+    __syncthreads();
+    if (tid < BN && n0 + tid < p.N) {
+      atomicAdd(p.col_sum + n0 + tid, (double)s_col[0][tid]);
+      atomicAdd(p.col_sq + n0 + tid, (double)s_col[1][tid]);
     }
   }
 }
@@ -324,16 +346,20 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   constexpr int BN = (8 / WARPS_M) * 32;
   const int KT = (a.K + BK - 1) / BK;
   const int nvec = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
-  size_t pipe = (size_t)STAGES * (BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1) + BN * BK * 2) + (size_t)nvec * KT * BK * 4;
+  size_t pipe = (size_t)STAGES * (BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1) + BN * BK * 2);
   size_t stagec = (size_t)BM * (BN + 4) * 4;
-  size_t smem = pipe > stagec ? pipe : stagec;
+  size_t smem = (pipe > stagec ? pipe : stagec) + (size_t)nvec * KT * BK * 4;
   static bool attr_set = false;
   if (!attr_set) {
     CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   CVB_CHECK(smem <= 200 * 1024, "cvb_pw_gemm: K=%d too large for the prologue parameter cache", a.K);
-  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
+  const int n_tiles = (a.N + BN - 1) / BN, m_tiles = (a.M + BM - 1) / BM;
+  int gy = (2 * cvb_num_sms() + n_tiles - 1) / n_tiles;  // ~2 resident CTAs per SM, each looping over M tiles
+  if (gy > m_tiles) gy = m_tiles;
+  if (gy < 1) gy = 1;
+  dim3 grid(n_tiles, gy);
   pw_gemm_kernel<WM, AMODE><<<grid, NTHREADS, smem, st>>>(a);
   CVB_LAUNCH_CHECK();
   return 0;
