@@ -129,8 +129,11 @@ __global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
+// Register-lean layout so that 2 CTAs (16 warps) fit per SM and overlap each other's load / compute phases:
+//  * phase A (dW): thread = (channel pair, pixel slice = warp); 9 taps x 2 channels = 18 accumulators kept over the batch loop
+//  * phase B (dX): thread = (8-channel chunk, pixel); the 72 weights are kept as 36 packed bf16x2 registers (they ARE bf16 values)
 template <int GMODE, int XMODE>
-__global__ void __launch_bounds__(NT) dw_bwd_kernel(const cvb_dw_bwd_args p, int Ho, int Wo, int TH, int TW, int logTW, int tiles_w) {
+__global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(const cvb_dw_bwd_args p, int Ho, int Wo, int TH, int TW, int logTW, int tiles_w) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ float s_cs[CB], s_cq[CB];
   __shared__ float s_dw[9][CB];
@@ -147,23 +150,28 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(const cvb_dw_bwd_args p, int
   const int ITH = s * TH, ITW = s * TW;     // owned input tile
   const int logITW = logTW + (s == 2 ? 1 : 0);
 
-  const int cgi = tid & 7, pt = tid >> 3;
+  const int cgi = tid & 7, pt = tid >> 3;   // phase B role
   const int cc = c0 + cgi * 8;
   const bool cc_ok = cc < p.C;
+  const int cp = lane, ps = warp;           // phase A role: channels c0 + 2cp, +1 ; pixel slice = warp
 
   for (int i = tid; i < 9 * CB; i += NT) (&s_dw[0][0])[i] = 0.f;
   if (tid < CB) { s_cs[tid] = 0.f; s_cq[tid] = 0.f; }
 
-  float accw[9][8];
+  float accw[9][2];
 #pragma unroll
-  for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) accw[tp][j] = 0.f;
+  for (int tp = 0; tp < 9; ++tp) { accw[tp][0] = 0.f; accw[tp][1] = 0.f; }
   float cs[8], cq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
+  uint32_t wpk[9][4];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      wpk[tp][j] = cc_ok ? pack_bf162(p.Wt[tp * p.C + cc + 2 * j], p.Wt[tp * p.C + cc + 2 * j + 1]) : 0u;
 
-  // loader-role parameters (chunk = lane & 7)
+  // loader role (chunk = lane & 7)
   const int lch = lane & 7;
   const int lc = c0 + lch * 8;
   const bool lc_ok = lc < p.C;
@@ -174,36 +182,39 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(const cvb_dw_bwd_args p, int
     const bf16* __restrict__ X = static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C;
     bf16* __restrict__ DX = static_cast<bf16*>(p.DX) + (size_t)b * p.H * p.W * p.C;
     __syncthreads();  // previous iteration done with smem
-    // ---- stage dy tile (per-channel coefficients are scoped here to keep them out of the stencil's live range)
+    // ---- stage dy tile (per-channel coefficients scoped here to keep them out of the stencil's live range)
     {
-    float g0[8], g1[8], g2[8];
+      float g0[8], g1[8], g2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      g0[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p0[lc + j] : 1.f;
-      g1[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p1[lc + j] : 0.f;
-      g2[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p2[lc + j] : 0.f;
-    }
-    for (int gi = warp; gi < GH; gi += NT / 32) {
-      const int oh = oh0 - go + gi;
-      const bool h_ok = oh >= 0 && oh < Ho;
-      for (int gj = lane >> 3; gj < GW; gj += 4) {
-        const int ow = ow0 - go + gj;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (h_ok && lc_ok && ow >= 0 && ow < Wo) {
-          float f[8];
-          const size_t off = ((size_t)oh * Wo + ow) * p.C + lc;
-          unpack8(ldg16(DZ + off), f);
-          if (GMODE == CVB_A_BNB) {
-            float y[8];
-            unpack8(ldg16(Y2 + off), y);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
-          }
-          v = pack8(f);
-        }
-        *reinterpret_cast<uint4*>(sG + pix_off(gi * GW + gj, lch)) = v;
+      for (int j = 0; j < 8; ++j) {
+        g0[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p0[lc + j] : 1.f;
+        g1[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p1[lc + j] : 0.f;
+        g2[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p2[lc + j] : 0.f;
       }
-    }
+      for (int gi = warp; gi < GH; gi += NT / 32) {
+        const int oh = oh0 - go + gi;
+        const bool h_ok = oh >= 0 && oh < Ho;
+        for (int gj = lane >> 3; gj < GW; gj += 4) {
+          const int ow = ow0 - go + gj;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (h_ok && lc_ok && ow >= 0 && ow < Wo) {
+            float f[8];
+            const size_t off = ((size_t)oh * Wo + ow) * p.C + lc;
+            const uint4 rz = ldg16(DZ + off);
+            if (GMODE == CVB_A_BNB) {
+              float y[8];
+              unpack8(ldg16(Y2 + off), y);
+              unpack8(rz, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
+              v = pack8(f);
+            } else {
+              v = rz;
+            }
+          }
+          *reinterpret_cast<uint4*>(sG + pix_off(gi * GW + gj, lch)) = v;
+        }
+      }
     }
     // ---- stage transformed input tile (+halo)
     {
@@ -221,88 +232,87 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(const cvb_dw_bwd_args p, int
           const int w = w_base + jw;
           uint4 v = make_uint4(0, 0, 0, 0);
           if (h_ok && lc_ok && w >= 0 && w < p.W) {
-            float f[8];
-            load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + lc, x0, x1, f);
-            v = pack8(f);
+            if (XMODE == CVB_A_RAW) {
+              v = ldg16(X + ((size_t)h * p.W + w) * p.C + lc);
+            } else {
+              float f[8];
+              load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + lc, x0, x1, f);
+              v = pack8(f);
+            }
           }
           *reinterpret_cast<uint4*>(sX + pix_off(ih * XW + jw, lch)) = v;
         }
       }
     }
     __syncthreads();
-    // ---- A: weight gradient partials  dW[u,v] += dy[oh,ow] * a[s*oh+u-1, s*ow+v-1]
-    for (int op = pt; op < TH * TW; op += NT / 8) {
-      const int oh = op >> logTW, ow = op & (TW - 1);
-      float dy[8];
-      unpack8(*reinterpret_cast<const uint4*>(sG + pix_off((oh + go) * GW + ow + go, cgi)), dy);
+    // ---- A: weight gradient partials  dW[u,v] += dy[oh,ow] * a[s*oh+u-1, s*ow+v-1]   (4-byte = 2-channel smem accesses)
+    {
+      const uint32_t sub = static_cast<uint32_t>((cp & 3) << 2);
+      const int chk = cp >> 2;
+      for (int op = ps; op < TH * TW; op += NT / 32) {
+        const int oh = op >> logTW, ow = op & (TW - 1);
+        const float2 dy = unpack_bf162(*reinterpret_cast<const uint32_t*>(sG + pix_off((oh + go) * GW + ow + go, chk) + sub));
 #pragma unroll
-      for (int u = 0; u < 3; ++u)
+        for (int u = 0; u < 3; ++u)
 #pragma unroll
-        for (int v = 0; v < 3; ++v) {
-          float a[8];
-          unpack8(*reinterpret_cast<const uint4*>(sX + pix_off((s * oh + u) * XW + s * ow + v, cgi)), a);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) accw[u * 3 + v][j] = fmaf(dy[j], a[j], accw[u * 3 + v][j]);
-        }
+          for (int v = 0; v < 3; ++v) {
+            const float2 a = unpack_bf162(*reinterpret_cast<const uint32_t*>(sX + pix_off((s * oh + u) * XW + s * ow + v, chk) + sub));
+            accw[u * 3 + v][0] = fmaf(dy.x, a.x, accw[u * 3 + v][0]);
+            accw[u * 3 + v][1] = fmaf(dy.y, a.y, accw[u * 3 + v][1]);
+          }
+      }
     }
     // ---- B: input gradient  da[h,w] = sum_{u,v} W[u,v] * dy[(h+1-u)/s, (w+1-v)/s]
-    {
-      float wt[9][8];
+    for (int ip = pt; ip < ITH * ITW; ip += NT / 8) {
+      const int ih = ip >> logITW, iw = ip & (ITW - 1);
+      const int h = s * oh0 + ih, w = s * ow0 + iw;
+      if (h < p.H && w < p.W && cc_ok) {
+        float da[8];
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp)
+        for (int j = 0; j < 8; ++j) da[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wt[tp][j] = cc_ok ? p.Wt[tp * p.C + cc + j] : 0.f;
-      for (int ip = pt; ip < ITH * ITW; ip += NT / 8) {
-        const int ih = ip >> logITW, iw = ip & (ITW - 1);
-        const int h = s * oh0 + ih, w = s * ow0 + iw;
-        if (h < p.H && w < p.W && cc_ok) {
-          float da[8];
+        for (int u = 0; u < 3; ++u) {
+          int gi;
+          if (s == 1) gi = ih + 2 - u;
+          else { if (((ih + 1 - u) & 1) != 0) continue; gi = (ih + 1 - u) >> 1; }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) da[j] = 0.f;
+          for (int v = 0; v < 3; ++v) {
+            int gj;
+            if (s == 1) gj = iw + 2 - v;
+            else { if (((iw + 1 - v) & 1) != 0) continue; gj = (iw + 1 - v) >> 1; }
+            float dy[8];
+            unpack8(*reinterpret_cast<const uint4*>(sG + pix_off(gi * GW + gj, cgi)), dy);
 #pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            int gi;
-            if (s == 1) gi = ih + 2 - u;
-            else { if (((ih + 1 - u) & 1) != 0) continue; gi = (ih + 1 - u) >> 1; }
-#pragma unroll
-            for (int v = 0; v < 3; ++v) {
-              int gj;
-              if (s == 1) gj = iw + 2 - v;
-              else { if (((iw + 1 - v) & 1) != 0) continue; gj = (iw + 1 - v) >> 1; }
-              float dy[8];
-              unpack8(*reinterpret_cast<const uint4*>(sG + pix_off(gi * GW + gj, cgi)), dy);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) da[j] = fmaf(wt[u * 3 + v][j], dy[j], da[j]);
+            for (int j = 0; j < 4; ++j) {
+              const float2 wv = unpack_bf162(wpk[u * 3 + v][j]);
+              da[2 * j] = fmaf(wv.x, dy[2 * j], da[2 * j]);
+              da[2 * j + 1] = fmaf(wv.y, dy[2 * j + 1], da[2 * j + 1]);
             }
           }
-          const size_t off = ((size_t)h * p.W + w) * p.C + cc;
-          if (XMODE != CVB_A_RAW) {
-            float xr[8];
-            unpack8(ldg16(static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C + off), xr);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (XMODE == CVB_A_AFF_SILU) da[j] *= silu_grad_f(fmaf(p.x_p0[cc + j], xr[j], p.x_p1[cc + j]));
-              da[j] = bf16_round(da[j]);
-              cs[j] += da[j];
-              cq[j] += da[j] * xr[j];
-            }
-          }
-          stg16(DX + off, pack8(da));
         }
+        const size_t off = ((size_t)h * p.W + w) * p.C + cc;
+        if (XMODE != CVB_A_RAW) {
+          float xr[8];
+          unpack8(ldg16(X + off), xr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (XMODE == CVB_A_AFF_SILU) da[j] *= silu_grad_f(fmaf(__ldg(p.x_p0 + cc + j), xr[j], __ldg(p.x_p1 + cc + j)));
+            da[j] = bf16_round(da[j]);
+            cs[j] += da[j];
+            cq[j] += da[j] * xr[j];
+          }
+        }
+        stg16(DX + off, pack8(da));
       }
     }
   }
 
-  // ---- reductions
+  // ---- reductions (once per CTA)
 #pragma unroll
-  for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = accw[tp][j];
-      a += __shfl_xor_sync(0xffffffffu, a, 8);
-      a += __shfl_xor_sync(0xffffffffu, a, 16);
-      if (lane < 8) atomicAdd(&s_dw[tp][cgi * 8 + j], a);
-    }
+  for (int tp = 0; tp < 9; ++tp) {
+    atomicAdd(&s_dw[tp][2 * cp], accw[tp][0]);
+    atomicAdd(&s_dw[tp][2 * cp + 1], accw[tp][1]);
+  }
   if (p.col_sum) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -389,7 +399,7 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   // batch loop inside the CTA keeps the number of dW atomics bounded: aim for ~8 CTAs per SM in flight
   int per_img = tiles_h * tiles_w * cblocks;
   int want = 8 * cvb_num_sms();
-  int gz = (want + per_img - 1) / per_img;
+  int gz = (want + per_img - 1) / per_img;  // >= 2 resident CTAs per SM x 4 waves
   if (gz > a.B) gz = a.B;
   if (gz < 1) gz = 1;
   dim3 grid(tiles_h * tiles_w, cblocks, gz);

@@ -377,7 +377,7 @@ int dispatch_tile(const cvb_gemm_args& a, cudaStream_t st) {
 // =====================================================================================================================
 // weight gradient
 // =====================================================================================================================
-constexpr int WG_TN = 64, WG_TK = 64, WG_MB = 32, WG_STAGES = 4;
+constexpr int WG_TN = 64, WG_TK = 64, WG_MB = 64, WG_STAGES = 4;
 
 __device__ __forceinline__ uint32_t swz128(int row, int ch) {  // 128-byte rows, 8 x 16B chunks
   return static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4));
@@ -386,7 +386,7 @@ __device__ __forceinline__ uint32_t swz128(int row, int ch) {  // 128-byte rows,
 template <int GMODE, int AMODE>
 __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const cvb_wgrad_args p, int m_per_cta) {
   constexpr bool TWO_G = (GMODE == CVB_A_BNB);
-  constexpr int T_STAGE = WG_MB * 64 * 2;  // 4 KB per operand tile
+  constexpr int T_STAGE = WG_MB * 64 * 2;  // bytes per operand tile and stage
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sG = smem;
   uint8_t* sG2 = smem + WG_STAGES * T_STAGE;
@@ -408,18 +408,21 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const cvb_wgrad_args
   const bf16* __restrict__ A = static_cast<const bf16*>(p.A);
 
   auto load_stage = [&](int s, int stage) {
-    const int row = tid >> 3, ch = tid & 7;
-    const int m = m_begin + s * WG_MB + row;
-    {
-      int n = n0 + ch * 8;
-      bool ok = (m < m_end) && (n < p.N);
-      cp_async16(smem_u32(sG + stage * T_STAGE) + swz128(row, ch), G + (ok ? (size_t)m * p.ldg + n : 0), ok);
-      if (TWO_G) cp_async16(smem_u32(sG2 + stage * T_STAGE) + swz128(row, ch), G2 + (ok ? (size_t)m * p.ldg2 + n : 0), ok);
-    }
-    {
-      int k = k0 + ch * 8;
-      bool ok = (m < m_end) && (k < p.K);
-      cp_async16(smem_u32(sA + stage * T_STAGE) + swz128(row, ch), A + (ok ? (size_t)m * p.lda + k : 0), ok);
+#pragma unroll
+    for (int i = 0; i < WG_MB / 32; ++i) {
+      const int row = (tid >> 3) + i * 32, ch = tid & 7;
+      const int m = m_begin + s * WG_MB + row;
+      {
+        int n = n0 + ch * 8;
+        bool ok = (m < m_end) && (n < p.N);
+        cp_async16(smem_u32(sG + stage * T_STAGE) + swz128(row, ch), G + (ok ? (size_t)m * p.ldg + n : 0), ok);
+        if (TWO_G) cp_async16(smem_u32(sG2 + stage * T_STAGE) + swz128(row, ch), G2 + (ok ? (size_t)m * p.ldg2 + n : 0), ok);
+      }
+      {
+        int k = k0 + ch * 8;
+        bool ok = (m < m_end) && (k < p.K);
+        cp_async16(smem_u32(sA + stage * T_STAGE) + swz128(row, ch), A + (ok ? (size_t)m * p.lda + k : 0), ok);
+      }
     }
   };
 
@@ -474,7 +477,7 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const cvb_wgrad_args
     const int ms0 = m_begin + s * WG_MB;
     const bool tail = (ms0 + WG_MB > m_end);
 #pragma unroll
-    for (int ms = 0; ms < 2; ++ms) {
+    for (int ms = 0; ms < WG_MB / 16; ++ms) {
       // G' fragments (mma A operand: rows = n, cols = m), two m16 tiles
       uint32_t gf[2][4];
 #pragma unroll
@@ -579,7 +582,7 @@ int launch_wgrad(const cvb_wgrad_args& a, cudaStream_t st) {
   size_t smem = (size_t)WG_STAGES * WG_MB * 64 * 2 * (GMODE == CVB_A_BNB ? 3 : 2);
   static bool attr_set = false;
   if (!attr_set) {
-    CVB_CUDA(cudaFuncSetAttribute(pw_wgrad_kernel<GMODE, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CVB_CUDA(cudaFuncSetAttribute(pw_wgrad_kernel<GMODE, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     attr_set = true;
   }
   dim3 grid(kt, nt, splits);
