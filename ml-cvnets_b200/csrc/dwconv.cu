@@ -26,10 +26,17 @@ __device__ __forceinline__ void load8_mode(int mode, const bf16* ptr, const floa
 }
 
 // ------------------------------------------------------------------------------------------------------------- forward
+// TMA-staged: one elected thread issues a 4-D tensor load of the [IH, IW, 64ch] halo tile (out-of-bounds = zero fill = the
+// conv padding) straight into 128B-swizzled shared memory; two buffers + mbarriers keep the NEXT image's tile in flight while
+// the current one is transformed (producer BN+SiLU, in place) and convolved.
 template <int XMODE>
-__global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int Ho, int Wo, int TH, int TW, int logTW, int tiles_w) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const cvb_dw_fwd_args p, int Ho, int Wo, int TH,
+                                                       int TW, int logTW, int tiles_w, int buf_bytes) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 128B-swizzled TMA destinations must be 1024-byte aligned in the shared window: align by hand (host adds 1 KB of slack)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ float s_cs[CB], s_cq[CB];
+  __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = p.stride;
   const int th_i = blockIdx.x / tiles_w, tw_i = blockIdx.x % tiles_w;
@@ -37,80 +44,100 @@ __global__ void __launch_bounds__(NT) dw_fwd_kernel(const cvb_dw_fwd_args p, int
   const int c0 = blockIdx.y * CB;
   const int IH = (TH - 1) * s + 3, IW = (TW - 1) * s + 3;
   const int h_base = oh0 * s - 1, w_base = ow0 * s - 1;
+  const uint32_t tile_bytes = (uint32_t)IH * IW * 128;
+  const int n_img = (p.B - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
 
   if (tid < CB) { s_cs[tid] = 0.f; s_cq[tid] = 0.f; }
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < 2 && i < n_img; ++i) {
+      mbar_expect_tx(&bar[i], tile_bytes);
+      tma_load_4d(smem + i * buf_bytes, &tmX, &bar[i], c0, w_base, h_base, (int)blockIdx.z + i * (int)gridDim.z);
+    }
+  }
+
   const int cgi = tid & 7, pt = tid >> 3;
   const int c = c0 + cgi * 8;
   const bool c_ok = c < p.C;
   float cs[8], cq[8];  // BatchNorm statistics, accumulated over the batch loop and flushed once per CTA
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-
-  for (int b = blockIdx.z; b < p.B; b += gridDim.z) {
-  const bf16* __restrict__ X = static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C;
-  __syncthreads();  // previous image's stencil reads are done before the tile is overwritten
-
-  // phase 1: stage transformed input tile (+halo)
-  {
-    const int ch = lane & 7;
-    const int lc = c0 + ch * 8;
-    const bool lc_ok = lc < p.C;
-    float p0[8], p1[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      p0[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p0[lc + j] : 1.f;
-      p1[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p1[lc + j] : 0.f;
-    }
-    for (int ih = warp; ih < IH; ih += NT / 32) {
-      const int h = h_base + ih;
-      const bool h_ok = (h >= 0) && (h < p.H);
-      for (int jw = lane >> 3; jw < IW; jw += 4) {
-        const int w = w_base + jw;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (h_ok && lc_ok && w >= 0 && w < p.W) {
-          float f[8];
-          load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + lc, p0, p1, f);
-          v = pack8(f);
-        }
-        *reinterpret_cast<uint4*>(smem + pix_off(ih * IW + jw, ch)) = v;
-      }
-    }
-  }
-  __syncthreads();
-
-  // phase 2: stencil
-  float wt[9][8];
+  uint32_t wpk[9][4];  // the 72 weights of this thread's 8 channels are bf16 values: keep them packed
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wt[tp][j] = c_ok ? p.Wt[tp * p.C + c + j] : 0.f;
-  bf16* __restrict__ Y = static_cast<bf16*>(p.Y) + (size_t)b * Ho * Wo * p.C;
-  for (int op = pt; op < TH * TW; op += NT / 8) {
-    const int oh = op >> logTW, ow = op & (TW - 1);
-    const int gh = oh0 + oh, gw = ow0 + ow;
-    if (gh < Ho && gw < Wo && c_ok) {
-      float acc[8];
+    for (int j = 0; j < 4; ++j) wpk[tp][j] = c_ok ? pack_bf162(p.Wt[tp * p.C + c + 2 * j], p.Wt[tp * p.C + c + 2 * j + 1]) : 0u;
+
+  for (int i = 0; i < n_img; ++i) {
+    const int b = (int)blockIdx.z + i * (int)gridDim.z;
+    uint8_t* tile = smem + (i & 1) * buf_bytes;
+    mbar_wait(&bar[i & 1], (i >> 1) & 1);
+    if (XMODE != CVB_A_RAW) {
+      // in-place producer transform; out-of-bounds pixels / channels stay zero (padding acts on the activated tensor)
+      const int pch = lane & 7;  // physical 16-byte chunk inside the pixel's 128-byte row
+      for (int ih = warp; ih < IH; ih += NT / 32) {
+        const int h = h_base + ih;
+        if (h < 0 || h >= p.H) continue;
+        for (int jw = lane >> 3; jw < IW; jw += 4) {
+          const int w = w_base + jw;
+          const int pix = ih * IW + jw;
+          const int lc = c0 + ((pch ^ (pix & 7)) << 3);  // logical channel of this physical chunk
+          if (w < 0 || w >= p.W || lc >= p.C) continue;
+          uint4* ptr = reinterpret_cast<uint4*>(tile + pix * 128 + (pch << 4));
+          float f[8];
+          unpack8(*ptr, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-      for (int u = 0; u < 3; ++u)
-#pragma unroll
-        for (int v = 0; v < 3; ++v) {
-          float xin[8];
-          unpack8(*reinterpret_cast<const uint4*>(smem + pix_off((oh * s + u) * IW + ow * s + v, cgi)), xin);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt[u * 3 + v][j], xin[j], acc[j]);
+          for (int j = 0; j < 8; ++j) {
+            float z = fmaf(__ldg(p.x_p0 + lc + j), f[j], __ldg(p.x_p1 + lc + j));
+            f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
+          }
+          *ptr = pack8(f);
         }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = bf16_round(acc[j]);
-        cs[j] += acc[j];
-        cq[j] += acc[j] * acc[j];
       }
-      stg16(Y + ((size_t)gh * Wo + gw) * p.C + c, pack8(acc));
+      __syncthreads();
+    }
+    bf16* __restrict__ Y = static_cast<bf16*>(p.Y) + (size_t)b * Ho * Wo * p.C;
+    for (int op = pt; op < TH * TW; op += NT / 8) {
+      const int oh = op >> logTW, ow = op & (TW - 1);
+      const int gh = oh0 + oh, gw = ow0 + ow;
+      if (gh < Ho && gw < Wo && c_ok) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            float xin[8];
+            unpack8(*reinterpret_cast<const uint4*>(tile + pix_off((oh * s + u) * IW + ow * s + v, cgi)), xin);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 wv = unpack_bf162(wpk[u * 3 + v][j]);
+              acc[2 * j] = fmaf(wv.x, xin[2 * j], acc[2 * j]);
+              acc[2 * j + 1] = fmaf(wv.y, xin[2 * j + 1], acc[2 * j + 1]);
+            }
+          }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = bf16_round(acc[j]);
+          cs[j] += acc[j];
+          cq[j] += acc[j] * acc[j];
+        }
+        stg16(Y + ((size_t)gh * Wo + gw) * p.C + c, pack8(acc));
+      }
+    }
+    __syncthreads();  // every thread is done with this buffer
+    if (tid == 0 && i + 2 < n_img) {
+      fence_proxy_async();  // order the generic-proxy accesses above before the async-proxy overwrite
+      mbar_expect_tx(&bar[i & 1], tile_bytes);
+      tma_load_4d(tile, &tmX, &bar[i & 1], c0, w_base, h_base, (int)blockIdx.z + (i + 2) * (int)gridDim.z);
     }
   }
-  }  // batch loop
   if (p.col_sum) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -356,19 +383,22 @@ extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   int TH, TW; pick_tile(Ho, Wo, a.stride, &TH, &TW);
   const int tiles_h = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
   const int IH = (TH - 1) * a.stride + 3, IW = (TW - 1) * a.stride + 3;
-  size_t smem = (size_t)IH * IW * 128;
+  const int buf_bytes = (IH * IW * 128 + 1023) / 1024 * 1024;  // 128B-swizzled TMA destinations are 1024-byte aligned
+  size_t smem = (size_t)2 * buf_bytes + 1024;
   const int cblocks = (a.C + CB - 1) / CB;
   int per_img = tiles_h * tiles_w * cblocks;
-  int gz = (16 * cvb_num_sms() + per_img - 1) / per_img;  // batch loop inside the CTA bounds the statistics atomics
+  int gz = (8 * cvb_num_sms() + per_img - 1) / per_img;  // batch loop inside the CTA: double-buffered TMA + bounded statistics atomics
   if (gz > a.B) gz = a.B;
   if (gz < 1) gz = 1;
   dim3 grid(tiles_h * tiles_w, cblocks, gz);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmX;
+  if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, IH, IW, CB)) return 1;
 #define CVB_DW_FWD(MODE)                                                                                                  \
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
-    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; } \
-    dw_fwd_kernel<MODE><<<grid, NT, smem, st>>>(a, Ho, Wo, TH, TW, ilog2(TW), tiles_w);                                  \
+    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+    dw_fwd_kernel<MODE><<<grid, NT, smem, st>>>(tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, buf_bytes);                   \
   }
   if (a.x_mode == CVB_A_RAW) CVB_DW_FWD(CVB_A_RAW)
   else if (a.x_mode == CVB_A_AFF) CVB_DW_FWD(CVB_A_AFF)

@@ -15,32 +15,39 @@ namespace {
 
 constexpr int BM = 128;       // CTA tile rows (pixels)
 constexpr int BK = 32;        // K step
-constexpr int STAGES = 4;
 constexpr int NTHREADS = 256;
 
 __device__ __forceinline__ uint32_t swz64(int row, int ch) {  // 64-byte rows, 4 x 16B chunks
   return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
 }
 
+template <int AMODE>
+struct GemmCfg {
+  // the BN-backward prologue streams two A tensors: one stage less keeps two CTAs per SM
+  static constexpr int kStages = (AMODE == CVB_A_BNB) ? 3 : 4;
+};
+
 template <int WM, int AMODE>
-__global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p) {
+__global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_args p) {
   constexpr int WARPS_M = BM / WM;
   constexpr int WARPS_N = 8 / WARPS_M;
   constexpr int BN = WARPS_N * 32;
   constexpr int MI = WM / 16;
   constexpr bool TWO_A = (AMODE == CVB_A_BNB);
+  constexpr int NST = GemmCfg<AMODE>::kStages;
   constexpr int A_STAGE = BM * BK * 2;
   constexpr int B_STAGE = BN * BK * 2;
-  constexpr int LDC_S = BN + 4;  // fp32 staging row stride
+  constexpr int LDC_S = BN + 4;      // fp32 staging row stride
+  constexpr int HALF = BM / 2;       // the epilogue stages the tile in two 64-row halves
+  constexpr bool HAS_P = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN || AMODE == CVB_A_BNB);
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sA2 = smem + STAGES * A_STAGE;
-  uint8_t* sB = smem + (TWO_A ? 2 : 1) * STAGES * A_STAGE;
-  constexpr int PIPE_BYTES = (TWO_A ? 2 : 1) * STAGES * A_STAGE + STAGES * B_STAGE;
-  constexpr int STAGE_C_BYTES = BM * LDC_S * 4;
-  // prologue parameters live behind BOTH the pipeline ring and the epilogue staging tile (which overlays the ring)
-  float* sP = reinterpret_cast<float*>(smem + (PIPE_BYTES > STAGE_C_BYTES ? PIPE_BYTES : STAGE_C_BYTES));
+  uint8_t* sA2 = smem + NST * A_STAGE;
+  uint8_t* sB = smem + (TWO_A ? 2 : 1) * NST * A_STAGE;
+  constexpr int PIPE_BYTES = (TWO_A ? 2 : 1) * NST * A_STAGE + NST * B_STAGE;
+  float* sC = reinterpret_cast<float*>(smem + PIPE_BYTES);                      // NOT overlaid: loads of the next tiles stay in flight
+  float* sP = reinterpret_cast<float*>(smem + PIPE_BYTES + HALF * LDC_S * 4);   // prologue parameters
   __shared__ float s_col[2][128];
   __shared__ double s_samp[2][128];  // fp64: cross-thread order must not change the GroupNorm statistics
 
@@ -51,10 +58,11 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
   const int KT = (p.K + BK - 1) / BK;
   const int Kpad = KT * BK;
   const int m_tiles = (p.M + BM - 1) / BM;
+  const int my_tiles = (m_tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int total = my_tiles * KT;  // flattened (tile, k-tile) iterations of this CTA
 
   if (tid < 128) { s_col[0][tid] = 0.f; s_col[1][tid] = 0.f; s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
-  // per-K prologue parameters -> smem (zero padded so that the K tail transforms to finite values)
-  if (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN || AMODE == CVB_A_BNB) {
+  if (HAS_P) {  // per-K prologue parameters -> smem (zero padded so that the K tail transforms to finite values)
     for (int k = tid; k < Kpad; k += NTHREADS) {
       bool ok = k < p.K;
       sP[k] = ok ? p.a_p0[k] : 0.f;
@@ -79,243 +87,246 @@ __global__ void __launch_bounds__(NTHREADS) pw_gemm_kernel(const cvb_gemm_args p
   const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
   const bf16* __restrict__ Yg = static_cast<const bf16*>(p.Y);
   const bf16* __restrict__ Rg = static_cast<const bf16*>(p.R);
-  float cs[8], cq[8];  // per-column statistics, accumulated over all tiles of this CTA
+  float cs[8], cq[8];  // per-column statistics, accumulated over all tiles of this CTA, flushed once
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
 
-  // persistent over M tiles: column statistics are flushed ONCE per CTA (not once per tile)
-  for (int mt = blockIdx.y; mt < m_tiles; mt += gridDim.y) {
-  const int m0 = mt * BM;
-  auto load_stage = [&](int kt, int stage) {
+  // one ring for the whole CTA lifetime: iteration `it` = (tile it / KT, k-tile it % KT)
+  auto issue = [&](int it) {
+    const int stage = it % NST;
+    const int j = it / KT, kt = it - j * KT;
+    const int m0i = ((int)blockIdx.y + j * (int)gridDim.y) * BM;
     const int k0 = kt * BK;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       int c = tid + i * NTHREADS;
       int row = c >> 2, ch = c & 3;
-      int m = m0 + row, k = k0 + ch * 8;
+      int m = m0i + row, k = k0 + ch * 8;
       bool ok = (m < p.M) && (k < p.K);
-      const bf16* src = A + (ok ? (size_t)m * p.lda + k : 0);
-      cp_async16(smem_u32(sA + stage * A_STAGE) + swz64(row, ch), src, ok);
-      if (TWO_A) {
-        const bf16* src2 = A2 + (ok ? (size_t)m * p.lda2 + k : 0);
-        cp_async16(smem_u32(sA2 + stage * A_STAGE) + swz64(row, ch), src2, ok);
-      }
+      cp_async16(smem_u32(sA + stage * A_STAGE) + swz64(row, ch), A + (ok ? (size_t)m * p.lda + k : 0), ok);
+      if (TWO_A) cp_async16(smem_u32(sA2 + stage * A_STAGE) + swz64(row, ch), A2 + (ok ? (size_t)m * p.lda2 + k : 0), ok);
     }
     for (int c = tid; c < BN * 4; c += NTHREADS) {
       int row = c >> 2, ch = c & 3;
       int n = n0 + row, k = k0 + ch * 8;
       bool ok = (n < p.N) && (k < p.K);
-      const bf16* src = Wg + (ok ? (size_t)n * p.ldw + k : 0);
-      cp_async16(smem_u32(sB + stage * B_STAGE) + swz64(row, ch), src, ok);
+      cp_async16(smem_u32(sB + stage * B_STAGE) + swz64(row, ch), Wg + (ok ? (size_t)n * p.ldw + k : 0), ok);
     }
   };
 
-  // GroupNorm prologue: per-row statistics of the rows this thread's fragments touch
-  float rmean[MI][2], rrstd[MI][2];
-  if (AMODE == CVB_A_GN) {
 #pragma unroll
-    for (int mi = 0; mi < MI; ++mi)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int m = m0 + wm0 + mi * 16 + (lane >> 2) + h * 8;
-        int b = (m < p.M ? m : p.M - 1) / p.rows_per_sample;
-        rmean[mi][h] = p.row_mean[b];
-        rrstd[mi][h] = p.row_rstd[b];
-      }
-  }
-
-  float acc[MI][4][4];
-#pragma unroll
-  for (int mi = 0; mi < MI; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
-
-#pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_stage(s, s);
+  for (int s = 0; s < NST - 1; ++s) {
+    if (s < total) issue(s);
     cp_async_commit();
   }
 
-  for (int kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    {
-      int nk = kt + STAGES - 1;
-      if (nk < KT) load_stage(nk, nk % STAGES);
-      cp_async_commit();
-    }
-    const int stage = kt % STAGES;
-    const uint32_t aBase = smem_u32(sA + stage * A_STAGE);
-    const uint32_t a2Base = smem_u32(sA2 + stage * A_STAGE);
-    const uint32_t bBase = smem_u32(sB + stage * B_STAGE);
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      // prologue parameters of the 4 k-columns this thread's A registers cover: k, k+1, k+8, k+9
-      float q0[4], q1[4], q2[4];
-      if (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN || AMODE == CVB_A_BNB) {
-        int kq = kt * BK + ks * 16 + 2 * (lane & 3);
-        q0[0] = sP[kq]; q0[1] = sP[kq + 1]; q0[2] = sP[kq + 8]; q0[3] = sP[kq + 9];
-        q1[0] = sP[Kpad + kq]; q1[1] = sP[Kpad + kq + 1]; q1[2] = sP[Kpad + kq + 8]; q1[3] = sP[Kpad + kq + 9];
-        if (AMODE == CVB_A_BNB) {
-          q2[0] = sP[2 * Kpad + kq]; q2[1] = sP[2 * Kpad + kq + 1]; q2[2] = sP[2 * Kpad + kq + 8]; q2[3] = sP[2 * Kpad + kq + 9];
-        }
-      }
-      uint32_t af[MI][4];
-#pragma unroll
-      for (int mi = 0; mi < MI; ++mi) {
-        int row = wm0 + mi * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-        int ch = ks * 2 + (lane >> 4);
-        ldmatrix_x4(aBase + swz64(row, ch), af[mi][0], af[mi][1], af[mi][2], af[mi][3]);
-        if (AMODE != CVB_A_RAW) {
-          uint32_t a2f[4] = {0, 0, 0, 0};
-          if (TWO_A) ldmatrix_x4(a2Base + swz64(row, ch), a2f[0], a2f[1], a2f[2], a2f[3]);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            // r: 0 (row g, k lo) 1 (row g+8, k lo) 2 (row g, k hi) 3 (row g+8, k hi)
-            const int kk = (r >> 1) * 2;  // index into q*: lo pair -> 0,1 ; hi pair -> 2,3
-            const int h = r & 1;          // row half
-            float2 x = unpack_bf162(af[mi][r]);
-            float y0, y1;
-            if (AMODE == CVB_A_AFF) {
-              y0 = fmaf(q0[kk], x.x, q1[kk]); y1 = fmaf(q0[kk + 1], x.y, q1[kk + 1]);
-            } else if (AMODE == CVB_A_AFF_SILU) {
-              y0 = silu_f(fmaf(q0[kk], x.x, q1[kk])); y1 = silu_f(fmaf(q0[kk + 1], x.y, q1[kk + 1]));
-            } else if (AMODE == CVB_A_SILU) {
-              y0 = silu_f(x.x); y1 = silu_f(x.y);
-            } else if (AMODE == CVB_A_GN) {
-              float xm0 = (x.x - rmean[mi][h]) * rrstd[mi][h], xm1 = (x.y - rmean[mi][h]) * rrstd[mi][h];
-              y0 = fmaf(xm0, q0[kk], q1[kk]); y1 = fmaf(xm1, q0[kk + 1], q1[kk + 1]);
-            } else {  // BNB
-              float2 x2 = unpack_bf162(a2f[r]);
-              y0 = fmaf(q0[kk], x.x, fmaf(q1[kk], x2.x, q2[kk]));
-              y1 = fmaf(q0[kk + 1], x.y, fmaf(q1[kk + 1], x2.y, q2[kk + 1]));
-            }
-            af[mi][r] = pack_bf162(y0, y1);
-          }
-        }
-      }
-      uint32_t bfr[4][2];
-#pragma unroll
-      for (int nj = 0; nj < 2; ++nj) {
-        int row = wn0 + nj * 16 + (lane & 7) + (lane >> 4) * 8;
-        int ch = ks * 2 + ((lane >> 3) & 1);
-        ldmatrix_x4(bBase + swz64(row, ch), bfr[nj * 2][0], bfr[nj * 2][1], bfr[nj * 2 + 1][0], bfr[nj * 2 + 1][1]);
-      }
+  int it = 0;
+  for (int jt = 0; jt < my_tiles; ++jt) {
+    const int m0 = ((int)blockIdx.y + jt * (int)gridDim.y) * BM;
+    // GroupNorm prologue: per-row statistics of the rows this thread's fragments touch
+    float rmean[MI][2], rrstd[MI][2];
+    if (AMODE == CVB_A_GN) {
 #pragma unroll
       for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) mma_bf16_16816(acc[mi][ni], af[mi], bfr[ni][0], bfr[ni][1]);
-    }
-  }
-
-  // ------------------------------------------------------------------ epilogue: stage the fp32 tile through smem
-  cp_async_wait<0>();
-  __syncthreads();
-  float* sC = reinterpret_cast<float*>(smem);
-#pragma unroll
-  for (int mi = 0; mi < MI; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      int r = wm0 + mi * 16 + (lane >> 2);
-      int c = wn0 + ni * 8 + 2 * (lane & 3);
-      *reinterpret_cast<float2*>(&sC[r * LDC_S + c]) = make_float2(acc[mi][ni][0], acc[mi][ni][1]);
-      *reinterpret_cast<float2*>(&sC[(r + 8) * LDC_S + c]) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
-    }
-  __syncthreads();
-
-  float bias8[8], ep0[8], ep1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    bias8[j] = (col_ok && p.bias) ? p.bias[nc + j] : 0.f;
-    ep0[j] = (col_ok && p.e_p0) ? p.e_p0[nc + j] : 1.f;
-    ep1[j] = (col_ok && p.e_p1) ? p.e_p1[nc + j] : 0.f;
-  }
-  const int first_sample = m0 / rps;
-
-  for (int r = r0; r < BM; r += ROWS_PER_PASS) {
-    const int m = m0 + r;
-    const bool valid = col_ok && (m < p.M);
-    float ssum = 0.f, ssq = 0.f;
-    if (valid) {
-      float v[8];
-      float4 t0 = *reinterpret_cast<const float4*>(&sC[r * LDC_S + cg * 8]);
-      float4 t1 = *reinterpret_cast<const float4*>(&sC[r * LDC_S + cg * 8 + 4]);
-      v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += bias8[j];
-      float y8[8];
-      if (emode == CVB_E_SILU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-      } else if (emode == CVB_E_SILU_BWD) {
-        unpack8(ldg16(Yg + (size_t)m * p.ldy + nc), y8);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= silu_grad_f(fmaf(ep0[j], y8[j], ep1[j]));
-      } else if (emode == CVB_E_GN_BWD) {
-        unpack8(ldg16(Yg + (size_t)m * p.ldy + nc), y8);
-        const int b = m / rps;
-        const float mu = p.row_mean[b], rs = p.row_rstd[b];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          y8[j] = (y8[j] - mu) * rs;  // x-hat
-          cs[j] += v[j];
-          cq[j] += v[j] * y8[j];
-          v[j] *= ep0[j];
+        for (int h = 0; h < 2; ++h) {
+          int m = m0 + wm0 + mi * 16 + (lane >> 2) + h * 8;
+          int b = (m < p.M ? m : p.M - 1) / p.rows_per_sample;
+          rmean[mi][h] = p.row_mean[b];
+          rrstd[mi][h] = p.row_rstd[b];
         }
+    }
+    float acc[MI][4][4];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+
+    for (int kt = 0; kt < KT; ++kt, ++it) {
+      cp_async_wait<NST - 2>();
+      __syncthreads();
+      {
+        int nxt = it + NST - 1;
+        if (nxt < total) issue(nxt);
+        cp_async_commit();
       }
-      if (Rg) {
-        float r8[8];
-        unpack8(ldg16(Rg + (size_t)m * p.ldr + nc), r8);
+      const int stage = it % NST;
+      const uint32_t aBase = smem_u32(sA + stage * A_STAGE);
+      const uint32_t a2Base = smem_u32(sA2 + stage * A_STAGE);
+      const uint32_t bBase = smem_u32(sB + stage * B_STAGE);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += r8[j];
+      for (int ks = 0; ks < 2; ++ks) {
+        // prologue parameters of the 4 k-columns this thread's A registers cover: k, k+1, k+8, k+9
+        float q0[4], q1[4], q2[4];
+        if (HAS_P) {
+          int kq = kt * BK + ks * 16 + 2 * (lane & 3);
+          q0[0] = sP[kq]; q0[1] = sP[kq + 1]; q0[2] = sP[kq + 8]; q0[3] = sP[kq + 9];
+          q1[0] = sP[Kpad + kq]; q1[1] = sP[Kpad + kq + 1]; q1[2] = sP[Kpad + kq + 8]; q1[3] = sP[Kpad + kq + 9];
+          if (AMODE == CVB_A_BNB) {
+            q2[0] = sP[2 * Kpad + kq]; q2[1] = sP[2 * Kpad + kq + 1]; q2[2] = sP[2 * Kpad + kq + 8]; q2[3] = sP[2 * Kpad + kq + 9];
+          }
+        }
+        uint32_t af[MI][4];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+          int row = wm0 + mi * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          int ch = ks * 2 + (lane >> 4);
+          ldmatrix_x4(aBase + swz64(row, ch), af[mi][0], af[mi][1], af[mi][2], af[mi][3]);
+          if (AMODE != CVB_A_RAW) {
+            uint32_t a2f[4] = {0, 0, 0, 0};
+            if (TWO_A) ldmatrix_x4(a2Base + swz64(row, ch), a2f[0], a2f[1], a2f[2], a2f[3]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              // r: 0 (row g, k lo) 1 (row g+8, k lo) 2 (row g, k hi) 3 (row g+8, k hi)
+              const int kk = (r >> 1) * 2;  // index into q*: lo pair -> 0,1 ; hi pair -> 2,3
+              const int h = r & 1;          // row half
+              float2 x = unpack_bf162(af[mi][r]);
+              float y0, y1;
+              if (AMODE == CVB_A_AFF) {
+                y0 = fmaf(q0[kk], x.x, q1[kk]); y1 = fmaf(q0[kk + 1], x.y, q1[kk + 1]);
+              } else if (AMODE == CVB_A_AFF_SILU) {
+                y0 = silu_f(fmaf(q0[kk], x.x, q1[kk])); y1 = silu_f(fmaf(q0[kk + 1], x.y, q1[kk + 1]));
+              } else if (AMODE == CVB_A_SILU) {
+                y0 = silu_f(x.x); y1 = silu_f(x.y);
+              } else if (AMODE == CVB_A_GN) {
+                float xm0 = (x.x - rmean[mi][h]) * rrstd[mi][h], xm1 = (x.y - rmean[mi][h]) * rrstd[mi][h];
+                y0 = fmaf(xm0, q0[kk], q1[kk]); y1 = fmaf(xm1, q0[kk + 1], q1[kk + 1]);
+              } else {  // BNB
+                float2 x2 = unpack_bf162(a2f[r]);
+                y0 = fmaf(q0[kk], x.x, fmaf(q1[kk], x2.x, q2[kk]));
+                y1 = fmaf(q0[kk + 1], x.y, fmaf(q1[kk + 1], x2.y, q2[kk + 1]));
+              }
+              af[mi][r] = pack_bf162(y0, y1);
+            }
+          }
+        }
+        uint32_t bfr[4][2];
+#pragma unroll
+        for (int nj = 0; nj < 2; ++nj) {
+          int row = wn0 + nj * 16 + (lane & 7) + (lane >> 4) * 8;
+          int ch = ks * 2 + ((lane >> 3) & 1);
+          ldmatrix_x4(bBase + swz64(row, ch), bfr[nj * 2][0], bfr[nj * 2][1], bfr[nj * 2 + 1][0], bfr[nj * 2 + 1][1]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) mma_bf16_16816(acc[mi][ni], af[mi], bfr[ni][0], bfr[ni][1]);
       }
-      if (p.c_fp32) {
-        float* Cg = static_cast<float*>(p.C) + (size_t)m * p.ldc + nc;
-        *reinterpret_cast<float4*>(Cg) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(Cg + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      } else {
+    }
+
+    // ---------------------------------------------------------------- epilogue: two 64-row halves through the fp32 staging tile
+    const int first_sample = m0 / rps;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      __syncthreads();  // staging tile free (previous half / previous tile fully consumed)
+      if (wm0 / HALF == half) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]);
-        stg16(static_cast<bf16*>(p.C) + (size_t)m * p.ldc + nc, pack8(v));
+        for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            int r = (wm0 % HALF) + mi * 16 + (lane >> 2);
+            int c = wn0 + ni * 8 + 2 * (lane & 3);
+            *reinterpret_cast<float2*>(&sC[r * LDC_S + c]) = make_float2(acc[mi][ni][0], acc[mi][ni][1]);
+            *reinterpret_cast<float2*>(&sC[(r + 8) * LDC_S + c]) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
+          }
       }
-      if (emode == CVB_E_STORE || emode == CVB_E_SILU) {
+      __syncthreads();
+      // per-column epilogue vectors are (re)loaded here (L1 hits) instead of living in registers across the main loop
+      float bias8[8], ep0[8], ep1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { cs[j] += v[j]; cq[j] += v[j] * v[j]; ssum += v[j]; ssq += v[j] * v[j]; }
-      } else if (emode == CVB_E_SILU_BWD) {
+      for (int j = 0; j < 8; ++j) {
+        bias8[j] = (col_ok && p.bias) ? __ldg(p.bias + nc + j) : 0.f;
+        ep0[j] = (col_ok && p.e_p0) ? __ldg(p.e_p0 + nc + j) : 1.f;
+        ep1[j] = (col_ok && p.e_p1) ? __ldg(p.e_p1 + nc + j) : 0.f;
+      }
+      for (int r = r0; r < HALF; r += ROWS_PER_PASS) {
+        const int m = m0 + half * HALF + r;
+        const bool valid = col_ok && (m < p.M);
+        float ssum = 0.f, ssq = 0.f;
+        if (valid) {
+          float v[8];
+          float4 t0 = *reinterpret_cast<const float4*>(&sC[r * LDC_S + cg * 8]);
+          float4 t1 = *reinterpret_cast<const float4*>(&sC[r * LDC_S + cg * 8 + 4]);
+          v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { cs[j] += v[j]; cq[j] += v[j] * y8[j]; }
-      } else {
+          for (int j = 0; j < 8; ++j) v[j] += bias8[j];
+          float y8[8];
+          if (emode == CVB_E_SILU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ssum += v[j]; ssq += v[j] * y8[j]; }
+            for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+          } else if (emode == CVB_E_SILU_BWD) {
+            unpack8(ldg16(Yg + (size_t)m * p.ldy + nc), y8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= silu_grad_f(fmaf(ep0[j], y8[j], ep1[j]));
+          } else if (emode == CVB_E_GN_BWD) {
+            unpack8(ldg16(Yg + (size_t)m * p.ldy + nc), y8);
+            const int b = m / rps;
+            const float mu = p.row_mean[b], rs = p.row_rstd[b];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              y8[j] = (y8[j] - mu) * rs;  // x-hat
+              cs[j] += v[j];
+              cq[j] += v[j] * y8[j];
+              v[j] *= ep0[j];
+            }
+          }
+          if (Rg) {
+            float r8[8];
+            unpack8(ldg16(Rg + (size_t)m * p.ldr + nc), r8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r8[j];
+          }
+          if (p.c_fp32) {
+            float* Cg = static_cast<float*>(p.C) + (size_t)m * p.ldc + nc;
+            *reinterpret_cast<float4*>(Cg) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(Cg + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]);
+            stg16(static_cast<bf16*>(p.C) + (size_t)m * p.ldc + nc, pack8(v));
+          }
+          if (emode == CVB_E_STORE || emode == CVB_E_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cs[j] += v[j]; cq[j] += v[j] * v[j]; ssum += v[j]; ssq += v[j] * v[j]; }
+          } else if (emode == CVB_E_SILU_BWD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cs[j] += v[j]; cq[j] += v[j] * y8[j]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ssum += v[j]; ssq += v[j] * y8[j]; }
+          }
+        }
+        if (want_samp) {
+#pragma unroll
+          for (int o = CGS / 2; o > 0; o >>= 1) {
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+            ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+          }
+          if (cg == 0 && m < p.M) {
+            int bi = m / rps - first_sample;
+            atomicAdd(&s_samp[0][bi], (double)ssum);
+            atomicAdd(&s_samp[1][bi], (double)ssq);
+          }
+        }
       }
     }
     if (want_samp) {
-#pragma unroll
-      for (int o = CGS / 2; o > 0; o >>= 1) {
-        ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-        ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
-      }
-      if (cg == 0 && m < p.M) {
-        int bi = m / rps - first_sample;
-        atomicAdd(&s_samp[0][bi], (double)ssum);
-        atomicAdd(&s_samp[1][bi], (double)ssq);
+      __syncthreads();  // s_samp complete for this tile
+      if (tid < 128) {
+        int mlast = min(m0 + BM, p.M) - 1;
+        int nsamp = mlast / rps - first_sample + 1;
+        if (tid < nsamp) {
+          atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
+          atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
+          s_samp[0][tid] = 0.0;
+          s_samp[1][tid] = 0.0;
+        }
       }
     }
-  }
-  __syncthreads();  // all reads of the staged tile are done (next tile's cp.async overwrites it); s_samp complete
-  if (want_samp && tid < 128) {
-    int mlast = min(m0 + BM, p.M) - 1;
-    int nsamp = mlast / rps - first_sample + 1;
-    if (tid < nsamp) {
-      atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
-      atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
-      s_samp[0][tid] = 0.0;
-      s_samp[1][tid] = 0.0;
-    }
-  }
   }  // tile loop
+  cp_async_wait<0>();
 
   if (want_col) {
     // reduce over the lanes that share a column group (lane stride CGS), then one smem atomic per warp and column
@@ -344,19 +355,22 @@ template <int WM, int AMODE>
 int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   constexpr int WARPS_M = BM / WM;
   constexpr int BN = (8 / WARPS_M) * 32;
+  constexpr int NST = GemmCfg<AMODE>::kStages;
   const int KT = (a.K + BK - 1) / BK;
   const int nvec = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
-  size_t pipe = (size_t)STAGES * (BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1) + BN * BK * 2);
-  size_t stagec = (size_t)BM * (BN + 4) * 4;
-  size_t smem = (pipe > stagec ? pipe : stagec) + (size_t)nvec * KT * BK * 4;
+  size_t smem = (size_t)NST * (BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1) + BN * BK * 2) + (size_t)(BM / 2) * (BN + 4) * 4 +
+                (size_t)nvec * KT * BK * 4;
   static bool attr_set = false;
   if (!attr_set) {
     CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   CVB_CHECK(smem <= 200 * 1024, "cvb_pw_gemm: K=%d too large for the prologue parameter cache", a.K);
+  int occ = 0;
+  CVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pw_gemm_kernel<WM, AMODE>, NTHREADS, smem));
+  if (occ < 1) occ = 1;
   const int n_tiles = (a.N + BN - 1) / BN, m_tiles = (a.M + BM - 1) / BM;
-  int gy = (2 * cvb_num_sms() + n_tiles - 1) / n_tiles;  // ~2 resident CTAs per SM, each looping over M tiles
+  int gy = (occ * cvb_num_sms() + n_tiles - 1) / n_tiles;  // all CTAs resident, each streaming over its M tiles
   if (gy > m_tiles) gy = m_tiles;
   if (gy < 1) gy = 1;
   dim3 grid(n_tiles, gy);
