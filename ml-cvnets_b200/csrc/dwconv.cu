@@ -156,14 +156,24 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
-// Register-lean layout so that 2 CTAs (16 warps) fit per SM and overlap each other's load / compute phases:
-//  * phase A (dW): thread = (channel pair, pixel slice = warp); 9 taps x 2 channels = 18 accumulators kept over the batch loop
-//  * phase B (dX): thread = (8-channel chunk, pixel); the 72 weights are kept as 36 packed bf16x2 registers (they ARE bf16 values)
+// One pass over (dz, y2, x) per image tile, all three staged by TMA (zero-filled halos) into two buffer sets so the next
+// image's tiles are in flight while this one is processed:
+//   1. dy = BN-backward(dz, y2) in place                      (generic transform of the dz tile)
+//   2. phase B: dX = conv_transpose(dy) * silu'(BN(x)) (+ the producer's BN-backward statistics), raw x read from the smem tile
+//   3. a = SiLU(BN(x)) in place, phase A: dW[9 taps] += dy * a(shifted)
+// 512 threads, register-lean roles: phase A thread = (channel pair, pixel slice = warp) with 18 accumulators kept over the batch
+// loop; phase B thread = (8-channel chunk, pixel) with the 72 weights as 36 packed bf16x2 registers.
+constexpr int NTB = 512;
+
 template <int GMODE, int XMODE>
-__global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(const cvb_dw_bwd_args p, int Ho, int Wo, int TH, int TW, int logTW, int tiles_w) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmY2,
+                                                        const __grid_constant__ CUtensorMap tmX, const cvb_dw_bwd_args p, int Ho, int Wo, int TH,
+                                                        int TW, int logTW, int tiles_w, int g_bytes, int x_bytes) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ float s_cs[CB], s_cq[CB];
   __shared__ float s_dw[9][CB];
+  __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = p.stride;
   const int th_i = blockIdx.x / tiles_w, tw_i = blockIdx.x % tiles_w;
@@ -172,18 +182,40 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(const cvb_dw_bwd_args p, 
   const int go = (s == 1) ? 1 : 0;          // halo of the dy tile on the low side
   const int GH = TH + (s == 1 ? 2 : 1), GW = TW + (s == 1 ? 2 : 1);
   const int XH = s * TH + 3 - s, XW = s * TW + 3 - s;  // input tile + halo (origin -1)
-  uint8_t* sG = smem;
-  uint8_t* sX = smem + (size_t)GH * GW * 128;
   const int ITH = s * TH, ITW = s * TW;     // owned input tile
   const int logITW = logTW + (s == 2 ? 1 : 0);
+  const int set_bytes = (GMODE == CVB_A_BNB ? 2 : 1) * g_bytes + x_bytes;
+  const uint32_t tx_bytes = (uint32_t)(GMODE == CVB_A_BNB ? 2 : 1) * GH * GW * 128 + (uint32_t)XH * XW * 128;
+  const int n_img = (p.B - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int gh_base = oh0 - go, gw_base = ow0 - go;
+  const int xh_base = s * oh0 - 1, xw_base = s * ow0 - 1;
+
+  auto issue = [&](int i) {  // one elected thread
+    uint8_t* base = smem + (i & 1) * set_bytes;
+    const int b = (int)blockIdx.z + i * (int)gridDim.z;
+    mbar_expect_tx(&bar[i & 1], tx_bytes);
+    tma_load_4d(base, &tmDZ, &bar[i & 1], c0, gw_base, gh_base, b);
+    if (GMODE == CVB_A_BNB) tma_load_4d(base + g_bytes, &tmY2, &bar[i & 1], c0, gw_base, gh_base, b);
+    tma_load_4d(base + (GMODE == CVB_A_BNB ? 2 : 1) * g_bytes, &tmX, &bar[i & 1], c0, xw_base, xh_base, b);
+  };
+
+  for (int i = tid; i < 9 * CB; i += NTB) (&s_dw[0][0])[i] = 0.f;
+  if (tid < CB) { s_cs[tid] = 0.f; s_cq[tid] = 0.f; }
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < 2 && i < n_img; ++i) issue(i);
+  }
 
   const int cgi = tid & 7, pt = tid >> 3;   // phase B role
   const int cc = c0 + cgi * 8;
   const bool cc_ok = cc < p.C;
   const int cp = lane, ps = warp;           // phase A role: channels c0 + 2cp, +1 ; pixel slice = warp
-
-  for (int i = tid; i < 9 * CB; i += NT) (&s_dw[0][0])[i] = 0.f;
-  if (tid < CB) { s_cs[tid] = 0.f; s_cq[tid] = 0.f; }
+  const int pch = lane & 7;                 // transform role: physical 16-byte chunk
 
   float accw[9][2];
 #pragma unroll
@@ -198,99 +230,36 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(const cvb_dw_bwd_args p, 
     for (int j = 0; j < 4; ++j)
       wpk[tp][j] = cc_ok ? pack_bf162(p.Wt[tp * p.C + cc + 2 * j], p.Wt[tp * p.C + cc + 2 * j + 1]) : 0u;
 
-  // loader role (chunk = lane & 7)
-  const int lch = lane & 7;
-  const int lc = c0 + lch * 8;
-  const bool lc_ok = lc < p.C;
-
-  for (int b = blockIdx.z; b < p.B; b += gridDim.z) {
-    const bf16* __restrict__ DZ = static_cast<const bf16*>(p.DZ) + (size_t)b * Ho * Wo * p.C;
-    const bf16* __restrict__ Y2 = (GMODE == CVB_A_BNB) ? static_cast<const bf16*>(p.Y2) + (size_t)b * Ho * Wo * p.C : nullptr;
-    const bf16* __restrict__ X = static_cast<const bf16*>(p.X) + (size_t)b * p.H * p.W * p.C;
+  for (int i = 0; i < n_img; ++i) {
+    const int b = (int)blockIdx.z + i * (int)gridDim.z;
+    uint8_t* sG = smem + (i & 1) * set_bytes;
+    uint8_t* sG2 = sG + g_bytes;
+    uint8_t* sX = sG + (GMODE == CVB_A_BNB ? 2 : 1) * g_bytes;
     bf16* __restrict__ DX = static_cast<bf16*>(p.DX) + (size_t)b * p.H * p.W * p.C;
-    __syncthreads();  // previous iteration done with smem
-    // ---- stage dy tile (per-channel coefficients scoped here to keep them out of the stencil's live range)
-    {
-      float g0[8], g1[8], g2[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        g0[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p0[lc + j] : 1.f;
-        g1[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p1[lc + j] : 0.f;
-        g2[j] = (GMODE == CVB_A_BNB && lc_ok) ? p.g_p2[lc + j] : 0.f;
-      }
-      for (int gi = warp; gi < GH; gi += NT / 32) {
-        const int oh = oh0 - go + gi;
-        const bool h_ok = oh >= 0 && oh < Ho;
+    mbar_wait(&bar[i & 1], (i >> 1) & 1);
+    // ---- 1. dy = c1*dz + c2*y2 + c3, in place, in-bounds pixels only (the zero-filled halo must stay zero)
+    if (GMODE == CVB_A_BNB) {
+      for (int gi = warp; gi < GH; gi += NTB / 32) {
+        const int oh = gh_base + gi;
+        if (oh < 0 || oh >= Ho) continue;
         for (int gj = lane >> 3; gj < GW; gj += 4) {
-          const int ow = ow0 - go + gj;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (h_ok && lc_ok && ow >= 0 && ow < Wo) {
-            float f[8];
-            const size_t off = ((size_t)oh * Wo + ow) * p.C + lc;
-            const uint4 rz = ldg16(DZ + off);
-            if (GMODE == CVB_A_BNB) {
-              float y[8];
-              unpack8(ldg16(Y2 + off), y);
-              unpack8(rz, f);
+          const int ow = gw_base + gj;
+          const int pix = gi * GW + gj;
+          const int lc = c0 + ((pch ^ (pix & 7)) << 3);
+          if (ow < 0 || ow >= Wo || lc >= p.C) continue;
+          uint4* pz = reinterpret_cast<uint4*>(sG + pix * 128 + (pch << 4));
+          float f[8], y[8];
+          unpack8(*pz, f);
+          unpack8(*reinterpret_cast<const uint4*>(sG2 + pix * 128 + (pch << 4)), y);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
-              v = pack8(f);
-            } else {
-              v = rz;
-            }
-          }
-          *reinterpret_cast<uint4*>(sG + pix_off(gi * GW + gj, lch)) = v;
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(__ldg(p.g_p0 + lc + j), f[j], fmaf(__ldg(p.g_p1 + lc + j), y[j], __ldg(p.g_p2 + lc + j)));
+          *pz = pack8(f);
         }
       }
+      __syncthreads();
     }
-    // ---- stage transformed input tile (+halo)
-    {
-      const int h_base = s * oh0 - 1, w_base = s * ow0 - 1;
-      float x0[8], x1[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        x0[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p0[lc + j] : 1.f;
-        x1[j] = (XMODE != CVB_A_RAW && lc_ok) ? p.x_p1[lc + j] : 0.f;
-      }
-      for (int ih = warp; ih < XH; ih += NT / 32) {
-        const int h = h_base + ih;
-        const bool h_ok = h >= 0 && h < p.H;
-        for (int jw = lane >> 3; jw < XW; jw += 4) {
-          const int w = w_base + jw;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (h_ok && lc_ok && w >= 0 && w < p.W) {
-            if (XMODE == CVB_A_RAW) {
-              v = ldg16(X + ((size_t)h * p.W + w) * p.C + lc);
-            } else {
-              float f[8];
-              load8_mode(XMODE, X + ((size_t)h * p.W + w) * p.C + lc, x0, x1, f);
-              v = pack8(f);
-            }
-          }
-          *reinterpret_cast<uint4*>(sX + pix_off(ih * XW + jw, lch)) = v;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- A: weight gradient partials  dW[u,v] += dy[oh,ow] * a[s*oh+u-1, s*ow+v-1]   (4-byte = 2-channel smem accesses)
-    {
-      const uint32_t sub = static_cast<uint32_t>((cp & 3) << 2);
-      const int chk = cp >> 2;
-      for (int op = ps; op < TH * TW; op += NT / 32) {
-        const int oh = op >> logTW, ow = op & (TW - 1);
-        const float2 dy = unpack_bf162(*reinterpret_cast<const uint32_t*>(sG + pix_off((oh + go) * GW + ow + go, chk) + sub));
-#pragma unroll
-        for (int u = 0; u < 3; ++u)
-#pragma unroll
-          for (int v = 0; v < 3; ++v) {
-            const float2 a = unpack_bf162(*reinterpret_cast<const uint32_t*>(sX + pix_off((s * oh + u) * XW + s * ow + v, chk) + sub));
-            accw[u * 3 + v][0] = fmaf(dy.x, a.x, accw[u * 3 + v][0]);
-            accw[u * 3 + v][1] = fmaf(dy.y, a.y, accw[u * 3 + v][1]);
-          }
-      }
-    }
-    // ---- B: input gradient  da[h,w] = sum_{u,v} W[u,v] * dy[(h+1-u)/s, (w+1-v)/s]
-    for (int ip = pt; ip < ITH * ITW; ip += NT / 8) {
+    // ---- 2. phase B: input gradient  da[h,w] = sum_{u,v} W[u,v] * dy[(h+1-u)/s, (w+1-v)/s]
+    for (int ip = pt; ip < ITH * ITW; ip += NTB / 8) {
       const int ih = ip >> logITW, iw = ip & (ITW - 1);
       const int h = s * oh0 + ih, w = s * ow0 + iw;
       if (h < p.H && w < p.W && cc_ok) {
@@ -317,10 +286,9 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(const cvb_dw_bwd_args p, 
             }
           }
         }
-        const size_t off = ((size_t)h * p.W + w) * p.C + cc;
         if (XMODE != CVB_A_RAW) {
-          float xr[8];
-          unpack8(ldg16(X + off), xr);
+          float xr[8];  // raw x of this pixel from the (not yet transformed) smem tile
+          unpack8(*reinterpret_cast<const uint4*>(sX + pix_off((ih + 1) * XW + iw + 1, cgi)), xr);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (XMODE == CVB_A_AFF_SILU) da[j] *= silu_grad_f(fmaf(__ldg(p.x_p0 + cc + j), xr[j], __ldg(p.x_p1 + cc + j)));
@@ -329,8 +297,53 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(const cvb_dw_bwd_args p, 
             cq[j] += da[j] * xr[j];
           }
         }
-        stg16(DX + off, pack8(da));
+        stg16(DX + ((size_t)h * p.W + w) * p.C + cc, pack8(da));
       }
+    }
+    // ---- 3. a = act(BN(x)) in place (in-bounds only), then phase A
+    if (XMODE != CVB_A_RAW) {
+      __syncthreads();  // phase B has read the raw x tile
+      for (int ih = warp; ih < XH; ih += NTB / 32) {
+        const int h = xh_base + ih;
+        if (h < 0 || h >= p.H) continue;
+        for (int jw = lane >> 3; jw < XW; jw += 4) {
+          const int w = xw_base + jw;
+          const int pix = ih * XW + jw;
+          const int lc = c0 + ((pch ^ (pix & 7)) << 3);
+          if (w < 0 || w >= p.W || lc >= p.C) continue;
+          uint4* px = reinterpret_cast<uint4*>(sX + pix * 128 + (pch << 4));
+          float f[8];
+          unpack8(*px, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float z = fmaf(__ldg(p.x_p0 + lc + j), f[j], __ldg(p.x_p1 + lc + j));
+            f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
+          }
+          *px = pack8(f);
+        }
+      }
+      __syncthreads();
+    }
+    {
+      const uint32_t sub = static_cast<uint32_t>((cp & 3) << 2);
+      const int chk = cp >> 2;
+      for (int op = ps; op < TH * TW; op += NTB / 32) {
+        const int oh = op >> logTW, ow = op & (TW - 1);
+        const float2 dy = unpack_bf162(*reinterpret_cast<const uint32_t*>(sG + pix_off((oh + go) * GW + ow + go, chk) + sub));
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            const float2 a = unpack_bf162(*reinterpret_cast<const uint32_t*>(sX + pix_off((s * oh + u) * XW + s * ow + v, chk) + sub));
+            accw[u * 3 + v][0] = fmaf(dy.x, a.x, accw[u * 3 + v][0]);
+            accw[u * 3 + v][1] = fmaf(dy.y, a.y, accw[u * 3 + v][1]);
+          }
+      }
+    }
+    __syncthreads();  // every thread is done with this buffer set
+    if (tid == 0 && i + 2 < n_img) {
+      fence_proxy_async();
+      issue(i + 2);
     }
   }
 
@@ -350,7 +363,7 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(const cvb_dw_bwd_args p, 
     }
   }
   __syncthreads();
-  for (int i = tid; i < 9 * CB; i += NT) {
+  for (int i = tid; i < 9 * CB; i += NTB) {
     int tp = i / CB, c = i % CB;
     if (c0 + c < p.C) atomicAdd(p.dWt + tp * p.C + c0 + c, s_dw[tp][c]);
   }
@@ -413,7 +426,7 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   const cvb_dw_bwd_args& a = *args;
   CVB_CHECK(a.B > 0 && a.H > 0 && a.W > 0 && a.C > 0 && a.C % 8 == 0, "cvb_dw_bwd: bad shape");
   CVB_CHECK(a.stride == 1 || a.stride == 2, "cvb_dw_bwd: stride must be 1 or 2");
-  CVB_CHECK(a.DZ && a.X && a.Wt && a.DX && a.dWt, "cvb_dw_bwd: null operand");
+  CVB_CHECK(a.DZ && a.X && a.Wt && a.DX && a.dWt && cvb_aligned16(a.DZ) && cvb_aligned16(a.X) && cvb_aligned16(a.DX), "cvb_dw_bwd: null / misaligned operand");
   CVB_CHECK(a.g_mode == CVB_A_RAW || (a.g_mode == CVB_A_BNB && a.Y2 && a.g_p0 && a.g_p1 && a.g_p2), "cvb_dw_bwd: bad g_mode %d", a.g_mode);
   CVB_CHECK(a.x_mode == CVB_A_RAW || ((a.x_mode == CVB_A_AFF || a.x_mode == CVB_A_AFF_SILU) && a.x_p0 && a.x_p1), "cvb_dw_bwd: bad x_mode %d", a.x_mode);
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_dw_bwd: col_sq missing");
@@ -424,21 +437,27 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   const int tiles_h = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
   const int GH = TH + (s == 1 ? 2 : 1), GW = TW + (s == 1 ? 2 : 1);
   const int XH = s * TH + 3 - s, XW = s * TW + 3 - s;
-  size_t smem = ((size_t)GH * GW + (size_t)XH * XW) * 128;
+  const int g_bytes = (GH * GW * 128 + 1023) / 1024 * 1024, x_bytes = (XH * XW * 128 + 1023) / 1024 * 1024;
+  const int nG = (a.g_mode == CVB_A_BNB) ? 2 : 1;
+  size_t smem = (size_t)2 * (nG * g_bytes + x_bytes) + 1024;
   const int cblocks = (a.C + CB - 1) / CB;
-  // batch loop inside the CTA keeps the number of dW atomics bounded: aim for ~8 CTAs per SM in flight
+  // batch loop inside the CTA (double-buffered TMA, dW / statistics flushed once): one CTA per SM, a few waves
   int per_img = tiles_h * tiles_w * cblocks;
-  int want = 8 * cvb_num_sms();
-  int gz = (want + per_img - 1) / per_img;  // >= 2 resident CTAs per SM x 4 waves
+  int want = 4 * cvb_num_sms();
+  int gz = (want + per_img - 1) / per_img;
   if (gz > a.B) gz = a.B;
   if (gz < 1) gz = 1;
   dim3 grid(tiles_h * tiles_w, cblocks, gz);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap tmDZ, tmY2, tmX;
+  if (cvb_make_tmap_nhwc(&tmDZ, a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB)) return 1;
+  if (cvb_make_tmap_nhwc(&tmY2, a.g_mode == CVB_A_BNB ? a.Y2 : a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB)) return 1;
+  if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, XH, XW, CB)) return 1;
 #define CVB_DW_BWD(GM, XM)                                                                                                \
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
-    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; } \
-    dw_bwd_kernel<GM, XM><<<grid, NT, smem, st>>>(a, Ho, Wo, TH, TW, ilog2(TW), tiles_w);                                \
+    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
+    dw_bwd_kernel<GM, XM><<<grid, NTB, smem, st>>>(tmDZ, tmY2, tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, g_bytes, x_bytes);   \
   }
   if (a.g_mode == CVB_A_RAW) {
     if (a.x_mode == CVB_A_RAW) CVB_DW_BWD(CVB_A_RAW, CVB_A_RAW)

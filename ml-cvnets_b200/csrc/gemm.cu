@@ -27,6 +27,14 @@ struct GemmCfg {
   static constexpr int kStages = (AMODE == CVB_A_BNB) ? 3 : 4;
 };
 
+// The kernel is INSTRUCTION-ISSUE bound, not tensor bound (ncu, profiles/): K <= 768 gives few MMAs per output element, so the
+// design minimises issued instructions per tile:
+//   * prologue (BN+SiLU / GroupNorm / BN-backward) is applied ONCE per element, in place in shared memory, by the thread that
+//     cp.async'ed the chunk (one k-tile ahead of the MMAs; no redundancy across the N-warps);
+//   * the epilogue works on the accumulator fragments directly (bias, activation(-backward), residual, statistics), exchanges
+//     only bf16 through a padded staging tile (aux tensor in, result out, in place) and copies out with 16-byte row-contiguous
+//     stores;
+//   * one cp.async ring runs across ALL tiles of the persistent CTA, so the loads of the next tiles overlap the epilogue.
 template <int WM, int AMODE>
 __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_args p) {
   constexpr int WARPS_M = BM / WM;
@@ -37,8 +45,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
   constexpr int NST = GemmCfg<AMODE>::kStages;
   constexpr int A_STAGE = BM * BK * 2;
   constexpr int B_STAGE = BN * BK * 2;
-  constexpr int LDC_S = BN + 4;      // fp32 staging row stride
-  constexpr int HALF = BM / 2;       // the epilogue stages the tile in two 64-row halves
+  constexpr int LDO = BN + 8;        // bf16 staging row stride (+16 B: conflict-free fragment access)
+  constexpr int CGS = BN / 8;        // 16-byte column groups per row
   constexpr bool HAS_P = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN || AMODE == CVB_A_BNB);
 
   extern __shared__ __align__(128) uint8_t smem[];
@@ -46,12 +54,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
   uint8_t* sA2 = smem + NST * A_STAGE;
   uint8_t* sB = smem + (TWO_A ? 2 : 1) * NST * A_STAGE;
   constexpr int PIPE_BYTES = (TWO_A ? 2 : 1) * NST * A_STAGE + NST * B_STAGE;
-  float* sC = reinterpret_cast<float*>(smem + PIPE_BYTES);                      // NOT overlaid: loads of the next tiles stay in flight
-  float* sP = reinterpret_cast<float*>(smem + PIPE_BYTES + HALF * LDC_S * 4);   // prologue parameters
+  uint8_t* sO = smem + PIPE_BYTES;                                          // bf16 [BM][LDO] aux-in / result-out staging
+  float* sP = reinterpret_cast<float*>(smem + PIPE_BYTES + BM * LDO * 2);   // prologue parameters
   __shared__ float s_col[2][128];
   __shared__ double s_samp[2][128];  // fp64: cross-thread order must not change the GroupNorm statistics
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int wm0 = (warp / WARPS_N) * WM;
   const int wn0 = (warp % WARPS_N) * 32;
   const int n0 = blockIdx.x * BN;
@@ -62,7 +71,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
   const int total = my_tiles * KT;  // flattened (tile, k-tile) iterations of this CTA
 
   if (tid < 128) { s_col[0][tid] = 0.f; s_col[1][tid] = 0.f; s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
-  if (HAS_P) {  // per-K prologue parameters -> smem (zero padded so that the K tail transforms to finite values)
+  if (HAS_P) {  // per-K prologue parameters -> smem (zero padded so that the K tail transforms to zero)
     for (int k = tid; k < Kpad; k += NTHREADS) {
       bool ok = k < p.K;
       sP[k] = ok ? p.a_p0[k] : 0.f;
@@ -74,20 +83,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
   const bf16* __restrict__ A = static_cast<const bf16*>(p.A);
   const bf16* __restrict__ A2 = static_cast<const bf16*>(p.A2);
   const bf16* __restrict__ Wg = static_cast<const bf16*>(p.W);
-
-  // epilogue thread mapping (fixed per thread across tiles): 8 consecutive columns of one row
-  constexpr int CGS = BN / 8;
-  constexpr int ROWS_PER_PASS = NTHREADS / CGS;
-  const int cg = tid % CGS, r0 = tid / CGS;
-  const int nc = n0 + cg * 8;
-  const bool col_ok = nc < p.N;
   const int emode = p.e_mode;
   const bool want_col = p.col_sum != nullptr;
   const bool want_samp = p.samp_sum != nullptr;
   const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
-  const bf16* __restrict__ Yg = static_cast<const bf16*>(p.Y);
-  const bf16* __restrict__ Rg = static_cast<const bf16*>(p.R);
-  float cs[8], cq[8];  // per-column statistics, accumulated over all tiles of this CTA, flushed once
+  // at most one auxiliary [M, N] tensor: Y (activation / GroupNorm backward) or the residual R
+  const bf16* __restrict__ AUX = static_cast<const bf16*>(emode >= CVB_E_SILU_BWD ? p.Y : p.R);
+  const int ldaux = emode >= CVB_E_SILU_BWD ? p.ldy : p.ldr;
+  const bool has_aux = AUX != nullptr;
+
+  float cs[8], cq[8];  // per-column statistics (columns wn0 + ni*8 + 2t + e), accumulated over all tiles, flushed once
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
 
@@ -113,29 +118,85 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
       cp_async16(smem_u32(sB + stage * B_STAGE) + swz64(row, ch), Wg + (ok ? (size_t)n * p.ldw + k : 0), ok);
     }
   };
+  auto issue_aux = [&](int jt) {  // aux tile of tile jt -> staging buffer (16-byte, row-contiguous)
+    const int m0i = ((int)blockIdx.y + jt * (int)gridDim.y) * BM;
+    for (int c = tid; c < BM * CGS; c += NTHREADS) {
+      int row = c / CGS, cgc = c % CGS;
+      int m = m0i + row, n = n0 + cgc * 8;
+      bool ok = (m < p.M) && (n < p.N);
+      cp_async16(smem_u32(sO + row * (LDO * 2) + cgc * 16), AUX + (ok ? (size_t)m * ldaux + n : 0), ok);
+    }
+  };
+  // in-place prologue of the chunks THIS thread loaded (rows tid>>2 and 64 + tid>>2), one k-tile ahead of the MMAs
+  float tmu[2] = {0.f, 0.f}, trs[2] = {1.f, 1.f};
+  auto transform = [&](int it) {
+    if (AMODE == CVB_A_RAW) return;
+    const int stage = it % NST;
+    const int j = it / KT, kt = it - j * KT;
+    const int k0 = kt * BK;
+    if (AMODE == CVB_A_GN && kt == 0) {
+      const int m0i = ((int)blockIdx.y + j * (int)gridDim.y) * BM;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        int m = m0i + (tid >> 2) + i * 64;
+        int b = (m < p.M ? m : p.M - 1) / p.rows_per_sample;
+        tmu[i] = __ldg(p.row_mean + b);
+        trs[i] = __ldg(p.row_rstd + b);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid + i * NTHREADS;
+      const int row = c >> 2, ch = c & 3;
+      const int k = k0 + ch * 8;
+      uint4* pa = reinterpret_cast<uint4*>(sA + stage * A_STAGE + swz64(row, ch));
+      float f[8];
+      unpack8(*pa, f);
+      float q0[8], q1[8];
+      if (HAS_P) {
+        *reinterpret_cast<float4*>(q0) = *reinterpret_cast<const float4*>(sP + k);
+        *reinterpret_cast<float4*>(q0 + 4) = *reinterpret_cast<const float4*>(sP + k + 4);
+        *reinterpret_cast<float4*>(q1) = *reinterpret_cast<const float4*>(sP + Kpad + k);
+        *reinterpret_cast<float4*>(q1 + 4) = *reinterpret_cast<const float4*>(sP + Kpad + k + 4);
+      }
+      if (AMODE == CVB_A_AFF) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(q0[e], f[e], q1[e]);
+      } else if (AMODE == CVB_A_AFF_SILU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = silu_f(fmaf(q0[e], f[e], q1[e]));
+      } else if (AMODE == CVB_A_SILU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+      } else if (AMODE == CVB_A_GN) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf((f[e] - tmu[i]) * trs[i], q0[e], q1[e]);
+      } else {  // BNB: c1*dz + c2*y + c3
+        float y[8], q2[8];
+        unpack8(*reinterpret_cast<const uint4*>(sA2 + stage * A_STAGE + swz64(row, ch)), y);
+        *reinterpret_cast<float4*>(q2) = *reinterpret_cast<const float4*>(sP + 2 * Kpad + k);
+        *reinterpret_cast<float4*>(q2 + 4) = *reinterpret_cast<const float4*>(sP + 2 * Kpad + k + 4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = fmaf(q0[e], f[e], fmaf(q1[e], y[e], q2[e]));
+      }
+      *pa = pack8(f);
+    }
+  };
 
+  // ---- prologue of the pipeline
+  if (has_aux && my_tiles > 0) issue_aux(0);
 #pragma unroll
   for (int s = 0; s < NST - 1; ++s) {
     if (s < total) issue(s);
     cp_async_commit();
   }
+  cp_async_wait<NST - 2>();  // this thread's chunks of stage 0 (and the parameters written above) ...
+  __syncthreads();           // ... sP visible to everyone
+  if (total > 0) transform(0);
 
   int it = 0;
   for (int jt = 0; jt < my_tiles; ++jt) {
     const int m0 = ((int)blockIdx.y + jt * (int)gridDim.y) * BM;
-    // GroupNorm prologue: per-row statistics of the rows this thread's fragments touch
-    float rmean[MI][2], rrstd[MI][2];
-    if (AMODE == CVB_A_GN) {
-#pragma unroll
-      for (int mi = 0; mi < MI; ++mi)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          int m = m0 + wm0 + mi * 16 + (lane >> 2) + h * 8;
-          int b = (m < p.M ? m : p.M - 1) / p.rows_per_sample;
-          rmean[mi][h] = p.row_mean[b];
-          rrstd[mi][h] = p.row_rstd[b];
-        }
-    }
     float acc[MI][4][4];
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi)
@@ -145,62 +206,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
         for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
 
     for (int kt = 0; kt < KT; ++kt, ++it) {
-      cp_async_wait<NST - 2>();
-      __syncthreads();
+      cp_async_wait<NST - 3>();  // stage it+1 has landed (for this thread's own chunks)
+      __syncthreads();           // transform(it) visible; everyone's stage it+1 landed; MMAs of it-1 done -> its slot is free
       {
         int nxt = it + NST - 1;
         if (nxt < total) issue(nxt);
         cp_async_commit();
       }
+      if (it + 1 < total) transform(it + 1);
       const int stage = it % NST;
       const uint32_t aBase = smem_u32(sA + stage * A_STAGE);
-      const uint32_t a2Base = smem_u32(sA2 + stage * A_STAGE);
       const uint32_t bBase = smem_u32(sB + stage * B_STAGE);
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        // prologue parameters of the 4 k-columns this thread's A registers cover: k, k+1, k+8, k+9
-        float q0[4], q1[4], q2[4];
-        if (HAS_P) {
-          int kq = kt * BK + ks * 16 + 2 * (lane & 3);
-          q0[0] = sP[kq]; q0[1] = sP[kq + 1]; q0[2] = sP[kq + 8]; q0[3] = sP[kq + 9];
-          q1[0] = sP[Kpad + kq]; q1[1] = sP[Kpad + kq + 1]; q1[2] = sP[Kpad + kq + 8]; q1[3] = sP[Kpad + kq + 9];
-          if (AMODE == CVB_A_BNB) {
-            q2[0] = sP[2 * Kpad + kq]; q2[1] = sP[2 * Kpad + kq + 1]; q2[2] = sP[2 * Kpad + kq + 8]; q2[3] = sP[2 * Kpad + kq + 9];
-          }
-        }
         uint32_t af[MI][4];
 #pragma unroll
         for (int mi = 0; mi < MI; ++mi) {
           int row = wm0 + mi * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
           int ch = ks * 2 + (lane >> 4);
           ldmatrix_x4(aBase + swz64(row, ch), af[mi][0], af[mi][1], af[mi][2], af[mi][3]);
-          if (AMODE != CVB_A_RAW) {
-            uint32_t a2f[4] = {0, 0, 0, 0};
-            if (TWO_A) ldmatrix_x4(a2Base + swz64(row, ch), a2f[0], a2f[1], a2f[2], a2f[3]);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              // r: 0 (row g, k lo) 1 (row g+8, k lo) 2 (row g, k hi) 3 (row g+8, k hi)
-              const int kk = (r >> 1) * 2;  // index into q*: lo pair -> 0,1 ; hi pair -> 2,3
-              const int h = r & 1;          // row half
-              float2 x = unpack_bf162(af[mi][r]);
-              float y0, y1;
-              if (AMODE == CVB_A_AFF) {
-                y0 = fmaf(q0[kk], x.x, q1[kk]); y1 = fmaf(q0[kk + 1], x.y, q1[kk + 1]);
-              } else if (AMODE == CVB_A_AFF_SILU) {
-                y0 = silu_f(fmaf(q0[kk], x.x, q1[kk])); y1 = silu_f(fmaf(q0[kk + 1], x.y, q1[kk + 1]));
-              } else if (AMODE == CVB_A_SILU) {
-                y0 = silu_f(x.x); y1 = silu_f(x.y);
-              } else if (AMODE == CVB_A_GN) {
-                float xm0 = (x.x - rmean[mi][h]) * rrstd[mi][h], xm1 = (x.y - rmean[mi][h]) * rrstd[mi][h];
-                y0 = fmaf(xm0, q0[kk], q1[kk]); y1 = fmaf(xm1, q0[kk + 1], q1[kk + 1]);
-              } else {  // BNB
-                float2 x2 = unpack_bf162(a2f[r]);
-                y0 = fmaf(q0[kk], x.x, fmaf(q1[kk], x2.x, q2[kk]));
-                y1 = fmaf(q0[kk + 1], x.y, fmaf(q1[kk + 1], x2.y, q2[kk + 1]));
-              }
-              af[mi][r] = pack_bf162(y0, y1);
-            }
-          }
         }
         uint32_t bfr[4][2];
 #pragma unroll
@@ -216,131 +240,123 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
       }
     }
 
-    // ---------------------------------------------------------------- epilogue: two 64-row halves through the fp32 staging tile
-    const int first_sample = m0 / rps;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      __syncthreads();  // staging tile free (previous half / previous tile fully consumed)
-      if (wm0 / HALF == half) {
-#pragma unroll
-        for (int mi = 0; mi < MI; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) {
-            int r = (wm0 % HALF) + mi * 16 + (lane >> 2);
-            int c = wn0 + ni * 8 + 2 * (lane & 3);
-            *reinterpret_cast<float2*>(&sC[r * LDC_S + c]) = make_float2(acc[mi][ni][0], acc[mi][ni][1]);
-            *reinterpret_cast<float2*>(&sC[(r + 8) * LDC_S + c]) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
-          }
-      }
+    // ------------------------------------------------------------------ epilogue on the accumulator fragments
+    if (has_aux) {
+      cp_async_wait<0>();  // the aux tile of this tile (issued after the previous copy-out) has landed
       __syncthreads();
-      // per-column epilogue vectors are (re)loaded here (L1 hits) instead of living in registers across the main loop
-      float bias8[8], ep0[8], ep1[8];
+    }
+    const int first_sample = m0 / rps;
+    float bias2[4][2], ep0[4][2], ep1[4][2];
+    bool ncol_ok[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        bias8[j] = (col_ok && p.bias) ? __ldg(p.bias + nc + j) : 0.f;
-        ep0[j] = (col_ok && p.e_p0) ? __ldg(p.e_p0 + nc + j) : 1.f;
-        ep1[j] = (col_ok && p.e_p1) ? __ldg(p.e_p1 + nc + j) : 0.f;
+    for (int ni = 0; ni < 4; ++ni) {
+      const int n = n0 + wn0 + ni * 8 + 2 * t;
+      ncol_ok[ni] = n < p.N;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        bias2[ni][e] = (ncol_ok[ni] && p.bias) ? __ldg(p.bias + n + e) : 0.f;
+        ep0[ni][e] = (ncol_ok[ni] && p.e_p0) ? __ldg(p.e_p0 + n + e) : 1.f;
+        ep1[ni][e] = (ncol_ok[ni] && p.e_p1) ? __ldg(p.e_p1 + n + e) : 0.f;
       }
-      for (int r = r0; r < HALF; r += ROWS_PER_PASS) {
-        const int m = m0 + half * HALF + r;
-        const bool valid = col_ok && (m < p.M);
+    }
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = wm0 + mi * 16 + g + h * 8;
+        const int m = m0 + row;
+        const bool row_ok = m < p.M;
+        float mu = 0.f, rs = 1.f;
+        if (emode == CVB_E_GN_BWD) {
+          const int b = (row_ok ? m : p.M - 1) / rps;
+          mu = __ldg(p.row_mean + b);
+          rs = __ldg(p.row_rstd + b);
+        }
         float ssum = 0.f, ssq = 0.f;
-        if (valid) {
-          float v[8];
-          float4 t0 = *reinterpret_cast<const float4*>(&sC[r * LDC_S + cg * 8]);
-          float4 t1 = *reinterpret_cast<const float4*>(&sC[r * LDC_S + cg * 8 + 4]);
-          v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += bias8[j];
-          float y8[8];
+        for (int ni = 0; ni < 4; ++ni) {
+          uint32_t* po = reinterpret_cast<uint32_t*>(sO + row * (LDO * 2) + (wn0 + ni * 8 + 2 * t) * 2);
+          float v0 = acc[mi][ni][2 * h] + bias2[ni][0], v1 = acc[mi][ni][2 * h + 1] + bias2[ni][1];
+          float y0 = 0.f, y1 = 0.f;
+          if (has_aux) { float2 a2 = unpack_bf162(*po); y0 = a2.x; y1 = a2.y; }
+          const bool ok = row_ok && ncol_ok[ni];
           if (emode == CVB_E_SILU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+            v0 = silu_f(v0); v1 = silu_f(v1);
           } else if (emode == CVB_E_SILU_BWD) {
-            unpack8(ldg16(Yg + (size_t)m * p.ldy + nc), y8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= silu_grad_f(fmaf(ep0[j], y8[j], ep1[j]));
+            v0 *= silu_grad_f(fmaf(ep0[ni][0], y0, ep1[ni][0]));
+            v1 *= silu_grad_f(fmaf(ep0[ni][1], y1, ep1[ni][1]));
           } else if (emode == CVB_E_GN_BWD) {
-            unpack8(ldg16(Yg + (size_t)m * p.ldy + nc), y8);
-            const int b = m / rps;
-            const float mu = p.row_mean[b], rs = p.row_rstd[b];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              y8[j] = (y8[j] - mu) * rs;  // x-hat
-              cs[j] += v[j];
-              cq[j] += v[j] * y8[j];
-              v[j] *= ep0[j];
+            y0 = (y0 - mu) * rs; y1 = (y1 - mu) * rs;  // x-hat
+            if (ok) { cs[ni * 2] += v0; cs[ni * 2 + 1] += v1; cq[ni * 2] += v0 * y0; cq[ni * 2 + 1] += v1 * y1; }
+            v0 *= ep0[ni][0]; v1 *= ep0[ni][1];
+          } else if (has_aux) {  // residual
+            v0 += y0; v1 += y1;
+          }
+          const uint32_t pk = pack_bf162(v0, v1);
+          *po = pk;
+          if (ok) {
+            const float2 r = unpack_bf162(pk);  // statistics of the STORED (bf16) values
+            if (emode == CVB_E_STORE || emode == CVB_E_SILU) {
+              cs[ni * 2] += r.x; cs[ni * 2 + 1] += r.y; cq[ni * 2] += r.x * r.x; cq[ni * 2 + 1] += r.y * r.y;
+              ssum += r.x + r.y; ssq += r.x * r.x + r.y * r.y;
+            } else if (emode == CVB_E_SILU_BWD) {
+              cs[ni * 2] += r.x; cs[ni * 2 + 1] += r.y; cq[ni * 2] += r.x * y0; cq[ni * 2 + 1] += r.y * y1;
+            } else {
+              ssum += r.x + r.y; ssq += r.x * y0 + r.y * y1;
             }
-          }
-          if (Rg) {
-            float r8[8];
-            unpack8(ldg16(Rg + (size_t)m * p.ldr + nc), r8);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += r8[j];
-          }
-          if (p.c_fp32) {
-            float* Cg = static_cast<float*>(p.C) + (size_t)m * p.ldc + nc;
-            *reinterpret_cast<float4*>(Cg) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(Cg + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j]);
-            stg16(static_cast<bf16*>(p.C) + (size_t)m * p.ldc + nc, pack8(v));
-          }
-          if (emode == CVB_E_STORE || emode == CVB_E_SILU) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { cs[j] += v[j]; cq[j] += v[j] * v[j]; ssum += v[j]; ssq += v[j] * v[j]; }
-          } else if (emode == CVB_E_SILU_BWD) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { cs[j] += v[j]; cq[j] += v[j] * y8[j]; }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { ssum += v[j]; ssq += v[j] * y8[j]; }
           }
         }
         if (want_samp) {
-#pragma unroll
-          for (int o = CGS / 2; o > 0; o >>= 1) {
-            ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-            ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
-          }
-          if (cg == 0 && m < p.M) {
-            int bi = m / rps - first_sample;
+          ssum += __shfl_xor_sync(0xffffffffu, ssum, 1); ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+          ssq += __shfl_xor_sync(0xffffffffu, ssq, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
+          if (t == 0 && row_ok) {
+            const int bi = m / rps - first_sample;
             atomicAdd(&s_samp[0][bi], (double)ssum);
             atomicAdd(&s_samp[1][bi], (double)ssq);
           }
         }
       }
-    }
-    if (want_samp) {
-      __syncthreads();  // s_samp complete for this tile
-      if (tid < 128) {
-        int mlast = min(m0 + BM, p.M) - 1;
-        int nsamp = mlast / rps - first_sample + 1;
-        if (tid < nsamp) {
-          atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
-          atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
-          s_samp[0][tid] = 0.0;
-          s_samp[1][tid] = 0.0;
-        }
+    __syncthreads();  // staged result complete (and s_samp complete)
+    {
+      bf16* __restrict__ Cg = static_cast<bf16*>(p.C);
+      for (int c = tid; c < BM * CGS; c += NTHREADS) {
+        const int row = c / CGS, cgc = c % CGS;
+        const int m = m0 + row, n = n0 + cgc * 8;
+        if (m < p.M && n < p.N) stg16(Cg + (size_t)m * p.ldc + n, *reinterpret_cast<const uint4*>(sO + row * (LDO * 2) + cgc * 16));
       }
     }
+    if (want_samp && tid < 128) {
+      int mlast = min(m0 + BM, p.M) - 1;
+      int nsamp = mlast / rps - first_sample + 1;
+      if (tid < nsamp) {
+        atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
+        atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
+        s_samp[0][tid] = 0.0;
+        s_samp[1][tid] = 0.0;
+      }
+    }
+    if (has_aux) {
+      __syncthreads();  // copy-out finished: the staging tile may be overwritten by the next tile's aux operand
+      if (jt + 1 < my_tiles) issue_aux(jt + 1);  // joins the next cp.async group
+    }
+    // (without aux the next write to sO happens after >= 1 __syncthreads of the next tile's k-loop)
   }  // tile loop
   cp_async_wait<0>();
 
   if (want_col) {
-    // reduce over the lanes that share a column group (lane stride CGS), then one smem atomic per warp and column
+    // reduce over the 8 row-lanes (g) that share the columns, then one smem atomic per warp and column
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float a = cs[j], q = cq[j];
 #pragma unroll
-      for (int o = CGS; o < 32; o <<= 1) {
+      for (int o = 4; o < 32; o <<= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
         q += __shfl_xor_sync(0xffffffffu, q, o);
       }
-      if (lane < CGS) {
-        atomicAdd(&s_col[0][cg * 8 + j], a);
-        atomicAdd(&s_col[1][cg * 8 + j], q);
+      if (g == 0) {
+        const int col = wn0 + (j >> 1) * 8 + 2 * t + (j & 1);
+        atomicAdd(&s_col[0][col], a);
+        atomicAdd(&s_col[1][col], q);
       }
     }
     __syncthreads();
@@ -358,7 +374,7 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   constexpr int NST = GemmCfg<AMODE>::kStages;
   const int KT = (a.K + BK - 1) / BK;
   const int nvec = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
-  size_t smem = (size_t)NST * (BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1) + BN * BK * 2) + (size_t)(BM / 2) * (BN + 4) * 4 +
+  size_t smem = (size_t)NST * (BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1) + BN * BK * 2) + (size_t)BM * (BN + 8) * 2 +
                 (size_t)nvec * KT * BK * 4;
   static bool attr_set = false;
   if (!attr_set) {
@@ -398,13 +414,16 @@ __device__ __forceinline__ uint32_t swz128(int row, int ch) {  // 128-byte rows,
 }
 
 template <int GMODE, int AMODE>
-__global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const cvb_wgrad_args p, int m_per_cta) {
+__global__ void __launch_bounds__(NTHREADS, 2) pw_wgrad_kernel(const cvb_wgrad_args p, int m_per_cta) {
   constexpr bool TWO_G = (GMODE == CVB_A_BNB);
+  constexpr bool A_HAS_P = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN);
   constexpr int T_STAGE = WG_MB * 64 * 2;  // bytes per operand tile and stage
+  constexpr int NST = WG_STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sG = smem;
-  uint8_t* sG2 = smem + WG_STAGES * T_STAGE;
-  uint8_t* sA = smem + (TWO_G ? 2 : 1) * WG_STAGES * T_STAGE;
+  uint8_t* sG2 = smem + NST * T_STAGE;
+  uint8_t* sA = smem + (TWO_G ? 2 : 1) * NST * T_STAGE;
+  __shared__ float s_db[WG_TN];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -420,49 +439,78 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const cvb_wgrad_args
   const bf16* __restrict__ G = static_cast<const bf16*>(p.G);
   const bf16* __restrict__ G2 = static_cast<const bf16*>(p.G2);
   const bf16* __restrict__ A = static_cast<const bf16*>(p.A);
+  const bool want_db = (p.dbias != nullptr) && (blockIdx.x == 0);
+  if (tid < WG_TN) s_db[tid] = 0.f;
 
-  auto load_stage = [&](int s, int stage) {
+  // loader / transformer role: this thread owns chunk column `lch` (8 channels) of rows (tid>>3) + 32*i of every stage
+  const int lch = tid & 7;
+  const int ln = n0 + lch * 8, lk = k0 + lch * 8;
+  const bool ln_ok = ln < p.N, lk_ok = lk < p.K;
+  float gp0[8], gp1[8], gp2[8], ap0[8], ap1[8], db[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    gp0[e] = (TWO_G && ln_ok) ? __ldg(p.g_p0 + ln + e) : 1.f;
+    gp1[e] = (TWO_G && ln_ok) ? __ldg(p.g_p1 + ln + e) : 0.f;
+    gp2[e] = (TWO_G && ln_ok) ? __ldg(p.g_p2 + ln + e) : 0.f;
+    ap0[e] = (A_HAS_P && lk_ok) ? __ldg(p.a_p0 + lk + e) : 1.f;
+    ap1[e] = (A_HAS_P && lk_ok) ? __ldg(p.a_p1 + lk + e) : 0.f;
+    db[e] = 0.f;
+  }
+  const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
+
+  auto load_stage = [&](int s) {
+    const int stage = s % NST;
 #pragma unroll
     for (int i = 0; i < WG_MB / 32; ++i) {
-      const int row = (tid >> 3) + i * 32, ch = tid & 7;
+      const int row = (tid >> 3) + i * 32;
       const int m = m_begin + s * WG_MB + row;
-      {
-        int n = n0 + ch * 8;
-        bool ok = (m < m_end) && (n < p.N);
-        cp_async16(smem_u32(sG + stage * T_STAGE) + swz128(row, ch), G + (ok ? (size_t)m * p.ldg + n : 0), ok);
-        if (TWO_G) cp_async16(smem_u32(sG2 + stage * T_STAGE) + swz128(row, ch), G2 + (ok ? (size_t)m * p.ldg2 + n : 0), ok);
+      const bool okg = (m < m_end) && ln_ok, oka = (m < m_end) && lk_ok;
+      cp_async16(smem_u32(sG + stage * T_STAGE) + swz128(row, lch), G + (okg ? (size_t)m * p.ldg + ln : 0), okg);
+      if (TWO_G) cp_async16(smem_u32(sG2 + stage * T_STAGE) + swz128(row, lch), G2 + (okg ? (size_t)m * p.ldg2 + ln : 0), okg);
+      cp_async16(smem_u32(sA + stage * T_STAGE) + swz128(row, lch), A + (oka ? (size_t)m * p.lda + lk : 0), oka);
+    }
+  };
+  // in-place operand transforms of this thread's own chunks (once per element; the MMA warps then only ldmatrix + mma)
+  auto transform = [&](int s) {
+    const int stage = s % NST;
+#pragma unroll
+    for (int i = 0; i < WG_MB / 32; ++i) {
+      const int row = (tid >> 3) + i * 32;
+      const int m = m_begin + s * WG_MB + row;
+      const bool in = m < m_end;
+      if (TWO_G || want_db) {
+        uint4* pg = reinterpret_cast<uint4*>(sG + stage * T_STAGE + swz128(row, lch));
+        float f[8];
+        unpack8(*pg, f);
+        if (TWO_G) {
+          float y[8];
+          unpack8(*reinterpret_cast<const uint4*>(sG2 + stage * T_STAGE + swz128(row, lch)), y);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = in ? bf16_round(fmaf(gp0[e], f[e], fmaf(gp1[e], y[e], gp2[e]))) : 0.f;
+          *pg = pack8(f);
+        }
+        if (want_db) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) db[e] += f[e];  // rows beyond m_end are zero (zero fill / masked above)
+        }
       }
-      {
-        int k = k0 + ch * 8;
-        bool ok = (m < m_end) && (k < p.K);
-        cp_async16(smem_u32(sA + stage * T_STAGE) + swz128(row, ch), A + (ok ? (size_t)m * p.lda + k : 0), ok);
+      if (AMODE != CVB_A_RAW) {
+        uint4* pa = reinterpret_cast<uint4*>(sA + stage * T_STAGE + swz128(row, lch));
+        float f[8];
+        unpack8(*pa, f);
+        if (AMODE == CVB_A_GN) {
+          const int b = min(m, p.M - 1) / rps;
+          const float mu = __ldg(p.row_mean + b), rs = __ldg(p.row_rstd + b);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaf((f[e] - mu) * rs, ap0[e], ap1[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = apply_mode(AMODE, f[e], ap0[e], ap1[e]);
+        }
+        *pa = pack8(f);  // G' of the tail rows is zero, so garbage here cannot reach dW
       }
     }
   };
-
-  // per-n parameters (rows g, g+8 of the two m16 tiles) and per-k parameters (cols g of the two n8 tiles)
-  float gp0[2][2], gp1[2][2], gp2[2][2];
-#pragma unroll
-  for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int n = n0 + wn0 + ni * 16 + g + h * 8;
-      bool ok = TWO_G && n < p.N;
-      gp0[ni][h] = ok ? p.g_p0[n] : 0.f;
-      gp1[ni][h] = ok ? p.g_p1[n] : 0.f;
-      gp2[ni][h] = ok ? p.g_p2[n] : 0.f;
-    }
-  float ap0[2], ap1[2];
-#pragma unroll
-  for (int kj = 0; kj < 2; ++kj) {
-    int k = k0 + wk0 + kj * 8 + g;
-    bool ok = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) && k < p.K;
-    ap0[kj] = ok ? p.a_p0[k] : 0.f;
-    ap1[kj] = ok ? p.a_p1[k] : 0.f;
-  }
-  const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
-  const bool want_db = (p.dbias != nullptr) && (blockIdx.x == 0) && ((warp & 3) == 0);
-  float db[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 
   float acc[2][2][4];
 #pragma unroll
@@ -473,83 +521,37 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const cvb_wgrad_args
       for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
 
 #pragma unroll
-  for (int s = 0; s < WG_STAGES - 1; ++s) {
-    if (s < NS) load_stage(s, s);
+  for (int s = 0; s < NST - 1; ++s) {
+    if (s < NS) load_stage(s);
     cp_async_commit();
   }
+  cp_async_wait<NST - 2>();
+  transform(0);
   for (int s = 0; s < NS; ++s) {
-    cp_async_wait<WG_STAGES - 2>();
-    __syncthreads();
+    cp_async_wait<NST - 3>();  // own chunks of stage s+1 landed
+    __syncthreads();           // transform(s) visible; MMAs of s-1 done
     {
-      int ns = s + WG_STAGES - 1;
-      if (ns < NS) load_stage(ns, ns % WG_STAGES);
+      int ns = s + NST - 1;
+      if (ns < NS) load_stage(ns);
       cp_async_commit();
     }
-    const int stage = s % WG_STAGES;
-    const uint32_t gBase = smem_u32(sG + stage * T_STAGE), g2Base = smem_u32(sG2 + stage * T_STAGE);
-    const uint32_t aBase = smem_u32(sA + stage * T_STAGE);
-    const int ms0 = m_begin + s * WG_MB;
-    const bool tail = (ms0 + WG_MB > m_end);
+    if (s + 1 < NS) transform(s + 1);
+    const int stage = s % NST;
+    const uint32_t gBase = smem_u32(sG + stage * T_STAGE), aBase = smem_u32(sA + stage * T_STAGE);
 #pragma unroll
     for (int ms = 0; ms < WG_MB / 16; ++ms) {
-      // G' fragments (mma A operand: rows = n, cols = m), two m16 tiles
       uint32_t gf[2][4];
 #pragma unroll
       for (int ni = 0; ni < 2; ++ni) {
         int row = ms * 16 + (lane & 7) + (lane >> 4) * 8;
         int ch = (wn0 + ni * 16) / 8 + ((lane >> 3) & 1);
         ldmatrix_x4_trans(gBase + swz128(row, ch), gf[ni][0], gf[ni][1], gf[ni][2], gf[ni][3]);
-        if (TWO_G || tail || want_db) {
-          uint32_t g2f[4] = {0, 0, 0, 0};
-          if (TWO_G) ldmatrix_x4_trans(g2Base + swz128(row, ch), g2f[0], g2f[1], g2f[2], g2f[3]);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            // r: 0 (n g, m lo) 1 (n g+8, m lo) 2 (n g, m hi) 3 (n g+8, m hi)
-            const int h = r & 1;
-            float2 x = unpack_bf162(gf[ni][r]);
-            if (TWO_G) {
-              float2 x2 = unpack_bf162(g2f[r]);
-              x.x = fmaf(gp0[ni][h], x.x, fmaf(gp1[ni][h], x2.x, gp2[ni][h]));
-              x.y = fmaf(gp0[ni][h], x.y, fmaf(gp1[ni][h], x2.y, gp2[ni][h]));
-            }
-            if (tail) {
-              int mm = ms0 + ms * 16 + (r >> 1) * 8 + 2 * t;
-              if (mm >= m_end) x.x = 0.f;
-              if (mm + 1 >= m_end) x.y = 0.f;
-            }
-            uint32_t pk = pack_bf162(x.x, x.y);
-            gf[ni][r] = pk;
-            if (want_db) {
-              float2 xr = unpack_bf162(pk);
-              db[ni][h] += xr.x + xr.y;
-            }
-          }
-        }
       }
-      // A' fragments (mma B operand: k16 = m, n8 = k), two n8 tiles from one x4
       uint32_t af[4];
       {
         int row = ms * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
         int ch = wk0 / 8 + (lane >> 4);
         ldmatrix_x4_trans(aBase + swz128(row, ch), af[0], af[1], af[2], af[3]);
-        if (AMODE != CVB_A_RAW) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            // r: 0 (kj0, m lo) 1 (kj0, m hi) 2 (kj1, m lo) 3 (kj1, m hi); element pair = m 2t, 2t+1
-            const int kj = r >> 1;
-            float2 x = unpack_bf162(af[r]);
-            if (AMODE == CVB_A_GN) {
-              int mm = ms0 + ms * 16 + (r & 1) * 8 + 2 * t;
-              int b0 = min(mm, p.M - 1) / rps, b1 = min(mm + 1, p.M - 1) / rps;
-              x.x = fmaf((x.x - p.row_mean[b0]) * p.row_rstd[b0], ap0[kj], ap1[kj]);
-              x.y = fmaf((x.y - p.row_mean[b1]) * p.row_rstd[b1], ap0[kj], ap1[kj]);
-            } else {
-              x.x = apply_mode(AMODE, x.x, ap0[kj], ap1[kj]);
-              x.y = apply_mode(AMODE, x.y, ap0[kj], ap1[kj]);
-            }
-            af[r] = pack_bf162(x.x, x.y);
-          }
-        }
       }
 #pragma unroll
       for (int ni = 0; ni < 2; ++ni)
@@ -571,15 +573,14 @@ __global__ void __launch_bounds__(NTHREADS) pw_wgrad_kernel(const cvb_wgrad_args
       }
   if (want_db) {
 #pragma unroll
-    for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v = db[ni][h];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        int n = n0 + wn0 + ni * 16 + g + h * 8;
-        if (t == 0 && n < p.N) atomicAdd(p.dbias + n, v);
-      }
+    for (int e = 0; e < 8; ++e) {
+      float v = db[e];  // reduce over the 4 row-lanes of this warp that share the chunk column (lane bits 3,4)
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) atomicAdd(&s_db[lch * 8 + e], v);
+    }
+    __syncthreads();
+    if (tid < WG_TN && n0 + tid < p.N) atomicAdd(p.dbias + n0 + tid, s_db[tid]);
   }
 }
 
@@ -629,6 +630,8 @@ extern "C" int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream) {
   CVB_CHECK(a.A && a.W && a.C, "cvb_pw_gemm: null operand");
   CVB_CHECK(cvb_aligned16(a.A) && cvb_aligned16(a.W) && cvb_aligned16(a.C), "cvb_pw_gemm: operands must be 16-byte aligned");
   CVB_CHECK(a.e_mode >= CVB_E_STORE && a.e_mode <= CVB_E_GN_BWD, "cvb_pw_gemm: bad e_mode %d", a.e_mode);
+  CVB_CHECK(!a.c_fp32, "cvb_pw_gemm: fp32 output is not supported (activations and logits are bf16 like the reference under autocast)");
+  CVB_CHECK(!(a.R && a.e_mode >= CVB_E_SILU_BWD), "cvb_pw_gemm: a residual cannot be combined with the backward epilogues");
   if (a.e_mode == CVB_E_SILU_BWD || a.e_mode == CVB_E_GN_BWD)
     CVB_CHECK(a.Y && a.ldy % 8 == 0 && cvb_aligned16(a.Y), "cvb_pw_gemm: epilogue mode %d needs Y", a.e_mode);
   if (a.e_mode == CVB_E_GN_BWD || a.a_mode == CVB_A_GN)

@@ -40,13 +40,13 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
             a_p: Sequence[Optional[Tensor]] = (None, None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,
             rows_per_sample: int = 0, bias: Optional[Tensor] = None, e_mode: int = E_STORE, Y: Optional[Tensor] = None,
             e_p: Sequence[Optional[Tensor]] = (None, None), R: Optional[Tensor] = None, out: Optional[Tensor] = None,
-            out_fp32: bool = False, col_stats: Optional[Tensor] = None, samp_stats: Optional[Tensor] = None) -> Tensor:
+            col_stats: Optional[Tensor] = None, samp_stats: Optional[Tensor] = None) -> Tensor:
     """C[M,N] = epi(load(A)[M,K] @ W[N,K]^T + bias).  ``col_stats``/``samp_stats``: fp64 [2, *] accumulators (pre-zeroed)."""
     lib = _lib()
     M = A.shape[0]
     K = A.shape[1] if K is None else K
     if out is None:
-        out = torch.empty((M, N), device=A.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+        out = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
     a = L.GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.A, a.lda = A.data_ptr(), A.stride(0)

@@ -101,14 +101,11 @@ def test_pw_gemm_modes(ops, M, N, K, a_mode):
     close_stat(samp[1], sq, "samp_sq")
 
 
-def test_pw_gemm_silu_and_fp32_out(ops):
+def test_pw_gemm_silu(ops):
     M, N, K = 384, 96, 64
     A, W, bias = bf(rnd(M, K)), bf(rnd(N, K, scale=0.1)), rnd(N)
     out = ops.pw_gemm(A, W, N, bias=bias, e_mode=ops.E_SILU)
     close(out, silu(A.float() @ W.float().t() + bias), what="silu epilogue")
-    out32 = ops.pw_gemm(A, W, N, bias=bias, out_fp32=True)
-    assert out32.dtype == torch.float32
-    close(out32, A.float() @ W.float().t() + bias, rtol=1e-4, atol=1e-4, what="fp32 out")
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 64, 128), (700, 136, 72)])
