@@ -162,6 +162,40 @@ class GemmTimer:
         return ms, byts, flops, len(self.records)
 
 
+class OpTimer:
+    """Optional (--profile-ops): CUDA-event time of every C-ABI launch, aggregated per entry point (diagnostics only)."""
+
+    NAMES = ["pw_gemm", "pw_wgrad", "dw_fwd", "dw_bwd", "stem_im2col", "bn_finalize", "bn_bwd_finalize", "bn_apply", "bn_bwd_reduce",
+             "gn_finalize", "gn_bwd_apply", "linattn_fwd", "linattn_bwd", "global_pool_fwd", "global_pool_bwd", "unprep_grad"]
+
+    def __init__(self, ops):
+        self.ops, self.rec = ops, []
+
+    def install(self):
+        import ml_cvnets_b200.functional as Fn
+        for name in self.NAMES:
+            orig = getattr(self.ops, name)
+
+            def wrapped(*a, _orig=orig, _name=name, **kw):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = _orig(*a, **kw)
+                e.record()
+                self.rec.append((_name, s, e))
+                return out
+
+            setattr(self.ops, name, wrapped)
+            setattr(Fn.ops, name, wrapped)
+
+    def summary(self, steps):
+        agg = {}
+        for name, s, e in self.rec:
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += s.elapsed_time(e)
+        return {k: {"n_per_step": v[0] / steps, "ms_per_step": v[1] / steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+
+
 def run_ours(args, rank, world, local_rank):
     import ml_cvnets_b200 as m
     from ml_cvnets_b200 import ops
@@ -213,6 +247,10 @@ def run_ours(args, rank, world, local_rank):
     timer = GemmTimer(ops)
     if not args.no_kernel_timing:
         timer.install()
+    optimer = None
+    if args.profile_ops:
+        optimer = OpTimer(ops)
+        optimer.install()
     sampler = ClockSampler(local_rank)
     # ---------------- timed region 1: inputs resident in HBM
     sync_all()
@@ -228,6 +266,9 @@ def run_ours(args, rank, world, local_rank):
     sync_all()
     timer.enabled = False
     launches = ops.launch_count - launches0
+    op_ms = optimer.summary(args.steps) if optimer is not None else None
+    if optimer is not None:
+        optimer.rec = []
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
@@ -308,6 +349,8 @@ def run_ours(args, rank, world, local_rank):
         "step_roofline": {"algorithmic_mb_per_image": 190.8, "frac_of_hbm_peak": step_frac, "peak_gbs": peak},
         "loss": final_loss,
     }
+    if op_ms is not None:
+        line["op_ms"] = op_ms
     print(json.dumps(line), flush=True)
 
 
@@ -321,6 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--profile-ops", action="store_true", help="CUDA-event time per C-ABI entry point (diagnostics)")
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":

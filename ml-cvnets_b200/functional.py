@@ -53,6 +53,43 @@ def _bn_forward(stats, count, gamma, beta, c):
     return ops.bn_eval_scale_shift(gamma, beta, c.running_mean, c.running_var, c.eps)
 
 
+class _Arena:
+    """One zero-filled fp32 and one fp64 buffer per backward pass (two memsets instead of ~100 tiny fills); slices are handed
+    out as accumulators / gradients.  Fresh per call: autograd may keep the returned gradient views alive."""
+
+    def __init__(self, device, n32: int, n64: int):
+        self.b32 = torch.zeros(n32, device=device, dtype=torch.float32)
+        self.b64 = torch.zeros(n64, device=device, dtype=torch.float64)
+        self.o32 = self.o64 = 0
+        self.c32 = None
+
+    def f32(self, *shape: int) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        v = self.b32[self.o32:self.o32 + n].view(*shape)
+        self.o32 += (n + 3) // 4 * 4
+        assert self.o32 <= self.b32.numel(), "fp32 arena exhausted"
+        return v
+
+    def f64(self, *shape: int) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        v = self.b64[self.o64:self.o64 + n].view(*shape)
+        self.o64 += (n + 1) // 2 * 2
+        assert self.o64 <= self.b64.numel(), "fp64 arena exhausted"
+        return v
+
+    def cast(self):
+        """fp64 statistics -> fp32 (ONE conversion kernel); call after the last kernel that accumulates into them."""
+        self.c32 = self.b64.float()
+
+    def as_f32(self, v64: torch.Tensor) -> torch.Tensor:
+        o = v64.storage_offset()
+        return self.c32[o:o + v64.numel()].view(v64.shape)
+
+
 def _zeros64(device, *sizes: int) -> List[torch.Tensor]:
     """One memset for all fp64 [2, n] accumulators of a pass."""
     buf = torch.zeros(2 * sum(sizes), device=device, dtype=torch.float64)
@@ -137,22 +174,23 @@ class InvertedResidualFn(torch.autograd.Function):
         P = cfg.prep
         ev = not cfg.bn[0].batch_stats
         dout = as_2d(to_bf16_cl(gout))
-        sd3, sd2, sd1 = _zeros64(dout.device, cout, hid, hid)
+        ar = _Arena(dout.device, cout * hid + hid * Cin + 9 * hid + 64, 2 * (cout + 2 * hid) + 16)
+        sd3, sd2, sd1 = ar.f64(2, cout), ar.f64(2, hid), ar.f64(2, hid)
         # red_1x1 + BN3 (no activation): dz3 = dout
         ops.bn_bwd_reduce(dout, y3, sd3)
         dgb3, c3 = ops.bn_bwd_finalize(sd3, M2, g3, bn3, ev)
         dz2 = ops.pw_gemm(dout, P.get(cfg.i_w3t), hid, K=cout, a_mode=A_BNB, A2=y3, a_p=c3, e_mode=E_SILU_BWD, Y=y2,
                           e_p=(bn2[2], bn2[3]), col_stats=sd2)
-        dW3 = ops.pw_wgrad(dout, y2, cout, hid, g_mode=A_BNB, G2=y3, g_p=c3, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]))
+        dW3 = ops.pw_wgrad(dout, y2, cout, hid, g_mode=A_BNB, G2=y3, g_p=c3, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), dW=ar.f32(cout, hid))
         # depthwise + BN2
         dgb2, c2 = ops.bn_bwd_finalize(sd2, M2, g2, bn2, ev)
         dz1, dWt = ops.dw_bwd(dz2, y1, B, H, W, hid, s, P.get(cfg.i_wd), g_mode=A_BNB, Y2=y2, g_p=c2, x_mode=A_AFF_SILU,
-                              x_p=(bn1[2], bn1[3]), col_stats=sd1)
+                              x_p=(bn1[2], bn1[3]), col_stats=sd1, dWt=ar.f32(9, hid))
         dWd = ops.unprep_grad(dWt, hid, 9, hid, 2).view(hid, 1, 3, 3)
         # exp_1x1 + BN1
         dgb1, c1 = ops.bn_bwd_finalize(sd1, M, g1, bn1, ev)
         dx = ops.pw_gemm(dz1, P.get(cfg.i_w1t), Cin, K=hid, a_mode=A_BNB, A2=y1, a_p=c1, R=dout if cfg.residual else None)
-        dW1 = ops.pw_wgrad(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1)
+        dW1 = ops.pw_wgrad(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, dW=ar.f32(hid, Cin))
         return (to_4d(dx, B, H, W), None, dW1.view(hid, Cin, 1, 1), dgb1[0], dgb1[1], dWd, dgb2[0], dgb2[1],
                 dW3.view(cout, hid, 1, 1), dgb3[0], dgb3[1])
 
@@ -221,21 +259,25 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         dev = x2.device
         gcount = HW * d
         dout = as_2d(to_bf16_cl(gout))
-        sdp, sd0 = _zeros64(dev, C, C)
+        n32 = sum(int(q.numel()) for q in params) + n * 8 * d + 16 * len(params) + 9 * C + 2 * (2 * d + 8) * n + 64
+        n64 = 4 * C + (n + 1) * (2 * d + 2 * B + 2 * d) + n * (2 * ffn + 2 * d + 2 * B + 2 * d) + 64
+        ar = _Arena(dev, n32, n64)
+        sdp, sd0 = ar.f64(2, C), ar.f64(2, C)
         grads = [None] * len(params)
+        late = []  # (index, fp64 view) gradients that are read out of the fp64 arena after the single cast at the end
         # ---- conv_proj (GN -> 1x1 -> BN, no act)
         ops.bn_bwd_reduce(dout, yp, sdp)
         dgbp, cp = ops.bn_bwd_finalize(sdp, M, gp, bnp, ev)
-        cs, ss = _zeros64(dev, d, B)
+        cs, ss = ar.f64(2, d), ar.f64(2, B)
         g = ops.pw_gemm(dout, P.get(cfg.i_wpt), d, K=C, a_mode=A_BNB, A2=yp, a_p=cp, e_mode=E_GN_BWD, Y=XL, e_p=(gL, None),
                         row_stats=(gnL[0], gnL[1]), rows_per_sample=HW, col_stats=cs, samp_stats=ss)
         dWp = ops.pw_wgrad(dout, XL, C, d, g_mode=A_BNB, G2=yp, g_p=cp, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]),
-                           rows_per_sample=HW)
+                           rows_per_sample=HW, dW=ar.f32(C, d))
         base = 4 + 12 * n
-        grads[base + 0], grads[base + 1] = cs[1].float(), cs[0].float()  # dgamma = sum v*xhat, dbeta = sum v
+        late += [(base + 0, cs[1]), (base + 1, cs[0])]  # dgamma = sum v*xhat, dbeta = sum v
         grads[base + 2], grads[base + 3], grads[base + 4] = dWp.view(C, d, 1, 1), dgbp[0], dgbp[1]
-        (bsum,) = _zeros64(dev, d)  # only row 0 used: column sums of the residual-stream gradient
-        dX = ops.gn_bwd_apply(g, XL, gnL, ss, gcount, B, HW, DRES=None, col_sum=bsum[0] if n > 0 else None)
+        bsum = ar.f64(d)  # column sums of the residual-stream gradient = bias gradient of the producing conv
+        dX = ops.gn_bwd_apply(g, XL, gnL, ss, gcount, B, HW, DRES=None, col_sum=bsum if n > 0 else None)
         # ---- attention/FFN units, last to first
         for i in reversed(range(n)):
             X, gnA, qkv, O, S, CTX, X1, gnF, h = blocks[i]
@@ -243,37 +285,42 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             ix = cfg.i_blk[i]
             o = 4 + 12 * i
             # FFN: X2 = X1 + W2 silu(h) + b2 ; h = W1 GN(X1) + b1
-            grads[o + 11] = bsum[0].float()  # db2
-            grads[o + 10] = ops.pw_wgrad(dX, h, d, ffn, a_mode=A_SILU).view(d, ffn, 1, 1)
-            csh, csf, ssf, bsum1 = _zeros64(dev, ffn, d, B, d)
+            late.append((o + 11, bsum))  # db2
+            grads[o + 10] = ops.pw_wgrad(dX, h, d, ffn, a_mode=A_SILU, dW=ar.f32(d, ffn)).view(d, ffn, 1, 1)
+            csh, csf, ssf, bsum1 = ar.f64(2, ffn), ar.f64(2, d), ar.f64(2, B), ar.f64(d)
             dh = ops.pw_gemm(dX, P.get(ix.w2t), ffn, K=d, e_mode=E_SILU_BWD, Y=h, col_stats=csh)
-            grads[o + 9] = csh[0].float()  # db1 = column sums of dh
-            grads[o + 8] = ops.pw_wgrad(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW).view(ffn, d, 1, 1)
+            late.append((o + 9, csh[0]))  # db1 = column sums of dh
+            grads[o + 8] = ops.pw_wgrad(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW,
+                                        dW=ar.f32(ffn, d)).view(ffn, d, 1, 1)
             gF = ops.pw_gemm(dh, P.get(ix.w1t), d, K=ffn, e_mode=E_GN_BWD, Y=X1, e_p=(gf, None), row_stats=(gnF[0], gnF[1]),
                              rows_per_sample=HW, col_stats=csf, samp_stats=ssf)
-            grads[o + 6], grads[o + 7] = csf[1].float(), csf[0].float()
-            dX1 = ops.gn_bwd_apply(gF, X1, gnF, ssf, gcount, B, HW, DRES=dX, col_sum=bsum1[0])
+            late += [(o + 6, csf[1]), (o + 7, csf[0])]
+            dX1 = ops.gn_bwd_apply(gF, X1, gnF, ssf, gcount, B, HW, DRES=dX, col_sum=bsum1)
             # attention: X1 = X + Wo O + bo ; O = linattn(qkv) ; qkv = Wqkv GN(X) + bqkv
-            grads[o + 5] = bsum1[0].float()  # dbo
-            grads[o + 4] = ops.pw_wgrad(dX1, O, d, d).view(d, d, 1, 1)
+            late.append((o + 5, bsum1))  # dbo
+            grads[o + 4] = ops.pw_wgrad(dX1, O, d, d, dW=ar.f32(d, d)).view(d, d, 1, 1)
             dO = ops.pw_gemm(dX1, P.get(ix.wot), d, K=d)
-            dbq = torch.zeros(2 * d + 8, device=dev, dtype=torch.float32)
+            dbq = ar.f32(2 * d + 8)
             dqkv = ops.linattn_bwd(qkv, dO, S, CTX, B, H, W, d, dbias=dbq)
-            dWq = ops.pw_wgrad(dqkv, X, 2 * d + 8, d, a_mode=A_GN, a_p=(ga, ba), row_stats=(gnA[0], gnA[1]), rows_per_sample=HW)
+            dWq = ops.pw_wgrad(dqkv, X, 2 * d + 8, d, a_mode=A_GN, a_p=(ga, ba), row_stats=(gnA[0], gnA[1]), rows_per_sample=HW,
+                               dW=ar.f32(2 * d + 8, d))
             grads[o + 2] = ops.unprep_grad(dWq, 2 * d + 1, d, d, 0, rot=1).view(2 * d + 1, d, 1, 1)
             grads[o + 3] = ops.unprep_grad(dbq, 2 * d + 1, 1, 1, 3, rot=1)
-            csa, ssa, bsum = _zeros64(dev, d, B, d)
+            csa, ssa, bsum = ar.f64(2, d), ar.f64(2, B), ar.f64(d)
             gA = ops.pw_gemm(dqkv, P.get(ix.wqkvt), d, K=2 * d + 8, e_mode=E_GN_BWD, Y=X, e_p=(ga, None), row_stats=(gnA[0], gnA[1]),
                              rows_per_sample=HW, col_stats=csa, samp_stats=ssa)
-            grads[o + 0], grads[o + 1] = csa[1].float(), csa[0].float()
-            dX = ops.gn_bwd_apply(gA, X, gnA, ssa, gcount, B, HW, DRES=dX1, col_sum=bsum[0] if i > 0 else None)
+            late += [(o + 0, csa[1]), (o + 1, csa[0])]
+            dX = ops.gn_bwd_apply(gA, X, gnA, ssa, gcount, B, HW, DRES=dX1, col_sum=bsum if i > 0 else None)
         # ---- local_rep: 1x1 (no bias / norm) <- SiLU <- BN0 <- dw3x3
-        grads[3] = ops.pw_wgrad(dX, y0, d, C, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3])).view(d, C, 1, 1)
+        grads[3] = ops.pw_wgrad(dX, y0, d, C, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), dW=ar.f32(d, C)).view(d, C, 1, 1)
         dz0 = ops.pw_gemm(dX, P.get(cfg.i_wlt), C, K=d, e_mode=E_SILU_BWD, Y=y0, e_p=(bn0[2], bn0[3]), col_stats=sd0)
         dgb0, c0 = ops.bn_bwd_finalize(sd0, M, g0, bn0, ev)
-        dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW)
+        dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW, dWt=ar.f32(9, C))
         grads[0] = ops.unprep_grad(dWt, C, 9, C, 2).view(C, 1, 3, 3)
         grads[1], grads[2] = dgb0[0], dgb0[1]
+        ar.cast()
+        for idx, v64 in late:
+            grads[idx] = ar.as_f32(v64)
         return (to_4d(dx, B, H, W), None) + tuple(grads)
 
 

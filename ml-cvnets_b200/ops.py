@@ -120,11 +120,13 @@ def dw_fwd(X: Tensor, B: int, H: int, W: int, C: int, stride: int, Wt: Tensor, *
 
 def dw_bwd(DZ: Tensor, X: Tensor, B: int, H: int, W: int, C: int, stride: int, Wt: Tensor, *, g_mode: int = A_RAW,
            Y2: Optional[Tensor] = None, g_p: Sequence[Optional[Tensor]] = (None, None, None), x_mode: int = A_RAW,
-           x_p: Sequence[Optional[Tensor]] = (None, None), col_stats: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-    """Returns (DX bf16 [B*H*W, C], dWt fp32 [9, C])."""
+           x_p: Sequence[Optional[Tensor]] = (None, None), col_stats: Optional[Tensor] = None,
+           dWt: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """Returns (DX bf16 [B*H*W, C], dWt fp32 [9, C]); ``dWt`` if given must be zero-initialised (it is accumulated into)."""
     lib = _lib()
     DX = torch.empty((B * H * W, C), device=X.device, dtype=torch.bfloat16)
-    dWt = torch.zeros((9, C), device=X.device, dtype=torch.float32)
+    if dWt is None:
+        dWt = torch.zeros((9, C), device=X.device, dtype=torch.float32)
     a = L.DwBwdArgs()
     a.B, a.H, a.W, a.C, a.stride = B, H, W, C, stride
     a.DZ, a.Y2, a.g_mode = DZ.data_ptr(), _p(Y2), g_mode
