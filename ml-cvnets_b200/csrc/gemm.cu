@@ -21,43 +21,31 @@ __device__ __forceinline__ uint32_t swz64(int row, int ch) {  // 64-byte rows, 4
   return static_cast<uint32_t>(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int AMODE>
-struct GemmCfg {
-  // the BN-backward prologue streams two A tensors: one stage less keeps two CTAs per SM
-  static constexpr int kStages = (AMODE == CVB_A_BNB) ? 3 : 4;
-};
-
-// The kernel is INSTRUCTION-ISSUE bound, not tensor bound (ncu, profiles/): K <= 768 gives few MMAs per output element, so the
-// design minimises issued instructions per tile:
-//   * prologue (BN+SiLU / GroupNorm / BN-backward) is applied ONCE per element, in place in shared memory, by the thread that
-//     cp.async'ed the chunk (one k-tile ahead of the MMAs; no redundancy across the N-warps);
+// The kernel is INSTRUCTION-ISSUE / latency bound, not tensor bound (ncu, profiles/): K <= 768 gives few MMAs per output
+// element, so the design minimises issued instructions per tile and maximises bytes in flight:
+//   * operands arrive by TMA (cp.async.bulk.tensor.2d, 64-byte swizzle == the ldmatrix XOR layout): ONE elected thread feeds a
+//     ring of A stages that runs across ALL M tiles of the persistent CTA (mbarrier completion); the weight panel [BN, K] is
+//     loaded once and stays resident in shared memory;
+//   * the prologue (BN+SiLU / GroupNorm / BN-backward) is applied ONCE per element, in place in shared memory, one k-tile
+//     ahead of the MMAs (no redundancy across the N-warps);
 //   * the epilogue works on the accumulator fragments directly (bias, activation(-backward), residual, statistics), exchanges
 //     only bf16 through a padded staging tile (aux tensor in, result out, in place) and copies out with 16-byte row-contiguous
-//     stores;
-//   * one cp.async ring runs across ALL tiles of the persistent CTA, so the loads of the next tiles overlap the epilogue.
+//     stores.
+constexpr int MAX_STAGES = 8;
+
 template <int WM, int AMODE>
-__global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_args p) {
+__global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                                                              const __grid_constant__ CUtensorMap tmW, const cvb_gemm_args p, int NST) {
   constexpr int WARPS_M = BM / WM;
   constexpr int WARPS_N = 8 / WARPS_M;
   constexpr int BN = WARPS_N * 32;
   constexpr int MI = WM / 16;
   constexpr bool TWO_A = (AMODE == CVB_A_BNB);
-  constexpr int NST = GemmCfg<AMODE>::kStages;
   constexpr int A_STAGE = BM * BK * 2;
   constexpr int B_STAGE = BN * BK * 2;
   constexpr int LDO = BN + 8;        // bf16 staging row stride (+16 B: conflict-free fragment access)
   constexpr int CGS = BN / 8;        // 16-byte column groups per row
   constexpr bool HAS_P = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN || AMODE == CVB_A_BNB);
-
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sA2 = smem + NST * A_STAGE;
-  uint8_t* sB = smem + (TWO_A ? 2 : 1) * NST * A_STAGE;
-  constexpr int PIPE_BYTES = (TWO_A ? 2 : 1) * NST * A_STAGE + NST * B_STAGE;
-  uint8_t* sO = smem + PIPE_BYTES;                                          // bf16 [BM][LDO] aux-in / result-out staging
-  float* sP = reinterpret_cast<float*>(smem + PIPE_BYTES + BM * LDO * 2);   // prologue parameters
-  __shared__ float s_col[2][128];
-  __shared__ double s_samp[2][128];  // fp64: cross-thread order must not change the GroupNorm statistics
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -70,6 +58,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
   const int my_tiles = (m_tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
   const int total = my_tiles * KT;  // flattened (tile, k-tile) iterations of this CTA
 
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzled TMA destinations: align by hand
+  uint8_t* sW = smem;                                  // resident weight panel: KT blocks of [BN][32]
+  uint8_t* sA = sW + KT * B_STAGE;                     // A ring
+  uint8_t* sA2 = sA + NST * A_STAGE;                   // second operand of the BN-backward prologue
+  uint8_t* sO = sA + (TWO_A ? 2 : 1) * NST * A_STAGE;  // bf16 [BM][LDO] aux-in / result-out staging
+  float* sP = reinterpret_cast<float*>(sO + BM * LDO * 2);
+  __shared__ float s_col[2][128];
+  __shared__ double s_samp[2][128];  // fp64: cross-thread order must not change the GroupNorm statistics
+  __shared__ __align__(8) uint64_t full[MAX_STAGES];
+  __shared__ __align__(8) uint64_t wbar;
+
   if (tid < 128) { s_col[0][tid] = 0.f; s_col[1][tid] = 0.f; s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
   if (HAS_P) {  // per-K prologue parameters -> smem (zero padded so that the K tail transforms to zero)
     for (int k = tid; k < Kpad; k += NTHREADS) {
@@ -79,10 +79,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
       if (AMODE == CVB_A_BNB) sP[2 * Kpad + k] = ok ? p.a_p2[k] : 0.f;
     }
   }
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
 
-  const bf16* __restrict__ A = static_cast<const bf16*>(p.A);
-  const bf16* __restrict__ A2 = static_cast<const bf16*>(p.A2);
-  const bf16* __restrict__ Wg = static_cast<const bf16*>(p.W);
   const int emode = p.e_mode;
   const bool want_col = p.col_sum != nullptr;
   const bool want_samp = p.samp_sum != nullptr;
@@ -96,27 +99,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
 #pragma unroll
   for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
 
-  // one ring for the whole CTA lifetime: iteration `it` = (tile it / KT, k-tile it % KT)
+  // one ring for the whole CTA lifetime: iteration `it` = (tile it / KT, k-tile it % KT); called by ONE thread
   auto issue = [&](int it) {
     const int stage = it % NST;
     const int j = it / KT, kt = it - j * KT;
     const int m0i = ((int)blockIdx.y + j * (int)gridDim.y) * BM;
-    const int k0 = kt * BK;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      int c = tid + i * NTHREADS;
-      int row = c >> 2, ch = c & 3;
-      int m = m0i + row, k = k0 + ch * 8;
-      bool ok = (m < p.M) && (k < p.K);
-      cp_async16(smem_u32(sA + stage * A_STAGE) + swz64(row, ch), A + (ok ? (size_t)m * p.lda + k : 0), ok);
-      if (TWO_A) cp_async16(smem_u32(sA2 + stage * A_STAGE) + swz64(row, ch), A2 + (ok ? (size_t)m * p.lda2 + k : 0), ok);
-    }
-    for (int c = tid; c < BN * 4; c += NTHREADS) {
-      int row = c >> 2, ch = c & 3;
-      int n = n0 + row, k = k0 + ch * 8;
-      bool ok = (n < p.N) && (k < p.K);
-      cp_async16(smem_u32(sB + stage * B_STAGE) + swz64(row, ch), Wg + (ok ? (size_t)n * p.ldw + k : 0), ok);
-    }
+    mbar_expect_tx(&full[stage], (TWO_A ? 2 : 1) * A_STAGE);
+    tma_load_2d(sA + stage * A_STAGE, &tmA, &full[stage], kt * BK, m0i);  // rows >= M / cols >= K are zero-filled by the TMA unit
+    if (TWO_A) tma_load_2d(sA2 + stage * A_STAGE, &tmA2, &full[stage], kt * BK, m0i);
   };
   auto issue_aux = [&](int jt) {  // aux tile of tile jt -> staging buffer (16-byte, row-contiguous)
     const int m0i = ((int)blockIdx.y + jt * (int)gridDim.y) * BM;
@@ -184,15 +174,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
   };
 
   // ---- prologue of the pipeline
-  if (has_aux && my_tiles > 0) issue_aux(0);
-#pragma unroll
-  for (int s = 0; s < NST - 1; ++s) {
-    if (s < total) issue(s);
+  if (tid == 0) {
+    mbar_expect_tx(&wbar, (uint32_t)KT * B_STAGE);
+    for (int kt = 0; kt < KT; ++kt) tma_load_2d(sW + kt * B_STAGE, &tmW, &wbar, kt * BK, n0);
+    for (int s = 0; s < NST - 1 && s < total; ++s) issue(s);
+  }
+  if (has_aux && my_tiles > 0) {
+    issue_aux(0);
     cp_async_commit();
   }
-  cp_async_wait<NST - 2>();  // this thread's chunks of stage 0 (and the parameters written above) ...
-  __syncthreads();           // ... sP visible to everyone
-  if (total > 0) transform(0);
+  mbar_wait(&wbar, 0);
+  if (AMODE != CVB_A_RAW && total > 0) {
+    mbar_wait(&full[0], 0);
+    transform(0);
+  }
 
   int it = 0;
   for (int jt = 0; jt < my_tiles; ++jt) {
@@ -206,17 +201,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
         for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
 
     for (int kt = 0; kt < KT; ++kt, ++it) {
-      cp_async_wait<NST - 3>();  // stage it+1 has landed (for this thread's own chunks)
-      __syncthreads();           // transform(it) visible; everyone's stage it+1 landed; MMAs of it-1 done -> its slot is free
-      {
-        int nxt = it + NST - 1;
-        if (nxt < total) issue(nxt);
-        cp_async_commit();
+      if (AMODE != CVB_A_RAW) {
+        if (it + 1 < total) mbar_wait(&full[(it + 1) % NST], ((it + 1) / NST) & 1);  // stage it+1 landed (transformed below)
+      } else {
+        mbar_wait(&full[it % NST], (it / NST) & 1);
       }
-      if (it + 1 < total) transform(it + 1);
+      fence_proxy_async();  // order this thread's generic smem accesses before the TMA write that refills a slot
+      __syncthreads();      // transform(it) visible; MMAs of it-1 done -> its slot is free
+      if (tid == 0) {
+        const int nxt = it + NST - 1;
+        if (nxt < total) issue(nxt);
+      }
+      if (AMODE != CVB_A_RAW && it + 1 < total) transform(it + 1);
       const int stage = it % NST;
       const uint32_t aBase = smem_u32(sA + stage * A_STAGE);
-      const uint32_t bBase = smem_u32(sB + stage * B_STAGE);
+      const uint32_t bBase = smem_u32(sW + kt * B_STAGE);
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         uint32_t af[MI][4];
@@ -337,7 +336,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const cvb_gemm_arg
     }
     if (has_aux) {
       __syncthreads();  // copy-out finished: the staging tile may be overwritten by the next tile's aux operand
-      if (jt + 1 < my_tiles) issue_aux(jt + 1);  // joins the next cp.async group
+      if (jt + 1 < my_tiles) { issue_aux(jt + 1); cp_async_commit(); }
     }
     // (without aux the next write to sO happens after >= 1 __syncthreads of the next tile's k-loop)
   }  // tile loop
@@ -371,26 +370,34 @@ template <int WM, int AMODE>
 int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   constexpr int WARPS_M = BM / WM;
   constexpr int BN = (8 / WARPS_M) * 32;
-  constexpr int NST = GemmCfg<AMODE>::kStages;
+  constexpr int A_STAGE_ALL = BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1);
   const int KT = (a.K + BK - 1) / BK;
   const int nvec = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
-  size_t smem = (size_t)NST * (BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1) + BN * BK * 2) + (size_t)BM * (BN + 8) * 2 +
-                (size_t)nvec * KT * BK * 4;
+  const size_t fixed = (size_t)KT * BN * BK * 2 + (size_t)BM * (BN + 8) * 2 + (size_t)nvec * KT * BK * 4 + 1024;
+  // stage count from the shared-memory budget: two CTAs per SM when >= 4 stages fit in half an SM, else one CTA with a deep ring
+  int nst = (int)(((size_t)112 * 1024 - fixed) / A_STAGE_ALL);
+  if (fixed >= (size_t)112 * 1024 || nst < 4) nst = (fixed < (size_t)224 * 1024) ? (int)(((size_t)224 * 1024 - fixed) / A_STAGE_ALL) : 0;
+  if (nst > MAX_STAGES) nst = MAX_STAGES;
+  CVB_CHECK(nst >= 2, "cvb_pw_gemm: weight panel [%d x %d] does not fit in shared memory", BN, a.K);
+  size_t smem = fixed + (size_t)nst * A_STAGE_ALL;
   static bool attr_set = false;
   if (!attr_set) {
-    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
-  CVB_CHECK(smem <= 200 * 1024, "cvb_pw_gemm: K=%d too large for the prologue parameter cache", a.K);
   int occ = 0;
   CVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pw_gemm_kernel<WM, AMODE>, NTHREADS, smem));
-  if (occ < 1) occ = 1;
+  CVB_CHECK(occ >= 1, "cvb_pw_gemm: kernel does not fit on an SM (smem %zu)", smem);
   const int n_tiles = (a.N + BN - 1) / BN, m_tiles = (a.M + BM - 1) / BM;
   int gy = (occ * cvb_num_sms() + n_tiles - 1) / n_tiles;  // all CTAs resident, each streaming over its M tiles
   if (gy > m_tiles) gy = m_tiles;
   if (gy < 1) gy = 1;
+  CUtensorMap tmA, tmA2, tmW;
+  if (cvb_make_tmap_2d_k32(&tmA, a.A, a.M, a.K, a.lda, BM)) return 1;
+  if (cvb_make_tmap_2d_k32(&tmA2, AMODE == CVB_A_BNB ? a.A2 : a.A, a.M, a.K, AMODE == CVB_A_BNB ? a.lda2 : a.lda, BM)) return 1;
+  if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, BN)) return 1;
   dim3 grid(n_tiles, gy);
-  pw_gemm_kernel<WM, AMODE><<<grid, NTHREADS, smem, st>>>(a);
+  pw_gemm_kernel<WM, AMODE><<<grid, NTHREADS, smem, st>>>(tmA, tmA2, tmW, a, nst);
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -400,7 +407,8 @@ int dispatch_tile(const cvb_gemm_args& a, cudaStream_t st) {
   int N = a.N;
   if (N <= 32) return launch_gemm<16, AMODE>(a, st);
   int pad128 = (N + 127) / 128 * 128, pad64 = (N + 63) / 64 * 64;
-  if (N <= 64 || pad64 < pad128) return launch_gemm<32, AMODE>(a, st);
+  const bool panel128_too_big = (size_t)((a.K + BK - 1) / BK) * 128 * BK * 2 > (size_t)150 * 1024;
+  if (N <= 64 || pad64 < pad128 || panel128_too_big) return launch_gemm<32, AMODE>(a, st);
   return launch_gemm<64, AMODE>(a, st);
 }
 

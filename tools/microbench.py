@@ -24,8 +24,8 @@ def report(name, ms, nbytes):
 B = 128
 def vec(n, s=1.0, o=0.0): return torch.randn(n, device=dev) * s + o
 
-prof = which == "prof"
-if which in ("all", "gemm", "prof"):
+prof = which in ("prof", "one")
+if which in ("all", "gemm", "prof", "one"):
     for (name, HW, K, N, mode, stats) in [c for c in [
         ("gemm L1.exp   RAW  K32 N64  @128^2 +stats", 128*128, 32, 64, A_RAW, True),
         ("gemm L1.red   AFFS K64 N64  @128^2 +stats", 128*128, 64, 64, A_AFF_SILU, True),
@@ -34,7 +34,7 @@ if which in ("all", "gemm", "prof"):
         ("gemm L2.0.red AFFS K128 N128 @64^2 +stats", 64*64, 128, 128, A_AFF_SILU, True),
         ("gemm L2.1.exp RAW  K128 N256 @64^2 +stats", 64*64, 128, 256, A_RAW, True),
         ("gemm L3.ffn1  GN   K128 N256 @32^2", 32*32, 128, 256, A_GN, False),
-    ] if not prof or c[0].startswith(("gemm L2.0.exp RAW  K64 N128 @128^2 +stats", "gemm L2.0.red AFFS"))]:
+    ] if not prof or c[0].startswith(("gemm L2.0.exp RAW  K64 N128 @128^2 +stats",) + (("gemm L2.0.red AFFS",) if which == "prof" else ()))]:
         M = B * HW
         A = torch.randn(M, K, device=dev).to(BF); W = (torch.randn(N, K, device=dev) * K**-0.5).to(BF)
         p = (vec(K, 0.2, 1.0), vec(K, 0.3), None)
@@ -43,6 +43,8 @@ if which in ("all", "gemm", "prof"):
         out = torch.empty(M, N, device=dev, dtype=BF)
         ms = t(lambda: ops.pw_gemm(A, W, N, a_mode=mode, a_p=p, row_stats=row if mode == A_GN else None, rows_per_sample=HW, col_stats=col, out=out))
         report(name, ms, 2.0 * M * (K + N))
+    if which == "one":
+        sys.exit(0)
     # BNB dX gemm with SILU_BWD epilogue (L2.0 red dX: K=128(cout) -> N=128(hid))
     M = B * 64 * 64; K = 128; N = 128
     A = torch.randn(M, K, device=dev).to(BF); A2 = torch.randn(M, K, device=dev).to(BF); W = (torch.randn(N, K, device=dev) * K**-0.5).to(BF)
