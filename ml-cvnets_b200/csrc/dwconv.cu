@@ -456,7 +456,7 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
 #define CVB_DW_BWD(GM, XM)                                                                                                \
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
-    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
+    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024)); attr = true; } \
     dw_bwd_kernel<GM, XM><<<grid, NTB, smem, st>>>(tmDZ, tmY2, tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, g_bytes, x_bytes);   \
   }
   if (a.g_mode == CVB_A_RAW) {

@@ -375,14 +375,14 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   const int nvec = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
   const size_t fixed = (size_t)KT * BN * BK * 2 + (size_t)BM * (BN + 8) * 2 + (size_t)nvec * KT * BK * 4 + 1024;
   // stage count from the shared-memory budget: two CTAs per SM when >= 4 stages fit in half an SM, else one CTA with a deep ring
-  int nst = (int)(((size_t)112 * 1024 - fixed) / A_STAGE_ALL);
-  if (fixed >= (size_t)112 * 1024 || nst < 4) nst = (fixed < (size_t)224 * 1024) ? (int)(((size_t)224 * 1024 - fixed) / A_STAGE_ALL) : 0;
+  int nst = (int)(((size_t)108 * 1024 - fixed) / A_STAGE_ALL);
+  if (fixed >= (size_t)108 * 1024 || nst < 4) nst = (fixed < (size_t)216 * 1024) ? (int)(((size_t)216 * 1024 - fixed) / A_STAGE_ALL) : 0;
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   CVB_CHECK(nst >= 2, "cvb_pw_gemm: weight panel [%d x %d] does not fit in shared memory", BN, a.K);
   size_t smem = fixed + (size_t)nst * A_STAGE_ALL;
   static bool attr_set = false;
   if (!attr_set) {
-    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr_set = true;
   }
   int occ = 0;
