@@ -287,26 +287,37 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
           }
         }
         if (XMODE != CVB_A_RAW) {
-          float xr[8];  // raw x of this pixel from the (not yet transformed) smem tile
-          unpack8(*reinterpret_cast<const uint4*>(sX + pix_off((ih + 1) * XW + iw + 1, cgi)), xr);
+          // one sigmoid per element serves both uses: a = z*s (kept in place for phase A) and silu'(z) = s + a*(1-s)
+          uint4* px = reinterpret_cast<uint4*>(sX + pix_off((ih + 1) * XW + iw + 1, cgi));
+          float xr[8], av[8];
+          unpack8(*px, xr);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (XMODE == CVB_A_AFF_SILU) da[j] *= silu_grad_f(fmaf(__ldg(p.x_p0 + cc + j), xr[j], __ldg(p.x_p1 + cc + j)));
+            const float z = fmaf(__ldg(p.x_p0 + cc + j), xr[j], __ldg(p.x_p1 + cc + j));
+            if (XMODE == CVB_A_AFF_SILU) {
+              const float sg = 1.0f / (1.0f + __expf(-z));
+              av[j] = z * sg;
+              da[j] *= fmaf(av[j], 1.0f - sg, sg);
+            } else {
+              av[j] = z;
+            }
             da[j] = bf16_round(da[j]);
             cs[j] += da[j];
             cq[j] += da[j] * xr[j];
           }
+          *px = pack8(av);
         }
         stg16(DX + ((size_t)h * p.W + w) * p.C + cc, pack8(da));
       }
     }
-    // ---- 3. a = act(BN(x)) in place (in-bounds only), then phase A
+    // ---- 3. halo ring of the input tile: a = act(BN(x)) in place (in-bounds only; the centre was done in phase B), then phase A
     if (XMODE != CVB_A_RAW) {
-      __syncthreads();  // phase B has read the raw x tile
       for (int ih = warp; ih < XH; ih += NTB / 32) {
         const int h = xh_base + ih;
         if (h < 0 || h >= p.H) continue;
+        const bool row_center = (ih >= 1 && ih <= ITH);
         for (int jw = lane >> 3; jw < XW; jw += 4) {
+          if (row_center && jw >= 1 && jw <= ITW) continue;
           const int w = xw_base + jw;
           const int pix = ih * XW + jw;
           const int lc = c0 + ((pch ^ (pix & 7)) << 3);
@@ -322,8 +333,8 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
           *px = pack8(f);
         }
       }
-      __syncthreads();
     }
+    __syncthreads();  // dX done with the dy tile; transformed input tile complete
     {
       const uint32_t sub = static_cast<uint32_t>((cp & 3) << 2);
       const int chk = cp >> 2;

@@ -33,7 +33,11 @@ __device__ __forceinline__ uint32_t swz64(int row, int ch) {  // 64-byte rows, 4
 //     stores.
 constexpr int MAX_STAGES = 8;
 
-template <int WM, int AMODE>
+// compile-time epilogue variants (keeps the SASS compact: the generic runtime-switched epilogue was 130 KB of code and stalled
+// on instruction fetch)
+enum { EPI_STORE = 0, EPI_STORE_R = 1, EPI_SILU = 2, EPI_SILU_BWD = 3, EPI_GN_BWD = 4 };
+
+template <int WM, int AMODE, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                                                               const __grid_constant__ CUtensorMap tmW, const cvb_gemm_args p, int NST) {
   constexpr int WARPS_M = BM / WM;
@@ -86,14 +90,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
   }
   __syncthreads();
 
-  const int emode = p.e_mode;
   const bool want_col = p.col_sum != nullptr;
   const bool want_samp = p.samp_sum != nullptr;
   const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
   // at most one auxiliary [M, N] tensor: Y (activation / GroupNorm backward) or the residual R
-  const bf16* __restrict__ AUX = static_cast<const bf16*>(emode >= CVB_E_SILU_BWD ? p.Y : p.R);
-  const int ldaux = emode >= CVB_E_SILU_BWD ? p.ldy : p.ldr;
-  const bool has_aux = AUX != nullptr;
+  constexpr bool has_aux = (EPI == EPI_STORE_R || EPI == EPI_SILU_BWD || EPI == EPI_GN_BWD);
+  const bf16* __restrict__ AUX = static_cast<const bf16*>(EPI == EPI_STORE_R ? p.R : p.Y);
+  const int ldaux = EPI == EPI_STORE_R ? p.ldr : p.ldy;
 
   float cs[8], cq[8];  // per-column statistics (columns wn0 + ni*8 + 2t + e), accumulated over all tiles, flushed once
 #pragma unroll
@@ -245,17 +248,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
       __syncthreads();
     }
     const int first_sample = m0 / rps;
+    // per-column vectors of this thread's 8 columns.  Out-of-range columns have zero weights and get zero bias; out-of-range
+    // rows have zero A rows and get their bias masked -> every such value is exactly 0 and needs no predicate in the statistics.
     float bias2[4][2], ep0[4][2], ep1[4][2];
-    bool ncol_ok[4];
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {
       const int n = n0 + wn0 + ni * 8 + 2 * t;
-      ncol_ok[ni] = n < p.N;
+      const bool nok = n < p.N;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        bias2[ni][e] = (ncol_ok[ni] && p.bias) ? __ldg(p.bias + n + e) : 0.f;
-        ep0[ni][e] = (ncol_ok[ni] && p.e_p0) ? __ldg(p.e_p0 + n + e) : 1.f;
-        ep1[ni][e] = (ncol_ok[ni] && p.e_p1) ? __ldg(p.e_p1 + n + e) : 0.f;
+        bias2[ni][e] = (nok && p.bias) ? __ldg(p.bias + n + e) : 0.f;
+        if (EPI == EPI_SILU_BWD || EPI == EPI_GN_BWD) ep0[ni][e] = (nok && p.e_p0) ? __ldg(p.e_p0 + n + e) : 1.f;
+        if (EPI == EPI_SILU_BWD) ep1[ni][e] = (nok && p.e_p1) ? __ldg(p.e_p1 + n + e) : 0.f;
       }
     }
 #pragma unroll
@@ -264,74 +268,96 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
       for (int h = 0; h < 2; ++h) {
         const int row = wm0 + mi * 16 + g + h * 8;
         const int m = m0 + row;
-        const bool row_ok = m < p.M;
+        const float rmask = m < p.M ? 1.f : 0.f;
         float mu = 0.f, rs = 1.f;
-        if (emode == CVB_E_GN_BWD) {
-          const int b = (row_ok ? m : p.M - 1) / rps;
+        if (EPI == EPI_GN_BWD) {
+          const int b = (m < p.M ? m : p.M - 1) / rps;
           mu = __ldg(p.row_mean + b);
           rs = __ldg(p.row_rstd + b);
         }
         float ssum = 0.f, ssq = 0.f;
+        uint32_t* prow = reinterpret_cast<uint32_t*>(sO + row * (LDO * 2) + (wn0 + 2 * t) * 2);
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
-          uint32_t* po = reinterpret_cast<uint32_t*>(sO + row * (LDO * 2) + (wn0 + ni * 8 + 2 * t) * 2);
-          float v0 = acc[mi][ni][2 * h] + bias2[ni][0], v1 = acc[mi][ni][2 * h + 1] + bias2[ni][1];
+          float v0 = fmaf(bias2[ni][0], rmask, acc[mi][ni][2 * h]), v1 = fmaf(bias2[ni][1], rmask, acc[mi][ni][2 * h + 1]);
           float y0 = 0.f, y1 = 0.f;
-          if (has_aux) { float2 a2 = unpack_bf162(*po); y0 = a2.x; y1 = a2.y; }
-          const bool ok = row_ok && ncol_ok[ni];
-          if (emode == CVB_E_SILU) {
+          if (has_aux) { const float2 a2 = unpack_bf162(prow[ni * 4]); y0 = a2.x; y1 = a2.y; }
+          if (EPI == EPI_STORE_R) {
+            v0 += y0; v1 += y1;
+          } else if (EPI == EPI_SILU) {
             v0 = silu_f(v0); v1 = silu_f(v1);
-          } else if (emode == CVB_E_SILU_BWD) {
+          } else if (EPI == EPI_SILU_BWD) {
             v0 *= silu_grad_f(fmaf(ep0[ni][0], y0, ep1[ni][0]));
             v1 *= silu_grad_f(fmaf(ep0[ni][1], y1, ep1[ni][1]));
-          } else if (emode == CVB_E_GN_BWD) {
+          } else if (EPI == EPI_GN_BWD) {
             y0 = (y0 - mu) * rs; y1 = (y1 - mu) * rs;  // x-hat
-            if (ok) { cs[ni * 2] += v0; cs[ni * 2 + 1] += v1; cq[ni * 2] += v0 * y0; cq[ni * 2 + 1] += v1 * y1; }
+            cs[ni * 2] += v0; cs[ni * 2 + 1] += v1;
+            cq[ni * 2] = fmaf(v0, y0, cq[ni * 2]); cq[ni * 2 + 1] = fmaf(v1, y1, cq[ni * 2 + 1]);
             v0 *= ep0[ni][0]; v1 *= ep0[ni][1];
-          } else if (has_aux) {  // residual
-            v0 += y0; v1 += y1;
           }
           const uint32_t pk = pack_bf162(v0, v1);
-          *po = pk;
-          if (ok) {
-            const float2 r = unpack_bf162(pk);  // statistics of the STORED (bf16) values
-            if (emode == CVB_E_STORE || emode == CVB_E_SILU) {
-              cs[ni * 2] += r.x; cs[ni * 2 + 1] += r.y; cq[ni * 2] += r.x * r.x; cq[ni * 2 + 1] += r.y * r.y;
-              ssum += r.x + r.y; ssq += r.x * r.x + r.y * r.y;
-            } else if (emode == CVB_E_SILU_BWD) {
-              cs[ni * 2] += r.x; cs[ni * 2 + 1] += r.y; cq[ni * 2] += r.x * y0; cq[ni * 2 + 1] += r.y * y1;
-            } else {
-              ssum += r.x + r.y; ssq += r.x * y0 + r.y * y1;
-            }
+          prow[ni * 4] = pk;
+          const float2 r = unpack_bf162(pk);  // statistics of the STORED (bf16) values
+          if (EPI == EPI_STORE || EPI == EPI_STORE_R || EPI == EPI_SILU) {
+            cs[ni * 2] += r.x; cs[ni * 2 + 1] += r.y;
+            cq[ni * 2] = fmaf(r.x, r.x, cq[ni * 2]); cq[ni * 2 + 1] = fmaf(r.y, r.y, cq[ni * 2 + 1]);
+          } else if (EPI == EPI_SILU_BWD) {
+            cs[ni * 2] += r.x; cs[ni * 2 + 1] += r.y;
+            cq[ni * 2] = fmaf(r.x, y0, cq[ni * 2]); cq[ni * 2 + 1] = fmaf(r.y, y1, cq[ni * 2 + 1]);
+          } else {
+            ssum += r.x + r.y;
+            ssq = fmaf(r.x, y0, fmaf(r.y, y1, ssq));
           }
         }
-        if (want_samp) {
+        if (EPI == EPI_GN_BWD) {  // per-sample sums of g and g*xhat (GroupNorm backward, phase 1)
           ssum += __shfl_xor_sync(0xffffffffu, ssum, 1); ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
           ssq += __shfl_xor_sync(0xffffffffu, ssq, 1); ssq += __shfl_xor_sync(0xffffffffu, ssq, 2);
-          if (t == 0 && row_ok) {
+          if (t == 0 && m < p.M && want_samp) {
             const int bi = m / rps - first_sample;
             atomicAdd(&s_samp[0][bi], (double)ssum);
             atomicAdd(&s_samp[1][bi], (double)ssq);
           }
         }
       }
-    __syncthreads();  // staged result complete (and s_samp complete)
+    __syncthreads();  // staged result complete
     {
       bf16* __restrict__ Cg = static_cast<bf16*>(p.C);
+      const bool samp_here = want_samp && EPI != EPI_GN_BWD;  // GroupNorm statistics of the stored output, per row of 16-byte chunks
       for (int c = tid; c < BM * CGS; c += NTHREADS) {
         const int row = c / CGS, cgc = c % CGS;
         const int m = m0 + row, n = n0 + cgc * 8;
-        if (m < p.M && n < p.N) stg16(Cg + (size_t)m * p.ldc + n, *reinterpret_cast<const uint4*>(sO + row * (LDO * 2) + cgc * 16));
+        const uint4 u = *reinterpret_cast<const uint4*>(sO + row * (LDO * 2) + cgc * 16);
+        if (m < p.M && n < p.N) stg16(Cg + (size_t)m * p.ldc + n, u);
+        if (samp_here) {
+          float f[8];
+          unpack8(u, f);
+          float sv = 0.f, sq = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sv += f[e]; sq = fmaf(f[e], f[e], sq); }
+#pragma unroll
+          for (int o = CGS / 2; o > 0; o >>= 1) {
+            sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+          if (cgc == 0 && m < p.M) {
+            const int bi = m / rps - first_sample;
+            atomicAdd(&s_samp[0][bi], (double)sv);
+            atomicAdd(&s_samp[1][bi], (double)sq);
+          }
+        }
       }
     }
-    if (want_samp && tid < 128) {
-      int mlast = min(m0 + BM, p.M) - 1;
-      int nsamp = mlast / rps - first_sample + 1;
-      if (tid < nsamp) {
-        atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
-        atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
-        s_samp[0][tid] = 0.0;
-        s_samp[1][tid] = 0.0;
+    if (want_samp) {
+      __syncthreads();  // s_samp complete
+      if (tid < 128) {
+        int mlast = min(m0 + BM, p.M) - 1;
+        int nsamp = mlast / rps - first_sample + 1;
+        if (tid < nsamp) {
+          atomicAdd(p.samp_sum + first_sample + tid, s_samp[0][tid]);
+          atomicAdd(p.samp_sq + first_sample + tid, s_samp[1][tid]);
+          s_samp[0][tid] = 0.0;
+          s_samp[1][tid] = 0.0;
+        }
       }
     }
     if (has_aux) {
@@ -366,7 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
   }
 }
 
-template <int WM, int AMODE>
+template <int WM, int AMODE, int EPI>
 int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   constexpr int WARPS_M = BM / WM;
   constexpr int BN = (8 / WARPS_M) * 32;
@@ -382,11 +408,11 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   size_t smem = fixed + (size_t)nst * A_STAGE_ALL;
   static bool attr_set = false;
   if (!attr_set) {
-    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<WM, AMODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr_set = true;
   }
   int occ = 0;
-  CVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pw_gemm_kernel<WM, AMODE>, NTHREADS, smem));
+  CVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pw_gemm_kernel<WM, AMODE, EPI>, NTHREADS, smem));
   CVB_CHECK(occ >= 1, "cvb_pw_gemm: kernel does not fit on an SM (smem %zu)", smem);
   const int n_tiles = (a.N + BN - 1) / BN, m_tiles = (a.M + BM - 1) / BM;
   int gy = (occ * cvb_num_sms() + n_tiles - 1) / n_tiles;  // all CTAs resident, each streaming over its M tiles
@@ -397,19 +423,33 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   if (cvb_make_tmap_2d_k32(&tmA2, AMODE == CVB_A_BNB ? a.A2 : a.A, a.M, a.K, AMODE == CVB_A_BNB ? a.lda2 : a.lda, BM)) return 1;
   if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, BN)) return 1;
   dim3 grid(n_tiles, gy);
-  pw_gemm_kernel<WM, AMODE><<<grid, NTHREADS, smem, st>>>(tmA, tmA2, tmW, a, nst);
+  pw_gemm_kernel<WM, AMODE, EPI><<<grid, NTHREADS, smem, st>>>(tmA, tmA2, tmW, a, nst);
   CVB_LAUNCH_CHECK();
   return 0;
 }
 
-template <int AMODE>
+template <int AMODE, int EPI>
 int dispatch_tile(const cvb_gemm_args& a, cudaStream_t st) {
   int N = a.N;
-  if (N <= 32) return launch_gemm<16, AMODE>(a, st);
+  if (N <= 32) return launch_gemm<16, AMODE, EPI>(a, st);
   int pad128 = (N + 127) / 128 * 128, pad64 = (N + 63) / 64 * 64;
   const bool panel128_too_big = (size_t)((a.K + BK - 1) / BK) * 128 * BK * 2 > (size_t)150 * 1024;
-  if (N <= 64 || pad64 < pad128 || panel128_too_big) return launch_gemm<32, AMODE>(a, st);
-  return launch_gemm<64, AMODE>(a, st);
+  if (N <= 64 || pad64 < pad128 || panel128_too_big) return launch_gemm<32, AMODE, EPI>(a, st);
+  return launch_gemm<64, AMODE, EPI>(a, st);
+}
+
+// the (prologue, epilogue) combinations the hot path uses (functional.py) plus STORE / STORE_R for every prologue
+template <int AMODE>
+int dispatch_epi(const cvb_gemm_args& a, int epi, cudaStream_t st) {
+  if (epi == EPI_STORE) return dispatch_tile<AMODE, EPI_STORE>(a, st);
+  if (epi == EPI_STORE_R) return dispatch_tile<AMODE, EPI_STORE_R>(a, st);
+  if (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB) {
+    if (epi == EPI_SILU_BWD) return dispatch_tile<AMODE, EPI_SILU_BWD>(a, st);
+    if (epi == EPI_GN_BWD) return dispatch_tile<AMODE, EPI_GN_BWD>(a, st);
+  }
+  if (AMODE == CVB_A_RAW && epi == EPI_SILU) return dispatch_tile<CVB_A_RAW, EPI_SILU>(a, st);
+  cvb_set_error("cvb_pw_gemm: load mode %d with epilogue %d is not instantiated", AMODE, epi);
+  return 1;
 }
 
 // =====================================================================================================================
@@ -647,15 +687,18 @@ extern "C" int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream) {
   if (a.R) CVB_CHECK(a.ldr % 8 == 0 && cvb_aligned16(a.R), "cvb_pw_gemm: bad residual");
   if (a.samp_sum) CVB_CHECK(a.samp_sq && a.rows_per_sample > 0, "cvb_pw_gemm: sample statistics need rows_per_sample");
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_pw_gemm: col_sq missing");
+  CVB_CHECK(!(a.R && a.e_mode == CVB_E_SILU), "cvb_pw_gemm: SiLU epilogue with a residual is not instantiated");
+  const int epi = a.e_mode == CVB_E_STORE ? (a.R ? EPI_STORE_R : EPI_STORE) : a.e_mode == CVB_E_SILU ? EPI_SILU
+                  : a.e_mode == CVB_E_SILU_BWD ? EPI_SILU_BWD : EPI_GN_BWD;
   switch (a.a_mode) {
-    case CVB_A_RAW: return dispatch_tile<CVB_A_RAW>(a, st);
-    case CVB_A_AFF: CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: AFF needs p0/p1"); return dispatch_tile<CVB_A_AFF>(a, st);
-    case CVB_A_AFF_SILU: CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: AFF_SILU needs p0/p1"); return dispatch_tile<CVB_A_AFF_SILU>(a, st);
-    case CVB_A_SILU: return dispatch_tile<CVB_A_SILU>(a, st);
-    case CVB_A_GN: CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: GN needs gamma/beta"); return dispatch_tile<CVB_A_GN>(a, st);
+    case CVB_A_RAW: return dispatch_epi<CVB_A_RAW>(a, epi, st);
+    case CVB_A_AFF: CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: AFF needs p0/p1"); return dispatch_epi<CVB_A_AFF>(a, epi, st);
+    case CVB_A_AFF_SILU: CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: AFF_SILU needs p0/p1"); return dispatch_epi<CVB_A_AFF_SILU>(a, epi, st);
+    case CVB_A_SILU: return dispatch_epi<CVB_A_SILU>(a, epi, st);
+    case CVB_A_GN: CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: GN needs gamma/beta"); return dispatch_epi<CVB_A_GN>(a, epi, st);
     case CVB_A_BNB:
       CVB_CHECK(a.A2 && a.a_p0 && a.a_p1 && a.a_p2 && a.lda2 % 8 == 0 && cvb_aligned16(a.A2), "cvb_pw_gemm: BNB needs A2 and p0/p1/p2");
-      return dispatch_tile<CVB_A_BNB>(a, st);
+      return dispatch_epi<CVB_A_BNB>(a, epi, st);
     default: cvb_set_error("cvb_pw_gemm: unsupported a_mode %d", a.a_mode); return 1;
   }
 }
