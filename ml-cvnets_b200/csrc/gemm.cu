@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
     const int stage = it % NST;
     const int j = it / KT, kt = it - j * KT;
     const int k0 = kt * BK;
+    const int m0i = ((int)blockIdx.y + j * (int)gridDim.y) * BM;
     if (AMODE == CVB_A_GN && kt == 0) {
-      const int m0i = ((int)blockIdx.y + j * (int)gridDim.y) * BM;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         int m = m0i + (tid >> 2) + i * 64;
@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = fmaf(q0[e], f[e], fmaf(q1[e], y[e], q2[e]));
       }
-      *pa = pack8(f);
+      // rows beyond M must stay exactly zero (their accumulators feed the statistics unmasked)
+      *pa = (m0i + row < p.M) ? pack8(f) : make_uint4(0u, 0u, 0u, 0u);
     }
   };
 
