@@ -405,7 +405,8 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   int nst = (int)(((size_t)108 * 1024 - fixed) / A_STAGE_ALL);
   if (fixed >= (size_t)108 * 1024 || nst < 4) nst = (fixed < (size_t)216 * 1024) ? (int)(((size_t)216 * 1024 - fixed) / A_STAGE_ALL) : 0;
   if (nst > MAX_STAGES) nst = MAX_STAGES;
-  CVB_CHECK(nst >= 2, "cvb_pw_gemm: weight panel [%d x %d] does not fit in shared memory", BN, a.K);
+  // the transform-ahead pipeline waits for stage it+1 before issuing stage it+NST-1: it needs >= 3 stages
+  if (nst < 3) return -1;  // caller retries with a narrower N tile (smaller resident weight panel)
   size_t smem = fixed + (size_t)nst * A_STAGE_ALL;
   static bool attr_set = false;
   if (!attr_set) {
@@ -431,12 +432,14 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
 
 template <int AMODE, int EPI>
 int dispatch_tile(const cvb_gemm_args& a, cudaStream_t st) {
-  int N = a.N;
-  if (N <= 32) return launch_gemm<16, AMODE, EPI>(a, st);
-  int pad128 = (N + 127) / 128 * 128, pad64 = (N + 63) / 64 * 64;
-  const bool panel128_too_big = (size_t)((a.K + BK - 1) / BK) * 128 * BK * 2 > (size_t)150 * 1024;
-  if (N <= 64 || pad64 < pad128 || panel128_too_big) return launch_gemm<32, AMODE, EPI>(a, st);
-  return launch_gemm<64, AMODE, EPI>(a, st);
+  const int N = a.N;
+  const int pad128 = (N + 127) / 128 * 128, pad64 = (N + 63) / 64 * 64;
+  int rc = -1;
+  if (N > 64 && pad64 >= pad128) rc = launch_gemm<64, AMODE, EPI>(a, st);  // BN = 128
+  if (rc == -1 && N > 32) rc = launch_gemm<32, AMODE, EPI>(a, st);         // BN = 64
+  if (rc == -1) rc = launch_gemm<16, AMODE, EPI>(a, st);                   // BN = 32
+  CVB_CHECK(rc != -1, "cvb_pw_gemm: K=%d is too large for the resident weight panel", a.K);
+  return rc;
 }
 
 // the (prologue, epilogue) combinations the hot path uses (functional.py) plus STORE / STORE_R for every prologue

@@ -101,6 +101,20 @@ def test_pw_gemm_modes(ops, M, N, K, a_mode):
     close_stat(samp[1], sq, "samp_sq")
 
 
+@pytest.mark.parametrize("M,N,K", [(32, 256, 512), (64, 512, 768), (128, 1000, 512), (40, 128, 1000), (8192, 768, 384)])
+@pytest.mark.parametrize("a_mode", [0, 2, 5])
+def test_pw_gemm_small_m_large_k(ops, M, N, K, a_mode):
+    """late-stage shapes: fewer rows than one tile, weight panels that force narrower N tiles / single-CTA rings"""
+    A, A2 = bf(rnd(M, K, seed=201)), bf(rnd(M, K, seed=202))
+    W = bf(rnd(N, K, scale=K ** -0.5, seed=203))
+    p = (1 + 0.2 * rnd(K, seed=204), 0.3 * rnd(K, seed=205), 0.1 * rnd(K, seed=206))
+    col = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+    out = ops.pw_gemm(A, W, N, a_mode=a_mode, A2=A2 if a_mode == 5 else None, a_p=p, col_stats=col)
+    ref = load_ref(a_mode, A, p, A2) @ W.float().t()
+    close(out, ref, what="out")
+    close_stat(col[0], out.float().sum(0), "col_sum")
+
+
 def test_pw_gemm_silu(ops):
     M, N, K = 384, 96, 64
     A, W, bias = bf(rnd(M, K)), bf(rnd(N, K, scale=0.1)), rnd(N)
