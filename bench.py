@@ -148,7 +148,7 @@ class GemmTimer:
             e.record()
             M, K = A.shape[0], kw.get("K") or A.shape[1]
             # algorithmic bytes: input activation read once + output written once, bf16
-            timer.records.append((s, e, 2.0 * M * (K + N), 2.0 * M * K * N))
+            timer.records.append((s, e, 2.0 * M * (K + N), 2.0 * M * K * N, (M, N, K, kw.get("a_mode", 0), kw.get("e_mode", 0))))
             return out
 
         ops.pw_gemm = timed_pw_gemm
@@ -156,10 +156,20 @@ class GemmTimer:
         Fn.ops.pw_gemm = timed_pw_gemm
 
     def summary(self):
-        ms = sum(s.elapsed_time(e) for s, e, _, _ in self.records)
-        byts = sum(b for _, _, b, _ in self.records)
-        flops = sum(f for _, _, _, f in self.records)
+        ms = sum(r[0].elapsed_time(r[1]) for r in self.records)
+        byts = sum(r[2] for r in self.records)
+        flops = sum(r[3] for r in self.records)
         return ms, byts, flops, len(self.records)
+
+    def per_shape(self, steps):
+        agg = {}
+        for r in self.records:
+            a = agg.setdefault(r[4], [0, 0.0, r[2]])
+            a[0] += 1
+            a[1] += r[0].elapsed_time(r[1])
+        out = [{"M,N,K,a_mode,e_mode": list(k), "n_per_step": v[0] / steps, "us_each": 1e3 * v[1] / v[0], "GBps": v[2] / (v[1] / v[0]) / 1e6}
+               for k, v in agg.items()]
+        return sorted(out, key=lambda d: -d["us_each"] * d["n_per_step"])
 
 
 class OpTimer:
@@ -402,6 +412,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if op_ms is not None:
         line["op_ms"] = op_ms
+        if timer.records:
+            line["gemm_shapes"] = timer.per_shape(3 if use_graph else args.steps)
     print(json.dumps(line), flush=True)
 
 
