@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
 }
 
 template <int WM, int AMODE, int EPI>
-int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
+int launch_gemm(const cvb_gemm_args& a, cudaStream_t st, bool require_two_ctas) {
   constexpr int WARPS_M = BM / WM;
   constexpr int BN = (8 / WARPS_M) * 32;
   constexpr int A_STAGE_ALL = BM * BK * 2 * (AMODE == CVB_A_BNB ? 2 : 1);
@@ -402,8 +402,12 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st) {
   const int nvec = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
   const size_t fixed = (size_t)KT * BN * BK * 2 + (size_t)BM * (BN + 8) * 2 + (size_t)nvec * KT * BK * 4 + 1024;
   // stage count from the shared-memory budget: two CTAs per SM when >= 4 stages fit in half an SM, else one CTA with a deep ring
-  int nst = (int)(((size_t)108 * 1024 - fixed) / A_STAGE_ALL);
-  if (fixed >= (size_t)108 * 1024 || nst < 4) nst = (fixed < (size_t)216 * 1024) ? (int)(((size_t)216 * 1024 - fixed) / A_STAGE_ALL) : 0;
+  int nst = (fixed < (size_t)108 * 1024) ? (int)(((size_t)108 * 1024 - fixed) / A_STAGE_ALL) : 0;
+  if (nst < 4) {
+    // one CTA per SM serialises main loop and epilogue (measured 3-4x slower per tile): let the caller try a narrower N tile first
+    if (require_two_ctas) return -1;
+    nst = (fixed < (size_t)216 * 1024) ? (int)(((size_t)216 * 1024 - fixed) / A_STAGE_ALL) : 0;
+  }
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   // the transform-ahead pipeline waits for stage it+1 before issuing stage it+NST-1: it needs >= 3 stages
   if (nst < 3) return -1;  // caller retries with a narrower N tile (smaller resident weight panel)
@@ -433,10 +437,16 @@ template <int AMODE, int EPI>
 int dispatch_tile(const cvb_gemm_args& a, cudaStream_t st) {
   const int N = a.N;
   const int pad128 = (N + 127) / 128 * 128, pad64 = (N + 63) / 64 * 64;
+  const bool want128 = N > 64 && pad64 >= pad128;
   int rc = -1;
-  if (N > 64 && pad64 >= pad128) rc = launch_gemm<64, AMODE, EPI>(a, st);  // BN = 128
-  if (rc == -1 && N > 32) rc = launch_gemm<32, AMODE, EPI>(a, st);         // BN = 64
-  if (rc == -1) rc = launch_gemm<16, AMODE, EPI>(a, st);                   // BN = 32
+  // first choice: the widest N tile that still leaves room for two resident CTAs per SM with a >= 4-stage ring
+  if (want128) rc = launch_gemm<64, AMODE, EPI>(a, st, true);              // BN = 128
+  if (rc == -1 && N > 32) rc = launch_gemm<32, AMODE, EPI>(a, st, true);   // BN = 64
+  if (rc == -1 && N <= 32) rc = launch_gemm<16, AMODE, EPI>(a, st, true);  // BN = 32
+  // otherwise one CTA per SM with a deep ring
+  if (rc == -1 && want128) rc = launch_gemm<64, AMODE, EPI>(a, st, false);
+  if (rc == -1 && N > 32) rc = launch_gemm<32, AMODE, EPI>(a, st, false);
+  if (rc == -1) rc = launch_gemm<16, AMODE, EPI>(a, st, false);
   CVB_CHECK(rc != -1, "cvb_pw_gemm: K=%d is too large for the resident weight panel", a.K);
   return rc;
 }
