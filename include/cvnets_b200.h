@@ -85,6 +85,10 @@ typedef struct {
   double* samp_sum; double* samp_sq; /* fp64 [M/rows_per_sample] or NULL (GroupNorm statistics of the stored output) */
 } cvb_gemm_args;
 CVB_API int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream);
+/* Two kernels implement cvb_pw_gemm: a warp-specialised tcgen05/TMEM/TMA kernel (prologue-free layers) and an mma.sync kernel
+ * (layers whose A operand needs an element-wise prologue).  Testing hook: disable (0) / enable (1) the tcgen05 kernel so the
+ * two can be compared on identical inputs; returns the previous setting. */
+CVB_API int cvb_set_tc_enabled(int on);
 
 /* Weight gradient of a pointwise conv / linear:  dW[N,K] += sum_m load(G)[m,n] * load(A)[m,k];  dbias[n] += sum_m load(G)[m,n]
  * (autograd of F.conv2d / F.linear at the call sites above).  G modes: RAW or BNB; A modes: RAW/AFF/AFF_SILU/SILU/GN. */

@@ -80,6 +80,7 @@ _SIGS = {
     "cvb_abi_version": (c_int, []),
     "cvb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "cvb_pw_gemm": (c_int, [POINTER(GemmArgs), c_void_p]),
+    "cvb_set_tc_enabled": (c_int, [c_int]),
     "cvb_pw_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
     "cvb_dw_fwd": (c_int, [POINTER(DwFwdArgs), c_void_p]),
     "cvb_dw_bwd": (c_int, [POINTER(DwBwdArgs), c_void_p]),

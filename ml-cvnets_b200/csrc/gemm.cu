@@ -681,6 +681,14 @@ int dispatch_wgrad_a(const cvb_wgrad_args& a, cudaStream_t st) {
 
 }  // namespace
 
+int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st);  // gemm_tc.cu: tcgen05 / TMEM kernel for the prologue-free layers
+static int g_tc_enabled = 1;
+extern "C" int cvb_set_tc_enabled(int on) {
+  int old = g_tc_enabled;
+  g_tc_enabled = on ? 1 : 0;
+  return old;
+}
+
 extern "C" int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream) {
   CVB_CHECK(args != nullptr, "cvb_pw_gemm: null args");
   const cvb_gemm_args& a = *args;
@@ -701,6 +709,10 @@ extern "C" int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream) {
   if (a.samp_sum) CVB_CHECK(a.samp_sq && a.rows_per_sample > 0, "cvb_pw_gemm: sample statistics need rows_per_sample");
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_pw_gemm: col_sq missing");
   CVB_CHECK(!(a.R && a.e_mode == CVB_E_SILU), "cvb_pw_gemm: SiLU epilogue with a residual is not instantiated");
+  if (g_tc_enabled) {
+    int rc = cvb_pw_gemm_tc(a, st);  // RAW prologue + STORE / residual / SiLU-backward epilogues run on tcgen05
+    if (rc != -1) return rc;
+  }
   const int epi = a.e_mode == CVB_E_STORE ? (a.R ? EPI_STORE_R : EPI_STORE) : a.e_mode == CVB_E_SILU ? EPI_SILU
                   : a.e_mode == CVB_E_SILU_BWD ? EPI_SILU_BWD : EPI_GN_BWD;
   switch (a.a_mode) {

@@ -1,0 +1,299 @@
+// tcgen05 / TMEM / TMA pointwise-conv GEMM for the prologue-free (RAW) layers (sm_100a).
+//
+//   C[M,N] = epi( A[M,K] * W[N,K]^T + bias )          same contract as the mma.sync kernel in gemm.cu
+//
+// Warp-specialised, one persistent CTA per SM:
+//   warp 0    TMA producer : ring of A stages [128 pixels x 32 k] (cp.async.bulk.tensor.2d, 64-byte swizzle) across ALL tiles
+//   warp 1    MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16; the accumulator lives in TMEM,
+//                            double buffered (2 x 128 columns), completion is signalled with tcgen05.commit -> mbarrier
+//   warps 2-5 epilogue     : tcgen05.ld (32 lanes x 32 columns), bias / residual / activation-backward / BatchNorm statistics,
+//                            bf16 staging tile in smem, 16-byte row-contiguous stores
+// The product is computed TRANSPOSED, D[channel, pixel] = W[channel, :] . A[pixel, :], i.e. the weight panel is the UMMA
+// "A" operand (M = 128 output channels = TMEM lanes) and the activation tile the "B" operand (N = 128 pixels = TMEM columns).
+// Each epilogue thread then owns ONE output channel: bias is a scalar, the per-channel BatchNorm sums are thread-local (no
+// shuffles, no smem atomics) and are flushed with one fp64 atomic per channel per CTA.  The epilogue of tile j overlaps the
+// MMAs of tile j+1 and the TMA loads of tiles j+2...
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;      // pixels per tile  (UMMA N)
+constexpr int TC_BN = 128;      // channels per tile (UMMA M)
+constexpr int TC_BK = 32;       // k per stage (64-byte rows)
+constexpr int TC_STAGE = TC_BM * TC_BK * 2;   // 8 KB
+constexpr int TC_WBLK = TC_BN * TC_BK * 2;    // 8 KB per k-block of the weight panel
+constexpr int TC_LDO = TC_BN + 8;             // bf16 staging row stride (elements)
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 12;
+constexpr int TC_TMEM_COLS = 256;             // 2 accumulators x 128 fp32 columns
+
+enum { TEPI_STORE = 0, TEPI_STORE_R = 1, TEPI_SILU_BWD = 2 };
+
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  // K-major operand, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (16 B; unused for swizzled K-major) bits [16,30)
+  d |= (uint64_t)(512 >> 4) << 32;           // stride byte offset = 512 B bits [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version 1 (Blackwell)
+  d |= (uint64_t)4 << 61;                    // layout type: SWIZZLE_64B
+  return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 128 (>>3), M = 128 (>>4)
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(TC_BN >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                                   const cvb_gemm_args p, int NST) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * TC_BN;
+  const int KT = (p.K + TC_BK - 1) / TC_BK;
+  const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
+  const int my_tiles = (m_tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int total = my_tiles * KT;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;                    // resident weight panel: KT blocks [128 ch][32 k]
+  uint8_t* sA = sW + KT * TC_WBLK;       // activation ring
+  uint8_t* sO = sA + NST * TC_STAGE;     // bf16 [128 pix][TC_LDO] staging (aux in / result out)
+  __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t wbar, tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ double s_samp[2][128];
+
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&wbar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_mbar_init();
+  }
+  if (tid < 128) { s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
+  if (warp == 1) {  // TMEM allocation (whole warp), address published through smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(&wbar, (uint32_t)KT * TC_WBLK);
+      for (int kt = 0; kt < KT; ++kt) tma_load_2d(sW + kt * TC_WBLK, &tmW, &wbar, kt * TC_BK, n0);
+      for (int it = 0; it < total; ++it) {
+        const int stage = it % NST;
+        if (it >= NST) mbar_wait(&empty[stage], ((it / NST) - 1) & 1);  // MMAs that read this slot have completed
+        const int j = it / KT, kt = it - j * KT;
+        const int m0 = ((int)blockIdx.y + j * (int)gridDim.y) * TC_BM;
+        mbar_expect_tx(&full[stage], TC_STAGE);
+        tma_load_2d(sA + stage * TC_STAGE, &tmA, &full[stage], kt * TC_BK, m0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      mbar_wait(&wbar, 0);
+      int it = 0;
+      for (int j = 0; j < my_tiles; ++j) {
+        const int buf = j & 1;
+        if (j >= 2) mbar_wait(&tempty[buf], ((j >> 1) - 1) & 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TC_BM);
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+          const int stage = it % NST;
+          mbar_wait(&full[stage], (it / NST) & 1);
+          tc_fence_after();
+          const uint32_t wa = smem_u32(sW + kt * TC_WBLK), aa = smem_u32(sA + stage * TC_STAGE);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_f16(tmem_d, umma_desc_sw64(wa + k * 32), umma_desc_sw64(aa + k * 32), (kt | k) ? 1u : 0u);
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&tfull[buf]);      // accumulator complete
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (threads 64..191): one output channel per thread
+    const int et = tid - 64;                 // 0..127
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int ch_local = quad * 32 + lane;   // output channel within the tile == TMEM lane
+    const int ch = n0 + ch_local;
+    const bool ch_ok = ch < p.N;
+    const float bias = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
+    const float ep0 = (EPI == TEPI_SILU_BWD && ch_ok && p.e_p0) ? __ldg(p.e_p0 + ch) : 1.f;
+    const float ep1 = (EPI == TEPI_SILU_BWD && ch_ok && p.e_p1) ? __ldg(p.e_p1 + ch) : 0.f;
+    constexpr bool has_aux = (EPI != TEPI_STORE);
+    const bf16* __restrict__ AUX = static_cast<const bf16*>(EPI == TEPI_STORE_R ? p.R : p.Y);
+    const int ldaux = EPI == TEPI_STORE_R ? p.ldr : p.ldy;
+    const bool want_samp = p.samp_sum != nullptr;
+    const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
+    float cs = 0.f, cq = 0.f;  // this channel's statistics over all tiles of the CTA
+    bf16* __restrict__ Cg = static_cast<bf16*>(p.C);
+    constexpr int CGS = TC_BN / 8;
+
+    auto issue_aux = [&](int j) {
+      const int m0 = ((int)blockIdx.y + j * (int)gridDim.y) * TC_BM;
+      for (int c = et; c < TC_BM * CGS; c += 128) {
+        const int row = c / CGS, cgc = c % CGS;
+        const int m = m0 + row, n = n0 + cgc * 8;
+        const bool ok = (m < p.M) && (n < p.N);
+        cp_async16(smem_u32(sO + row * (TC_LDO * 2) + cgc * 16), AUX + (ok ? (size_t)m * ldaux + n : 0), ok);
+      }
+      cp_async_commit();
+    };
+    if (has_aux && my_tiles > 0) issue_aux(0);
+
+    for (int j = 0; j < my_tiles; ++j) {
+      const int buf = j & 1;
+      const int m0 = ((int)blockIdx.y + j * (int)gridDim.y) * TC_BM;
+      if (has_aux) {
+        cp_async_wait<0>();
+        epi_bar_sync();  // aux tile visible to all epilogue threads
+      }
+      mbar_wait(&tfull[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TC_BM);
+#pragma unroll 1
+      for (int cc = 0; cc < TC_BM / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(taddr + cc * 32, r);
+        bf16* so = reinterpret_cast<bf16*>(sO) + (cc * 32) * TC_LDO + ch_local;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int m = m0 + cc * 32 + i;
+          float v = __uint_as_float(r[i]) + (m < p.M ? bias : 0.f);  // rows >= M have zero A rows: they stay exactly 0
+          float y = 0.f;
+          if (has_aux) y = __bfloat162float(so[i * TC_LDO]);
+          if (EPI == TEPI_STORE_R) v += y;
+          if (EPI == TEPI_SILU_BWD) v *= silu_grad_f(fmaf(ep0, y, ep1));
+          const bf16 vb = __float2bfloat16_rn(v);
+          so[i * TC_LDO] = vb;
+          const float vr = __bfloat162float(vb);  // statistics of the STORED values
+          cs += vr;
+          cq = fmaf(vr, EPI == TEPI_SILU_BWD ? y : vr, cq);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);  // 4 arrivals (one per epilogue warp) release the accumulator
+      epi_bar_sync();                            // staged tile complete
+      const int first_sample = m0 / rps;
+      for (int c = et; c < TC_BM * CGS; c += 128) {
+        const int row = c / CGS, cgc = c % CGS;
+        const int m = m0 + row, n = n0 + cgc * 8;
+        const uint4 u = *reinterpret_cast<const uint4*>(sO + row * (TC_LDO * 2) + cgc * 16);
+        if (m < p.M && n < p.N) stg16(Cg + (size_t)m * p.ldc + n, u);
+        if (want_samp) {
+          float f[8];
+          unpack8(u, f);
+          float sv = 0.f, sq = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sv += f[e]; sq = fmaf(f[e], f[e], sq); }
+#pragma unroll
+          for (int o = CGS / 2; o > 0; o >>= 1) {
+            sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+          if (cgc == 0 && m < p.M) {
+            atomicAdd(&s_samp[0][m / rps - first_sample], (double)sv);
+            atomicAdd(&s_samp[1][m / rps - first_sample], (double)sq);
+          }
+        }
+      }
+      epi_bar_sync();  // staging tile free again (and s_samp complete)
+      if (want_samp) {
+        const int mlast = min(m0 + TC_BM, p.M) - 1;
+        const int nsamp = mlast / rps - first_sample + 1;
+        if (et < nsamp) {
+          atomicAdd(p.samp_sum + first_sample + et, s_samp[0][et]);
+          atomicAdd(p.samp_sq + first_sample + et, s_samp[1][et]);
+          s_samp[0][et] = 0.0;
+          s_samp[1][et] = 0.0;
+        }
+      }
+      if (has_aux && j + 1 < my_tiles) issue_aux(j + 1);
+    }
+    if (p.col_sum && ch_ok) {
+      atomicAdd(p.col_sum + ch, (double)cs);
+      atomicAdd(p.col_sq + ch, (double)cq);
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+template <int EPI>
+int launch_tc(const cvb_gemm_args& a, cudaStream_t st) {
+  const int KT = (a.K + TC_BK - 1) / TC_BK;
+  const size_t fixed = (size_t)KT * TC_WBLK + (size_t)TC_BM * TC_LDO * 2 + 1024;
+  const size_t budget = (size_t)216 * 1024;
+  if (fixed + 4 * TC_STAGE > budget) return -1;  // weight panel too large: caller falls back to the mma.sync kernel
+  int nst = (int)((budget - fixed) / TC_STAGE);
+  if (nst > TC_MAX_STAGES) nst = TC_MAX_STAGES;
+  const size_t smem = fixed + (size_t)nst * TC_STAGE;
+  static bool attr = false;
+  if (!attr) {
+    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    attr = true;
+  }
+  const int n_tiles = (a.N + TC_BN - 1) / TC_BN, m_tiles = (a.M + TC_BM - 1) / TC_BM;
+  int gy = (cvb_num_sms() + n_tiles - 1) / n_tiles;  // one persistent CTA per SM
+  if (gy > m_tiles) gy = m_tiles;
+  if (gy < 1) gy = 1;
+  CUtensorMap tmA, tmW;
+  if (cvb_make_tmap_2d_k32(&tmA, a.A, a.M, a.K, a.lda, TC_BM)) return 1;
+  if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, TC_BN)) return 1;
+  dim3 grid(n_tiles, gy);
+  pw_gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, a, nst);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// Returns -1 when the shape / mode is not handled by the tcgen05 kernel (caller uses the mma.sync kernel), 0 on success, > 0 on error.
+int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st) {
+  if (a.a_mode != CVB_A_RAW) return -1;
+  if (a.e_mode == CVB_E_STORE) return a.R ? launch_tc<TEPI_STORE_R>(a, st) : launch_tc<TEPI_STORE>(a, st);
+  if (a.e_mode == CVB_E_SILU_BWD) return launch_tc<TEPI_SILU_BWD>(a, st);
+  return -1;
+}

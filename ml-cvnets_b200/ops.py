@@ -35,6 +35,11 @@ def _count(n=1):
     launch_count += n
 
 
+def set_tc_enabled(on: bool) -> bool:
+    """Testing hook: route prologue-free GEMMs to the tcgen05 kernel (default) or to the mma.sync kernel."""
+    return bool(_lib().cvb_set_tc_enabled(int(on)))
+
+
 # --------------------------------------------------------------------------------------------------------------- GEMM
 def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: int = A_RAW, A2: Optional[Tensor] = None,
             a_p: Sequence[Optional[Tensor]] = (None, None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,

@@ -115,6 +115,47 @@ def test_pw_gemm_small_m_large_k(ops, M, N, K, a_mode):
     close_stat(col[0], out.float().sum(0), "col_sum")
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 64, 64), (1000, 128, 128), (513, 264, 40), (4096, 384, 192), (70000, 128, 64), (33, 1000, 512)])
+@pytest.mark.parametrize("epi", ["store", "store_r", "silu_bwd"])
+def test_pw_gemm_tcgen05_vs_mma_sync(ops, M, N, K, epi):
+    """The tcgen05/TMEM kernel and the mma.sync kernel implement the same contract: same inputs -> same outputs / statistics
+    (up to fp32 accumulation order), and both match the fp32 restatement."""
+    rps = 64
+    nb = (M + rps - 1) // rps
+    A = bf(rnd(M, K, seed=301))
+    W = bf(rnd(N, K, scale=K ** -0.5, seed=302))
+    bias = rnd(N, seed=303)
+    aux = bf(rnd(M, N, seed=304))
+    sc, sh = 1 + 0.2 * rnd(N, seed=305), 0.3 * rnd(N, seed=306)
+    outs = []
+    for tc in (True, False):
+        prev = ops.set_tc_enabled(tc)
+        try:
+            col = torch.zeros(2, N, device="cuda", dtype=torch.float64)
+            samp = torch.zeros(2, nb, device="cuda", dtype=torch.float64)
+            if epi == "store":
+                o = ops.pw_gemm(A, W, N, bias=bias, col_stats=col, samp_stats=samp, rows_per_sample=rps)
+            elif epi == "store_r":
+                o = ops.pw_gemm(A, W, N, bias=bias, R=aux, col_stats=col, samp_stats=samp, rows_per_sample=rps)
+            else:
+                o = ops.pw_gemm(A, W, N, e_mode=ops.E_SILU_BWD, Y=aux, e_p=(sc, sh), col_stats=col)
+            torch.cuda.synchronize()
+            outs.append((o, col.clone(), samp.clone()))
+        finally:
+            ops.set_tc_enabled(prev)
+    acc = A.float() @ W.float().t()
+    ref = acc + bias if epi == "store" else acc + bias + aux.float() if epi == "store_r" else acc * dsilu(sc * aux.float() + sh)
+    for name, (o, col, samp) in zip(("tcgen05", "mma.sync"), outs):
+        close(o, ref, what=f"{name} out")
+        of = o.float()
+        close_stat(col[0], of.sum(0), f"{name} col_sum")
+        close_stat(col[1], (of * (aux.float() if epi == "silu_bwd" else of)).sum(0), f"{name} col_sq")
+    close(outs[0][0], outs[1][0], rtol=1e-2, atol=1e-2 * float(ref.abs().max()), what="tcgen05 vs mma.sync")
+    if epi != "silu_bwd":
+        close_stat(outs[0][2][0], outs[1][2][0], "samp_sum tc vs mma")
+        close_stat(outs[0][2][1], outs[1][2][1], "samp_sq tc vs mma")
+
+
 def test_pw_gemm_silu(ops):
     M, N, K = 384, 96, 64
     A, W, bias = bf(rnd(M, K)), bf(rnd(N, K, scale=0.1)), rnd(N)
