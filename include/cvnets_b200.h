@@ -104,6 +104,12 @@ typedef struct {
 } cvb_wgrad_args;
 CVB_API int cvb_pw_wgrad(const cvb_wgrad_args* args, cvb_stream_t stream);
 
+/* OUT[m,k] = load(A[,A2])[m,k] (bf16): materialises one of the operand load modes above.  Used for WIDE layers (K >= 384 with
+ * several N tiles, all late-stage and L2-resident) where applying the prologue once is cheaper than once per N tile. */
+CVB_API int cvb_apply_load_mode(const void* A, int lda, const void* A2, int lda2, int mode, const float* p0, const float* p1, const float* p2,
+                                const float* row_mean, const float* row_rstd, int rows_per_sample, void* OUT, int ldo, int64_t M, int K,
+                                cvb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Depthwise 3x3 convolution, pad 1, stride 1|2, NHWC (ConvLayer2d(groups=C): mobilenetv2.py:194-207,
  * mobilevit_block.py:369-379).  The producer's BN(+SiLU) is applied on load (x_mode RAW/AFF/AFF_SILU); zero padding

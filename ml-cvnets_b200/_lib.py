@@ -82,6 +82,8 @@ _SIGS = {
     "cvb_pw_gemm": (c_int, [POINTER(GemmArgs), c_void_p]),
     "cvb_set_tc_enabled": (c_int, [c_int]),
     "cvb_pw_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
+    "cvb_apply_load_mode": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                    c_int, c_int64, c_int, c_void_p]),
     "cvb_dw_fwd": (c_int, [POINTER(DwFwdArgs), c_void_p]),
     "cvb_dw_bwd": (c_int, [POINTER(DwBwdArgs), c_void_p]),
     "cvb_stem_im2col": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),

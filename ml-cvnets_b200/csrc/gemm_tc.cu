@@ -6,7 +6,7 @@
 //   warp 0    TMA producer : ring of A stages [128 pixels x 32 k] (cp.async.bulk.tensor.2d, 64-byte swizzle) across ALL tiles
 //   warp 1    MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16; the accumulator lives in TMEM,
 //                            double buffered (2 x 128 columns), completion is signalled with tcgen05.commit -> mbarrier
-//   warps 2-5 epilogue     : tcgen05.ld (32 lanes x 32 columns), bias / residual / activation-backward / BatchNorm statistics,
+//   warps 2-9 epilogue     : tcgen05.ld (32 lanes x 32 columns), bias / residual / activation-backward / BatchNorm statistics,
 //                            bf16 staging tile in smem, 16-byte row-contiguous stores
 // The product is computed TRANSPOSED, D[channel, pixel] = W[channel, :] . A[pixel, :], i.e. the weight panel is the UMMA
 // "A" operand (M = 128 output channels = TMEM lanes) and the activation tile the "B" operand (N = 128 pixels = TMEM columns).
@@ -23,7 +23,9 @@ constexpr int TC_BK = 32;       // k per stage (64-byte rows)
 constexpr int TC_STAGE = TC_BM * TC_BK * 2;   // 8 KB
 constexpr int TC_WBLK = TC_BN * TC_BK * 2;    // 8 KB per k-block of the weight panel
 constexpr int TC_LDO = TC_BN + 8;             // bf16 staging row stride (elements)
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;             // two warps per TMEM lane quadrant, each draining half of the pixel columns
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_TMEM_COLS = 256;             // 2 accumulators x 128 fp32 columns
 
@@ -70,9 +72,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
-template <int EPI>
+// WRES: the weight panel [128 ch, K] stays resident in smem (loaded once); otherwise (large K) its k-blocks stream through the
+// ring next to the activation k-blocks (they are L2 hits: every CTA of an N tile reads the same panel).
+template <int EPI, bool WRES>
 __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                                                                    const cvb_gemm_args p, int NST) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -84,9 +88,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sW = smem;                    // resident weight panel: KT blocks [128 ch][32 k]
-  uint8_t* sA = sW + KT * TC_WBLK;       // activation ring
-  uint8_t* sO = sA + NST * TC_STAGE;     // bf16 [128 pix][TC_LDO] staging (aux in / result out)
+  constexpr int RING_STAGE = WRES ? TC_STAGE : (TC_STAGE + TC_WBLK);
+  uint8_t* sW = smem;                               // resident weight panel: KT blocks [128 ch][32 k] (WRES only)
+  uint8_t* sA = sW + (WRES ? KT * TC_WBLK : 0);     // ring: activation block (+ weight block when streaming)
+  uint8_t* sO = sA + NST * RING_STAGE;              // bf16 [128 pix][TC_LDO] staging (aux in / result out)
   __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t wbar, tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_smem;
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&wbar, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_mbar_init();
   }
   if (tid < 128) { s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
@@ -111,21 +116,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      mbar_expect_tx(&wbar, (uint32_t)KT * TC_WBLK);
-      for (int kt = 0; kt < KT; ++kt) tma_load_2d(sW + kt * TC_WBLK, &tmW, &wbar, kt * TC_BK, n0);
+      if (WRES) {
+        mbar_expect_tx(&wbar, (uint32_t)KT * TC_WBLK);
+        for (int kt = 0; kt < KT; ++kt) tma_load_2d(sW + kt * TC_WBLK, &tmW, &wbar, kt * TC_BK, n0);
+      }
       for (int it = 0; it < total; ++it) {
         const int stage = it % NST;
         if (it >= NST) mbar_wait(&empty[stage], ((it / NST) - 1) & 1);  // MMAs that read this slot have completed
         const int j = it / KT, kt = it - j * KT;
         const int m0 = ((int)blockIdx.y + j * (int)gridDim.y) * TC_BM;
-        mbar_expect_tx(&full[stage], TC_STAGE);
-        tma_load_2d(sA + stage * TC_STAGE, &tmA, &full[stage], kt * TC_BK, m0);
+        mbar_expect_tx(&full[stage], RING_STAGE);
+        tma_load_2d(sA + stage * RING_STAGE, &tmA, &full[stage], kt * TC_BK, m0);
+        if (!WRES) tma_load_2d(sA + stage * RING_STAGE + TC_STAGE, &tmW, &full[stage], kt * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      mbar_wait(&wbar, 0);
+      if (WRES) mbar_wait(&wbar, 0);
       int it = 0;
       for (int j = 0; j < my_tiles; ++j) {
         const int buf = j & 1;
@@ -136,7 +144,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
           const int stage = it % NST;
           mbar_wait(&full[stage], (it / NST) & 1);
           tc_fence_after();
-          const uint32_t wa = smem_u32(sW + kt * TC_WBLK), aa = smem_u32(sA + stage * TC_STAGE);
+          const uint32_t aa = smem_u32(sA + stage * RING_STAGE);
+          const uint32_t wa = WRES ? smem_u32(sW + kt * TC_WBLK) : aa + TC_STAGE;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_f16(tmem_d, umma_desc_sw64(wa + k * 32), umma_desc_sw64(aa + k * 32), (kt | k) ? 1u : 0u);
@@ -147,8 +156,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
     }
   } else {
     // ===================================================== epilogue warps (threads 64..191): one output channel per thread
-    const int et = tid - 64;                 // 0..127
+    const int et = tid - 64;                 // 0..TC_EPI_THREADS-1
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;       // which half of the pixel columns this warp drains
     const int ch_local = quad * 32 + lane;   // output channel within the tile == TMEM lane
     const int ch = n0 + ch_local;
     const bool ch_ok = ch < p.N;
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
 
     auto issue_aux = [&](int j) {
       const int m0 = ((int)blockIdx.y + j * (int)gridDim.y) * TC_BM;
-      for (int c = et; c < TC_BM * CGS; c += 128) {
+      for (int c = et; c < TC_BM * CGS; c += TC_EPI_THREADS) {
         const int row = c / CGS, cgc = c % CGS;
         const int m = m0 + row, n = n0 + cgc * 8;
         const bool ok = (m < p.M) && (n < p.N);
@@ -186,15 +196,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
       mbar_wait(&tfull[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TC_BM);
+      const bool full_tile = (m0 + TC_BM <= p.M);  // rows >= M have zero A rows; only their bias must be masked (last tile)
 #pragma unroll 1
-      for (int cc = 0; cc < TC_BM / 32; ++cc) {
+      for (int cc = chalf * (TC_BM / 64); cc < (chalf + 1) * (TC_BM / 64); ++cc) {
         uint32_t r[32];
         tmem_ld32(taddr + cc * 32, r);
         bf16* so = reinterpret_cast<bf16*>(sO) + (cc * 32) * TC_LDO + ch_local;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int m = m0 + cc * 32 + i;
-          float v = __uint_as_float(r[i]) + (m < p.M ? bias : 0.f);  // rows >= M have zero A rows: they stay exactly 0
+          float v = __uint_as_float(r[i]) + ((full_tile || m0 + cc * 32 + i < p.M) ? bias : 0.f);
           float y = 0.f;
           if (has_aux) y = __bfloat162float(so[i * TC_LDO]);
           if (EPI == TEPI_STORE_R) v += y;
@@ -208,10 +218,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);  // 4 arrivals (one per epilogue warp) release the accumulator
+      if (lane == 0) mbar_arrive(&tempty[buf]);  // one arrival per epilogue warp releases the accumulator
       epi_bar_sync();                            // staged tile complete
       const int first_sample = m0 / rps;
-      for (int c = et; c < TC_BM * CGS; c += 128) {
+      for (int c = et; c < TC_BM * CGS; c += TC_EPI_THREADS) {
         const int row = c / CGS, cgc = c % CGS;
         const int m = m0 + row, n = n0 + cgc * 8;
         const uint4 u = *reinterpret_cast<const uint4*>(sO + row * (TC_LDO * 2) + cgc * 16);
@@ -261,18 +271,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
   }
 }
 
-template <int EPI>
-int launch_tc(const cvb_gemm_args& a, cudaStream_t st) {
-  const int KT = (a.K + TC_BK - 1) / TC_BK;
-  const size_t fixed = (size_t)KT * TC_WBLK + (size_t)TC_BM * TC_LDO * 2 + 1024;
+template <int EPI, bool WRES>
+int launch_tc_impl(const cvb_gemm_args& a, cudaStream_t st, size_t fixed, int stage_bytes) {
   const size_t budget = (size_t)216 * 1024;
-  if (fixed + 4 * TC_STAGE > budget) return -1;  // weight panel too large: caller falls back to the mma.sync kernel
-  int nst = (int)((budget - fixed) / TC_STAGE);
+  int nst = (int)((budget - fixed) / stage_bytes);
   if (nst > TC_MAX_STAGES) nst = TC_MAX_STAGES;
-  const size_t smem = fixed + (size_t)nst * TC_STAGE;
+  const size_t smem = fixed + (size_t)nst * stage_bytes;
   static bool attr = false;
   if (!attr) {
-    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<EPI, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr = true;
   }
   const int n_tiles = (a.N + TC_BN - 1) / TC_BN, m_tiles = (a.M + TC_BM - 1) / TC_BM;
@@ -283,9 +290,18 @@ int launch_tc(const cvb_gemm_args& a, cudaStream_t st) {
   if (cvb_make_tmap_2d_k32(&tmA, a.A, a.M, a.K, a.lda, TC_BM)) return 1;
   if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, TC_BN)) return 1;
   dim3 grid(n_tiles, gy);
-  pw_gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, a, nst);
+  pw_gemm_tc_kernel<EPI, WRES><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, a, nst);
   CVB_LAUNCH_CHECK();
   return 0;
+}
+
+template <int EPI>
+int launch_tc(const cvb_gemm_args& a, cudaStream_t st) {
+  const int KT = (a.K + TC_BK - 1) / TC_BK;
+  const size_t stagebuf = (size_t)TC_BM * TC_LDO * 2 + 1024;
+  const size_t panel = (size_t)KT * TC_WBLK;
+  if (panel + stagebuf + 6 * TC_STAGE <= (size_t)216 * 1024) return launch_tc_impl<EPI, true>(a, st, panel + stagebuf, TC_STAGE);
+  return launch_tc_impl<EPI, false>(a, st, stagebuf, TC_STAGE + TC_WBLK);  // large K: weight k-blocks ride the ring
 }
 
 }  // namespace
@@ -293,6 +309,8 @@ int launch_tc(const cvb_gemm_args& a, cudaStream_t st) {
 // Returns -1 when the shape / mode is not handled by the tcgen05 kernel (caller uses the mma.sync kernel), 0 on success, > 0 on error.
 int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st) {
   if (a.a_mode != CVB_A_RAW) return -1;
+  // every epilogue thread owns one of 128 output channels: narrow layers would idle most of them -> mma.sync kernel
+  if (a.N < 96 || (a.N % 128 != 0 && a.N % 128 < 64 && a.N < 256)) return -1;
   if (a.e_mode == CVB_E_STORE) return a.R ? launch_tc<TEPI_STORE_R>(a, st) : launch_tc<TEPI_STORE>(a, st);
   if (a.e_mode == CVB_E_SILU_BWD) return launch_tc<TEPI_SILU_BWD>(a, st);
   return -1;

@@ -185,6 +185,36 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(const bf16* __restrict__ Y
   }
 }
 
+// ------------------------------------------------------------------------------------------------ elementwise: operand load modes
+// OUT[m, k] = load(A[, A2])[m, k]: materialises a prologue once for WIDE layers (many N tiles would each repeat it in the GEMM)
+__global__ void __launch_bounds__(NT) apply_load_mode_kernel(const bf16* __restrict__ A, const bf16* __restrict__ A2, int mode,
+                                                             const float* __restrict__ p0, const float* __restrict__ p1,
+                                                             const float* __restrict__ p2, const float* __restrict__ row_mean,
+                                                             const float* __restrict__ row_rstd, int rps, bf16* __restrict__ OUT, int64_t nvec,
+                                                             int cgs, int lda, int lda2, int ldo) {
+  for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
+    const int64_t m = v / cgs;
+    const int c = (int)(v % cgs) * 8;
+    float f[8];
+    unpack8(ldg16_stream(A + m * lda + c), f);
+    if (mode == CVB_A_BNB) {
+      float y[8];
+      unpack8(ldg16_stream(A2 + m * lda2 + c), y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(__ldg(p0 + c + j), f[j], fmaf(__ldg(p1 + c + j), y[j], __ldg(p2 + c + j)));
+    } else if (mode == CVB_A_GN) {
+      const int b = (int)(m / rps);
+      const float mu = __ldg(row_mean + b), rs = __ldg(row_rstd + b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf((f[j] - mu) * rs, __ldg(p0 + c + j), __ldg(p1 + c + j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = apply_mode(mode, f[j], (mode == CVB_A_SILU) ? 1.f : __ldg(p0 + c + j), (mode == CVB_A_SILU) ? 0.f : __ldg(p1 + c + j));
+    }
+    stg16(OUT + m * ldo + c, pack8(f));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ per-channel reductions
 // mode 0: BN backward reduce: dz = dout (act 0) or dout*silu'(sc*y+sh) (act 1); s0 += dz, s1 += dz*y; optional DZ store.
 __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const bf16* __restrict__ DOUT, const bf16* __restrict__ Y, const float* __restrict__ scale,
@@ -464,6 +494,22 @@ extern "C" int cvb_bn_apply(const void* Y, const float* scale, const float* shif
   int64_t nvec = M * (C / 8);
   bn_apply_kernel<<<grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(Y), scale, shift, act,
                                                                                static_cast<const bf16*>(R), static_cast<bf16*>(OUT), nvec, C / 8);
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_apply_load_mode(const void* A, int lda, const void* A2, int lda2, int mode, const float* p0, const float* p1, const float* p2,
+                                   const float* row_mean, const float* row_rstd, int rows_per_sample, void* OUT, int ldo, int64_t M, int K,
+                                   cvb_stream_t stream) {
+  CVB_CHECK(A && OUT && M > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0, "cvb_apply_load_mode: bad arguments");
+  CVB_CHECK(mode >= CVB_A_AFF && mode <= CVB_A_BNB, "cvb_apply_load_mode: mode %d", mode);
+  if (mode == CVB_A_BNB) CVB_CHECK(A2 && p0 && p1 && p2 && lda2 % 8 == 0, "cvb_apply_load_mode: BNB needs A2 and p0/p1/p2");
+  if (mode == CVB_A_GN) CVB_CHECK(row_mean && row_rstd && rows_per_sample > 0 && p0 && p1, "cvb_apply_load_mode: GN needs statistics");
+  if (mode == CVB_A_AFF || mode == CVB_A_AFF_SILU) CVB_CHECK(p0 && p1, "cvb_apply_load_mode: AFF needs p0/p1");
+  int64_t nvec = M * (K / 8);
+  apply_load_mode_kernel<<<grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(A), static_cast<const bf16*>(A2), mode, p0, p1, p2, row_mean, row_rstd, rows_per_sample > 0 ? rows_per_sample : 1,
+      static_cast<bf16*>(OUT), nvec, K / 8, lda, lda2, ldo);
   CVB_LAUNCH_CHECK();
   return 0;
 }

@@ -50,6 +50,11 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
     lib = _lib()
     M = A.shape[0]
     K = A.shape[1] if K is None else K
+    if a_mode != A_RAW and K >= 384 and N > 128:
+        # wide late-stage layer (small, L2-resident operand): apply the prologue once instead of once per N tile, then run the
+        # prologue-free (tcgen05) GEMM
+        A = apply_load_mode(A, a_mode, K, A2=A2, a_p=a_p, row_stats=row_stats, rows_per_sample=rows_per_sample)
+        a_mode, A2, a_p, row_stats = A_RAW, None, (None, None, None), None
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
     a = L.GemmArgs()
@@ -76,6 +81,19 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
     if samp_stats is not None:
         a.samp_sum, a.samp_sq = samp_stats[0].data_ptr(), samp_stats[1].data_ptr()
     L.check(lib.cvb_pw_gemm(ctypes.byref(a), _stream()), "cvb_pw_gemm")
+    _count()
+    return out
+
+
+def apply_load_mode(A: Tensor, mode: int, K: int, *, A2: Optional[Tensor] = None, a_p: Sequence[Optional[Tensor]] = (None, None, None),
+                    row_stats: Optional[Tuple[Tensor, Tensor]] = None, rows_per_sample: int = 0) -> Tensor:
+    lib = _lib()
+    M = A.shape[0]
+    out = torch.empty((M, K), device=A.device, dtype=torch.bfloat16)
+    p2 = a_p[2] if len(a_p) > 2 else None
+    L.check(lib.cvb_apply_load_mode(A.data_ptr(), A.stride(0), _p(A2), A2.stride(0) if A2 is not None else 0, mode, _p(a_p[0]), _p(a_p[1]), _p(p2),
+                                    _p(row_stats[0]) if row_stats is not None else None, _p(row_stats[1]) if row_stats is not None else None,
+                                    rows_per_sample, out.data_ptr(), out.stride(0), M, K, _stream()), "cvb_apply_load_mode")
     _count()
     return out
 
