@@ -54,7 +54,9 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
         # wide late-stage layer (small, L2-resident operand): apply the prologue once instead of once per N tile, then run the
         # prologue-free (tcgen05) GEMM
         A = apply_load_mode(A, a_mode, K, A2=A2, a_p=a_p, row_stats=row_stats, rows_per_sample=rows_per_sample)
-        a_mode, A2, a_p, row_stats = A_RAW, None, (None, None, None), None
+        a_mode, A2, a_p = A_RAW, None, (None, None, None)
+        if e_mode != E_GN_BWD:  # the GroupNorm-backward epilogue reads the same per-sample statistics
+            row_stats = None
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
     a = L.GemmArgs()
