@@ -191,24 +191,33 @@ class OpTimer:
                 s.record()
                 out = _orig(*a, **kw)
                 e.record()
-                self.rec.append((_name, s, e))
+                shape = tuple(tuple(x.shape) for x in a if isinstance(x, torch.Tensor))[:2] + tuple(x for x in a if isinstance(x, int))[:5]
+                self.rec.append((_name, s, e, shape))
                 return out
 
             setattr(self.ops, name, wrapped)
             setattr(Fn.ops, name, wrapped)
 
     def summary(self, steps):
-        agg = {}
-        for name, s, e in self.rec:
+        agg, shp = {}, {}
+        for name, s, e, shape in self.rec:
+            t = s.elapsed_time(e)
             a = agg.setdefault(name, [0, 0.0])
             a[0] += 1
-            a[1] += s.elapsed_time(e)
-        return {k: {"n_per_step": v[0] / steps, "ms_per_step": v[1] / steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+            a[1] += t
+            if name in ("pw_wgrad", "dw_fwd", "dw_bwd"):
+                b = shp.setdefault(name + str(shape), [0, 0.0])
+                b[0] += 1
+                b[1] += t
+        out = {k: {"n_per_step": v[0] / steps, "ms_per_step": v[1] / steps} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        out["_by_shape"] = {k: {"n_per_step": v[0] / steps, "us_each": 1e3 * v[1] / v[0]} for k, v in sorted(shp.items(), key=lambda kv: -kv[1][1])[:40]}
+        return out
 
 
 def run_ours(args, rank, world, local_rank):
     import ml_cvnets_b200 as m
     from ml_cvnets_b200 import ops
+    from ml_cvnets_b200 import dist as D
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -216,11 +225,20 @@ def run_ours(args, rank, world, local_rank):
     B = args.batch
     model = m.MobileViTv2(m.default_opts(width_multiplier=1.0)).to(dev).train()
     train_model = model
-    if world > 1:
+    use_ddp_wrapper = world > 1 and args.no_graph
+    if use_ddp_wrapper:
+        # eager multi-GPU path: the reference's own wrapper (main_train.py:90-96), bucketed all-reduce overlapped with backward
         from torch.nn.parallel import DistributedDataParallel as DDP
         train_model = DDP(model, device_ids=[local_rank], output_device=local_rank, broadcast_buffers=True, gradient_as_bucket_view=True)
+    elif world > 1:
+        # graph-captured multi-GPU path: same semantics as DDP's gradient averaging (SUM / world of the fp32 gradients over
+        # NCCL), issued as ONE flat all-reduce after backward so that it is part of the captured CUDA graph.  19.6 MB per step
+        # (~0.1 ms on NVLink) -- overlap with backward would buy nothing here.  Initial weights: broadcast from rank 0.
+        # BatchNorm running statistics stay per-rank (DDP's per-forward buffer broadcast, SURVEY.md C2, is not replayed).
+        for t in list(model.parameters()) + list(model.buffers()):
+            torch.distributed.broadcast(t.data, src=0)
     groups, _ = model.get_trainable_parameters(weight_decay=0.05, no_decay_bn_filter_bias=True)
-    opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999), fused=True, capturable=(world == 1 and not args.no_graph))
+    opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999), fused=True, capturable=not args.no_graph)
     scaler = torch.amp.GradScaler("cuda", enabled=True)  # the reference enables it even for bf16 (main_train.py:114)
     params = [p for p in model.parameters()]
 
@@ -229,6 +247,8 @@ def run_ours(args, rank, world, local_rank):
         loss = F.cross_entropy(logits.float(), y, label_smoothing=0.1)
         opt.zero_grad(set_to_none=True)
         scaler.scale(loss).backward()
+        if world > 1 and not use_ddp_wrapper:
+            D.allreduce_mean_([p.grad for p in params], world)
         scaler.unscale_(opt)
         torch.nn.utils.clip_grad_norm_(params, 10.0)
         scaler.step(opt)
@@ -255,8 +275,9 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(x_dev, y_dev)
     # ---- whole training step as ONE CUDA graph (single GPU): fwd + loss + bwd + unscale/clip + fused AdamW + scaler update.
-    # Kernel arguments (incl. TMA tensor maps) are baked at capture; inputs live in static buffers.  Multi-GPU (DDP) stays eager.
-    use_graph = (world == 1) and not args.no_graph and not args.profile_ops
+    # Kernel arguments (incl. TMA tensor maps) are baked at capture; inputs live in static buffers.  At N > 1 the flat NCCL
+    # gradient all-reduce is captured in the same graph.
+    use_graph = not args.no_graph and not args.profile_ops
     graph = None
     if use_graph:
         static_x, static_y = x_dev.clone(), y_dev.clone()
@@ -402,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "MobileViTv2-1.0 bf16 training step, synthetic ImageNet 256x256 (BASELINE.json configs[1])",
-                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "optimizer": "AdamW(fused) + GradScaler + clip_grad_norm 10", "execution": "one CUDA graph per step" if use_graph else "eager launches",
+                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_sync": ("none" if world == 1 else "DDP wrapper (eager)" if use_ddp_wrapper else "flat fp32 NCCL all-reduce inside the CUDA graph"), "optimizer": "AdamW(fused) + GradScaler + clip_grad_norm 10", "execution": "one CUDA graph per step" if use_graph else "eager launches",
                    "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                   "ms_per_step": e2e_ms},
