@@ -12,7 +12,9 @@ namespace {
 constexpr int CB = 64;  // channels per CTA (8 x 16-byte chunks)
 constexpr int NT = 256;
 
-__device__ __forceinline__ uint32_t pix_off(int pix, int ch) { return static_cast<uint32_t>(pix * 128 + ((ch ^ (pix & 7)) << 4)); }
+// smem tiles are plain [pixel][64 channels] (128 B per pixel, no swizzle): every access pattern below touches one pixel's 128 B per
+// quarter-warp / warp and is conflict-free as is, and linear addresses keep the address arithmetic out of the instruction stream
+__device__ __forceinline__ uint32_t pix_off(int pix, int ch) { return static_cast<uint32_t>(pix * 128 + (ch << 4)); }
 
 __device__ __forceinline__ void load8_mode(int mode, const bf16* ptr, const float* p0, const float* p1, float* out) {
   unpack8(ldg16(ptr), out);
@@ -73,6 +75,13 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
 #pragma unroll
     for (int j = 0; j < 4; ++j) wpk[tp][j] = c_ok ? pack_bf162(p.Wt[tp * p.C + c + 2 * j], p.Wt[tp * p.C + c + 2 * j + 1]) : 0u;
 
+  // producer BN scale/shift of this thread's 8 channels (transform role: chunk = lane & 7 == cgi), hoisted out of all loops
+  float xp0[8], xp1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    xp0[j] = (XMODE != CVB_A_RAW && c_ok) ? __ldg(p.x_p0 + c + j) : 1.f;
+    xp1[j] = (XMODE != CVB_A_RAW && c_ok) ? __ldg(p.x_p1 + c + j) : 0.f;
+  }
   for (int i = 0; i < n_img; ++i) {
     const int b = (int)blockIdx.z + i * (int)gridDim.z;
     uint8_t* tile = smem + (i & 1) * buf_bytes;
@@ -86,14 +95,14 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
         for (int jw = lane >> 3; jw < IW; jw += 4) {
           const int w = w_base + jw;
           const int pix = ih * IW + jw;
-          const int lc = c0 + ((pch ^ (pix & 7)) << 3);  // logical channel of this physical chunk
+          const int lc = c0 + (pch << 3);
           if (w < 0 || w >= p.W || lc >= p.C) continue;
           uint4* ptr = reinterpret_cast<uint4*>(tile + pix * 128 + (pch << 4));
           float f[8];
           unpack8(*ptr, f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float z = fmaf(__ldg(p.x_p0 + lc + j), f[j], __ldg(p.x_p1 + lc + j));
+            float z = fmaf(xp0[j], f[j], xp1[j]);
             f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
           }
           *ptr = pack8(f);
@@ -230,6 +239,14 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
     for (int j = 0; j < 4; ++j)
       wpk[tp][j] = cc_ok ? pack_bf162(p.Wt[tp * p.C + cc + 2 * j], p.Wt[tp * p.C + cc + 2 * j + 1]) : 0u;
 
+  // producer BN scale/shift of the CTA's 64 channels live in smem (the register budget of 512 threads is spent on the stencil)
+  __shared__ __align__(16) float s_xp[2][CB];
+  if (tid < CB) {
+    const bool ok = (XMODE != CVB_A_RAW) && (c0 + tid < p.C);
+    s_xp[0][tid] = ok ? __ldg(p.x_p0 + c0 + tid) : 1.f;
+    s_xp[1][tid] = ok ? __ldg(p.x_p1 + c0 + tid) : 0.f;
+  }
+  __syncthreads();
   for (int i = 0; i < n_img; ++i) {
     const int b = (int)blockIdx.z + i * (int)gridDim.z;
     uint8_t* sG = smem + (i & 1) * set_bytes;
@@ -239,20 +256,29 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
     mbar_wait(&bar[i & 1], (i >> 1) & 1);
     // ---- 1. dy = c1*dz + c2*y2 + c3, in place, in-bounds pixels only (the zero-filled halo must stay zero)
     if (GMODE == CVB_A_BNB) {
+      float g0[8], g1[8], g2[8];  // BN-backward coefficients of this thread's chunk (scoped: live only during this pass)
+      const int glc = c0 + (pch << 3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = glc < p.C;
+        g0[j] = ok ? __ldg(p.g_p0 + glc + j) : 0.f;
+        g1[j] = ok ? __ldg(p.g_p1 + glc + j) : 0.f;
+        g2[j] = ok ? __ldg(p.g_p2 + glc + j) : 0.f;
+      }
       for (int gi = warp; gi < GH; gi += NTB / 32) {
         const int oh = gh_base + gi;
         if (oh < 0 || oh >= Ho) continue;
         for (int gj = lane >> 3; gj < GW; gj += 4) {
           const int ow = gw_base + gj;
           const int pix = gi * GW + gj;
-          const int lc = c0 + ((pch ^ (pix & 7)) << 3);
+          const int lc = c0 + (pch << 3);
           if (ow < 0 || ow >= Wo || lc >= p.C) continue;
           uint4* pz = reinterpret_cast<uint4*>(sG + pix * 128 + (pch << 4));
           float f[8], y[8];
           unpack8(*pz, f);
           unpack8(*reinterpret_cast<const uint4*>(sG2 + pix * 128 + (pch << 4)), y);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaf(__ldg(p.g_p0 + lc + j), f[j], fmaf(__ldg(p.g_p1 + lc + j), y[j], __ldg(p.g_p2 + lc + j)));
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
           *pz = pack8(f);
         }
       }
@@ -289,11 +315,15 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
         if (XMODE != CVB_A_RAW) {
           // one sigmoid per element serves both uses: a = z*s (kept in place for phase A) and silu'(z) = s + a*(1-s)
           uint4* px = reinterpret_cast<uint4*>(sX + pix_off((ih + 1) * XW + iw + 1, cgi));
-          float xr[8], av[8];
+          float xr[8], av[8], xp0[8], xp1[8];
           unpack8(*px, xr);
+          *reinterpret_cast<float4*>(xp0) = *reinterpret_cast<const float4*>(&s_xp[0][cgi * 8]);
+          *reinterpret_cast<float4*>(xp0 + 4) = *reinterpret_cast<const float4*>(&s_xp[0][cgi * 8 + 4]);
+          *reinterpret_cast<float4*>(xp1) = *reinterpret_cast<const float4*>(&s_xp[1][cgi * 8]);
+          *reinterpret_cast<float4*>(xp1 + 4) = *reinterpret_cast<const float4*>(&s_xp[1][cgi * 8 + 4]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(__ldg(p.x_p0 + cc + j), xr[j], __ldg(p.x_p1 + cc + j));
+            const float z = fmaf(xp0[j], xr[j], xp1[j]);
             if (XMODE == CVB_A_AFF_SILU) {
               const float sg = 1.0f / (1.0f + __expf(-z));
               av[j] = z * sg;
@@ -320,14 +350,14 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
           if (row_center && jw >= 1 && jw <= ITW) continue;
           const int w = xw_base + jw;
           const int pix = ih * XW + jw;
-          const int lc = c0 + ((pch ^ (pix & 7)) << 3);
+          const int lc = c0 + (pch << 3);
           if (w < 0 || w >= p.W || lc >= p.C) continue;
           uint4* px = reinterpret_cast<uint4*>(sX + pix * 128 + (pch << 4));
           float f[8];
           unpack8(*px, f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float z = fmaf(__ldg(p.x_p0 + lc + j), f[j], __ldg(p.x_p1 + lc + j));
+            float z = fmaf(s_xp[0][pch * 8 + j], f[j], s_xp[1][pch * 8 + j]);
             f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
           }
           *px = pack8(f);
@@ -417,7 +447,7 @@ extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   dim3 grid(tiles_h * tiles_w, cblocks, gz);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmX;
-  if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, IH, IW, CB)) return 1;
+  if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, IH, IW, CB, 0)) return 1;
 #define CVB_DW_FWD(MODE)                                                                                                  \
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
@@ -461,9 +491,9 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   dim3 grid(tiles_h * tiles_w, cblocks, gz);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmDZ, tmY2, tmX;
-  if (cvb_make_tmap_nhwc(&tmDZ, a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB)) return 1;
-  if (cvb_make_tmap_nhwc(&tmY2, a.g_mode == CVB_A_BNB ? a.Y2 : a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB)) return 1;
-  if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, XH, XW, CB)) return 1;
+  if (cvb_make_tmap_nhwc(&tmDZ, a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB, 0)) return 1;
+  if (cvb_make_tmap_nhwc(&tmY2, a.g_mode == CVB_A_BNB ? a.Y2 : a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB, 0)) return 1;
+  if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, XH, XW, CB, 0)) return 1;
 #define CVB_DW_BWD(GM, XM)                                                                                                \
   {                                                                                                                      \
     static bool attr = false;                                                                                            \

@@ -201,19 +201,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
       for (int cc = chalf * (TC_BM / 64); cc < (chalf + 1) * (TC_BM / 64); ++cc) {
         uint32_t r[32];
         tmem_ld32(taddr + cc * 32, r);
-        bf16* so = reinterpret_cast<bf16*>(sO) + (cc * 32) * TC_LDO + ch_local;
+        uint16_t* so = reinterpret_cast<uint16_t*>(sO) + (cc * 32) * TC_LDO + ch_local;
+        if (full_tile && !has_aux) {
+          // hot path (conv -> BN statistics): ~5 instructions per value.  The BatchNorm sums are taken from the fp32 values
+          // (before bf16 rounding): the rounding error averages out over the >= 128 pixels of the tile.
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]) + ((full_tile || m0 + cc * 32 + i < p.M) ? bias : 0.f);
-          float y = 0.f;
-          if (has_aux) y = __bfloat162float(so[i * TC_LDO]);
-          if (EPI == TEPI_STORE_R) v += y;
-          if (EPI == TEPI_SILU_BWD) v *= silu_grad_f(fmaf(ep0, y, ep1));
-          const bf16 vb = __float2bfloat16_rn(v);
-          so[i * TC_LDO] = vb;
-          const float vr = __bfloat162float(vb);  // statistics of the STORED values
-          cs += vr;
-          cq = fmaf(vr, EPI == TEPI_SILU_BWD ? y : vr, cq);
+          for (int i = 0; i < 32; i += 2) {
+            const float v0 = __uint_as_float(r[i]) + bias, v1 = __uint_as_float(r[i + 1]) + bias;
+            const uint32_t pk = pack_bf162(v0, v1);
+            so[i * TC_LDO] = (uint16_t)pk;
+            so[(i + 1) * TC_LDO] = (uint16_t)(pk >> 16);
+            cs += v0 + v1;
+            cq = fmaf(v0, v0, fmaf(v1, v1, cq));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = __uint_as_float(r[i]) + ((full_tile || m0 + cc * 32 + i < p.M) ? bias : 0.f);
+            float y = 0.f;
+            if (has_aux) y = __bfloat162float(reinterpret_cast<const bf16*>(so)[i * TC_LDO]);
+            if (EPI == TEPI_STORE_R) v += y;
+            if (EPI == TEPI_SILU_BWD) v *= silu_grad_f(fmaf(ep0, y, ep1));
+            const bf16 vb = __float2bfloat16_rn(v);
+            reinterpret_cast<bf16*>(so)[i * TC_LDO] = vb;
+            const float vr = __bfloat162float(vb);  // statistics of the STORED values
+            cs += vr;
+            cq = fmaf(vr, EPI == TEPI_SILU_BWD ? y : vr, cq);
+          }
         }
       }
       tc_fence_before();
