@@ -709,8 +709,11 @@ extern "C" int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream) {
   if (a.samp_sum) CVB_CHECK(a.samp_sq && a.rows_per_sample > 0, "cvb_pw_gemm: sample statistics need rows_per_sample");
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_pw_gemm: col_sq missing");
   CVB_CHECK(!(a.R && a.e_mode == CVB_E_SILU), "cvb_pw_gemm: SiLU epilogue with a residual is not instantiated");
+  if (a.a_mode == CVB_A_AFF || a.a_mode == CVB_A_AFF_SILU || a.a_mode == CVB_A_GN) CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: load mode %d needs p0/p1", a.a_mode);
+  if (a.a_mode == CVB_A_BNB)
+    CVB_CHECK(a.A2 && a.a_p0 && a.a_p1 && a.a_p2 && a.lda2 % 8 == 0 && cvb_aligned16(a.A2), "cvb_pw_gemm: BNB needs A2 and p0/p1/p2");
   if (g_tc_enabled) {
-    int rc = cvb_pw_gemm_tc(a, st);  // RAW prologue + STORE / residual / SiLU-backward epilogues run on tcgen05
+    int rc = cvb_pw_gemm_tc(a, st);  // tcgen05 / TMEM kernel: STORE / residual / SiLU-backward epilogues, N >= 96
     if (rc != -1) return rc;
   }
   const int epi = a.e_mode == CVB_E_STORE ? (a.R ? EPI_STORE_R : EPI_STORE) : a.e_mode == CVB_E_SILU ? EPI_SILU

@@ -8,6 +8,8 @@
 //                            double buffered (2 x 128 columns), completion is signalled with tcgen05.commit -> mbarrier
 //   warps 2-9 epilogue     : tcgen05.ld (32 lanes x 32 columns), bias / residual / activation-backward / BatchNorm statistics,
 //                            bf16 staging tile in smem, 16-byte row-contiguous stores
+//   warps 10-13 transform  : (layers with a prologue) apply the producer's BN(+SiLU) / GroupNorm / BN-backward to the landed A
+//                            stage in place, fence.proxy.async, then hand the stage to the MMA warp through a second mbarrier
 // The product is computed TRANSPOSED, D[channel, pixel] = W[channel, :] . A[pixel, :], i.e. the weight panel is the UMMA
 // "A" operand (M = 128 output channels = TMEM lanes) and the activation tile the "B" operand (N = 128 pixels = TMEM columns).
 // Each epilogue thread then owns ONE output channel: bias is a scalar, the per-channel BatchNorm sums are thread-local (no
@@ -26,6 +28,7 @@ constexpr int TC_LDO = TC_BN + 8;             // bf16 staging row stride (elemen
 constexpr int TC_EPI_WARPS = 8;             // two warps per TMEM lane quadrant, each draining half of the pixel columns
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
+constexpr int TC_XF_THREADS = 128;          // transform warps (only launched for layers with a prologue)
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_TMEM_COLS = 256;             // 2 accumulators x 128 fp32 columns
 
@@ -76,9 +79,13 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 
 // WRES: the weight panel [128 ch, K] stays resident in smem (loaded once); otherwise (large K) its k-blocks stream through the
 // ring next to the activation k-blocks (they are L2 hits: every CTA of an N tile reads the same panel).
-template <int EPI, bool WRES>
-__global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                                                                   const cvb_gemm_args p, int NST) {
+template <int AMODE, int EPI, bool WRES>
+__global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
+    pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
+                      const cvb_gemm_args p, int NST) {
+  constexpr bool XF = (AMODE != CVB_A_RAW);     // has transform warps
+  constexpr bool TWO_A = (AMODE == CVB_A_BNB);  // BN-backward prologue streams two tensors
+  constexpr bool HAS_P = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN || AMODE == CVB_A_BNB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * TC_BN;
   const int KT = (p.K + TC_BK - 1) / TC_BK;
@@ -88,17 +95,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int RING_STAGE = WRES ? TC_STAGE : (TC_STAGE + TC_WBLK);
+  constexpr int A_BYTES = (TWO_A ? 2 : 1) * TC_STAGE;
+  constexpr int RING_STAGE = A_BYTES + (WRES ? 0 : TC_WBLK);  // [A | A2 (BNB) | W block (streaming)]
   uint8_t* sW = smem;                               // resident weight panel: KT blocks [128 ch][32 k] (WRES only)
-  uint8_t* sA = sW + (WRES ? KT * TC_WBLK : 0);     // ring: activation block (+ weight block when streaming)
+  uint8_t* sA = sW + (WRES ? KT * TC_WBLK : 0);     // ring
   uint8_t* sO = sA + NST * RING_STAGE;              // bf16 [128 pix][TC_LDO] staging (aux in / result out)
-  __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES];
+  float* sP = reinterpret_cast<float*>(sO + TC_BM * TC_LDO * 2);  // prologue parameters [3][Kpad]
+  __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], ready[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t wbar, tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ double s_samp[2][128];
 
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], TC_XF_THREADS / 32); }
     mbar_init(&wbar, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_mbar_init();
@@ -127,7 +136,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
         const int m0 = ((int)blockIdx.y + j * (int)gridDim.y) * TC_BM;
         mbar_expect_tx(&full[stage], RING_STAGE);
         tma_load_2d(sA + stage * RING_STAGE, &tmA, &full[stage], kt * TC_BK, m0);
-        if (!WRES) tma_load_2d(sA + stage * RING_STAGE + TC_STAGE, &tmW, &full[stage], kt * TC_BK, n0);
+        if (TWO_A) tma_load_2d(sA + stage * RING_STAGE + TC_STAGE, &tmA2, &full[stage], kt * TC_BK, m0);
+        if (!WRES) tma_load_2d(sA + stage * RING_STAGE + A_BYTES, &tmW, &full[stage], kt * TC_BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -142,10 +152,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TC_BM);
         for (int kt = 0; kt < KT; ++kt, ++it) {
           const int stage = it % NST;
-          mbar_wait(&full[stage], (it / NST) & 1);
+          mbar_wait(XF ? &ready[stage] : &full[stage], (it / NST) & 1);  // landed (and transformed in place)
           tc_fence_after();
           const uint32_t aa = smem_u32(sA + stage * RING_STAGE);
-          const uint32_t wa = WRES ? smem_u32(sW + kt * TC_WBLK) : aa + TC_STAGE;
+          const uint32_t wa = WRES ? smem_u32(sW + kt * TC_WBLK) : aa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_f16(tmem_d, umma_desc_sw64(wa + k * 32), umma_desc_sw64(aa + k * 32), (kt | k) ? 1u : 0u);
@@ -154,8 +164,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
         umma_commit(&tfull[buf]);      // accumulator complete
       }
     }
+  } else if (warp >= 2 + TC_EPI_WARPS) {
+    // ===================================================== transform warps: producer's normalisation / activation, in place
+    if (XF) {
+      const int tt = tid - TC_THREADS;  // 0..127
+      const int Kpad = KT * TC_BK;
+      if (HAS_P) {
+        for (int k = tt; k < Kpad; k += TC_XF_THREADS) {
+          const bool ok = k < p.K;
+          sP[k] = ok ? p.a_p0[k] : 0.f;
+          sP[Kpad + k] = ok ? p.a_p1[k] : 0.f;
+          if (AMODE == CVB_A_BNB) sP[2 * Kpad + k] = ok ? p.a_p2[k] : 0.f;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(TC_XF_THREADS) : "memory");
+      }
+      float tmu[4] = {0.f, 0.f, 0.f, 0.f}, trs[4] = {1.f, 1.f, 1.f, 1.f};
+      for (int it = 0; it < total; ++it) {
+        const int stage = it % NST;
+        const int j = it / KT, kt = it - j * KT;
+        const int m0 = ((int)blockIdx.y + j * (int)gridDim.y) * TC_BM;
+        const int k0 = kt * TC_BK;
+        if (AMODE == CVB_A_GN && kt == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = m0 + (tt >> 2) + i * 32;
+            const int b = (m < p.M ? m : p.M - 1) / p.rows_per_sample;
+            tmu[i] = __ldg(p.row_mean + b);
+            trs[i] = __ldg(p.row_rstd + b);
+          }
+        }
+        mbar_wait(&full[stage], (it / NST) & 1);
+        uint8_t* st = sA + stage * RING_STAGE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = tt + i * TC_XF_THREADS;
+          const int row = c >> 2, ch = c & 3;
+          const int k = k0 + ch * 8;
+          const uint32_t off = (uint32_t)(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));  // 64-byte swizzle (TMA == UMMA layout)
+          uint4* pa = reinterpret_cast<uint4*>(st + off);
+          float f[8], q0[8], q1[8];
+          unpack8(*pa, f);
+          if (HAS_P) {
+            *reinterpret_cast<float4*>(q0) = *reinterpret_cast<const float4*>(sP + k);
+            *reinterpret_cast<float4*>(q0 + 4) = *reinterpret_cast<const float4*>(sP + k + 4);
+            *reinterpret_cast<float4*>(q1) = *reinterpret_cast<const float4*>(sP + Kpad + k);
+            *reinterpret_cast<float4*>(q1 + 4) = *reinterpret_cast<const float4*>(sP + Kpad + k + 4);
+          }
+          if (AMODE == CVB_A_AFF) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaf(q0[e], f[e], q1[e]);
+          } else if (AMODE == CVB_A_AFF_SILU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = silu_f(fmaf(q0[e], f[e], q1[e]));
+          } else if (AMODE == CVB_A_SILU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+          } else if (AMODE == CVB_A_GN) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaf((f[e] - tmu[i]) * trs[i], q0[e], q1[e]);
+          } else if (AMODE == CVB_A_BNB) {
+            float y[8], q2[8];
+            unpack8(*reinterpret_cast<const uint4*>(st + TC_STAGE + off), y);
+            *reinterpret_cast<float4*>(q2) = *reinterpret_cast<const float4*>(sP + 2 * Kpad + k);
+            *reinterpret_cast<float4*>(q2 + 4) = *reinterpret_cast<const float4*>(sP + 2 * Kpad + k + 4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaf(q0[e], f[e], fmaf(q1[e], y[e], q2[e]));
+          }
+          // rows beyond M must stay exactly zero (their accumulators would otherwise pollute the statistics)
+          *pa = (m0 + row < p.M) ? pack8(f) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[stage]);
+      }
+    }
   } else {
-    // ===================================================== epilogue warps (threads 64..191): one output channel per thread
+    // ===================================================== epilogue warps (threads 64..319): one output channel per thread
     const int et = tid - 64;                 // 0..TC_EPI_THREADS-1
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int chalf = (warp - 2) >> 2;       // which half of the pixel columns this warp drains
@@ -285,7 +369,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pw_gemm_tc_kernel(const __grid_
   }
 }
 
-template <int EPI, bool WRES>
+template <int AMODE, int EPI, bool WRES>
 int launch_tc_impl(const cvb_gemm_args& a, cudaStream_t st, size_t fixed, int stage_bytes) {
   const size_t budget = (size_t)216 * 1024;
   int nst = (int)((budget - fixed) / stage_bytes);
@@ -293,39 +377,55 @@ int launch_tc_impl(const cvb_gemm_args& a, cudaStream_t st, size_t fixed, int st
   const size_t smem = fixed + (size_t)nst * stage_bytes;
   static bool attr = false;
   if (!attr) {
-    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<EPI, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    CVB_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<AMODE, EPI, WRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr = true;
   }
   const int n_tiles = (a.N + TC_BN - 1) / TC_BN, m_tiles = (a.M + TC_BM - 1) / TC_BM;
   int gy = (cvb_num_sms() + n_tiles - 1) / n_tiles;  // one persistent CTA per SM
   if (gy > m_tiles) gy = m_tiles;
   if (gy < 1) gy = 1;
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmA2, tmW;
   if (cvb_make_tmap_2d_k32(&tmA, a.A, a.M, a.K, a.lda, TC_BM)) return 1;
+  if (cvb_make_tmap_2d_k32(&tmA2, AMODE == CVB_A_BNB ? a.A2 : a.A, a.M, a.K, AMODE == CVB_A_BNB ? a.lda2 : a.lda, TC_BM)) return 1;
   if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, TC_BN)) return 1;
   dim3 grid(n_tiles, gy);
-  pw_gemm_tc_kernel<EPI, WRES><<<grid, TC_THREADS, smem, st>>>(tmA, tmW, a, nst);
+  const int threads = TC_THREADS + (AMODE != CVB_A_RAW ? TC_XF_THREADS : 0);
+  pw_gemm_tc_kernel<AMODE, EPI, WRES><<<grid, threads, smem, st>>>(tmA, tmA2, tmW, a, nst);
   CVB_LAUNCH_CHECK();
   return 0;
 }
 
-template <int EPI>
+template <int AMODE, int EPI>
 int launch_tc(const cvb_gemm_args& a, cudaStream_t st) {
   const int KT = (a.K + TC_BK - 1) / TC_BK;
-  const size_t stagebuf = (size_t)TC_BM * TC_LDO * 2 + 1024;
+  const int nvec = (AMODE == CVB_A_AFF || AMODE == CVB_A_AFF_SILU || AMODE == CVB_A_GN) ? 2 : (AMODE == CVB_A_BNB ? 3 : 0);
+  const int a_bytes = (AMODE == CVB_A_BNB ? 2 : 1) * TC_STAGE;
+  const size_t stagebuf = (size_t)TC_BM * TC_LDO * 2 + (size_t)nvec * KT * TC_BK * 4 + 1024;
   const size_t panel = (size_t)KT * TC_WBLK;
-  if (panel + stagebuf + 6 * TC_STAGE <= (size_t)216 * 1024) return launch_tc_impl<EPI, true>(a, st, panel + stagebuf, TC_STAGE);
-  return launch_tc_impl<EPI, false>(a, st, stagebuf, TC_STAGE + TC_WBLK);  // large K: weight k-blocks ride the ring
+  if (panel + stagebuf + 6 * (size_t)a_bytes <= (size_t)216 * 1024) return launch_tc_impl<AMODE, EPI, true>(a, st, panel + stagebuf, a_bytes);
+  return launch_tc_impl<AMODE, EPI, false>(a, st, stagebuf, a_bytes + TC_WBLK);  // large K: weight k-blocks ride the ring
+}
+
+template <int AMODE>
+int dispatch_tc_epi(const cvb_gemm_args& a, cudaStream_t st) {
+  if (a.e_mode == CVB_E_STORE) return a.R ? launch_tc<AMODE, TEPI_STORE_R>(a, st) : launch_tc<AMODE, TEPI_STORE>(a, st);
+  if (a.e_mode == CVB_E_SILU_BWD && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB)) return launch_tc<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW, TEPI_SILU_BWD>(a, st);
+  return -1;
 }
 
 }  // namespace
 
 // Returns -1 when the shape / mode is not handled by the tcgen05 kernel (caller uses the mma.sync kernel), 0 on success, > 0 on error.
 int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st) {
-  if (a.a_mode != CVB_A_RAW) return -1;
   // every epilogue thread owns one of 128 output channels: narrow layers would idle most of them -> mma.sync kernel
   if (a.N < 96 || (a.N % 128 != 0 && a.N % 128 < 64 && a.N < 256)) return -1;
-  if (a.e_mode == CVB_E_STORE) return a.R ? launch_tc<TEPI_STORE_R>(a, st) : launch_tc<TEPI_STORE>(a, st);
-  if (a.e_mode == CVB_E_SILU_BWD) return launch_tc<TEPI_SILU_BWD>(a, st);
-  return -1;
+  switch (a.a_mode) {
+    case CVB_A_RAW: return dispatch_tc_epi<CVB_A_RAW>(a, st);
+    case CVB_A_AFF: return dispatch_tc_epi<CVB_A_AFF>(a, st);
+    case CVB_A_AFF_SILU: return dispatch_tc_epi<CVB_A_AFF_SILU>(a, st);
+    case CVB_A_SILU: return dispatch_tc_epi<CVB_A_SILU>(a, st);
+    case CVB_A_GN: return dispatch_tc_epi<CVB_A_GN>(a, st);
+    case CVB_A_BNB: return dispatch_tc_epi<CVB_A_BNB>(a, st);
+    default: return -1;
+  }
 }

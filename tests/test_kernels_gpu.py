@@ -116,13 +116,17 @@ def test_pw_gemm_small_m_large_k(ops, M, N, K, a_mode):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 64, 64), (1000, 128, 128), (513, 264, 40), (4096, 384, 192), (70000, 128, 64), (33, 1000, 512)])
-@pytest.mark.parametrize("epi", ["store", "store_r", "silu_bwd"])
-def test_pw_gemm_tcgen05_vs_mma_sync(ops, M, N, K, epi):
+@pytest.mark.parametrize("epi,a_mode", [("store", 0), ("store_r", 0), ("silu_bwd", 0), ("store", 2), ("store_r", 3), ("store", 4), ("store", 5),
+                                         ("silu_bwd", 5), ("store", 1)])
+def test_pw_gemm_tcgen05_vs_mma_sync(ops, M, N, K, epi, a_mode):
     """The tcgen05/TMEM kernel and the mma.sync kernel implement the same contract: same inputs -> same outputs / statistics
     (up to fp32 accumulation order), and both match the fp32 restatement."""
     rps = 64
     nb = (M + rps - 1) // rps
-    A = bf(rnd(M, K, seed=301))
+    A, A2 = bf(rnd(M, K, seed=301)), bf(rnd(M, K, seed=311))
+    pk = (1 + 0.2 * rnd(K, seed=312), 0.3 * rnd(K, seed=313), 0.1 * rnd(K, seed=314))
+    row = (0.2 * rnd(nb, seed=315), 1 + 0.3 * rnd(nb, seed=316).abs())
+    kwa = dict(a_mode=a_mode, A2=A2 if a_mode == 5 else None, a_p=pk, row_stats=row if a_mode == 4 else None)
     W = bf(rnd(N, K, scale=K ** -0.5, seed=302))
     bias = rnd(N, seed=303)
     aux = bf(rnd(M, N, seed=304))
@@ -134,16 +138,16 @@ def test_pw_gemm_tcgen05_vs_mma_sync(ops, M, N, K, epi):
             col = torch.zeros(2, N, device="cuda", dtype=torch.float64)
             samp = torch.zeros(2, nb, device="cuda", dtype=torch.float64)
             if epi == "store":
-                o = ops.pw_gemm(A, W, N, bias=bias, col_stats=col, samp_stats=samp, rows_per_sample=rps)
+                o = ops.pw_gemm(A, W, N, bias=bias, col_stats=col, samp_stats=samp, rows_per_sample=rps, **kwa)
             elif epi == "store_r":
-                o = ops.pw_gemm(A, W, N, bias=bias, R=aux, col_stats=col, samp_stats=samp, rows_per_sample=rps)
+                o = ops.pw_gemm(A, W, N, bias=bias, R=aux, col_stats=col, samp_stats=samp, rows_per_sample=rps, **kwa)
             else:
-                o = ops.pw_gemm(A, W, N, e_mode=ops.E_SILU_BWD, Y=aux, e_p=(sc, sh), col_stats=col)
+                o = ops.pw_gemm(A, W, N, e_mode=ops.E_SILU_BWD, Y=aux, e_p=(sc, sh), col_stats=col, rows_per_sample=rps, **kwa)
             torch.cuda.synchronize()
             outs.append((o, col.clone(), samp.clone()))
         finally:
             ops.set_tc_enabled(prev)
-    acc = A.float() @ W.float().t()
+    acc = load_ref(a_mode, A, pk, A2, row, rps) @ W.float().t()
     ref = acc + bias if epi == "store" else acc + bias + aux.float() if epi == "store_r" else acc * dsilu(sc * aux.float() + sh)
     for name, (o, col, samp) in zip(("tcgen05", "mma.sync"), outs):
         close(o, ref, what=f"{name} out")
