@@ -327,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
     ev0.record()
     for _ in range(args.steps):
         if args.profile_ops:
-            torch.cuda._sleep(int(0.06 * 1.9e9))  # diagnostics only: queue the step behind a spin so op timings exclude launch gaps
+            torch.cuda._sleep(int(0.25 * 1.9e9))  # diagnostics only: queue the step behind a spin so op timings exclude launch gaps
         loss = run_step(static_x, static_y) if use_graph else step(x_dev, y_dev)
         if args.profile_ops:
             torch.cuda.synchronize(dev)
@@ -395,7 +395,7 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(3):
             # eager launches are CPU-bound here; a GPU-side spin first lets the host queue the whole step so that the event
             # pairs bracket back-to-back kernel execution only (no launch gaps inside the measured intervals)
-            torch.cuda._sleep(int(0.06 * 1.9e9))
+            torch.cuda._sleep(int(0.12 * 1.9e9))
             step(x_dev, y_dev)
             torch.cuda.synchronize(dev)
         timer.enabled = False
