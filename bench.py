@@ -226,6 +226,8 @@ def run_ours(args, rank, world, local_rank):
     model = m.MobileViTv2(m.default_opts(width_multiplier=1.0)).to(dev).train()
     train_model = model
     use_ddp_wrapper = world > 1 and args.no_graph
+    if args.no_pdl:
+        ops.set_pdl_enabled(False)
     if use_ddp_wrapper:
         # eager multi-GPU path: the reference's own wrapper (main_train.py:90-96), bucketed all-reduce overlapped with backward
         from torch.nn.parallel import DistributedDataParallel as DDP
@@ -449,6 +451,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="CUDA-event time per C-ABI entry point (diagnostics)")
+    ap.add_argument("--no-pdl", action="store_true", help="diagnostics: plain stream-ordered launches instead of programmatic dependent launch")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph (N=1)")
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

@@ -89,6 +89,10 @@ CVB_API int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream);
  * (layers whose A operand needs an element-wise prologue).  Testing hook: disable (0) / enable (1) the tcgen05 kernel so the
  * two can be compared on identical inputs; returns the previous setting. */
 CVB_API int cvb_set_tc_enabled(int on);
+/* Every kernel is launched with programmatic dependent launch (its set-up overlaps the previous kernel's tail; the kernel
+ * itself orders its data accesses with griddepcontrol.wait).  Testing hook: plain stream-ordered launches (0) / PDL (1);
+ * returns the previous setting. */
+CVB_API int cvb_set_pdl_enabled(int on);
 
 /* Weight gradient of a pointwise conv / linear:  dW[N,K] += sum_m load(G)[m,n] * load(A)[m,k];  dbias[n] += sum_m load(G)[m,n]
  * (autograd of F.conv2d / F.linear at the call sites above).  G modes: RAW or BNB; A modes: RAW/AFF/AFF_SILU/SILU/GN. */

@@ -81,6 +81,7 @@ _SIGS = {
     "cvb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "cvb_pw_gemm": (c_int, [POINTER(GemmArgs), c_void_p]),
     "cvb_set_tc_enabled": (c_int, [c_int]),
+    "cvb_set_pdl_enabled": (c_int, [c_int]),
     "cvb_pw_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
     "cvb_apply_load_mode": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                     c_int, c_int64, c_int, c_void_p]),

@@ -119,6 +119,31 @@ __device__ __forceinline__ float apply_mode(int mode, float x, float p0, float p
   }
 }
 
+// ---------------------------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute: its CTAs may become resident
+// while the previous kernel in the stream is still draining, run their private set-up (mbarrier init, TMEM allocation,
+// tensor-map prefetch), and block in pdl_wait() until the previous grid has completed and flushed its memory.  RULES: nothing
+// produced by an earlier kernel is read, and no global memory is written, before pdl_wait(); every kernel executes
+// pdl_wait() in every thread (so "grid B complete" always implies "grid A complete" along the stream).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int cvb_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cvb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cvb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------- TMA + mbarrier (sm_90+/sm_100a)
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 

@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   if (tid == 0) {
     for (int i = 0; i < 2 && i < n_img; ++i) {
       mbar_expect_tx(&bar[i], tile_bytes);
@@ -216,6 +218,8 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   if (tid == 0) {
     for (int i = 0; i < 2 && i < n_img; ++i) issue(i);
   }
@@ -452,7 +456,7 @@ extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
     if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-    dw_fwd_kernel<MODE><<<grid, NT, smem, st>>>(tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, buf_bytes);                   \
+    CVB_CUDA(cvb_launch(dw_fwd_kernel<MODE>, grid, NT, smem, st, tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, buf_bytes));                   \
   }
   if (a.x_mode == CVB_A_RAW) CVB_DW_FWD(CVB_A_RAW)
   else if (a.x_mode == CVB_A_AFF) CVB_DW_FWD(CVB_A_AFF)
@@ -498,7 +502,7 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
     if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024)); attr = true; } \
-    dw_bwd_kernel<GM, XM><<<grid, NTB, smem, st>>>(tmDZ, tmY2, tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, g_bytes, x_bytes);   \
+    CVB_CUDA(cvb_launch(dw_bwd_kernel<GM, XM>, grid, NTB, smem, st, tmDZ, tmY2, tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, g_bytes, x_bytes));   \
   }
   if (a.g_mode == CVB_A_RAW) {
     if (a.x_mode == CVB_A_RAW) CVB_DW_BWD(CVB_A_RAW, CVB_A_RAW)

@@ -75,6 +75,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
   __shared__ __align__(8) uint64_t wbar;
 
   if (tid < 128) { s_col[0][tid] = 0.f; s_col[1][tid] = 0.f; s_samp[0][tid] = 0.0; s_samp[1][tid] = 0.0; }
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+  }
+  pdl_wait();  // everything below may read what the previous kernel wrote
+  pdl_trigger();
   if (HAS_P) {  // per-K prologue parameters -> smem (zero padded so that the K tail transforms to zero)
     for (int k = tid; k < Kpad; k += NTHREADS) {
       bool ok = k < p.K;
@@ -82,11 +89,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
       sP[Kpad + k] = ok ? p.a_p1[k] : 0.f;
       if (AMODE == CVB_A_BNB) sP[2 * Kpad + k] = ok ? p.a_p2[k] : 0.f;
     }
-  }
-  if (tid == 0) {
-    for (int i = 0; i < NST; ++i) mbar_init(&full[i], 1);
-    mbar_init(&wbar, 1);
-    fence_mbar_init();
   }
   __syncthreads();
 
@@ -428,7 +430,7 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st, bool require_two_ctas) 
   if (cvb_make_tmap_2d_k32(&tmA2, AMODE == CVB_A_BNB ? a.A2 : a.A, a.M, a.K, AMODE == CVB_A_BNB ? a.lda2 : a.lda, BM)) return 1;
   if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, BN)) return 1;
   dim3 grid(n_tiles, gy);
-  pw_gemm_kernel<WM, AMODE, EPI><<<grid, NTHREADS, smem, st>>>(tmA, tmA2, tmW, a, nst);
+  CVB_CUDA(cvb_launch(pw_gemm_kernel<WM, AMODE, EPI>, grid, NTHREADS, smem, st, tmA, tmA2, tmW, a, nst));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -495,6 +497,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_wgrad_kernel(const cvb_wgrad_a
   const int m_begin = blockIdx.z * m_per_cta;
   const int m_end = min(p.M, m_begin + m_per_cta);
   const int NS = (m_end - m_begin + WG_MB - 1) / WG_MB;
+  pdl_wait();
+  pdl_trigger();
   if (NS <= 0) return;
 
   const bf16* __restrict__ G = static_cast<const bf16*>(p.G);
@@ -662,7 +666,7 @@ int launch_wgrad(const cvb_wgrad_args& a, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(kt, nt, splits);
-  pw_wgrad_kernel<GMODE, AMODE><<<grid, NTHREADS, smem, st>>>(a, m_per_cta);
+  CVB_CUDA(cvb_launch(pw_wgrad_kernel<GMODE, AMODE>, grid, NTHREADS, smem, st, a, m_per_cta));
   CVB_LAUNCH_CHECK();
   return 0;
 }

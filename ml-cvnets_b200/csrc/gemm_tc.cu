@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // barriers, TMEM allocation and CTA scheduling overlapped the previous kernel's tail; data accesses start here
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -390,7 +392,7 @@ int launch_tc_impl(const cvb_gemm_args& a, cudaStream_t st, size_t fixed, int st
   if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, TC_BN)) return 1;
   dim3 grid(n_tiles, gy);
   const int threads = TC_THREADS + (AMODE != CVB_A_RAW ? TC_XF_THREADS : 0);
-  pw_gemm_tc_kernel<AMODE, EPI, WRES><<<grid, threads, smem, st>>>(tmA, tmA2, tmW, a, nst);
+  CVB_CUDA(cvb_launch(pw_gemm_tc_kernel<AMODE, EPI, WRES>, grid, threads, smem, st, tmA, tmA2, tmW, a, nst));
   CVB_LAUNCH_CHECK();
   return 0;
 }

@@ -39,6 +39,8 @@ __device__ float block_reduce_max(float v, float* ws) {
 // dynamic smem: s[N] | ctx[d] | partials[ngrp][d]
 __global__ void __launch_bounds__(NT) linattn_fwd_kernel(const bf16* __restrict__ QKV, int ldq, int H, int W, int d, bf16* __restrict__ O, int ldo,
                                                          float* __restrict__ S, float* __restrict__ CTX) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   __shared__ float ws[NT / 32];
   const int N = (H >> 1) * (W >> 1);
@@ -116,6 +118,8 @@ __global__ void __launch_bounds__(NT) linattn_fwd_kernel(const bf16* __restrict_
 __global__ void __launch_bounds__(NT) linattn_bwd_kernel(const bf16* __restrict__ QKV, int ldq, const bf16* __restrict__ DO, int ldo,
                                                          const float* __restrict__ S, const float* __restrict__ CTX, int H, int W, int d,
                                                          bf16* __restrict__ DQKV, float* __restrict__ dbias) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   __shared__ float ws[NT / 32];
   const int N = (H >> 1) * (W >> 1);
@@ -226,8 +230,8 @@ extern "C" int cvb_linattn_fwd(const void* QKV, int ldq, int B, int H, int W, in
   CVB_CHECK(smem <= 200 * 1024, "cvb_linattn_fwd: N=%d too large", N);
   static bool attr = false;
   if (!attr) { CVB_CUDA(cudaFuncSetAttribute(linattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-  linattn_fwd_kernel<<<B * 4, nthreads, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(QKV), ldq, H, W, d, static_cast<bf16*>(O), ldo,
-                                                                                  S, CTX);
+  CVB_CUDA(cvb_launch(linattn_fwd_kernel, B * 4, nthreads, smem, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(QKV), ldq, H, W, d, static_cast<bf16*>(O), ldo,
+                                                                                  S, CTX));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -242,8 +246,8 @@ extern "C" int cvb_linattn_bwd(const void* QKV, int ldq, const void* DO, int ldo
   CVB_CHECK(smem <= 200 * 1024, "cvb_linattn_bwd: N=%d too large", N);
   static bool attr = false;
   if (!attr) { CVB_CUDA(cudaFuncSetAttribute(linattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-  linattn_bwd_kernel<<<B * 4, nthreads, smem, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(QKV), ldq, static_cast<const bf16*>(DO), ldo, S,
-                                                                                  CTX, H, W, d, static_cast<bf16*>(DQKV), dbias);
+  CVB_CUDA(cvb_launch(linattn_bwd_kernel, B * 4, nthreads, smem, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(QKV), ldq, static_cast<const bf16*>(DO), ldo, S,
+                                                                                  CTX, H, W, d, static_cast<bf16*>(DQKV), dbias));
   CVB_LAUNCH_CHECK();
   return 0;
 }

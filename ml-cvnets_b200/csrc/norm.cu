@@ -16,6 +16,14 @@ void cvb_set_error(const char* fmt, ...) {
 }
 extern "C" const char* cvb_last_error(void) { return g_err; }
 extern "C" int cvb_abi_version(void) { return CVB_ABI_VERSION; }
+static int g_pdl_enabled = 1;
+int cvb_pdl_enabled() { return g_pdl_enabled; }
+extern "C" int cvb_set_pdl_enabled(int on) {
+  int old = g_pdl_enabled;
+  g_pdl_enabled = on ? 1 : 0;
+  return old;
+}
+
 int cvb_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -101,6 +109,8 @@ RowGeom row_geom(int64_t M, int C) {
 __global__ void bn_finalize_kernel(const double* sum, const double* sq, double count, const float* gamma, const float* beta, float eps,
                                    float momentum, float* rmean, float* rvar, int64_t* nbt, float* mean, float* rstd, float* scale,
                                    float* shift, int C) {
+  pdl_wait();
+  pdl_trigger();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
@@ -122,6 +132,8 @@ __global__ void bn_finalize_kernel(const double* sum, const double* sq, double c
 
 __global__ void bn_eval_kernel(const float* gamma, const float* beta, const float* rmean, const float* rvar, float eps, float* mean,
                                float* rstd, float* scale, float* shift, int C) {
+  pdl_wait();
+  pdl_trigger();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float r = rsqrtf(rvar[c] + eps);
@@ -135,6 +147,8 @@ __global__ void bn_eval_kernel(const float* gamma, const float* beta, const floa
 __global__ void bn_bwd_finalize_kernel(const double* sdz, const double* sdzy, double count, const float* gamma, const float* mean,
                                        const float* rstd, int eval_mode, float* dgamma, float* dbeta, float* c1, float* c2, float* c3,
                                        int C) {
+  pdl_wait();
+  pdl_trigger();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double db = sdz[c];
@@ -151,6 +165,8 @@ __global__ void bn_bwd_finalize_kernel(const double* sdz, const double* sdzy, do
 }
 
 __global__ void gn_finalize_kernel(const double* ssum, const double* ssq, double count, float eps, float* mean, float* rstd, int B) {
+  pdl_wait();
+  pdl_trigger();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double m = ssum[b] / count;
@@ -163,6 +179,8 @@ __global__ void gn_finalize_kernel(const double* ssum, const double* ssq, double
 // ------------------------------------------------------------------------------------------------ elementwise: BN apply
 __global__ void __launch_bounds__(NT) bn_apply_kernel(const bf16* __restrict__ Y, const float* __restrict__ scale, const float* __restrict__ shift,
                                                       int act, const bf16* __restrict__ R, bf16* __restrict__ OUT, int64_t nvec, int cgs) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
     int c = (int)(v % cgs) * 8;
     float f[8];
@@ -193,6 +211,8 @@ __global__ void __launch_bounds__(NT) apply_load_mode_kernel(const bf16* __restr
                                                              const float* __restrict__ p2, const float* __restrict__ row_mean,
                                                              const float* __restrict__ row_rstd, int rps, bf16* __restrict__ OUT, int64_t nvec,
                                                              int cgs, int lda, int lda2, int ldo) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
     const int64_t m = v / cgs;
     const int c = (int)(v % cgs) * 8;
@@ -221,6 +241,8 @@ __global__ void __launch_bounds__(NT) apply_load_mode_kernel(const bf16* __restr
 __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const bf16* __restrict__ DOUT, const bf16* __restrict__ Y, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, int act, bf16* __restrict__ DZ, double* s0, double* s1,
                                                            int64_t M, int C, int cgs, int rpp, int rows_per_cta) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sred[];  // [2][C]
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
@@ -252,6 +274,8 @@ __global__ void __launch_bounds__(NT) bn_bwd_reduce_kernel(const bf16* __restric
 
 // column sums of a bf16 / fp32 [M, ld] matrix into fp32
 __global__ void __launch_bounds__(NT) col_sum_kernel(const void* __restrict__ X, int x_fp32, int ld, int64_t M, int N, float* out, int rows_per_cta) {
+  pdl_wait();
+  pdl_trigger();
   // thread per column (strided), rows looped: N is small (<= 1024) and M small for the fp32 use (classifier)
   int64_t r_begin = (int64_t)blockIdx.y * rows_per_cta, r_end = r_begin + rows_per_cta;
   if (r_end > M) r_end = M;
@@ -271,6 +295,8 @@ __global__ void __launch_bounds__(NT) col_sum_kernel(const void* __restrict__ X,
 // per-sample sum / sumsq
 __global__ void __launch_bounds__(NT) gn_stats_kernel(const bf16* __restrict__ X, int ldx, int rows_per_sample, int C, int chunks_per_sample,
                                                       double* ssum, double* ssq) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x / chunks_per_sample, chunk = blockIdx.x % chunks_per_sample;
   const int cgs = C / 8;
   const int64_t nvec = (int64_t)rows_per_sample * cgs;
@@ -303,6 +329,8 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict
                                                           const float* __restrict__ rstd, const double* __restrict__ sg, const double* __restrict__ sgx,
                                                           double count, const bf16* __restrict__ DRES, bf16* __restrict__ DX, int64_t M,
                                                           int rows_per_sample, int C, double* col_sum, int cgs, int rpp, int rows_per_cta) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sred[];  // [C]
   const int tid = threadIdx.x;
   if (col_sum) { for (int i = tid; i < C; i += blockDim.x) sred[i] = 0.f; __syncthreads(); }
@@ -345,6 +373,8 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict
 
 // ------------------------------------------------------------------------------------------------ global average pool
 __global__ void __launch_bounds__(NT) pool_fwd_kernel(const bf16* __restrict__ X, int HW, int C, bf16* __restrict__ OUT) {
+  pdl_wait();
+  pdl_trigger();
   // grid: (C/8 chunks rounded to blocks of 32 lanes..., B); thread = (chunk, row group)
   extern __shared__ float sred[];  // [C]
   const int b = blockIdx.x;
@@ -369,6 +399,8 @@ __global__ void __launch_bounds__(NT) pool_fwd_kernel(const bf16* __restrict__ X
 }
 
 __global__ void __launch_bounds__(NT) pool_bwd_kernel(const bf16* __restrict__ DOUT, int HW, int C, bf16* __restrict__ DX, int64_t nvec) {
+  pdl_wait();
+  pdl_trigger();
   const int cgs = C / 8;
   const float inv = 1.f / (float)HW;
   for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
@@ -387,6 +419,8 @@ __global__ void __launch_bounds__(NT) pool_bwd_kernel(const bf16* __restrict__ D
 // A[(b,oh,ow), ci*9+u*3+v] = bf16(X[b,ci,2oh+u-1,2ow+v-1]) (zero padded), columns 27..31 = 0
 __global__ void __launch_bounds__(NT) stem_im2col_kernel(const float* __restrict__ X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H,
                                                          int W, bf16* __restrict__ A) {
+  pdl_wait();
+  pdl_trigger();
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)B * Ho * Wo * 4;  // 4 chunks of 8 columns per output pixel
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -415,6 +449,8 @@ __global__ void __launch_bounds__(NT) stem_im2col_kernel(const float* __restrict
 __device__ __forceinline__ int perm_row(int r, int rows, int rot) { return rot ? (r + rot) % rows : r; }
 
 __global__ void __launch_bounds__(NT) prep_weights_kernel(const cvb_prep_desc* __restrict__ descs) {
+  pdl_wait();
+  pdl_trigger();
   const cvb_prep_desc d = descs[blockIdx.y];
   const int64_t total = (d.kind == 2) ? (int64_t)d.rows * d.cols : (d.kind == 3 ? (int64_t)d.dst_rows : (int64_t)d.dst_rows * d.ldd);
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -438,6 +474,8 @@ __global__ void __launch_bounds__(NT) prep_weights_kernel(const cvb_prep_desc* _
 
 __global__ void __launch_bounds__(NT) unprep_grad_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int lds, int kind,
                                                          int rot) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = (int64_t)rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
     if (kind == 0) {
@@ -466,8 +504,8 @@ extern "C" int cvb_bn_finalize(const double* sum, const double* sq, double count
                                float* running_mean, float* running_var, int64_t* nbt, float* mean, float* rstd, float* scale, float* shift, int C,
                                cvb_stream_t stream) {
   CVB_CHECK(sum && sq && mean && rstd && scale && shift && C > 0 && count > 0, "cvb_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sum, sq, count, gamma, beta, eps, momentum, running_mean,
-                                                                                     running_var, nbt, mean, rstd, scale, shift, C);
+  CVB_CUDA(cvb_launch(bn_finalize_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), sum, sq, count, gamma, beta, eps, momentum, running_mean,
+                                                                                     running_var, nbt, mean, rstd, scale, shift, C));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -475,7 +513,7 @@ extern "C" int cvb_bn_finalize(const double* sum, const double* sq, double count
 extern "C" int cvb_bn_eval_scale_shift(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
                                        float* mean, float* rstd, float* scale, float* shift, int C, cvb_stream_t stream) {
   CVB_CHECK(running_mean && running_var && mean && rstd && scale && shift && C > 0, "cvb_bn_eval_scale_shift: bad arguments");
-  bn_eval_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(gamma, beta, running_mean, running_var, eps, mean, rstd, scale, shift, C);
+  CVB_CUDA(cvb_launch(bn_eval_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), gamma, beta, running_mean, running_var, eps, mean, rstd, scale, shift, C));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -483,8 +521,8 @@ extern "C" int cvb_bn_eval_scale_shift(const float* gamma, const float* beta, co
 extern "C" int cvb_bn_bwd_finalize(const double* sum_dz, const double* sum_dzy, double count, const float* gamma, const float* mean, const float* rstd,
                                    int eval_mode, float* dgamma, float* dbeta, float* c1, float* c2, float* c3, int C, cvb_stream_t stream) {
   CVB_CHECK(sum_dz && sum_dzy && mean && rstd && c1 && c2 && c3 && C > 0 && count > 0, "cvb_bn_bwd_finalize: bad arguments");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sum_dz, sum_dzy, count, gamma, mean, rstd, eval_mode, dgamma,
-                                                                                         dbeta, c1, c2, c3, C);
+  CVB_CUDA(cvb_launch(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), sum_dz, sum_dzy, count, gamma, mean, rstd, eval_mode, dgamma,
+                                                                                         dbeta, c1, c2, c3, C));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -493,8 +531,8 @@ extern "C" int cvb_bn_apply(const void* Y, const float* scale, const float* shif
                             cvb_stream_t stream) {
   CVB_CHECK(Y && scale && shift && OUT && M > 0 && C > 0 && C % 8 == 0, "cvb_bn_apply: bad arguments");
   int64_t nvec = M * (C / 8);
-  bn_apply_kernel<<<grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(Y), scale, shift, act,
-                                                                               static_cast<const bf16*>(R), static_cast<bf16*>(OUT), nvec, C / 8);
+  CVB_CUDA(cvb_launch(bn_apply_kernel, grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(Y), scale, shift, act,
+                                                                               static_cast<const bf16*>(R), static_cast<bf16*>(OUT), nvec, C / 8));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -508,9 +546,9 @@ extern "C" int cvb_apply_load_mode(const void* A, int lda, const void* A2, int l
   if (mode == CVB_A_GN) CVB_CHECK(row_mean && row_rstd && rows_per_sample > 0 && p0 && p1, "cvb_apply_load_mode: GN needs statistics");
   if (mode == CVB_A_AFF || mode == CVB_A_AFF_SILU) CVB_CHECK(p0 && p1, "cvb_apply_load_mode: AFF needs p0/p1");
   int64_t nvec = M * (K / 8);
-  apply_load_mode_kernel<<<grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream)>>>(
+  CVB_CUDA(cvb_launch(apply_load_mode_kernel, grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const bf16*>(A), static_cast<const bf16*>(A2), mode, p0, p1, p2, row_mean, row_rstd, rows_per_sample > 0 ? rows_per_sample : 1,
-      static_cast<bf16*>(OUT), nvec, K / 8, lda, lda2, ldo);
+      static_cast<bf16*>(OUT), nvec, K / 8, lda, lda2, ldo));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -520,9 +558,9 @@ extern "C" int cvb_bn_bwd_reduce(const void* DOUT, const void* Y, const float* s
   CVB_CHECK(DOUT && Y && sum_dz && sum_dzy && M > 0 && C > 0 && C % 8 == 0 && C <= 2048, "cvb_bn_bwd_reduce: bad arguments");
   if (act) CVB_CHECK(scale && shift, "cvb_bn_bwd_reduce: act needs scale/shift");
   RowGeom g = row_geom(M, C);
-  bn_bwd_reduce_kernel<<<g.ctas, g.nthreads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  CVB_CUDA(cvb_launch(bn_bwd_reduce_kernel, g.ctas, g.nthreads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const bf16*>(DOUT), static_cast<const bf16*>(Y), scale, shift, act, static_cast<bf16*>(DZ), sum_dz, sum_dzy, M, C, g.cgs, g.rpp,
-      g.rows_per_cta);
+      g.rows_per_cta));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -530,7 +568,7 @@ extern "C" int cvb_bn_bwd_reduce(const void* DOUT, const void* Y, const float* s
 extern "C" int cvb_gn_finalize(const double* samp_sum, const double* samp_sq, double count, float eps, float* mean, float* rstd, int B,
                                cvb_stream_t stream) {
   CVB_CHECK(samp_sum && samp_sq && mean && rstd && B > 0 && count > 0, "cvb_gn_finalize: bad arguments");
-  gn_finalize_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(samp_sum, samp_sq, count, eps, mean, rstd, B);
+  CVB_CUDA(cvb_launch(gn_finalize_kernel, (B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), samp_sum, samp_sq, count, eps, mean, rstd, B));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -540,8 +578,8 @@ extern "C" int cvb_gn_stats(const void* X, int ldx, int B, int rows_per_sample, 
   int64_t nvec = (int64_t)rows_per_sample * (C / 8);
   int chunks = (int)((nvec + 4095) / 4096);
   if (chunks < 1) chunks = 1;
-  gn_stats_kernel<<<B * chunks, NT, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(X), ldx, rows_per_sample, C, chunks, samp_sum,
-                                                                           samp_sq);
+  CVB_CUDA(cvb_launch(gn_stats_kernel, B * chunks, NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X), ldx, rows_per_sample, C, chunks, samp_sum,
+                                                                           samp_sq));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -552,9 +590,9 @@ extern "C" int cvb_gn_bwd_apply(const void* G, const void* X, const float* mean,
             "cvb_gn_bwd_apply: bad arguments");
   int64_t M = (int64_t)B * rows_per_sample;
   RowGeom g = row_geom(M, C);
-  gn_bwd_apply_kernel<<<g.ctas, g.nthreads, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  CVB_CUDA(cvb_launch(gn_bwd_apply_kernel, g.ctas, g.nthreads, C * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const bf16*>(G), static_cast<const bf16*>(X), mean, rstd, sg, sgx, count, static_cast<const bf16*>(DRES), static_cast<bf16*>(DX), M,
-      rows_per_sample, C, col_sum, g.cgs, g.rpp, g.rows_per_cta);
+      rows_per_sample, C, col_sum, g.cgs, g.rpp, g.rows_per_cta));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -563,7 +601,7 @@ extern "C" int cvb_global_pool_fwd(const void* X, int B, int HW, int C, void* OU
   CVB_CHECK(X && OUT && B > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 2048, "cvb_global_pool_fwd: bad arguments");
   int cgs = C / 8;
   int rpp = NT / cgs; if (rpp < 1) rpp = 1;
-  pool_fwd_kernel<<<B, cgs * rpp, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(X), HW, C, static_cast<bf16*>(OUT));
+  CVB_CUDA(cvb_launch(pool_fwd_kernel, B, cgs * rpp, C * sizeof(float), static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X), HW, C, static_cast<bf16*>(OUT)));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -571,7 +609,7 @@ extern "C" int cvb_global_pool_fwd(const void* X, int B, int HW, int C, void* OU
 extern "C" int cvb_global_pool_bwd(const void* DOUT, int B, int HW, int C, void* DX, cvb_stream_t stream) {
   CVB_CHECK(DOUT && DX && B > 0 && HW > 0 && C > 0 && C % 8 == 0, "cvb_global_pool_bwd: bad arguments");
   int64_t nvec = (int64_t)B * HW * (C / 8);
-  pool_bwd_kernel<<<grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(DOUT), HW, C, static_cast<bf16*>(DX), nvec);
+  CVB_CUDA(cvb_launch(pool_bwd_kernel, grid_for(nvec), NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(DOUT), HW, C, static_cast<bf16*>(DX), nvec));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -580,7 +618,7 @@ extern "C" int cvb_col_sum(const void* X, int x_fp32, int ld, int64_t M, int N, 
   CVB_CHECK(X && out && M > 0 && N > 0 && ld >= N, "cvb_col_sum: bad arguments");
   int rows_per_cta = 256;
   dim3 grid((N + NT - 1) / NT, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
-  col_sum_kernel<<<grid, NT, 0, static_cast<cudaStream_t>(stream)>>>(X, x_fp32, ld, M, N, out, rows_per_cta);
+  CVB_CUDA(cvb_launch(col_sum_kernel, grid, NT, 0, static_cast<cudaStream_t>(stream), X, x_fp32, ld, M, N, out, rows_per_cta));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -588,7 +626,7 @@ extern "C" int cvb_col_sum(const void* X, int x_fp32, int ld, int64_t M, int N, 
 extern "C" int cvb_stem_im2col(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A, cvb_stream_t stream) {
   CVB_CHECK(X && A && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "cvb_stem_im2col: bad arguments (H, W must be even)");
   int64_t total = (int64_t)B * (H / 2) * (W / 2) * 4;
-  stem_im2col_kernel<<<grid_for(total), NT, 0, static_cast<cudaStream_t>(stream)>>>(X, sxn, sxc, sxh, sxw, B, H, W, static_cast<bf16*>(A));
+  CVB_CUDA(cvb_launch(stem_im2col_kernel, grid_for(total), NT, 0, static_cast<cudaStream_t>(stream), X, sxn, sxc, sxh, sxw, B, H, W, static_cast<bf16*>(A)));
   CVB_LAUNCH_CHECK();
   return 0;
 }
@@ -599,14 +637,14 @@ extern "C" int cvb_prep_weights(const cvb_prep_desc* descs_device, int n_desc, i
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
   dim3 grid(gx, n_desc);
-  prep_weights_kernel<<<grid, NT, 0, static_cast<cudaStream_t>(stream)>>>(descs_device);
+  CVB_CUDA(cvb_launch(prep_weights_kernel, grid, NT, 0, static_cast<cudaStream_t>(stream), descs_device));
   CVB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int cvb_unprep_grad(const float* src, float* dst, int rows, int cols, int lds, int kind, int rot, cvb_stream_t stream) {
   CVB_CHECK(src && dst && rows > 0 && cols > 0, "cvb_unprep_grad: bad arguments");
-  unprep_grad_kernel<<<grid_for((int64_t)rows * cols), NT, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, rows, cols, lds, kind, rot);
+  CVB_CUDA(cvb_launch(unprep_grad_kernel, grid_for((int64_t)rows * cols), NT, 0, static_cast<cudaStream_t>(stream), src, dst, rows, cols, lds, kind, rot));
   CVB_LAUNCH_CHECK();
   return 0;
 }

@@ -40,6 +40,11 @@ def set_tc_enabled(on: bool) -> bool:
     return bool(_lib().cvb_set_tc_enabled(int(on)))
 
 
+def set_pdl_enabled(on: bool) -> bool:
+    """Testing hook: programmatic dependent launch for every kernel (default) or plain stream-ordered launches."""
+    return bool(_lib().cvb_set_pdl_enabled(int(on)))
+
+
 # --------------------------------------------------------------------------------------------------------------- GEMM
 def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: int = A_RAW, A2: Optional[Tensor] = None,
             a_p: Sequence[Optional[Tensor]] = (None, None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,
