@@ -1,51 +1,105 @@
 // Depthwise 3x3 convolution (pad 1, stride 1|2), NHWC bf16, forward and fused backward (sm_100a).
 //
-// Pure HBM-bound stencils (9 MAC per element): the kernels stage a spatial tile x 64 channels (+halo) in shared memory
-// with the PRODUCER's BatchNorm(+SiLU) already applied (so every input element is transformed exactly once), use
-// 16-byte channel vectors everywhere, and emit the BatchNorm statistics of their own output in the epilogue.
-// The backward kernel fuses  dy = BN-backward(dz, y)  ->  dX (transposed stencil)  ->  activation backward of the
-// producer + its BN-backward statistics  and  dW (per-channel 9-tap reduction) into one pass over the tensors.
+// HBM-bound stencils whose first implementation was instruction-issue bound (~85 instructions per element).  This version is
+// built around the instruction count:
+//   * a warp spans the CTA's 64 channels (lane = channel pair, one 4-byte bf16x2 access per lane = one conflict-free 128-byte
+//     shared-memory wavefront per warp) and WALKS along a strip of pixels, keeping the 3x3 neighbourhood of the strip's rows in
+//     registers (sliding window: each neighbour is loaded (R+2)/R times instead of 9);
+//   * all arithmetic is packed fp32 (FFMA2 = fma.rn.f32x2 on the channel pair), weights / dW accumulators / BN statistics stay in
+//     registers for the whole batch loop of the CTA;
+//   * backward: for every INPUT pixel p the same neighbourhood dy[p - tap] feeds both products,
+//         dX[p] = sum_t W[t] * dy[p - t]        dW[t] += act(x[p]) * dy[p - t],
+//     so one walk produces the input gradient, the weight gradient, the producer's activation backward and its BN-backward
+//     statistics; x needs no halo and is read exactly once;
+//   * tiles (+ zero-filled halos = the conv padding) are staged by TMA into two buffer sets with mbarriers, the next image's tiles
+//     are in flight while the current one is processed.
 #include "common.cuh"
 
 namespace {
 
-constexpr int CB = 64;  // channels per CTA (8 x 16-byte chunks)
-constexpr int NT = 256;
+constexpr int CB = 64;    // channels per CTA (32 lanes x channel pair)
+constexpr int NT = 256;   // forward: 8 warps, 2 CTAs / SM
+constexpr int NTB = 512;  // backward: 16 warps, 1 CTA / SM
+constexpr int SEG = 8;    // pixels a warp walks per strip (fully unrolled: the window shift is register renaming)
 
-// smem tiles are plain [pixel][64 channels] (128 B per pixel, no swizzle): every access pattern below touches one pixel's 128 B per
-// quarter-warp / warp and is conflict-free as is, and linear addresses keep the address arithmetic out of the instruction stream
-__device__ __forceinline__ uint32_t pix_off(int pix, int ch) { return static_cast<uint32_t>(pix * 128 + (ch << 4)); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{ .reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mov.b64 c,{%6,%7}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1}, d; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mul.rn.f32x2 d,a,b; mov.b64 {%0,%1}, d; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; add.rn.f32x2 d,a,b; mov.b64 {%0,%1}, d; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+// bf16x2 -> two fp32 (exact): two integer-pipe instructions, no conversion unit
+__device__ __forceinline__ float2 up2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ float2 lds2(const uint8_t* tile, int pix, int lane) {
+  return up2(*reinterpret_cast<const uint32_t*>(tile + pix * 128 + lane * 4));
+}
 
-__device__ __forceinline__ void load8_mode(int mode, const bf16* ptr, const float* p0, const float* p1, float* out) {
-  unpack8(ldg16(ptr), out);
-  if (mode == CVB_A_AFF) {
+// in-place producer transform of a staged tile, 16-byte chunks: a = act(scale * x + shift) for in-bounds pixels; the zero-filled
+// halo / out-of-range channels stay zero (the padding acts on the activated tensor).  s_par: [2][64] scale, shift.
+template <int XMODE, int NTHR>
+__device__ __forceinline__ void transform_tile(uint8_t* tile, int TH_, int TW_, int h_base, int w_base, int H, int W, int c0, int C,
+                                               const float* s_par, int warp, int lane) {
+  const int pch = lane & 7;
+  const int lc = c0 + (pch << 3);
+  if (lc >= C) return;
+  float sc[8], sh[8];
+  *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(s_par + pch * 8);
+  *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(s_par + pch * 8 + 4);
+  *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(s_par + CB + pch * 8);
+  *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(s_par + CB + pch * 8 + 4);
+  for (int ih = warp; ih < TH_; ih += NTHR / 32) {
+    const int h = h_base + ih;
+    if (h < 0 || h >= H) continue;
+    for (int jw = lane >> 3; jw < TW_; jw += 4) {
+      const int w = w_base + jw;
+      if (w < 0 || w >= W) continue;
+      uint4* ptr = reinterpret_cast<uint4*>(tile + (ih * TW_ + jw) * 128 + (pch << 4));
+      float f[8];
+      unpack8(*ptr, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = fmaf(p0[j], out[j], p1[j]);
-  } else if (mode == CVB_A_AFF_SILU) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = silu_f(fmaf(p0[j], out[j], p1[j]));
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(sc[j], f[j], sh[j]);
+        f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
+      }
+      *ptr = pack8(f);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------- forward
-// TMA-staged: one elected thread issues a 4-D tensor load of the [IH, IW, 64ch] halo tile (out-of-bounds = zero fill = the
-// conv padding) straight into 128B-swizzled shared memory; two buffers + mbarriers keep the NEXT image's tile in flight while
-// the current one is transformed (producer BN+SiLU, in place) and convolved.
-template <int XMODE>
+// Output tile TH x TW, input tile IH x IW = ((TH-1)S+3) x ((TW-1)S+3) with origin (S*oh0 - 1, S*ow0 - 1).
+//   stride 1: strip = 2 output rows x SEG columns, window 4 x 3;  stride 2: strip = 1 output row x SEG columns, window 3 x 3.
+template <int XMODE, int S>
 __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const cvb_dw_fwd_args p, int Ho, int Wo, int TH,
-                                                       int TW, int logTW, int tiles_w, int buf_bytes) {
+                                                       int TW, int tiles_w, int buf_bytes) {
+  constexpr int R = (S == 1) ? 2 : 1;
+  constexpr int WR = (S == 1) ? 4 : 3;  // window rows
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 128B-swizzled TMA destinations must be 1024-byte aligned in the shared window: align by hand (host adds 1 KB of slack)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ float s_cs[CB], s_cq[CB];
+  __shared__ __align__(16) float s_xp[2 * CB];
   __shared__ __align__(8) uint64_t bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = p.stride;
   const int th_i = blockIdx.x / tiles_w, tw_i = blockIdx.x % tiles_w;
   const int oh0 = th_i * TH, ow0 = tw_i * TW;
   const int c0 = blockIdx.y * CB;
-  const int IH = (TH - 1) * s + 3, IW = (TW - 1) * s + 3;
-  const int h_base = oh0 * s - 1, w_base = ow0 * s - 1;
+  const int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3;
+  const int h_base = oh0 * S - 1, w_base = ow0 * S - 1;
   const uint32_t tile_bytes = (uint32_t)IH * IW * 128;
   const int n_img = (p.B - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
 
@@ -64,82 +118,74 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
       tma_load_4d(smem + i * buf_bytes, &tmX, &bar[i], c0, w_base, h_base, (int)blockIdx.z + i * (int)gridDim.z);
     }
   }
-
-  const int cgi = tid & 7, pt = tid >> 3;
-  const int c = c0 + cgi * 8;
-  const bool c_ok = c < p.C;
-  float cs[8], cq[8];  // BatchNorm statistics, accumulated over the batch loop and flushed once per CTA
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-  uint32_t wpk[9][4];  // the 72 weights of this thread's 8 channels are bf16 values: keep them packed
-#pragma unroll
-  for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) wpk[tp][j] = c_ok ? pack_bf162(p.Wt[tp * p.C + c + 2 * j], p.Wt[tp * p.C + c + 2 * j + 1]) : 0u;
-
-  // producer BN scale/shift of this thread's 8 channels (transform role: chunk = lane & 7 == cgi), hoisted out of all loops
-  float xp0[8], xp1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    xp0[j] = (XMODE != CVB_A_RAW && c_ok) ? __ldg(p.x_p0 + c + j) : 1.f;
-    xp1[j] = (XMODE != CVB_A_RAW && c_ok) ? __ldg(p.x_p1 + c + j) : 0.f;
+  if (XMODE != CVB_A_RAW && tid < CB) {
+    const bool ok = c0 + tid < p.C;
+    s_xp[tid] = ok ? __ldg(p.x_p0 + c0 + tid) : 1.f;
+    s_xp[CB + tid] = ok ? __ldg(p.x_p1 + c0 + tid) : 0.f;
   }
+  const int cl = c0 + 2 * lane;  // this lane's channel pair
+  const bool lane_ok = cl < p.C;
+  float2 wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wv[t] = lane_ok ? make_float2(p.Wt[t * p.C + cl], p.Wt[t * p.C + cl + 1]) : make_float2(0.f, 0.f);
+  float2 cs = make_float2(0.f, 0.f), cq = make_float2(0.f, 0.f);
+  const int strips_w = TW / SEG;
+  const int n_strips = (TH / R) * strips_w;
+  __syncthreads();  // s_xp visible
+
   for (int i = 0; i < n_img; ++i) {
     const int b = (int)blockIdx.z + i * (int)gridDim.z;
     uint8_t* tile = smem + (i & 1) * buf_bytes;
     mbar_wait(&bar[i & 1], (i >> 1) & 1);
     if (XMODE != CVB_A_RAW) {
-      // in-place producer transform; out-of-bounds pixels / channels stay zero (padding acts on the activated tensor)
-      const int pch = lane & 7;  // physical 16-byte chunk inside the pixel's 128-byte row
-      for (int ih = warp; ih < IH; ih += NT / 32) {
-        const int h = h_base + ih;
-        if (h < 0 || h >= p.H) continue;
-        for (int jw = lane >> 3; jw < IW; jw += 4) {
-          const int w = w_base + jw;
-          const int pix = ih * IW + jw;
-          const int lc = c0 + (pch << 3);
-          if (w < 0 || w >= p.W || lc >= p.C) continue;
-          uint4* ptr = reinterpret_cast<uint4*>(tile + pix * 128 + (pch << 4));
-          float f[8];
-          unpack8(*ptr, f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float z = fmaf(xp0[j], f[j], xp1[j]);
-            f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
-          }
-          *ptr = pack8(f);
-        }
-      }
+      transform_tile<XMODE, NT>(tile, IH, IW, h_base, w_base, p.H, p.W, c0, p.C, s_xp, warp, lane);
       __syncthreads();
     }
-    bf16* __restrict__ Y = static_cast<bf16*>(p.Y) + (size_t)b * Ho * Wo * p.C;
-    for (int op = pt; op < TH * TW; op += NT / 8) {
-      const int oh = op >> logTW, ow = op & (TW - 1);
-      const int gh = oh0 + oh, gw = ow0 + ow;
-      if (gh < Ho && gw < Wo && c_ok) {
-        float acc[8];
+    bf16* __restrict__ Y = static_cast<bf16*>(p.Y) + (size_t)b * Ho * Wo * p.C + cl;
+    for (int st = warp; st < n_strips; st += NT / 32) {
+      const int orow = (st / strips_w) * R, ocol = (st % strips_w) * SEG;  // tile-local output origin of the strip
+      const int irow = orow * S, icol = ocol * S;                         // tile-local input origin (halo included)
+      bf16* yrow[R];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int r = 0; r < R; ++r) yrow[r] = Y + ((size_t)(oh0 + orow + r) * Wo + ow0 + ocol) * p.C;
+      float2 win[WR][3];
+      if (S == 1) {
 #pragma unroll
-        for (int u = 0; u < 3; ++u)
+        for (int k = 0; k < WR; ++k) { win[k][1] = lds2(tile, (irow + k) * IW + icol, lane); win[k][2] = lds2(tile, (irow + k) * IW + icol + 1, lane); }
+      } else {
 #pragma unroll
-          for (int v = 0; v < 3; ++v) {
-            float xin[8];
-            unpack8(*reinterpret_cast<const uint4*>(tile + pix_off((oh * s + u) * IW + ow * s + v, cgi)), xin);
+        for (int k = 0; k < WR; ++k) win[k][2] = lds2(tile, (irow + k) * IW + icol, lane);
+      }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 wv = unpack_bf162(wpk[u * 3 + v][j]);
-              acc[2 * j] = fmaf(wv.x, xin[2 * j], acc[2 * j]);
-              acc[2 * j + 1] = fmaf(wv.y, xin[2 * j + 1], acc[2 * j + 1]);
-            }
+      for (int x = 0; x < SEG; ++x) {
+        if (S == 1) {
+#pragma unroll
+          for (int k = 0; k < WR; ++k) { win[k][0] = win[k][1]; win[k][1] = win[k][2]; win[k][2] = lds2(tile, (irow + k) * IW + icol + x + 2, lane); }
+        } else {
+#pragma unroll
+          for (int k = 0; k < WR; ++k) {
+            win[k][0] = win[k][2];
+            win[k][1] = lds2(tile, (irow + k) * IW + icol + 2 * x + 1, lane);
+            win[k][2] = lds2(tile, (irow + k) * IW + icol + 2 * x + 2, lane);
           }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[j] = bf16_round(acc[j]);
-          cs[j] += acc[j];
-          cq[j] += acc[j] * acc[j];
         }
-        stg16(Y + ((size_t)gh * Wo + gw) * p.C + c, pack8(acc));
+        const int gw = ow0 + ocol + x;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 3; ++u)
+#pragma unroll
+            for (int v = 0; v < 3; ++v) acc = ffma2(wv[u * 3 + v], win[r + u][v], acc);
+          const bool ok = (oh0 + orow + r < Ho) && (gw < Wo) && lane_ok;
+          const uint32_t pk = pack_bf162(acc.x, acc.y);
+          float2 rv = up2(pk);  // statistics of the stored (rounded) values; branch-free, only the store is predicated
+          rv.x = ok ? rv.x : 0.f;
+          rv.y = ok ? rv.y : 0.f;
+          cs = fadd2(cs, rv);
+          cq = ffma2(rv, rv, cq);
+          if (ok) *reinterpret_cast<uint32_t*>(yrow[r] + (size_t)x * p.C) = pk;
+        }
       }
     }
     __syncthreads();  // every thread is done with this buffer
@@ -150,13 +196,9 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
     }
   }
   if (p.col_sum) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // reduce over the 4 pixel-threads of this warp that share the channel chunk (lane bits 3,4)
-      float a = cs[j], q = cq[j];
-      a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
-      q += __shfl_xor_sync(0xffffffffu, q, 8); q += __shfl_xor_sync(0xffffffffu, q, 16);
-      if (lane < 8) { atomicAdd(&s_cs[cgi * 8 + j], a); atomicAdd(&s_cq[cgi * 8 + j], q); }
+    if (lane_ok) {
+      atomicAdd(&s_cs[2 * lane], cs.x); atomicAdd(&s_cs[2 * lane + 1], cs.y);
+      atomicAdd(&s_cq[2 * lane], cq.x); atomicAdd(&s_cq[2 * lane + 1], cq.y);
     }
     __syncthreads();
     if (tid < CB && c0 + tid < p.C) {
@@ -167,47 +209,89 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------------------------ backward
-// One pass over (dz, y2, x) per image tile, all three staged by TMA (zero-filled halos) into two buffer sets so the next
-// image's tiles are in flight while this one is processed:
-//   1. dy = BN-backward(dz, y2) in place                      (generic transform of the dz tile)
-//   2. phase B: dX = conv_transpose(dy) * silu'(BN(x)) (+ the producer's BN-backward statistics), raw x read from the smem tile
-//   3. a = SiLU(BN(x)) in place, phase A: dW[9 taps] += dy * a(shifted)
-// 512 threads, register-lean roles: phase A thread = (channel pair, pixel slice = warp) with 18 accumulators kept over the batch
-// loop; phase B thread = (8-channel chunk, pixel) with the 72 weights as 36 packed bf16x2 registers.
-constexpr int NTB = 512;
+// Per image tile: (dz, x) double-buffered, y2 single-buffered (it is consumed by step 1 only and refilled right after it).
+//   1. dy = c1*dz + c2*y2 + c3 in place (in-bounds pixels only: the zero halo is the transposed conv's padding)
+//   2. one walk over the tile's INPUT pixels: dX, dW, activation backward, BN-backward statistics of the producer.
+// stride 1: strip = 2 input rows x SEG columns, dy window 4 x 3 (halo origin -1).
+// stride 2: strip = 1 OUTPUT row x SEG output columns = 2 x 2SEG input pixels, dy window 2 x 2 (halo +1 on the high side):
+//   x(2i,2j)     <- W11 dy[i,j]                      x(2i,2j+1)   <- W10 dy[i,j+1] + W12 dy[i,j]
+//   x(2i+1,2j)   <- W01 dy[i+1,j] + W21 dy[i,j]      x(2i+1,2j+1) <- W00 dy[i+1,j+1] + W02 dy[i+1,j] + W20 dy[i,j+1] + W22 dy[i,j]
+struct PixOut {
+  float2 a;     // act(BN(x)) (dW operand)
+  float2 dact;  // d act / d z
+  float2 xr;    // raw x (statistics operand)
+};
+template <int XMODE>
+__device__ __forceinline__ PixOut load_x(const uint8_t* sX, int pix, int lane, float2 xsc, float2 xsh, bool ok) {
+  PixOut o;
+  o.xr = lds2(sX, pix, lane);
+  if (XMODE == CVB_A_RAW) {
+    o.a = o.xr;
+    o.dact = make_float2(1.f, 1.f);
+  } else {
+    const float2 z = ffma2(xsc, o.xr, xsh);
+    if (XMODE == CVB_A_AFF_SILU) {
+      // one sigmoid per element serves both uses: a = z*s and silu'(z) = s + a*(1-s)
+      const float sx = 1.0f / (1.0f + __expf(-z.x)), sy = 1.0f / (1.0f + __expf(-z.y));
+      o.a = make_float2(z.x * sx, z.y * sy);
+      o.dact = make_float2(fmaf(o.a.x, 1.0f - sx, sx), fmaf(o.a.y, 1.0f - sy, sy));
+    } else {
+      o.a = z;
+      o.dact = make_float2(1.f, 1.f);
+    }
+  }
+  if (!ok) o.a = make_float2(0.f, 0.f);  // pixels past the image edge must not reach dW
+  return o;
+}
+template <int XMODE>
+__device__ __forceinline__ void finish_pixel(float2 d, const PixOut& o, float2& cs, float2& cq, bf16* dst, bool ok) {
+  // branch-free: out-of-image pixels / channels contribute zeros to the statistics and only the store is predicated
+  if (XMODE == CVB_A_AFF_SILU) d = fmul2(d, o.dact);
+  const uint32_t pk = pack_bf162(d.x, d.y);
+  if (XMODE != CVB_A_RAW) {
+    float2 rv = up2(pk);
+    rv.x = ok ? rv.x : 0.f;
+    rv.y = ok ? rv.y : 0.f;
+    cs = fadd2(cs, rv);
+    cq = ffma2(rv, o.xr, cq);
+  }
+  if (ok) *reinterpret_cast<uint32_t*>(dst) = pk;
+}
 
-template <int GMODE, int XMODE>
+template <int GMODE, int XMODE, int S>
 __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant__ CUtensorMap tmY2,
                                                         const __grid_constant__ CUtensorMap tmX, const cvb_dw_bwd_args p, int Ho, int Wo, int TH,
-                                                        int TW, int logTW, int tiles_w, int g_bytes, int x_bytes) {
+                                                        int TW, int tiles_w, int g_bytes, int x_bytes) {
+  constexpr bool BNB = (GMODE == CVB_A_BNB);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ float s_cs[CB], s_cq[CB];
   __shared__ float s_dw[9][CB];
-  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ __align__(16) float s_gp[3 * CB];
+  __shared__ __align__(8) uint64_t bar[2], ybar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = p.stride;
   const int th_i = blockIdx.x / tiles_w, tw_i = blockIdx.x % tiles_w;
   const int oh0 = th_i * TH, ow0 = tw_i * TW;
   const int c0 = blockIdx.y * CB;
-  const int go = (s == 1) ? 1 : 0;          // halo of the dy tile on the low side
-  const int GH = TH + (s == 1 ? 2 : 1), GW = TW + (s == 1 ? 2 : 1);
-  const int XH = s * TH + 3 - s, XW = s * TW + 3 - s;  // input tile + halo (origin -1)
-  const int ITH = s * TH, ITW = s * TW;     // owned input tile
-  const int logITW = logTW + (s == 2 ? 1 : 0);
-  const int set_bytes = (GMODE == CVB_A_BNB ? 2 : 1) * g_bytes + x_bytes;
-  const uint32_t tx_bytes = (uint32_t)(GMODE == CVB_A_BNB ? 2 : 1) * GH * GW * 128 + (uint32_t)XH * XW * 128;
+  const int GH = TH + (S == 1 ? 2 : 1), GW = TW + (S == 1 ? 2 : 1);
+  const int XH = S * TH, XW = S * TW;  // input tile, no halo
+  const int gh_base = oh0 - (S == 1 ? 1 : 0), gw_base = ow0 - (S == 1 ? 1 : 0);
+  const int xh_base = S * oh0, xw_base = S * ow0;
+  const int set_bytes = g_bytes + x_bytes;
+  uint8_t* sY2 = smem + 2 * set_bytes;
+  const uint32_t g_tx = (uint32_t)GH * GW * 128, x_tx = (uint32_t)XH * XW * 128;
   const int n_img = (p.B - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
-  const int gh_base = oh0 - go, gw_base = ow0 - go;
-  const int xh_base = s * oh0 - 1, xw_base = s * ow0 - 1;
 
-  auto issue = [&](int i) {  // one elected thread
+  auto issue = [&](int i) {  // one elected thread: (dz, x) of the CTA's i-th image into set i & 1
     uint8_t* base = smem + (i & 1) * set_bytes;
     const int b = (int)blockIdx.z + i * (int)gridDim.z;
-    mbar_expect_tx(&bar[i & 1], tx_bytes);
+    mbar_expect_tx(&bar[i & 1], g_tx + x_tx);
     tma_load_4d(base, &tmDZ, &bar[i & 1], c0, gw_base, gh_base, b);
-    if (GMODE == CVB_A_BNB) tma_load_4d(base + g_bytes, &tmY2, &bar[i & 1], c0, gw_base, gh_base, b);
-    tma_load_4d(base + (GMODE == CVB_A_BNB ? 2 : 1) * g_bytes, &tmX, &bar[i & 1], c0, xw_base, xh_base, b);
+    tma_load_4d(base + g_bytes, &tmX, &bar[i & 1], c0, xw_base, xh_base, b);
+  };
+  auto issue_y2 = [&](int i) {
+    mbar_expect_tx(&ybar, g_tx);
+    tma_load_4d(sY2, &tmY2, &ybar, c0, gw_base, gh_base, (int)blockIdx.z + i * (int)gridDim.z);
   };
 
   for (int i = tid; i < 9 * CB; i += NTB) (&s_dw[0][0])[i] = 0.f;
@@ -215,6 +299,7 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&ybar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -222,167 +307,160 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
   pdl_trigger();
   if (tid == 0) {
     for (int i = 0; i < 2 && i < n_img; ++i) issue(i);
+    if (BNB) issue_y2(0);
   }
-
-  const int cgi = tid & 7, pt = tid >> 3;   // phase B role
-  const int cc = c0 + cgi * 8;
-  const bool cc_ok = cc < p.C;
-  const int cp = lane, ps = warp;           // phase A role: channels c0 + 2cp, +1 ; pixel slice = warp
-  const int pch = lane & 7;                 // transform role: physical 16-byte chunk
-
-  float accw[9][2];
-#pragma unroll
-  for (int tp = 0; tp < 9; ++tp) { accw[tp][0] = 0.f; accw[tp][1] = 0.f; }
-  float cs[8], cq[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { cs[j] = 0.f; cq[j] = 0.f; }
-  uint32_t wpk[9][4];
-#pragma unroll
-  for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      wpk[tp][j] = cc_ok ? pack_bf162(p.Wt[tp * p.C + cc + 2 * j], p.Wt[tp * p.C + cc + 2 * j + 1]) : 0u;
-
-  // producer BN scale/shift of the CTA's 64 channels live in smem (the register budget of 512 threads is spent on the stencil)
-  __shared__ __align__(16) float s_xp[2][CB];
-  if (tid < CB) {
-    const bool ok = (XMODE != CVB_A_RAW) && (c0 + tid < p.C);
-    s_xp[0][tid] = ok ? __ldg(p.x_p0 + c0 + tid) : 1.f;
-    s_xp[1][tid] = ok ? __ldg(p.x_p1 + c0 + tid) : 0.f;
+  if (BNB && tid < CB) {
+    const bool ok = c0 + tid < p.C;
+    s_gp[tid] = ok ? __ldg(p.g_p0 + c0 + tid) : 0.f;
+    s_gp[CB + tid] = ok ? __ldg(p.g_p1 + c0 + tid) : 0.f;
+    s_gp[2 * CB + tid] = ok ? __ldg(p.g_p2 + c0 + tid) : 0.f;
   }
-  __syncthreads();
+  const int cl = c0 + 2 * lane;
+  const bool lane_ok = cl < p.C;
+  float2 wv[9], accw[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    wv[t] = lane_ok ? make_float2(p.Wt[t * p.C + cl], p.Wt[t * p.C + cl + 1]) : make_float2(0.f, 0.f);
+    accw[t] = make_float2(0.f, 0.f);
+  }
+  float2 xsc = make_float2(1.f, 1.f), xsh = make_float2(0.f, 0.f);
+  if (XMODE != CVB_A_RAW && lane_ok) {
+    xsc = make_float2(__ldg(p.x_p0 + cl), __ldg(p.x_p0 + cl + 1));
+    xsh = make_float2(__ldg(p.x_p1 + cl), __ldg(p.x_p1 + cl + 1));
+  }
+  float2 cs = make_float2(0.f, 0.f), cq = make_float2(0.f, 0.f);
+  const int strips_w = TW / SEG;
+  const int n_strips = (S == 1 ? TH / 2 : TH) * strips_w;
+  __syncthreads();  // s_gp visible
+
   for (int i = 0; i < n_img; ++i) {
     const int b = (int)blockIdx.z + i * (int)gridDim.z;
     uint8_t* sG = smem + (i & 1) * set_bytes;
-    uint8_t* sG2 = sG + g_bytes;
-    uint8_t* sX = sG + (GMODE == CVB_A_BNB ? 2 : 1) * g_bytes;
-    bf16* __restrict__ DX = static_cast<bf16*>(p.DX) + (size_t)b * p.H * p.W * p.C;
+    const uint8_t* sX = sG + g_bytes;
     mbar_wait(&bar[i & 1], (i >> 1) & 1);
-    // ---- 1. dy = c1*dz + c2*y2 + c3, in place, in-bounds pixels only (the zero-filled halo must stay zero)
-    if (GMODE == CVB_A_BNB) {
-      float g0[8], g1[8], g2[8];  // BN-backward coefficients of this thread's chunk (scoped: live only during this pass)
-      const int glc = c0 + (pch << 3);
+    // ---- 1. dy = c1*dz + c2*y2 + c3, in place, in-bounds pixels only
+    if (BNB) {
+      mbar_wait(&ybar, i & 1);
+      const int pch = lane & 7;
+      if (c0 + (pch << 3) < p.C) {
+        float g0[8], g1[8], g2[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool ok = glc < p.C;
-        g0[j] = ok ? __ldg(p.g_p0 + glc + j) : 0.f;
-        g1[j] = ok ? __ldg(p.g_p1 + glc + j) : 0.f;
-        g2[j] = ok ? __ldg(p.g_p2 + glc + j) : 0.f;
-      }
-      for (int gi = warp; gi < GH; gi += NTB / 32) {
-        const int oh = gh_base + gi;
-        if (oh < 0 || oh >= Ho) continue;
-        for (int gj = lane >> 3; gj < GW; gj += 4) {
-          const int ow = gw_base + gj;
-          const int pix = gi * GW + gj;
-          const int lc = c0 + (pch << 3);
-          if (ow < 0 || ow >= Wo || lc >= p.C) continue;
-          uint4* pz = reinterpret_cast<uint4*>(sG + pix * 128 + (pch << 4));
-          float f[8], y[8];
-          unpack8(*pz, f);
-          unpack8(*reinterpret_cast<const uint4*>(sG2 + pix * 128 + (pch << 4)), y);
+        for (int q = 0; q < 2; ++q) {
+          *reinterpret_cast<float4*>(g0 + 4 * q) = *reinterpret_cast<const float4*>(s_gp + pch * 8 + 4 * q);
+          *reinterpret_cast<float4*>(g1 + 4 * q) = *reinterpret_cast<const float4*>(s_gp + CB + pch * 8 + 4 * q);
+          *reinterpret_cast<float4*>(g2 + 4 * q) = *reinterpret_cast<const float4*>(s_gp + 2 * CB + pch * 8 + 4 * q);
+        }
+        for (int gi = warp; gi < GH; gi += NTB / 32) {
+          const int oh = gh_base + gi;
+          if (oh < 0 || oh >= Ho) continue;
+          for (int gj = lane >> 3; gj < GW; gj += 4) {
+            const int ow = gw_base + gj;
+            if (ow < 0 || ow >= Wo) continue;
+            const int off = (gi * GW + gj) * 128 + (pch << 4);
+            uint4* pz = reinterpret_cast<uint4*>(sG + off);
+            float f[8], y[8];
+            unpack8(*pz, f);
+            unpack8(*reinterpret_cast<const uint4*>(sY2 + off), y);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
-          *pz = pack8(f);
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
+            *pz = pack8(f);
+          }
         }
       }
       __syncthreads();
-    }
-    // ---- 2. phase B: input gradient  da[h,w] = sum_{u,v} W[u,v] * dy[(h+1-u)/s, (w+1-v)/s]
-    for (int ip = pt; ip < ITH * ITW; ip += NTB / 8) {
-      const int ih = ip >> logITW, iw = ip & (ITW - 1);
-      const int h = s * oh0 + ih, w = s * ow0 + iw;
-      if (h < p.H && w < p.W && cc_ok) {
-        float da[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) da[j] = 0.f;
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          int gi;
-          if (s == 1) gi = ih + 2 - u;
-          else { if (((ih + 1 - u) & 1) != 0) continue; gi = (ih + 1 - u) >> 1; }
-#pragma unroll
-          for (int v = 0; v < 3; ++v) {
-            int gj;
-            if (s == 1) gj = iw + 2 - v;
-            else { if (((iw + 1 - v) & 1) != 0) continue; gj = (iw + 1 - v) >> 1; }
-            float dy[8];
-            unpack8(*reinterpret_cast<const uint4*>(sG + pix_off(gi * GW + gj, cgi)), dy);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 wv = unpack_bf162(wpk[u * 3 + v][j]);
-              da[2 * j] = fmaf(wv.x, dy[2 * j], da[2 * j]);
-              da[2 * j + 1] = fmaf(wv.y, dy[2 * j + 1], da[2 * j + 1]);
-            }
-          }
-        }
-        if (XMODE != CVB_A_RAW) {
-          // one sigmoid per element serves both uses: a = z*s (kept in place for phase A) and silu'(z) = s + a*(1-s)
-          uint4* px = reinterpret_cast<uint4*>(sX + pix_off((ih + 1) * XW + iw + 1, cgi));
-          float xr[8], av[8], xp0[8], xp1[8];
-          unpack8(*px, xr);
-          *reinterpret_cast<float4*>(xp0) = *reinterpret_cast<const float4*>(&s_xp[0][cgi * 8]);
-          *reinterpret_cast<float4*>(xp0 + 4) = *reinterpret_cast<const float4*>(&s_xp[0][cgi * 8 + 4]);
-          *reinterpret_cast<float4*>(xp1) = *reinterpret_cast<const float4*>(&s_xp[1][cgi * 8]);
-          *reinterpret_cast<float4*>(xp1 + 4) = *reinterpret_cast<const float4*>(&s_xp[1][cgi * 8 + 4]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(xp0[j], xr[j], xp1[j]);
-            if (XMODE == CVB_A_AFF_SILU) {
-              const float sg = 1.0f / (1.0f + __expf(-z));
-              av[j] = z * sg;
-              da[j] *= fmaf(av[j], 1.0f - sg, sg);
-            } else {
-              av[j] = z;
-            }
-            da[j] = bf16_round(da[j]);
-            cs[j] += da[j];
-            cq[j] += da[j] * xr[j];
-          }
-          *px = pack8(av);
-        }
-        stg16(DX + ((size_t)h * p.W + w) * p.C + cc, pack8(da));
+      if (tid == 0 && i + 1 < n_img) {
+        fence_proxy_async();
+        issue_y2(i + 1);
       }
     }
-    // ---- 3. halo ring of the input tile: a = act(BN(x)) in place (in-bounds only; the centre was done in phase B), then phase A
-    if (XMODE != CVB_A_RAW) {
-      for (int ih = warp; ih < XH; ih += NTB / 32) {
-        const int h = xh_base + ih;
-        if (h < 0 || h >= p.H) continue;
-        const bool row_center = (ih >= 1 && ih <= ITH);
-        for (int jw = lane >> 3; jw < XW; jw += 4) {
-          if (row_center && jw >= 1 && jw <= ITW) continue;
-          const int w = xw_base + jw;
-          const int pix = ih * XW + jw;
-          const int lc = c0 + (pch << 3);
-          if (w < 0 || w >= p.W || lc >= p.C) continue;
-          uint4* px = reinterpret_cast<uint4*>(sX + pix * 128 + (pch << 4));
-          float f[8];
-          unpack8(*px, f);
+    // ---- 2. the walk
+    bf16* __restrict__ DX = static_cast<bf16*>(p.DX) + (size_t)b * p.H * p.W * p.C + cl;
+    for (int st = warp; st < n_strips; st += NTB / 32) {
+      const int scol = (st % strips_w) * SEG;
+      if (S == 1) {
+        const int r0 = (st / strips_w) * 2;  // tile-local input rows r0, r0+1; dy halo rows r0 .. r0+3, halo cols scol .. scol+SEG+1
+        bf16* dxrow[2];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float z = fmaf(s_xp[0][pch * 8 + j], f[j], s_xp[1][pch * 8 + j]);
-            f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
+        for (int r = 0; r < 2; ++r) dxrow[r] = DX + ((size_t)(oh0 + r0 + r) * p.W + ow0 + scol) * p.C;
+        float2 win[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { win[k][1] = lds2(sG, (r0 + k) * GW + scol, lane); win[k][2] = lds2(sG, (r0 + k) * GW + scol + 1, lane); }
+#pragma unroll
+        for (int x = 0; x < SEG; ++x) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { win[k][0] = win[k][1]; win[k][1] = win[k][2]; win[k][2] = lds2(sG, (r0 + k) * GW + scol + x + 2, lane); }
+          const int w = ow0 + scol + x;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int h = oh0 + r0 + r;
+            const bool ok = (h < p.H) && (w < p.W) && lane_ok;
+            const PixOut o = load_x<XMODE>(sX, (r0 + r) * XW + scol + x, lane, xsc, xsh, ok);
+            float2 d = make_float2(0.f, 0.f);
+            // dyn[u][v] = dy[h+1-u][w+1-v] = win[r+2-u][2-v]
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+              for (int v = 0; v < 3; ++v) {
+                d = ffma2(wv[u * 3 + v], win[r + 2 - u][2 - v], d);
+                accw[u * 3 + v] = ffma2(o.a, win[r + 2 - u][2 - v], accw[u * 3 + v]);
+              }
+            finish_pixel<XMODE>(d, o, cs, cq, dxrow[r] + (size_t)x * p.C, ok);
           }
-          *px = pack8(f);
         }
-      }
-    }
-    __syncthreads();  // dX done with the dy tile; transformed input tile complete
-    {
-      const uint32_t sub = static_cast<uint32_t>((cp & 3) << 2);
-      const int chk = cp >> 2;
-      for (int op = ps; op < TH * TW; op += NTB / 32) {
-        const int oh = op >> logTW, ow = op & (TW - 1);
-        const float2 dy = unpack_bf162(*reinterpret_cast<const uint32_t*>(sG + pix_off((oh + go) * GW + ow + go, chk) + sub));
+      } else {
+        const int i0 = st / strips_w;  // tile-local output row; dy rows i0, i0+1; input rows 2*i0, 2*i0+1
+        bf16* dxrow0 = DX + ((size_t)(2 * (oh0 + i0)) * p.W + 2 * (ow0 + scol)) * p.C;
+        float2 win[2][2];
 #pragma unroll
-        for (int u = 0; u < 3; ++u)
+        for (int k = 0; k < 2; ++k) win[k][1] = lds2(sG, (i0 + k) * GW + scol, lane);
 #pragma unroll
-          for (int v = 0; v < 3; ++v) {
-            const float2 a = unpack_bf162(*reinterpret_cast<const uint32_t*>(sX + pix_off((s * oh + u) * XW + s * ow + v, chk) + sub));
-            accw[u * 3 + v][0] = fmaf(dy.x, a.x, accw[u * 3 + v][0]);
-            accw[u * 3 + v][1] = fmaf(dy.y, a.y, accw[u * 3 + v][1]);
+        for (int x = 0; x < SEG; ++x) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) { win[k][0] = win[k][1]; win[k][1] = lds2(sG, (i0 + k) * GW + scol + x + 1, lane); }
+          const int hh = 2 * (oh0 + i0), ww = 2 * (ow0 + scol + x);
+          const int xp = (2 * i0) * XW + 2 * (scol + x);
+          bf16* dx0 = dxrow0 + (size_t)(2 * x) * p.C;
+          bf16* dx1 = dx0 + (size_t)p.W * p.C;
+          const bool ok0 = hh < p.H, ok1 = hh + 1 < p.H, okc0 = ww < p.W, okc1 = ww + 1 < p.W;
+          {  // (2i, 2j)
+            const bool ok = ok0 && okc0 && lane_ok;
+            const PixOut o = load_x<XMODE>(sX, xp, lane, xsc, xsh, ok);
+            float2 d = fmul2(wv[4], win[0][0]);
+            accw[4] = ffma2(o.a, win[0][0], accw[4]);
+            finish_pixel<XMODE>(d, o, cs, cq, dx0, ok);
           }
+          {  // (2i, 2j+1)
+            const bool ok = ok0 && okc1 && lane_ok;
+            const PixOut o = load_x<XMODE>(sX, xp + 1, lane, xsc, xsh, ok);
+            float2 d = fmul2(wv[3], win[0][1]);
+            d = ffma2(wv[5], win[0][0], d);
+            accw[3] = ffma2(o.a, win[0][1], accw[3]);
+            accw[5] = ffma2(o.a, win[0][0], accw[5]);
+            finish_pixel<XMODE>(d, o, cs, cq, dx0 + p.C, ok);
+          }
+          {  // (2i+1, 2j)
+            const bool ok = ok1 && okc0 && lane_ok;
+            const PixOut o = load_x<XMODE>(sX, xp + XW, lane, xsc, xsh, ok);
+            float2 d = fmul2(wv[1], win[1][0]);
+            d = ffma2(wv[7], win[0][0], d);
+            accw[1] = ffma2(o.a, win[1][0], accw[1]);
+            accw[7] = ffma2(o.a, win[0][0], accw[7]);
+            finish_pixel<XMODE>(d, o, cs, cq, dx1, ok);
+          }
+          {  // (2i+1, 2j+1)
+            const bool ok = ok1 && okc1 && lane_ok;
+            const PixOut o = load_x<XMODE>(sX, xp + XW + 1, lane, xsc, xsh, ok);
+            float2 d = fmul2(wv[0], win[1][1]);
+            d = ffma2(wv[2], win[1][0], d);
+            d = ffma2(wv[6], win[0][1], d);
+            d = ffma2(wv[8], win[0][0], d);
+            accw[0] = ffma2(o.a, win[1][1], accw[0]);
+            accw[2] = ffma2(o.a, win[1][0], accw[2]);
+            accw[6] = ffma2(o.a, win[0][1], accw[6]);
+            accw[8] = ffma2(o.a, win[0][0], accw[8]);
+            finish_pixel<XMODE>(d, o, cs, cq, dx1 + p.C, ok);
+          }
+        }
       }
     }
     __syncthreads();  // every thread is done with this buffer set
@@ -393,18 +471,15 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
   }
 
   // ---- reductions (once per CTA)
+  if (lane_ok) {
 #pragma unroll
-  for (int tp = 0; tp < 9; ++tp) {
-    atomicAdd(&s_dw[tp][2 * cp], accw[tp][0]);
-    atomicAdd(&s_dw[tp][2 * cp + 1], accw[tp][1]);
-  }
-  if (p.col_sum) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = cs[j], q = cq[j];
-      a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
-      q += __shfl_xor_sync(0xffffffffu, q, 8); q += __shfl_xor_sync(0xffffffffu, q, 16);
-      if (lane < 8) { atomicAdd(&s_cs[cgi * 8 + j], a); atomicAdd(&s_cq[cgi * 8 + j], q); }
+    for (int t = 0; t < 9; ++t) {
+      atomicAdd(&s_dw[t][2 * lane], accw[t].x);
+      atomicAdd(&s_dw[t][2 * lane + 1], accw[t].y);
+    }
+    if (p.col_sum) {
+      atomicAdd(&s_cs[2 * lane], cs.x); atomicAdd(&s_cs[2 * lane + 1], cs.y);
+      atomicAdd(&s_cq[2 * lane], cq.x); atomicAdd(&s_cq[2 * lane + 1], cq.y);
     }
   }
   __syncthreads();
@@ -418,14 +493,7 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
   }
 }
 
-int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
-
-void pick_tile(int Ho, int Wo, int stride, int* TH, int* TW) {
-  int tw = 1 << ilog2(Wo); if (tw > 16) tw = 16;
-  int budget = (stride == 1 ? 128 : 64) / tw;
-  int th = 1 << ilog2(Ho); if (th > budget) th = budget; if (th < 1) th = 1;
-  *TH = th; *TW = tw;
-}
+int round1k(int v) { return (v + 1023) / 1024 * 1024; }
 
 }  // namespace
 
@@ -437,11 +505,14 @@ extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   CVB_CHECK(a.X && a.Wt && a.Y && cvb_aligned16(a.X) && cvb_aligned16(a.Y), "cvb_dw_fwd: null / misaligned operand");
   CVB_CHECK(a.x_mode == CVB_A_RAW || ((a.x_mode == CVB_A_AFF || a.x_mode == CVB_A_AFF_SILU) && a.x_p0 && a.x_p1), "cvb_dw_fwd: bad x_mode %d", a.x_mode);
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_dw_fwd: col_sq missing");
-  const int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
-  int TH, TW; pick_tile(Ho, Wo, a.stride, &TH, &TW);
+  const int s = a.stride;
+  const int Ho = (a.H - 1) / s + 1, Wo = (a.W - 1) / s + 1;
+  // two CTAs per SM: two input buffers of <= ~42 KB each
+  const int TW = (s == 1 && Wo > 8) ? 16 : 8;
+  const int TH = (s == 1) ? (Ho > 8 ? 16 : 8) : 8;
   const int tiles_h = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
-  const int IH = (TH - 1) * a.stride + 3, IW = (TW - 1) * a.stride + 3;
-  const int buf_bytes = (IH * IW * 128 + 1023) / 1024 * 1024;  // 128B-swizzled TMA destinations are 1024-byte aligned
+  const int IH = (TH - 1) * s + 3, IW = (TW - 1) * s + 3;
+  const int buf_bytes = round1k(IH * IW * 128);
   size_t smem = (size_t)2 * buf_bytes + 1024;
   const int cblocks = (a.C + CB - 1) / CB;
   int per_img = tiles_h * tiles_w * cblocks;
@@ -452,15 +523,21 @@ extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmX;
   if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, IH, IW, CB, 0)) return 1;
-#define CVB_DW_FWD(MODE)                                                                                                  \
+#define CVB_DW_FWD(MODE, S)                                                                                               \
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
-    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-    CVB_CUDA(cvb_launch(dw_fwd_kernel<MODE>, grid, NT, smem, st, tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, buf_bytes));                   \
+    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_fwd_kernel<MODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; } \
+    CVB_CUDA(cvb_launch(dw_fwd_kernel<MODE, S>, grid, NT, smem, st, tmX, a, Ho, Wo, TH, TW, tiles_w, buf_bytes));         \
   }
-  if (a.x_mode == CVB_A_RAW) CVB_DW_FWD(CVB_A_RAW)
-  else if (a.x_mode == CVB_A_AFF) CVB_DW_FWD(CVB_A_AFF)
-  else CVB_DW_FWD(CVB_A_AFF_SILU)
+  if (s == 1) {
+    if (a.x_mode == CVB_A_RAW) CVB_DW_FWD(CVB_A_RAW, 1)
+    else if (a.x_mode == CVB_A_AFF) CVB_DW_FWD(CVB_A_AFF, 1)
+    else CVB_DW_FWD(CVB_A_AFF_SILU, 1)
+  } else {
+    if (a.x_mode == CVB_A_RAW) CVB_DW_FWD(CVB_A_RAW, 2)
+    else if (a.x_mode == CVB_A_AFF) CVB_DW_FWD(CVB_A_AFF, 2)
+    else CVB_DW_FWD(CVB_A_AFF_SILU, 2)
+  }
 #undef CVB_DW_FWD
   CVB_LAUNCH_CHECK();
   return 0;
@@ -476,15 +553,17 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   CVB_CHECK(a.x_mode == CVB_A_RAW || ((a.x_mode == CVB_A_AFF || a.x_mode == CVB_A_AFF_SILU) && a.x_p0 && a.x_p1), "cvb_dw_bwd: bad x_mode %d", a.x_mode);
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_dw_bwd: col_sq missing");
   if (a.stride == 2) CVB_CHECK(a.H % 2 == 0 && a.W % 2 == 0, "cvb_dw_bwd: stride 2 needs even H, W");
-  const int Ho = (a.H - 1) / a.stride + 1, Wo = (a.W - 1) / a.stride + 1;
-  int TH, TW; pick_tile(Ho, Wo, a.stride, &TH, &TW);
   const int s = a.stride;
+  const int Ho = (a.H - 1) / s + 1, Wo = (a.W - 1) / s + 1;
+  // one CTA per SM; stride 1: 16 x 16 input pixels, stride 2: 8 x 16 outputs = 16 x 32 input pixels (small maps: 8-wide tiles)
+  const int TW = Wo > 8 ? 16 : 8;
+  const int TH = (s == 1) ? (Ho > 8 ? 16 : 8) : 8;
   const int tiles_h = (Ho + TH - 1) / TH, tiles_w = (Wo + TW - 1) / TW;
   const int GH = TH + (s == 1 ? 2 : 1), GW = TW + (s == 1 ? 2 : 1);
-  const int XH = s * TH + 3 - s, XW = s * TW + 3 - s;
-  const int g_bytes = (GH * GW * 128 + 1023) / 1024 * 1024, x_bytes = (XH * XW * 128 + 1023) / 1024 * 1024;
-  const int nG = (a.g_mode == CVB_A_BNB) ? 2 : 1;
-  size_t smem = (size_t)2 * (nG * g_bytes + x_bytes) + 1024;
+  const int XH = s * TH, XW = s * TW;
+  const int g_bytes = round1k(GH * GW * 128), x_bytes = round1k(XH * XW * 128);
+  const bool bnb = (a.g_mode == CVB_A_BNB);
+  size_t smem = (size_t)2 * (g_bytes + x_bytes) + (bnb ? g_bytes : 0) + 1024;
   const int cblocks = (a.C + CB - 1) / CB;
   // batch loop inside the CTA (double-buffered TMA, dW / statistics flushed once): one CTA per SM, a few waves
   int per_img = tiles_h * tiles_w * cblocks;
@@ -496,23 +575,26 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap tmDZ, tmY2, tmX;
   if (cvb_make_tmap_nhwc(&tmDZ, a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB, 0)) return 1;
-  if (cvb_make_tmap_nhwc(&tmY2, a.g_mode == CVB_A_BNB ? a.Y2 : a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB, 0)) return 1;
+  if (cvb_make_tmap_nhwc(&tmY2, bnb ? a.Y2 : a.DZ, a.B, Ho, Wo, a.C, GH, GW, CB, 0)) return 1;
   if (cvb_make_tmap_nhwc(&tmX, a.X, a.B, a.H, a.W, a.C, XH, XW, CB, 0)) return 1;
-#define CVB_DW_BWD(GM, XM)                                                                                                \
+#define CVB_DW_BWD(GM, XM, S)                                                                                             \
   {                                                                                                                      \
     static bool attr = false;                                                                                            \
-    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024)); attr = true; } \
-    CVB_CUDA(cvb_launch(dw_bwd_kernel<GM, XM>, grid, NTB, smem, st, tmDZ, tmY2, tmX, a, Ho, Wo, TH, TW, ilog2(TW), tiles_w, g_bytes, x_bytes));   \
+    if (!attr) { CVB_CUDA(cudaFuncSetAttribute(dw_bwd_kernel<GM, XM, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024)); attr = true; } \
+    CVB_CUDA(cvb_launch(dw_bwd_kernel<GM, XM, S>, grid, NTB, smem, st, tmDZ, tmY2, tmX, a, Ho, Wo, TH, TW, tiles_w, g_bytes, x_bytes));   \
   }
-  if (a.g_mode == CVB_A_RAW) {
-    if (a.x_mode == CVB_A_RAW) CVB_DW_BWD(CVB_A_RAW, CVB_A_RAW)
-    else if (a.x_mode == CVB_A_AFF) CVB_DW_BWD(CVB_A_RAW, CVB_A_AFF)
-    else CVB_DW_BWD(CVB_A_RAW, CVB_A_AFF_SILU)
+#define CVB_DW_BWD_X(GM, S)                                                   \
+  {                                                                          \
+    if (a.x_mode == CVB_A_RAW) CVB_DW_BWD(GM, CVB_A_RAW, S)                   \
+    else if (a.x_mode == CVB_A_AFF) CVB_DW_BWD(GM, CVB_A_AFF, S)              \
+    else CVB_DW_BWD(GM, CVB_A_AFF_SILU, S)                                    \
+  }
+  if (!bnb) {
+    if (s == 1) CVB_DW_BWD_X(CVB_A_RAW, 1) else CVB_DW_BWD_X(CVB_A_RAW, 2)
   } else {
-    if (a.x_mode == CVB_A_RAW) CVB_DW_BWD(CVB_A_BNB, CVB_A_RAW)
-    else if (a.x_mode == CVB_A_AFF) CVB_DW_BWD(CVB_A_BNB, CVB_A_AFF)
-    else CVB_DW_BWD(CVB_A_BNB, CVB_A_AFF_SILU)
+    if (s == 1) CVB_DW_BWD_X(CVB_A_BNB, 1) else CVB_DW_BWD_X(CVB_A_BNB, 2)
   }
+#undef CVB_DW_BWD_X
 #undef CVB_DW_BWD
   CVB_LAUNCH_CHECK();
   return 0;
