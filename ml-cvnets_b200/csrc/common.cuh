@@ -153,6 +153,9 @@ int cvb_make_tmap_nhwc(CUtensorMap* map, const void* base, int B, int H, int W, 
 // Host: tensor map of a row-major bf16 matrix [rows, cols] (leading dimension ld elements) with a [box_rows, 32 cols] box and
 // 64-byte swizzle: the shared-memory image is exactly the 64-byte-row XOR layout (swz64) the GEMM's ldmatrix addressing uses.
 int cvb_make_tmap_2d_k32(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows);
+// Same matrix view with a [box_rows, 64 cols] box and 128-byte swizzle: the image is the canonical MN-major SWIZZLE_128B UMMA
+// operand layout (8-row x 128-byte atoms) when the ROWS are the reduction dimension (weight-gradient GEMM).
+int cvb_make_tmap_2d_c64(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows);
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -685,6 +685,7 @@ int dispatch_wgrad_a(const cvb_wgrad_args& a, cudaStream_t st) {
 
 }  // namespace
 
+int cvb_pw_wgrad_tc(const cvb_wgrad_args& a, cudaStream_t st);  // wgrad_tc.cu: tcgen05 / TMEM weight-gradient kernel
 int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st);  // gemm_tc.cu: tcgen05 / TMEM kernel for the prologue-free layers
 static int g_tc_enabled = 1;
 extern "C" int cvb_set_tc_enabled(int on) {
@@ -745,6 +746,11 @@ extern "C" int cvb_pw_wgrad(const cvb_wgrad_args* args, cvb_stream_t stream) {
   CVB_CHECK(a.ldg % 8 == 0 && a.lda % 8 == 0 && cvb_aligned16(a.G) && cvb_aligned16(a.A), "cvb_pw_wgrad: operands must be 16-byte aligned / ld % 8");
   if (a.a_mode == CVB_A_GN) CVB_CHECK(a.row_mean && a.row_rstd && a.rows_per_sample > 0 && a.a_p0 && a.a_p1, "cvb_pw_wgrad: GN needs statistics");
   if (a.a_mode == CVB_A_AFF || a.a_mode == CVB_A_AFF_SILU) CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_wgrad: AFF needs p0/p1");
+  if (a.g_mode == CVB_A_BNB) CVB_CHECK(a.G2 && a.g_p0 && a.g_p1 && a.g_p2 && a.ldg2 % 8 == 0 && cvb_aligned16(a.G2), "cvb_pw_wgrad: BNB needs G2 and p0/p1/p2");
+  if (g_tc_enabled && (a.g_mode == CVB_A_RAW || a.g_mode == CVB_A_BNB)) {
+    int rc = cvb_pw_wgrad_tc(a, st);  // tcgen05 kernel: whole [128 x 256] dW blocks in TMEM, operands read once
+    if (rc >= 0) return rc;
+  }
   if (a.g_mode == CVB_A_RAW) return dispatch_wgrad_a<CVB_A_RAW>(a, st);
   if (a.g_mode == CVB_A_BNB) {
     CVB_CHECK(a.G2 && a.g_p0 && a.g_p1 && a.g_p2 && a.ldg2 % 8 == 0 && cvb_aligned16(a.G2), "cvb_pw_wgrad: BNB needs G2 and p0/p1/p2");

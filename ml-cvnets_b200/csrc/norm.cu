@@ -84,6 +84,20 @@ int cvb_make_tmap_2d_k32(CUtensorMap* map, const void* base, int64_t rows, int c
   return 0;
 }
 
+int cvb_make_tmap_2d_c64(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows) {
+  cvb_encode_tiled_fn enc = cvb_get_encoder();
+  CVB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  CVB_CHECK(box_rows > 0 && box_rows <= 256 && ld % 8 == 0 && cols > 0 && rows > 0, "bad 2-D TMA box");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CVB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (2-D, 64-column box) failed with %d", (int)r);
+  return 0;
+}
+
 namespace {
 
 constexpr int NT = 256;

@@ -205,7 +205,9 @@ def test_pw_gemm_gn_bwd(ops, M, N, K, rps):
 
 
 # ----------------------------------------------------------------------------------------------------------- GEMM wgrad
-@pytest.mark.parametrize("M,N,K", [(1000, 64, 32), (4096, 128, 64), (777, 264, 40), (300, 72, 200)])
+# K % 64 == 0 shapes run on the tcgen05 kernel (wgrad_tc.cu: MN-major operands, dW block in TMEM), the others on mma.sync
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 32), (4096, 128, 64), (777, 264, 40), (300, 72, 200), (5000, 192, 192), (3001, 264, 128),
+                                   (2500, 64, 384), (20000, 256, 256), (700, 512, 768), (64, 128, 64)])
 @pytest.mark.parametrize("g_mode,a_mode", [(0, 0), (5, 0), (5, 2), (0, 3), (0, 4), (5, 4), (0, 1)])
 def test_pw_wgrad(ops, M, N, K, g_mode, a_mode):
     rps = 100
@@ -222,6 +224,31 @@ def test_pw_wgrad(ops, M, N, K, g_mode, a_mode):
     ref = Gr.t() @ Ar
     close(dW, ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()) + 1e-5, what="dW")
     close(db, Gr.sum(0), rtol=2e-3, atol=2e-3 * float(Gr.sum(0).abs().max()) + 1e-4, what="dbias")
+
+
+@pytest.mark.parametrize("M,N,K", [(9000, 128, 256), (4097, 392, 192)])
+@pytest.mark.parametrize("g_mode,a_mode", [(0, 0), (5, 2), (0, 4)])
+def test_pw_wgrad_tcgen05_vs_mma_sync(ops, M, N, K, g_mode, a_mode):
+    """Both weight-gradient kernels on identical inputs (they round the transformed operands identically: differences are fp32 summation order)."""
+    rps = 128
+    nb = (M + rps - 1) // rps
+    G, G2, A = bf(rnd(M, N, seed=51)), bf(rnd(M, N, seed=52)), bf(rnd(M, K, seed=53))
+    gp = (1 + 0.2 * rnd(N, seed=54), 0.3 * rnd(N, seed=55), 0.1 * rnd(N, seed=56))
+    ap = (1 + 0.2 * rnd(K, seed=57), 0.3 * rnd(K, seed=58))
+    row = (0.2 * rnd(nb, seed=59), 1 + 0.3 * rnd(nb, seed=60).abs())
+    outs = []
+    for tc in (True, False):
+        prev = ops.set_tc_enabled(tc)
+        try:
+            db = torch.zeros(N, device="cuda")
+            dW = ops.pw_wgrad(G, A, N, K, g_mode=g_mode, G2=G2 if g_mode == 5 else None, g_p=gp, a_mode=a_mode, a_p=ap,
+                              row_stats=row if a_mode == 4 else None, rows_per_sample=rps, dbias=db)
+            outs.append((dW.clone(), db.clone()))
+        finally:
+            ops.set_tc_enabled(prev)
+    scale = float(outs[1][0].abs().max())
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= 2e-4 * scale + 1e-5
+    assert float((outs[0][1] - outs[1][1]).abs().max()) <= 2e-4 * float(outs[1][1].abs().max()) + 1e-4
 
 
 # ------------------------------------------------------------------------------------------------------------ depthwise
