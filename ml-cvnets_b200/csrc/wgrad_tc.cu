@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
         }
       }  // RAW gradient: nothing to do (pixel ranges are multiples of the stage, rows past M are zero-filled by TMA)
       if (AMODE != CVB_A_RAW && a_active) {
+#pragma unroll 4
         for (int row = ar0; row < WT_BMP; row += rpp) {
           uint4* pa = reinterpret_cast<uint4*>(st + a_off + a_box + sw128(row, ac & 7));
           float f[8];
@@ -312,6 +313,7 @@ int cvb_pw_wgrad_tc(const cvb_wgrad_args& a, cudaStream_t st) {
   // 64-channel TMA boxes on the reduced-over operand: K must be a multiple of 64 (the 3x3 stem / K = 32 layers stay on mma.sync);
   // fp32 vector reductions want 16-byte aligned dW rows
   if (a.K % 64 != 0 || a.K < 64 || a.N < 32) return -1;
+  if (a.N <= 64 && a.K <= 64) return -1;  // half-empty 128-lane block and one 64-column box: the 64x64-tile mma.sync kernel is faster (measured)
   if ((reinterpret_cast<uintptr_t>(a.dW) & 15) != 0) return -1;
   if (a.g_mode == CVB_A_RAW) return dispatch_wgrad_tc_a<CVB_A_RAW>(a, st);
   if (a.g_mode == CVB_A_BNB) return dispatch_wgrad_tc_a<CVB_A_BNB>(a, st);
