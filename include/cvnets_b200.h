@@ -31,7 +31,7 @@ typedef void* cvb_stream_t; /* cudaStream_t */
 #define CVB_API
 #endif
 
-#define CVB_ABI_VERSION 3
+#define CVB_ABI_VERSION 4
 
 /* operand "load modes": the normalisation / activation of the PRODUCER layer is applied while the CONSUMER loads it
  * (training-mode BatchNorm cannot be fused into its own conv: SURVEY.md section 7 "hard parts"). */
@@ -201,6 +201,23 @@ CVB_API int cvb_linattn_fwd(const void* QKV, int ldq, int B, int H, int W, int d
 /* bwd: from dO -> dQKV (same layout as QKV; pad columns zeroed); dbias_qkv[2d+1 (+pad)] += column sums if not NULL */
 CVB_API int cvb_linattn_bwd(const void* QKV, int ldq, const void* DO, int ldo, const float* S, const float* CTX, int B, int H, int W,
                     int d, int patch, void* DQKV, float* dbias, cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MultiHeadAttention core (cvnets/layers/multi_head_attention.py:135-239, self-attention branch) and LayerNorm statistics
+ * (cvnets/layers/normalization/layer_norm.py:14-72: nn.LayerNorm over the last dimension of [N, S, C]).
+ * QKV: bf16 [B*S, ldq] rows = tokens, columns [q (H*c) | k (H*c) | v (H*c)] exactly as qkv_proj writes them (:148-153);
+ * O: bf16 [B*S, ldo] with head h at columns h*c.. (the layout out_proj reads, :236).  scale = head_dim^-0.5 (:70, :187).
+ * attn_mask: fp32 [B, S, S] additive (or NULL, :197-208); key_padding_mask: uint8 [B, S], non-zero = masked with -inf (:210-224).
+ * Softmax in fp32 (:226-228).  LSE: fp32 [B, H, S] log-sum-exp (base 2) saved for the backward.  S <= 256, c in {16, 32, 64}.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_mha_fwd(const void* QKV, int ldq, int B, int S, int H, int head_dim, float scale, const float* attn_mask,
+                const unsigned char* key_padding_mask, void* O, int ldo, float* LSE, cvb_stream_t stream);
+/* dQKV (bf16 [B*S, lddq], same column layout as QKV) from dO; recomputes the probabilities from LSE. */
+CVB_API int cvb_mha_bwd(const void* QKV, int ldq, const void* O, const void* DO, int ldo, const float* LSE, int B, int S, int H, int head_dim,
+                float scale, const float* attn_mask, const unsigned char* key_padding_mask, void* DQKV, int lddq, cvb_stream_t stream);
+/* per-token LayerNorm statistics of a bf16 [M, C] matrix: mean[m], rstd[m] = 1/sqrt(var + eps) (biased variance, fp32 math like
+ * nn.LayerNorm under autocast).  The normalisation itself is the GN load mode of the consuming GEMM with rows_per_sample = 1. */
+CVB_API int cvb_ln_stats(const void* X, int ldx, int64_t M, int C, float eps, float* mean, float* rstd, cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GlobalPool(mean) (cvnets/layers/global_pool.py:60-71) and small utilities

@@ -339,6 +339,33 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const bf16* __restrict__ X
 }
 
 // GroupNorm backward phase 2 (+ residual-stream gradient, + column sums of the result)
+// LayerNorm statistics: one warp per token row
+__global__ void __launch_bounds__(NT) ln_stats_kernel(const bf16* __restrict__ X, int ldx, int64_t M, int C, float eps, float* __restrict__ mean,
+                                                      float* __restrict__ rstd) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const bf16* x = X + row * ldx;
+  float s = 0.f, q = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    unpack8(ldg16(x + c), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s += f[e]; q = fmaf(f[e], f[e], q); }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    const float mu = s / (float)C;
+    float var = q / (float)C - mu * mu;
+    if (var < 0.f) var = 0.f;
+    mean[row] = mu;
+    rstd[row] = rsqrtf(var + eps);
+  }
+}
+
 __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict__ G, const bf16* __restrict__ X, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const double* __restrict__ sg, const double* __restrict__ sgx,
                                                           double count, const bf16* __restrict__ DRES, bf16* __restrict__ DX, int64_t M,
@@ -594,6 +621,15 @@ extern "C" int cvb_gn_stats(const void* X, int ldx, int B, int rows_per_sample, 
   if (chunks < 1) chunks = 1;
   CVB_CUDA(cvb_launch(gn_stats_kernel, B * chunks, NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X), ldx, rows_per_sample, C, chunks, samp_sum,
                                                                            samp_sq));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_ln_stats(const void* X, int ldx, int64_t M, int C, float eps, float* mean, float* rstd, cvb_stream_t stream) {
+  CVB_CHECK(X && mean && rstd && M > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && cvb_aligned16(X), "cvb_ln_stats: bad arguments");
+  const int rows_per_cta = NT / 32;
+  CVB_CUDA(cvb_launch(ln_stats_kernel, (unsigned)((M + rows_per_cta - 1) / rows_per_cta), NT, 0, static_cast<cudaStream_t>(stream),
+                      static_cast<const bf16*>(X), ldx, M, C, eps, mean, rstd));
   CVB_LAUNCH_CHECK();
   return 0;
 }

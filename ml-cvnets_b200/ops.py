@@ -289,6 +289,38 @@ def linattn_bwd(QKV: Tensor, DO: Tensor, S: Tensor, CTX: Tensor, B: int, H: int,
     return DQKV
 
 
+def mha_fwd(QKV: Tensor, B: int, S: int, H: int, head_dim: int, scale: float, attn_mask: Optional[Tensor] = None,
+            key_padding_mask: Optional[Tensor] = None):
+    """softmax(scale * Q K^T + masks) V for the packed projection QKV [B*S, 3*H*head_dim]; returns O [B*S, H*head_dim] and LSE [B,H,S]."""
+    lib = _lib()
+    O = torch.empty((B * S, H * head_dim), device=QKV.device, dtype=torch.bfloat16)
+    LSE = torch.empty((B, H, S), device=QKV.device, dtype=torch.float32)
+    L.check(lib.cvb_mha_fwd(QKV.data_ptr(), QKV.stride(0), B, S, H, head_dim, float(scale), _p(attn_mask), _p(key_padding_mask), O.data_ptr(),
+                            O.stride(0), LSE.data_ptr(), _stream()), "cvb_mha_fwd")
+    _count()
+    return O, LSE
+
+
+def mha_bwd(QKV: Tensor, O: Tensor, DO: Tensor, LSE: Tensor, B: int, S: int, H: int, head_dim: int, scale: float,
+            attn_mask: Optional[Tensor] = None, key_padding_mask: Optional[Tensor] = None) -> Tensor:
+    lib = _lib()
+    DQKV = torch.empty_like(QKV)
+    L.check(lib.cvb_mha_bwd(QKV.data_ptr(), QKV.stride(0), O.data_ptr(), DO.data_ptr(), O.stride(0), LSE.data_ptr(), B, S, H, head_dim, float(scale),
+                            _p(attn_mask), _p(key_padding_mask), DQKV.data_ptr(), DQKV.stride(0), _stream()), "cvb_mha_bwd")
+    _count()
+    return DQKV
+
+
+def ln_stats(X: Tensor, eps: float) -> Tensor:
+    """per-token LayerNorm statistics of a bf16 [M, C] matrix -> fp32 [2, M] (mean, rstd)."""
+    lib = _lib()
+    M, C = X.shape
+    out = torch.empty((2, M), device=X.device, dtype=torch.float32)
+    L.check(lib.cvb_ln_stats(X.data_ptr(), X.stride(0), M, C, float(eps), out[0].data_ptr(), out[1].data_ptr(), _stream()), "cvb_ln_stats")
+    _count()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------------- misc
 def global_pool_fwd(X: Tensor, B: int, HW: int) -> Tensor:
     lib = _lib()

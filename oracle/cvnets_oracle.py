@@ -138,6 +138,58 @@ def linear_attn_ffn(P: Params, pre: str, x: Tensor) -> Tensor:
     return x + f
 
 
+def layer_norm(P: Params, pre: str, x: Tensor, eps: float = 1e-5) -> Tensor:
+    """LayerNorm, channel-last branch (cvnets/layers/normalization/layer_norm.py:14-72, ``super().forward``): nn.LayerNorm over
+    the last dimension.  (The reference switches to a channel-first formula when ``x.shape[1] == C`` and ``x.ndim > 2``,
+    ``:52-65`` -- i.e. for [N, S, C] inputs with S == C; the hot-path configs never have S == C and the product rejects it.)"""
+    return F.layer_norm(x, (x.shape[-1],), P[pre + ".weight"], P[pre + ".bias"], eps)
+
+
+def multi_head_attention(P: Params, pre: str, x: Tensor, num_heads: int, key_padding_mask: Optional[Tensor] = None,
+                         attn_mask: Optional[Tensor] = None) -> Tensor:
+    """MultiHeadAttention.forward_default, self-attention branch (cvnets/layers/multi_head_attention.py:135-239), dropout p=0.
+
+    x: [N, S, C].  qkv = Linear(C -> 3C) reshaped [N,S,3,h,c] -> [N,h,3,S,c] (:148-153); q *= c^-0.5 (:187); attn = q k^T (:194);
+    + attn_mask[N,1,S,T] (:197-208); masked_fill(key_padding_mask, -inf) (:210-224); softmax in fp32 then cast back (:226-228);
+    attn v (:233); merge heads (:236); out_proj (:237).
+    """
+    b, s_len, c = x.shape
+    hd = c // num_heads
+    qkv = F.linear(x, P[pre + ".qkv_proj.weight"], P[pre + ".qkv_proj.bias"]).reshape(b, s_len, 3, num_heads, hd)
+    qkv = qkv.transpose(1, 3).contiguous()
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    q = q * (hd ** -0.5)
+    attn = torch.matmul(q, k.transpose(-1, -2))
+    if attn_mask is not None:
+        attn = attn + attn_mask.unsqueeze(1)
+    if key_padding_mask is not None:
+        attn = attn.masked_fill(key_padding_mask.unsqueeze(1).unsqueeze(2).to(torch.bool), float("-inf"))
+    attn = F.softmax(attn.float(), dim=-1).to(attn.dtype)
+    out = torch.matmul(attn, v).transpose(1, 2).reshape(b, s_len, -1)
+    return F.linear(out, P[pre + ".out_proj.weight"], P[pre + ".out_proj.bias"])
+
+
+def activation(x: Tensor, name: str) -> Tensor:
+    """build_activation_layer(opts) for the two activations of the transformer recipes: swish (MobileViT) and gelu (ViT / CLIP)."""
+    if name == "swish":
+        return F.silu(x)
+    if name == "gelu":
+        return F.gelu(x)
+    raise NotImplementedError(name)
+
+
+def transformer_encoder(P: Params, pre: str, x: Tensor, num_heads: int, act: str = "swish", eps: float = 1e-5,
+                        key_padding_mask: Optional[Tensor] = None, attn_mask: Optional[Tensor] = None) -> Tensor:
+    """TransformerEncoder.forward (cvnets/modules/transformer.py:129-156), pre-norm, dropout / stochastic depth p=0:
+    x = x + MHA(LN(x));  x = x + Linear(act(Linear(LN(x)))).  Child indices pre_norm_mha.{0,1}, pre_norm_ffn.{0,1,4} (:77-95)."""
+    a = layer_norm(P, pre + ".pre_norm_mha.0", x, eps)
+    x = x + multi_head_attention(P, pre + ".pre_norm_mha.1", a, num_heads, key_padding_mask, attn_mask)
+    f = layer_norm(P, pre + ".pre_norm_ffn.0", x, eps)
+    f = activation(F.linear(f, P[pre + ".pre_norm_ffn.1.weight"], P[pre + ".pre_norm_ffn.1.bias"]), act)
+    f = F.linear(f, P[pre + ".pre_norm_ffn.4.weight"], P[pre + ".pre_norm_ffn.4.bias"])
+    return x + f
+
+
 # --------------------------------------------------------------------------------------------
 # modules
 # --------------------------------------------------------------------------------------------
@@ -251,6 +303,24 @@ def inverted_residual_shapes(P: Dict, pre: str, cin: int, cout: int, expand_rati
 def _gn(P: Dict, pre: str, c: int):
     P[pre + ".weight"] = torch.empty(c)
     P[pre + ".bias"] = torch.empty(c)
+
+
+def _linear(P: Dict, pre: str, cin: int, cout: int):
+    P[pre + ".weight"] = torch.empty(cout, cin)
+    P[pre + ".bias"] = torch.empty(cout)
+
+
+def multi_head_attention_shapes(P: Dict, pre: str, c: int):
+    _linear(P, pre + ".qkv_proj", c, 3 * c)
+    _linear(P, pre + ".out_proj", c, c)
+
+
+def transformer_encoder_shapes(P: Dict, pre: str, c: int, ffn: int):
+    _gn(P, pre + ".pre_norm_mha.0", c)
+    multi_head_attention_shapes(P, pre + ".pre_norm_mha.1", c)
+    _gn(P, pre + ".pre_norm_ffn.0", c)
+    _linear(P, pre + ".pre_norm_ffn.1", c, ffn)
+    _linear(P, pre + ".pre_norm_ffn.4", ffn, c)
 
 
 def linear_attn_ffn_shapes(P: Dict, pre: str, d: int, ffn: int):

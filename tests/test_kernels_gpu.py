@@ -463,3 +463,49 @@ def test_pool_colsum_im2col_prep(ops):
     assert torch.equal(back[1:], g[: 2 * d]) and torch.equal(back[0], g[2 * d])
     gt = rnd(9, 24, seed=108)
     assert torch.equal(ops.unprep_grad(gt, 24, 9, 24, 2), gt.t())
+
+
+# ------------------------------------------------------------------------------------------------- multi-head attention
+def _mha_ref(qkv, B, S, H, c, scale, amask, kpm):
+    """fp32 restatement of cvnets/layers/multi_head_attention.py:148-235 on the packed projection."""
+    x = qkv.float().view(B, S, 3, H, c).permute(2, 0, 3, 1, 4)  # [3, B, H, S, c]
+    q, k, v = x[0] * scale, x[1], x[2]
+    att = q @ k.transpose(-1, -2)
+    if amask is not None:
+        att = att + amask[:, None]
+    if kpm is not None:
+        att = att.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    att = torch.softmax(att, dim=-1)
+    return (att @ v).transpose(1, 2).reshape(B * S, H * c)
+
+
+@pytest.mark.parametrize("B,S,H,c", [(2, 197, 12, 64), (3, 77, 8, 64), (2, 256, 4, 16), (2, 64, 4, 32), (5, 16, 2, 16), (1, 130, 3, 32)])
+@pytest.mark.parametrize("mask", ["none", "causal", "padding"])
+def test_mha_fwd_bwd(ops, B, S, H, c, mask):
+    C = H * c
+    qkv = bf(rnd(B * S, 3 * C, seed=71))
+    dO = bf(rnd(B * S, C, seed=72))
+    amask = kpm = None
+    if mask == "causal":
+        amask = torch.full((S, S), float("-inf"), device="cuda").triu(1)[None].repeat(B, 1, 1).contiguous()
+    if mask == "padding":
+        kpm = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+        kpm[:, S - max(1, S // 5):] = 1
+    scale = c ** -0.5
+    O, LSE = ops.mha_fwd(qkv, B, S, H, c, scale, attn_mask=amask, key_padding_mask=kpm)
+    x = qkv.float().requires_grad_(True)
+    ref = _mha_ref(x, B, S, H, c, scale, amask, kpm)
+    close(O, ref.detach(), what="mha fwd")
+    ref.backward(dO.float())
+    DQKV = ops.mha_bwd(qkv, O, dO, LSE, B, S, H, c, scale, attn_mask=amask, key_padding_mask=kpm)
+    close(DQKV, x.grad, rtol=3e-2, atol=2e-2 * float(x.grad.abs().max()) + 1e-6, what="mha bwd")
+
+
+@pytest.mark.parametrize("M,C", [(1000, 768), (333, 64), (50, 1000)])
+def test_ln_stats(ops, M, C):
+    X = bf(rnd(M, C, seed=81) * 2 + 0.5)
+    st = ops.ln_stats(X, 1e-5)
+    xf = X.float()
+    assert float((st[0] - xf.mean(1)).abs().max()) < 1e-4
+    rstd = 1.0 / torch.sqrt(xf.var(1, unbiased=False) + 1e-5)
+    assert float(((st[1] - rstd) / rstd).abs().max()) < 1e-3

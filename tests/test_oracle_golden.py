@@ -130,3 +130,39 @@ def test_mobilevit_v2_model(golden_dir, width):
         torch.testing.assert_close(P[k].grad, g, atol=1e-4 * float(g.abs().max()) + 1e-7, rtol=2e-3, msg=lambda m, k=k: f"{k}: {m}")
     for k, b in fx["buffers_after"].items():
         torch.testing.assert_close(P[k].detach(), b, atol=1e-5, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- transformer rows (a10-a12)
+@pytest.fixture(scope="module")
+def tfx(golden_dir):
+    return torch.load(os.path.join(golden_dir, "transformer_fp32.pt"), weights_only=False)
+
+
+def _check_nobuf(P, fx, x, y, prefix="m."):
+    torch.testing.assert_close(y, fx["y"], **TOL)
+    torch.testing.assert_close(x.grad, fx["gx"], **TOL)
+    for k, g in fx["grads"].items():
+        torch.testing.assert_close(P[prefix + k].grad, g, atol=5e-5, rtol=5e-4, msg=lambda m, k=k: f"{k}: {m}")
+
+
+@pytest.mark.parametrize("name", ["mha", "mha_hd32", "mha_causal", "mha_padding"])
+def test_multi_head_attention(tfx, name):
+    fx = tfx[name]
+    c = fx["cfg"]
+    P = {}
+    O.multi_head_attention_shapes(P, "m", c["c"])
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.multi_head_attention(P, "m", x, c["heads"], key_padding_mask=fx.get("key_padding_mask"),
+                                                     attn_mask=fx.get("attn_mask")), P, fx)
+    _check_nobuf(P, fx, x, y)
+
+
+@pytest.mark.parametrize("name", ["enc_swish", "enc_gelu"])
+def test_transformer_encoder(tfx, name):
+    fx = tfx[name]
+    c = fx["cfg"]
+    P = {}
+    O.transformer_encoder_shapes(P, "m", c["c"], c["ffn"])
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.transformer_encoder(P, "m", x, c["heads"], act=c["act"], eps=c["eps"]), P, fx)
+    _check_nobuf(P, fx, x, y)
