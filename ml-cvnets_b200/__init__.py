@@ -1,13 +1,13 @@
 """ml-cvnets_b200: the apple/ml-cvnets vision-backbone hot path (MobileViTv2: InvertedResidual, MobileViTBlockv2,
-LinearSelfAttention, LinearAttnFFN, conv+BN+SiLU) as hand-written sm_100a CUDA kernels behind a C ABI
+LinearSelfAttention, LinearAttnFFN, conv+BN+SiLU; plus the ViT-style MultiHeadAttention / TransformerEncoder / LayerNorm) as hand-written sm_100a CUDA kernels behind a C ABI
 (include/cvnets_b200.h) with drop-in ``nn.Module``s on top.  Import name: ``ml_cvnets_b200`` (alias package at the repo root).
 """
 from . import _lib  # noqa: F401
-from .layers import (BatchNorm2d, ConvLayer2d, Dropout, GlobalPool, Identity, LayerNorm2D_NCHW, LinearLayer,  # noqa: F401
-                     LinearSelfAttention, Swish)
+from .layers import (GELU, BatchNorm2d, ConvLayer2d, Dropout, GlobalPool, Identity, LayerNorm, LayerNorm2D_NCHW,  # noqa: F401
+                     LinearLayer, LinearSelfAttention, MultiHeadAttention, Swish)
 from .models import MobileViTv2, default_opts, get_configuration  # noqa: F401
-from .modules import InvertedResidual, LinearAttnFFN, MobileViTBlockv2  # noqa: F401
+from .modules import InvertedResidual, LinearAttnFFN, MobileViTBlockv2, TransformerEncoder  # noqa: F401
 
 __all__ = ["MobileViTv2", "default_opts", "get_configuration", "InvertedResidual", "LinearAttnFFN", "MobileViTBlockv2",
            "ConvLayer2d", "LinearSelfAttention", "BatchNorm2d", "LayerNorm2D_NCHW", "GlobalPool", "LinearLayer", "Swish",
-           "Dropout", "Identity"]
+           "Dropout", "Identity", "TransformerEncoder", "MultiHeadAttention", "LayerNorm", "GELU"]

@@ -339,6 +339,125 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const bf16* __restrict__ X
 }
 
 // GroupNorm backward phase 2 (+ residual-stream gradient, + column sums of the result)
+// LayerNorm backward in ONE pass (a "sample" is a single token row, so both phases of the GroupNorm backward fit in a warp):
+//   g = v * gamma;  dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)) + dres;   dbeta += v;  dgamma += v * xhat;  col_sum += dx
+// (autograd of nn.LayerNorm, cvnets/layers/normalization/layer_norm.py:14-72).  One warp per row, rows grid-strided; the per-channel
+// sums live in registers (lane owns chunks lane, lane+32, ...: C <= 1024) and are flushed once per CTA.
+constexpr int LNB_MAXCH = 4;
+__global__ void __launch_bounds__(NT) ln_bwd_kernel(const bf16* __restrict__ V, const bf16* __restrict__ X, const float* __restrict__ mean,
+                                                    const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ DRES,
+                                                    bf16* __restrict__ DX, int64_t M, int C, double* dgamma, double* dbeta, double* col_sum) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sred[];  // [3][C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 3 * C; i += NT) sred[i] = 0.f;
+  __syncthreads();
+  const int nch = C / 8;
+  float gm[LNB_MAXCH][8], sb[LNB_MAXCH][8], sg[LNB_MAXCH][8], sx[LNB_MAXCH][8];
+#pragma unroll
+  for (int q = 0; q < LNB_MAXCH; ++q) {
+    const int ch = lane + 32 * q;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gm[q][e] = (ch < nch) ? __ldg(gamma + ch * 8 + e) : 0.f;
+      sb[q][e] = 0.f; sg[q][e] = 0.f; sx[q][e] = 0.f;
+    }
+  }
+  const float invC = 1.0f / (float)C;
+  for (int64_t row = (int64_t)blockIdx.x * (NT / 32) + warp; row < M; row += (int64_t)gridDim.x * (NT / 32)) {
+    const float mu = mean[row], rs = rstd[row];
+    float v[LNB_MAXCH][8], xh[LNB_MAXCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < LNB_MAXCH; ++q) {
+      const int ch = lane + 32 * q;
+      if (ch < nch) {
+        unpack8(ldg16_stream(V + row * C + ch * 8), v[q]);
+        unpack8(ldg16_stream(X + row * C + ch * 8), xh[q]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[q][e] = (xh[q][e] - mu) * rs;
+          const float g = v[q][e] * gm[q][e];
+          s1 += g;
+          s2 = fmaf(g, xh[q][e], s2);
+          sb[q][e] += v[q][e];
+          sg[q][e] = fmaf(v[q][e], xh[q][e], sg[q][e]);
+        }
+      }
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int q = 0; q < LNB_MAXCH; ++q) {
+      const int ch = lane + 32 * q;
+      if (ch < nch) {
+        float d[8];
+        if (DRES) unpack8(ldg16_stream(DRES + row * C + ch * 8), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float o = rs * (v[q][e] * gm[q][e] - s1 - xh[q][e] * s2);
+          if (DRES) o += d[e];
+          d[e] = o;
+          sx[q][e] += o;
+        }
+        stg16(DX + row * C + ch * 8, pack8(d));
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < LNB_MAXCH; ++q) {
+    const int ch = lane + 32 * q;
+    if (ch < nch) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&sred[ch * 8 + e], sb[q][e]);
+        atomicAdd(&sred[C + ch * 8 + e], sg[q][e]);
+        atomicAdd(&sred[2 * C + ch * 8 + e], sx[q][e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += NT) {
+    atomicAdd(dbeta + i, (double)sred[i]);
+    atomicAdd(dgamma + i, (double)sred[C + i]);
+    if (col_sum) atomicAdd(col_sum + i, (double)sred[2 * C + i]);
+  }
+}
+
+// stand-alone activation passes for the transformer FFN when the activation is not SiLU (GELU of the ViT / CLIP recipes; the
+// SiLU FFN keeps the activation fused into the GEMM load / epilogue modes).  kind: 0 = SiLU, 1 = GELU (erf form, nn.GELU default)
+__device__ __forceinline__ float act_fwd_f(float x, int kind) { return kind == 0 ? silu_f(x) : 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float act_grad_f(float x, int kind) {
+  if (kind == 0) return silu_grad_f(x);
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__global__ void __launch_bounds__(NT) act_fwd_kernel(const bf16* __restrict__ X, bf16* __restrict__ Y, int64_t nvec, int kind) {
+  pdl_wait();
+  pdl_trigger();
+  for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
+    float f[8];
+    unpack8(ldg16_stream(X + v * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = act_fwd_f(f[j], kind);
+    stg16(Y + v * 8, pack8(f));
+  }
+}
+__global__ void __launch_bounds__(NT) act_bwd_kernel(const bf16* __restrict__ DY, const bf16* __restrict__ X, bf16* __restrict__ DX, int64_t nvec,
+                                                     int kind) {
+  pdl_wait();
+  pdl_trigger();
+  for (int64_t v = (int64_t)blockIdx.x * NT + threadIdx.x; v < nvec; v += (int64_t)gridDim.x * NT) {
+    float g[8], x[8];
+    unpack8(ldg16_stream(DY + v * 8), g);
+    unpack8(ldg16_stream(X + v * 8), x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= act_grad_f(x[j], kind);
+    stg16(DX + v * 8, pack8(g));
+  }
+}
+
 // LayerNorm statistics: one warp per token row
 __global__ void __launch_bounds__(NT) ln_stats_kernel(const bf16* __restrict__ X, int ldx, int64_t M, int C, float eps, float* __restrict__ mean,
                                                       float* __restrict__ rstd) {
@@ -621,6 +740,36 @@ extern "C" int cvb_gn_stats(const void* X, int ldx, int B, int rows_per_sample, 
   if (chunks < 1) chunks = 1;
   CVB_CUDA(cvb_launch(gn_stats_kernel, B * chunks, NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X), ldx, rows_per_sample, C, chunks, samp_sum,
                                                                            samp_sq));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_ln_bwd(const void* V, const void* X, const float* mean, const float* rstd, const float* gamma, const void* DRES, void* DX,
+                          int64_t M, int C, double* dgamma, double* dbeta, double* col_sum, cvb_stream_t stream) {
+  CVB_CHECK(V && X && mean && rstd && gamma && DX && dgamma && dbeta && M > 0 && C > 0 && C % 8 == 0, "cvb_ln_bwd: bad arguments");
+  CVB_CHECK(C <= 256 * LNB_MAXCH, "cvb_ln_bwd: C = %d > %d is not supported", C, 256 * LNB_MAXCH);
+  CVB_CHECK(cvb_aligned16(V) && cvb_aligned16(X) && cvb_aligned16(DX) && (!DRES || cvb_aligned16(DRES)), "cvb_ln_bwd: misaligned operand");
+  int64_t ctas = (M + NT / 32 - 1) / (NT / 32);
+  const int64_t cap = 4 * (int64_t)cvb_num_sms();
+  if (ctas > cap) ctas = cap;
+  CVB_CUDA(cvb_launch(ln_bwd_kernel, (unsigned)ctas, NT, (size_t)3 * C * sizeof(float), static_cast<cudaStream_t>(stream), static_cast<const bf16*>(V),
+                      static_cast<const bf16*>(X), mean, rstd, gamma, static_cast<const bf16*>(DRES), static_cast<bf16*>(DX), M, C, dgamma, dbeta,
+                      col_sum));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_act_fwd(const void* X, void* Y, int64_t n, int kind, cvb_stream_t stream) {
+  CVB_CHECK(X && Y && n > 0 && n % 8 == 0 && cvb_aligned16(X) && cvb_aligned16(Y) && (kind == 0 || kind == 1), "cvb_act_fwd: bad arguments");
+  CVB_CUDA(cvb_launch(act_fwd_kernel, grid_for(n / 8), NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X), static_cast<bf16*>(Y), n / 8, kind));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int cvb_act_bwd(const void* DY, const void* X, void* DX, int64_t n, int kind, cvb_stream_t stream) {
+  CVB_CHECK(DY && X && DX && n > 0 && n % 8 == 0 && cvb_aligned16(DY) && cvb_aligned16(X) && cvb_aligned16(DX) && (kind == 0 || kind == 1),
+            "cvb_act_bwd: bad arguments");
+  CVB_CUDA(cvb_launch(act_bwd_kernel, grid_for(n / 8), NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(DY), static_cast<const bf16*>(X),
+                      static_cast<bf16*>(DX), n / 8, kind));
   CVB_LAUNCH_CHECK();
   return 0;
 }

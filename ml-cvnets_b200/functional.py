@@ -352,3 +352,122 @@ class PoolLinearFn(torch.autograd.Function):
         dp = ops.pw_gemm(g, cfg.prep.get(cfg.i_wt), C, K=npad)
         dx = ops.global_pool_bwd(dp, B, H * W)
         return to_4d(dx, B, H, W), None, dW[:ncls], db[:ncls]
+
+
+# ==================================================================================================================
+# Transformer rows: MultiHeadAttention (cvnets/layers/multi_head_attention.py:135-239) and the pre-norm
+# TransformerEncoder (cvnets/modules/transformer.py:129-156) on token matrices [M = N*S, C] (bf16).  LayerNorm is the GroupNorm
+# load mode of the consuming GEMM with rows_per_sample = 1 (per-token statistics); its backward is the one-pass
+# cvb_ln_bwd kernel behind a plain dX GEMM.  dropout / stochastic depth p = 0 (the module raises otherwise).
+# ==================================================================================================================
+def _masks(cfg_masks, N, S, device):
+    """(attn_mask fp32 [N,S,S] or None, key_padding_mask uint8 [N,S] or None) in the layout cvb_mha_* reads."""
+    amask, kpm = cfg_masks
+    if amask is not None:
+        if list(amask.shape) != [N, S, S]:
+            raise ValueError(f"Shape of attention mask should be [{N}, {S}, {S}]. Got: {list(amask.shape)}")  # multi_head_attention.py:199-205
+        amask = amask.to(device=device, dtype=torch.float32).contiguous()
+    if kpm is not None:
+        if kpm.dim() != 2 or list(kpm.shape) != [N, S]:
+            raise ValueError(f"Key_padding_mask should be 2-dimension with shape [{N}, {S}]. Got: {list(kpm.shape)}")  # :213-219
+        kpm = kpm.to(device=device).to(torch.uint8).contiguous()
+    return amask, kpm
+
+
+class MultiHeadAttentionFn(torch.autograd.Function):
+    """Stand-alone self-attention: qkv_proj GEMM (+bias) -> attention core -> out_proj GEMM (+bias)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, wqkv, bqkv, wo, bo):
+        N, S, C = x.shape
+        P = cfg.prep
+        x2 = x.reshape(N * S, C)
+        amask, kpm = _masks(cfg.masks, N, S, x.device)
+        qkv = ops.pw_gemm(x2, P.get(cfg.i_wqkv), 3 * C, bias=bqkv)
+        O, LSE = ops.mha_fwd(qkv, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
+        y = ops.pw_gemm(O, P.get(cfg.i_wo), cfg.out_dim, bias=bo)
+        ctx.cfg, ctx.dims = cfg, (N, S, C)
+        ctx.saved = (x2, qkv, O, LSE, amask, kpm)
+        return y.view(N, S, cfg.out_dim)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        N, S, C = ctx.dims
+        P = cfg.prep
+        x2, qkv, O, LSE, amask, kpm = ctx.saved
+        dy = gout.reshape(N * S, cfg.out_dim).to(BF16).contiguous()
+        dbo = torch.zeros(cfg.out_dim, device=dy.device, dtype=torch.float32)
+        dWo = ops.pw_wgrad(dy, O, cfg.out_dim, C, dbias=dbo)
+        dO = ops.pw_gemm(dy, P.get(cfg.i_wot), C, K=cfg.out_dim)
+        dqkv = ops.mha_bwd(qkv, O, dO, LSE, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
+        dbq = torch.zeros(3 * C, device=dy.device, dtype=torch.float32)
+        dWq = ops.pw_wgrad(dqkv, x2, 3 * C, C, dbias=dbq)
+        dx = ops.pw_gemm(dqkv, P.get(cfg.i_wqkvt), C, K=3 * C)
+        return dx.view(N, S, C), None, dWq, dbq, dWo, dbo
+
+
+class TransformerEncoderFn(torch.autograd.Function):
+    """x = x + MHA(LN1(x));  x = x + W2 act(W1 LN2(x) + b1) + b2   (transformer.py:139-156)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, g1, b1, wqkv, bqkv, wo, bo, g2, b2, w1, bb1, w2, bb2):
+        N, S, C = x.shape
+        M, ffn = N * S, cfg.ffn
+        P = cfg.prep
+        x2 = x.reshape(M, C)
+        amask, kpm = _masks(cfg.masks, N, S, x.device)
+        ln1 = ops.ln_stats(x2, cfg.eps)
+        qkv = ops.pw_gemm(x2, P.get(cfg.i_wqkv), 3 * C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, bias=bqkv)
+        O, LSE = ops.mha_fwd(qkv, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
+        (samp,) = _zeros64(x.device, M)
+        X1 = ops.pw_gemm(O, P.get(cfg.i_wo), C, bias=bo, R=x2, samp_stats=samp, rows_per_sample=1)
+        ln2 = ops.gn_finalize(samp, C, cfg.eps)
+        h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
+        if cfg.act == ops.ACT_SILU:
+            ha = None
+            X2 = ops.pw_gemm(h, P.get(cfg.i_w2), C, a_mode=A_SILU, bias=bb2, R=X1)
+        else:
+            ha = ops.act_fwd(h, cfg.act)
+            X2 = ops.pw_gemm(ha, P.get(cfg.i_w2), C, bias=bb2, R=X1)
+        ctx.cfg, ctx.dims = cfg, (N, S, C)
+        ctx.saved = (x2, ln1, qkv, O, LSE, X1, ln2, h, ha, amask, kpm)
+        ctx.save_for_backward(g1, b1, g2, b2)
+        return X2.view(N, S, C)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        N, S, C = ctx.dims
+        M, ffn = N * S, cfg.ffn
+        P = cfg.prep
+        x2, ln1, qkv, O, LSE, X1, ln2, h, ha, amask, kpm = ctx.saved
+        g1, b1, g2, b2 = ctx.saved_tensors
+        dev = x2.device
+        dY = gout.reshape(M, C).to(BF16).contiguous()
+        ar = _Arena(dev, 4 * C * C + 2 * C * ffn + 8 * C + ffn + 64, 8 * C + 2 * ffn + 64)
+        # ---- FFN
+        db2, db1 = ar.f32(C), ar.f32(ffn)
+        if cfg.act == ops.ACT_SILU:
+            dW2 = ops.pw_wgrad(dY, h, C, ffn, a_mode=A_SILU, dW=ar.f32(C, ffn), dbias=db2)
+            dh = ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C, e_mode=E_SILU_BWD, Y=h)
+        else:
+            dW2 = ops.pw_wgrad(dY, ha, C, ffn, dW=ar.f32(C, ffn), dbias=db2)
+            dh = ops.act_bwd(ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C), h, cfg.act)
+        dW1 = ops.pw_wgrad(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=ar.f32(ffn, C), dbias=db1)
+        csf, bsum1 = ar.f64(2, C), ar.f64(C)
+        vF = ops.pw_gemm(dh, P.get(cfg.i_w1t), C, K=ffn)
+        dX1 = ops.ln_bwd(vF, X1, ln2, g2, csf, DRES=dY, col_sum=bsum1)  # bsum1 = column sums of dX1 = d(out_proj bias)
+        # ---- attention
+        dWo = ops.pw_wgrad(dX1, O, C, C, dW=ar.f32(C, C))
+        dO = ops.pw_gemm(dX1, P.get(cfg.i_wot), C, K=C)
+        dqkv = ops.mha_bwd(qkv, O, dO, LSE, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
+        dbq = ar.f32(3 * C)
+        dWq = ops.pw_wgrad(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=ar.f32(3 * C, C), dbias=dbq)
+        csa = ar.f64(2, C)
+        vA = ops.pw_gemm(dqkv, P.get(cfg.i_wqkvt), C, K=3 * C)
+        dx = ops.ln_bwd(vA, x2, ln1, g1, csa, DRES=dX1)
+        ar.cast()
+        f = ar.as_f32
+        # (x, cfg, g1, b1, wqkv, bqkv, wo, bo, g2, b2, w1, bb1, w2, bb2)
+        return (dx.view(N, S, C), None, f(csa[1]), f(csa[0]), dWq, dbq, dWo, f(bsum1), f(csf[1]), f(csf[0]), dW1, db1, dW2, db2)

@@ -75,7 +75,25 @@ class LayerNorm2D_NCHW(nn.GroupNorm):
         return "{}(num_channels={}, eps={}, affine={})".format(self.__class__.__name__, self.num_channels, self.eps, self.affine)
 
 
-norm_layers_tuple = (nn.BatchNorm2d, nn.GroupNorm)
+class LayerNorm(nn.LayerNorm):
+    """cvnets/layers/normalization/layer_norm.py:14-72 (``layer_norm``): nn.LayerNorm over the last dimension of [N, S, C].
+    Runs fused: per-token statistics (cvb_ln_stats / a producer epilogue) + the normalising load mode of the consuming GEMM."""
+
+    def __init__(self, normalized_shape, eps: Optional[float] = 1e-5, elementwise_affine: Optional[bool] = True, *args, **kwargs):
+        super().__init__(normalized_shape=normalized_shape, eps=eps, elementwise_affine=elementwise_affine)
+
+    def forward(self, x: Tensor) -> Tensor:
+        raise NotImplementedError("LayerNorm runs fused inside TransformerEncoder (no standalone kernel path)")
+
+
+class GELU(nn.GELU):
+    """cvnets/layers/activation/gelu.py."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        super().__init__()
+
+
+norm_layers_tuple = (nn.BatchNorm2d, nn.GroupNorm, nn.LayerNorm)
 
 
 def get_normalization_layer(opts, num_features: int, norm_type: Optional[str] = None, *args, **kwargs) -> nn.Module:
@@ -86,14 +104,18 @@ def get_normalization_layer(opts, num_features: int, norm_type: Optional[str] = 
         return BatchNorm2d(num_features=num_features, momentum=momentum)
     if norm_type in ("layer_norm_2d", "layer_norm_nchw"):
         return LayerNorm2D_NCHW(num_features=num_features)
-    raise NotImplementedError(f"normalization '{norm_type}' is not on the B200 hot path (batch_norm, layer_norm_2d are)")
+    if norm_type == "layer_norm":
+        return LayerNorm(num_features)
+    raise NotImplementedError(f"normalization '{norm_type}' is not on the B200 hot path (batch_norm, layer_norm_2d, layer_norm are)")
 
 
 def build_activation_layer(opts, *args, **kwargs) -> nn.Module:
     name = _opt(opts, "model.activation.name", "swish")
     if name in ("swish", "silu"):
         return Swish()
-    raise NotImplementedError(f"activation '{name}' is not on the B200 hot path (swish is)")
+    if name == "gelu":
+        return GELU()
+    raise NotImplementedError(f"activation '{name}' is not on the B200 hot path (swish and gelu are)")
 
 
 class Conv2d(nn.Conv2d):
@@ -218,3 +240,72 @@ class LinearSelfAttention(BaseLayer):
 
     def __repr__(self):
         return "{}(embed_dim={}, attn_dropout={})".format(self.__class__.__name__, self.embed_dim, self.attn_dropout.p)
+
+
+class MultiHeadAttention(BaseLayer):
+    """cvnets/layers/multi_head_attention.py:18-309.  Same constructor (note: no ``opts``), children ``qkv_proj`` (C -> 3C) and
+    ``out_proj`` (C -> output_dim) as ``LinearLayer``s, same ``forward(x_q, x_kv, key_padding_mask, attn_mask)`` signature.
+    Self-attention only (the cross-attention branch, :159-185, raises); attention dropout must be 0."""
+
+    def __init__(self, embed_dim: int, num_heads: int, attn_dropout: Optional[float] = 0.0, bias: Optional[bool] = True,
+                 output_dim: Optional[int] = None, coreml_compatible: Optional[bool] = False, *args, **kwargs) -> None:
+        if output_dim is None:
+            output_dim = embed_dim
+        super().__init__()
+        if embed_dim % num_heads != 0:
+            raise ValueError("Embedding dim must be divisible by number of heads in {}. Got: embed_dim={} and num_heads={}".format(
+                self.__class__.__name__, embed_dim, num_heads))
+        self.qkv_proj = LinearLayer(in_features=embed_dim, out_features=3 * embed_dim, bias=bias)
+        self.attn_dropout = Dropout(p=attn_dropout)
+        self.out_proj = LinearLayer(in_features=embed_dim, out_features=output_dim, bias=bias)
+        self.head_dim = embed_dim // num_heads
+        self.scaling = self.head_dim ** -0.5
+        self.softmax = nn.Softmax(dim=-1)
+        self.num_heads = num_heads
+        self.embed_dim = embed_dim
+        self.coreml_compatible = coreml_compatible
+        self.use_separate_proj_weight = embed_dim != output_dim
+        self._cfg = None
+
+    def __repr__(self):
+        return "{}(head_dim={}, num_heads={}, attn_dropout={})".format(self.__class__.__name__, self.head_dim, self.num_heads, self.attn_dropout.p)
+
+    def check_supported(self):
+        if self.attn_dropout.p:
+            raise NotImplementedError("attention dropout > 0 is not implemented")
+        if self.head_dim not in (16, 32, 64):
+            raise NotImplementedError(f"head_dim {self.head_dim} is not implemented (16, 32, 64 are)")
+        if self.qkv_proj.bias is None or self.out_proj.bias is None:
+            raise NotImplementedError("bias=False is not implemented")
+
+    def build_cfg(self, prep):
+        """Register the kernel-layout weight copies in ``prep``; returns the index namespace used by the autograd functions."""
+        from types import SimpleNamespace
+        from .ops import PreparedWeights as PW
+        self.check_supported()
+        ix = SimpleNamespace(heads=self.num_heads, head_dim=self.head_dim, scale=self.scaling, out_dim=self.out_proj.out_features)
+        ix.i_wqkv = prep.add(self.qkv_proj.weight, PW.KIND_ROWMAJOR)
+        ix.i_wqkvt = prep.add(self.qkv_proj.weight, PW.KIND_TRANSPOSED)
+        ix.i_wo = prep.add(self.out_proj.weight, PW.KIND_ROWMAJOR)
+        ix.i_wot = prep.add(self.out_proj.weight, PW.KIND_TRANSPOSED)
+        return ix
+
+    def forward(self, x_q: Tensor, x_kv: Optional[Tensor] = None, key_padding_mask: Optional[Tensor] = None,
+                attn_mask: Optional[Tensor] = None, *args, **kwargs) -> Tensor:
+        from . import functional as Fn
+        from .ops import PreparedWeights as PW
+        if x_kv is not None:
+            raise NotImplementedError("cross-attention (x_kv) is not implemented on the B200 path")
+        if not x_q.is_cuda:
+            raise RuntimeError("MultiHeadAttention: ml-cvnets_b200 has no CPU path")
+        if x_q.dim() != 3 or x_q.shape[1] > 256:
+            raise NotImplementedError("MultiHeadAttention expects [N, S, C] with S <= 256")
+        if self._cfg is None:
+            prep = PW()
+            self._cfg = self.build_cfg(prep)
+            self._cfg.prep = prep
+        cfg = self._cfg
+        cfg.masks = (attn_mask, key_padding_mask)
+        cfg.prep.prepare(force=self.training)
+        x = x_q.to(torch.bfloat16).contiguous()
+        return Fn.MultiHeadAttentionFn.apply(x, cfg, self.qkv_proj.weight, self.qkv_proj.bias, self.out_proj.weight, self.out_proj.bias)

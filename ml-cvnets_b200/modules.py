@@ -14,7 +14,8 @@ import torch
 from torch import Tensor, nn
 
 from . import functional as Fn
-from .layers import ConvLayer2d, Dropout, LinearSelfAttention, get_normalization_layer
+from .layers import (ConvLayer2d, Dropout, Identity, LinearLayer, LinearSelfAttention, MultiHeadAttention, build_activation_layer,
+                     get_normalization_layer)
 from .ops import PreparedWeights as PW
 
 
@@ -260,3 +261,77 @@ class MobileViTBlockv2(BaseModule):
             return self.forward_spatial(x)
         else:
             raise NotImplementedError
+
+
+class TransformerEncoder(BaseModule):
+    """cvnets/modules/transformer.py:26-156: pre-norm encoder, ``x = x + MHA(LN(x)); x = x + FFN(LN(x))``.
+
+    Same constructor, child tree (``pre_norm_mha = [norm, MultiHeadAttention, Dropout]``, ``pre_norm_ffn = [norm, LinearLayer,
+    act, Dropout, LinearLayer, Dropout]``) and ``state_dict`` keys as the reference; the forward is one fused autograd function
+    (LayerNorm as a GEMM load mode, attention core in shared memory, residuals in the GEMM epilogues).  Not implemented (raises):
+    ``num_heads == 1`` (SingleHeadAttention), dropout / stochastic depth > 0, cross-attention (``x_prev``), norms other than
+    ``layer_norm``, activations other than swish / gelu."""
+
+    def __init__(self, opts, embed_dim: int, ffn_latent_dim: int, num_heads: Optional[int] = 8, attn_dropout: Optional[float] = 0.0,
+                 dropout: Optional[float] = 0.0, ffn_dropout: Optional[float] = 0.0, transformer_norm_layer: Optional[str] = "layer_norm",
+                 stochastic_dropout: Optional[float] = 0.0, *args, **kwargs) -> None:
+        super().__init__()
+        if num_heads <= 1:
+            raise NotImplementedError("SingleHeadAttention (num_heads == 1) is not on the B200 path")
+        attn_unit = MultiHeadAttention(embed_dim, num_heads, attn_dropout=attn_dropout, bias=True)
+        self.pre_norm_mha = nn.Sequential(get_normalization_layer(opts=opts, norm_type=transformer_norm_layer, num_features=embed_dim),
+                                          attn_unit, Dropout(p=dropout))
+        act_name = build_activation_layer(opts, num_parameters=1)
+        self.pre_norm_ffn = nn.Sequential(get_normalization_layer(opts=opts, norm_type=transformer_norm_layer, num_features=embed_dim),
+                                          LinearLayer(in_features=embed_dim, out_features=ffn_latent_dim, bias=True), act_name,
+                                          Dropout(p=ffn_dropout),
+                                          LinearLayer(in_features=ffn_latent_dim, out_features=embed_dim, bias=True), Dropout(p=dropout))
+        self.drop_path = Identity()
+        if stochastic_dropout > 0.0:
+            raise NotImplementedError("stochastic depth > 0 is not implemented")
+        self.embed_dim, self.ffn_dim, self.ffn_dropout = embed_dim, ffn_latent_dim, ffn_dropout
+        self.stochastic_dropout, self.std_dropout = stochastic_dropout, dropout
+        self.attn_fn_name, self.act_fn_name, self.norm_type = attn_unit.__class__.__name__, act_name.__class__.__name__, transformer_norm_layer
+        self._cfg = None
+
+    def __repr__(self) -> str:
+        return "{}(embed_dim={}, ffn_dim={}, dropout={}, ffn_dropout={}, stochastic_dropout={}, attn_fn={}, act_fn={}, norm_fn={})".format(
+            self.__class__.__name__, self.embed_dim, self.ffn_dim, self.std_dropout, self.ffn_dropout, self.stochastic_dropout,
+            self.attn_fn_name, self.act_fn_name, self.norm_type)
+
+    def _build_cfg(self):
+        from . import ops
+        if self.norm_type != "layer_norm":
+            raise NotImplementedError("transformer_norm_layer must be layer_norm")
+        if self.std_dropout or self.ffn_dropout:
+            raise NotImplementedError("dropout > 0 is not implemented")
+        if self.embed_dim % 8 or self.ffn_dim % 8:
+            raise NotImplementedError("embed_dim / ffn_latent_dim must be multiples of 8")
+        prep = PW()
+        cfg = self.pre_norm_mha[1].build_cfg(prep)
+        cfg.prep, cfg.ffn, cfg.eps = prep, self.ffn_dim, float(self.pre_norm_mha[0].eps)
+        cfg.act = ops.ACT_SILU if self.act_fn_name == "Swish" else ops.ACT_GELU
+        cfg.i_w1 = prep.add(self.pre_norm_ffn[1].weight, PW.KIND_ROWMAJOR)
+        cfg.i_w1t = prep.add(self.pre_norm_ffn[1].weight, PW.KIND_TRANSPOSED)
+        cfg.i_w2 = prep.add(self.pre_norm_ffn[4].weight, PW.KIND_ROWMAJOR)
+        cfg.i_w2t = prep.add(self.pre_norm_ffn[4].weight, PW.KIND_TRANSPOSED)
+        self._cfg = cfg
+
+    def forward(self, x: Tensor, x_prev: Optional[Tensor] = None, key_padding_mask: Optional[Tensor] = None,
+                attn_mask: Optional[Tensor] = None, *args, **kwargs) -> Tensor:
+        _require_cuda(x, "TransformerEncoder")
+        if x_prev is not None:
+            raise NotImplementedError("cross-attention (x_prev) is not implemented on the B200 path")
+        if x.dim() != 3 or x.shape[1] > 256:
+            raise NotImplementedError("TransformerEncoder expects [N, S, C] with S <= 256")
+        if x.shape[1] == x.shape[2]:
+            raise NotImplementedError("S == C: the reference's LayerNorm would take its channel-first branch (layer_norm.py:52-65)")
+        if self._cfg is None:
+            self._build_cfg()
+        cfg = self._cfg
+        cfg.masks = (attn_mask, key_padding_mask)
+        cfg.prep.prepare(force=self.training)
+        n1, mha, n2 = self.pre_norm_mha[0], self.pre_norm_mha[1], self.pre_norm_ffn[0]
+        l1, l2 = self.pre_norm_ffn[1], self.pre_norm_ffn[4]
+        return Fn.TransformerEncoderFn.apply(x.to(torch.bfloat16).contiguous(), cfg, n1.weight, n1.bias, mha.qkv_proj.weight, mha.qkv_proj.bias,
+                                             mha.out_proj.weight, mha.out_proj.bias, n2.weight, n2.bias, l1.weight, l1.bias, l2.weight, l2.bias)

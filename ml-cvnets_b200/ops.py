@@ -311,6 +311,34 @@ def mha_bwd(QKV: Tensor, O: Tensor, DO: Tensor, LSE: Tensor, B: int, S: int, H: 
     return DQKV
 
 
+def ln_bwd(V: Tensor, X: Tensor, ln: Tensor, gamma: Tensor, col_stats: Tensor, DRES: Optional[Tensor] = None,
+           col_sum: Optional[Tensor] = None) -> Tensor:
+    """One-pass LayerNorm backward; ``col_stats`` fp64 [2, C] receives (dbeta, dgamma) like the GN_BWD epilogue's col_stats."""
+    M, C = V.shape
+    DX = torch.empty_like(V)
+    L.check(_lib().cvb_ln_bwd(V.data_ptr(), X.data_ptr(), ln[0].data_ptr(), ln[1].data_ptr(), gamma.data_ptr(), _p(DRES), DX.data_ptr(), M, C,
+                              col_stats[1].data_ptr(), col_stats[0].data_ptr(), _p(col_sum), _stream()), "cvb_ln_bwd")
+    _count()
+    return DX
+
+
+ACT_SILU, ACT_GELU = 0, 1
+
+
+def act_fwd(X: Tensor, kind: int) -> Tensor:
+    Y = torch.empty_like(X)
+    L.check(_lib().cvb_act_fwd(X.data_ptr(), Y.data_ptr(), X.numel(), kind, _stream()), "cvb_act_fwd")
+    _count()
+    return Y
+
+
+def act_bwd(DY: Tensor, X: Tensor, kind: int) -> Tensor:
+    DX = torch.empty_like(DY)
+    L.check(_lib().cvb_act_bwd(DY.data_ptr(), X.data_ptr(), DX.data_ptr(), X.numel(), kind, _stream()), "cvb_act_bwd")
+    _count()
+    return DX
+
+
 def ln_stats(X: Tensor, eps: float) -> Tensor:
     """per-token LayerNorm statistics of a bf16 [M, C] matrix -> fp32 [2, M] (mean, rstd)."""
     lib = _lib()

@@ -18,6 +18,7 @@ def rebind_modules() -> None:
     from . import modules as ours
     cm.InvertedResidual = ours.InvertedResidual
     cm.MobileViTBlockv2 = ours.MobileViTBlockv2
+    cm.TransformerEncoder = ours.TransformerEncoder  # used by vit.py:29, mobilevit_block.py (v1), text_encoders/transformer.py:20
 
 
 def register_with_cvnets(name: str = "mobilevit_v2_b200"):

@@ -509,3 +509,27 @@ def test_ln_stats(ops, M, C):
     assert float((st[0] - xf.mean(1)).abs().max()) < 1e-4
     rstd = 1.0 / torch.sqrt(xf.var(1, unbiased=False) + 1e-5)
     assert float(((st[1] - rstd) / rstd).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("M,C", [(500, 768), (77, 64), (1000, 1024)])
+@pytest.mark.parametrize("res", [False, True])
+def test_ln_bwd(ops, M, C, res):
+    X = bf(rnd(M, C, seed=91) * 1.5 + 0.3)
+    V = bf(rnd(M, C, seed=92))
+    R = bf(rnd(M, C, seed=93)) if res else None
+    gamma = 1 + 0.2 * rnd(C, seed=94)
+    beta = 0.1 * rnd(C, seed=95)
+    ln = ops.ln_stats(X, 1e-5)
+    col = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    cs = torch.zeros(C, device="cuda", dtype=torch.float64)
+    DX = ops.ln_bwd(V, X, ln, gamma, col, DRES=R, col_sum=cs)
+    x = X.float().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    y = torch.nn.functional.layer_norm(x, (C,), g, b, 1e-5)
+    y.backward(V.float())
+    ref = x.grad + (R.float() if res else 0)
+    close(DX, ref, what="ln_bwd dx")
+    close_stat(col[0], b.grad, "dbeta", rtol=5e-3)
+    close_stat(col[1], g.grad, "dgamma", rtol=5e-3)
+    close_stat(cs, DX.float().sum(0), "col_sum", rtol=5e-3)

@@ -80,7 +80,7 @@ def run_and_check(module, fx, out_tol=2e-2, gx_tol=4e-2, gp_tol=5e-2, check_gx=T
         small = float(g.norm()) < 1e-3 * float(fx["gy"].norm())  # e.g. d(query bias): softmax grads sum to ~0
         assert (e <= tol and c >= 1 - tol) or small, f"{k}: rel-L2 {e:.4g} (tol {tol:.3g}) cos {c:.5f} |g|={float(g.norm()):.3g}"
     bufs = dict(module.named_buffers())
-    for k, b in fx["buffers"].items():
+    for k, b in fx.get("buffers", {}).items():
         if k.endswith("num_batches_tracked"):
             assert int(bufs[k]) == int(b), k
         else:
@@ -225,3 +225,66 @@ def test_state_dict_roundtrip_and_deepcopy(pkg):
         fresh.load_state_dict(model.state_dict(), strict=True)
         y2 = fresh(x)
     assert rel_l2(y1, y0) <= 1e-3 and rel_l2(y2, y0) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------- transformer rows (a10-a12)
+@pytest.fixture(scope="module")
+def tfx(golden_dir):
+    return torch.load(os.path.join(golden_dir, "transformer_fp32.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["mha", "mha_hd32", "mha_causal", "mha_padding"])
+def test_multi_head_attention(pkg, tfx, name):
+    fx = tfx[name]
+    c = fx["cfg"]
+    shapes = {}
+    O.multi_head_attention_shapes(shapes, "m", c["c"])
+    kw = {}
+    if "attn_mask" in fx:
+        kw["attn_mask"] = fx["attn_mask"].cuda()
+    if "key_padding_mask" in fx:
+        kw["key_padding_mask"] = fx["key_padding_mask"].cuda()
+    auto = autocast_errors(lambda P, x: O.multi_head_attention(P, "m", x, c["heads"], key_padding_mask=kw.get("key_padding_mask"),
+                                                               attn_mask=kw.get("attn_mask")), shapes, fx["seed"], fx)
+    m = load_seeded(pkg.MultiHeadAttention(c["c"], c["heads"]), shapes, fx["seed"])
+    mod = lambda x: m(x, **kw)  # noqa: E731
+    mod.named_parameters, mod.named_buffers = m.named_parameters, m.named_buffers
+    run_and_check(mod, fx, auto=auto)
+
+
+@pytest.mark.parametrize("name", ["enc_swish", "enc_gelu"])
+def test_transformer_encoder(pkg, tfx, name):
+    fx = tfx[name]
+    c = fx["cfg"]
+    shapes = {}
+    O.transformer_encoder_shapes(shapes, "m", c["c"], c["ffn"])
+    auto = autocast_errors(lambda P, x: O.transformer_encoder(P, "m", x, c["heads"], act=c["act"], eps=c["eps"]), shapes, fx["seed"], fx)
+    opts = pkg.default_opts(**{"model.activation.name": c["act"]})
+    m = load_seeded(pkg.TransformerEncoder(opts, c["c"], c["ffn"], num_heads=c["heads"]), shapes, fx["seed"])
+    assert abs(float(m.pre_norm_mha[0].eps) - c["eps"]) < 1e-12
+    run_and_check(m, fx, auto=auto)
+
+
+def test_transformer_encoder_vit_base_shape(pkg):
+    """ViT-B/16 geometry ([N,197,768], 12 heads, f=3072, GELU) against the fp32 oracle on this GPU."""
+    torch.manual_seed(0)
+    C, F_, H, N, S = 768, 3072, 12, 4, 197
+    shapes = {}
+    O.transformer_encoder_shapes(shapes, "m", C, F_)
+    opts = pkg.default_opts(**{"model.activation.name": "gelu"})
+    m = load_seeded(pkg.TransformerEncoder(opts, C, F_, num_heads=H), shapes, 77)
+    P = O.clone_params(O.seeded_fill_(dict(shapes), 77), device="cuda")
+    x = torch.randn(N, S, C, device="cuda").bfloat16().float()
+    gy = torch.randn(N, S, C, device="cuda").bfloat16().float()
+    xo = x.clone().requires_grad_(True)
+    yo = O.transformer_encoder(P, "m", xo, H, act="gelu")
+    yo.backward(gy)
+    xg = x.clone().requires_grad_(True)
+    y = m(xg)
+    y.backward(gy.to(y.dtype))
+    assert rel_l2(y, yo) <= 2e-2
+    assert rel_l2(xg.grad, xo.grad) <= 5e-2
+    named = dict(m.named_parameters())
+    for k, p in named.items():
+        e = rel_l2(p.grad, P["m." + k].grad)
+        assert e <= 6e-2, f"{k}: {e:.4g}"
