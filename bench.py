@@ -394,10 +394,19 @@ def run_ours(args, rank, world, local_rank):
         # region (same process, same tensors; kernels and shapes identical to the ones baked into the graph)
         timer.install()
         timer.enabled = True
+        # eager launches are CPU-bound here; a GPU-side spin first lets the host queue the whole step so that the event pairs
+        # bracket back-to-back kernel execution only (no launch gaps inside the measured intervals).  The spin is sized from the
+        # measured host enqueue time of one eager step on THIS box (slow host cores otherwise leak gaps into the numbers).
+        timer.enabled = False
+        torch.cuda.synchronize(dev)
+        t_h = time.perf_counter()
+        step(x_dev, y_dev)
+        host_s = time.perf_counter() - t_h
+        torch.cuda.synchronize(dev)
+        spin_s = min(2.0, 2.0 * host_s + 0.05)
+        timer.enabled = True
         for _ in range(3):
-            # eager launches are CPU-bound here; a GPU-side spin first lets the host queue the whole step so that the event
-            # pairs bracket back-to-back kernel execution only (no launch gaps inside the measured intervals)
-            torch.cuda._sleep(int(0.12 * 1.9e9))
+            torch.cuda._sleep(int(spin_s * 2.0e9))
             step(x_dev, y_dev)
             torch.cuda.synchronize(dev)
         timer.enabled = False
