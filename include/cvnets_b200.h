@@ -31,7 +31,7 @@ typedef void* cvb_stream_t; /* cudaStream_t */
 #define CVB_API
 #endif
 
-#define CVB_ABI_VERSION 4
+#define CVB_ABI_VERSION 5
 
 /* operand "load modes": the normalisation / activation of the PRODUCER layer is applied while the CONSUMER loads it
  * (training-mode BatchNorm cannot be fused into its own conv: SURVEY.md section 7 "hard parts"). */
@@ -83,6 +83,9 @@ typedef struct {
   void* C; int ldc; int c_fp32; /* output bf16 (or fp32 if c_fp32) [M, ldc] */
   double* col_sum; double* col_sq;   /* fp64 [N] accumulators or NULL (BatchNorm statistics of the stored output) */
   double* samp_sum; double* samp_sq; /* fp64 [M/rows_per_sample] or NULL (GroupNorm statistics of the stored output) */
+  double* gn_ws;            /* CVB_E_GN_BWD only, optional: ZEROED fp64 workspace [2][M/rows_per_sample][N].  When given (and
+                               rows_per_sample % 128 == 0) the epilogue runs on the tcgen05 kernel: it accumulates the per-(sample, channel)
+                               sums of v and v*x there and a finalize kernel derives col_sum/col_sq/samp_sum/samp_sq from them. */
 } cvb_gemm_args;
 CVB_API int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream);
 /* Two kernels implement cvb_pw_gemm: a warp-specialised tcgen05/TMEM/TMA kernel (prologue-free layers) and an mma.sync kernel

@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcvnets_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # load modes / epilogue modes (mirror include/cvnets_b200.h)
 A_RAW, A_AFF, A_AFF_SILU, A_SILU, A_GN, A_BNB = 0, 1, 2, 3, 4, 5
@@ -37,6 +37,7 @@ class GemmArgs(Structure):
         ("C", c_void_p), ("ldc", c_int), ("c_fp32", c_int),
         ("col_sum", c_void_p), ("col_sq", c_void_p),
         ("samp_sum", c_void_p), ("samp_sq", c_void_p),
+        ("gn_ws", c_void_p),
     ]
 
 

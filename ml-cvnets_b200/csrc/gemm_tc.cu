@@ -32,7 +32,7 @@ constexpr int TC_XF_THREADS = 128;          // transform warps (only launched fo
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_TMEM_COLS = 256;             // 2 accumulators x 128 fp32 columns
 
-enum { TEPI_STORE = 0, TEPI_STORE_R = 1, TEPI_SILU_BWD = 2 };
+enum { TEPI_STORE = 0, TEPI_STORE_R = 1, TEPI_SILU_BWD = 2, TEPI_GN_BWD = 3 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
   // K-major operand, 64-byte swizzle: rows of 64 B, 8-row groups 512 B apart (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp)
@@ -249,12 +249,12 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
     const int ch = n0 + ch_local;
     const bool ch_ok = ch < p.N;
     const float bias = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
-    const float ep0 = (EPI == TEPI_SILU_BWD && ch_ok && p.e_p0) ? __ldg(p.e_p0 + ch) : 1.f;
+    const float ep0 = ((EPI == TEPI_SILU_BWD || EPI == TEPI_GN_BWD) && ch_ok && p.e_p0) ? __ldg(p.e_p0 + ch) : 1.f;
     const float ep1 = (EPI == TEPI_SILU_BWD && ch_ok && p.e_p1) ? __ldg(p.e_p1 + ch) : 0.f;
     constexpr bool has_aux = (EPI != TEPI_STORE);
     const bf16* __restrict__ AUX = static_cast<const bf16*>(EPI == TEPI_STORE_R ? p.R : p.Y);
     const int ldaux = EPI == TEPI_STORE_R ? p.ldr : p.ldy;
-    const bool want_samp = p.samp_sum != nullptr;
+    const bool want_samp = (p.samp_sum != nullptr) && (EPI != TEPI_GN_BWD);  // GN_BWD: the sample sums come from the workspace finalize
     const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
     float cs = 0.f, cq = 0.f;  // this channel's statistics over all tiles of the CTA
     bf16* __restrict__ Cg = static_cast<bf16*>(p.C);
@@ -308,13 +308,31 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
             if (has_aux) y = __bfloat162float(reinterpret_cast<const bf16*>(so)[i * TC_LDO]);
             if (EPI == TEPI_STORE_R) v += y;
             if (EPI == TEPI_SILU_BWD) v *= silu_grad_f(fmaf(ep0, y, ep1));
-            const bf16 vb = __float2bfloat16_rn(v);
-            reinterpret_cast<bf16*>(so)[i * TC_LDO] = vb;
-            const float vr = __bfloat162float(vb);  // statistics of the STORED values
-            cs += vr;
-            cq = fmaf(vr, EPI == TEPI_SILU_BWD ? y : vr, cq);
+            if (EPI == TEPI_GN_BWD) {
+              // GroupNorm backward, phase 1 in sum form: per (sample, channel) A = sum v, Bx = sum v*x (raw x); everything else
+              // (dgamma, dbeta, per-sample sums of g and g*xhat) is linear in A and Bx and is derived by the finalize kernel
+              cs += v;
+              cq = fmaf(v, y, cq);
+              reinterpret_cast<bf16*>(so)[i * TC_LDO] = __float2bfloat16_rn(v * ep0);
+            } else {
+              const bf16 vb = __float2bfloat16_rn(v);
+              reinterpret_cast<bf16*>(so)[i * TC_LDO] = vb;
+              const float vr = __bfloat162float(vb);  // statistics of the STORED values
+              cs += vr;
+              cq = fmaf(vr, EPI == TEPI_SILU_BWD ? y : vr, cq);
+            }
           }
         }
+      }
+      if (EPI == TEPI_GN_BWD) {  // tiles never straddle samples (rows_per_sample % 128 == 0, checked on the host)
+        if (ch_ok && m0 < p.M) {
+          const int nsamples = (p.M + rps - 1) / rps;
+          double* wsA = p.gn_ws + (size_t)(m0 / rps) * p.N + ch;
+          atomicAdd(wsA, (double)cs);
+          atomicAdd(wsA + (size_t)nsamples * p.N, (double)cq);
+        }
+        cs = 0.f;
+        cq = 0.f;
       }
       tc_fence_before();
       __syncwarp();
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
       }
       if (has_aux && j + 1 < my_tiles) issue_aux(j + 1);
     }
-    if (p.col_sum && ch_ok) {
+    if (EPI != TEPI_GN_BWD && p.col_sum && ch_ok) {
       atomicAdd(p.col_sum + ch, (double)cs);
       atomicAdd(p.col_sq + ch, (double)cq);
     }
@@ -408,8 +426,53 @@ int launch_tc(const cvb_gemm_args& a, cudaStream_t st) {
   return launch_tc_impl<AMODE, EPI, false>(a, st, stagebuf, a_bytes + TC_WBLK);  // large K: weight k-blocks ride the ring
 }
 
+// GroupNorm backward, phase 1 finalize: from A[b,c] = sum_m v, Bx[b,c] = sum_m v*x over the pixels of sample b
+//   dbeta[c] += A;  dgamma[c] += t,  t = rstd_b (Bx - mean_b A) = sum_m v*xhat;   sum g = sum_c gamma_c A;   sum g*xhat = sum_c gamma_c t
+__global__ void __launch_bounds__(128) gn_bwd_ws_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, const float* __restrict__ gamma, int B, int N,
+                                                                  double* col_sum, double* col_sq, double* samp_sum, double* samp_sq) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ double s_red[2][4];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const double mu = (double)mean[b], rs = (double)rstd[b];
+  double sg = 0.0, sgx = 0.0;
+  for (int c = tid; c < N; c += 128) {
+    const double A = ws[(size_t)b * N + c], Bx = ws[((size_t)B + b) * N + c];
+    const double t = rs * (Bx - mu * A);
+    const double gm = gamma ? (double)gamma[c] : 1.0;
+    if (col_sum) { atomicAdd(col_sum + c, A); atomicAdd(col_sq + c, t); }
+    sg += gm * A;
+    sgx += gm * t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+  }
+  if ((tid & 31) == 0) { s_red[0][tid >> 5] = sg; s_red[1][tid >> 5] = sgx; }
+  __syncthreads();
+  if (tid == 0 && samp_sum) {
+    atomicAdd(samp_sum + b, s_red[0][0] + s_red[0][1] + s_red[0][2] + s_red[0][3]);
+    atomicAdd(samp_sq + b, s_red[1][0] + s_red[1][1] + s_red[1][2] + s_red[1][3]);
+  }
+}
+
+template <int AMODE>
+int launch_tc_gn_bwd(const cvb_gemm_args& a, cudaStream_t st) {
+  int rc = launch_tc<AMODE, TEPI_GN_BWD>(a, st);
+  if (rc != 0) return rc;
+  const int B = (a.M + a.rows_per_sample - 1) / a.rows_per_sample;
+  CVB_CUDA(cvb_launch(gn_bwd_ws_finalize_kernel, B, 128, 0, st, static_cast<const double*>(a.gn_ws), a.row_mean, a.row_rstd, a.e_p0, B, a.N, a.col_sum,
+                      a.col_sq, a.samp_sum, a.samp_sq));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int AMODE>
 int dispatch_tc_epi(const cvb_gemm_args& a, cudaStream_t st) {
+  if (a.e_mode == CVB_E_GN_BWD && a.gn_ws && a.rows_per_sample % TC_BM == 0 && !a.bias && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB))
+    return launch_tc_gn_bwd<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW>(a, st);
   if (a.e_mode == CVB_E_STORE) return a.R ? launch_tc<AMODE, TEPI_STORE_R>(a, st) : launch_tc<AMODE, TEPI_STORE>(a, st);
   if (a.e_mode == CVB_E_SILU_BWD && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB)) return launch_tc<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW, TEPI_SILU_BWD>(a, st);
   return -1;

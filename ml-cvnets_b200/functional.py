@@ -260,7 +260,7 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         gcount = HW * d
         dout = as_2d(to_bf16_cl(gout))
         n32 = sum(int(q.numel()) for q in params) + n * 8 * d + 16 * len(params) + 9 * C + 2 * (2 * d + 8) * n + 64
-        n64 = 4 * C + (n + 1) * (2 * d + 2 * B + 2 * d) + n * (2 * ffn + 2 * d + 2 * B + 2 * d) + 64
+        n64 = 4 * C + (n + 1) * (2 * d + 2 * B + 2 * d) + n * (2 * ffn + 2 * d + 2 * B + 2 * d) + 64 + (2 * n + 1) * (2 * B * d + 2)
         ar = _Arena(dev, n32, n64)
         sdp, sd0 = ar.f64(2, C), ar.f64(2, C)
         grads = [None] * len(params)
@@ -270,7 +270,7 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         dgbp, cp = ops.bn_bwd_finalize(sdp, M, gp, bnp, ev)
         cs, ss = ar.f64(2, d), ar.f64(2, B)
         g = ops.pw_gemm(dout, P.get(cfg.i_wpt), d, K=C, a_mode=A_BNB, A2=yp, a_p=cp, e_mode=E_GN_BWD, Y=XL, e_p=(gL, None),
-                        row_stats=(gnL[0], gnL[1]), rows_per_sample=HW, col_stats=cs, samp_stats=ss)
+                        row_stats=(gnL[0], gnL[1]), rows_per_sample=HW, col_stats=cs, samp_stats=ss, gn_ws=ar.f64(2, B, d))
         dWp = ops.pw_wgrad(dout, XL, C, d, g_mode=A_BNB, G2=yp, g_p=cp, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]),
                            rows_per_sample=HW, dW=ar.f32(C, d))
         base = 4 + 12 * n
@@ -293,7 +293,7 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             grads[o + 8] = ops.pw_wgrad(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW,
                                         dW=ar.f32(ffn, d)).view(ffn, d, 1, 1)
             gF = ops.pw_gemm(dh, P.get(ix.w1t), d, K=ffn, e_mode=E_GN_BWD, Y=X1, e_p=(gf, None), row_stats=(gnF[0], gnF[1]),
-                             rows_per_sample=HW, col_stats=csf, samp_stats=ssf)
+                             rows_per_sample=HW, col_stats=csf, samp_stats=ssf, gn_ws=ar.f64(2, B, d))
             late += [(o + 6, csf[1]), (o + 7, csf[0])]
             dX1 = ops.gn_bwd_apply(gF, X1, gnF, ssf, gcount, B, HW, DRES=dX, col_sum=bsum1)
             # attention: X1 = X + Wo O + bo ; O = linattn(qkv) ; qkv = Wqkv GN(X) + bqkv
@@ -308,7 +308,7 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             grads[o + 3] = ops.unprep_grad(dbq, 2 * d + 1, 1, 1, 3, rot=1)
             csa, ssa, bsum = ar.f64(2, d), ar.f64(2, B), ar.f64(d)
             gA = ops.pw_gemm(dqkv, P.get(ix.wqkvt), d, K=2 * d + 8, e_mode=E_GN_BWD, Y=X, e_p=(ga, None), row_stats=(gnA[0], gnA[1]),
-                             rows_per_sample=HW, col_stats=csa, samp_stats=ssa)
+                             rows_per_sample=HW, col_stats=csa, samp_stats=ssa, gn_ws=ar.f64(2, B, d))
             late += [(o + 0, csa[1]), (o + 1, csa[0])]
             dX = ops.gn_bwd_apply(gA, X, gnA, ssa, gcount, B, HW, DRES=dX1, col_sum=bsum if i > 0 else None)
         # ---- local_rep: 1x1 (no bias / norm) <- SiLU <- BN0 <- dw3x3

@@ -50,7 +50,7 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
             a_p: Sequence[Optional[Tensor]] = (None, None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,
             rows_per_sample: int = 0, bias: Optional[Tensor] = None, e_mode: int = E_STORE, Y: Optional[Tensor] = None,
             e_p: Sequence[Optional[Tensor]] = (None, None), R: Optional[Tensor] = None, out: Optional[Tensor] = None,
-            col_stats: Optional[Tensor] = None, samp_stats: Optional[Tensor] = None) -> Tensor:
+            col_stats: Optional[Tensor] = None, samp_stats: Optional[Tensor] = None, gn_ws: Optional[Tensor] = None) -> Tensor:
     """C[M,N] = epi(load(A)[M,K] @ W[N,K]^T + bias).  ``col_stats``/``samp_stats``: fp64 [2, *] accumulators (pre-zeroed)."""
     lib = _lib()
     M = A.shape[0]
@@ -87,6 +87,8 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
         a.col_sum, a.col_sq = col_stats[0].data_ptr(), col_stats[1].data_ptr()
     if samp_stats is not None:
         a.samp_sum, a.samp_sq = samp_stats[0].data_ptr(), samp_stats[1].data_ptr()
+    if gn_ws is not None:
+        a.gn_ws = gn_ws.data_ptr()
     L.check(lib.cvb_pw_gemm(ctypes.byref(a), _stream()), "cvb_pw_gemm")
     _count()
     return out

@@ -184,8 +184,11 @@ def test_pw_gemm_silu_bwd(ops, M, N, K):
     close(out2, (A.float() @ W.float().t()) * dsilu(Y.float()), what="silu_bwd identity")
 
 
-@pytest.mark.parametrize("M,N,K,rps", [(512, 64, 136, 64), (768, 128, 256, 256), (160, 16, 40, 16)])
-def test_pw_gemm_gn_bwd(ops, M, N, K, rps):
+@pytest.mark.parametrize("M,N,K,rps,ws", [(512, 64, 136, 64, False), (768, 128, 256, 256, False), (160, 16, 40, 16, False),
+                                           # with a workspace and rows_per_sample % 128 == 0 the epilogue runs on the tcgen05 kernel (sum form)
+                                           (768, 128, 256, 256, True), (4096, 192, 392, 1024, True), (1280, 256, 520, 128, True)])
+@pytest.mark.parametrize("bnb", [False, True])
+def test_pw_gemm_gn_bwd(ops, M, N, K, rps, ws, bnb):
     nb = M // rps
     A, W = bf(rnd(M, K, seed=21)), bf(rnd(N, K, scale=K ** -0.5, seed=22))
     X = bf(rnd(M, N, seed=23))
@@ -193,8 +196,17 @@ def test_pw_gemm_gn_bwd(ops, M, N, K, rps):
     row = (0.2 * rnd(nb, seed=25), 1 + 0.3 * rnd(nb, seed=26).abs())
     col = torch.zeros(2, N, device="cuda", dtype=torch.float64)
     samp = torch.zeros(2, nb, device="cuda", dtype=torch.float64)
-    out = ops.pw_gemm(A, W, N, e_mode=ops.E_GN_BWD, Y=X, e_p=(gamma, None), row_stats=row, rows_per_sample=rps, col_stats=col, samp_stats=samp)
-    v = A.float() @ W.float().t()
+    gn_ws = torch.zeros(2, nb, N, device="cuda", dtype=torch.float64) if ws else None
+    kw = {}
+    Af = A.float()
+    if bnb:
+        A2 = bf(rnd(M, K, seed=27))
+        c = (1 + 0.2 * rnd(K, seed=28), 0.1 * rnd(K, seed=29), 0.1 * rnd(K, seed=30))
+        kw = dict(a_mode=5, A2=A2, a_p=c)
+        Af = bf(c[0] * A.float() + c[1] * A2.float() + c[2]).float()
+    out = ops.pw_gemm(A, W, N, e_mode=ops.E_GN_BWD, Y=X, e_p=(gamma, None), row_stats=row, rows_per_sample=rps, col_stats=col, samp_stats=samp,
+                      gn_ws=gn_ws, **kw)
+    v = Af @ W.float().t()
     xh = (X.float() - row[0].repeat_interleave(rps)[:, None]) * row[1].repeat_interleave(rps)[:, None]
     close(out, v * gamma, what="g")
     close_stat(col[0], v.sum(0), "dbeta", rtol=5e-3)
