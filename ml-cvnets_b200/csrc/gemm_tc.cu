@@ -483,7 +483,7 @@ int dispatch_tc_epi(const cvb_gemm_args& a, cudaStream_t st) {
 // Returns -1 when the shape / mode is not handled by the tcgen05 kernel (caller uses the mma.sync kernel), 0 on success, > 0 on error.
 int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st) {
   // every epilogue thread owns one of 128 output channels: narrow layers would idle most of them -> mma.sync kernel
-  if (a.N < 96 || (a.N % 128 != 0 && a.N % 128 < 64 && a.N < 256)) return -1;
+  if (a.N < 96 || (a.N % 128 != 0 && a.N % 128 < 64 && a.N < 256)) return -1;  // N = 64 on this kernel measured slower than mma.sync
   switch (a.a_mode) {
     case CVB_A_RAW: return dispatch_tc_epi<CVB_A_RAW>(a, st);
     case CVB_A_AFF: return dispatch_tc_epi<CVB_A_AFF>(a, st);

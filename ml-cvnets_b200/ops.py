@@ -7,6 +7,7 @@ every wrapper launches on ``torch.cuda.current_stream()`` and never synchronises
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -46,6 +47,9 @@ def set_pdl_enabled(on: bool) -> bool:
 
 
 # --------------------------------------------------------------------------------------------------------------- GEMM
+WIDE_K = int(os.environ.get("CVB_WIDE_K", "384"))  # wide-layer policy threshold (diagnostics: CVB_WIDE_K=100000 disables the pre-pass)
+
+
 def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: int = A_RAW, A2: Optional[Tensor] = None,
             a_p: Sequence[Optional[Tensor]] = (None, None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,
             rows_per_sample: int = 0, bias: Optional[Tensor] = None, e_mode: int = E_STORE, Y: Optional[Tensor] = None,
@@ -55,7 +59,7 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
     lib = _lib()
     M = A.shape[0]
     K = A.shape[1] if K is None else K
-    if a_mode != A_RAW and K >= 384 and N > 128:
+    if a_mode != A_RAW and K >= WIDE_K and N > 128:
         # wide late-stage layer (small, L2-resident operand): apply the prologue once instead of once per N tile, then run the
         # prologue-free (tcgen05) GEMM
         A = apply_load_mode(A, a_mode, K, A2=A2, a_p=a_p, row_stats=row_stats, rows_per_sample=rows_per_sample)
