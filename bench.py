@@ -29,6 +29,29 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: route everything else that libraries print there (e.g. the "NCCL version ..." banner)
+    to stderr by pointing fd 1 at fd 2 for the duration of the run; emit() writes the result to the saved original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 METRIC = "images/sec training step, MobileViTv2-1.0 bf16 256x256"
 RES, NCLS = 256, 1000
 
@@ -125,7 +148,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------- our arm
@@ -446,7 +469,7 @@ def run_ours(args, rank, world, local_rank):
         line["op_ms"] = op_ms
         if timer.records:
             line["gemm_shapes"] = timer.per_shape(3 if use_graph else args.steps)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -464,6 +487,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph (N=1)")
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
