@@ -116,7 +116,8 @@ def cpu_training_throughput(batch, steps, warmup, threads=None):
     """The reference's own nn.Module path restated by the oracle (fp32: the reference refuses AMP on CPU,
     engine/utils.py:31-32), all host threads, AdamW(lr 2e-3, wd 0.05).  Returns (img/s, ms/step, cores)."""
     from oracle import cvnets_oracle as O
-    cores = threads or os.cpu_count() or 1
+    # usable cores = the affinity mask (a container may expose 128 CPUs in os.cpu_count() but schedule far fewer)
+    cores = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     torch.set_num_threads(cores)
     P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(1.0), 0))
     params = [v for k, v in P.items() if v.requires_grad]
@@ -134,16 +135,22 @@ def cpu_training_throughput(batch, steps, warmup, threads=None):
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port), all host threads, EXACTLY --steps timed and
+    --warmup untimed steps; each step is a bounded sample of the per-GPU batch, sized from a one-step probe so that the whole run
+    ends within a few minutes on this box."""
     if rank != 0:
         return
-    batch = args.cpu_batch
-    ips, ms, cores = cpu_training_throughput(batch, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    probe_ips, _, _ = cpu_training_throughput(2, 1, 0)
+    budget_s = 150.0
+    total_steps = max(1, args.steps + args.warmup)
+    batch = int(max(1, min(args.cpu_batch, probe_ips * budget_s / total_steps)))
+    ips, ms, cores = cpu_training_throughput(batch, max(1, args.steps), args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": max(1, args.steps),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32 (reference refuses AMP on CPU)", "data": "synthetic",
         "config": {"workload": "MobileViTv2-1.0 training step, 256x256, CPU nn.Module path (oracle port of the Python reference)",
-                   "batch_sample": batch, "note": "bounded sample of the per-GPU batch of 128"},
+                   "batch_sample": batch, "note": "bounded sample of the per-GPU batch of 128, sized from a one-step probe"},
         "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": f"batch {batch}, fwd+bwd+AdamW, fp32"},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
