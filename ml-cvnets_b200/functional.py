@@ -132,8 +132,9 @@ class StemFn(torch.autograd.Function):
         (sd,) = _zeros64(g2.device, C0)
         dz = ops.bn_bwd_reduce(g2, y, sd, bn, act=True, store_dz=True)
         dgb, coef = ops.bn_bwd_finalize(sd, M, gamma, bn, eval_mode=not cfg.bn.batch_stats)
-        dW = ops.pw_wgrad(dz, A0, C0, 32, g_mode=A_BNB, G2=y, g_p=coef)
-        dw = ops.unprep_grad(dW, C0, 27, 32, 0).view(C0, 3, 3, 3)
+        dW = ops.pw_wgrad_side(dz, A0, C0, 32, g_mode=A_BNB, G2=y, g_p=coef)
+        dw = ops.unprep_grad(dW, C0, 27, 32, 0, side=True).view(C0, 3, 3, 3)
+        ops.join_side()
         return None, None, dw, dgb[0], dgb[1]
 
 
@@ -181,7 +182,7 @@ class InvertedResidualFn(torch.autograd.Function):
         dgb3, c3 = ops.bn_bwd_finalize(sd3, M2, g3, bn3, ev)
         dz2 = ops.pw_gemm(dout, P.get(cfg.i_w3t), hid, K=cout, a_mode=A_BNB, A2=y3, a_p=c3, e_mode=E_SILU_BWD, Y=y2,
                           e_p=(bn2[2], bn2[3]), col_stats=sd2)
-        dW3 = ops.pw_wgrad(dout, y2, cout, hid, g_mode=A_BNB, G2=y3, g_p=c3, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), dW=ar.f32(cout, hid))
+        dW3 = ops.pw_wgrad_side(dout, y2, cout, hid, g_mode=A_BNB, G2=y3, g_p=c3, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), dW=ar.f32(cout, hid))
         # depthwise + BN2
         dgb2, c2 = ops.bn_bwd_finalize(sd2, M2, g2, bn2, ev)
         dz1, dWt = ops.dw_bwd(dz2, y1, B, H, W, hid, s, P.get(cfg.i_wd), g_mode=A_BNB, Y2=y2, g_p=c2, x_mode=A_AFF_SILU,
@@ -190,7 +191,8 @@ class InvertedResidualFn(torch.autograd.Function):
         # exp_1x1 + BN1
         dgb1, c1 = ops.bn_bwd_finalize(sd1, M, g1, bn1, ev)
         dx = ops.pw_gemm(dz1, P.get(cfg.i_w1t), Cin, K=hid, a_mode=A_BNB, A2=y1, a_p=c1, R=dout if cfg.residual else None)
-        dW1 = ops.pw_wgrad(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, dW=ar.f32(hid, Cin))
+        dW1 = ops.pw_wgrad_side(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, dW=ar.f32(hid, Cin))
+        ops.join_side()
         return (to_4d(dx, B, H, W), None, dW1.view(hid, Cin, 1, 1), dgb1[0], dgb1[1], dWd, dgb2[0], dgb2[1],
                 dW3.view(cout, hid, 1, 1), dgb3[0], dgb3[1])
 
@@ -271,7 +273,7 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         cs, ss = ar.f64(2, d), ar.f64(2, B)
         g = ops.pw_gemm(dout, P.get(cfg.i_wpt), d, K=C, a_mode=A_BNB, A2=yp, a_p=cp, e_mode=E_GN_BWD, Y=XL, e_p=(gL, None),
                         row_stats=(gnL[0], gnL[1]), rows_per_sample=HW, col_stats=cs, samp_stats=ss, gn_ws=ar.f64(2, B, d))
-        dWp = ops.pw_wgrad(dout, XL, C, d, g_mode=A_BNB, G2=yp, g_p=cp, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]),
+        dWp = ops.pw_wgrad_side(dout, XL, C, d, g_mode=A_BNB, G2=yp, g_p=cp, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]),
                            rows_per_sample=HW, dW=ar.f32(C, d))
         base = 4 + 12 * n
         late += [(base + 0, cs[1]), (base + 1, cs[0])]  # dgamma = sum v*xhat, dbeta = sum v
@@ -286,11 +288,11 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             o = 4 + 12 * i
             # FFN: X2 = X1 + W2 silu(h) + b2 ; h = W1 GN(X1) + b1
             late.append((o + 11, bsum))  # db2
-            grads[o + 10] = ops.pw_wgrad(dX, h, d, ffn, a_mode=A_SILU, dW=ar.f32(d, ffn)).view(d, ffn, 1, 1)
+            grads[o + 10] = ops.pw_wgrad_side(dX, h, d, ffn, a_mode=A_SILU, dW=ar.f32(d, ffn)).view(d, ffn, 1, 1)
             csh, csf, ssf, bsum1 = ar.f64(2, ffn), ar.f64(2, d), ar.f64(2, B), ar.f64(d)
             dh = ops.pw_gemm(dX, P.get(ix.w2t), ffn, K=d, e_mode=E_SILU_BWD, Y=h, col_stats=csh)
             late.append((o + 9, csh[0]))  # db1 = column sums of dh
-            grads[o + 8] = ops.pw_wgrad(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW,
+            grads[o + 8] = ops.pw_wgrad_side(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW,
                                         dW=ar.f32(ffn, d)).view(ffn, d, 1, 1)
             gF = ops.pw_gemm(dh, P.get(ix.w1t), d, K=ffn, e_mode=E_GN_BWD, Y=X1, e_p=(gf, None), row_stats=(gnF[0], gnF[1]),
                              rows_per_sample=HW, col_stats=csf, samp_stats=ssf, gn_ws=ar.f64(2, B, d))
@@ -298,13 +300,13 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             dX1 = ops.gn_bwd_apply(gF, X1, gnF, ssf, gcount, B, HW, DRES=dX, col_sum=bsum1)
             # attention: X1 = X + Wo O + bo ; O = linattn(qkv) ; qkv = Wqkv GN(X) + bqkv
             late.append((o + 5, bsum1))  # dbo
-            grads[o + 4] = ops.pw_wgrad(dX1, O, d, d, dW=ar.f32(d, d)).view(d, d, 1, 1)
+            grads[o + 4] = ops.pw_wgrad_side(dX1, O, d, d, dW=ar.f32(d, d)).view(d, d, 1, 1)
             dO = ops.pw_gemm(dX1, P.get(ix.wot), d, K=d)
             dbq = ar.f32(2 * d + 8)
             dqkv = ops.linattn_bwd(qkv, dO, S, CTX, B, H, W, d, dbias=dbq)
-            dWq = ops.pw_wgrad(dqkv, X, 2 * d + 8, d, a_mode=A_GN, a_p=(ga, ba), row_stats=(gnA[0], gnA[1]), rows_per_sample=HW,
+            dWq = ops.pw_wgrad_side(dqkv, X, 2 * d + 8, d, a_mode=A_GN, a_p=(ga, ba), row_stats=(gnA[0], gnA[1]), rows_per_sample=HW,
                                dW=ar.f32(2 * d + 8, d))
-            grads[o + 2] = ops.unprep_grad(dWq, 2 * d + 1, d, d, 0, rot=1).view(2 * d + 1, d, 1, 1)
+            grads[o + 2] = ops.unprep_grad(dWq, 2 * d + 1, d, d, 0, rot=1, side=True).view(2 * d + 1, d, 1, 1)
             grads[o + 3] = ops.unprep_grad(dbq, 2 * d + 1, 1, 1, 3, rot=1)
             csa, ssa, bsum = ar.f64(2, d), ar.f64(2, B), ar.f64(d)
             gA = ops.pw_gemm(dqkv, P.get(ix.wqkvt), d, K=2 * d + 8, e_mode=E_GN_BWD, Y=X, e_p=(ga, None), row_stats=(gnA[0], gnA[1]),
@@ -312,12 +314,13 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             late += [(o + 0, csa[1]), (o + 1, csa[0])]
             dX = ops.gn_bwd_apply(gA, X, gnA, ssa, gcount, B, HW, DRES=dX1, col_sum=bsum if i > 0 else None)
         # ---- local_rep: 1x1 (no bias / norm) <- SiLU <- BN0 <- dw3x3
-        grads[3] = ops.pw_wgrad(dX, y0, d, C, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), dW=ar.f32(d, C)).view(d, C, 1, 1)
+        grads[3] = ops.pw_wgrad_side(dX, y0, d, C, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), dW=ar.f32(d, C)).view(d, C, 1, 1)
         dz0 = ops.pw_gemm(dX, P.get(cfg.i_wlt), C, K=d, e_mode=E_SILU_BWD, Y=y0, e_p=(bn0[2], bn0[3]), col_stats=sd0)
         dgb0, c0 = ops.bn_bwd_finalize(sd0, M, g0, bn0, ev)
         dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW, dWt=ar.f32(9, C))
         grads[0] = ops.unprep_grad(dWt, C, 9, C, 2).view(C, 1, 3, 3)
         grads[1], grads[2] = dgb0[0], dgb0[1]
+        ops.join_side()
         ar.cast()
         for idx, v64 in late:
             grads[idx] = ar.as_f32(v64)
@@ -348,9 +351,10 @@ class PoolLinearFn(torch.autograd.Function):
         g = torch.zeros((B, npad), device=pooled.device, dtype=BF16)
         g[:, :ncls] = gout
         db = torch.zeros(npad, device=pooled.device, dtype=torch.float32)
-        dW = ops.pw_wgrad(g, pooled, npad, C, dbias=db)
+        dW = ops.pw_wgrad_side(g, pooled, npad, C, dbias=db)
         dp = ops.pw_gemm(g, cfg.prep.get(cfg.i_wt), C, K=npad)
         dx = ops.global_pool_bwd(dp, B, H * W)
+        ops.join_side()
         return to_4d(dx, B, H, W), None, dW[:ncls], db[:ncls]
 
 
@@ -398,12 +402,13 @@ class MultiHeadAttentionFn(torch.autograd.Function):
         x2, qkv, O, LSE, amask, kpm = ctx.saved
         dy = gout.reshape(N * S, cfg.out_dim).to(BF16).contiguous()
         dbo = torch.zeros(cfg.out_dim, device=dy.device, dtype=torch.float32)
-        dWo = ops.pw_wgrad(dy, O, cfg.out_dim, C, dbias=dbo)
+        dWo = ops.pw_wgrad_side(dy, O, cfg.out_dim, C, dbias=dbo)
         dO = ops.pw_gemm(dy, P.get(cfg.i_wot), C, K=cfg.out_dim)
         dqkv = ops.mha_bwd(qkv, O, dO, LSE, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
         dbq = torch.zeros(3 * C, device=dy.device, dtype=torch.float32)
-        dWq = ops.pw_wgrad(dqkv, x2, 3 * C, C, dbias=dbq)
+        dWq = ops.pw_wgrad_side(dqkv, x2, 3 * C, C, dbias=dbq)
         dx = ops.pw_gemm(dqkv, P.get(cfg.i_wqkvt), C, K=3 * C)
+        ops.join_side()
         return dx.view(N, S, C), None, dWq, dbq, dWo, dbo
 
 
@@ -449,24 +454,25 @@ class TransformerEncoderFn(torch.autograd.Function):
         # ---- FFN
         db2, db1 = ar.f32(C), ar.f32(ffn)
         if cfg.act == ops.ACT_SILU:
-            dW2 = ops.pw_wgrad(dY, h, C, ffn, a_mode=A_SILU, dW=ar.f32(C, ffn), dbias=db2)
+            dW2 = ops.pw_wgrad_side(dY, h, C, ffn, a_mode=A_SILU, dW=ar.f32(C, ffn), dbias=db2)
             dh = ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C, e_mode=E_SILU_BWD, Y=h)
         else:
-            dW2 = ops.pw_wgrad(dY, ha, C, ffn, dW=ar.f32(C, ffn), dbias=db2)
+            dW2 = ops.pw_wgrad_side(dY, ha, C, ffn, dW=ar.f32(C, ffn), dbias=db2)
             dh = ops.act_bwd(ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C), h, cfg.act)
-        dW1 = ops.pw_wgrad(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=ar.f32(ffn, C), dbias=db1)
+        dW1 = ops.pw_wgrad_side(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=ar.f32(ffn, C), dbias=db1)
         csf, bsum1 = ar.f64(2, C), ar.f64(C)
         vF = ops.pw_gemm(dh, P.get(cfg.i_w1t), C, K=ffn)
         dX1 = ops.ln_bwd(vF, X1, ln2, g2, csf, DRES=dY, col_sum=bsum1)  # bsum1 = column sums of dX1 = d(out_proj bias)
         # ---- attention
-        dWo = ops.pw_wgrad(dX1, O, C, C, dW=ar.f32(C, C))
+        dWo = ops.pw_wgrad_side(dX1, O, C, C, dW=ar.f32(C, C))
         dO = ops.pw_gemm(dX1, P.get(cfg.i_wot), C, K=C)
         dqkv = ops.mha_bwd(qkv, O, dO, LSE, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
         dbq = ar.f32(3 * C)
-        dWq = ops.pw_wgrad(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=ar.f32(3 * C, C), dbias=dbq)
+        dWq = ops.pw_wgrad_side(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=ar.f32(3 * C, C), dbias=dbq)
         csa = ar.f64(2, C)
         vA = ops.pw_gemm(dqkv, P.get(cfg.i_wqkvt), C, K=3 * C)
         dx = ops.ln_bwd(vA, x2, ln1, g1, csa, DRES=dX1)
+        ops.join_side()
         ar.cast()
         f = ar.as_f32
         # (x, cfg, g1, b1, wqkv, bqkv, wo, bo, g2, b2, w1, bb1, w2, bb2)

@@ -31,6 +31,48 @@ def _lib():
     return L.load()
 
 
+# ---------------------------------------------------------------------------------------------------- side stream
+# Weight-gradient GEMMs are off the critical path of the backward pass (their results are only needed by the optimizer), so the
+# autograd functions issue them on a second stream: `side=True` forks from the current stream (everything enqueued so far is a
+# dependency), and `join_side()` at the end of each backward makes the current stream wait for them.  Under CUDA-graph capture this
+# becomes a parallel branch of the graph whose CTAs fill the tails of the main-branch kernels.  CVB_WGRAD_STREAM=0 disables it.
+_SIDE = {"on": os.environ.get("CVB_WGRAD_STREAM", "1") != "0", "streams": {}, "dirty": False}
+
+
+class _SideCtx:
+    def __init__(self, active: bool):
+        self.active = active and _SIDE["on"]
+
+    def __enter__(self):
+        if not self.active:
+            return self
+        main = torch.cuda.current_stream()
+        dev = main.device
+        side = _SIDE["streams"].get(dev)
+        if side is None:
+            side = _SIDE["streams"][dev] = torch.cuda.Stream(device=dev)
+        side.wait_stream(main)
+        self._cm = torch.cuda.stream(side)
+        self._cm.__enter__()
+        _SIDE["dirty"] = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self._cm.__exit__(*exc)
+        return False
+
+
+def join_side():
+    """Make the current stream wait for everything issued with ``side=True`` (call before the results are consumed)."""
+    if _SIDE["dirty"]:
+        main = torch.cuda.current_stream()
+        side = _SIDE["streams"].get(main.device)
+        if side is not None:
+            main.wait_stream(side)
+        _SIDE["dirty"] = False
+
+
 def _count(n=1):
     global launch_count
     launch_count += n
@@ -114,8 +156,8 @@ def apply_load_mode(A: Tensor, mode: int, K: int, *, A2: Optional[Tensor] = None
 def pw_wgrad(G: Tensor, A: Tensor, N: int, K: int, *, g_mode: int = A_RAW, G2: Optional[Tensor] = None,
              g_p: Sequence[Optional[Tensor]] = (None, None, None), a_mode: int = A_RAW,
              a_p: Sequence[Optional[Tensor]] = (None, None), row_stats: Optional[Tuple[Tensor, Tensor]] = None,
-             rows_per_sample: int = 0, dW: Optional[Tensor] = None, dbias: Optional[Tensor] = None) -> Tensor:
-    """dW[N,K] (fp32, zero-initialised here unless given) += load(G)^T @ load(A)."""
+             rows_per_sample: int = 0, dW: Optional[Tensor] = None, dbias: Optional[Tensor] = None, side: bool = False) -> Tensor:
+    """dW[N,K] (fp32, zero-initialised here unless given) += load(G)^T @ load(A).  ``side``: issue on the side stream (see join_side)."""
     lib = _lib()
     if dW is None:
         dW = torch.zeros((N, K), device=G.device, dtype=torch.float32)
@@ -132,7 +174,8 @@ def pw_wgrad(G: Tensor, A: Tensor, N: int, K: int, *, g_mode: int = A_RAW, G2: O
     a.rows_per_sample = rows_per_sample
     a.dW, a.lddw = dW.data_ptr(), dW.stride(0)
     a.dbias = _p(dbias)
-    L.check(lib.cvb_pw_wgrad(ctypes.byref(a), _stream()), "cvb_pw_wgrad")
+    with _SideCtx(side):
+        L.check(lib.cvb_pw_wgrad(ctypes.byref(a), _stream()), "cvb_pw_wgrad")
     _count()
     return dW
 
@@ -384,10 +427,16 @@ def col_sum(X: Tensor, N: Optional[int] = None, out: Optional[Tensor] = None) ->
     return out
 
 
-def unprep_grad(src: Tensor, rows: int, cols: int, lds: int, kind: int, rot: int = 0) -> Tensor:
+def pw_wgrad_side(G: Tensor, A: Tensor, N: int, K: int, **kw) -> Tensor:
+    """pw_wgrad on the side stream (the caller joins with join_side() before the result is consumed)."""
+    return pw_wgrad(G, A, N, K, side=True, **kw)
+
+
+def unprep_grad(src: Tensor, rows: int, cols: int, lds: int, kind: int, rot: int = 0, side: bool = False) -> Tensor:
     lib = _lib()
     dst = torch.empty((rows, cols) if kind != 3 else (rows,), device=src.device, dtype=torch.float32)
-    L.check(lib.cvb_unprep_grad(src.data_ptr(), dst.data_ptr(), rows, cols, lds, kind, rot, _stream()), "cvb_unprep_grad")
+    with _SideCtx(side):
+        L.check(lib.cvb_unprep_grad(src.data_ptr(), dst.data_ptr(), rows, cols, lds, kind, rot, _stream()), "cvb_unprep_grad")
     _count()
     return dst
 
