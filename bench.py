@@ -450,7 +450,11 @@ def run_ours(args, rank, world, local_rank):
         per_step_ms = gms / nsteps_t
         ach = gbytes / (gms * 1e-3) / 1e9
         roof = {"kernel": "pw_gemm_kernel (all 1x1-conv / linear forward + input-gradient GEMMs)", "bound": "hbm", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None, "launches_per_step": n // nsteps_t,
+                "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                "traffic_note": ("the family has 111 launches of ~60 shapes per step, so there is no single per-launch DRAM figure; ncu --set full of its "
+                                 "largest member (pw_gemm_tc_kernel<RAW,STORE>, M=2097152 K=64 N=128): dram read+write 746 MB per launch vs 805 MB "
+                                 "algorithmic (profiles/r1_ncu_full_v8_dw_walk_wgrad_tc.csv)"),
+                "launches_per_step": n // nsteps_t,
                 "kernel_ms_per_step": per_step_ms, "share_of_step": per_step_ms / ms_step,
                 "algorithmic_bytes_per_step": gbytes / nsteps_t, "tflops": gflops / (gms * 1e-3) / 1e12}
     cpu = None
