@@ -22,27 +22,6 @@ constexpr int NT = 256;   // forward: 8 warps, 2 CTAs / SM
 constexpr int NTB = 512;  // backward: 16 warps, 1 CTA / SM
 constexpr int SEG = 8;    // pixels a warp walks per strip (fully unrolled: the window shift is register renaming)
 
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 r;
-  asm("{ .reg .b64 a,b,c,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mov.b64 c,{%6,%7}; fma.rn.f32x2 d,a,b,c; mov.b64 {%0,%1}, d; }"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return r;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  float2 r;
-  asm("{ .reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; mul.rn.f32x2 d,a,b; mov.b64 {%0,%1}, d; }"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return r;
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  float2 r;
-  asm("{ .reg .b64 a,b,d; mov.b64 a,{%2,%3}; mov.b64 b,{%4,%5}; add.rn.f32x2 d,a,b; mov.b64 {%0,%1}, d; }"
-      : "=f"(r.x), "=f"(r.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return r;
-}
 // bf16x2 -> two fp32 (exact): two integer-pipe instructions, no conversion unit
 __device__ __forceinline__ float2 up2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
 __device__ __forceinline__ float2 lds2(const uint8_t* tile, int pix, int lane) {

@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
     const bool want_samp = (p.samp_sum != nullptr) && (EPI != TEPI_GN_BWD);  // GN_BWD: the sample sums come from the workspace finalize
     const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
     float cs = 0.f, cq = 0.f;  // this channel's statistics over all tiles of the CTA
+    float2 cs2 = make_float2(0.f, 0.f), cq2 = make_float2(0.f, 0.f);  // hot-path partials (even / odd pixel columns), folded in at the end
     bf16* __restrict__ Cg = static_cast<bf16*>(p.C);
     constexpr int CGS = TC_BN / 8;
 
@@ -291,14 +292,16 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
         if (full_tile && !has_aux) {
           // hot path (conv -> BN statistics): ~5 instructions per value.  The BatchNorm sums are taken from the fp32 values
           // (before bf16 rounding): the rounding error averages out over the >= 128 pixels of the tile.
+          // packed fp32 pairs (adjacent pixel columns are adjacent registers of the tcgen05.ld result): 7 instructions per 2 values
+          const float2 b2 = make_float2(bias, bias);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float v0 = __uint_as_float(r[i]) + bias, v1 = __uint_as_float(r[i + 1]) + bias;
-            const uint32_t pk = pack_bf162(v0, v1);
+            const float2 v = fadd2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), b2);
+            const uint32_t pk = pack_bf162(v.x, v.y);
             so[i * TC_LDO] = (uint16_t)pk;
             so[(i + 1) * TC_LDO] = (uint16_t)(pk >> 16);
-            cs += v0 + v1;
-            cq = fmaf(v0, v0, fmaf(v1, v1, cq));
+            cs2 = fadd2(cs2, v);
+            cq2 = ffma2(v, v, cq2);
           }
         } else {
 #pragma unroll
@@ -374,6 +377,8 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
       }
       if (has_aux && j + 1 < my_tiles) issue_aux(j + 1);
     }
+    cs += cs2.x + cs2.y;
+    cq += cq2.x + cq2.y;
     if (EPI != TEPI_GN_BWD && p.col_sum && ch_ok) {
       atomicAdd(p.col_sum + ch, (double)cs);
       atomicAdd(p.col_sq + ch, (double)cq);
