@@ -119,6 +119,50 @@ print("OK", sum(p.numel() for p in ours.parameters()), [len(x["params"]) for x i
     assert "OK 4901841" in out.stdout
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cvnets"), reason="reference checkout not present (GPU box)")
+def test_transformer_dropins_match_reference_contract():
+    """MultiHeadAttention / TransformerEncoder: same constructor parameters, forward parameters, state_dict keys and shapes as the
+    reference classes, checked against the reference checkout itself; rebind_modules() swaps them in."""
+    code = r"""
+import sys, os, argparse, inspect
+sys.path.insert(0, %r); sys.path.insert(0, "/root/reference"); os.chdir("/root/reference")
+import ml_cvnets_b200 as ours
+import ml_cvnets_b200.register as r
+from cvnets import modeling_arguments
+from cvnets.layers import MultiHeadAttention as RefMHA
+from cvnets.modules import TransformerEncoder as RefEnc
+def params(f): return [p for p in inspect.signature(f).parameters if p not in ("args", "kwargs")]
+assert params(ours.MultiHeadAttention.__init__) == params(RefMHA.__init__)
+assert params(ours.MultiHeadAttention.forward)[:5] == ["self", "x_q", "x_kv", "key_padding_mask", "attn_mask"]
+assert params(ours.TransformerEncoder.__init__) == params(RefEnc.__init__)
+assert params(ours.TransformerEncoder.forward) == params(RefEnc.forward)
+opts = modeling_arguments(argparse.ArgumentParser()).parse_args([])
+for act in ("swish", "gelu"):
+    setattr(opts, "model.activation.name", act)
+    a, b = ours.TransformerEncoder(opts, 64, 128, num_heads=4), RefEnc(opts, 64, 128, num_heads=4)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys()), (list(sa.keys()), list(sb.keys()))
+    assert all(sa[k].shape == sb[k].shape and sa[k].dtype == sb[k].dtype for k in sa)
+    a.load_state_dict(sb, strict=True)
+    assert float(a.pre_norm_mha[0].eps) == float(b.pre_norm_mha[0].eps)
+    assert repr(a).split("(")[0] == repr(b).split("(")[0]
+m1, m2 = ours.MultiHeadAttention(64, 4), RefMHA(64, 4)
+assert list(m1.state_dict().keys()) == list(m2.state_dict().keys())
+r.rebind_modules()
+import cvnets.modules as cm
+assert cm.TransformerEncoder is ours.TransformerEncoder and cm.MobileViTBlockv2 is ours.MobileViTBlockv2
+try:
+    a(__import__("torch").zeros(2, 5, 64))
+    raise SystemExit("CPU input must raise")
+except RuntimeError:
+    pass
+print("OK")
+""" % REPO
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "OK" in out.stdout
+
+
 def _gloo_worker(rank, world, port, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, REPO)
