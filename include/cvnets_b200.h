@@ -84,7 +84,7 @@ typedef struct {
   double* col_sum; double* col_sq;   /* fp64 [N] accumulators or NULL (BatchNorm statistics of the stored output) */
   double* samp_sum; double* samp_sq; /* fp64 [M/rows_per_sample] or NULL (GroupNorm statistics of the stored output) */
   double* gn_ws;            /* CVB_E_GN_BWD only, optional: ZEROED fp64 workspace [2][M/rows_per_sample][N].  When given (and
-                               rows_per_sample % 128 == 0) the epilogue runs on the tcgen05 kernel: it accumulates the per-(sample, channel)
+                               rows_per_sample % 64 == 0) the epilogue runs on the tcgen05 kernel: it accumulates the per-(sample, channel)
                                sums of v and v*x there and a finalize kernel derives col_sum/col_sq/samp_sum/samp_sq from them. */
 } cvb_gemm_args;
 CVB_API int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream);

@@ -327,10 +327,11 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
           }
         }
       }
-      if (EPI == TEPI_GN_BWD) {  // tiles never straddle samples (rows_per_sample % 128 == 0, checked on the host)
-        if (ch_ok && m0 < p.M) {
+      if (EPI == TEPI_GN_BWD) {  // this thread's 64 pixel columns never straddle samples (rows_per_sample % 64 == 0, checked on the host)
+        const int mh = m0 + chalf * (TC_BM / 2);
+        if (ch_ok && mh < p.M) {
           const int nsamples = (p.M + rps - 1) / rps;
-          double* wsA = p.gn_ws + (size_t)(m0 / rps) * p.N + ch;
+          double* wsA = p.gn_ws + (size_t)(mh / rps) * p.N + ch;
           atomicAdd(wsA, (double)cs);
           atomicAdd(wsA + (size_t)nsamples * p.N, (double)cq);
         }
@@ -476,7 +477,7 @@ int launch_tc_gn_bwd(const cvb_gemm_args& a, cudaStream_t st) {
 
 template <int AMODE>
 int dispatch_tc_epi(const cvb_gemm_args& a, cudaStream_t st) {
-  if (a.e_mode == CVB_E_GN_BWD && a.gn_ws && a.rows_per_sample % TC_BM == 0 && !a.bias && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB))
+  if (a.e_mode == CVB_E_GN_BWD && a.gn_ws && a.rows_per_sample % (TC_BM / 2) == 0 && !a.bias && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB))
     return launch_tc_gn_bwd<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW>(a, st);
   if (a.e_mode == CVB_E_STORE) return a.R ? launch_tc<AMODE, TEPI_STORE_R>(a, st) : launch_tc<AMODE, TEPI_STORE>(a, st);
   if (a.e_mode == CVB_E_SILU_BWD && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB)) return launch_tc<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW, TEPI_SILU_BWD>(a, st);

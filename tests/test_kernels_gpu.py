@@ -185,8 +185,8 @@ def test_pw_gemm_silu_bwd(ops, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,rps,ws", [(512, 64, 136, 64, False), (768, 128, 256, 256, False), (160, 16, 40, 16, False),
-                                           # with a workspace and rows_per_sample % 128 == 0 the epilogue runs on the tcgen05 kernel (sum form)
-                                           (768, 128, 256, 256, True), (4096, 192, 392, 1024, True), (1280, 256, 520, 128, True)])
+                                           # with a workspace and rows_per_sample % 64 == 0 the epilogue runs on the tcgen05 kernel (sum form)
+                                           (768, 128, 256, 256, True), (4096, 192, 392, 1024, True), (1280, 256, 520, 128, True), (1344, 256, 512, 64, True)])
 @pytest.mark.parametrize("bnb", [False, True])
 def test_pw_gemm_gn_bwd(ops, M, N, K, rps, ws, bnb):
     nb = M // rps
