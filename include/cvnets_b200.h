@@ -88,9 +88,9 @@ typedef struct {
                                sums of v and v*x there and a finalize kernel derives col_sum/col_sq/samp_sum/samp_sq from them. */
 } cvb_gemm_args;
 CVB_API int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream);
-/* Two kernels implement cvb_pw_gemm: a warp-specialised tcgen05/TMEM/TMA kernel (prologue-free layers) and an mma.sync kernel
- * (layers whose A operand needs an element-wise prologue).  Testing hook: disable (0) / enable (1) the tcgen05 kernel so the
- * two can be compared on identical inputs; returns the previous setting. */
+/* Two kernels implement cvb_pw_gemm (and two cvb_pw_wgrad): warp-specialised tcgen05/TMEM/TMA kernels (N >= 96 resp. K % 64 == 0)
+ * and mma.sync kernels (narrow / odd shapes).  Testing hook: disable (0) / enable (1) the tcgen05 kernels so the two can be compared
+ * on identical inputs; returns the previous setting. */
 CVB_API int cvb_set_tc_enabled(int on);
 /* Every kernel is launched with programmatic dependent launch (its set-up overlaps the previous kernel's tail; the kernel
  * itself orders its data accesses with griddepcontrol.wait).  Testing hook: plain stream-ordered launches (0) / PDL (1);

@@ -4,11 +4,12 @@
 //   cvb_pw_wgrad: dW[N,K] += sum_m load(G)[m,n] * load(A)[m,k]        weight-gradient GEMM (reduction over pixels)
 //
 // Every layer here is HBM-bound (K,N <= 768: <= 170 FLOP/B, B200 ridge ~250 FLOP/B), so the design goal is
-// "read each activation once, write each activation once": the producer's BatchNorm/SiLU/GroupNorm is applied to the
-// A fragments in registers between ldmatrix and mma (no extra pass, no extra smem traffic), and bias / activation /
-// residual / BN-statistics / GN-statistics / activation-backward are applied in the epilogue on a smem-staged tile so
-// that all global traffic is 16-byte, row-contiguous.  Tensor-core path: mma.sync.m16n8k16 bf16 -> fp32 (register
-// prologue is what makes the fusion free); operands arrive through a 4-stage cp.async ring with XOR-swizzled smem.
+// "read each activation once, write each activation once": the producer's BatchNorm/SiLU/GroupNorm (or the BN-backward of the
+// consumer) is a LOAD MODE of the A operand, and bias / activation / residual / BN statistics / GN statistics / activation
+// backward / GroupNorm backward are EPILOGUE modes, so no stand-alone normalisation or activation pass exists inside a module.
+// This file holds the mma.sync.m16n8k16 (bf16 -> fp32) kernels: the forward / input-gradient GEMM for narrow layers (N < 96) and
+// shapes the tcgen05 kernels do not take, the 64x64-tile weight-gradient kernel (K % 64 != 0 or tiny N, K), and the C-ABI entry
+// points that route to the tcgen05 / TMEM kernels in gemm_tc.cu and wgrad_tc.cu first.
 #include "common.cuh"
 
 namespace {
@@ -686,7 +687,7 @@ int dispatch_wgrad_a(const cvb_wgrad_args& a, cudaStream_t st) {
 }  // namespace
 
 int cvb_pw_wgrad_tc(const cvb_wgrad_args& a, cudaStream_t st);  // wgrad_tc.cu: tcgen05 / TMEM weight-gradient kernel
-int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st);  // gemm_tc.cu: tcgen05 / TMEM kernel for the prologue-free layers
+int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st);  // gemm_tc.cu: tcgen05 / TMEM kernel (all load modes; STORE / residual / SiLU-backward / GroupNorm-backward epilogues)
 static int g_tc_enabled = 1;
 extern "C" int cvb_set_tc_enabled(int on) {
   int old = g_tc_enabled;

@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA pointwise-conv GEMM for the prologue-free (RAW) layers (sm_100a).
+// tcgen05 / TMEM / TMA pointwise-conv GEMM (sm_100a): every load mode, STORE / residual / SiLU-backward / GroupNorm-backward epilogues.
 //
 //   C[M,N] = epi( A[M,K] * W[N,K]^T + bias )          same contract as the mma.sync kernel in gemm.cu
 //
