@@ -270,13 +270,28 @@ def run_ours(args, rank, world, local_rank):
         for t in list(model.parameters()) + list(model.buffers()):
             torch.distributed.broadcast(t.data, src=0)
     groups, _ = model.get_trainable_parameters(weight_decay=0.05, no_decay_bn_filter_bias=True)
-    opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999), fused=True, capturable=not args.no_graph)
-    scaler = torch.amp.GradScaler("cuda", enabled=True)  # the reference enables it even for bf16 (main_train.py:114)
     params = [p for p in model.parameters()]
+    tail = None
+    if args.fused_tail and not use_ddp_wrapper:
+        # unscale + inf check + clip + AdamW + scaler update as two launches on flat buffers
+        from ml_cvnets_b200.optim import FlatAdamW
+        tail = FlatAdamW(model, lr=2e-3, betas=(0.9, 0.999), weight_decay=0.05, no_decay_bn_filter_bias=True, max_norm=10.0)
+
+        def flat_allreduce(g):
+            torch.distributed.all_reduce(g)
+            g.div_(world)
+    else:
+        opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999), fused=True, capturable=not args.no_graph)
+        scaler = torch.amp.GradScaler("cuda", enabled=True)  # the reference enables it even for bf16 (main_train.py:114)
 
     def step(x, y):
         logits = train_model(x)
         loss = F.cross_entropy(logits.float(), y, label_smoothing=0.1)
+        if tail is not None:
+            model.zero_grad(set_to_none=True)
+            (loss * tail.loss_scale()).backward()
+            tail.step(world, flat_allreduce if world > 1 else None)
+            return loss
         opt.zero_grad(set_to_none=True)
         scaler.scale(loss).backward()
         if world > 1 and not use_ddp_wrapper:
@@ -322,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        opt.zero_grad(set_to_none=True)
+        model.zero_grad(set_to_none=True)
         launches_before_capture = ops.launch_count
         with torch.cuda.graph(graph):
             static_loss = step(static_x, static_y)
@@ -468,7 +483,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "MobileViTv2-1.0 bf16 training step, synthetic ImageNet 256x256 (BASELINE.json configs[1])",
-                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_sync": ("none" if world == 1 else "DDP wrapper (eager)" if use_ddp_wrapper else "flat fp32 NCCL all-reduce inside the CUDA graph"), "optimizer": "AdamW(fused) + GradScaler + clip_grad_norm 10", "execution": "one CUDA graph per step" if use_graph else "eager launches",
+                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_sync": ("none" if world == 1 else "DDP wrapper (eager)" if use_ddp_wrapper else "flat fp32 NCCL all-reduce inside the CUDA graph"), "optimizer": ("FlatAdamW: cvb_grad_norm + cvb_adamw_step (unscale, clip 10, AdamW, scaler update)" if tail is not None else "AdamW(fused) + GradScaler + clip_grad_norm 10"), "execution": "one CUDA graph per step" if use_graph else "eager launches",
                    "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                   "ms_per_step": e2e_ms},
@@ -494,6 +509,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="CUDA-event time per C-ABI entry point (diagnostics)")
+    ap.add_argument("--fused-tail", action="store_true", help="fused flat-buffer unscale/clip/AdamW/scaler tail (ml_cvnets_b200.optim.FlatAdamW)")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostics: plain stream-ordered launches instead of programmatic dependent launch")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph (N=1)")
     args = ap.parse_args()

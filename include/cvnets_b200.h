@@ -31,7 +31,7 @@ typedef void* cvb_stream_t; /* cudaStream_t */
 #define CVB_API
 #endif
 
-#define CVB_ABI_VERSION 5
+#define CVB_ABI_VERSION 6
 
 /* operand "load modes": the normalisation / activation of the PRODUCER layer is applied while the CONSUMER loads it
  * (training-mode BatchNorm cannot be fused into its own conv: SURVEY.md section 7 "hard parts"). */
@@ -232,6 +232,22 @@ CVB_API int cvb_ln_bwd(const void* V, const void* X, const float* mean, const fl
 CVB_API int cvb_act_fwd(const void* X, void* Y, int64_t n, int kind, cvb_stream_t stream);
 CVB_API int cvb_act_bwd(const void* DY, const void* X, void* DX, int64_t n, int kind, cvb_stream_t stream);
 CVB_API int cvb_ln_stats(const void* X, int ldx, int64_t M, int C, float eps, float* mean, float* rstd, cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Per-step tail of the training loop (engine/training_engine.py:289-312) on FLAT fp32 buffers of n elements: GradScaler unscale +
+ * inf check, clip_grad_norm_, AdamW, GradScaler update -- two launches, all state on the device (CUDA-graph friendly).
+ *   stats : fp32[4], zero-initialised once; [0] sum of squares of the unscaled gradients, [1] # non-finite elements,
+ *           [2] 1/scale used by this step, [3] internal block counter (the step kernel clears [0], [1], [3] when it is done)
+ *   scale : fp32[2] = {loss scale, growth tracker}   (torch.amp.GradScaler: init 65536, growth 2.0, backoff 0.5, interval 2000)
+ *   step  : fp32[1] optimizer step count
+ * cvb_grad_norm must precede cvb_adamw_step.  AdamW follows torch.optim.AdamW exactly (decoupled weight decay p *= 1 - lr*wd[i],
+ * bias-corrected moments, eps added after the sqrt); weight_decay is per ELEMENT so the reference's two parameter groups
+ * (cvnets/misc/common.py:122-176: 1-D parameters are not decayed) need no segment table.  max_norm <= 0 disables clipping.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_grad_norm(const float* grads, int64_t n, const float* scale, float* stats, cvb_stream_t stream);
+CVB_API int cvb_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float max_norm, float* stats, float* scale, float* step, float growth_factor,
+                   float backoff_factor, int growth_interval, cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GlobalPool(mean) (cvnets/layers/global_pool.py:60-71) and small utilities

@@ -545,3 +545,40 @@ def test_ln_bwd(ops, M, C, res):
     close_stat(col[0], b.grad, "dbeta", rtol=5e-3)
     close_stat(col[1], g.grad, "dgamma", rtol=5e-3)
     close_stat(cs, DX.float().sum(0), "col_sum", rtol=5e-3)
+
+
+# ------------------------------------------------------------------------------------------------- fused training-step tail
+def test_flat_adamw_matches_torch_pipeline():
+    """cvb_grad_norm + cvb_adamw_step vs GradScaler.unscale_ -> clip_grad_norm_(10) -> torch.optim.AdamW -> GradScaler.update
+    (engine/training_engine.py:289-312), including a step with an inf gradient (skipped, scale backed off)."""
+    import copy
+    from ml_cvnets_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.BatchNorm1d(96), torch.nn.Linear(96, 33)).cuda()
+    ref = copy.deepcopy(net)
+    decay = [p for p in ref.parameters() if p.dim() > 1]
+    no_decay = [p for p in ref.parameters() if p.dim() == 1]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}], lr=2e-3, betas=(0.9, 0.999))
+    scaler = torch.amp.GradScaler("cuda", enabled=True, growth_interval=3)
+    scaler.scale(torch.zeros(1, device="cuda"))
+    tail = FlatAdamW(net, lr=2e-3, weight_decay=0.05, max_norm=10.0, growth_interval=3)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for it in range(6):
+        scale = float(scaler.get_scale())
+        assert abs(float(tail.loss_scale()) - scale) < 1e-3 * scale
+        for p_ours, p_ref in zip(net.parameters(), ref.parameters()):
+            grad = torch.randn(p_ref.shape, device="cuda", generator=g) * (30.0 if it == 1 else 1.0)  # it == 1: the clip is active
+            if it == 3 and p_ref.dim() == 2:
+                grad[0, 0] = float("inf")
+            p_ref.grad = grad * scale
+            p_ours.grad = (grad * scale).clone()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(list(ref.parameters()), 10.0)
+        scaler.step(opt)
+        scaler.update()
+        tail.step()
+        for p_ours, p_ref in zip(net.parameters(), ref.parameters()):
+            assert torch.isfinite(p_ours).all()
+            err = float((p_ours - p_ref).abs().max())
+            assert err <= 2e-6 + 1e-5 * float(p_ref.abs().max()), f"step {it}: max abs diff {err}"
+    assert abs(float(tail.step_count) - 5.0) < 1e-6  # one of the six steps was skipped
