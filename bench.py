@@ -52,7 +52,7 @@ def emit(line: dict):
         os.write(_JSON_FD, data)
 
 
-METRIC = "images/sec training step, MobileViTv2-1.0 bf16 256x256"
+METRIC = "images/sec training step, MobileViTv2-1.0 bf16 256x256"  # BASELINE.json metric (the --width 2.0 run is configs[3], named in config.workload)
 RES, NCLS = 256, 1000
 
 
@@ -112,50 +112,208 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU (reference) arm
-def cpu_training_throughput(batch, steps, warmup, threads=None):
-    """The reference's own nn.Module path restated by the oracle (fp32: the reference refuses AMP on CPU,
-    engine/utils.py:31-32), all host threads, AdamW(lr 2e-3, wd 0.05).  Returns (img/s, ms/step, cores)."""
-    from oracle import cvnets_oracle as O
-    # usable cores = the affinity mask (a container may expose 128 CPUs in os.cpu_count() but schedule far fewer)
-    cores = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    torch.set_num_threads(cores)
-    P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(1.0), 0))
-    params = [v for k, v in P.items() if v.requires_grad]
-    opt = torch.optim.AdamW(params, lr=2e-3, weight_decay=0.05)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 3, RES, RES, generator=g)
-    y = torch.randint(0, NCLS, (batch,), generator=g)
-    for _ in range(warmup):
-        O.training_step(P, opt, x, y)
+ALGO_MB_PER_IMAGE = {1.0: 190.8, 2.0: 380.5}  # 3 x (sum of conv/linear in+out activation elements) x 2 B
+
+
+def workload_config(width, B, world):
+    """The workload description BOTH arms print (identical dict => the driver's same_config check can pass)."""
+    cfg_no = {1.0: 1, 2.0: 3}.get(width)
+    return {"workload": f"MobileViTv2-{width:.1f} bf16 training step, synthetic ImageNet 256x256"
+                        + (f" (BASELINE.json configs[{cfg_no}])" if cfg_no is not None else ""),
+            "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "resolution": RES,
+            "l2": "activations per step (>7 GB at batch 128) exceed the 126 MB L2; no explicit flush"}
+
+
+def usable_cores():
+    """Cores this process may really use: the affinity mask capped by the cgroup CPU quota (a container can expose 128 CPUs in its mask
+    and be throttled to a handful; oversubscribing them made round 1's CPU numbers vary 21x between boxes)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                txt = f.read().split()
+            if path.endswith("cpu.max"):
+                quota, period = txt[0], float(txt[1])
+            else:
+                quota = txt[0]
+                with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                    period = float(f.read().split()[0])
+            if quota not in ("max", "-1"):
+                n = min(n, max(1, int(-(-float(quota) // period))))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
+class CpuArm:
+    """The reference's own nn.Module path restated by the oracle (fp32: the reference refuses AMP on CPU, engine/utils.py:31-32):
+    forward + CE(label_smoothing 0.1) + backward + AdamW(lr 2e-3, wd 0.05) on the host cores."""
+
+    def __init__(self, width=1.0):
+        from oracle import cvnets_oracle as O
+        self.O, self.width = O, width
+        self.P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(width), 0))
+        self.opt = torch.optim.AdamW([v for v in self.P.values() if v.requires_grad], lr=2e-3, weight_decay=0.05)
+        self.gen = torch.Generator().manual_seed(0)
+
+    def batch(self, b):
+        return torch.randn(b, 3, RES, RES, generator=self.gen), torch.randint(0, NCLS, (b,), generator=self.gen)
+
+    def step(self, x, y):
+        t0 = time.perf_counter()
+        self.O.training_step(self.P, self.opt, x, y, width_multiplier=self.width)
+        return time.perf_counter() - t0
+
+    def calibrate_threads(self, budget_s=45.0):
+        """Pick the torch thread count that is fastest on THIS box (hyper-threads / noisy neighbours make 'all of them' a bad default):
+        one warm + one timed 2-image step per candidate, smallest first, stop when it gets slower or the budget is spent."""
+        cores = usable_cores()
+        cands = sorted({min(cores, c) for c in (4, 8, 16, 32, 64, cores)})
+        x, y = self.batch(2)
+        t_start, best, log = time.perf_counter(), None, []
+        for c in cands:
+            torch.set_num_threads(c)
+            self.step(x, y)
+            dt = min(self.step(x, y), self.step(x, y)) if (time.perf_counter() - t_start) < 0.5 * budget_s else self.step(x, y)
+            ips = 2.0 / dt
+            log.append((c, round(ips, 3)))
+            if best is None or ips > best[1]:
+                best = (c, ips)
+            elif ips < 0.9 * best[1]:
+                break
+            if time.perf_counter() - t_start > budget_s:
+                break
+        torch.set_num_threads(best[0])
+        return best[0], best[1], cores, log
+
+
+def cpu_training_throughput(width, steps, warmup, budget_s, max_batch=128):
+    """Bounded CPU measurement: thread count calibrated, per-step sample sized so that warmup+steps fit in ``budget_s``; if even one
+    image per step does not fit, fewer steps are timed and the line says so.  Returns a dict."""
+    arm = CpuArm(width)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        O.training_step(P, opt, x, y)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return batch / dt, dt * 1e3, cores
+    threads, probe_ips, cores, calib = arm.calibrate_threads(budget_s=min(45.0, 0.4 * budget_s))
+    remaining = max(10.0, budget_s - (time.perf_counter() - t0))
+    total = max(1, steps + warmup)
+    batch = int(max(1, min(max_batch, probe_ips * remaining / total)))
+    per_step = batch / probe_ips
+    if per_step * total > remaining:  # even batch 1 is too slow for the requested step count: shrink the step count, honestly
+        steps_done = int(max(1, min(steps, remaining / per_step - 1)))
+        warm_done = 1 if warmup > 0 else 0
+    else:
+        steps_done, warm_done = max(1, steps), warmup
+    x, y = arm.batch(batch)
+    for _ in range(warm_done):
+        arm.step(x, y)
+    times, t_loop = [], time.perf_counter()
+    for i in range(steps_done):
+        times.append(arm.step(x, y))
+        if time.perf_counter() - t_loop > 1.5 * remaining and i + 1 < steps_done:  # hard stop: never run into the driver's limit
+            break
+    dt = sum(times) / len(times)
+    return {"ips": batch / dt, "ms": dt * 1e3, "threads": threads, "cores_available": cores, "batch": batch, "steps": len(times),
+            "warmup": warm_done, "calibration": calib}
 
 
 def run_reference_arm(args, rank, world):
-    """`--impl reference`: the reference's own CPU implementation of the path (oracle port), all host threads, EXACTLY --steps timed and
-    --warmup untimed steps; each step is a bounded sample of the per-GPU batch, sized from a one-step probe so that the whole run
-    ends within a few minutes on this box."""
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port), on the box's host cores, wall-clock bounded
+    (~2.5 minutes in total regardless of how slow the host is).  Under torchrun only rank 0 works."""
     if rank != 0:
         return
-    probe_ips, _, _ = cpu_training_throughput(2, 1, 0)
-    budget_s = 150.0
-    total_steps = max(1, args.steps + args.warmup)
-    batch = int(max(1, min(args.cpu_batch, probe_ips * budget_s / total_steps)))
-    ips, ms, cores = cpu_training_throughput(batch, max(1, args.steps), args.warmup)
+    r = cpu_training_throughput(args.width, args.steps, args.warmup, budget_s=args.cpu_budget)
+    sample = (f"batch {r['batch']} of the per-GPU batch of {args.batch}, fwd+bwd+AdamW, fp32, {r['threads']} torch threads "
+              f"(calibrated; {r['cores_available']} usable cores)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": max(1, args.steps),
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": r["ips"], "unit": "images/sec", "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": r["warmup"], "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32 (reference refuses AMP on CPU)", "data": "synthetic",
-        "config": {"workload": "MobileViTv2-1.0 training step, 256x256, CPU nn.Module path (oracle port of the Python reference)",
-                   "batch_sample": batch, "note": "bounded sample of the per-GPU batch of 128, sized from a one-step probe"},
-        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": f"batch {batch}, fwd+bwd+AdamW, fp32"},
-        "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args.width, args.batch, world),
+        "requested": {"steps": args.steps, "warmup": args.warmup},
+        "cpu_baseline": {"value": r["ips"], "unit": "images/sec", "cores": r["threads"], "kind": "port", "sample": sample,
+                         "thread_calibration_img_s": r["calibration"]},
+        "e2e": {"value": r["ips"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------- eager-GPU comparator
+def gpu_eager_baseline(dev, B, width, steps, warmup):
+    """SURVEY.md 8d / BASELINE.md 3: the reference modules' own GPU path = PyTorch eager (cuDNN / cuBLAS) under bf16 autocast +
+    channels_last + GradScaler + clip_grad_norm_(10) + AdamW(fused), same batch, same step definition (protocol of the reference's
+    main_benchmark.py:94-117 extended with backward + optimizer as engine/training_engine.py:257-312).  The reference cannot travel to
+    the GPU box, so its restatement (the oracle, pinned to the reference by tests/golden) stands in.  Timed eagerly (what a reference
+    user gets) and as ONE CUDA graph (host overhead removed: the stronger comparator)."""
+    from oracle import cvnets_oracle as O
+    P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(width), 0), device=dev)
+    for k, v in list(P.items()):
+        if v.dim() == 4:
+            P[k] = v.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    decay = [v for v in P.values() if v.requires_grad and v.dim() > 1]
+    no_decay = [v for v in P.values() if v.requires_grad and v.dim() <= 1]
+    params = decay + no_decay
+    gen = torch.Generator(device=dev).manual_seed(99)
+    x = torch.randn(B, 3, RES, RES, device=dev, generator=gen).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, NCLS, (B,), device=dev, generator=gen)
+
+    def make(capturable):
+        opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": no_decay, "weight_decay": 0.0}], lr=2e-3,
+                                betas=(0.9, 0.999), fused=True, capturable=capturable)
+        scaler = torch.amp.GradScaler("cuda", enabled=True)
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = O.mobilevit_v2_forward(P, x, width_multiplier=width, training=True)
+                loss = F.cross_entropy(logits, y, label_smoothing=0.1)
+            opt.zero_grad(set_to_none=True)
+            scaler.scale(loss).backward()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(params, 10.0)
+            scaler.step(opt)
+            scaler.update()
+            return loss
+        return step
+
+    def timed(fn, n):
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    out = {"what": "oracle restatement of the reference modules, torch eager bf16 autocast + channels_last + GradScaler + clip 10 + AdamW(fused)",
+           "per_gpu_batch": B, "unit": "images/sec"}
+    step = make(False)
+    for _ in range(max(3, warmup)):
+        step()
+    ms = timed(step, steps)
+    out.update({"value": B / (ms * 1e-3), "ms_per_step": ms, "steps": steps})
+    try:
+        gstep = make(True)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                gstep()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            gstep()
+        for _ in range(3):
+            g.replay()
+        gms = timed(g.replay, steps)
+        out.update({"graphed_value": B / (gms * 1e-3), "graphed_ms_per_step": gms})
+        del g
+    except Exception as e:  # the comparator must never take the bench line down
+        out["graphed_error"] = repr(e)[:200]
+    del P
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------- our arm
@@ -253,54 +411,35 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     torch.manual_seed(0 + rank)
     B = args.batch
-    model = m.MobileViTv2(m.default_opts(width_multiplier=1.0)).to(dev).train()
-    train_model = model
-    use_ddp_wrapper = world > 1 and args.no_graph
+    model = m.MobileViTv2(m.default_opts(width_multiplier=args.width)).to(dev).train()
     if args.no_pdl:
         ops.set_pdl_enabled(False)
-    if use_ddp_wrapper:
-        # eager multi-GPU path: the reference's own wrapper (main_train.py:90-96), bucketed all-reduce overlapped with backward
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        train_model = DDP(model, device_ids=[local_rank], output_device=local_rank, broadcast_buffers=True, gradient_as_bucket_view=True)
-    elif world > 1:
-        # graph-captured multi-GPU path: same semantics as DDP's gradient averaging (SUM / world of the fp32 gradients over
-        # NCCL), issued as ONE flat all-reduce after backward so that it is part of the captured CUDA graph.  19.6 MB per step
-        # (~0.1 ms on NVLink) -- overlap with backward would buy nothing here.  Initial weights: broadcast from rank 0.
-        # BatchNorm running statistics stay per-rank (DDP's per-forward buffer broadcast, SURVEY.md C2, is not replayed).
-        for t in list(model.parameters()) + list(model.buffers()):
-            torch.distributed.broadcast(t.data, src=0)
-    groups, _ = model.get_trainable_parameters(weight_decay=0.05, no_decay_bn_filter_bias=True)
-    params = [p for p in model.parameters()]
-    tail = None
-    if args.fused_tail and not use_ddp_wrapper:
-        # unscale + inf check + clip + AdamW + scaler update as two launches on flat buffers
-        from ml_cvnets_b200.optim import FlatAdamW
-        tail = FlatAdamW(model, lr=2e-3, betas=(0.9, 0.999), weight_decay=0.05, no_decay_bn_filter_bias=True, max_norm=10.0)
-
-        def flat_allreduce(g):
-            torch.distributed.all_reduce(g)
-            g.div_(world)
-    else:
-        opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999), fused=True, capturable=not args.no_graph)
+    use_graph = not args.no_graph and not args.profile_ops
+    ts = None
+    if args.torch_optim:
+        # A/B path (one GPU): the torch pipeline of round 1 -- F.cross_entropy, GradScaler, clip_grad_norm_, torch.optim.AdamW(fused)
+        assert world == 1, "--torch-optim is a single-GPU comparison path"
+        groups, _ = model.get_trainable_parameters(weight_decay=0.05, no_decay_bn_filter_bias=True)
+        params = [p for p in model.parameters()]
+        opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999), fused=True, capturable=use_graph)
         scaler = torch.amp.GradScaler("cuda", enabled=True)  # the reference enables it even for bf16 (main_train.py:114)
 
-    def step(x, y):
-        logits = train_model(x)
-        loss = F.cross_entropy(logits.float(), y, label_smoothing=0.1)
-        if tail is not None:
-            model.zero_grad(set_to_none=True)
-            (loss * tail.loss_scale()).backward()
-            tail.step(world, flat_allreduce if world > 1 else None)
+        def step(x, y):
+            logits = model(x)
+            loss = F.cross_entropy(logits.float(), y, label_smoothing=0.1)
+            opt.zero_grad(set_to_none=True)
+            scaler.scale(loss).backward()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(params, 10.0)
+            scaler.step(opt)
+            scaler.update()
             return loss
-        opt.zero_grad(set_to_none=True)
-        scaler.scale(loss).backward()
-        if world > 1 and not use_ddp_wrapper:
-            D.allreduce_mean_([p.grad for p in params], world)
-        scaler.unscale_(opt)
-        torch.nn.utils.clip_grad_norm_(params, 10.0)
-        scaler.step(opt)
-        scaler.update()
-        return loss
+    else:
+        # the product path: engine.TrainStep = forward + cvb_ce loss + backward writing into one flat gradient buffer + bucketed NCCL
+        # all-reduce overlapped with backward (N > 1) + two-launch unscale/clip/AdamW(+EMA)/scaler tail; no ATen kernel in the step
+        ts = m.TrainStep(model, lr=2e-3, betas=(0.9, 0.999), weight_decay=0.05, no_decay_bn_filter_bias=True, max_norm=10.0, label_smoothing=0.1,
+                         ema_momentum=(0.0005 if args.ema else None), n_buckets=args.buckets)
+        step = ts._step
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x_dev = torch.randn(B, 3, RES, RES, device=dev, generator=gen)
@@ -319,39 +458,42 @@ def run_ours(args, rank, world, local_rank):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step(x_dev, y_dev)
-    # ---- whole training step as ONE CUDA graph (single GPU): fwd + loss + bwd + unscale/clip + fused AdamW + scaler update.
-    # Kernel arguments (incl. TMA tensor maps) are baked at capture; inputs live in static buffers.  At N > 1 the flat NCCL
-    # gradient all-reduce is captured in the same graph.
-    use_graph = not args.no_graph and not args.profile_ops
-    graph = None
+    # ---- whole training step as ONE CUDA graph: fwd + loss + bwd (+ bucketed NCCL all-reduce at N > 1) + optimizer tail.
+    # Kernel arguments (incl. TMA tensor maps) are baked at capture; inputs live in static buffers.
     if use_graph:
-        static_x, static_y = x_dev.clone(), y_dev.clone()
-        torch.cuda.synchronize(dev)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                step(static_x, static_y)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        model.zero_grad(set_to_none=True)
-        launches_before_capture = ops.launch_count
-        with torch.cuda.graph(graph):
-            static_loss = step(static_x, static_y)
-        launches_per_graph = ops.launch_count - launches_before_capture
+        if ts is not None:
+            ts.eager_steps = max(args.warmup, 3)
+            ts.capture(x_dev, y_dev)
+            static_x, static_y = ts.static_inputs
+            launches_per_graph = ts.launches_per_step
+            run_step = ts.step
+        else:
+            static_x, static_y = x_dev.clone(), y_dev.clone()
+            torch.cuda.synchronize(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(static_x, static_y)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            model.zero_grad(set_to_none=True)
+            launches_before_capture = ops.launch_count
+            with torch.cuda.graph(graph):
+                static_loss = step(static_x, static_y)
+            launches_per_graph = ops.launch_count - launches_before_capture
 
-        def graph_step(x, y):
-            if x is not static_x:
-                static_x.copy_(x, non_blocking=True)
-                static_y.copy_(y, non_blocking=True)
-            graph.replay()
-            return static_loss
+            def run_step(x, y):
+                if x is not static_x:
+                    static_x.copy_(x, non_blocking=True)
+                    static_y.copy_(y, non_blocking=True)
+                graph.replay()
+                return static_loss
 
-        run_step = graph_step
-        for _ in range(2):
+        for _ in range(max(10, args.warmup)):  # settle the replay path (NCCL inside the graph needs more than a couple of replays)
             run_step(static_x, static_y)
     else:
         run_step = step
@@ -370,16 +512,20 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     timer.enabled = not args.no_kernel_timing and not use_graph
     launches0 = ops.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    marks[0].record()
+    for i in range(args.steps):
         if args.profile_ops:
             torch.cuda._sleep(int(0.25 * 1.9e9))  # diagnostics only: queue the step behind a spin so op timings exclude launch gaps
         loss = run_step(static_x, static_y) if use_graph else step(x_dev, y_dev)
         if args.profile_ops:
             torch.cuda.synchronize(dev)
-    ev1.record()
+        marks[i + 1].record()
+    ev0, ev1 = marks[0], marks[-1]
     sync_all()
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    step_stats = {"min": per_step[0], "median": per_step[len(per_step) // 2], "p90": per_step[min(len(per_step) - 1, int(0.9 * len(per_step)))],
+                  "max": per_step[-1], "note": "this rank's CUDA-event time of each timed step"}
     timer.enabled = False
     launches = (launches_per_graph * args.steps) if use_graph else (ops.launch_count - launches0)
     op_ms = optimer.summary(args.steps) if optimer is not None else None
@@ -473,22 +619,37 @@ def run_ours(args, rank, world, local_rank):
                 "kernel_ms_per_step": per_step_ms, "share_of_step": per_step_ms / ms_step,
                 "algorithmic_bytes_per_step": gbytes / nsteps_t, "tflops": gflops / (gms * 1e-3) / 1e12}
     cpu = None
-    if not args.no_cpu_baseline:
-        ips, cms, cores = cpu_training_throughput(args.cpu_batch, 1, 1)
-        cpu = {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port",
-               "sample": f"oracle fp32 training step, batch {args.cpu_batch} (of 128), 1 warm-up + 1 timed step ({cms:.0f} ms)"}
-    # whole-step roofline: SURVEY.md 8d algorithmic bytes: 190.8 MB / image
-    step_frac = (value / world) * 190.8e6 / 1e9 / peak
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_training_throughput(args.width, 3, 1, budget_s=min(60.0, args.cpu_budget))
+        cpu = {"value": r["ips"], "unit": "images/sec", "cores": r["threads"], "kind": "port",
+               "sample": (f"oracle fp32 training step, batch {r['batch']} (of {B}), {r['warmup']} warm-up + {r['steps']} timed steps "
+                          f"({r['ms']:.0f} ms each), {r['threads']} torch threads calibrated on this box ({r['cores_available']} usable cores)"),
+               "thread_calibration_img_s": r["calibration"]}
+    eager = None
+    if not args.no_eager_baseline and world == 1:
+        try:
+            eager = gpu_eager_baseline(dev, B, args.width, args.steps, args.warmup)
+            eager["ours_over_eager"] = value / eager["value"]
+            if "graphed_value" in eager:
+                eager["ours_over_graphed"] = value / eager["graphed_value"]
+        except Exception as e:
+            eager = {"error": repr(e)[:300]}
+    # whole-step roofline: SURVEY.md 8d algorithmic bytes per image
+    algo_mb = ALGO_MB_PER_IMAGE.get(args.width)
+    step_frac = (value / world) * algo_mb * 1e6 / 1e9 / peak if algo_mb else None
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "MobileViTv2-1.0 bf16 training step, synthetic ImageNet 256x256 (BASELINE.json configs[1])",
-                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_sync": ("none" if world == 1 else "DDP wrapper (eager)" if use_ddp_wrapper else "flat fp32 NCCL all-reduce inside the CUDA graph"), "optimizer": ("FlatAdamW: cvb_grad_norm + cvb_adamw_step (unscale, clip 10, AdamW, scaler update)" if tail is not None else "AdamW(fused) + GradScaler + clip_grad_norm 10"), "execution": "one CUDA graph per step" if use_graph else "eager launches",
-                   "l2": "activations per step (>7 GB) exceed the 126 MB L2; no explicit flush"},
+        "config": workload_config(args.width, B, world),
+        "impl_detail": {"grad_sync": ("none" if world == 1 else f"{args.buckets} flat fp32 NCCL all-reduce buckets issued as the backward of their modules finishes (overlapped), inside the CUDA graph"),
+                        "optimizer": ("engine.TrainStep: cvb_ce loss, gradients written into one flat buffer, cvb_grad_norm + cvb_adamw_step (unscale, clip 10, AdamW, scaler update"
+                                      + (", EMA 0.0005)" if args.ema else ")") if ts is not None else "torch: F.cross_entropy + GradScaler + clip_grad_norm_ 10 + AdamW(fused)"),
+                        "execution": "one CUDA graph per step" if use_graph else "eager launches"},
+        "step_ms": step_stats, "gpu_eager_baseline": eager,
         "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                   "ms_per_step": e2e_ms},
         "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-        "step_roofline": {"algorithmic_mb_per_image": 190.8, "frac_of_hbm_peak": step_frac, "peak_gbs": peak},
+        "step_roofline": {"algorithmic_mb_per_image": algo_mb, "frac_of_hbm_peak": step_frac, "peak_gbs": peak},
         "loss": final_loss,
     }
     if op_ms is not None:
@@ -504,12 +665,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (recipe: 128)")
-    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--width", type=float, default=1.0, help="MobileViTv2 width multiplier (1.0 = the metric config, 2.0 = BASELINE.json configs[3])")
+    ap.add_argument("--cpu-budget", type=float, default=120.0, help="wall-clock bound (s) of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="CUDA-event time per C-ABI entry point (diagnostics)")
-    ap.add_argument("--fused-tail", action="store_true", help="fused flat-buffer unscale/clip/AdamW/scaler tail (ml_cvnets_b200.optim.FlatAdamW)")
+    ap.add_argument("--torch-optim", action="store_true", help="A/B: torch loss/GradScaler/clip/AdamW instead of engine.TrainStep (1 GPU)")
+    ap.add_argument("--ema", action="store_true", help="EMA of the weights (momentum 0.0005, the recipe's ema.enable) fused into the optimizer tail")
+    ap.add_argument("--buckets", type=int, default=3, help="gradient all-reduce buckets (N > 1)")
     ap.add_argument("--no-pdl", action="store_true", help="diagnostics: plain stream-ordered launches instead of programmatic dependent launch")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying one captured CUDA graph (N=1)")
     args = ap.parse_args()

@@ -31,7 +31,7 @@ typedef void* cvb_stream_t; /* cudaStream_t */
 #define CVB_API
 #endif
 
-#define CVB_ABI_VERSION 6
+#define CVB_ABI_VERSION 7
 
 /* operand "load modes": the normalisation / activation of the PRODUCER layer is applied while the CONSUMER loads it
  * (training-mode BatchNorm cannot be fused into its own conv: SURVEY.md section 7 "hard parts"). */
@@ -243,11 +243,36 @@ CVB_API int cvb_ln_stats(const void* X, int ldx, int64_t M, int C, float eps, fl
  * cvb_grad_norm must precede cvb_adamw_step.  AdamW follows torch.optim.AdamW exactly (decoupled weight decay p *= 1 - lr*wd[i],
  * bias-corrected moments, eps added after the sqrt); weight_decay is per ELEMENT so the reference's two parameter groups
  * (cvnets/misc/common.py:122-176: 1-D parameters are not decayed) need no segment table.  max_norm <= 0 disables clipping.
+ * hp    : fp32[1] DEVICE scalar = learning rate (written by the scheduler each iteration: scheduler.update_lr, training_engine.py:246-249)
+ * grad_div : gradients are divided by loss_scale * grad_div (DDP's mean over ranks: grad_div = world size, main_train.py:90-96)
+ * ema / ema_momentum : optional fp32[n] moving average updated in the same pass, ema = ema*(1-momentum) + momentum*param
+ *           (cvnets/misc/averaging_utils.py:43-55; also on skipped steps, like the reference's per-iteration update); NULL = off
  * ------------------------------------------------------------------------------------------------------------- */
-CVB_API int cvb_grad_norm(const float* grads, int64_t n, const float* scale, float* stats, cvb_stream_t stream);
-CVB_API int cvb_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay, int64_t n, float lr,
-                   float beta1, float beta2, float eps, float max_norm, float* stats, float* scale, float* step, float growth_factor,
-                   float backoff_factor, int growth_interval, cvb_stream_t stream);
+CVB_API int cvb_grad_norm(const float* grads, int64_t n, const float* scale, float grad_div, float* stats, cvb_stream_t stream);
+CVB_API int cvb_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay, int64_t n,
+                   const float* hp, float beta1, float beta2, float eps, float max_norm, float* stats, float* scale, float* step,
+                   float growth_factor, float backoff_factor, int growth_interval, float* ema, float ema_momentum, cvb_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Classification loss of the step: F.cross_entropy(prediction, target, ignore_index, label_smoothing), mean over the non-ignored
+ * rows (loss_fn/classification/cross_entropy.py:74-95).  logits: bf16 [B, ld] (C valid columns); target: int64 [B].
+ * fwd: lse fp32[B] (saved), loss fp32[1], n_valid fp32[1].   bwd: dlogits bf16 [B, ldd] (columns >= C zeroed) =
+ * grad_out * grad_scale * (softmax - smoothed one-hot) / n_valid; grad_out / grad_scale are DEVICE scalars or NULL (= 1): the
+ * GradScaler's loss scale (engine/training_engine.py:287) multiplies here instead of in a separate kernel.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_ce_fwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, float* lse,
+               float* loss, float* n_valid, cvb_stream_t stream);
+CVB_API int cvb_ce_bwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, const float* lse,
+               const float* n_valid, const float* grad_out, const float* grad_scale, void* dlogits, int ldd, cvb_stream_t stream);
+
+/* Batched fp64 -> fp32 scatter: dst[i] = (float)src[i] for every descriptor (one launch per module backward: the fp64 statistics
+ * accumulators that ARE gradients -- GroupNorm dgamma/dbeta, bias gradients -- go straight into the flat gradient buffer). */
+typedef struct {
+  const double* src; float* dst; int n; int pad;
+} cvb_cast_desc;
+CVB_API int cvb_cast_f64_f32(const cvb_cast_desc* descs_device, int n_desc, int max_n, cvb_stream_t stream);
+/* cudaMemsetAsync(ptr, 0, bytes): the step's ONE workspace clear (a memset node under graph capture, not a kernel) */
+CVB_API int cvb_memset_zero(void* ptr, int64_t bytes, cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GlobalPool(mean) (cvnets/layers/global_pool.py:60-71) and small utilities

@@ -7,7 +7,11 @@ from .layers import (GELU, BatchNorm2d, ConvLayer2d, Dropout, GlobalPool, Identi
                      LinearLayer, LinearSelfAttention, MultiHeadAttention, Swish)
 from .models import MobileViTv2, default_opts, get_configuration  # noqa: F401
 from .modules import InvertedResidual, LinearAttnFFN, MobileViTBlockv2, TransformerEncoder  # noqa: F401
+from .engine import TrainStep, cross_entropy  # noqa: F401
+from .optim import FlatAdamW  # noqa: F401
+from .workspace import StepWorkspace  # noqa: F401
 
 __all__ = ["MobileViTv2", "default_opts", "get_configuration", "InvertedResidual", "LinearAttnFFN", "MobileViTBlockv2",
            "ConvLayer2d", "LinearSelfAttention", "BatchNorm2d", "LayerNorm2D_NCHW", "GlobalPool", "LinearLayer", "Swish",
-           "Dropout", "Identity", "TransformerEncoder", "MultiHeadAttention", "LayerNorm", "GELU"]
+           "Dropout", "Identity", "TransformerEncoder", "MultiHeadAttention", "LayerNorm", "GELU", "TrainStep", "cross_entropy", "FlatAdamW",
+           "StepWorkspace"]

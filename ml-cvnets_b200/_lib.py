@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcvnets_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # load modes / epilogue modes (mirror include/cvnets_b200.h)
 A_RAW, A_AFF, A_AFF_SILU, A_SILU, A_GN, A_BNB = 0, 1, 2, 3, 4, 5
@@ -76,6 +76,10 @@ class PrepDesc(Structure):
                 ("dst_rows", c_int), ("kind", c_int), ("rot", c_int)]
 
 
+class CastDesc(Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("n", c_int), ("pad", c_int)]
+
+
 _SIGS = {
     "cvb_last_error": (c_char_p, []),
     "cvb_abi_version": (c_int, []),
@@ -111,9 +115,14 @@ _SIGS = {
     "cvb_act_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "cvb_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "cvb_ln_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p]),
-    "cvb_grad_norm": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "cvb_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_float, c_void_p,
-                               c_void_p, c_void_p, c_float, c_float, c_int, c_void_p]),
+    "cvb_grad_norm": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p]),
+    "cvb_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float, c_float, c_float, c_void_p,
+                               c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_float, c_void_p]),
+    "cvb_ce_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cvb_ce_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                           c_void_p]),
+    "cvb_cast_f64_f32": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "cvb_memset_zero": (c_int, [c_void_p, c_int64, c_void_p]),
     "cvb_global_pool_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cvb_global_pool_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cvb_col_sum": (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p]),

@@ -4,18 +4,22 @@
 //                      reference, cvnets/optim/adamw.py), GradScaler.step "skip on inf" and GradScaler.update (growth / backoff)
 // State (all device resident, so the whole step stays one CUDA graph): stats[0] = sum of squares of the unscaled gradients,
 // stats[1] = number of non-finite gradient elements, stats[2] = 1 / loss_scale used by this step; scale[0] = loss scale,
-// scale[1] = growth tracker; step[0] = optimizer step count (fp32).
+// scale[1] = growth tracker; step[0] = optimizer step count (fp32); hp[0] = learning rate (device scalar: a scheduler writes it every
+// iteration, scheduler.update_lr at engine/training_engine.py:246-249, without re-capturing the step's CUDA graph).
+// Optional: the EMA of the weights (cvnets/misc/averaging_utils.py:43-55: ema = ema*(1-momentum) + momentum*param, every iteration)
+// rides in the same pass, and grad_div folds DDP's division by the world size into the unscale.
 #include "common.cuh"
 
 namespace {
 
 constexpr int ONT = 256;
 
-__global__ void __launch_bounds__(ONT) grad_norm_kernel(const float* __restrict__ g, int64_t n, const float* __restrict__ scale, float* stats) {
+__global__ void __launch_bounds__(ONT) grad_norm_kernel(const float* __restrict__ g, int64_t n, const float* __restrict__ scale, float grad_div,
+                                                        float* stats) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_sq[ONT / 32], s_bad[ONT / 32];
-  const float inv = 1.0f / scale[0];
+  const float inv = 1.0f / (scale[0] * grad_div);
   float sq = 0.f, bad = 0.f;
   const int64_t nvec = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * ONT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * ONT) {
@@ -45,13 +49,18 @@ __global__ void __launch_bounds__(ONT) grad_norm_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(ONT) adamw_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                                         const float* __restrict__ wd, int64_t n, float lr, float beta1, float beta2, float eps,
-                                                         float max_norm, float* stats, float* scale, float* step, float growth, float backoff,
-                                                         int growth_interval) {
+                                                         const float* __restrict__ wd, int64_t n, const float* __restrict__ hp, float beta1, float beta2,
+                                                         float eps, float max_norm, float* stats, float* scale, float* step, float growth,
+                                                         float backoff, int growth_interval, float* __restrict__ ema, float ema_momentum) {
   pdl_wait();
   pdl_trigger();
   const bool skip = stats[1] > 0.f;  // GradScaler.step: no optimizer step when any gradient is inf / nan
-  if (!skip) {
+  const float lr = hp[0];
+  if (skip) {
+    if (ema != nullptr)  // the reference updates the EMA every iteration, also when GradScaler skipped the optimizer step
+      for (int64_t i = (int64_t)blockIdx.x * ONT + threadIdx.x; i < n; i += (int64_t)gridDim.x * ONT)
+        ema[i] = fmaf(ema[i], 1.0f - ema_momentum, ema_momentum * p[i]);
+  } else {
     const float inv = stats[2];
     const float norm = sqrtf(stats[0]);
     float coef = max_norm / (norm + 1e-6f);  // torch.nn.utils.clip_grad_norm_: clip_coef clamped to 1
@@ -71,6 +80,7 @@ __global__ void __launch_bounds__(ONT) adamw_step_kernel(float* __restrict__ p, 
       p[i] = pi;
       m[i] = mi;
       v[i] = vi;
+      if (ema != nullptr) ema[i] = fmaf(ema[i], 1.0f - ema_momentum, ema_momentum * pi);
     }
   }
   // every block has read stats / step above; the LAST block to finish updates the scalar state and clears the statistics
@@ -100,26 +110,26 @@ __global__ void __launch_bounds__(ONT) adamw_step_kernel(float* __restrict__ p, 
 
 }  // namespace
 
-extern "C" int cvb_grad_norm(const float* grads, int64_t n, const float* scale, float* stats, cvb_stream_t stream) {
-  CVB_CHECK(grads && scale && stats && n > 0 && cvb_aligned16(grads), "cvb_grad_norm: bad arguments");
+extern "C" int cvb_grad_norm(const float* grads, int64_t n, const float* scale, float grad_div, float* stats, cvb_stream_t stream) {
+  CVB_CHECK(grads && scale && stats && n > 0 && grad_div > 0.f && cvb_aligned16(grads), "cvb_grad_norm: bad arguments");
   int blocks = (int)((n / 4 + ONT - 1) / ONT);
   const int cap = 4 * cvb_num_sms();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  CVB_CUDA(cvb_launch(grad_norm_kernel, blocks, ONT, 0, static_cast<cudaStream_t>(stream), grads, n, scale, stats));
+  CVB_CUDA(cvb_launch(grad_norm_kernel, blocks, ONT, 0, static_cast<cudaStream_t>(stream), grads, n, scale, grad_div, stats));
   CVB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int cvb_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay, int64_t n, float lr,
-                              float beta1, float beta2, float eps, float max_norm, float* stats, float* scale, float* step, float growth_factor,
-                              float backoff_factor, int growth_interval, cvb_stream_t stream) {
-  CVB_CHECK(params && grads && exp_avg && exp_avg_sq && weight_decay && stats && scale && step && n > 0, "cvb_adamw_step: bad arguments");
+extern "C" int cvb_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay, int64_t n,
+                              const float* hp, float beta1, float beta2, float eps, float max_norm, float* stats, float* scale, float* step,
+                              float growth_factor, float backoff_factor, int growth_interval, float* ema, float ema_momentum, cvb_stream_t stream) {
+  CVB_CHECK(params && grads && exp_avg && exp_avg_sq && weight_decay && hp && stats && scale && step && n > 0, "cvb_adamw_step: bad arguments");
   int blocks = (int)((n + ONT - 1) / ONT);
   const int cap = 8 * cvb_num_sms();
   if (blocks > cap) blocks = cap;
-  CVB_CUDA(cvb_launch(adamw_step_kernel, blocks, ONT, 0, static_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, weight_decay, n, lr, beta1,
-                      beta2, eps, max_norm, stats, scale, step, growth_factor, backoff_factor, growth_interval));
+  CVB_CUDA(cvb_launch(adamw_step_kernel, blocks, ONT, 0, static_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, weight_decay, n, hp, beta1,
+                      beta2, eps, max_norm, stats, scale, step, growth_factor, backoff_factor, growth_interval, ema, ema_momentum));
   CVB_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,137 @@
+"""The reference's training iteration (engine/training_engine.py:236-312) for the hot-path models, as ONE replayable CUDA graph:
+
+    forward -> cross entropy (label smoothing) -> backward (weight gradients written straight into a flat buffer)
+            -> [data parallel: bucketed all-reduce of that buffer over NCCL, overlapped with the rest of the backward]
+            -> GradScaler unscale + inf check + clip_grad_norm_ + AdamW (+ EMA) + GradScaler update   (two launches)
+
+``TrainStep`` is host code only -- every kernel it launches is one of the library's (include/cvnets_b200.h); there is no ATen kernel
+inside the step (zero-fills are memset nodes, the loss is cvb_ce_*).  Semantics follow the reference: per-GPU BatchNorm statistics
+(``batch_norm``, not ``sync_batch_norm``), DDP's gradient mean over ranks and per-step buffer broadcast from rank 0
+(main_train.py:90-96), the two AdamW parameter groups of cvnets/misc/common.py:122-176, max-norm clipping at
+``common.grad_clip`` (10.0 in the recipe, config/classification/imagenet/mobilevit_v2.yaml:9), EMA as averaging_utils.py:43-55.
+
+    step = TrainStep(model, lr=2e-3, weight_decay=0.05, max_norm=10.0, label_smoothing=0.1)
+    step.capture(x_example, y_example)        # optional: whole step as one CUDA graph (inputs are copied into static buffers)
+    for x, y in loader:
+        step.set_lr(scheduler_lr)             # device scalar: schedulers keep working under replay
+        loss = step(x, y)                     # device tensor; no host sync
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from . import functional as Fn
+from . import ops
+from .optim import FlatAdamW
+from .workspace import StepWorkspace
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, label_smoothing: float = 0.0, ignore_index: int = -1,
+                  _cfg: Optional[SimpleNamespace] = None) -> torch.Tensor:
+    """F.cross_entropy(logits, target, ignore_index=..., label_smoothing=...) with mean reduction (the reference's classification loss,
+    loss_fn/classification/cross_entropy.py:74-95) on the library's kernels; returns a 0-dim fp32 tensor."""
+    if not logits.is_cuda:
+        raise RuntimeError("cross_entropy: ml-cvnets_b200 runs on CUDA only (no CPU fallback)")
+    cfg = _cfg if _cfg is not None else SimpleNamespace(label_smoothing=float(label_smoothing), ignore_index=int(ignore_index), scale=None)
+    return Fn.CrossEntropyFn.apply(logits, target, cfg)
+
+
+class TrainStep:
+    def __init__(self, model: torch.nn.Module, *, lr: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
+                 no_decay_bn_filter_bias: bool = True, max_norm: float = 10.0, label_smoothing: float = 0.1, ignore_index: int = -1,
+                 ema_momentum: Optional[float] = None, init_scale: float = 65536.0, growth_interval: int = 2000,
+                 process_group=None, data_parallel: Optional[bool] = None, n_buckets: int = 3, broadcast_buffers: bool = True):
+        import torch.distributed as dist
+        self.model = model
+        self.ws = StepWorkspace(model)
+        self.opt = FlatAdamW(model, self.ws, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, no_decay_bn_filter_bias=no_decay_bn_filter_bias,
+                             max_norm=max_norm, init_scale=init_scale, growth_interval=growth_interval, ema_momentum=ema_momentum)
+        if data_parallel is None:
+            data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        self.world = 1
+        self.broadcast_buffers = broadcast_buffers
+        if data_parallel:
+            self.ws.enable_ddp(process_group, n_buckets)
+            self.world = self.ws.world
+            # DDP's constructor broadcasts rank 0's parameters and buffers (torch DistributedDataParallel._sync_module_states)
+            dist.broadcast(self.opt.flat_p, src=0, group=process_group)
+            if self.opt.ema is not None:
+                self.opt.ema.copy_(self.opt.flat_p)
+            self.ws.broadcast_buffers()
+        self.loss_cfg = SimpleNamespace(label_smoothing=float(label_smoothing), ignore_index=int(ignore_index), scale=self.opt.loss_scale())
+        self._one = torch.ones((), device=self.ws.device, dtype=torch.float32)
+        self._graph = None
+        self._static = None
+        self.eager_steps = 0
+
+    # ---- scheduler / checkpoint hooks
+    def set_lr(self, lr: float) -> None:
+        self.opt.set_lr(lr)
+
+    def state_dict(self):
+        return self.opt.state_dict()
+
+    def load_state_dict(self, sd):
+        self.opt.load_state_dict(sd)
+
+    # ---- one iteration, eager launches
+    def _step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        ws = self.ws
+        ws.begin_step()
+        if self.world > 1 and self.broadcast_buffers:
+            ws.broadcast_buffers()
+        ws.active = True
+        try:
+            logits = self.model(x)
+            loss = cross_entropy(logits, y, _cfg=self.loss_cfg)
+            torch.autograd.backward(loss, grad_tensors=self._one)
+        finally:
+            ws.active = False
+        ws.finish_reduce()
+        self.opt.step(grad_div=float(self.world))
+        return loss
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self._graph is None:
+            self.eager_steps += 1
+            return self._step(x, y)
+        sx, sy, sloss = self._static
+        if x is not sx:
+            sx.copy_(x, non_blocking=True)
+        if y is not sy:
+            sy.copy_(y, non_blocking=True)
+        self._graph.replay()
+        ops.invalidate_prepared_weights()
+        return sloss
+
+    __call__ = step
+
+    # ---- whole step as one CUDA graph
+    def capture(self, x: torch.Tensor, y: torch.Tensor, warmup: int = 3):
+        """Warm up eagerly (workspace planning needs two steps), then capture fwd + loss + bwd (+ all-reduce) + optimizer tail."""
+        assert self._graph is None, "already captured"
+        dev = self.ws.device
+        sx, sy = x.to(dev).clone(), y.to(dev).clone()
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(0, max(warmup, 3) - self.eager_steps)):
+                self._step(sx, sy)
+                self.eager_steps += 1
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count
+        with torch.cuda.graph(graph):
+            sloss = self._step(sx, sy)
+        self.launches_per_step = ops.launch_count - n0
+        self._graph, self._static = graph, (sx, sy, sloss)
+        return self
+
+    @property
+    def static_inputs(self):
+        return None if self._static is None else self._static[:2]

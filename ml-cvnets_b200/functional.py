@@ -15,6 +15,7 @@ from typing import List
 import torch
 
 from . import ops
+from .workspace import Arena
 from .ops import A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU, E_GN_BWD, E_SILU_BWD, E_STORE
 
 BF16 = torch.bfloat16
@@ -53,43 +54,6 @@ def _bn_forward(stats, count, gamma, beta, c):
     return ops.bn_eval_scale_shift(gamma, beta, c.running_mean, c.running_var, c.eps)
 
 
-class _Arena:
-    """One zero-filled fp32 and one fp64 buffer per backward pass (two memsets instead of ~100 tiny fills); slices are handed
-    out as accumulators / gradients.  Fresh per call: autograd may keep the returned gradient views alive."""
-
-    def __init__(self, device, n32: int, n64: int):
-        self.b32 = torch.zeros(n32, device=device, dtype=torch.float32)
-        self.b64 = torch.zeros(n64, device=device, dtype=torch.float64)
-        self.o32 = self.o64 = 0
-        self.c32 = None
-
-    def f32(self, *shape: int) -> torch.Tensor:
-        n = 1
-        for d in shape:
-            n *= d
-        v = self.b32[self.o32:self.o32 + n].view(*shape)
-        self.o32 += (n + 3) // 4 * 4
-        assert self.o32 <= self.b32.numel(), "fp32 arena exhausted"
-        return v
-
-    def f64(self, *shape: int) -> torch.Tensor:
-        n = 1
-        for d in shape:
-            n *= d
-        v = self.b64[self.o64:self.o64 + n].view(*shape)
-        self.o64 += (n + 1) // 2 * 2
-        assert self.o64 <= self.b64.numel(), "fp64 arena exhausted"
-        return v
-
-    def cast(self):
-        """fp64 statistics -> fp32 (ONE conversion kernel); call after the last kernel that accumulates into them."""
-        self.c32 = self.b64.float()
-
-    def as_f32(self, v64: torch.Tensor) -> torch.Tensor:
-        o = v64.storage_offset()
-        return self.c32[o:o + v64.numel()].view(v64.shape)
-
-
 def _zeros64(device, *sizes: int) -> List[torch.Tensor]:
     """One memset for all fp64 [2, n] accumulators of a pass."""
     buf = torch.zeros(2 * sum(sizes), device=device, dtype=torch.float64)
@@ -100,6 +64,78 @@ def _zeros64(device, *sizes: int) -> List[torch.Tensor]:
     return out
 
 
+def _ws_of(cfg, params):
+    """The module's StepWorkspace if gradients are to be written in place (inside TrainStep, every parameter registered), else None."""
+    ws = getattr(cfg, "ws", None)
+    if ws is None or not ws.active:
+        return None
+    return ws if all(ws.has(p) for p in params) else None
+
+
+def _fwd_arena(cfg, device, n64: int) -> Arena:
+    """fp64 statistics accumulators of one forward: one memset per module, or a slice of the step arena (no launch at all)."""
+    ws = getattr(cfg, "ws", None)
+    if ws is not None and ws.active:
+        return ws.arena((id(cfg), "fwd"), 0, n64)
+    return Arena(device, 0, n64)
+
+
+class _Dst:
+    """Where the parameter gradients of one module backward go.
+
+    Workspace mode (inside ``engine.TrainStep``): straight into the flat gradient buffer -- ``p.grad`` is a view of it -- and the autograd
+    function returns ``None`` for the parameters (no AccumulateGrad kernels, no gather for the optimizer / all-reduce).  Otherwise: fresh
+    slices of a per-call arena, returned to autograd as usual (what a plain ``loss.backward()`` on the drop-in modules gets)."""
+
+    def __init__(self, cfg, params, device, n32: int, n64: int, use_ws: bool):
+        self.params = list(params)
+        self.ws = _ws_of(cfg, self.params) if use_ws else None
+        self.key = (id(cfg), "bwd")
+        self.ar = self.ws.arena(self.key, n32, n64) if self.ws is not None else Arena(device, n32, n64)
+        self.grads = [None] * len(self.params)
+        self.late = []
+
+    def mat(self, i: int, rows: int, cols: int) -> torch.Tensor:
+        """zeroed fp32 [rows, cols] accumulator that IS the gradient of params[i] (same memory layout)."""
+        if self.ws is not None:
+            return self.ws.gview(self.params[i]).view(rows, cols)
+        v = self.ar.f32(rows, cols)
+        self.grads[i] = v.view(self.params[i].shape)
+        return v
+
+    def pair(self, i: int, j: int):
+        """(dgamma, dbeta) destinations for bn_bwd_finalize, or None (it allocates)."""
+        if self.ws is not None:
+            return (self.ws.gview(self.params[i]), self.ws.gview(self.params[j]))
+        return None
+
+    def set_pair(self, i: int, j: int, dgb):
+        if self.ws is None:
+            self.grads[i], self.grads[j] = dgb[0], dgb[1]
+
+    def unprep(self, i: int, src, rows: int, cols: int, lds: int, kind: int, rot: int = 0, side: bool = False):
+        """kernel-layout gradient (rotated / padded / tap-major) -> the parameter's own layout."""
+        out = self.ws.gview(self.params[i]).view((rows, cols) if kind != 3 else (rows,)) if self.ws is not None else None
+        g = ops.unprep_grad(src, rows, cols, lds, kind, rot=rot, side=side, out=out)
+        if self.ws is None:
+            self.grads[i] = g.view(self.params[i].shape)
+
+    def late64(self, i: int, v64: torch.Tensor):
+        """fp64 accumulator that is a gradient: converted after the last kernel that accumulates into it."""
+        self.late.append((i, v64))
+
+    def finish(self):
+        if self.ws is not None:
+            self.ws.scatter64(self.key, [(v, self.ws.gview(self.params[i]).view(v.shape)) for i, v in self.late])
+            self.ws.unit_done(self.params)
+            return (None,) * len(self.params)
+        if self.late:
+            self.ar.cast()
+            for i, v in self.late:
+                self.grads[i] = self.ar.as_f32(v).view(self.params[i].shape)
+        return tuple(self.grads)
+
+
 # ==================================================================================================================
 # Stem: ConvLayer2d(3 -> C0, k3, s2) + BN + SiLU  (cvnets/models/classification/mobilevit_v2.py:37-45)
 # ==================================================================================================================
@@ -108,17 +144,20 @@ class StemFn(torch.autograd.Function):
     def forward(ctx, x, cfg, w, gamma, beta):
         B, _, H, W = x.shape
         C0 = w.shape[0]
+        if H % 2 or W % 2:
+            raise NotImplementedError("stem: odd H or W (the reference's 3x3/s2/p1 conv gives ceil(H/2)) is not implemented")
         Ho, Wo = H // 2, W // 2
         M = B * Ho * Wo
         xin = x if x.dtype == torch.float32 else x.float()
         A0 = ops.stem_im2col(xin)
         Ws = cfg.prep.get(cfg.i_w)
-        (st,) = _zeros64(x.device, C0)
+        st = _fwd_arena(cfg, x.device, 2 * C0 + 8).f64(2, C0)
         y = ops.pw_gemm(A0, Ws, C0, col_stats=st if cfg.bn.batch_stats else None)
         bn = _bn_forward(st, M, gamma, beta, cfg.bn)
         out = ops.bn_apply(y, bn, act=True)
-        ctx.cfg, ctx.dims = cfg, (B, Ho, Wo, C0, M)
+        ctx.cfg, ctx.dims, ctx.ev = cfg, (B, Ho, Wo, C0, M), (not cfg.bn.batch_stats,)
         ctx.saved = (A0, y, bn)
+        ctx.plist = cfg.plist
         ctx.save_for_backward(gamma)
         return to_4d(out, B, Ho, Wo)
 
@@ -129,13 +168,15 @@ class StemFn(torch.autograd.Function):
         A0, y, bn = ctx.saved
         (gamma,) = ctx.saved_tensors
         g2 = as_2d(to_bf16_cl(gout))
-        (sd,) = _zeros64(g2.device, C0)
+        D = _Dst(cfg, ctx.plist, g2.device, C0 * 32 + 64, 2 * C0 + 16, True)
+        sd = D.ar.f64(2, C0)
         dz = ops.bn_bwd_reduce(g2, y, sd, bn, act=True, store_dz=True)
-        dgb, coef = ops.bn_bwd_finalize(sd, M, gamma, bn, eval_mode=not cfg.bn.batch_stats)
-        dW = ops.pw_wgrad_side(dz, A0, C0, 32, g_mode=A_BNB, G2=y, g_p=coef)
-        dw = ops.unprep_grad(dW, C0, 27, 32, 0, side=True).view(C0, 3, 3, 3)
+        dgb, coef = ops.bn_bwd_finalize(sd, M, gamma, bn, eval_mode=ctx.ev[0], out=D.pair(1, 2))
+        D.set_pair(1, 2, dgb)
+        dW = ops.pw_wgrad_side(dz, A0, C0, 32, g_mode=A_BNB, G2=y, g_p=coef, dW=D.ar.f32(C0, 32))
+        D.unprep(0, dW, C0, 27, 32, 0, side=True)
         ops.join_side()
-        return None, None, dw, dgb[0], dgb[1]
+        return (None, None) + D.finish()
 
 
 # ==================================================================================================================
@@ -150,17 +191,19 @@ class InvertedResidualFn(torch.autograd.Function):
         M, M2 = B * H * W, B * Ho * Wo
         x2 = as_2d(x)
         P = cfg.prep
-        st1, st2, st3 = _zeros64(x.device, hid, hid, cout)
-        bs = cfg.bn[0].batch_stats
-        y1 = ops.pw_gemm(x2, P.get(cfg.i_w1), hid, col_stats=st1 if bs else None)
+        fa = _fwd_arena(cfg, x.device, 2 * (2 * hid + cout) + 16)
+        st1, st2, st3 = fa.f64(2, hid), fa.f64(2, hid), fa.f64(2, cout)
+        bs = [c.batch_stats for c in cfg.bn]  # per layer: individual BatchNorms may be frozen (base_model.py:139-165)
+        y1 = ops.pw_gemm(x2, P.get(cfg.i_w1), hid, col_stats=st1 if bs[0] else None)
         bn1 = _bn_forward(st1, M, g1, b1, cfg.bn[0])
-        y2 = ops.dw_fwd(y1, B, H, W, hid, s, P.get(cfg.i_wd), x_mode=A_AFF_SILU, x_p=(bn1[2], bn1[3]), col_stats=st2 if bs else None)
+        y2 = ops.dw_fwd(y1, B, H, W, hid, s, P.get(cfg.i_wd), x_mode=A_AFF_SILU, x_p=(bn1[2], bn1[3]), col_stats=st2 if bs[1] else None)
         bn2 = _bn_forward(st2, M2, g2, b2, cfg.bn[1])
-        y3 = ops.pw_gemm(y2, P.get(cfg.i_w3), cout, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), col_stats=st3 if bs else None)
+        y3 = ops.pw_gemm(y2, P.get(cfg.i_w3), cout, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), col_stats=st3 if bs[2] else None)
         bn3 = _bn_forward(st3, M2, g3, b3, cfg.bn[2])
         out = ops.bn_apply(y3, bn3, act=False, R=x2 if cfg.residual else None)
-        ctx.cfg, ctx.dims = cfg, (B, Cin, H, W, Ho, Wo)
+        ctx.cfg, ctx.dims, ctx.ev = cfg, (B, Cin, H, W, Ho, Wo), tuple(not b for b in bs)  # BN modes snapshotted for backward
         ctx.saved = (x2, y1, bn1, y2, bn2, y3, bn3)
+        ctx.plist = cfg.plist
         ctx.save_for_backward(g1, g2, g3)
         return to_4d(out, B, Ho, Wo)
 
@@ -173,28 +216,32 @@ class InvertedResidualFn(torch.autograd.Function):
         x2, y1, bn1, y2, bn2, y3, bn3 = ctx.saved
         g1, g2, g3 = ctx.saved_tensors
         P = cfg.prep
-        ev = not cfg.bn[0].batch_stats
+        ev = ctx.ev
         dout = as_2d(to_bf16_cl(gout))
-        ar = _Arena(dout.device, cout * hid + hid * Cin + 9 * hid + 64, 2 * (cout + 2 * hid) + 16)
+        # parameter order: (w1, g1, b1, wd, g2, b2, w3, g3, b3)
+        D = _Dst(cfg, ctx.plist, dout.device, cout * hid + hid * Cin + 9 * hid + 64, 2 * (cout + 2 * hid) + 16, True)
+        ar = D.ar
         sd3, sd2, sd1 = ar.f64(2, cout), ar.f64(2, hid), ar.f64(2, hid)
         # red_1x1 + BN3 (no activation): dz3 = dout
         ops.bn_bwd_reduce(dout, y3, sd3)
-        dgb3, c3 = ops.bn_bwd_finalize(sd3, M2, g3, bn3, ev)
+        dgb3, c3 = ops.bn_bwd_finalize(sd3, M2, g3, bn3, ev[2], out=D.pair(7, 8))
+        D.set_pair(7, 8, dgb3)
         dz2 = ops.pw_gemm(dout, P.get(cfg.i_w3t), hid, K=cout, a_mode=A_BNB, A2=y3, a_p=c3, e_mode=E_SILU_BWD, Y=y2,
                           e_p=(bn2[2], bn2[3]), col_stats=sd2)
-        dW3 = ops.pw_wgrad_side(dout, y2, cout, hid, g_mode=A_BNB, G2=y3, g_p=c3, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), dW=ar.f32(cout, hid))
+        ops.pw_wgrad_side(dout, y2, cout, hid, g_mode=A_BNB, G2=y3, g_p=c3, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), dW=D.mat(6, cout, hid))
         # depthwise + BN2
-        dgb2, c2 = ops.bn_bwd_finalize(sd2, M2, g2, bn2, ev)
+        dgb2, c2 = ops.bn_bwd_finalize(sd2, M2, g2, bn2, ev[1], out=D.pair(4, 5))
+        D.set_pair(4, 5, dgb2)
         dz1, dWt = ops.dw_bwd(dz2, y1, B, H, W, hid, s, P.get(cfg.i_wd), g_mode=A_BNB, Y2=y2, g_p=c2, x_mode=A_AFF_SILU,
                               x_p=(bn1[2], bn1[3]), col_stats=sd1, dWt=ar.f32(9, hid))
-        dWd = ops.unprep_grad(dWt, hid, 9, hid, 2).view(hid, 1, 3, 3)
+        D.unprep(3, dWt, hid, 9, hid, 2)
         # exp_1x1 + BN1
-        dgb1, c1 = ops.bn_bwd_finalize(sd1, M, g1, bn1, ev)
+        dgb1, c1 = ops.bn_bwd_finalize(sd1, M, g1, bn1, ev[0], out=D.pair(1, 2))
+        D.set_pair(1, 2, dgb1)
         dx = ops.pw_gemm(dz1, P.get(cfg.i_w1t), Cin, K=hid, a_mode=A_BNB, A2=y1, a_p=c1, R=dout if cfg.residual else None)
-        dW1 = ops.pw_wgrad_side(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, dW=ar.f32(hid, Cin))
+        ops.pw_wgrad_side(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, dW=D.mat(0, hid, Cin))
         ops.join_side()
-        return (to_4d(dx, B, H, W), None, dW1.view(hid, Cin, 1, 1), dgb1[0], dgb1[1], dWd, dgb2[0], dgb2[1],
-                dW3.view(cout, hid, 1, 1), dgb3[0], dgb3[1])
+        return (to_4d(dx, B, H, W), None) + D.finish()
 
 
 # ==================================================================================================================
@@ -213,12 +260,13 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         x2 = as_2d(x)
         wd0, g0, b0, wl = params[:4]
         gL, bL, wp, gp, bp = params[4 + 12 * n:]
-        bs = cfg.bn[0].batch_stats
-        st0, stp = _zeros64(x.device, C, C)
-        samp = _zeros64(x.device, *([B] * (2 * n + 1)))
+        bs = [c.batch_stats for c in cfg.bn]
+        fa = _fwd_arena(cfg, x.device, 4 * C + (2 * n + 1) * (2 * B + 2) + 16)
+        st0, stp = fa.f64(2, C), fa.f64(2, C)
+        samp = [fa.f64(2, B) for _ in range(2 * n + 1)]
         gcount = HW * d
         # local_rep: dw3x3 + BN + SiLU -> 1x1 (C -> d)
-        y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), col_stats=st0 if bs else None)
+        y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), col_stats=st0 if bs[0] else None)
         bn0 = _bn_forward(st0, M, g0, b0, cfg.bn[0])
         X = ops.pw_gemm(y0, P.get(cfg.i_wl), d, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), samp_stats=samp[0], rows_per_sample=HW)
         blocks = []
@@ -237,11 +285,12 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             X = X2
         gnL = ops.gn_finalize(samp[2 * n], gcount, cfg.gn_eps)
         yp = ops.pw_gemm(X, P.get(cfg.i_wp), C, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]), rows_per_sample=HW,
-                         col_stats=stp if bs else None)
+                         col_stats=stp if bs[1] else None)
         bnp = _bn_forward(stp, M, gp, bp, cfg.bn[1])
         out = ops.bn_apply(yp, bnp, act=False)
-        ctx.cfg, ctx.dims = cfg, (B, C, H, W)
+        ctx.cfg, ctx.dims, ctx.ev = cfg, (B, C, H, W), tuple(not b for b in bs)
         ctx.saved = (x2, y0, bn0, blocks, X, gnL, yp, bnp)
+        ctx.plist = cfg.plist
         ctx.save_for_backward(*params)
         return to_4d(out, B, H, W)
 
@@ -257,27 +306,27 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         x2, y0, bn0, blocks, XL, gnL, yp, bnp = ctx.saved
         wd0, g0, b0, wl = params[:4]
         gL, bL, wp, gp, bp = params[4 + 12 * n:]
-        ev = not cfg.bn[0].batch_stats
+        ev = ctx.ev
         dev = x2.device
         gcount = HW * d
         dout = as_2d(to_bf16_cl(gout))
         n32 = sum(int(q.numel()) for q in params) + n * 8 * d + 16 * len(params) + 9 * C + 2 * (2 * d + 8) * n + 64
         n64 = 4 * C + (n + 1) * (2 * d + 2 * B + 2 * d) + n * (2 * ffn + 2 * d + 2 * B + 2 * d) + 64 + (2 * n + 1) * (2 * B * d + 2)
-        ar = _Arena(dev, n32, n64)
+        D = _Dst(cfg, ctx.plist, dev, n32, n64, True)
+        ar = D.ar
         sdp, sd0 = ar.f64(2, C), ar.f64(2, C)
-        grads = [None] * len(params)
-        late = []  # (index, fp64 view) gradients that are read out of the fp64 arena after the single cast at the end
         # ---- conv_proj (GN -> 1x1 -> BN, no act)
+        base = 4 + 12 * n
         ops.bn_bwd_reduce(dout, yp, sdp)
-        dgbp, cp = ops.bn_bwd_finalize(sdp, M, gp, bnp, ev)
+        dgbp, cp = ops.bn_bwd_finalize(sdp, M, gp, bnp, ev[1], out=D.pair(base + 3, base + 4))
+        D.set_pair(base + 3, base + 4, dgbp)
         cs, ss = ar.f64(2, d), ar.f64(2, B)
         g = ops.pw_gemm(dout, P.get(cfg.i_wpt), d, K=C, a_mode=A_BNB, A2=yp, a_p=cp, e_mode=E_GN_BWD, Y=XL, e_p=(gL, None),
                         row_stats=(gnL[0], gnL[1]), rows_per_sample=HW, col_stats=cs, samp_stats=ss, gn_ws=ar.f64(2, B, d))
-        dWp = ops.pw_wgrad_side(dout, XL, C, d, g_mode=A_BNB, G2=yp, g_p=cp, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]),
-                           rows_per_sample=HW, dW=ar.f32(C, d))
-        base = 4 + 12 * n
-        late += [(base + 0, cs[1]), (base + 1, cs[0])]  # dgamma = sum v*xhat, dbeta = sum v
-        grads[base + 2], grads[base + 3], grads[base + 4] = dWp.view(C, d, 1, 1), dgbp[0], dgbp[1]
+        ops.pw_wgrad_side(dout, XL, C, d, g_mode=A_BNB, G2=yp, g_p=cp, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]),
+                          rows_per_sample=HW, dW=D.mat(base + 2, C, d))
+        D.late64(base + 0, cs[1])  # dgamma = sum v*xhat
+        D.late64(base + 1, cs[0])  # dbeta = sum v
         bsum = ar.f64(d)  # column sums of the residual-stream gradient = bias gradient of the producing conv
         dX = ops.gn_bwd_apply(g, XL, gnL, ss, gcount, B, HW, DRES=None, col_sum=bsum if n > 0 else None)
         # ---- attention/FFN units, last to first
@@ -287,44 +336,42 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             ix = cfg.i_blk[i]
             o = 4 + 12 * i
             # FFN: X2 = X1 + W2 silu(h) + b2 ; h = W1 GN(X1) + b1
-            late.append((o + 11, bsum))  # db2
-            grads[o + 10] = ops.pw_wgrad_side(dX, h, d, ffn, a_mode=A_SILU, dW=ar.f32(d, ffn)).view(d, ffn, 1, 1)
+            D.late64(o + 11, bsum)  # db2
+            ops.pw_wgrad_side(dX, h, d, ffn, a_mode=A_SILU, dW=D.mat(o + 10, d, ffn))
             csh, csf, ssf, bsum1 = ar.f64(2, ffn), ar.f64(2, d), ar.f64(2, B), ar.f64(d)
             dh = ops.pw_gemm(dX, P.get(ix.w2t), ffn, K=d, e_mode=E_SILU_BWD, Y=h, col_stats=csh)
-            late.append((o + 9, csh[0]))  # db1 = column sums of dh
-            grads[o + 8] = ops.pw_wgrad_side(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW,
-                                        dW=ar.f32(ffn, d)).view(ffn, d, 1, 1)
+            D.late64(o + 9, csh[0])  # db1 = column sums of dh
+            ops.pw_wgrad_side(dh, X1, ffn, d, a_mode=A_GN, a_p=(gf, bf), row_stats=(gnF[0], gnF[1]), rows_per_sample=HW, dW=D.mat(o + 8, ffn, d))
             gF = ops.pw_gemm(dh, P.get(ix.w1t), d, K=ffn, e_mode=E_GN_BWD, Y=X1, e_p=(gf, None), row_stats=(gnF[0], gnF[1]),
                              rows_per_sample=HW, col_stats=csf, samp_stats=ssf, gn_ws=ar.f64(2, B, d))
-            late += [(o + 6, csf[1]), (o + 7, csf[0])]
+            D.late64(o + 6, csf[1])
+            D.late64(o + 7, csf[0])
             dX1 = ops.gn_bwd_apply(gF, X1, gnF, ssf, gcount, B, HW, DRES=dX, col_sum=bsum1)
             # attention: X1 = X + Wo O + bo ; O = linattn(qkv) ; qkv = Wqkv GN(X) + bqkv
-            late.append((o + 5, bsum1))  # dbo
-            grads[o + 4] = ops.pw_wgrad_side(dX1, O, d, d, dW=ar.f32(d, d)).view(d, d, 1, 1)
+            D.late64(o + 5, bsum1)  # dbo
+            ops.pw_wgrad_side(dX1, O, d, d, dW=D.mat(o + 4, d, d))
             dO = ops.pw_gemm(dX1, P.get(ix.wot), d, K=d)
             dbq = ar.f32(2 * d + 8)
             dqkv = ops.linattn_bwd(qkv, dO, S, CTX, B, H, W, d, dbias=dbq)
             dWq = ops.pw_wgrad_side(dqkv, X, 2 * d + 8, d, a_mode=A_GN, a_p=(ga, ba), row_stats=(gnA[0], gnA[1]), rows_per_sample=HW,
-                               dW=ar.f32(2 * d + 8, d))
-            grads[o + 2] = ops.unprep_grad(dWq, 2 * d + 1, d, d, 0, rot=1, side=True).view(2 * d + 1, d, 1, 1)
-            grads[o + 3] = ops.unprep_grad(dbq, 2 * d + 1, 1, 1, 3, rot=1)
+                                    dW=ar.f32(2 * d + 8, d))
+            D.unprep(o + 2, dWq, 2 * d + 1, d, d, 0, rot=1, side=True)
+            D.unprep(o + 3, dbq, 2 * d + 1, 1, 1, 3, rot=1)
             csa, ssa, bsum = ar.f64(2, d), ar.f64(2, B), ar.f64(d)
             gA = ops.pw_gemm(dqkv, P.get(ix.wqkvt), d, K=2 * d + 8, e_mode=E_GN_BWD, Y=X, e_p=(ga, None), row_stats=(gnA[0], gnA[1]),
                              rows_per_sample=HW, col_stats=csa, samp_stats=ssa, gn_ws=ar.f64(2, B, d))
-            late += [(o + 0, csa[1]), (o + 1, csa[0])]
+            D.late64(o + 0, csa[1])
+            D.late64(o + 1, csa[0])
             dX = ops.gn_bwd_apply(gA, X, gnA, ssa, gcount, B, HW, DRES=dX1, col_sum=bsum if i > 0 else None)
         # ---- local_rep: 1x1 (no bias / norm) <- SiLU <- BN0 <- dw3x3
-        grads[3] = ops.pw_wgrad_side(dX, y0, d, C, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), dW=ar.f32(d, C)).view(d, C, 1, 1)
+        ops.pw_wgrad_side(dX, y0, d, C, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), dW=D.mat(3, d, C))
         dz0 = ops.pw_gemm(dX, P.get(cfg.i_wlt), C, K=d, e_mode=E_SILU_BWD, Y=y0, e_p=(bn0[2], bn0[3]), col_stats=sd0)
-        dgb0, c0 = ops.bn_bwd_finalize(sd0, M, g0, bn0, ev)
+        dgb0, c0 = ops.bn_bwd_finalize(sd0, M, g0, bn0, ev[0], out=D.pair(1, 2))
+        D.set_pair(1, 2, dgb0)
         dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW, dWt=ar.f32(9, C))
-        grads[0] = ops.unprep_grad(dWt, C, 9, C, 2).view(C, 1, 3, 3)
-        grads[1], grads[2] = dgb0[0], dgb0[1]
+        D.unprep(0, dWt, C, 9, C, 2)
         ops.join_side()
-        ar.cast()
-        for idx, v64 in late:
-            grads[idx] = ar.as_f32(v64)
-        return (to_4d(dx, B, H, W), None) + tuple(grads)
+        return (to_4d(dx, B, H, W), None) + D.finish()
 
 
 # ==================================================================================================================
@@ -341,6 +388,7 @@ class PoolLinearFn(torch.autograd.Function):
         logits = ops.pw_gemm(pooled, cfg.prep.get(cfg.i_w), npad, bias=cfg.prep.get(cfg.i_b))
         ctx.cfg, ctx.dims = cfg, (B, C, H, W, ncls, npad)
         ctx.saved = (pooled,)
+        ctx.plist = cfg.plist
         return logits[:, :ncls]
 
     @staticmethod
@@ -348,14 +396,52 @@ class PoolLinearFn(torch.autograd.Function):
         cfg = ctx.cfg
         B, C, H, W, ncls, npad = ctx.dims
         (pooled,) = ctx.saved
-        g = torch.zeros((B, npad), device=pooled.device, dtype=BF16)
-        g[:, :ncls] = gout
-        db = torch.zeros(npad, device=pooled.device, dtype=torch.float32)
-        dW = ops.pw_wgrad_side(g, pooled, npad, C, dbias=db)
+        if (gout.dtype == BF16 and gout.dim() == 2 and gout.stride() == (npad, 1) and gout.storage_offset() == 0
+                and gout.untyped_storage().nbytes() >= B * npad * 2):
+            g = gout.as_strided((B, npad), (npad, 1))  # the padded dlogits matrix cvb_ce_bwd wrote (pad columns are zero)
+        else:
+            g = torch.zeros((B, npad), device=pooled.device, dtype=BF16)
+            g[:, :ncls] = gout
+        D = _Dst(cfg, ctx.plist, pooled.device, npad * C + npad + 64, 8, npad == ncls)
+        if npad == ncls:
+            dW, db = D.mat(0, npad, C), D.mat(1, 1, npad).view(npad)
+            ops.pw_wgrad_side(g, pooled, npad, C, dW=dW, dbias=db)
+        else:
+            dW, db = D.ar.f32(npad, C), D.ar.f32(npad)
+            ops.pw_wgrad_side(g, pooled, npad, C, dW=dW, dbias=db)
+            D.grads[0], D.grads[1] = dW[:ncls], db[:ncls]
         dp = ops.pw_gemm(g, cfg.prep.get(cfg.i_wt), C, K=npad)
         dx = ops.global_pool_bwd(dp, B, H * W)
         ops.join_side()
-        return to_4d(dx, B, H, W), None, dW[:ncls], db[:ncls]
+        return (to_4d(dx, B, H, W), None) + D.finish()
+
+
+# ==================================================================================================================
+# Classification loss (loss_fn/classification/cross_entropy.py:74-95): F.cross_entropy(label_smoothing, ignore_index), mean reduction.
+# Two launches; the GradScaler's loss scale (a device scalar) multiplies inside the backward kernel.
+# ==================================================================================================================
+class CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, cfg):
+        B, C = logits.shape
+        lg = logits
+        if lg.dtype != BF16 or lg.stride(1) != 1 or lg.stride(0) % 8:
+            lg = logits.to(BF16).contiguous()
+        if target.dtype != torch.int64 or target.dim() != 1 or target.shape[0] != B:
+            raise ValueError("cross_entropy: target must be an int64 tensor of shape [batch] (class indices)")
+        target = target.contiguous()
+        loss, lse, nv = ops.ce_fwd(lg, C, target, cfg.ignore_index, cfg.label_smoothing)
+        ctx.cfg, ctx.saved, ctx.C = cfg, (lg, target, lse, nv), C
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        lg, target, lse, nv = ctx.saved
+        cfg, C = ctx.cfg, ctx.C
+        g = gout if (gout.dtype == torch.float32 and gout.is_contiguous()) else gout.float().contiguous()
+        ldd = lg.stride(0) if lg.stride(0) >= C else (C + 7) // 8 * 8
+        d = ops.ce_bwd(lg, C, target, cfg.ignore_index, cfg.label_smoothing, lse, nv, g, getattr(cfg, "scale", None), ldd)
+        return d[:, :C], None, None
 
 
 # ==================================================================================================================
@@ -450,7 +536,7 @@ class TransformerEncoderFn(torch.autograd.Function):
         g1, b1, g2, b2 = ctx.saved_tensors
         dev = x2.device
         dY = gout.reshape(M, C).to(BF16).contiguous()
-        ar = _Arena(dev, 4 * C * C + 2 * C * ffn + 8 * C + ffn + 64, 8 * C + 2 * ffn + 64)
+        ar = Arena(dev, 4 * C * C + 2 * C * ffn + 8 * C + ffn + 64, 8 * C + 2 * ffn + 64)
         # ---- FFN
         db2, db1 = ar.f32(C), ar.f32(ffn)
         if cfg.act == ops.ACT_SILU:

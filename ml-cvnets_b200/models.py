@@ -190,6 +190,8 @@ class MobileViTv2(nn.Module):
                                          i_w=prep.add(lin.weight, PW.KIND_ROWMAJOR, dst_rows=npad),
                                          i_wt=prep.add(lin.weight, PW.KIND_TRANSPOSED, ldd=npad),
                                          i_b=prep.add(lin.bias, PW.KIND_VECTOR_F32, dst_rows=npad))
+        self._head.ws = getattr(self, "_ws", None)
+        self._head.plist = [lin.weight, lin.bias]
         self._head.prep.prepare(force=self.training)
         return Fn.PoolLinearFn.apply(Fn.to_bf16_cl(x), self._head, lin.weight, lin.bias)
 

@@ -53,8 +53,10 @@ def _stem_forward(layer: ConvLayer2d, x: Tensor) -> Tensor:
         layer._stem = cfg
     cfg = layer._stem
     cfg.bn = Fn.bn_cfg(layer.block.norm)
+    cfg.ws = getattr(layer, "_ws", None)
+    cfg.plist = [layer.block.conv.weight, layer.block.norm.weight, layer.block.norm.bias]
     cfg.prep.prepare(force=layer.training)
-    return Fn.StemFn.apply(x, cfg, layer.block.conv.weight, layer.block.norm.weight, layer.block.norm.bias)
+    return Fn.StemFn.apply(x, cfg, *cfg.plist)
 
 
 # ---------------------------------------------------------------------------------------------------- InvertedResidual
@@ -101,12 +103,12 @@ class InvertedResidual(BaseModule):
             self._build_cfg()
         cfg, b = self._cfg, self.block
         cfg.bn = [Fn.bn_cfg(b.exp_1x1.block.norm), Fn.bn_cfg(b.conv_3x3.block.norm), Fn.bn_cfg(b.red_1x1.block.norm)]
+        cfg.ws = getattr(self, "_ws", None)
+        cfg.plist = [b.exp_1x1.block.conv.weight, b.exp_1x1.block.norm.weight, b.exp_1x1.block.norm.bias,
+                     b.conv_3x3.block.conv.weight, b.conv_3x3.block.norm.weight, b.conv_3x3.block.norm.bias,
+                     b.red_1x1.block.conv.weight, b.red_1x1.block.norm.weight, b.red_1x1.block.norm.bias]
         cfg.prep.prepare(force=self.training)
-        return Fn.InvertedResidualFn.apply(
-            Fn.to_bf16_cl(x), cfg,
-            b.exp_1x1.block.conv.weight, b.exp_1x1.block.norm.weight, b.exp_1x1.block.norm.bias,
-            b.conv_3x3.block.conv.weight, b.conv_3x3.block.norm.weight, b.conv_3x3.block.norm.bias,
-            b.red_1x1.block.conv.weight, b.red_1x1.block.norm.weight, b.red_1x1.block.norm.bias)
+        return Fn.InvertedResidualFn.apply(Fn.to_bf16_cl(x), cfg, *cfg.plist)
 
     def __repr__(self) -> str:
         return "{}(in_channels={}, out_channels={}, stride={}, exp={}, dilation={}, skip_conn={})".format(
@@ -251,8 +253,10 @@ class MobileViTBlockv2(BaseModule):
             self._build_cfg()
         cfg = self._cfg
         cfg.bn = [Fn.bn_cfg(self.local_rep[0].block.norm), Fn.bn_cfg(self.conv_proj.block.norm)]
+        cfg.ws = getattr(self, "_ws", None)
+        cfg.plist = self._params()
         cfg.prep.prepare(force=self.training)
-        return Fn.MobileViTBlockv2Fn.apply(Fn.to_bf16_cl(x), cfg, *self._params())
+        return Fn.MobileViTBlockv2Fn.apply(Fn.to_bf16_cl(x), cfg, *cfg.plist)
 
     def forward(self, x: Union[Tensor, Tuple[Tensor]], *args, **kwargs) -> Union[Tensor, Tuple[Tensor, Tensor]]:
         if isinstance(x, Tuple) and len(x) == 2:

@@ -36,7 +36,7 @@ def _lib():
 # autograd functions issue them on a second stream: `side=True` forks from the current stream (everything enqueued so far is a
 # dependency), and `join_side()` at the end of each backward makes the current stream wait for them.  Under CUDA-graph capture this
 # becomes a parallel branch of the graph whose CTAs fill the tails of the main-branch kernels.  CVB_WGRAD_STREAM=0 disables it.
-_SIDE = {"on": os.environ.get("CVB_WGRAD_STREAM", "1") != "0", "streams": {}, "dirty": False}
+_SIDE = {"on": os.environ.get("CVB_WGRAD_STREAM", "1") != "0", "streams": {}, "dirty": False, "held": []}
 
 
 class _SideCtx:
@@ -71,6 +71,15 @@ def join_side():
         if side is not None:
             main.wait_stream(side)
         _SIDE["dirty"] = False
+    _SIDE["held"].clear()
+
+
+def _hold(*tensors):
+    """Keep the operands of side-stream work alive until join_side(): the caching allocator only knows about the stream a block was
+    allocated on, so a tensor freed (name rebound) on the main stream while a queued side-stream kernel still reads it could be handed
+    to a later main-stream allocation -- a write-after-read race, also between the parallel branches of a captured graph."""
+    if _SIDE["dirty"]:
+        _SIDE["held"].extend(t for t in tensors if t is not None)
 
 
 def _count(n=1):
@@ -176,6 +185,8 @@ def pw_wgrad(G: Tensor, A: Tensor, N: int, K: int, *, g_mode: int = A_RAW, G2: O
     a.dbias = _p(dbias)
     with _SideCtx(side):
         L.check(lib.cvb_pw_wgrad(ctypes.byref(a), _stream()), "cvb_pw_wgrad")
+        if side:
+            _hold(G, G2, A, dW, dbias)
     _count()
     return dW
 
@@ -255,11 +266,13 @@ def bn_eval_scale_shift(gamma: Tensor, beta: Tensor, running_mean: Tensor, runni
     return out
 
 
-def bn_bwd_finalize(stats: Tensor, count: float, gamma: Tensor, bn: Tensor, eval_mode: bool = False) -> Tuple[Tensor, Tensor]:
-    """stats: fp64 [2, C] (sum dz, sum dz*y); bn: the [4, C] forward record.  Returns (dgb fp32 [2,C] = dgamma,dbeta; coef fp32 [3,C])."""
+def bn_bwd_finalize(stats: Tensor, count: float, gamma: Tensor, bn: Tensor, eval_mode: bool = False,
+                    out: Optional[Tuple[Tensor, Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """stats: fp64 [2, C] (sum dz, sum dz*y); bn: the [4, C] forward record.  Returns (dgb = (dgamma, dbeta) fp32 [C] each -- written into
+    ``out`` when given, e.g. slices of the flat gradient buffer --, coef fp32 [3,C])."""
     lib = _lib()
     C = stats.shape[1]
-    dgb = torch.empty((2, C), device=stats.device, dtype=torch.float32)
+    dgb = torch.empty((2, C), device=stats.device, dtype=torch.float32) if out is None else out
     coef = torch.empty((3, C), device=stats.device, dtype=torch.float32)
     L.check(lib.cvb_bn_bwd_finalize(stats[0].data_ptr(), stats[1].data_ptr(), float(count), _p(gamma), bn[0].data_ptr(), bn[1].data_ptr(),
                                     int(eval_mode), dgb[0].data_ptr(), dgb[1].data_ptr(), coef[0].data_ptr(), coef[1].data_ptr(),
@@ -427,18 +440,51 @@ def col_sum(X: Tensor, N: Optional[int] = None, out: Optional[Tensor] = None) ->
     return out
 
 
+def ce_fwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float):
+    """logits: bf16 [B, ld] (C valid columns).  Returns (loss fp32 [1], lse fp32 [B], n_valid fp32 [1])."""
+    B = logits.shape[0]
+    lse = torch.empty(B, device=logits.device, dtype=torch.float32)
+    out = torch.empty(2, device=logits.device, dtype=torch.float32)
+    L.check(_lib().cvb_ce_fwd(logits.data_ptr(), logits.stride(0), B, C, target.data_ptr(), int(ignore_index), float(smoothing), lse.data_ptr(),
+                              out[0:1].data_ptr(), out[1:2].data_ptr(), _stream()), "cvb_ce_fwd")
+    _count()
+    return out[0:1], lse, out[1:2]
+
+
+def ce_bwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float, lse: Tensor, n_valid: Tensor, gout: Optional[Tensor],
+           gscale: Optional[Tensor], ldd: int) -> Tensor:
+    B = logits.shape[0]
+    d = torch.empty((B, ldd), device=logits.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_ce_bwd(logits.data_ptr(), logits.stride(0), B, C, target.data_ptr(), int(ignore_index), float(smoothing), lse.data_ptr(),
+                              n_valid.data_ptr(), _p(gout), _p(gscale), d.data_ptr(), ldd, _stream()), "cvb_ce_bwd")
+    _count()
+    return d
+
+
 def pw_wgrad_side(G: Tensor, A: Tensor, N: int, K: int, **kw) -> Tensor:
     """pw_wgrad on the side stream (the caller joins with join_side() before the result is consumed)."""
     return pw_wgrad(G, A, N, K, side=True, **kw)
 
 
-def unprep_grad(src: Tensor, rows: int, cols: int, lds: int, kind: int, rot: int = 0, side: bool = False) -> Tensor:
+def unprep_grad(src: Tensor, rows: int, cols: int, lds: int, kind: int, rot: int = 0, side: bool = False, out: Optional[Tensor] = None) -> Tensor:
     lib = _lib()
-    dst = torch.empty((rows, cols) if kind != 3 else (rows,), device=src.device, dtype=torch.float32)
+    dst = torch.empty((rows, cols) if kind != 3 else (rows,), device=src.device, dtype=torch.float32) if out is None else out
+    assert dst.is_contiguous() and dst.numel() == rows * (cols if kind != 3 else 1)
     with _SideCtx(side):
         L.check(lib.cvb_unprep_grad(src.data_ptr(), dst.data_ptr(), rows, cols, lds, kind, rot, _stream()), "cvb_unprep_grad")
+        if side:
+            _hold(src, dst)
     _count()
     return dst
+
+
+_WEIGHTS_GENERATION = [0]
+
+
+def invalidate_prepared_weights() -> None:
+    """Tell every PreparedWeights cache that parameters may have changed WITHOUT a Tensor._version bump (raw-pointer kernels such as
+    cvb_adamw_step, optimizer updates replayed inside a CUDA graph): the next eval-mode forward refreshes its kernel-layout copies."""
+    _WEIGHTS_GENERATION[0] += 1
 
 
 class PreparedWeights:
@@ -455,6 +501,7 @@ class PreparedWeights:
         self._table = None
         self._key = None
         self._versions = None
+        self._forced_last = False
         self._max_elems = 1
 
     def add(self, param: Tensor, kind: int, *, rot: int = 0, ldd: Optional[int] = None, dst_rows: Optional[int] = None) -> int:
@@ -506,8 +553,12 @@ class PreparedWeights:
             self._table = raw.to(device)
             self._key = key
             self._versions = None
-        if not force and versions == self._versions:
+        versions = versions + (_WEIGHTS_GENERATION[0],)
+        # eval-mode callers pass force=False: skip only if nothing can have changed -- same versions, same generation, and the previous
+        # refresh was not a training-mode one (a training forward refreshes BEFORE that step's optimizer update)
+        if not force and versions == self._versions and not self._forced_last:
             return
         L.check(_lib().cvb_prep_weights(self._table.data_ptr(), len(self._entries), int(self._max_elems), _stream()), "cvb_prep_weights")
         _count()
         self._versions = versions
+        self._forced_last = bool(force)

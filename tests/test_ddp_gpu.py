@@ -1,0 +1,102 @@
+"""Data-parallel gradient equivalence on real GPUs (-m gpu, needs >= 2 devices; run with `gpurun --gpus 2`).
+
+SURVEY.md 8e: the path shards by the batch dimension, BatchNorm statistics stay per-GPU, the one exchange is the gradient mean.
+Claim checked: after engine.TrainStep's bucketed, backward-overlapped NCCL all-reduce, every rank holds
+(g(shard_0) + g(shard_1)) / 2 -- the single-GPU gradient of the concatenated batch with per-shard BatchNorm -- and the ranks' weights
+stay identical after optimizer steps, eagerly and under CUDA-graph replay."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    import ml_cvnets_b200 as m
+    from oracle import cvnets_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        width, B, res = 0.5, 8, 64
+        P = O.seeded_fill_(O.mobilevit_v2_shapes(width), 7)
+
+        def fresh():
+            model = m.MobileViTv2(m.default_opts(width_multiplier=width))
+            model.load_state_dict(P, strict=True)
+            return model.cuda().train()
+
+        shards = [(O.seeded_input((B, 3, res, res), 50 + r).cuda(), ((torch.arange(B, device="cuda") + 11 * r) % 1000)) for r in range(world)]
+        # reference on THIS GPU: every shard through the same kernels, gradients averaged (BatchNorm per shard, as in the recipe)
+        ref_sum = None
+        for xs, ys in shards:
+            mod = fresh()
+            ts = m.TrainStep(mod, lr=0.0, weight_decay=0.0, data_parallel=False)
+            ts.step(xs, ys)
+            g = ts.ws.flat_g.clone()
+            ref_sum = g if ref_sum is None else ref_sum + g
+        ref = ref_sum / world
+        # data-parallel step: three eager steps (plan, tables, bucketed) then graph replay
+        model = fresh()
+        ts = m.TrainStep(model, lr=0.0, weight_decay=0.0, n_buckets=3)
+        assert ts.world == world
+        x, y = shards[rank]
+        errs = []
+        for it in range(3):
+            ts.step(x, y)
+            got = ts.ws.flat_g / world  # the tail divides by world inside cvb_grad_norm (grad_div); flat_g holds the SUM over ranks
+            errs.append(float((got - ref).norm() / ref.norm()))
+        n_fire = len(ts.ws._fire_at)
+        ts.capture(x, y)
+        ts.step(x, y)
+        got = ts.ws.flat_g / world
+        errs.append(float((got - ref).norm() / ref.norm()))
+        # weights stay in lock-step across ranks with a real learning rate (captured step, 3 replays)
+        ts.set_lr(1e-3)
+        for _ in range(3):
+            ts.step(x, y)
+        flat = ts.opt.flat_p.clone()
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        drift = max(float((g - gathered[0]).abs().max()) for g in gathered)
+        ts.ws.broadcast_buffers()  # what the next forward starts with (DDP syncs buffers at the START of each forward)
+        bufs = torch.cat([b.flatten().float() for b in model.buffers()])
+        gb = [torch.empty_like(bufs) for _ in range(world)]
+        dist.all_gather(gb, bufs)
+        bdrift = max(float((g - gb[0]).abs().max()) for g in gb)
+        torch.cuda.synchronize()
+        q.put((rank, errs, n_fire, drift, bdrift))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduced_gradients_equal_single_gpu_gradients_of_the_concatenated_batch():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs, n_fire, drift, bdrift in res:
+        print(f"rank {rank}: rel-L2 of all-reduced gradients vs single-GPU concatenated-batch gradients per step {errs}; buckets {n_fire}; "
+              f"weight drift across ranks {drift:.3g}; buffer drift {bdrift:.3g}")
+        assert all(e <= 2e-3 for e in errs), errs  # atomics-order noise of the bf16/fp32 kernels, same on one GPU run twice
+        assert n_fire == 3, "the bucket plan did not form (gradients were exchanged in one piece)"
+        assert drift == 0.0, "ranks diverged: every rank must apply the identical update to identical weights"
+        assert bdrift == 0.0, "BatchNorm running statistics must follow rank 0 (DDP broadcast_buffers semantics)"

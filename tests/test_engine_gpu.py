@@ -1,0 +1,164 @@
+"""engine.TrainStep / cross_entropy / FlatAdamW / StepWorkspace (-m gpu): the fused step against the torch pipeline the reference runs
+(engine/training_engine.py:257-312: F.cross_entropy -> GradScaler.scale().backward() -> unscale_ -> clip_grad_norm_ -> AdamW -> update)."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cvnets_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import ml_cvnets_b200 as m
+    return m
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("B,C,smoothing,ignore", [(128, 1000, 0.1, False), (7, 1000, 0.0, False), (33, 37, 0.2, True), (4, 8, 0.1, True)])
+def test_cross_entropy_matches_torch(pkg, B, C, smoothing, ignore):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + C)
+    logits = (3 * torch.randn(B, C, device="cuda", generator=g)).bfloat16()
+    y = torch.randint(0, C, (B,), device="cuda", generator=g)
+    if ignore:
+        y[::3] = -1
+    ours_in = logits.clone().requires_grad_(True)
+    ref_in = logits.float().requires_grad_(True)
+    loss = pkg.cross_entropy(ours_in, y, label_smoothing=smoothing, ignore_index=-1)
+    ref = F.cross_entropy(ref_in, y, ignore_index=-1, label_smoothing=smoothing)
+    assert abs(float(loss) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (float(loss), float(ref))
+    gscale = torch.tensor(3.0, device="cuda")
+    loss.backward(gscale)
+    ref.backward(gscale)
+    # dlogits are stored in bf16 (they feed the bf16 classifier GEMMs): bf16 rounding is the tolerance
+    assert rel_l2(ours_in.grad, ref_in.grad) <= 4e-3
+    assert float((ours_in.grad.float() - ref_in.grad).abs().max()) <= 2 ** -8 * float(ref_in.grad.abs().max()) + 1e-8
+
+
+def _small_model(pkg, seed=11, width=0.5):
+    model = pkg.MobileViTv2(pkg.default_opts(width_multiplier=width))
+    model.load_state_dict(O.seeded_fill_(O.mobilevit_v2_shapes(width), seed), strict=True)
+    return model.cuda().train()
+
+
+def test_train_step_gradients_match_autograd_path(pkg):
+    """Workspace mode (gradients written in place, Functions return None) == the plain autograd path of the same kernels."""
+    B, res = 8, 64
+    x = O.seeded_input((B, 3, res, res), 5).cuda()
+    y = torch.arange(B, device="cuda") % 1000
+    ref = _small_model(pkg)
+    logits = ref(x)
+    scale = 65536.0
+    (pkg.cross_entropy(logits, y, label_smoothing=0.1) * scale).backward()
+    model = _small_model(pkg)
+    ts = pkg.TrainStep(model, lr=0.0, weight_decay=0.0)  # lr 0: parameters stay put, gradients can be compared after the step
+    for it in range(3):  # step 0 plans the arena, step 1 builds the descriptor tables, step 2 runs fully planned
+        loss = ts.step(x, y)
+        for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            e = rel_l2(p.grad, q.grad)
+            small = float(q.grad.norm()) < 1e-6 * scale
+            assert e <= 2e-3 or small, f"step {it} {k}: rel-L2 {e:.3g} (|g| {float(q.grad.norm()):.3g})"
+    assert abs(float(loss) - float(F.cross_entropy(logits.float(), y, label_smoothing=0.1))) < 2e-3
+    # running statistics advanced 3x in `model`, once in `ref`: only the counters are comparable
+    assert int(model.conv_1.block.norm.num_batches_tracked) == 3
+
+
+def test_train_step_matches_torch_pipeline_and_graph_replay(pkg):
+    """Three optimizer steps: TrainStep eager == TrainStep captured (bitwise-level agreement of the loss trajectory up to atomics noise),
+    and both follow the torch pipeline run on the same kernels (loss trajectory within 1e-3)."""
+    B, res = 8, 64
+    xs = [O.seeded_input((B, 3, res, res), 100 + i).cuda() for i in range(4)]
+    ys = [(torch.arange(B, device="cuda") * (i + 3)) % 1000 for i in range(4)]
+    # torch pipeline
+    ref = _small_model(pkg)
+    groups, _ = ref.get_trainable_parameters(weight_decay=0.05, no_decay_bn_filter_bias=True)
+    opt = torch.optim.AdamW(groups, lr=2e-3, betas=(0.9, 0.999))
+    scaler = torch.amp.GradScaler("cuda", enabled=True)
+    ref_losses = []
+    for x, y in zip(xs, ys):
+        loss = F.cross_entropy(ref(x).float(), y, label_smoothing=0.1)
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(list(ref.parameters()), 10.0)
+        scaler.step(opt)
+        scaler.update()
+        ref_losses.append(float(loss))
+    # eager TrainStep
+    m1 = _small_model(pkg)
+    t1 = pkg.TrainStep(m1, lr=2e-3, weight_decay=0.05, max_norm=10.0, label_smoothing=0.1)
+    l1 = [float(t1.step(x, y)) for x, y in zip(xs, ys)]
+    # captured TrainStep: the warm-up steps inside capture() use lr = 0 so that the trajectory starts from the same weights
+    m2 = _small_model(pkg)
+    t2 = pkg.TrainStep(m2, lr=0.0, weight_decay=0.0, max_norm=10.0, label_smoothing=0.1)
+    sd0 = {k: v.clone() for k, v in m2.state_dict().items()}
+    t2.capture(xs[0], ys[0])
+    m2.load_state_dict(sd0)  # undo the BatchNorm running-stat updates of the warm-up steps
+    t2.opt.exp_avg.zero_(); t2.opt.exp_avg_sq.zero_(); t2.opt.step_count.zero_(); t2.opt.scale.copy_(torch.tensor([65536.0, 0.0]))
+    t2.opt.wd.copy_(t1.opt.wd)
+    t2.set_lr(2e-3)
+    l2 = [float(t2.step(x, y)) for x, y in zip(xs, ys)]
+    for a, b, r in zip(l1, l2, ref_losses):
+        assert abs(a - b) <= 2e-3 * abs(a), (l1, l2)
+        assert abs(a - r) <= 5e-3 * abs(r), (l1, ref_losses)
+    for (k, p), (_, q) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert float((p - q).abs().max()) <= 4 * 2e-3 * 4 + 1e-6, k  # at most a few AdamW steps of size lr apart (sign flips of ~0 grads)
+    e = torch.tensor([rel_l2(p, q) for p, q in zip(m1.parameters(), ref.parameters())])
+    assert float(e.median()) <= 2e-2, float(e.median())
+
+
+def test_ema_and_lr_schedule_and_state_dict(pkg):
+    B, res = 4, 64
+    x = O.seeded_input((B, 3, res, res), 9).cuda()
+    y = torch.arange(B, device="cuda")
+    model = _small_model(pkg)
+    mom = 0.05
+    ts = pkg.TrainStep(model, lr=1e-3, ema_momentum=mom)
+    ema_ref = {k: p.detach().clone() for k, p in model.named_parameters()}
+    for it in range(3):
+        ts.set_lr(1e-3 * (it + 1))
+        ts.step(x, y)
+        for k, p in model.named_parameters():  # cvnets/misc/averaging_utils.py:55
+            ema_ref[k] = ema_ref[k] * (1.0 - mom) + mom * p.detach()
+    ema = ts.opt.ema_parameters(model)
+    for k, v in ema_ref.items():
+        assert rel_l2(ema[k], v) <= 1e-5, k
+    assert abs(float(ts.opt.hp[0]) - 3e-3) < 1e-9
+    sd = ts.state_dict()
+    assert float(sd["step"]) == 3.0
+    ts2 = pkg.TrainStep(_small_model(pkg), lr=5.0, ema_momentum=mom)
+    ts2.load_state_dict(sd)
+    assert torch.equal(ts2.opt.exp_avg, ts.opt.exp_avg) and abs(float(ts2.opt.hp[0]) - 3e-3) < 1e-9
+
+
+def test_eval_after_train_step_sees_new_weights(pkg):
+    """raw-pointer / replayed optimizer updates do not bump Tensor._version; eval-mode weight caches must still refresh."""
+    B, res = 4, 64
+    x = O.seeded_input((B, 3, res, res), 9).cuda()
+    y = torch.arange(B, device="cuda")
+    model = _small_model(pkg)
+    ts = pkg.TrainStep(model, lr=5e-2)
+    ts.capture(x, y)
+    model.eval()
+    with torch.no_grad():
+        a = model(x).float().clone()
+    model.train()
+    for _ in range(3):
+        ts.step(x, y)
+    model.eval()
+    with torch.no_grad():
+        b = model(x).float()
+        fresh = pkg.MobileViTv2(pkg.default_opts(width_multiplier=0.5)).cuda().eval()
+        fresh.load_state_dict(model.state_dict(), strict=True)
+        c = fresh(x).float()
+    assert rel_l2(b, c) <= 1e-3, "eval forward used stale bf16 weight copies"
+    assert rel_l2(a, b) > 1e-2, "weights did not move?"
