@@ -191,6 +191,12 @@ CVB_API int cvb_gn_bwd_apply(const void* G, const void* X, const float* mean, co
                      double count, const void* DRES, void* DX, int B, int rows_per_sample, int C, double* col_sum,
                      cvb_stream_t stream);
 
+/* Stand-alone GroupNorm(1, C) backward (autograd of F.group_norm as LayerNorm2D_NCHW calls it, layer_norm.py:105-108) in two launches:
+ * V = gradient w.r.t. the normalised+affine output, X = the layer's input, mean/rstd per sample.  dgamma[c] += sum V*xhat, dbeta[c] += sum V
+ * (fp64, caller zeroes), samp_ws: ZEROED fp64 [2][B] scratch; DX = rstd*(V*gamma - mean(V*gamma) - xhat*mean(V*gamma*xhat)) (+ DRES). */
+CVB_API int cvb_gn_bwd(const void* V, const void* X, const float* mean, const float* rstd, const float* gamma, double count, const void* DRES,
+               void* DX, int B, int rows_per_sample, int C, double* dgamma, double* dbeta, double* samp_ws, cvb_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * LinearSelfAttention core between qkv_proj and out_proj (cvnets/layers/linear_attention.py:134-161),
  * with unfold/fold (mobilevit_block.py:526-555) collapsed into indexing: the feature map stays [B,H,W,*] and the four
@@ -204,6 +210,16 @@ CVB_API int cvb_linattn_fwd(const void* QKV, int ldq, int B, int H, int W, int d
 /* bwd: from dO -> dQKV (same layout as QKV; pad columns zeroed); dbias_qkv[2d+1 (+pad)] += column sums if not NULL */
 CVB_API int cvb_linattn_bwd(const void* QKV, int ldq, const void* DO, int ldo, const float* S, const float* CTX, int B, int H, int W,
                     int d, int patch, void* DQKV, float* dbias, cvb_stream_t stream);
+/* patch = 2: folded feature map as above.  patch = 0: the tensor is the UNFOLDED matrix [B, P = H, N = W, ld] itself, i.e. a stand-alone
+ * LinearSelfAttention applied to a [B, d, P, N] input in channels-last memory (linear_attention.py:134-161, 209-215).
+ * Cross-attention (LinearSelfAttention._forward_cross_attn, linear_attention.py:163-207; LinearAttnFFN cross branch transformer.py:254-260):
+ * query + key come from the projection of x_prev (QK_prev: [B, P, M, ldq], columns as above), the values from the projection of x
+ * (V_x: [B, P, N, ldv], value columns [d, 2d)); softmax / context over M, output O [B, P, N, ldo].  S: [B, P, M], CTX: [B, P, d].
+ * bwd writes the key/query columns of DQK_prev and the value columns of DV_x (the caller zero-fills the other columns of both). */
+CVB_API int cvb_linattn_cross_fwd(const void* QK_prev, int ldq, int B, int P, int M, int d, const void* V_x, int ldv, int N, void* O, int ldo,
+                          float* S, float* CTX, cvb_stream_t stream);
+CVB_API int cvb_linattn_cross_bwd(const void* QK_prev, int ldq, const void* V_x, int ldv, const void* DO, int ldo, const float* S, const float* CTX,
+                          int B, int P, int M, int N, int d, void* DQK_prev, void* DV_x, float* dbias, cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MultiHeadAttention core (cvnets/layers/multi_head_attention.py:135-239, self-attention branch) and LayerNorm statistics

@@ -3,7 +3,7 @@ LinearSelfAttention, LinearAttnFFN, conv+BN+SiLU; plus the ViT-style MultiHeadAt
 (include/cvnets_b200.h) with drop-in ``nn.Module``s on top.  Import name: ``ml_cvnets_b200`` (alias package at the repo root).
 """
 from . import _lib  # noqa: F401
-from .layers import (GELU, BatchNorm2d, ConvLayer2d, Dropout, GlobalPool, Identity, LayerNorm, LayerNorm2D_NCHW,  # noqa: F401
+from .layers import (GELU, BatchNorm2d, ConvLayer2d, Dropout, GlobalPool, Identity, LayerNorm, LayerNorm2D_NCHW, LayerNormFP32,  # noqa: F401
                      LinearLayer, LinearSelfAttention, MultiHeadAttention, Swish)
 from .models import MobileViTv2, default_opts, get_configuration  # noqa: F401
 from .modules import InvertedResidual, LinearAttnFFN, MobileViTBlockv2, TransformerEncoder  # noqa: F401
@@ -14,4 +14,4 @@ from .workspace import StepWorkspace  # noqa: F401
 __all__ = ["MobileViTv2", "default_opts", "get_configuration", "InvertedResidual", "LinearAttnFFN", "MobileViTBlockv2",
            "ConvLayer2d", "LinearSelfAttention", "BatchNorm2d", "LayerNorm2D_NCHW", "GlobalPool", "LinearLayer", "Swish",
            "Dropout", "Identity", "TransformerEncoder", "MultiHeadAttention", "LayerNorm", "GELU", "TrainStep", "cross_entropy", "FlatAdamW",
-           "StepWorkspace"]
+           "StepWorkspace", "LayerNormFP32"]

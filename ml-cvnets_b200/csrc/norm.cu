@@ -338,6 +338,55 @@ __global__ void __launch_bounds__(NT) gn_stats_kernel(const bf16* __restrict__ X
   }
 }
 
+// Stand-alone GroupNorm(1, C) backward, phase 1 (when no producing GEMM epilogue took the sums): per-channel dbeta += v, dgamma += v*xhat and
+// per-sample sums of g = v*gamma and g*xhat.  CTA = (row chunk, sample); a thread owns one 8-channel group.
+__global__ void __launch_bounds__(NT) gn_bwd_stats_kernel(const bf16* __restrict__ V, const bf16* __restrict__ X, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const float* __restrict__ gamma, int rows_per_sample, int C,
+                                                          int cgs, int rpp, int rows_per_cta, double* dgamma, double* dbeta, double* sg, double* sgx) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float sred[];  // [2][C]
+  __shared__ float ws[2][NT / 32];
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cg = tid % cgs, rr = tid / cgs, c = cg * 8;
+  const float mu = mean[b], rs = rstd[b];
+  float db[8], dg[8], gm[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { db[j] = 0.f; dg[j] = 0.f; gm[j] = gamma[c + j]; }
+  int r_begin = blockIdx.x * rows_per_cta, r_end = r_begin + rows_per_cta;
+  if (r_end > rows_per_sample) r_end = rows_per_sample;
+  if (rr < rpp) {
+    for (int r = r_begin + rr; r < r_end; r += rpp) {
+      const int64_t row = (int64_t)b * rows_per_sample + r;
+      float v[8], x[8];
+      unpack8(ldg16_stream(V + row * C + c), v);
+      unpack8(ldg16_stream(X + row * C + c), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - mu) * rs, g = v[j] * gm[j];
+        db[j] += v[j];
+        dg[j] = fmaf(v[j], xh, dg[j]);
+        s1 += g;
+        s2 = fmaf(g, xh, s2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&sred[c + j], db[j]); atomicAdd(&sred[C + c + j], dg[j]); }
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((tid & 31) == 0) { ws[0][tid >> 5] = s1; ws[1][tid >> 5] = s2; }
+  __syncthreads();
+  for (int i = tid; i < C; i += blockDim.x) { atomicAdd(dbeta + i, (double)sred[i]); atomicAdd(dgamma + i, (double)sred[C + i]); }
+  if (tid == 0) {
+    float a = 0.f, q = 0.f;
+    for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) { a += ws[0][i]; q += ws[1][i]; }
+    atomicAdd(sg + b, (double)a);
+    atomicAdd(sgx + b, (double)q);
+  }
+}
+
 // GroupNorm backward phase 2 (+ residual-stream gradient, + column sums of the result)
 // LayerNorm backward in ONE pass (a "sample" is a single token row, so both phases of the GroupNorm backward fit in a warp):
 //   g = v * gamma;  dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)) + dres;   dbeta += v;  dgamma += v * xhat;  col_sum += dx
@@ -488,7 +537,8 @@ __global__ void __launch_bounds__(NT) ln_stats_kernel(const bf16* __restrict__ X
 __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict__ G, const bf16* __restrict__ X, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const double* __restrict__ sg, const double* __restrict__ sgx,
                                                           double count, const bf16* __restrict__ DRES, bf16* __restrict__ DX, int64_t M,
-                                                          int rows_per_sample, int C, double* col_sum, int cgs, int rpp, int rows_per_cta) {
+                                                          int rows_per_sample, int C, double* col_sum, int cgs, int rpp, int rows_per_cta,
+                                                          const float* __restrict__ gamma) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sred[];  // [C]
@@ -496,9 +546,9 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict
   if (col_sum) { for (int i = tid; i < C; i += blockDim.x) sred[i] = 0.f; __syncthreads(); }
   const int cg = tid % cgs, rr = tid / cgs;
   const int c = cg * 8;
-  float a0[8];
+  float a0[8], gm[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a0[j] = 0.f;
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; gm[j] = gamma ? gamma[c + j] : 1.0f; }
   int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = r_begin + rows_per_cta;
   if (r_end > M) r_end = M;
   for (int64_t r = r_begin + rr; r < r_end; r += rpp) {
@@ -511,7 +561,7 @@ __global__ void __launch_bounds__(NT) gn_bwd_apply_kernel(const bf16* __restrict
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float xh = (x[j] - mu) * rs;
-      g[j] = rs * (g[j] - m1 - xh * m2);
+      g[j] = rs * (g[j] * gm[j] - m1 - xh * m2);
     }
     if (DRES) {
       float d[8];
@@ -791,7 +841,30 @@ extern "C" int cvb_gn_bwd_apply(const void* G, const void* X, const float* mean,
   RowGeom g = row_geom(M, C);
   CVB_CUDA(cvb_launch(gn_bwd_apply_kernel, g.ctas, g.nthreads, C * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const bf16*>(G), static_cast<const bf16*>(X), mean, rstd, sg, sgx, count, static_cast<const bf16*>(DRES), static_cast<bf16*>(DX), M,
-      rows_per_sample, C, col_sum, g.cgs, g.rpp, g.rows_per_cta));
+      rows_per_sample, C, col_sum, g.cgs, g.rpp, g.rows_per_cta, static_cast<const float*>(nullptr)));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_gn_bwd(const void* V, const void* X, const float* mean, const float* rstd, const float* gamma, double count, const void* DRES,
+                          void* DX, int B, int rows_per_sample, int C, double* dgamma, double* dbeta, double* samp_ws, cvb_stream_t stream) {
+  CVB_CHECK(V && X && mean && rstd && gamma && DX && dgamma && dbeta && samp_ws && B > 0 && rows_per_sample > 0 && C > 0 && C % 8 == 0 && C <= 2048,
+            "cvb_gn_bwd: bad arguments");
+  int64_t M = (int64_t)B * rows_per_sample;
+  RowGeom g1 = row_geom(rows_per_sample, C);
+  int chunks = g1.ctas;
+  const int cap = (6 * cvb_num_sms() + B - 1) / B;
+  int rows_per_cta = g1.rows_per_cta;
+  if (chunks > cap) { rows_per_cta = ((rows_per_sample + cap - 1) / cap + g1.rpp - 1) / g1.rpp * g1.rpp; chunks = (rows_per_sample + rows_per_cta - 1) / rows_per_cta; }
+  CVB_CUDA(cvb_launch(gn_bwd_stats_kernel, dim3(chunks, B), g1.nthreads, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream),
+                      static_cast<const bf16*>(V), static_cast<const bf16*>(X), mean, rstd, gamma, rows_per_sample, C, g1.cgs, g1.rpp, rows_per_cta, dgamma,
+                      dbeta, samp_ws, samp_ws + B));
+  CVB_LAUNCH_CHECK();
+  RowGeom g = row_geom(M, C);
+  CVB_CUDA(cvb_launch(gn_bwd_apply_kernel, g.ctas, g.nthreads, C * sizeof(float), static_cast<cudaStream_t>(stream), static_cast<const bf16*>(V),
+                      static_cast<const bf16*>(X), mean, rstd, static_cast<const double*>(samp_ws), static_cast<const double*>(samp_ws + B), count,
+                      static_cast<const bf16*>(DRES), static_cast<bf16*>(DX), M, rows_per_sample, C, static_cast<double*>(nullptr), g.cgs, g.rpp,
+                      g.rows_per_cta, gamma));
   CVB_LAUNCH_CHECK();
   return 0;
 }

@@ -445,6 +445,322 @@ class CrossEntropyFn(torch.autograd.Function):
 
 
 # ==================================================================================================================
+# Stand-alone layer functions: the hot-path LAYERS used outside the fused modules (north_star:
+# "MultiHeadAttention and MobileViTv2 LinearSelfAttention in cvnets/layers ... drop-in nn.Module").  Same kernels, one layer per
+# autograd function, outputs materialised -- the unfused but native path every layer falls back to when it is not inside a fused block.
+# ==================================================================================================================
+class PointwiseConvFn(torch.autograd.Function):
+    """ConvLayer2d with a 1x1 kernel: conv (+bias) [-> BatchNorm2d] [-> activation] [+ residual] on a [B, Cin, H, W] map
+    (cvnets/layers/conv_layer.py:200-226, 254-255).  params = (w, bias | None, gamma | None, beta | None)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, residual, w, bias, gamma, beta):
+        B, Cin, H, W = x.shape
+        M, cout = B * H * W, cfg.cout
+        x2 = as_2d(x)
+        P = cfg.prep
+        R = as_2d(residual) if residual is not None else None
+        if cfg.bn is not None:
+            st = _fwd_arena(cfg, x.device, 2 * cout + 8).f64(2, cout)
+            y = ops.pw_gemm(x2, P.get(cfg.i_w), cout, bias=bias, col_stats=st if cfg.bn.batch_stats else None)
+            bn = _bn_forward(st, M, gamma, beta, cfg.bn)
+            out = ops.bn_apply(y, bn, act=cfg.act is not None, R=R)
+            if cfg.act not in (None, ops.ACT_SILU):
+                raise NotImplementedError("BatchNorm followed by an activation other than Swish")
+            ctx.saved, ctx.ev = (x2, y, bn), (not cfg.bn.batch_stats,)
+        elif cfg.act is not None:
+            h = ops.pw_gemm(x2, P.get(cfg.i_w), cout, bias=bias)
+            out = ops.act_fwd(h, cfg.act)
+            if R is not None:
+                raise NotImplementedError("activation + residual in one stand-alone ConvLayer2d")
+            ctx.saved = (x2, h)
+        else:
+            out = ops.pw_gemm(x2, P.get(cfg.i_w), cout, bias=bias, R=R)
+            ctx.saved = (x2,)
+        ctx.cfg, ctx.dims, ctx.plist, ctx.has_res = cfg, (B, Cin, H, W), cfg.plist, residual is not None
+        ctx.save_for_backward(gamma) if gamma is not None else None
+        return to_4d(out, B, H, W)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, Cin, H, W = ctx.dims
+        M, cout = B * H * W, cfg.cout
+        P = cfg.prep
+        dout = as_2d(to_bf16_cl(gout))
+        D = _Dst(cfg, ctx.plist, dout.device, cout * Cin + cout + 64, 2 * cout + 16, True)
+        has_bias = cfg.has_bias
+        db = D.mat(1, 1, cout).view(cout) if has_bias else None
+        if cfg.bn is not None:
+            x2, y, bn = ctx.saved
+            (gamma,) = ctx.saved_tensors
+            act = cfg.act is not None
+            sd = D.ar.f64(2, cout)
+            dz = ops.bn_bwd_reduce(dout, y, sd, bn, act=act, store_dz=act)
+            if not act:
+                dz = dout
+            gi, bi = (2, 3) if has_bias else (1, 2)
+            dgb, c = ops.bn_bwd_finalize(sd, M, gamma, bn, ctx.ev[0], out=D.pair(gi, bi))
+            D.set_pair(gi, bi, dgb)
+            dx = ops.pw_gemm(dz, P.get(cfg.i_wt), Cin, K=cout, a_mode=A_BNB, A2=y, a_p=c)
+            ops.pw_wgrad_side(dz, x2, cout, Cin, g_mode=A_BNB, G2=y, g_p=c, dW=D.mat(0, cout, Cin), dbias=db)
+        else:
+            if cfg.act is not None:
+                x2, h = ctx.saved
+                dh = ops.act_bwd(dout, h, cfg.act)
+            else:
+                (x2,) = ctx.saved
+                dh = dout
+            dx = ops.pw_gemm(dh, P.get(cfg.i_wt), Cin, K=cout)
+            ops.pw_wgrad_side(dh, x2, cout, Cin, dW=D.mat(0, cout, Cin), dbias=db)
+        ops.join_side()
+        grads = D.finish()
+        g = {0: grads[0]}
+        full = [grads[0], None, None, None]
+        if has_bias:
+            full[1] = grads[1]
+        if cfg.bn is not None:
+            full[2], full[3] = grads[2 if has_bias else 1], grads[3 if has_bias else 2]
+        return (to_4d(dx, B, H, W), None, gout if ctx.has_res else None) + tuple(full)
+
+
+class DepthwiseConvFn(torch.autograd.Function):
+    """ConvLayer2d with a depthwise 3x3 kernel (groups = channels, stride 1 | 2, no bias) [-> BatchNorm2d] [-> Swish]."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, w, gamma, beta):
+        B, C, H, W = x.shape
+        s = cfg.stride
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        M2 = B * Ho * Wo
+        x2 = as_2d(x)
+        if cfg.bn is not None:
+            st = _fwd_arena(cfg, x.device, 2 * C + 8).f64(2, C)
+            y = ops.dw_fwd(x2, B, H, W, C, s, cfg.prep.get(cfg.i_w), col_stats=st if cfg.bn.batch_stats else None)
+            bn = _bn_forward(st, M2, gamma, beta, cfg.bn)
+            out = ops.bn_apply(y, bn, act=cfg.act is not None)
+            ctx.saved, ctx.ev = (x2, y, bn), (not cfg.bn.batch_stats,)
+        else:
+            y = ops.dw_fwd(x2, B, H, W, C, s, cfg.prep.get(cfg.i_w))
+            out = ops.act_fwd(y, cfg.act) if cfg.act is not None else y
+            ctx.saved = (x2, y)
+        ctx.cfg, ctx.dims, ctx.plist = cfg, (B, C, H, W, Ho, Wo), cfg.plist
+        ctx.save_for_backward(gamma) if gamma is not None else None
+        return to_4d(out, B, Ho, Wo)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, C, H, W, Ho, Wo = ctx.dims
+        M2 = B * Ho * Wo
+        dout = as_2d(to_bf16_cl(gout))
+        D = _Dst(cfg, ctx.plist, dout.device, 9 * C + 64, 2 * C + 16, True)
+        if cfg.bn is not None:
+            x2, y, bn = ctx.saved
+            (gamma,) = ctx.saved_tensors
+            act = cfg.act is not None
+            sd = D.ar.f64(2, C)
+            dz = ops.bn_bwd_reduce(dout, y, sd, bn, act=act, store_dz=act)
+            if not act:
+                dz = dout
+            dgb, c = ops.bn_bwd_finalize(sd, M2, gamma, bn, ctx.ev[0], out=D.pair(1, 2))
+            D.set_pair(1, 2, dgb)
+            dx, dWt = ops.dw_bwd(dz, x2, B, H, W, C, cfg.stride, cfg.prep.get(cfg.i_w), g_mode=A_BNB, Y2=y, g_p=c, dWt=D.ar.f32(9, C))
+        else:
+            x2, y = ctx.saved
+            dz = ops.act_bwd(dout, y, cfg.act) if cfg.act is not None else dout
+            dx, dWt = ops.dw_bwd(dz, x2, B, H, W, C, cfg.stride, cfg.prep.get(cfg.i_w), dWt=D.ar.f32(9, C))
+        D.unprep(0, dWt, C, 9, C, 2)
+        grads = D.finish()
+        return (to_4d(dx, B, H, W), None, grads[0]) + ((grads[1], grads[2]) if cfg.bn is not None else (None, None))
+
+
+class GroupNorm1Fn(torch.autograd.Function):
+    """LayerNorm2D_NCHW == nn.GroupNorm(1, C) on [B, C, H, W] (cvnets/layers/normalization/layer_norm.py:75-108): statistics over all of
+    (C, H, W) per sample in fp32 (fp64 accumulation), per-channel affine."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, gamma, beta):
+        B, C, H, W = x.shape
+        rps = H * W
+        x2 = as_2d(x)
+        st = _fwd_arena(cfg, x.device, 2 * B + 8).f64(2, B)
+        ops.gn_stats(x2, B, rps, st)
+        gn = ops.gn_finalize(st, rps * C, cfg.eps)
+        out = ops.apply_load_mode(x2, ops.A_GN, C, a_p=(gamma, beta, None), row_stats=(gn[0], gn[1]), rows_per_sample=rps)
+        ctx.cfg, ctx.dims, ctx.saved, ctx.plist = cfg, (B, C, H, W), (x2, gn), cfg.plist
+        ctx.save_for_backward(gamma)
+        return to_4d(out, B, H, W)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, C, H, W = ctx.dims
+        x2, gn = ctx.saved
+        (gamma,) = ctx.saved_tensors
+        dout = as_2d(to_bf16_cl(gout))
+        D = _Dst(cfg, ctx.plist, dout.device, 64, 2 * C + 2 * B + 16, True)
+        dgb, wsp = D.ar.f64(2, C), D.ar.f64(2, B)
+        dx = ops.gn_bwd(dout, x2, gn, gamma, float(H * W * C), B, H * W, dgb[0], dgb[1], wsp)
+        D.late64(0, dgb[0])
+        D.late64(1, dgb[1])
+        return (to_4d(dx, B, H, W), None) + D.finish()
+
+
+class LayerNormFn(torch.autograd.Function):
+    """LayerNorm / LayerNormFP32 over the last dimension of a [..., C] tensor (cvnets/layers/normalization/layer_norm.py:14-72, 111-137).
+    Statistics and the normalisation are computed in fp32 from the bf16 input for both variants (the FP32 variant's upcast is implicit)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, gamma, beta):
+        shape = x.shape
+        C = shape[-1]
+        x2 = x.reshape(-1, C)
+        if x2.dtype != BF16 or not x2.is_contiguous():
+            x2 = x2.to(BF16).contiguous()
+        ln = ops.ln_stats(x2, cfg.eps)
+        out = ops.apply_load_mode(x2, ops.A_GN, C, a_p=(gamma, beta, None), row_stats=(ln[0], ln[1]), rows_per_sample=1)
+        ctx.cfg, ctx.shape, ctx.saved, ctx.plist = cfg, shape, (x2, ln), cfg.plist
+        ctx.save_for_backward(gamma)
+        return out.view(shape)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        C = ctx.shape[-1]
+        x2, ln = ctx.saved
+        (gamma,) = ctx.saved_tensors
+        dy = gout.reshape(-1, C)
+        if dy.dtype != BF16 or not dy.is_contiguous():
+            dy = dy.to(BF16).contiguous()
+        D = _Dst(cfg, ctx.plist, dy.device, 64, 2 * C + 16, True)
+        cs = D.ar.f64(2, C)
+        dx = ops.ln_bwd(dy, x2, ln, gamma, cs)
+        D.late64(0, cs[1])
+        D.late64(1, cs[0])
+        return (dx.view(ctx.shape), None) + D.finish()
+
+
+class LinearSelfAttentionFn(torch.autograd.Function):
+    """Stand-alone LinearSelfAttention on the unfolded tensor x [B, d, P, N] (cvnets/layers/linear_attention.py:134-215): self-attention, or
+    cross-attention against x_prev [B, d, P, M] (query/key from x_prev, value from x).  ``residual`` (optional, [B, d, P, N]) is added in
+    the out_proj epilogue.  params = (wqkv, bqkv, wo, bo)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, x_prev, residual, wqkv, bqkv, wo, bo):
+        B, d, Pp, N = x.shape
+        Pw = cfg.prep
+        x2 = as_2d(x)
+        R = as_2d(residual) if residual is not None else None
+        qkv = ops.pw_gemm(x2, Pw.get(cfg.i_wqkv), 2 * d + 8, bias=Pw.get(cfg.i_bqkv))
+        if x_prev is None:
+            xp2, qkp = None, None
+            O, S, CTX = ops.linattn_fwd(qkv, B, Pp, N, d, patch=0)
+        else:
+            if x_prev.shape[0] != B or x_prev.shape[1] != d or x_prev.shape[2] != Pp:
+                raise ValueError("The number of pixels in a patch for query and key_value should be the same")  # linear_attention.py:172-174
+            xp2 = as_2d(x_prev)
+            qkp = ops.pw_gemm(xp2, Pw.get(cfg.i_wqkv), 2 * d + 8, bias=Pw.get(cfg.i_bqkv))
+            O, S, CTX = ops.linattn_cross_fwd(qkp, qkv, B, Pp, x_prev.shape[3], N, d)
+        y = ops.pw_gemm(O, Pw.get(cfg.i_wo), d, bias=bo, R=R)
+        ctx.cfg, ctx.dims, ctx.plist = cfg, (B, d, Pp, N, x_prev.shape[3] if x_prev is not None else N), cfg.plist
+        ctx.saved = (x2, qkv, xp2, qkp, O, S, CTX)
+        ctx.has_res = residual is not None
+        return to_4d(y, B, Pp, N)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        B, d, Pp, N, Mp = ctx.dims
+        Pw = cfg.prep
+        x2, qkv, xp2, qkp, O, S, CTX = ctx.saved
+        dy = as_2d(to_bf16_cl(gout))
+        D = _Dst(cfg, ctx.plist, dy.device, (2 * d + 8) * (d + 1) + d * d + d + 64, 16, True)
+        ar = D.ar
+        ops.pw_wgrad_side(dy, O, d, d, dW=D.mat(2, d, d), dbias=D.mat(3, 1, d).view(d))
+        dO = ops.pw_gemm(dy, Pw.get(cfg.i_wot), d, K=d)
+        dbq = ar.f32(2 * d + 8)
+        dWq = ar.f32(2 * d + 8, d)
+        if xp2 is None:
+            dqkv = ops.linattn_bwd(qkv, dO, S, CTX, B, Pp, N, d, dbias=dbq, patch=0)
+            ops.pw_wgrad_side(dqkv, x2, 2 * d + 8, d, dW=dWq)
+            dx = ops.pw_gemm(dqkv, Pw.get(cfg.i_wqkvt), d, K=2 * d + 8)
+            dxp = None
+        else:
+            dqkp, dqkv = ops.linattn_cross_bwd(qkp, qkv, dO, S, CTX, B, Pp, Mp, N, d, dbias=dbq)
+            ops.pw_wgrad_side(dqkp, xp2, 2 * d + 8, d, dW=dWq)
+            ops.pw_wgrad_side(dqkv, x2, 2 * d + 8, d, dW=dWq)
+            dx = ops.pw_gemm(dqkv, Pw.get(cfg.i_wqkvt), d, K=2 * d + 8)
+            dxp = to_4d(ops.pw_gemm(dqkp, Pw.get(cfg.i_wqkvt), d, K=2 * d + 8), B, Pp, Mp)
+        D.unprep(0, dWq, 2 * d + 1, d, d, 0, rot=1, side=True)
+        D.unprep(1, dbq, 2 * d + 1, 1, 1, 3, rot=1)
+        ops.join_side()
+        return (to_4d(dx, B, Pp, N), None, dxp, gout if ctx.has_res else None) + D.finish()
+
+
+class LinearFn(torch.autograd.Function):
+    """LinearLayer: y = x W^T + b on [..., Cin] (cvnets/layers/linear_layer.py:74-96)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, w, b):
+        shape = x.shape
+        cin, cout, npad = shape[-1], cfg.cout, cfg.npad
+        x2 = x.reshape(-1, cin)
+        if x2.dtype != BF16 or not x2.is_contiguous():
+            x2 = x2.to(BF16).contiguous()
+        y = ops.pw_gemm(x2, cfg.prep.get(cfg.i_w), npad, bias=cfg.prep.get(cfg.i_b) if b is not None else None)
+        ctx.cfg, ctx.shape, ctx.saved, ctx.plist = cfg, shape, (x2,), cfg.plist
+        return y[:, :cout].view(*shape[:-1], cout)
+
+    @staticmethod
+    def backward(ctx, gout):
+        cfg = ctx.cfg
+        cin, cout, npad = ctx.shape[-1], cfg.cout, cfg.npad
+        (x2,) = ctx.saved
+        M = x2.shape[0]
+        g = gout.reshape(M, cout)
+        if npad != cout:
+            gp = torch.zeros((M, npad), device=g.device, dtype=BF16)
+            gp[:, :cout] = g
+            g = gp
+        elif g.dtype != BF16 or not g.is_contiguous():
+            g = g.to(BF16).contiguous()
+        has_b = len(ctx.plist) > 1
+        D = _Dst(cfg, ctx.plist, g.device, npad * cin + npad + 64, 8, npad == cout)
+        if npad == cout:
+            ops.pw_wgrad_side(g, x2, npad, cin, dW=D.mat(0, npad, cin), dbias=D.mat(1, 1, npad).view(npad) if has_b else None)
+        else:
+            dW, db = D.ar.f32(npad, cin), D.ar.f32(npad)
+            ops.pw_wgrad_side(g, x2, npad, cin, dW=dW, dbias=db if has_b else None)
+            D.grads[0] = dW[:cout]
+            if has_b:
+                D.grads[1] = db[:cout]
+        dx = ops.pw_gemm(g, cfg.prep.get(cfg.i_wt), cin, K=npad)
+        ops.join_side()
+        grads = D.finish()
+        return (dx.view(ctx.shape), None, grads[0], grads[1] if has_b else None)
+
+
+class GlobalPoolFn(torch.autograd.Function):
+    """GlobalPool(mean) on [B, C, H, W] (cvnets/layers/global_pool.py:60-71)."""
+
+    @staticmethod
+    def forward(ctx, x, keep_dim):
+        B, C, H, W = x.shape
+        out = ops.global_pool_fwd(as_2d(x), B, H * W)
+        ctx.dims = (B, C, H, W)
+        return out.view(B, C, 1, 1) if keep_dim else out
+
+    @staticmethod
+    def backward(ctx, gout):
+        B, C, H, W = ctx.dims
+        g = gout.reshape(B, C)
+        if g.dtype != BF16 or not g.is_contiguous():
+            g = g.to(BF16).contiguous()
+        return to_4d(ops.global_pool_bwd(g, B, H * W), B, H, W), None
+
+
+# ==================================================================================================================
 # Transformer rows (SURVEY.md 8a a10-a12): MultiHeadAttention (cvnets/layers/multi_head_attention.py:135-239) and the pre-norm
 # TransformerEncoder (cvnets/modules/transformer.py:129-156) on token matrices [M = N*S, C] (bf16).  LayerNorm is the GroupNorm
 # load mode of the consuming GEMM with rows_per_sample = 1 (per-token statistics); its backward is the one-pass

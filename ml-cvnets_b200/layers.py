@@ -4,7 +4,9 @@ reference's isinstance/name based machinery (weight init, BN momentum annealing,
 keeps working.  Parameters are ordinary ``nn.Parameter``s inside ordinary ``nn.Conv2d`` / ``nn.BatchNorm2d`` /
 ``nn.GroupNorm`` / ``nn.Linear`` children; only ``forward`` is ours and it runs hand-written sm_100a kernels.
 
-There is deliberately NO PyTorch fallback: a layer used outside a fused module raises unless its own kernel path exists.
+There is deliberately NO PyTorch fallback.  Inside InvertedResidual / MobileViTBlockv2 / TransformerEncoder the layers are parameter
+containers executed by the fused autograd functions; used on their own they run the stand-alone functions of functional.py (same
+kernels, one layer per function).  What has no kernel path (dense k x k convs other than the stem, dilation, dropout p > 0) raises.
 """
 from __future__ import annotations
 
@@ -68,8 +70,16 @@ class LayerNorm2D_NCHW(nn.GroupNorm):
         super().__init__(num_channels=num_features, eps=eps, affine=elementwise_affine, num_groups=1)
         self.num_channels = num_features
 
-    def forward(self, x: Tensor) -> Tensor:  # only ever applied inside the fused MobileViTBlockv2 path
-        raise NotImplementedError("LayerNorm2D_NCHW runs fused inside MobileViTBlockv2 (no standalone kernel path)")
+    def forward(self, x: Tensor) -> Tensor:
+        """Stand-alone use (inside MobileViTBlockv2 the norm is a load mode of the consuming GEMM)."""
+        from types import SimpleNamespace
+        from . import functional as Fn
+        _need_cuda(x, "LayerNorm2D_NCHW")
+        if x.dim() != 4 or x.shape[1] % 8 or not self.affine:
+            raise NotImplementedError("LayerNorm2D_NCHW: expects [B, C, H, W] with C % 8 == 0 and affine=True")
+        cfg = SimpleNamespace(eps=float(self.eps), ws=getattr(self, "_ws", None), plist=[self.weight, self.bias])
+        self._cfg = cfg
+        return Fn.GroupNorm1Fn.apply(Fn.to_bf16_cl(x), cfg, self.weight, self.bias)
 
     def __repr__(self):
         return "{}(num_channels={}, eps={}, affine={})".format(self.__class__.__name__, self.num_channels, self.eps, self.affine)
@@ -83,7 +93,24 @@ class LayerNorm(nn.LayerNorm):
         super().__init__(normalized_shape=normalized_shape, eps=eps, elementwise_affine=elementwise_affine)
 
     def forward(self, x: Tensor) -> Tensor:
-        raise NotImplementedError("LayerNorm runs fused inside TransformerEncoder (no standalone kernel path)")
+        """Stand-alone use on [..., C] (inside TransformerEncoder the norm is a load mode of the consuming GEMM)."""
+        from types import SimpleNamespace
+        from . import functional as Fn
+        _need_cuda(x, self.__class__.__name__)
+        C = self.normalized_shape[0]
+        if len(self.normalized_shape) != 1 or x.shape[-1] != C or C % 8 or C > 1024 or not self.elementwise_affine:
+            raise NotImplementedError("LayerNorm: last-dimension normalisation with C % 8 == 0, C <= 1024 and affine weights is implemented")
+        if x.dim() > 2 and x.shape[1] == C:
+            raise NotImplementedError("LayerNorm on a channel-first tensor (x.shape[1] == C, layer_norm.py:52-65) is not implemented")
+        cfg = SimpleNamespace(eps=float(self.eps), ws=getattr(self, "_ws", None), plist=[self.weight, self.bias])
+        self._cfg = cfg
+        return Fn.LayerNormFn.apply(x, cfg, self.weight, self.bias)
+
+
+class LayerNormFP32(LayerNorm):
+    """cvnets/layers/normalization/layer_norm.py:111-137 (``layer_norm_fp32``, the ViT-B recipe's norm): the reference upcasts the
+    input to fp32 around nn.LayerNorm.  Here every LayerNorm already computes its statistics and the normalisation in fp32 from the
+    bf16 activation, so the two classes share one kernel path; the class exists for the registry name / isinstance checks."""
 
 
 class GELU(nn.GELU):
@@ -96,6 +123,11 @@ class GELU(nn.GELU):
 norm_layers_tuple = (nn.BatchNorm2d, nn.GroupNorm, nn.LayerNorm)
 
 
+def _need_cuda(x: Tensor, who: str):
+    if not x.is_cuda:
+        raise RuntimeError(f"{who}: ml-cvnets_b200 runs on CUDA (sm_100a) only and has no CPU fallback; got a {x.device} tensor")
+
+
 def get_normalization_layer(opts, num_features: int, norm_type: Optional[str] = None, *args, **kwargs) -> nn.Module:
     """cvnets/layers/normalization_layers.py: factory restricted to the norms on the hot path."""
     norm_type = norm_type or _opt(opts, "model.normalization.name", "batch_norm")
@@ -106,7 +138,9 @@ def get_normalization_layer(opts, num_features: int, norm_type: Optional[str] = 
         return LayerNorm2D_NCHW(num_features=num_features)
     if norm_type == "layer_norm":
         return LayerNorm(num_features)
-    raise NotImplementedError(f"normalization '{norm_type}' is not on the B200 hot path (batch_norm, layer_norm_2d, layer_norm are)")
+    if norm_type == "layer_norm_fp32":
+        return LayerNormFP32(num_features)
+    raise NotImplementedError(f"normalization '{norm_type}' is not on the B200 hot path (batch_norm, layer_norm_2d, layer_norm, layer_norm_fp32 are)")
 
 
 def build_activation_layer(opts, *args, **kwargs) -> nn.Module:
@@ -160,17 +194,54 @@ class ConvLayer2d(BaseLayer):
         self.stride, self.groups, self.kernel_size, self.bias, self.dilation = st, groups, ks, bias, dl
         self._stem = None
 
-    def forward(self, x: Tensor) -> Tensor:
-        """Standalone use is supported for the MobileViT stem pattern (3 -> C0, 3x3, stride 2, BN, SiLU)."""
+    def forward(self, x: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+        """Stand-alone use: the MobileViT stem pattern (3 -> C0, 3x3, stride 2, BN, Swish), any 1x1 conv (+bias) [+BatchNorm] [+Swish/GELU]
+        and the depthwise 3x3 conv [+BatchNorm] [+Swish].  ``residual`` (1x1 only, extension) is added in the GEMM epilogue."""
+        from types import SimpleNamespace
+        from . import functional as Fn
+        from . import ops
+        from .ops import PreparedWeights as PW
         conv = self.block.conv
+        _need_cuda(x, "ConvLayer2d")
         if (self.in_channels == 3 and self.kernel_size == (3, 3) and self.stride == (2, 2) and self.groups == 1
                 and self.dilation == (1, 1) and conv.bias is None and self.norm_name == "BatchNorm2d" and self.act_name is not None
                 and self.out_channels % 8 == 0):
             from .modules import _stem_forward
             return _stem_forward(self, x)
-        raise NotImplementedError(
-            "standalone ConvLayer2d.forward exists only for the MobileViT stem; other convs run fused inside "
-            "InvertedResidual / MobileViTBlockv2 (no PyTorch fallback by design)")
+        if self.norm_name not in (None, "BatchNorm2d") or self.act_name not in (None, "Swish", "GELU") or conv.padding_mode != "zeros":
+            raise NotImplementedError(f"stand-alone ConvLayer2d with norm={self.norm_name}, act={self.act_name} has no kernel path")
+        act = None if self.act_name is None else (ops.ACT_SILU if self.act_name == "Swish" else ops.ACT_GELU)
+        norm = self.block.norm if self.norm_name is not None else None
+        pointwise = self.kernel_size == (1, 1) and self.stride == (1, 1) and self.groups == 1
+        depthwise = (self.kernel_size == (3, 3) and self.groups == self.in_channels == self.out_channels and self.dilation == (1, 1)
+                     and self.stride in ((1, 1), (2, 2)) and conv.bias is None and tuple(conv.padding) == (1, 1))
+        if not (pointwise or depthwise) or self.in_channels % 8 or self.out_channels % 8:
+            raise NotImplementedError("stand-alone ConvLayer2d: 1x1 convs and depthwise 3x3 convs with channel counts that are multiples of 8 "
+                                      "have kernel paths (dense k x k convs other than the stem are SURVEY.md 8a row a9)")
+        if self._stem is None:
+            prep = PW()
+            cfg = SimpleNamespace(prep=prep, cout=self.out_channels, act=act, has_bias=conv.bias is not None, stride=self.stride[0])
+            if pointwise:
+                cfg.i_w = prep.add(conv.weight, PW.KIND_ROWMAJOR)
+                cfg.i_wt = prep.add(conv.weight, PW.KIND_TRANSPOSED)
+            else:
+                cfg.i_w = prep.add(conv.weight, PW.KIND_TAPMAJOR_F32)
+            self._stem = cfg
+        cfg = self._stem
+        cfg.bn = Fn.bn_cfg(norm) if norm is not None else None
+        cfg.ws = getattr(self, "_ws", None)
+        cfg.prep.prepare(force=self.training)
+        x = Fn.to_bf16_cl(x)
+        g, b = (norm.weight, norm.bias) if norm is not None else (None, None)
+        if pointwise:
+            cfg.plist = [conv.weight] + ([conv.bias] if conv.bias is not None else []) + ([g, b] if norm is not None else [])
+            return Fn.PointwiseConvFn.apply(x, cfg, Fn.to_bf16_cl(residual) if residual is not None else None, conv.weight, conv.bias, g, b)
+        if residual is not None:
+            raise NotImplementedError("residual is supported for 1x1 convs only")
+        if act not in (None, ops.ACT_SILU):
+            raise NotImplementedError("depthwise conv followed by an activation other than Swish")
+        cfg.plist = [conv.weight] + ([g, b] if norm is not None else [])
+        return Fn.DepthwiseConvFn.apply(x, cfg, conv.weight, g, b)
 
     def __repr__(self):
         s = self.block[0].__repr__()[:-1]
@@ -198,7 +269,26 @@ class LinearLayer(BaseLayer):
             nn.init.constant_(self.bias, 0)
 
     def forward(self, x: Tensor) -> Tensor:
-        raise NotImplementedError("LinearLayer runs fused with GlobalPool in the classifier head (PoolLinearFn)")
+        """Stand-alone use (the classifier head fuses it with GlobalPool; TransformerEncoder fuses its four linears)."""
+        from types import SimpleNamespace
+        from . import functional as Fn
+        from .ops import PreparedWeights as PW
+        _need_cuda(x, "LinearLayer")
+        if self.channel_first or x.shape[-1] != self.in_features or self.in_features % 8:
+            raise NotImplementedError("LinearLayer: channel-last inputs with in_features % 8 == 0 are implemented")
+        if getattr(self, "_cfg", None) is None:
+            prep = PW()
+            npad = (self.out_features + 7) // 8 * 8
+            cfg = SimpleNamespace(prep=prep, cout=self.out_features, npad=npad, i_w=prep.add(self.weight, PW.KIND_ROWMAJOR, dst_rows=npad),
+                                  i_wt=prep.add(self.weight, PW.KIND_TRANSPOSED, ldd=npad))
+            if self.bias is not None:
+                cfg.i_b = prep.add(self.bias, PW.KIND_VECTOR_F32, dst_rows=npad)
+            self._cfg = cfg
+        cfg = self._cfg
+        cfg.ws = getattr(self, "_ws", None)
+        cfg.plist = [self.weight] + ([self.bias] if self.bias is not None else [])
+        cfg.prep.prepare(force=self.training)
+        return Fn.LinearFn.apply(x, cfg, self.weight, self.bias)
 
     def __repr__(self):
         return "{}(in_features={}, out_features={}, bias={}, channel_first={})".format(
@@ -215,7 +305,11 @@ class GlobalPool(BaseLayer):
         self.pool_type, self.keep_dim = pool_type, keep_dim
 
     def forward(self, x: Tensor) -> Tensor:
-        raise NotImplementedError("GlobalPool runs fused with the classifier LinearLayer (PoolLinearFn)")
+        from . import functional as Fn
+        _need_cuda(x, "GlobalPool")
+        if x.dim() != 4 or x.shape[1] % 8:
+            raise NotImplementedError("GlobalPool: expects [B, C, H, W] with C % 8 == 0")
+        return Fn.GlobalPoolFn.apply(Fn.to_bf16_cl(x), self.keep_dim)
 
     def __repr__(self):
         return "{}(type={})".format(self.__class__.__name__, self.pool_type)
@@ -234,9 +328,33 @@ class LinearSelfAttention(BaseLayer):
                                     use_norm=False, use_act=False)
         self.embed_dim = embed_dim
 
-    def forward(self, x: Tensor, x_prev: Optional[Tensor] = None, *args, **kwargs) -> Tensor:
-        raise NotImplementedError("LinearSelfAttention runs fused inside MobileViTBlockv2 (self-attention on [B,C,H,W]); "
-                                  "the cross-attention (video) path is out of scope (SURVEY.md App. A5)")
+    def forward(self, x: Tensor, x_prev: Optional[Tensor] = None, *args, residual: Optional[Tensor] = None, **kwargs) -> Tensor:
+        """Stand-alone self-attention on x [B, d, P, N] / cross-attention against x_prev [B, d, P, M] (linear_attention.py:134-215).
+        Inside MobileViTBlockv2 the same kernels run on the folded feature map.  ``residual`` (extension) is added in out_proj's epilogue."""
+        from types import SimpleNamespace
+        from . import functional as Fn
+        from .ops import PreparedWeights as PW
+        _need_cuda(x, "LinearSelfAttention")
+        d = self.embed_dim
+        if x.dim() != 4 or x.shape[1] != d or d % 8 or self.attn_dropout.p:
+            raise NotImplementedError("LinearSelfAttention: expects [B, d, P, N] with d % 8 == 0 and attn_dropout == 0")
+        if self.qkv_proj.block.conv.bias is None or self.out_proj.block.conv.bias is None:
+            raise NotImplementedError("LinearSelfAttention with bias=False is not implemented")
+        if getattr(self, "_cfg", None) is None:
+            prep = PW()
+            wq, bq, wo = self.qkv_proj.block.conv.weight, self.qkv_proj.block.conv.bias, self.out_proj.block.conv.weight
+            # reference row order [q, K(d), V(d)] -> kernel order [K, V, q, pad(7)]  (rot = 1)
+            self._cfg = SimpleNamespace(prep=prep, i_wqkv=prep.add(wq, PW.KIND_ROWMAJOR, rot=1, dst_rows=2 * d + 8),
+                                        i_wqkvt=prep.add(wq, PW.KIND_TRANSPOSED, rot=1, ldd=2 * d + 8),
+                                        i_bqkv=prep.add(bq, PW.KIND_VECTOR_F32, rot=1, dst_rows=2 * d + 8),
+                                        i_wo=prep.add(wo, PW.KIND_ROWMAJOR), i_wot=prep.add(wo, PW.KIND_TRANSPOSED))
+        cfg = self._cfg
+        cfg.ws = getattr(self, "_ws", None)
+        cfg.plist = [self.qkv_proj.block.conv.weight, self.qkv_proj.block.conv.bias, self.out_proj.block.conv.weight, self.out_proj.block.conv.bias]
+        cfg.prep.prepare(force=self.training)
+        xp = Fn.to_bf16_cl(x_prev) if x_prev is not None else None
+        res = Fn.to_bf16_cl(residual) if residual is not None else None
+        return Fn.LinearSelfAttentionFn.apply(Fn.to_bf16_cl(x), cfg, xp, res, *cfg.plist)
 
     def __repr__(self):
         return "{}(embed_dim={}, attn_dropout={})".format(self.__class__.__name__, self.embed_dim, self.attn_dropout.p)

@@ -139,7 +139,16 @@ class LinearAttnFFN(BaseModule):
         self.attn_dropout_p = attn_dropout
 
     def forward(self, x: Tensor, x_prev: Optional[Tensor] = None, *args, **kwargs) -> Tensor:
-        raise NotImplementedError("LinearAttnFFN runs fused inside MobileViTBlockv2 (no standalone kernel path)")
+        """Stand-alone use on the unfolded tensor [B, d, P, N] (transformer.py:248-264), self- or cross-attention: the layers' own
+        kernel paths composed, residual additions inside the out_proj / second FFN conv epilogues.  Inside MobileViTBlockv2 the unit runs
+        in the block's fused function instead."""
+        _require_cuda(x, "LinearAttnFFN")
+        if self.std_dropout or self.ffn_dropout or self.attn_dropout_p:
+            raise NotImplementedError("dropout > 0 is not implemented")
+        norm1, attn = self.pre_norm_attn[0], self.pre_norm_attn[1]
+        x = attn(norm1(x), x_prev, residual=x)      # x + LSA(GN(x)[, x_prev])   (:253 / :254-260)
+        norm2, conv1, conv2 = self.pre_norm_ffn[0], self.pre_norm_ffn[1], self.pre_norm_ffn[3]
+        return conv2(conv1(norm2(x)), residual=x)   # x + conv(act(conv(GN(x))))  (:263)
 
     def __repr__(self) -> str:
         return "{}(embed_dim={}, ffn_dim={}, dropout={}, ffn_dropout={}, attn_fn={}, norm_layer={})".format(

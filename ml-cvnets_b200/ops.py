@@ -329,26 +329,59 @@ def gn_bwd_apply(G: Tensor, X: Tensor, gn: Tensor, sstats: Tensor, count: float,
 
 
 # ---------------------------------------------------------------------------------------------------------- attention
-def linattn_fwd(QKV: Tensor, B: int, H: int, W: int, d: int):
+def linattn_fwd(QKV: Tensor, B: int, H: int, W: int, d: int, patch: int = 2):
+    """patch = 2: QKV is the folded feature map [B, H, W, ld] (2x2 patches by indexing); patch = 0: QKV is the unfolded [B, P=H, N=W, ld]."""
     lib = _lib()
     M = QKV.shape[0]
-    N = (H // 2) * (W // 2)
+    Pp, N = (4, (H // 2) * (W // 2)) if patch == 2 else (H, W)
     O = torch.empty((M, d), device=QKV.device, dtype=torch.bfloat16)
-    S = torch.empty((B, 4, N), device=QKV.device, dtype=torch.float32)
-    CTX = torch.empty((B, 4, d), device=QKV.device, dtype=torch.float32)
-    L.check(lib.cvb_linattn_fwd(QKV.data_ptr(), QKV.stride(0), B, H, W, d, 2, O.data_ptr(), O.stride(0), S.data_ptr(), CTX.data_ptr(), _stream()),
+    S = torch.empty((B, Pp, N), device=QKV.device, dtype=torch.float32)
+    CTX = torch.empty((B, Pp, d), device=QKV.device, dtype=torch.float32)
+    L.check(lib.cvb_linattn_fwd(QKV.data_ptr(), QKV.stride(0), B, H, W, d, patch, O.data_ptr(), O.stride(0), S.data_ptr(), CTX.data_ptr(), _stream()),
             "cvb_linattn_fwd")
     _count()
     return O, S, CTX
 
 
-def linattn_bwd(QKV: Tensor, DO: Tensor, S: Tensor, CTX: Tensor, B: int, H: int, W: int, d: int, dbias: Optional[Tensor] = None) -> Tensor:
+def linattn_bwd(QKV: Tensor, DO: Tensor, S: Tensor, CTX: Tensor, B: int, H: int, W: int, d: int, dbias: Optional[Tensor] = None,
+                patch: int = 2) -> Tensor:
     lib = _lib()
     DQKV = torch.empty_like(QKV)
-    L.check(lib.cvb_linattn_bwd(QKV.data_ptr(), QKV.stride(0), DO.data_ptr(), DO.stride(0), S.data_ptr(), CTX.data_ptr(), B, H, W, d, 2,
+    L.check(lib.cvb_linattn_bwd(QKV.data_ptr(), QKV.stride(0), DO.data_ptr(), DO.stride(0), S.data_ptr(), CTX.data_ptr(), B, H, W, d, patch,
                                 DQKV.data_ptr(), _p(dbias), _stream()), "cvb_linattn_bwd")
     _count()
     return DQKV
+
+
+def linattn_cross_fwd(QKP: Tensor, QKVX: Tensor, B: int, Pp: int, Mp: int, N: int, d: int):
+    """query/key from QKP [B*P*M, ld] (projection of x_prev), values from QKVX [B*P*N, ld] (projection of x)."""
+    O = torch.empty((B * Pp * N, d), device=QKP.device, dtype=torch.bfloat16)
+    S = torch.empty((B, Pp, Mp), device=QKP.device, dtype=torch.float32)
+    CTX = torch.empty((B, Pp, d), device=QKP.device, dtype=torch.float32)
+    L.check(_lib().cvb_linattn_cross_fwd(QKP.data_ptr(), QKP.stride(0), B, Pp, Mp, d, QKVX.data_ptr(), QKVX.stride(0), N, O.data_ptr(), O.stride(0),
+                                         S.data_ptr(), CTX.data_ptr(), _stream()), "cvb_linattn_cross_fwd")
+    _count()
+    return O, S, CTX
+
+
+def linattn_cross_bwd(QKP: Tensor, QKVX: Tensor, DO: Tensor, S: Tensor, CTX: Tensor, B: int, Pp: int, Mp: int, N: int, d: int,
+                      dbias: Optional[Tensor] = None):
+    DQKP, DQKVX = torch.zeros_like(QKP), torch.zeros_like(QKVX)  # the kernel writes k/q columns of the first, v columns of the second
+    L.check(_lib().cvb_linattn_cross_bwd(QKP.data_ptr(), QKP.stride(0), QKVX.data_ptr(), QKVX.stride(0), DO.data_ptr(), DO.stride(0), S.data_ptr(),
+                                         CTX.data_ptr(), B, Pp, Mp, N, d, DQKP.data_ptr(), DQKVX.data_ptr(), _p(dbias), _stream()),
+            "cvb_linattn_cross_bwd")
+    _count()
+    return DQKP, DQKVX
+
+
+def gn_bwd(V: Tensor, X: Tensor, gn: Tensor, gamma: Tensor, count: float, B: int, rows_per_sample: int, dgamma: Tensor, dbeta: Tensor, samp_ws: Tensor,
+           DRES: Optional[Tensor] = None) -> Tensor:
+    """Stand-alone GroupNorm(1, C) backward (two launches); dgamma/dbeta fp64 [C] accumulators, samp_ws zeroed fp64 [2, B]."""
+    DX = torch.empty_like(V)
+    L.check(_lib().cvb_gn_bwd(V.data_ptr(), X.data_ptr(), gn[0].data_ptr(), gn[1].data_ptr(), gamma.data_ptr(), float(count), _p(DRES), DX.data_ptr(), B,
+                              rows_per_sample, V.shape[1], dgamma.data_ptr(), dbeta.data_ptr(), samp_ws.data_ptr(), _stream()), "cvb_gn_bwd")
+    _count(2)
+    return DX
 
 
 def mha_fwd(QKV: Tensor, B: int, S: int, H: int, head_dim: int, scale: float, attn_mask: Optional[Tensor] = None,

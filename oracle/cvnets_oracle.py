@@ -109,14 +109,26 @@ def layer_norm_2d(P: Params, pre: str, x: Tensor) -> Tensor:
     return F.group_norm(x, 1, P[pre + ".weight"], P[pre + ".bias"], GN_EPS)
 
 
-def linear_self_attention(P: Params, pre: str, x: Tensor) -> Tensor:
-    """LinearSelfAttention._forward_self_attn (cvnets/layers/linear_attention.py:134-161).
+def linear_self_attention(P: Params, pre: str, x: Tensor, x_prev: Optional[Tensor] = None) -> Tensor:
+    """LinearSelfAttention._forward_self_attn (cvnets/layers/linear_attention.py:134-161) and, with ``x_prev`` [B, d, P, M],
+    _forward_cross_attn (:163-207): query + key are projected from x_prev with the first 1+d rows of the packed weight, the
+    value from x with the last d rows; softmax / context over M.
 
     x: [B, d, P, N].  qkv 1x1 (d -> 1+2d, bias) -> split [1, d, d] -> softmax over N (dim=-1) ->
     ctx = sum_N(key * scores) -> relu(value) * ctx -> out_proj 1x1 (d -> d, bias).
     """
     d = x.shape[1]
-    qkv = F.conv2d(x, P[pre + ".qkv_proj.block.conv.weight"], P[pre + ".qkv_proj.block.conv.bias"])
+    w, b = P[pre + ".qkv_proj.block.conv.weight"], P[pre + ".qkv_proj.block.conv.bias"]
+    if x_prev is not None:
+        assert x_prev.shape[2] == x.shape[2], "The number of pixels in a patch for query and key_value should be the same"
+        qk = F.conv2d(x_prev, w[: d + 1], b[: d + 1])
+        query, key = torch.split(qk, [1, d], dim=1)
+        value = F.conv2d(x, w[d + 1:], b[d + 1:])
+        context_scores = F.softmax(query, dim=-1)
+        context_vector = (key * context_scores).sum(dim=-1, keepdim=True)
+        out = F.relu(value) * context_vector.expand_as(value)
+        return F.conv2d(out, P[pre + ".out_proj.block.conv.weight"], P[pre + ".out_proj.block.conv.bias"])
+    qkv = F.conv2d(x, w, b)
     query, key, value = torch.split(qkv, [1, d, d], dim=1)
     context_scores = F.softmax(query, dim=-1)
     context_vector = (key * context_scores).sum(dim=-1, keepdim=True)
@@ -124,14 +136,15 @@ def linear_self_attention(P: Params, pre: str, x: Tensor) -> Tensor:
     return F.conv2d(out, P[pre + ".out_proj.block.conv.weight"], P[pre + ".out_proj.block.conv.bias"])
 
 
-def linear_attn_ffn(P: Params, pre: str, x: Tensor) -> Tensor:
-    """LinearAttnFFN.forward, self-attention branch (cvnets/modules/transformer.py:248-264), dropout p=0.
+def linear_attn_ffn(P: Params, pre: str, x: Tensor, x_prev: Optional[Tensor] = None) -> Tensor:
+    """LinearAttnFFN.forward (cvnets/modules/transformer.py:248-264), dropout p=0; with ``x_prev`` the cross-attention branch (:254-260:
+    only x is normalised, x_prev enters the attention raw).
 
-    x = x + LSA(GN1(x));  x = x + conv1x1(silu(conv1x1(GN1(x)))).  Child indices: pre_norm_attn.{0,1},
+    x = x + LSA(GN1(x)[, x_prev]);  x = x + conv1x1(silu(conv1x1(GN1(x)))).  Child indices: pre_norm_attn.{0,1},
     pre_norm_ffn.{0,1,3} (``:192-228``).
     """
     a = layer_norm_2d(P, pre + ".pre_norm_attn.0", x)
-    x = x + linear_self_attention(P, pre + ".pre_norm_attn.1", a)
+    x = x + linear_self_attention(P, pre + ".pre_norm_attn.1", a, x_prev)
     f = layer_norm_2d(P, pre + ".pre_norm_ffn.0", x)
     f = F.silu(F.conv2d(f, P[pre + ".pre_norm_ffn.1.block.conv.weight"], P[pre + ".pre_norm_ffn.1.block.conv.bias"]))
     f = F.conv2d(f, P[pre + ".pre_norm_ffn.3.block.conv.weight"], P[pre + ".pre_norm_ffn.3.block.conv.bias"])

@@ -1,0 +1,102 @@
+"""Round-2 golden fixtures FROM THE REAL REFERENCE (apple/ml-cvnets @ /root/reference); see make_golden.py for the method.
+
+  * ``lsa_cross`` / ``laffn_cross``: LinearSelfAttention / LinearAttnFFN cross-attention (linear_attention.py:163-207, transformer.py:254-260)
+  * ``pw_bn_act`` / ``pw_bias`` / ``dw_bn_act`` / ``ln2d`` / ``ln`` / ``ln_fp32`` / ``linear`` / ``pool``: the stand-alone layers
+  * ``model_b16``: MobileViTv2-1.0, batch 16 at 128x128, train mode -- a WELL-CONDITIONED end-to-end fixture (the batch-2
+    fixtures let train-mode BatchNorm amplify bf16 rounding to ~10 %): logits, loss and every gradient tensor <= 64k elements.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_r2.py
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from make_golden import O, F, ConvLayer2d, LinearSelfAttention, LinearAttnFFN, get_model, load_seeded, make_opts, run_module, strip, torch  # noqa: E402
+
+from cvnets.layers import GlobalPool, LinearLayer  # noqa: E402
+from cvnets.layers.normalization.layer_norm import LayerNorm, LayerNorm2D_NCHW, LayerNormFP32  # noqa: E402
+
+
+def run_cross(module, x, xp, gy_seed):
+    module.train()
+    x = x.clone().requires_grad_(True)
+    xp = xp.clone().requires_grad_(True)
+    y = module(x, xp)
+    gy = O.seeded_input(tuple(y.shape), gy_seed)
+    y.backward(gy)
+    return {"x": x.detach().clone(), "x_prev": xp.detach().clone(), "y": y.detach().clone(), "gy": gy, "gx": x.grad.clone(), "gx_prev": xp.grad.clone(),
+            "grads": {k: p.grad.clone() for k, p in module.named_parameters()}, "buffers": {}}
+
+
+def main():
+    torch.manual_seed(0)
+    opts = make_opts(1.0)
+    fx = {}
+    P = {}
+    O._conv_bn(P, "m.qkv_proj", 16, 33, 1, norm=False, bias=True)
+    O._conv_bn(P, "m.out_proj", 16, 16, 1, norm=False, bias=True)
+    m = LinearSelfAttention(opts, embed_dim=16, attn_dropout=0.0, bias=True)
+    load_seeded(m, strip("m.", P), 34)
+    fx["lsa_cross"] = dict(cfg=dict(d=16), seed=34, **run_cross(m, O.seeded_input((2, 16, 4, 9), 134), O.seeded_input((2, 16, 4, 12), 135), 234))
+    P = {}
+    O.linear_attn_ffn_shapes(P, "m", 16, 32)
+    m = LinearAttnFFN(opts, embed_dim=16, ffn_latent_dim=32, attn_dropout=0.0, dropout=0.0, ffn_dropout=0.0)
+    load_seeded(m, strip("m.", P), 35)
+    fx["laffn_cross"] = dict(cfg=dict(d=16, ffn=32), seed=35, **run_cross(m, O.seeded_input((2, 16, 4, 9), 136), O.seeded_input((2, 16, 4, 12), 137), 235))
+
+    # ---- stand-alone layers
+    P = {}
+    O._conv_bn(P, "m", 16, 24, 1)
+    m = ConvLayer2d(opts, 16, 24, 1, use_norm=True, use_act=True)
+    load_seeded(m, strip("m.", P), 36)
+    fx["pw_bn_act"] = dict(cfg=dict(cin=16, cout=24), seed=36, **run_module(m, O.seeded_input((3, 16, 6, 5), 138), 238))
+    P = {}
+    O._conv_bn(P, "m", 16, 24, 1, norm=False, bias=True)
+    m = ConvLayer2d(opts, 16, 24, 1, use_norm=False, use_act=False, bias=True)
+    load_seeded(m, strip("m.", P), 37)
+    fx["pw_bias"] = dict(cfg=dict(cin=16, cout=24), seed=37, **run_module(m, O.seeded_input((3, 16, 6, 5), 139), 239))
+    P = {}
+    O._conv_bn(P, "m", 16, 16, 3, groups=16)
+    m = ConvLayer2d(opts, 16, 16, 3, stride=2, groups=16, use_norm=True, use_act=True)
+    load_seeded(m, strip("m.", P), 38)
+    fx["dw_bn_act"] = dict(cfg=dict(c=16, stride=2), seed=38, **run_module(m, O.seeded_input((3, 16, 8, 8), 140), 240))
+    for name, cls, shape in (("ln2d", LayerNorm2D_NCHW, (3, 16, 4, 9)), ("ln", LayerNorm, (3, 7, 32)), ("ln_fp32", LayerNormFP32, (3, 7, 32))):
+        C = shape[1] if name == "ln2d" else shape[-1]
+        P = {}
+        O._gn(P, "m", C)
+        m = cls(C)
+        load_seeded(m, strip("m.", P), 39)
+        fx[name] = dict(cfg=dict(c=C), seed=39, **run_module(m, O.seeded_input(shape, 141), 241))
+    P = {}
+    O._linear(P, "m", 32, 40)
+    m = LinearLayer(32, 40, bias=True)
+    load_seeded(m, strip("m.", P), 40)
+    fx["linear"] = dict(cfg=dict(cin=32, cout=40), seed=40, **run_module(m, O.seeded_input((3, 7, 32), 142), 242))
+    m = GlobalPool(pool_type="mean", keep_dim=False)
+    fx["pool"] = dict(cfg={}, seed=0, **run_module(m, O.seeded_input((3, 16, 5, 4), 143), 243))
+    torch.save(fx, os.path.join(HERE, "standalone_fp32.pt"))
+
+    # ---- well-conditioned model fixture
+    width, res, seed, B = 1.0, 128, 41, 16
+    model = get_model(make_opts(width))
+    P = O.mobilevit_v2_shapes(width)
+    load_seeded(model, P, seed)
+    model.train()
+    x = O.seeded_input((B, 3, res, res), 300 + seed)
+    labels = (torch.arange(B) * 61) % 1000
+    logits = model(x)
+    loss = F.cross_entropy(logits, labels, label_smoothing=0.1)
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    fixture = dict(width=width, res=res, seed=seed, x_seed=300 + seed, batch=B, labels=labels, logits=logits.detach().clone(), loss=loss.detach().clone(),
+                   grad_norms={k: float(g.norm()) for k, g in grads.items()},
+                   grads={k: g.clone().half() if g.numel() > 4096 else g.clone() for k, g in grads.items() if g.numel() <= 65536},
+                   buffers_after={k: b.detach().clone() for k, b in model.named_buffers() if b.numel() <= 4096})
+    torch.save(fixture, os.path.join(HERE, "mobilevit_v2_b16_fp32.pt"))
+    for fn in ("standalone_fp32.pt", "mobilevit_v2_b16_fp32.pt"):
+        print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

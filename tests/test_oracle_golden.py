@@ -166,3 +166,49 @@ def test_transformer_encoder(tfx, name):
     P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
     x, y = _run(lambda P, x: O.transformer_encoder(P, "m", x, c["heads"], act=c["act"], eps=c["eps"]), P, fx)
     _check_nobuf(P, fx, x, y)
+
+
+# ---------------------------------------------------------------------------------------- round-2 fixtures (make_golden_r2.py)
+@pytest.fixture(scope="module")
+def standalone(golden_dir):
+    return torch.load(os.path.join(golden_dir, "standalone_fp32.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["lsa_cross", "laffn_cross"])
+def test_cross_attention(standalone, name):
+    """LinearSelfAttention / LinearAttnFFN cross-attention branch against the real reference (linear_attention.py:163-207)."""
+    fx = standalone[name]
+    shapes = {}
+    if name == "lsa_cross":
+        O._conv_bn(shapes, "m.qkv_proj", 16, 33, 1, norm=False, bias=True)
+        O._conv_bn(shapes, "m.out_proj", 16, 16, 1, norm=False, bias=True)
+        fn = O.linear_self_attention
+    else:
+        O.linear_attn_ffn_shapes(shapes, "m", fx["cfg"]["d"], fx["cfg"]["ffn"])
+        fn = O.linear_attn_ffn
+    P = O.clone_params(O.seeded_fill_(shapes, fx["seed"]))
+    x, xp = fx["x"].clone().requires_grad_(True), fx["x_prev"].clone().requires_grad_(True)
+    y = fn(P, "m", x, xp)
+    y.backward(fx["gy"])
+    assert torch.allclose(y, fx["y"], atol=2e-5, rtol=2e-5)
+    assert torch.allclose(x.grad, fx["gx"], atol=2e-5, rtol=2e-4) and torch.allclose(xp.grad, fx["gx_prev"], atol=2e-5, rtol=2e-4)
+    for k, g in fx["grads"].items():
+        assert torch.allclose(P["m." + k].grad, g, atol=5e-5, rtol=5e-4), k
+
+
+def test_model_batch16_fixture(golden_dir):
+    """The well-conditioned end-to-end fixture (batch 16, 128x128, train mode): oracle == real reference (logits, loss, gradients)."""
+    import torch.nn.functional as F
+    fx = torch.load(os.path.join(golden_dir, "mobilevit_v2_b16_fp32.pt"), weights_only=False)
+    P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(fx["width"]), fx["seed"]))
+    x = O.seeded_input((fx["batch"], 3, fx["res"], fx["res"]), fx["x_seed"])
+    logits = O.mobilevit_v2_forward(P, x, width_multiplier=fx["width"], training=True)
+    loss = F.cross_entropy(logits, fx["labels"], label_smoothing=0.1)
+    loss.backward()
+    assert float((logits - fx["logits"]).norm() / fx["logits"].norm()) <= 2e-5
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5
+    for k, n in fx["grad_norms"].items():
+        assert abs(float(P[k].grad.norm()) - n) <= 2e-3 * n + 1e-7, k
+    for k, g in fx["grads"].items():
+        e = float((P[k].grad - g.float()).norm() / (g.float().norm() + 1e-12))
+        assert e <= (2e-3 if g.dtype == torch.float16 else 2e-4), (k, e)

@@ -1,0 +1,136 @@
+"""Stand-alone drop-in layers (-m gpu): the layers north_star names as drop-in nn.Modules (LinearSelfAttention incl. cross-attention,
+LinearAttnFFN, ConvLayer2d 1x1 / depthwise, LayerNorm2D_NCHW, LayerNorm / LayerNormFP32, LinearLayer, GlobalPool) used OUTSIDE the fused
+blocks, against fixtures generated from the real reference (tests/golden/make_golden.py, make_golden_r2.py).  Tolerances as in
+test_modules_gpu.py: bf16 activations (rel-L2 <= 2e-2 outputs, 4e-2 input gradients, 5e-2 parameter gradients or 3x torch-autocast)."""
+import os
+
+import pytest
+import torch
+
+from oracle import cvnets_oracle as O
+from tests.test_modules_gpu import autocast_errors, load_seeded, rel_l2, run_and_check  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import ml_cvnets_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def mods(golden_dir):
+    d = torch.load(os.path.join(golden_dir, "modules_fp32.pt"), weights_only=False)
+    d.update(torch.load(os.path.join(golden_dir, "standalone_fp32.pt"), weights_only=False))
+    return d
+
+
+def _lsa_shapes(d=16):
+    shapes = {}
+    O._conv_bn(shapes, "m.qkv_proj", d, 2 * d + 1, 1, norm=False, bias=True)
+    O._conv_bn(shapes, "m.out_proj", d, d, 1, norm=False, bias=True)
+    return shapes
+
+
+def test_linear_self_attention_standalone(pkg, mods):
+    fx = mods["lsa"]
+    shapes = _lsa_shapes()
+    auto = autocast_errors(lambda P, x: O.linear_self_attention(P, "m", x), shapes, fx["seed"], fx)
+    m = load_seeded(pkg.LinearSelfAttention(pkg.default_opts(), embed_dim=16), shapes, fx["seed"])
+    run_and_check(m, fx, auto=auto)
+
+
+def test_linear_attn_ffn_standalone(pkg, mods):
+    fx = mods["laffn"]
+    shapes = {}
+    O.linear_attn_ffn_shapes(shapes, "m", 16, 32)
+    auto = autocast_errors(lambda P, x: O.linear_attn_ffn(P, "m", x), shapes, fx["seed"], fx)
+    m = load_seeded(pkg.LinearAttnFFN(pkg.default_opts(), embed_dim=16, ffn_latent_dim=32, dropout=0.0), shapes, fx["seed"])
+    run_and_check(m, fx, auto=auto)
+
+
+@pytest.mark.parametrize("name", ["lsa_cross", "laffn_cross"])
+def test_cross_attention(pkg, mods, name):
+    fx = mods[name]
+    if name == "lsa_cross":
+        shapes = _lsa_shapes()
+        m = load_seeded(pkg.LinearSelfAttention(pkg.default_opts(), embed_dim=16), shapes, fx["seed"])
+    else:
+        shapes = {}
+        O.linear_attn_ffn_shapes(shapes, "m", 16, 32)
+        m = load_seeded(pkg.LinearAttnFFN(pkg.default_opts(), embed_dim=16, ffn_latent_dim=32, dropout=0.0), shapes, fx["seed"])
+    x, xp = fx["x"].cuda().requires_grad_(True), fx["x_prev"].cuda().requires_grad_(True)
+    y = m(x, xp)
+    y.backward(fx["gy"].cuda().to(y.dtype))
+    assert rel_l2(y, fx["y"]) <= 2e-2
+    assert rel_l2(x.grad, fx["gx"]) <= 4e-2 and rel_l2(xp.grad, fx["gx_prev"]) <= 4e-2
+    named = dict(m.named_parameters())
+    for k, g in fx["grads"].items():
+        small = float(g.norm()) < 1e-3 * float(fx["gy"].norm())
+        assert rel_l2(named[k].grad, g) <= 6e-2 or small, (k, rel_l2(named[k].grad, g))
+
+
+@pytest.mark.parametrize("name", ["pw_bn_act", "pw_bias", "dw_bn_act"])
+def test_conv_layer_standalone(pkg, mods, name):
+    fx = mods[name]
+    c = fx["cfg"]
+    shapes = {}
+    if name == "dw_bn_act":
+        O._conv_bn(shapes, "m", c["c"], c["c"], 3, groups=c["c"])
+        m = pkg.ConvLayer2d(pkg.default_opts(), c["c"], c["c"], 3, stride=c["stride"], groups=c["c"], use_norm=True, use_act=True)
+    elif name == "pw_bn_act":
+        O._conv_bn(shapes, "m", c["cin"], c["cout"], 1)
+        m = pkg.ConvLayer2d(pkg.default_opts(), c["cin"], c["cout"], 1, use_norm=True, use_act=True)
+    else:
+        O._conv_bn(shapes, "m", c["cin"], c["cout"], 1, norm=False, bias=True)
+        m = pkg.ConvLayer2d(pkg.default_opts(), c["cin"], c["cout"], 1, use_norm=False, use_act=False, bias=True)
+    run_and_check(load_seeded(m, shapes, fx["seed"]), fx)
+
+
+@pytest.mark.parametrize("name", ["ln2d", "ln", "ln_fp32"])
+def test_norm_layers_standalone(pkg, mods, name):
+    fx = mods[name]
+    shapes = {}
+    O._gn(shapes, "m", fx["cfg"]["c"])
+    cls = {"ln2d": pkg.LayerNorm2D_NCHW, "ln": pkg.LayerNorm, "ln_fp32": pkg.LayerNormFP32}[name]
+    run_and_check(load_seeded(cls(fx["cfg"]["c"]), shapes, fx["seed"]), fx)
+
+
+def test_linear_and_pool_standalone(pkg, mods):
+    fx = mods["linear"]
+    shapes = {}
+    O._linear(shapes, "m", fx["cfg"]["cin"], fx["cfg"]["cout"])
+    run_and_check(load_seeded(pkg.LinearLayer(fx["cfg"]["cin"], fx["cfg"]["cout"]), shapes, fx["seed"]), fx)
+    fx = mods["pool"]
+    run_and_check(pkg.GlobalPool(pool_type="mean").cuda(), fx)
+
+
+def test_model_batch16_reference_fixture(pkg, golden_dir):
+    """Well-conditioned end-to-end fixture from the REAL reference (batch 16, 128x128, train): fixed bounds, no comparator needed."""
+    import torch.nn.functional as F
+    fx = torch.load(os.path.join(golden_dir, "mobilevit_v2_b16_fp32.pt"), weights_only=False)
+    model = pkg.MobileViTv2(pkg.default_opts(width_multiplier=fx["width"]))
+    model.load_state_dict(O.seeded_fill_(O.mobilevit_v2_shapes(fx["width"]), fx["seed"]), strict=True)
+    model = model.cuda().train()
+    x = O.seeded_input((fx["batch"], 3, fx["res"], fx["res"]), fx["x_seed"]).cuda()
+    logits = model(x)
+    loss = F.cross_entropy(logits.float(), fx["labels"].cuda(), label_smoothing=0.1)
+    loss.backward()
+    e = rel_l2(logits, fx["logits"])
+    print(f"[b16 fixture] logits rel-L2 vs the reference {e:.4g}; loss {float(loss):.5f} vs {float(fx['loss']):.5f}")
+    assert e <= 2e-2
+    assert abs(float(loss) - float(fx["loss"])) <= 3e-3 * abs(float(fx["loss"]))
+    named = dict(model.named_parameters())
+    total = sum(n * n for n in fx["grad_norms"].values()) ** 0.5
+    errs = []
+    for k, g in fx["grads"].items():
+        if fx["grad_norms"][k] < 1e-3 * total:
+            continue
+        errs.append((rel_l2(named[k].grad, g.float()), k))
+    errs.sort()
+    med, worst = errs[len(errs) // 2], errs[-1]
+    print(f"[b16 fixture] parameter-gradient rel-L2 vs the reference: median {med[0]:.4g}, worst {worst[0]:.4g} ({worst[1]}), n={len(errs)}")
+    assert med[0] <= 5e-2 and worst[0] <= 0.2
