@@ -3,12 +3,15 @@ LinearAttnFFN, ConvLayer2d 1x1 / depthwise, LayerNorm2D_NCHW, LayerNorm / LayerN
 blocks, against fixtures generated from the real reference (tests/golden/make_golden.py, make_golden_r2.py).  Tolerances as in
 test_modules_gpu.py: bf16 activations (rel-L2 <= 2e-2 outputs, 4e-2 input gradients, 5e-2 parameter gradients or 3x torch-autocast)."""
 import os
+import sys
 
 import pytest
 import torch
 
 from oracle import cvnets_oracle as O
-from tests.test_modules_gpu import autocast_errors, load_seeded, rel_l2, run_and_check  # noqa: F401
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from test_modules_gpu import autocast_errors, load_seeded, rel_l2, run_and_check  # noqa: F401,E402
 
 pytestmark = pytest.mark.gpu
 
