@@ -81,8 +81,14 @@ def test_no_cpu_fallback():
         model(torch.randn(1, 3, 64, 64))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.InvertedResidual(m.default_opts(), 16, 16, 1, 2)(torch.randn(1, 16, 8, 8))
-    with pytest.raises(NotImplementedError):
-        m.LinearSelfAttention(m.default_opts(), 16)(torch.randn(1, 16, 4, 4))
+    # the stand-alone layers have kernel paths of their own (round 2) -- and likewise no CPU path
+    for layer, x in ((m.LinearSelfAttention(m.default_opts(), 16), torch.randn(1, 16, 4, 4)), (m.LayerNorm2D_NCHW(16), torch.randn(1, 16, 4, 4)),
+                     (m.LayerNorm(16), torch.randn(1, 4, 16)), (m.LinearLayer(16, 16), torch.randn(1, 4, 16)), (m.GlobalPool(), torch.randn(1, 16, 4, 4)),
+                     (m.ConvLayer2d(m.default_opts(), 16, 16, 1), torch.randn(1, 16, 4, 4))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            layer(x)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m.cross_entropy(torch.randn(2, 8), torch.tensor([1, 2]))
 
 
 def test_product_does_not_import_the_oracle():
