@@ -189,27 +189,28 @@ class CpuArm:
 
 
 def cpu_training_throughput(width, steps, warmup, budget_s, max_batch=128):
-    """Bounded CPU measurement: thread count calibrated, per-step sample sized so that warmup+steps fit in ``budget_s``; if even one
-    image per step does not fit, fewer steps are timed and the line says so.  Returns a dict."""
+    """Bounded CPU measurement.  Thread count calibrated on this box; the per-step sample is sized from a probe at batch 8 (per-image cost
+    grows with the batch on these hosts: a 2-image probe over-estimated the rate 3x in round 2's first run); every step is timed and the
+    loop stops -- saying so in the line -- as soon as the wall-clock budget is spent.  Returns a dict."""
     arm = CpuArm(width)
     t0 = time.perf_counter()
-    threads, probe_ips, cores, calib = arm.calibrate_threads(budget_s=min(45.0, 0.4 * budget_s))
+    threads, probe_ips, cores, calib = arm.calibrate_threads(budget_s=min(40.0, 0.3 * budget_s))
+    xb, yb = arm.batch(min(8, max_batch))
+    arm.step(xb, yb)
+    probe_ips = min(probe_ips, xb.shape[0] / arm.step(xb, yb))
     remaining = max(10.0, budget_s - (time.perf_counter() - t0))
     total = max(1, steps + warmup)
-    batch = int(max(1, min(max_batch, probe_ips * remaining / total)))
-    per_step = batch / probe_ips
-    if per_step * total > remaining:  # even batch 1 is too slow for the requested step count: shrink the step count, honestly
-        steps_done = int(max(1, min(steps, remaining / per_step - 1)))
-        warm_done = 1 if warmup > 0 else 0
-    else:
-        steps_done, warm_done = max(1, steps), warmup
+    batch = int(max(1, min(max_batch, 0.8 * probe_ips * remaining / total)))
     x, y = arm.batch(batch)
-    for _ in range(warm_done):
-        arm.step(x, y)
-    times, t_loop = [], time.perf_counter()
-    for i in range(steps_done):
-        times.append(arm.step(x, y))
-        if time.perf_counter() - t_loop > 1.5 * remaining and i + 1 < steps_done:  # hard stop: never run into the driver's limit
+    t_loop, times, warm_done = time.perf_counter(), [], 0
+    for i in range(total):
+        dt = arm.step(x, y)
+        left = remaining - (time.perf_counter() - t_loop)
+        if i < warmup and left >= 2.0 * dt:  # untimed warm-up, as long as at least one timed step still fits afterwards
+            warm_done += 1
+        else:
+            times.append(dt)
+        if len(times) >= steps or left < 1.1 * dt:
             break
     dt = sum(times) / len(times)
     return {"ips": batch / dt, "ms": dt * 1e3, "threads": threads, "cores_available": cores, "batch": batch, "steps": len(times),

@@ -49,8 +49,10 @@ enum {
   CVB_E_STORE = 0,    /* out = acc + bias (+R)                                                               */
   CVB_E_SILU = 1,     /* out = silu(acc + bias) (+R)                                                         */
   CVB_E_SILU_BWD = 2, /* out = acc * silu'(e_p0[n]*Y + e_p1[n]);   col_sum += out, col_sq += out*Y           */
-  CVB_E_GN_BWD = 3    /* xh=(Y-mean[b])*rstd[b]; col_sum += acc, col_sq += acc*xh; out = acc*e_p0[n];
+  CVB_E_GN_BWD = 3,   /* xh=(Y-mean[b])*rstd[b]; col_sum += acc, col_sq += acc*xh; out = acc*e_p0[n];
                          samp_sum += out, samp_sq += out*xh   (GroupNorm backward, phase 1)                   */
+  CVB_E_LIN_BWD = 4   /* out = acc;   col_sum += out, col_sq += out*Y    (BatchNorm-backward statistics of a producer whose
+                         BatchNorm has NO activation: the consumer of a lazily normalised module output)      */
 };
 
 CVB_API const char* cvb_last_error(void);

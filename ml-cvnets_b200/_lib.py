@@ -16,7 +16,7 @@ ABI_VERSION = 7
 
 # load modes / epilogue modes (mirror include/cvnets_b200.h)
 A_RAW, A_AFF, A_AFF_SILU, A_SILU, A_GN, A_BNB = 0, 1, 2, 3, 4, 5
-E_STORE, E_SILU, E_SILU_BWD, E_GN_BWD = 0, 1, 2, 3
+E_STORE, E_SILU, E_SILU_BWD, E_GN_BWD, E_LIN_BWD = 0, 1, 2, 3, 4
 
 
 class GemmArgs(Structure):

@@ -291,8 +291,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) pw_gemm_kernel(const __grid_const
           } else if (EPI == EPI_SILU) {
             v0 = silu_f(v0); v1 = silu_f(v1);
           } else if (EPI == EPI_SILU_BWD) {
-            v0 *= silu_grad_f(fmaf(ep0[ni][0], y0, ep1[ni][0]));
-            v1 *= silu_grad_f(fmaf(ep0[ni][1], y1, ep1[ni][1]));
+            if (p.e_mode != CVB_E_LIN_BWD) {  // LIN_BWD: same statistics, no activation factor (BatchNorm without an activation)
+              v0 *= silu_grad_f(fmaf(ep0[ni][0], y0, ep1[ni][0]));
+              v1 *= silu_grad_f(fmaf(ep0[ni][1], y1, ep1[ni][1]));
+            }
           } else if (EPI == EPI_GN_BWD) {
             y0 = (y0 - mu) * rs; y1 = (y1 - mu) * rs;  // x-hat
             cs[ni * 2] += v0; cs[ni * 2 + 1] += v1;
@@ -704,10 +706,10 @@ extern "C" int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream) {
   CVB_CHECK(a.lda % 8 == 0 && a.ldw % 8 == 0 && a.ldc % (a.c_fp32 ? 4 : 8) == 0, "cvb_pw_gemm: leading dims must be multiples of 8");
   CVB_CHECK(a.A && a.W && a.C, "cvb_pw_gemm: null operand");
   CVB_CHECK(cvb_aligned16(a.A) && cvb_aligned16(a.W) && cvb_aligned16(a.C), "cvb_pw_gemm: operands must be 16-byte aligned");
-  CVB_CHECK(a.e_mode >= CVB_E_STORE && a.e_mode <= CVB_E_GN_BWD, "cvb_pw_gemm: bad e_mode %d", a.e_mode);
+  CVB_CHECK(a.e_mode >= CVB_E_STORE && a.e_mode <= CVB_E_LIN_BWD, "cvb_pw_gemm: bad e_mode %d", a.e_mode);
   CVB_CHECK(!a.c_fp32, "cvb_pw_gemm: fp32 output is not supported (activations and logits are bf16 like the reference under autocast)");
   CVB_CHECK(!(a.R && a.e_mode >= CVB_E_SILU_BWD), "cvb_pw_gemm: a residual cannot be combined with the backward epilogues");
-  if (a.e_mode == CVB_E_SILU_BWD || a.e_mode == CVB_E_GN_BWD)
+  if (a.e_mode == CVB_E_SILU_BWD || a.e_mode == CVB_E_GN_BWD || a.e_mode == CVB_E_LIN_BWD)
     CVB_CHECK(a.Y && a.ldy % 8 == 0 && cvb_aligned16(a.Y), "cvb_pw_gemm: epilogue mode %d needs Y", a.e_mode);
   if (a.e_mode == CVB_E_GN_BWD || a.a_mode == CVB_A_GN)
     CVB_CHECK(a.row_mean && a.row_rstd && a.rows_per_sample > 0, "cvb_pw_gemm: GroupNorm modes need row_mean/row_rstd/rows_per_sample");
@@ -723,7 +725,7 @@ extern "C" int cvb_pw_gemm(const cvb_gemm_args* args, cvb_stream_t stream) {
     if (rc != -1) return rc;
   }
   const int epi = a.e_mode == CVB_E_STORE ? (a.R ? EPI_STORE_R : EPI_STORE) : a.e_mode == CVB_E_SILU ? EPI_SILU
-                  : a.e_mode == CVB_E_SILU_BWD ? EPI_SILU_BWD : EPI_GN_BWD;
+                  : (a.e_mode == CVB_E_SILU_BWD || a.e_mode == CVB_E_LIN_BWD) ? EPI_SILU_BWD : EPI_GN_BWD;
   switch (a.a_mode) {
     case CVB_A_RAW: return dispatch_epi<CVB_A_RAW>(a, epi, st);
     case CVB_A_AFF: CVB_CHECK(a.a_p0 && a.a_p1, "cvb_pw_gemm: AFF needs p0/p1"); return dispatch_epi<CVB_A_AFF>(a, epi, st);

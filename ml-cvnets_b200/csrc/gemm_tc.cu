@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
     const bf16* __restrict__ AUX = static_cast<const bf16*>(EPI == TEPI_STORE_R ? p.R : p.Y);
     const int ldaux = EPI == TEPI_STORE_R ? p.ldr : p.ldy;
     const bool want_samp = (p.samp_sum != nullptr) && (EPI != TEPI_GN_BWD);  // GN_BWD: the sample sums come from the workspace finalize
+    const bool lin_bwd = (p.e_mode == CVB_E_LIN_BWD);  // SiLU-backward epilogue without the activation factor (BatchNorm with no act)
     const int rps = p.rows_per_sample > 0 ? p.rows_per_sample : 1;
     float cs = 0.f, cq = 0.f;  // this channel's statistics over all tiles of the CTA
     float2 cs2 = make_float2(0.f, 0.f), cq2 = make_float2(0.f, 0.f);  // hot-path partials (even / odd pixel columns), folded in at the end
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
             float y = 0.f;
             if (has_aux) y = __bfloat162float(reinterpret_cast<const bf16*>(so)[i * TC_LDO]);
             if (EPI == TEPI_STORE_R) v += y;
-            if (EPI == TEPI_SILU_BWD) v *= silu_grad_f(fmaf(ep0, y, ep1));
+            if (EPI == TEPI_SILU_BWD && !lin_bwd) v *= silu_grad_f(fmaf(ep0, y, ep1));
             if (EPI == TEPI_GN_BWD) {
               // GroupNorm backward, phase 1 in sum form: per (sample, channel) A = sum v, Bx = sum v*x (raw x); everything else
               // (dgamma, dbeta, per-sample sums of g and g*xhat) is linear in A and Bx and is derived by the finalize kernel
@@ -480,7 +481,7 @@ int dispatch_tc_epi(const cvb_gemm_args& a, cudaStream_t st) {
   if (a.e_mode == CVB_E_GN_BWD && a.gn_ws && a.rows_per_sample % (TC_BM / 2) == 0 && !a.bias && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB))
     return launch_tc_gn_bwd<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW>(a, st);
   if (a.e_mode == CVB_E_STORE) return a.R ? launch_tc<AMODE, TEPI_STORE_R>(a, st) : launch_tc<AMODE, TEPI_STORE>(a, st);
-  if (a.e_mode == CVB_E_SILU_BWD && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB)) return launch_tc<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW, TEPI_SILU_BWD>(a, st);
+  if ((a.e_mode == CVB_E_SILU_BWD || a.e_mode == CVB_E_LIN_BWD) && (AMODE == CVB_A_RAW || AMODE == CVB_A_BNB)) return launch_tc<AMODE == CVB_A_BNB ? CVB_A_BNB : CVB_A_RAW, TEPI_SILU_BWD>(a, st);
   return -1;
 }
 

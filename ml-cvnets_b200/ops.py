@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (A_AFF, A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU, E_GN_BWD, E_SILU, E_SILU_BWD, E_STORE)  # noqa: F401
+from ._lib import (A_AFF, A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU, E_GN_BWD, E_LIN_BWD, E_SILU, E_SILU_BWD, E_STORE)  # noqa: F401
 
 Tensor = torch.Tensor
 launch_count = 0  # number of kernels launched through this module (bench.py reports it as gpu_launches)
