@@ -305,7 +305,9 @@ CVB_API int cvb_col_sum(const void* X, int x_fp32, int ld, int64_t M, int N, flo
  * kind 1: dst[c*ldd + r] = bf16(src[perm(r)*cols + c])           (transposed:          -> bf16 [cols, ldd])
  * kind 2: dst_f32[c*rows + r] = float(bf16(src[r*cols + c]))     (depthwise / stem: [C, taps] -> fp32 [taps, C], bf16-rounded)
  * kind 3: dst_f32[perm^-1 ...]: dst_f32[r] = src[perm(r)]        (fp32 vector gather, e.g. permuted bias; cols = 1)
- * perm(r) = (r + rot) % rows for r < rows (rot = 1 moves the reference's leading query row of qkv_proj to the end). */
+ * kind 4: dst[r*ldd + (t*Cin + ci)] = bf16(src[r*cols + ci*taps + t])   (dense conv weight [Cout, Cin, k, k] -> patch-matrix order; rot = taps = k*k)
+ * kind 5: the same, transposed: dst[(t*Cin + ci)*ldd + r]
+ * perm(r) = (r + rot) % rows for r < rows (rot = 1 moves the reference's leading query row of qkv_proj to the end; kinds 0, 1, 3). */
 typedef struct {
   const float* src; void* dst; int rows, cols, ldd, dst_rows; int kind; int rot;
 } cvb_prep_desc;
@@ -314,6 +316,23 @@ CVB_API int cvb_prep_weights(const cvb_prep_desc* descs_device, int n_desc, int 
 /* fp32 gradient scatter-back for permuted layouts: dst[perm(r)*cols + c] = src[r*lds + c] (kind 0) or
  * dst[c*?]..: kind 2 (tap-major [taps, C] -> [C, taps]).  Used for qkv / depthwise / stem weight gradients. */
 CVB_API int cvb_unprep_grad(const float* src, float* dst, int rows, int cols, int lds, int kind, int rot, cvb_stream_t stream);
+/* (kind 4: dst[r*cols + ci*taps + t] = src[r*lds + t*Cin + ci], rot = taps: the inverse of prep kind 4 for dense-conv weight gradients) */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dense (groups = 1) k x k convolution = im2col + cvb_pw_gemm (ConvLayer2d at cvnets/models/classification/vit.py:90-121 -- the ViT / CLIP
+ * conv stem -- and cvnets/modules/mobilevit_block.py:86-131 -- MobileViT-v1's 3x3 convs).  A[(b,i,j), (u*k+v)*Cin + ci] =
+ * X[b, i*stride+u-pad, j*stride+v-pad, ci], zero outside the image and in the pad columns [k*k*Cin, lda).  X: fp32 or bf16 with arbitrary
+ * ELEMENT strides (sxn, sxc, sxh, sxw) -- NCHW images as well as channels-last feature maps.  cvb_col2im is the adjoint for channels-last
+ * bf16 gradients (a gather: no atomics), Cin % 8 == 0.
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_im2col(const void* X, int x_fp32, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int Cin, int H, int W, int k, int stride,
+               int pad, void* A, int lda, cvb_stream_t stream);
+CVB_API int cvb_col2im(const void* dA, int lda, int B, int Cin, int H, int W, int k, int stride, int pad, void* dX, cvb_stream_t stream);
+/* ViT token assembly (vit.py:476-507): out[b,0] = cls (no positional term), out[b,1+n] = patch[b,n] + pos[n]; patch bf16 [B*N, C] (the
+ * channels-last output of the last stem conv IS token-major), pos fp32 [N, C], cls fp32 [C] or NULL, out bf16 [B, N(+1), C].
+ * bwd: dpatch = dout[:, 1:], dpos += sum_b dout[:, 1:], dcls += sum_b dout[:, 0] (fp32, accumulated into caller-zeroed buffers). */
+CVB_API int cvb_vit_tokens_fwd(const void* patch, const float* pos, const float* cls, void* out, int B, int N, int C, cvb_stream_t stream);
+CVB_API int cvb_vit_tokens_bwd(const void* dout, void* dpatch, float* dpos, float* dcls, int B, int N, int C, cvb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -6,9 +6,9 @@
 //   warp 0    TMA producer : ring of A stages [128 pixels x 32 k] (cp.async.bulk.tensor.2d, 64-byte swizzle) across ALL tiles
 //   warp 1    MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16; the accumulator lives in TMEM,
 //                            double buffered (2 x 128 columns), completion is signalled with tcgen05.commit -> mbarrier
-//   warps 2-9 epilogue     : tcgen05.ld (32 lanes x 32 columns), bias / residual / activation-backward / BatchNorm statistics,
+//   warps 2-17 epilogue    : tcgen05.ld (32 lanes x 32 columns), bias / residual / activation-backward / BatchNorm statistics,
 //                            bf16 staging tile in smem, 16-byte row-contiguous stores
-//   warps 10-13 transform  : (layers with a prologue) apply the producer's BN(+SiLU) / GroupNorm / BN-backward to the landed A
+//   warps 18-21 transform  : (layers with a prologue) apply the producer's BN(+SiLU) / GroupNorm / BN-backward to the landed A
 //                            stage in place, fence.proxy.async, then hand the stage to the MMA warp through a second mbarrier
 // The product is computed TRANSPOSED, D[channel, pixel] = W[channel, :] . A[pixel, :], i.e. the weight panel is the UMMA
 // "A" operand (M = 128 output channels = TMEM lanes) and the activation tile the "B" operand (N = 128 pixels = TMEM columns).
@@ -25,7 +25,8 @@ constexpr int TC_BK = 32;       // k per stage (64-byte rows)
 constexpr int TC_STAGE = TC_BM * TC_BK * 2;   // 8 KB
 constexpr int TC_WBLK = TC_BN * TC_BK * 2;    // 8 KB per k-block of the weight panel
 constexpr int TC_LDO = TC_BN + 8;             // bf16 staging row stride (elements)
-constexpr int TC_EPI_WARPS = 8;             // two warps per TMEM lane quadrant, each draining half of the pixel columns
+constexpr int TC_EPI_WARPS = 16;            // four warps per TMEM lane quadrant, each draining a quarter (32) of the pixel columns: the
+                                            // epilogue, not HBM, bounded round 1's kernel (2 warps / scheduler, ~3000 cycles per tile)
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 constexpr int TC_XF_THREADS = 128;          // transform warps (only launched for layers with a prologue)
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
     // ===================================================== epilogue warps (threads 64..319): one output channel per thread
     const int et = tid - 64;                 // 0..TC_EPI_THREADS-1
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int chalf = (warp - 2) >> 2;       // which half of the pixel columns this warp drains
+    const int cquart = (warp - 2) >> 2;      // which quarter (32) of the pixel columns this warp drains
     const int ch_local = quad * 32 + lane;   // output channel within the tile == TMEM lane
     const int ch = n0 + ch_local;
     const bool ch_ok = ch < p.N;
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TC_BM);
       const bool full_tile = (m0 + TC_BM <= p.M);  // rows >= M have zero A rows; only their bias must be masked (last tile)
-#pragma unroll 1
-      for (int cc = chalf * (TC_BM / 64); cc < (chalf + 1) * (TC_BM / 64); ++cc) {
+      {
+        const int cc = cquart;
         uint32_t r[32];
         tmem_ld32(taddr + cc * 32, r);
         uint16_t* so = reinterpret_cast<uint16_t*>(sO) + (cc * 32) * TC_LDO + ch_local;
@@ -328,8 +329,8 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
           }
         }
       }
-      if (EPI == TEPI_GN_BWD) {  // this thread's 64 pixel columns never straddle samples (rows_per_sample % 64 == 0, checked on the host)
-        const int mh = m0 + chalf * (TC_BM / 2);
+      if (EPI == TEPI_GN_BWD) {  // this thread's 32 pixel columns never straddle samples (rows_per_sample % 64 == 0, checked on the host)
+        const int mh = m0 + cquart * 32;
         if (ch_ok && mh < p.M) {
           const int nsamples = (p.M + rps - 1) / rps;
           double* wsA = p.gn_ws + (size_t)(mh / rps) * p.N + ch;

@@ -675,6 +675,14 @@ __global__ void __launch_bounds__(NT) prep_weights_kernel(const cvb_prep_desc* _
     } else if (d.kind == 2) {
       int tap = (int)(i / d.rows), ch = (int)(i % d.rows);
       static_cast<float*>(d.dst)[i] = bf16_round(d.src[(int64_t)ch * d.cols + tap]);
+    } else if (d.kind == 4 || d.kind == 5) {
+      // dense conv weight [rows = Cout][cols = Cin * taps] in (ci, tap) order -> patch-matrix order (tap, ci); rot = taps.
+      // kind 4: row-major [dst_rows, ldd];  kind 5: transposed [cols, ldd >= rows]
+      const int r = (d.kind == 4) ? (int)(i / d.ldd) : (int)(i % d.ldd), c = (d.kind == 4) ? (int)(i % d.ldd) : (int)(i / d.ldd);
+      const int cin = d.cols / d.rot;
+      float v = 0.f;
+      if (r < d.rows && c < d.cols) v = d.src[(int64_t)r * d.cols + (c % cin) * d.rot + c / cin];
+      static_cast<bf16*>(d.dst)[i] = __float2bfloat16_rn(v);
     } else {
       int r = (int)i;
       static_cast<float*>(d.dst)[i] = (r < d.rows) ? d.src[perm_row(r, d.rows, d.rot)] : 0.f;
@@ -694,6 +702,10 @@ __global__ void __launch_bounds__(NT) unprep_grad_kernel(const float* __restrict
     } else if (kind == 2) {  // src [taps=cols][C=rows] -> dst [C][taps]
       int ch = (int)(i / cols), tap = (int)(i % cols);
       dst[i] = src[(int64_t)tap * rows + ch];
+    } else if (kind == 4) {  // src [rows][(tap, ci)] (leading dim lds) -> dst [rows][(ci, tap)], rot = taps
+      int r = (int)(i / cols), c = (int)(i % cols);
+      const int cin = cols / rot;
+      dst[(int64_t)r * cols + (c % cin) * rot + c / cin] = src[(int64_t)r * lds + c];
     } else {
       dst[perm_row((int)i, rows, rot)] = src[i];
     }

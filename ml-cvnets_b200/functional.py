@@ -64,6 +64,24 @@ def _zeros64(device, *sizes: int) -> List[torch.Tensor]:
     return out
 
 
+class LazyBN:
+    """A module output handed to the NEXT hot-path module still PRE-BatchNorm (DESIGN.md "lazy module boundaries").
+
+    The producer skips its ``bn_apply`` pass and returns the pre-BN tensor tagged with this record; the consumer applies
+    ``scale * y + shift`` (+ SiLU) as the load mode of its first kernel and, in the backward, its input-gradient kernel emits
+    dz (the gradient w.r.t. the BatchNorm output, through the activation) together with the BatchNorm-backward sums
+    (sum dz, sum dz*y) into ``stats`` -- so the producer needs no ``bn_bwd_reduce`` pass either.  Only the model assembler wires this
+    (both neighbours must be ours); a module called on its own always materialises its output."""
+    __slots__ = ("bn", "act", "stats")
+
+    def __init__(self, bn, act):
+        self.bn, self.act, self.stats = bn, bool(act), None
+
+
+def _lazy_modes(lz):
+    return (A_AFF_SILU if lz.act else A_AFF), (E_SILU_BWD if lz.act else ops.E_LIN_BWD), (lz.bn[2], lz.bn[3])
+
+
 def _ws_of(cfg, params):
     """The module's StepWorkspace if gradients are to be written in place (inside TrainStep, every parameter registered), else None."""
     ws = getattr(cfg, "ws", None)
@@ -154,7 +172,8 @@ class StemFn(torch.autograd.Function):
         st = _fwd_arena(cfg, x.device, 2 * C0 + 8).f64(2, C0)
         y = ops.pw_gemm(A0, Ws, C0, col_stats=st if cfg.bn.batch_stats else None)
         bn = _bn_forward(st, M, gamma, beta, cfg.bn)
-        out = ops.bn_apply(y, bn, act=True)
+        ctx.lz_out = cfg.last_lazy = LazyBN(bn, True) if cfg.lazy_out else None
+        out = y if cfg.lazy_out else ops.bn_apply(y, bn, act=True)
         ctx.cfg, ctx.dims, ctx.ev = cfg, (B, Ho, Wo, C0, M), (not cfg.bn.batch_stats,)
         ctx.saved = (A0, y, bn)
         ctx.plist = cfg.plist
@@ -169,8 +188,12 @@ class StemFn(torch.autograd.Function):
         (gamma,) = ctx.saved_tensors
         g2 = as_2d(to_bf16_cl(gout))
         D = _Dst(cfg, ctx.plist, g2.device, C0 * 32 + 64, 2 * C0 + 16, True)
-        sd = D.ar.f64(2, C0)
-        dz = ops.bn_bwd_reduce(g2, y, sd, bn, act=True, store_dz=True)
+        if ctx.lz_out is not None:  # the consumer already went through the activation and took the BatchNorm-backward sums
+            assert ctx.lz_out.stats is not None, "lazy module output was consumed by a module that does not know the protocol"
+            dz, sd = g2, ctx.lz_out.stats
+        else:
+            sd = D.ar.f64(2, C0)
+            dz = ops.bn_bwd_reduce(g2, y, sd, bn, act=True, store_dz=True)
         dgb, coef = ops.bn_bwd_finalize(sd, M, gamma, bn, eval_mode=ctx.ev[0], out=D.pair(1, 2))
         D.set_pair(1, 2, dgb)
         dW = ops.pw_wgrad_side(dz, A0, C0, 32, g_mode=A_BNB, G2=y, g_p=coef, dW=D.ar.f32(C0, 32))
@@ -194,13 +217,21 @@ class InvertedResidualFn(torch.autograd.Function):
         fa = _fwd_arena(cfg, x.device, 2 * (2 * hid + cout) + 16)
         st1, st2, st3 = fa.f64(2, hid), fa.f64(2, hid), fa.f64(2, cout)
         bs = [c.batch_stats for c in cfg.bn]  # per layer: individual BatchNorms may be frozen (base_model.py:139-165)
-        y1 = ops.pw_gemm(x2, P.get(cfg.i_w1), hid, col_stats=st1 if bs[0] else None)
+        lz = ctx.lz_in = cfg.lazy_in
+        if lz is not None:
+            assert not cfg.residual, "a lazily normalised input cannot also be the residual"
+            am, _, ap = _lazy_modes(lz)
+            y1 = ops.pw_gemm(x2, P.get(cfg.i_w1), hid, a_mode=am, a_p=ap, col_stats=st1 if bs[0] else None)
+        else:
+            y1 = ops.pw_gemm(x2, P.get(cfg.i_w1), hid, col_stats=st1 if bs[0] else None)
         bn1 = _bn_forward(st1, M, g1, b1, cfg.bn[0])
         y2 = ops.dw_fwd(y1, B, H, W, hid, s, P.get(cfg.i_wd), x_mode=A_AFF_SILU, x_p=(bn1[2], bn1[3]), col_stats=st2 if bs[1] else None)
         bn2 = _bn_forward(st2, M2, g2, b2, cfg.bn[1])
         y3 = ops.pw_gemm(y2, P.get(cfg.i_w3), cout, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), col_stats=st3 if bs[2] else None)
         bn3 = _bn_forward(st3, M2, g3, b3, cfg.bn[2])
-        out = ops.bn_apply(y3, bn3, act=False, R=x2 if cfg.residual else None)
+        lazy_out = cfg.lazy_out and not cfg.residual
+        ctx.lz_out = cfg.last_lazy = LazyBN(bn3, False) if lazy_out else None
+        out = y3 if lazy_out else ops.bn_apply(y3, bn3, act=False, R=x2 if cfg.residual else None)
         ctx.cfg, ctx.dims, ctx.ev = cfg, (B, Cin, H, W, Ho, Wo), tuple(not b for b in bs)  # BN modes snapshotted for backward
         ctx.saved = (x2, y1, bn1, y2, bn2, y3, bn3)
         ctx.plist = cfg.plist
@@ -219,11 +250,15 @@ class InvertedResidualFn(torch.autograd.Function):
         ev = ctx.ev
         dout = as_2d(to_bf16_cl(gout))
         # parameter order: (w1, g1, b1, wd, g2, b2, w3, g3, b3)
-        D = _Dst(cfg, ctx.plist, dout.device, cout * hid + hid * Cin + 9 * hid + 64, 2 * (cout + 2 * hid) + 16, True)
+        D = _Dst(cfg, ctx.plist, dout.device, cout * hid + hid * Cin + 9 * hid + 64, 2 * (cout + 2 * hid + Cin) + 16, True)
         ar = D.ar
         sd3, sd2, sd1 = ar.f64(2, cout), ar.f64(2, hid), ar.f64(2, hid)
         # red_1x1 + BN3 (no activation): dz3 = dout
-        ops.bn_bwd_reduce(dout, y3, sd3)
+        if ctx.lz_out is not None:
+            assert ctx.lz_out.stats is not None, "lazy module output was consumed by a module that does not know the protocol"
+            sd3 = ctx.lz_out.stats
+        else:
+            ops.bn_bwd_reduce(dout, y3, sd3)
         dgb3, c3 = ops.bn_bwd_finalize(sd3, M2, g3, bn3, ev[2], out=D.pair(7, 8))
         D.set_pair(7, 8, dgb3)
         dz2 = ops.pw_gemm(dout, P.get(cfg.i_w3t), hid, K=cout, a_mode=A_BNB, A2=y3, a_p=c3, e_mode=E_SILU_BWD, Y=y2,
@@ -238,8 +273,15 @@ class InvertedResidualFn(torch.autograd.Function):
         # exp_1x1 + BN1
         dgb1, c1 = ops.bn_bwd_finalize(sd1, M, g1, bn1, ev[0], out=D.pair(1, 2))
         D.set_pair(1, 2, dgb1)
-        dx = ops.pw_gemm(dz1, P.get(cfg.i_w1t), Cin, K=hid, a_mode=A_BNB, A2=y1, a_p=c1, R=dout if cfg.residual else None)
-        ops.pw_wgrad_side(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, dW=D.mat(0, hid, Cin))
+        lz = ctx.lz_in
+        if lz is not None:  # the producer's BatchNorm (+SiLU) lives in this module's load mode: emit dz and its BN-backward sums for it
+            am, em, ap = _lazy_modes(lz)
+            lz.stats = ar.f64(2, Cin)
+            dx = ops.pw_gemm(dz1, P.get(cfg.i_w1t), Cin, K=hid, a_mode=A_BNB, A2=y1, a_p=c1, e_mode=em, Y=x2, e_p=ap, col_stats=lz.stats)
+            ops.pw_wgrad_side(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, a_mode=am, a_p=ap, dW=D.mat(0, hid, Cin))
+        else:
+            dx = ops.pw_gemm(dz1, P.get(cfg.i_w1t), Cin, K=hid, a_mode=A_BNB, A2=y1, a_p=c1, R=dout if cfg.residual else None)
+            ops.pw_wgrad_side(dz1, x2, hid, Cin, g_mode=A_BNB, G2=y1, g_p=c1, dW=D.mat(0, hid, Cin))
         ops.join_side()
         return (to_4d(dx, B, H, W), None) + D.finish()
 
@@ -266,7 +308,12 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         samp = [fa.f64(2, B) for _ in range(2 * n + 1)]
         gcount = HW * d
         # local_rep: dw3x3 + BN + SiLU -> 1x1 (C -> d)
-        y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), col_stats=st0 if bs[0] else None)
+        lz = ctx.lz_in = cfg.lazy_in
+        if lz is not None:
+            am, _, ap = _lazy_modes(lz)
+            y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), x_mode=am, x_p=ap, col_stats=st0 if bs[0] else None)
+        else:
+            y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), col_stats=st0 if bs[0] else None)
         bn0 = _bn_forward(st0, M, g0, b0, cfg.bn[0])
         X = ops.pw_gemm(y0, P.get(cfg.i_wl), d, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), samp_stats=samp[0], rows_per_sample=HW)
         blocks = []
@@ -287,7 +334,8 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         yp = ops.pw_gemm(X, P.get(cfg.i_wp), C, a_mode=A_GN, a_p=(gL, bL), row_stats=(gnL[0], gnL[1]), rows_per_sample=HW,
                          col_stats=stp if bs[1] else None)
         bnp = _bn_forward(stp, M, gp, bp, cfg.bn[1])
-        out = ops.bn_apply(yp, bnp, act=False)
+        ctx.lz_out = cfg.last_lazy = LazyBN(bnp, False) if cfg.lazy_out else None
+        out = yp if cfg.lazy_out else ops.bn_apply(yp, bnp, act=False)
         ctx.cfg, ctx.dims, ctx.ev = cfg, (B, C, H, W), tuple(not b for b in bs)
         ctx.saved = (x2, y0, bn0, blocks, X, gnL, yp, bnp)
         ctx.plist = cfg.plist
@@ -311,13 +359,17 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         gcount = HW * d
         dout = as_2d(to_bf16_cl(gout))
         n32 = sum(int(q.numel()) for q in params) + n * 8 * d + 16 * len(params) + 9 * C + 2 * (2 * d + 8) * n + 64
-        n64 = 4 * C + (n + 1) * (2 * d + 2 * B + 2 * d) + n * (2 * ffn + 2 * d + 2 * B + 2 * d) + 64 + (2 * n + 1) * (2 * B * d + 2)
+        n64 = 6 * C + (n + 1) * (2 * d + 2 * B + 2 * d) + n * (2 * ffn + 2 * d + 2 * B + 2 * d) + 64 + (2 * n + 1) * (2 * B * d + 2)
         D = _Dst(cfg, ctx.plist, dev, n32, n64, True)
         ar = D.ar
         sdp, sd0 = ar.f64(2, C), ar.f64(2, C)
         # ---- conv_proj (GN -> 1x1 -> BN, no act)
         base = 4 + 12 * n
-        ops.bn_bwd_reduce(dout, yp, sdp)
+        if ctx.lz_out is not None:
+            assert ctx.lz_out.stats is not None, "lazy module output was consumed by a module that does not know the protocol"
+            sdp = ctx.lz_out.stats
+        else:
+            ops.bn_bwd_reduce(dout, yp, sdp)
         dgbp, cp = ops.bn_bwd_finalize(sdp, M, gp, bnp, ev[1], out=D.pair(base + 3, base + 4))
         D.set_pair(base + 3, base + 4, dgbp)
         cs, ss = ar.f64(2, d), ar.f64(2, B)
@@ -368,7 +420,14 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         dz0 = ops.pw_gemm(dX, P.get(cfg.i_wlt), C, K=d, e_mode=E_SILU_BWD, Y=y0, e_p=(bn0[2], bn0[3]), col_stats=sd0)
         dgb0, c0 = ops.bn_bwd_finalize(sd0, M, g0, bn0, ev[0], out=D.pair(1, 2))
         D.set_pair(1, 2, dgb0)
-        dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW, dWt=ar.f32(9, C))
+        lz = ctx.lz_in
+        if lz is not None:
+            am, _, ap = _lazy_modes(lz)
+            lz.stats = ar.f64(2, C)
+            dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=am, x_p=ap, col_stats=lz.stats,
+                                 dWt=ar.f32(9, C))
+        else:
+            dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW, dWt=ar.f32(9, C))
         D.unprep(0, dWt, C, 9, C, 2)
         ops.join_side()
         return (to_4d(dx, B, H, W), None) + D.finish()
@@ -450,24 +509,34 @@ class CrossEntropyFn(torch.autograd.Function):
 # autograd function, outputs materialised -- the unfused but native path every layer falls back to when it is not inside a fused block.
 # ==================================================================================================================
 class PointwiseConvFn(torch.autograd.Function):
-    """ConvLayer2d with a 1x1 kernel: conv (+bias) [-> BatchNorm2d] [-> activation] [+ residual] on a [B, Cin, H, W] map
-    (cvnets/layers/conv_layer.py:200-226, 254-255).  params = (w, bias | None, gamma | None, beta | None)."""
+    """ConvLayer2d, groups = 1: conv (+bias) [-> BatchNorm2d] [-> Swish | GELU] [+ residual] on a [B, Cin, H, W] map
+    (cvnets/layers/conv_layer.py:200-226, 254-255).  1x1 convs ARE the GEMM; k x k convs (the ViT / CLIP conv stem, MobileViT-v1's dense
+    3x3 convs) go through the gathered patch matrix of cvb_im2col (csrc/conv.cu).  params = (w, bias | None, gamma | None, beta | None)."""
 
     @staticmethod
     def forward(ctx, x, cfg, residual, w, bias, gamma, beta):
         B, Cin, H, W = x.shape
-        M, cout = B * H * W, cfg.cout
-        x2 = as_2d(x)
+        cout = cfg.cout
         P = cfg.prep
+        if cfg.k == 1 and cfg.stride == 1:
+            x2, Ho, Wo = as_2d(x), H, W
+        else:
+            x2, Ho, Wo = ops.im2col(x, cfg.k, cfg.stride, cfg.pad)
+        M = B * Ho * Wo
         R = as_2d(residual) if residual is not None else None
+        ob = None
         if cfg.bn is not None:
             st = _fwd_arena(cfg, x.device, 2 * cout + 8).f64(2, cout)
             y = ops.pw_gemm(x2, P.get(cfg.i_w), cout, bias=bias, col_stats=st if cfg.bn.batch_stats else None)
             bn = _bn_forward(st, M, gamma, beta, cfg.bn)
-            out = ops.bn_apply(y, bn, act=cfg.act is not None, R=R)
-            if cfg.act not in (None, ops.ACT_SILU):
-                raise NotImplementedError("BatchNorm followed by an activation other than Swish")
-            ctx.saved, ctx.ev = (x2, y, bn), (not cfg.bn.batch_stats,)
+            if cfg.act in (None, ops.ACT_SILU):
+                out = ops.bn_apply(y, bn, act=cfg.act is not None, R=R)
+            else:  # BatchNorm -> GELU (the ViT conv stem under model.activation.name = gelu): two passes, the stem is ~1 % of the model
+                if R is not None:
+                    raise NotImplementedError("BatchNorm + GELU + residual in one stand-alone ConvLayer2d")
+                ob = ops.bn_apply(y, bn, act=False)
+                out = ops.act_fwd(ob, cfg.act)
+            ctx.saved, ctx.ev = (x2, y, bn, ob), (not cfg.bn.batch_stats,)
         elif cfg.act is not None:
             h = ops.pw_gemm(x2, P.get(cfg.i_w), cout, bias=bias)
             out = ops.act_fwd(h, cfg.act)
@@ -477,51 +546,60 @@ class PointwiseConvFn(torch.autograd.Function):
         else:
             out = ops.pw_gemm(x2, P.get(cfg.i_w), cout, bias=bias, R=R)
             ctx.saved = (x2,)
-        ctx.cfg, ctx.dims, ctx.plist, ctx.has_res = cfg, (B, Cin, H, W), cfg.plist, residual is not None
+        ctx.cfg, ctx.dims, ctx.plist, ctx.has_res = cfg, (B, Cin, H, W, Ho, Wo), cfg.plist, residual is not None
         ctx.save_for_backward(gamma) if gamma is not None else None
-        return to_4d(out, B, H, W)
+        return to_4d(out, B, Ho, Wo)
 
     @staticmethod
     def backward(ctx, gout):
         cfg = ctx.cfg
-        B, Cin, H, W = ctx.dims
-        M, cout = B * H * W, cfg.cout
+        B, Cin, H, W, Ho, Wo = ctx.dims
+        M, cout = B * Ho * Wo, cfg.cout
         P = cfg.prep
+        dense = not (cfg.k == 1 and cfg.stride == 1)
         dout = as_2d(to_bf16_cl(gout))
-        D = _Dst(cfg, ctx.plist, dout.device, cout * Cin + cout + 64, 2 * cout + 16, True)
+        x2 = ctx.saved[0]
+        Kc = x2.shape[1]
+        D = _Dst(cfg, ctx.plist, dout.device, cout * Kc + cout + 64, 2 * cout + 16, True)
         has_bias = cfg.has_bias
         db = D.mat(1, 1, cout).view(cout) if has_bias else None
+        dW = D.ar.f32(cout, Kc) if dense else D.mat(0, cout, Cin)
+        need_dx = ctx.needs_input_grad[0]
+        dA = None
         if cfg.bn is not None:
-            x2, y, bn = ctx.saved
+            _, y, bn, ob = ctx.saved
             (gamma,) = ctx.saved_tensors
-            act = cfg.act is not None
             sd = D.ar.f64(2, cout)
+            if ob is not None:
+                dout = ops.act_bwd(dout, ob, cfg.act)
+            act = cfg.act == ops.ACT_SILU
             dz = ops.bn_bwd_reduce(dout, y, sd, bn, act=act, store_dz=act)
             if not act:
                 dz = dout
             gi, bi = (2, 3) if has_bias else (1, 2)
             dgb, c = ops.bn_bwd_finalize(sd, M, gamma, bn, ctx.ev[0], out=D.pair(gi, bi))
             D.set_pair(gi, bi, dgb)
-            dx = ops.pw_gemm(dz, P.get(cfg.i_wt), Cin, K=cout, a_mode=A_BNB, A2=y, a_p=c)
-            ops.pw_wgrad_side(dz, x2, cout, Cin, g_mode=A_BNB, G2=y, g_p=c, dW=D.mat(0, cout, Cin), dbias=db)
+            if need_dx:
+                dA = ops.pw_gemm(dz, P.get(cfg.i_wt), Kc, K=cout, a_mode=A_BNB, A2=y, a_p=c)
+            ops.pw_wgrad_side(dz, x2, cout, Kc, g_mode=A_BNB, G2=y, g_p=c, dW=dW, dbias=db)
         else:
-            if cfg.act is not None:
-                x2, h = ctx.saved
-                dh = ops.act_bwd(dout, h, cfg.act)
-            else:
-                (x2,) = ctx.saved
-                dh = dout
-            dx = ops.pw_gemm(dh, P.get(cfg.i_wt), Cin, K=cout)
-            ops.pw_wgrad_side(dh, x2, cout, Cin, dW=D.mat(0, cout, Cin), dbias=db)
+            dh = ops.act_bwd(dout, ctx.saved[1], cfg.act) if cfg.act is not None else dout
+            if need_dx:
+                dA = ops.pw_gemm(dh, P.get(cfg.i_wt), Kc, K=cout)
+            ops.pw_wgrad_side(dh, x2, cout, Kc, dW=dW, dbias=db)
+        if dense:
+            D.unprep(0, dW, cout, cfg.k * cfg.k * Cin, Kc, 4, rot=cfg.k * cfg.k, side=True)
         ops.join_side()
+        dx = None
+        if need_dx:
+            dx = to_4d(ops.col2im(dA, B, Cin, H, W, cfg.k, cfg.stride, cfg.pad) if dense else dA, B, H, W)
         grads = D.finish()
-        g = {0: grads[0]}
         full = [grads[0], None, None, None]
         if has_bias:
             full[1] = grads[1]
         if cfg.bn is not None:
             full[2], full[3] = grads[2 if has_bias else 1], grads[3 if has_bias else 2]
-        return (to_4d(dx, B, H, W), None, gout if ctx.has_res else None) + tuple(full)
+        return (dx, None, gout if ctx.has_res else None) + tuple(full)
 
 
 class DepthwiseConvFn(torch.autograd.Function):
@@ -760,6 +838,32 @@ class GlobalPoolFn(torch.autograd.Function):
         return to_4d(ops.global_pool_bwd(g, B, H * W), B, H, W), None
 
 
+class VitTokensFn(torch.autograd.Function):
+    """ViT token assembly (cvnets/models/classification/vit.py:476-507): tokens = cat(cls, patch_embedding + positional_embedding).
+    patch: [B, C, nh, nw] channels-last (== token-major [B*N, C]); pos: [1, 1, N, C]; cls: [1, 1, C] or None.  Returns [B, N(+1), C]."""
+
+    @staticmethod
+    def forward(ctx, patch, cfg, pos, cls):
+        B, C, nh, nw = patch.shape
+        N = nh * nw
+        p2 = as_2d(to_bf16_cl(patch))
+        out = ops.vit_tokens_fwd(p2, pos, cls, B, N, C)
+        ctx.cfg, ctx.dims, ctx.plist, ctx.has_cls = cfg, (B, C, nh, nw), cfg.plist, cls is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        B, C, nh, nw = ctx.dims
+        N = nh * nw
+        g = gout if (gout.dtype == BF16 and gout.is_contiguous()) else gout.to(BF16).contiguous()
+        D = _Dst(ctx.cfg, ctx.plist, g.device, N * C + C + 64, 8, True)
+        dpos = D.mat(0, N, C)
+        dcls = D.mat(1, 1, C).view(C) if ctx.has_cls else None
+        dpatch = ops.vit_tokens_bwd(g, dpos, dcls, B, N, C)
+        grads = D.finish()
+        return to_4d(dpatch, B, nh, nw), None, grads[0], grads[1] if ctx.has_cls else None
+
+
 # ==================================================================================================================
 # Transformer rows (SURVEY.md 8a a10-a12): MultiHeadAttention (cvnets/layers/multi_head_attention.py:135-239) and the pre-norm
 # TransformerEncoder (cvnets/modules/transformer.py:129-156) on token matrices [M = N*S, C] (bf16).  LayerNorm is the GroupNorm
@@ -827,7 +931,7 @@ class TransformerEncoderFn(torch.autograd.Function):
         ln1 = ops.ln_stats(x2, cfg.eps)
         qkv = ops.pw_gemm(x2, P.get(cfg.i_wqkv), 3 * C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, bias=bqkv)
         O, LSE = ops.mha_fwd(qkv, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
-        (samp,) = _zeros64(x.device, M)
+        samp = _fwd_arena(cfg, x.device, 2 * M + 8).f64(2, M)
         X1 = ops.pw_gemm(O, P.get(cfg.i_wo), C, bias=bo, R=x2, samp_stats=samp, rows_per_sample=1)
         ln2 = ops.gn_finalize(samp, C, cfg.eps)
         h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
@@ -837,7 +941,7 @@ class TransformerEncoderFn(torch.autograd.Function):
         else:
             ha = ops.act_fwd(h, cfg.act)
             X2 = ops.pw_gemm(ha, P.get(cfg.i_w2), C, bias=bb2, R=X1)
-        ctx.cfg, ctx.dims = cfg, (N, S, C)
+        ctx.cfg, ctx.dims, ctx.plist = cfg, (N, S, C), cfg.plist
         ctx.saved = (x2, ln1, qkv, O, LSE, X1, ln2, h, ha, amask, kpm)
         ctx.save_for_backward(g1, b1, g2, b2)
         return X2.view(N, S, C)
@@ -852,30 +956,35 @@ class TransformerEncoderFn(torch.autograd.Function):
         g1, b1, g2, b2 = ctx.saved_tensors
         dev = x2.device
         dY = gout.reshape(M, C).to(BF16).contiguous()
-        ar = Arena(dev, 4 * C * C + 2 * C * ffn + 8 * C + ffn + 64, 8 * C + 2 * ffn + 64)
+        # parameter order: (g1, b1, wqkv, bqkv, wo, bo, g2, b2, w1, bb1, w2, bb2)
+        D = _Dst(cfg, ctx.plist, dev, 4 * C * C + 2 * C * ffn + 8 * C + ffn + 64, 8 * C + 2 * ffn + 64, True)
+        ar = D.ar
+        vec = lambda i, n: D.mat(i, 1, n).view(n)  # noqa: E731
         # ---- FFN
-        db2, db1 = ar.f32(C), ar.f32(ffn)
+        db2, db1 = vec(11, C), vec(9, ffn)
         if cfg.act == ops.ACT_SILU:
-            dW2 = ops.pw_wgrad_side(dY, h, C, ffn, a_mode=A_SILU, dW=ar.f32(C, ffn), dbias=db2)
+            ops.pw_wgrad_side(dY, h, C, ffn, a_mode=A_SILU, dW=D.mat(10, C, ffn), dbias=db2)
             dh = ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C, e_mode=E_SILU_BWD, Y=h)
         else:
-            dW2 = ops.pw_wgrad_side(dY, ha, C, ffn, dW=ar.f32(C, ffn), dbias=db2)
+            ops.pw_wgrad_side(dY, ha, C, ffn, dW=D.mat(10, C, ffn), dbias=db2)
             dh = ops.act_bwd(ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C), h, cfg.act)
-        dW1 = ops.pw_wgrad_side(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=ar.f32(ffn, C), dbias=db1)
+        ops.pw_wgrad_side(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=D.mat(8, ffn, C), dbias=db1)
         csf, bsum1 = ar.f64(2, C), ar.f64(C)
         vF = ops.pw_gemm(dh, P.get(cfg.i_w1t), C, K=ffn)
         dX1 = ops.ln_bwd(vF, X1, ln2, g2, csf, DRES=dY, col_sum=bsum1)  # bsum1 = column sums of dX1 = d(out_proj bias)
+        D.late64(5, bsum1)
+        D.late64(6, csf[1])
+        D.late64(7, csf[0])
         # ---- attention
-        dWo = ops.pw_wgrad_side(dX1, O, C, C, dW=ar.f32(C, C))
+        ops.pw_wgrad_side(dX1, O, C, C, dW=D.mat(4, C, C))
         dO = ops.pw_gemm(dX1, P.get(cfg.i_wot), C, K=C)
         dqkv = ops.mha_bwd(qkv, O, dO, LSE, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
-        dbq = ar.f32(3 * C)
-        dWq = ops.pw_wgrad_side(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=ar.f32(3 * C, C), dbias=dbq)
+        ops.pw_wgrad_side(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=D.mat(2, 3 * C, C),
+                          dbias=vec(3, 3 * C))
         csa = ar.f64(2, C)
         vA = ops.pw_gemm(dqkv, P.get(cfg.i_wqkvt), C, K=3 * C)
         dx = ops.ln_bwd(vA, x2, ln1, g1, csa, DRES=dX1)
+        D.late64(0, csa[1])
+        D.late64(1, csa[0])
         ops.join_side()
-        ar.cast()
-        f = ar.as_f32
-        # (x, cfg, g1, b1, wqkv, bqkv, wo, bo, g2, b2, w1, bb1, w2, bb2)
-        return (dx.view(N, S, C), None, f(csa[1]), f(csa[0]), dWq, dbq, dWo, f(bsum1), f(csf[1]), f(csf[0]), dW1, db1, dW2, db2)
+        return (dx.view(N, S, C), None) + D.finish()

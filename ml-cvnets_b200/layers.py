@@ -212,18 +212,28 @@ class ConvLayer2d(BaseLayer):
             raise NotImplementedError(f"stand-alone ConvLayer2d with norm={self.norm_name}, act={self.act_name} has no kernel path")
         act = None if self.act_name is None else (ops.ACT_SILU if self.act_name == "Swish" else ops.ACT_GELU)
         norm = self.block.norm if self.norm_name is not None else None
-        pointwise = self.kernel_size == (1, 1) and self.stride == (1, 1) and self.groups == 1
+        pad = tuple(conv.padding) if not isinstance(conv.padding, str) else None
+        # groups = 1: 1x1 convs are the GEMM itself; square k x k convs run as im2col + GEMM (ViT conv stem, MobileViT-v1 3x3 convs)
+        pointwise = (self.groups == 1 and self.dilation == (1, 1) and self.kernel_size[0] == self.kernel_size[1] and self.stride[0] == self.stride[1]
+                     and pad is not None and pad[0] == pad[1] and (self.in_channels % 8 == 0 or self.kernel_size[0] > 1))
         depthwise = (self.kernel_size == (3, 3) and self.groups == self.in_channels == self.out_channels and self.dilation == (1, 1)
                      and self.stride in ((1, 1), (2, 2)) and conv.bias is None and tuple(conv.padding) == (1, 1))
-        if not (pointwise or depthwise) or self.in_channels % 8 or self.out_channels % 8:
-            raise NotImplementedError("stand-alone ConvLayer2d: 1x1 convs and depthwise 3x3 convs with channel counts that are multiples of 8 "
-                                      "have kernel paths (dense k x k convs other than the stem are SURVEY.md 8a row a9)")
+        if depthwise:
+            pointwise = False
+        if not (pointwise or depthwise) or self.out_channels % 8 or (depthwise and self.in_channels % 8):
+            raise NotImplementedError("stand-alone ConvLayer2d: undilated groups=1 convs with square kernels (out_channels % 8 == 0; in_channels % 8 == 0 "
+                                      "for 1x1) and depthwise 3x3 convs have kernel paths")
         if self._stem is None:
             prep = PW()
-            cfg = SimpleNamespace(prep=prep, cout=self.out_channels, act=act, has_bias=conv.bias is not None, stride=self.stride[0])
-            if pointwise:
+            k = self.kernel_size[0]
+            cfg = SimpleNamespace(prep=prep, cout=self.out_channels, act=act, has_bias=conv.bias is not None, stride=self.stride[0], k=k,
+                                  pad=pad[0] if pad is not None else 0)
+            if pointwise and k == 1 and self.stride[0] == 1:
                 cfg.i_w = prep.add(conv.weight, PW.KIND_ROWMAJOR)
                 cfg.i_wt = prep.add(conv.weight, PW.KIND_TRANSPOSED)
+            elif pointwise:
+                cfg.i_w = prep.add(conv.weight, PW.KIND_PATCH, rot=k * k)
+                cfg.i_wt = prep.add(conv.weight, PW.KIND_PATCH_T, rot=k * k)
             else:
                 cfg.i_w = prep.add(conv.weight, PW.KIND_TAPMAJOR_F32)
             self._stem = cfg
@@ -231,7 +241,8 @@ class ConvLayer2d(BaseLayer):
         cfg.bn = Fn.bn_cfg(norm) if norm is not None else None
         cfg.ws = getattr(self, "_ws", None)
         cfg.prep.prepare(force=self.training)
-        x = Fn.to_bf16_cl(x)
+        if not (pointwise and cfg.k > 1 and x.dtype == torch.float32 and self.in_channels % 8):
+            x = Fn.to_bf16_cl(x)  # (fp32 images with few channels go through the gather kernel as they are)
         g, b = (norm.weight, norm.bias) if norm is not None else (None, None)
         if pointwise:
             cfg.plist = [conv.weight] + ([conv.bias] if conv.bias is not None else []) + ([g, b] if norm is not None else [])

@@ -90,6 +90,14 @@ class MobileViTv2(nn.Module):
                                         LinearLayer(in_features=in_c, out_features=num_classes, bias=True))
         self._head = None
         self.reset_parameters(opts)
+        # lazy module boundaries (functional.LazyBN): a module whose successor in THIS chain is a hot-path module without a residual on its
+        # input hands over its output pre-BatchNorm; the successor normalises on load.  Active only inside extract_features().
+        self.fuse_boundaries = True
+        chain = [self.conv_1] + [m for li in range(1, 6) for m in getattr(self, f"layer_{li}")]
+        for prod, cons in zip(chain[:-1], chain[1:]):
+            takes_lazy = isinstance(cons, MobileViTBlockv2) or (isinstance(cons, InvertedResidual) and not cons.use_res_connect)
+            object.__setattr__(prod, "_lazy_out", bool(takes_lazy))
+        self._chain = chain
 
     # ---- construction (mobilevit_v2.py:137-226)
     def _make_layer(self, opts, input_channel, cfg: Dict, dilate: Optional[bool] = False) -> Tuple[nn.Sequential, int]:
@@ -172,12 +180,18 @@ class MobileViTv2(nn.Module):
 
     # ---- forward (base_image_encoder.py:261-301)
     def extract_features(self, x: Tensor, *args, **kwargs) -> Tensor:
-        x = self.conv_1(x)
-        x = self.layer_1(x)
-        x = self.layer_2(x)
-        x = self.layer_3(x)
-        x = self.layer_4(x)
-        x = self.layer_5(x)
+        for m in self._chain:
+            object.__setattr__(m, "_lazy_active", bool(self.fuse_boundaries))
+        try:
+            x = self.conv_1(x)
+            x = self.layer_1(x)
+            x = self.layer_2(x)
+            x = self.layer_3(x)
+            x = self.layer_4(x)
+            x = self.layer_5(x)
+        finally:
+            for m in self._chain:
+                object.__setattr__(m, "_lazy_active", False)
         return self.conv_1x1_exp(x)
 
     def forward_classifier(self, x: Tensor, *args, **kwargs) -> Tensor:

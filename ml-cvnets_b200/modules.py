@@ -44,6 +44,22 @@ class BaseModule(nn.Module):
         raise NotImplementedError
 
 
+# ------------------------------------------------------------------------------------------------ lazy module boundaries
+def _lazy_out(module) -> bool:
+    """True while the model assembler runs its own chain and has marked this module's consumer as one of ours (functional.LazyBN)."""
+    return bool(getattr(module, "_lazy_out", False) and getattr(module, "_lazy_active", False))
+
+
+def _tag(out: Tensor, cfg) -> Tensor:
+    if cfg.lazy_out:
+        out._cvb_lazy = cfg.last_lazy  # the tensor is PRE-BatchNorm; only the next hot-path module may consume it
+    return out
+
+
+def _lazy_in(x: Tensor):
+    return getattr(x, "_cvb_lazy", None)
+
+
 # -------------------------------------------------------------------------------------------------------------- stem
 def _stem_forward(layer: ConvLayer2d, x: Tensor) -> Tensor:
     _require_cuda(x, "ConvLayer2d(stem)")
@@ -55,8 +71,9 @@ def _stem_forward(layer: ConvLayer2d, x: Tensor) -> Tensor:
     cfg.bn = Fn.bn_cfg(layer.block.norm)
     cfg.ws = getattr(layer, "_ws", None)
     cfg.plist = [layer.block.conv.weight, layer.block.norm.weight, layer.block.norm.bias]
+    cfg.lazy_out = _lazy_out(layer)
     cfg.prep.prepare(force=layer.training)
-    return Fn.StemFn.apply(x, cfg, *cfg.plist)
+    return _tag(Fn.StemFn.apply(x, cfg, *cfg.plist), cfg)
 
 
 # ---------------------------------------------------------------------------------------------------- InvertedResidual
@@ -107,8 +124,9 @@ class InvertedResidual(BaseModule):
         cfg.plist = [b.exp_1x1.block.conv.weight, b.exp_1x1.block.norm.weight, b.exp_1x1.block.norm.bias,
                      b.conv_3x3.block.conv.weight, b.conv_3x3.block.norm.weight, b.conv_3x3.block.norm.bias,
                      b.red_1x1.block.conv.weight, b.red_1x1.block.norm.weight, b.red_1x1.block.norm.bias]
+        cfg.lazy_in, cfg.lazy_out = _lazy_in(x), _lazy_out(self) and not self.use_res_connect
         cfg.prep.prepare(force=self.training)
-        return Fn.InvertedResidualFn.apply(Fn.to_bf16_cl(x), cfg, *cfg.plist)
+        return _tag(Fn.InvertedResidualFn.apply(Fn.to_bf16_cl(x), cfg, *cfg.plist), cfg)
 
     def __repr__(self) -> str:
         return "{}(in_channels={}, out_channels={}, stride={}, exp={}, dilation={}, skip_conn={})".format(
@@ -264,8 +282,9 @@ class MobileViTBlockv2(BaseModule):
         cfg.bn = [Fn.bn_cfg(self.local_rep[0].block.norm), Fn.bn_cfg(self.conv_proj.block.norm)]
         cfg.ws = getattr(self, "_ws", None)
         cfg.plist = self._params()
+        cfg.lazy_in, cfg.lazy_out = _lazy_in(x), _lazy_out(self)
         cfg.prep.prepare(force=self.training)
-        return Fn.MobileViTBlockv2Fn.apply(Fn.to_bf16_cl(x), cfg, *cfg.plist)
+        return _tag(Fn.MobileViTBlockv2Fn.apply(Fn.to_bf16_cl(x), cfg, *cfg.plist), cfg)
 
     def forward(self, x: Union[Tensor, Tuple[Tensor]], *args, **kwargs) -> Union[Tensor, Tuple[Tensor, Tensor]]:
         if isinstance(x, Tuple) and len(x) == 2:
@@ -314,8 +333,8 @@ class TransformerEncoder(BaseModule):
 
     def _build_cfg(self):
         from . import ops
-        if self.norm_type != "layer_norm":
-            raise NotImplementedError("transformer_norm_layer must be layer_norm")
+        if self.norm_type not in ("layer_norm", "layer_norm_fp32"):
+            raise NotImplementedError("transformer_norm_layer must be layer_norm or layer_norm_fp32")
         if self.std_dropout or self.ffn_dropout:
             raise NotImplementedError("dropout > 0 is not implemented")
         if self.embed_dim % 8 or self.ffn_dim % 8:
@@ -343,8 +362,11 @@ class TransformerEncoder(BaseModule):
             self._build_cfg()
         cfg = self._cfg
         cfg.masks = (attn_mask, key_padding_mask)
+        cfg.eps = float(self.pre_norm_mha[0].eps)  # VisionTransformer.update_layer_norm_eps rewrites it after construction (vit.py:204-208)
         cfg.prep.prepare(force=self.training)
         n1, mha, n2 = self.pre_norm_mha[0], self.pre_norm_mha[1], self.pre_norm_ffn[0]
         l1, l2 = self.pre_norm_ffn[1], self.pre_norm_ffn[4]
-        return Fn.TransformerEncoderFn.apply(x.to(torch.bfloat16).contiguous(), cfg, n1.weight, n1.bias, mha.qkv_proj.weight, mha.qkv_proj.bias,
-                                             mha.out_proj.weight, mha.out_proj.bias, n2.weight, n2.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+        cfg.ws = getattr(self, "_ws", None)
+        cfg.plist = [n1.weight, n1.bias, mha.qkv_proj.weight, mha.qkv_proj.bias, mha.out_proj.weight, mha.out_proj.bias, n2.weight, n2.bias,
+                     l1.weight, l1.bias, l2.weight, l2.bias]
+        return Fn.TransformerEncoderFn.apply(x.to(torch.bfloat16).contiguous(), cfg, *cfg.plist)

@@ -230,6 +230,43 @@ def dw_bwd(DZ: Tensor, X: Tensor, B: int, H: int, W: int, C: int, stride: int, W
     return DX, dWt
 
 
+def im2col(x: Tensor, k: int, stride: int, pad: int, lda: Optional[int] = None) -> Tuple[Tensor, int, int]:
+    """x: [B, Cin, H, W] logical (fp32 or bf16, any strides) -> bf16 patch matrix [B*Ho*Wo, lda], columns (u, v, ci), zero padded."""
+    B, Cin, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    lda = lda or (k * k * Cin + 7) // 8 * 8
+    A = torch.empty((B * Ho * Wo, lda), device=x.device, dtype=torch.bfloat16)
+    assert x.dtype in (torch.float32, torch.bfloat16)
+    sn, sc, sh, sw = x.stride()
+    L.check(_lib().cvb_im2col(x.data_ptr(), int(x.dtype == torch.float32), sn, sc, sh, sw, B, Cin, H, W, k, stride, pad, A.data_ptr(), lda, _stream()),
+            "cvb_im2col")
+    _count()
+    return A, Ho, Wo
+
+
+def col2im(dA: Tensor, B: int, Cin: int, H: int, W: int, k: int, stride: int, pad: int) -> Tensor:
+    """adjoint of im2col for channels-last bf16: returns dX as the [B*H*W, Cin] matrix."""
+    dX = torch.empty((B * H * W, Cin), device=dA.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_col2im(dA.data_ptr(), dA.stride(0), B, Cin, H, W, k, stride, pad, dX.data_ptr(), _stream()), "cvb_col2im")
+    _count()
+    return dX
+
+
+def vit_tokens_fwd(patch: Tensor, pos: Tensor, cls: Optional[Tensor], B: int, N: int, C: int) -> Tensor:
+    S = N + (1 if cls is not None else 0)
+    out = torch.empty((B, S, C), device=patch.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_vit_tokens_fwd(patch.data_ptr(), pos.data_ptr(), _p(cls), out.data_ptr(), B, N, C, _stream()), "cvb_vit_tokens_fwd")
+    _count()
+    return out
+
+
+def vit_tokens_bwd(dout: Tensor, dpos: Tensor, dcls: Optional[Tensor], B: int, N: int, C: int) -> Tensor:
+    dpatch = torch.empty((B * N, C), device=dout.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_vit_tokens_bwd(dout.data_ptr(), dpatch.data_ptr(), dpos.data_ptr(), _p(dcls), B, N, C, _stream()), "cvb_vit_tokens_bwd")
+    _count()
+    return dpatch
+
+
 def stem_im2col(x: Tensor) -> Tensor:
     """fp32 image [B,3,H,W] (any strides) -> bf16 patch matrix [B*(H/2)*(W/2), 32]."""
     lib = _lib()
@@ -528,6 +565,7 @@ class PreparedWeights:
     """
 
     KIND_ROWMAJOR, KIND_TRANSPOSED, KIND_TAPMAJOR_F32, KIND_VECTOR_F32 = 0, 1, 2, 3
+    KIND_PATCH, KIND_PATCH_T = 4, 5  # dense conv weight [Cout, Cin, k, k] -> [Cout, (tap, ci)] / its transpose (rot = taps = k*k)
 
     def __init__(self):
         self._entries = []  # (param, dst, rows, cols, ldd, dst_rows, kind, rot)
@@ -547,13 +585,13 @@ class PreparedWeights:
     def _alloc(self, device):
         for e in self._entries:
             param, _, rows, cols, ldd, dst_rows, kind, rot = e
-            if kind == self.KIND_ROWMAJOR:
+            if kind in (self.KIND_ROWMAJOR, self.KIND_PATCH):
                 ldd = ldd or (cols + 7) // 8 * 8
                 dst_rows = dst_rows or rows
                 dst = torch.empty((dst_rows, ldd), device=device, dtype=torch.bfloat16)
-            elif kind == self.KIND_TRANSPOSED:
+            elif kind in (self.KIND_TRANSPOSED, self.KIND_PATCH_T):
                 ldd = ldd or (rows + 7) // 8 * 8
-                dst_rows = dst_rows or cols
+                dst_rows = dst_rows or (cols + 7) // 8 * 8 if kind == self.KIND_PATCH_T else (dst_rows or cols)
                 dst = torch.empty((dst_rows, ldd), device=device, dtype=torch.bfloat16)
             elif kind == self.KIND_TAPMAJOR_F32:
                 ldd, dst_rows = rows, cols

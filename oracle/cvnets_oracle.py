@@ -86,7 +86,7 @@ def batch_norm(P: Params, pre: str, x: Tensor, training: bool, momentum: float =
 
 
 def conv_layer_2d(P: Params, pre: str, x: Tensor, *, stride: int = 1, groups: int = 1, use_norm: bool = True,
-                  use_act: bool = True, training: bool = True, momentum: float = 0.1) -> Tensor:
+                  use_act: bool = True, training: bool = True, momentum: float = 0.1, act: str = "swish") -> Tensor:
     """ConvLayer2d = Sequential(conv[, norm][, act]) (cvnets/layers/conv_layer.py:200-226,254-255).
 
     Auto padding ``(k-1)//2`` (``:182-185``); norm = BatchNorm2d (``model.normalization.name=batch_norm``,
@@ -99,7 +99,7 @@ def conv_layer_2d(P: Params, pre: str, x: Tensor, *, stride: int = 1, groups: in
     if use_norm:
         x = batch_norm(P, pre + ".block.norm", x, training, momentum)
     if use_act:
-        x = F.silu(x)
+        x = F.silu(x) if act == "swish" else F.gelu(x)
     return x
 
 
@@ -291,6 +291,45 @@ def mobilevit_v2_forward(P: Params, x: Tensor, *, width_multiplier: float = 1.0,
 
 
 # --------------------------------------------------------------------------------------------
+# VisionTransformer (cvnets/models/classification/vit.py:33-649, classification path; config/vit.py:12-116)
+# --------------------------------------------------------------------------------------------
+VIT_MODES = {"tiny": (192, 12, 3), "small": (384, 12, 6), "base": (768, 12, 12)}
+
+
+def vit_shapes(mode: str = "base", n_classes: int = 1000) -> Dict[str, Tensor]:
+    d, n, _ = VIT_MODES[mode]
+    stem = max(32, d // 4)
+    P: Dict[str, Tensor] = {"cls_token": torch.empty(1, 1, d)}
+    _conv_bn(P, "patch_emb.0", 3, stem, 4)
+    _conv_bn(P, "patch_emb.1", stem, stem, 2)
+    _conv_bn(P, "patch_emb.2", stem, d, 2, norm=False, bias=True)
+    _gn(P, "post_transformer_norm", d)
+    for i in range(n):
+        transformer_encoder_shapes(P, f"transformer.{i}", d, 4 * d)
+    _linear(P, "classifier", d, n_classes)
+    P["pos_embed.pos_embed.pos_embed"] = torch.empty(1, 1, 196, d)
+    return P
+
+
+def vit_forward(P: Params, x: Tensor, *, mode: str = "base", training: bool = True, act: str = "gelu") -> Tensor:
+    """VisionTransformer.forward for 224x224 inputs: conv stem (4x4 s4 p1 + BN + act, 2x2 s2 + BN + act, 2x2 s2 + bias; vit.py:90-121),
+    tokens = cat(cls, patch + pos) (:476-507: no positional term on the cls token), N pre-norm encoders with LayerNorm eps 1e-6
+    (:204-208), post_transformer_norm, classifier on the cls token (:545-560, :563-573)."""
+    d, n, heads = VIT_MODES[mode]
+    h = conv_layer_2d(P, "patch_emb.0", x, stride=4, training=training, act=act)
+    h = conv_layer_2d(P, "patch_emb.1", h, stride=2, training=training, act=act)
+    h = conv_layer_2d(P, "patch_emb.2", h, stride=2, use_norm=False, use_act=False)
+    tok = h.flatten(2).transpose(1, 2)
+    assert tok.shape[1] == P["pos_embed.pos_embed.pos_embed"].shape[2], "interpolated positional embeddings are out of scope"
+    tok = tok + P["pos_embed.pos_embed.pos_embed"].reshape(1, tok.shape[1], d)
+    tok = torch.cat((P["cls_token"].expand(x.shape[0], -1, -1), tok), dim=1)
+    for i in range(n):
+        tok = transformer_encoder(P, f"transformer.{i}", tok, heads, act=act, eps=1e-6)
+    tok = layer_norm(P, "post_transformer_norm", tok, eps=1e-6)
+    return F.linear(tok[:, 0], P["classifier.weight"], P["classifier.bias"])
+
+
+# --------------------------------------------------------------------------------------------
 # parameter construction (shape contract: SURVEY.md App. B) + deterministic seeding used by the golden files
 # --------------------------------------------------------------------------------------------
 def _conv_bn(P: Dict, pre: str, cin: int, cout: int, k: int, groups: int = 1, norm: bool = True, bias: bool = False):
@@ -388,6 +427,8 @@ def seeded_fill_(P: Dict[str, Tensor], seed: int) -> Dict[str, Tensor]:
             t.copy_(0.1 * torch.randn(t.shape, generator=g))
         elif k.endswith("running_var"):
             t.copy_(1.0 + 0.2 * torch.rand(t.shape, generator=g))
+        elif k in ("cls_token", "pos_embed.pos_embed.pos_embed"):
+            t.copy_(0.05 * torch.randn(t.shape, generator=g))
         elif t.dim() == 1 and k.endswith(".weight"):  # BN / GN gamma
             t.copy_(1.0 + 0.2 * torch.randn(t.shape, generator=g))
         elif t.dim() == 1:  # biases, beta

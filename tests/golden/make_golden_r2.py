@@ -66,7 +66,8 @@ def main():
         P = {}
         O._gn(P, "m", C)
         m = cls(C)
-        load_seeded(m, strip("m.", P), 39)
+        O.seeded_fill_(P, 39)  # fill under the PREFIXED keys ("m.weight" is a norm gamma; a bare "weight" would be seeded like a bias)
+        m.load_state_dict({k: v.clone() for k, v in strip("m.", P).items()}, strict=True)
         fx[name] = dict(cfg=dict(c=C), seed=39, **run_module(m, O.seeded_input(shape, 141), 241))
     P = {}
     O._linear(P, "m", 32, 40)
@@ -94,7 +95,27 @@ def main():
                    grads={k: g.clone().half() if g.numel() > 4096 else g.clone() for k, g in grads.items() if g.numel() <= 65536},
                    buffers_after={k: b.detach().clone() for k, b in model.named_buffers() if b.numel() <= 4096})
     torch.save(fixture, os.path.join(HERE, "mobilevit_v2_b16_fp32.pt"))
-    for fn in ("standalone_fp32.pt", "mobilevit_v2_b16_fp32.pt"):
+    # ---- VisionTransformer, "small" geometry (same code path as base: 12 layers, head_dim 64, S = 197), batch 2 @ 224
+    opts = make_opts(1.0)
+    for k, v in {"model.classification.name": "vit", "model.classification.vit.mode": "small", "model.classification.vit.norm_layer": "layer_norm_fp32",
+                 "model.activation.name": "gelu", "model.classification.activation.name": "gelu", "model.classification.n_classes": 1000}.items():
+        setattr(opts, k, v)
+    model = get_model(opts)
+    P = O.vit_shapes("small")
+    load_seeded(model, P, 51)
+    model.train()
+    x = O.seeded_input((2, 3, 224, 224), 351)
+    labels = torch.tensor([5, 701])
+    logits = model(x)
+    loss = F.cross_entropy(logits, labels, label_smoothing=0.1)
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    vit_fx = dict(mode="small", seed=51, x_seed=351, labels=labels, logits=logits.detach().clone(), loss=loss.detach().clone(),
+                  keys=[[k, list(v.shape)] for k, v in model.state_dict().items()],
+                  grad_norms={k: float(g.norm()) for k, g in grads.items()},
+                  grads={k: g.clone() for k, g in grads.items() if g.numel() <= 20000})
+    torch.save(vit_fx, os.path.join(HERE, "vit_small_fp32.pt"))
+    for fn in ("standalone_fp32.pt", "mobilevit_v2_b16_fp32.pt", "vit_small_fp32.pt"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 
 

@@ -212,3 +212,22 @@ def test_model_batch16_fixture(golden_dir):
     for k, g in fx["grads"].items():
         e = float((P[k].grad - g.float()).norm() / (g.float().norm() + 1e-12))
         assert e <= (2e-3 if g.dtype == torch.float16 else 2e-4), (k, e)
+
+
+def test_vit_small_fixture(golden_dir):
+    """VisionTransformer restatement (conv stem, cls / positional embedding, 12 encoders, post norm, classifier) == the real reference."""
+    import torch.nn.functional as F
+    fx = torch.load(os.path.join(golden_dir, "vit_small_fp32.pt"), weights_only=False)
+    shapes = O.vit_shapes(fx["mode"])
+    assert {k: list(v.shape) for k, v in shapes.items()} == {k: s for k, s in fx["keys"]}
+    P = O.clone_params(O.seeded_fill_(shapes, fx["seed"]))
+    x = O.seeded_input((2, 3, 224, 224), fx["x_seed"])
+    logits = O.vit_forward(P, x, mode=fx["mode"], training=True)
+    loss = F.cross_entropy(logits, fx["labels"], label_smoothing=0.1)
+    loss.backward()
+    assert float((logits - fx["logits"]).norm() / fx["logits"].norm()) <= 2e-5
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5
+    for k, n in fx["grad_norms"].items():
+        assert abs(float(P[k].grad.norm()) - n) <= 2e-3 * n + 1e-7, k
+    for k, g in fx["grads"].items():
+        assert float((P[k].grad - g).norm() / (g.norm() + 1e-12)) <= 5e-4, k
