@@ -660,12 +660,158 @@ def run_ours(args, rank, world, local_rank):
     emit(line)
 
 
+# ------------------------------------------------------------------------------------- secondary workload: ViT-B/16 (BASELINE configs[2])
+VIT_GFLOP_PER_IMAGE = {"base": 106.2, "small": 27.6, "tiny": 7.5}  # 3 x 2 x forward GMAC (fwd + bwd)
+
+
+def vit_eager_baseline(dev, B, mode, steps, warmup):
+    """The reference's ViT path on this GPU: oracle restatement under torch bf16 autocast + GradScaler + clip + AdamW(fused), eager."""
+    from oracle import cvnets_oracle as O
+    P = O.clone_params(O.seeded_fill_(O.vit_shapes(mode), 0), device=dev)
+    decay = [v for v in P.values() if v.requires_grad and v.dim() > 1]
+    no_decay = [v for v in P.values() if v.requires_grad and v.dim() <= 1]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.2}, {"params": no_decay, "weight_decay": 0.0}], lr=2e-3, fused=True)
+    scaler = torch.amp.GradScaler("cuda", enabled=True)
+    gen = torch.Generator(device=dev).manual_seed(99)
+    x = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
+    y = torch.randint(0, NCLS, (B,), device=dev, generator=gen)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(O.vit_forward(P, x, mode=mode, training=True), y, label_smoothing=0.1)
+        opt.zero_grad(set_to_none=True)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(decay + no_decay, 1.0)
+        scaler.step(opt)
+        scaler.update()
+
+    for _ in range(max(3, warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    del P
+    torch.cuda.empty_cache()
+    return {"what": "oracle restatement of the reference ViT, torch eager bf16 autocast + GradScaler + clip 1.0 + AdamW(fused)", "per_gpu_batch": B,
+            "value": B / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms, "steps": steps}
+
+
+def run_vit(args, rank, world, local_rank):
+    """`--workload vit_<mode>`: ViT-B/16 training step (fwd + CE + bwd + clip + AdamW), bf16, 224x224, per-GPU batch 256 by default
+    (examples/vit/classification/vit_base.yaml:13-14).  Tensor-bound: the roofline is dense-bf16 TFLOP/s."""
+    import ml_cvnets_b200 as m
+    from ml_cvnets_b200 import ops
+    mode = args.workload.split("_", 1)[1].replace("b16", "base")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(rank)
+    B = args.batch if args.batch != 128 else 256
+    model = m.VisionTransformer(m.default_vit_opts(mode)).to(dev).train()
+    ts = m.TrainStep(model, lr=2e-3, weight_decay=0.2, max_norm=1.0, label_smoothing=0.1, ema_momentum=(0.0005 if args.ema else None), n_buckets=args.buckets)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x_dev = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
+    y_dev = torch.randint(0, NCLS, (B,), device=dev, generator=gen)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        ts.step(x_dev, y_dev)
+    if not args.no_graph:
+        ts.capture(x_dev, y_dev)
+        x_dev, y_dev = ts.static_inputs
+        for _ in range(5):
+            ts.step(x_dev, y_dev)
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    marks[0].record()
+    for i in range(args.steps):
+        loss = ts.step(x_dev, y_dev)
+        marks[i + 1].record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(marks[0].elapsed_time(marks[-1])) / args.steps
+    per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
+    value = world * B / (ms_step * 1e-3)
+    launches = (ts.launches_per_step * args.steps) if not args.no_graph else (ops.launch_count - n0)
+    # end to end: pinned host -> device every step, loss read back every step
+    hx, hy = torch.randn(B, 3, 224, 224).pin_memory(), torch.randint(0, NCLS, (B,)).pin_memory()
+    dx, dy = torch.empty_like(x_dev), torch.empty_like(y_dev)
+    hloss = torch.zeros(1).pin_memory()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        dx.copy_(hx, non_blocking=True)
+        dy.copy_(hy, non_blocking=True)
+        loss = ts.step(dx, dy)
+        hloss.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _ = float(hloss[0])
+    e1.record()
+    sync_all()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1440.0))
+    gflop = VIT_GFLOP_PER_IMAGE.get(mode)
+    ach = (value / world) * gflop / 1e3 if gflop else None
+    eager = None
+    if not args.no_eager_baseline and world == 1:
+        try:
+            eager = vit_eager_baseline(dev, B, mode, max(3, args.steps // 2), 3)
+            eager["ours_over_eager"] = value / eager["value"]
+        except Exception as e:
+            eager = {"error": repr(e)[:300]}
+    emit({
+        "metric": f"images/sec training step, ViT-{mode}/16 bf16 224x224", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"ViT-{mode}/16 bf16 forward + loss + backward + clip + AdamW, synthetic 224x224 (BASELINE.json configs[2])", "per_gpu_batch": B,
+                   "global_batch": B * world, "parallelism": f"dp{world}", "resolution": 224, "l2": "activations per step (> 10 GB) exceed the 126 MB L2"},
+        "step_ms": {"min": per[0], "median": per[len(per) // 2], "max": per[-1]}, "clocks": clocks,
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": world * (hx.numel() * 4 + hy.numel() * 8), "d2h_bytes_per_step": world * 4,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "whole step (one CUDA-graph launch): tensor-bound GEMMs + attention", "bound": "tensor", "achieved": ach, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "traffic": None,
+                     "algorithmic_gflop_per_image": gflop},
+        "gpu_eager_baseline": eager, "loss": float(loss.detach()),
+    })
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (recipe: 128)")
+    ap.add_argument("--workload", default="mobilevit_v2", help="mobilevit_v2 (the metric) | vit_b16 | vit_small (BASELINE.json configs[2] family)")
     ap.add_argument("--width", type=float, default=1.0, help="MobileViTv2 width multiplier (1.0 = the metric config, 2.0 = BASELINE.json configs[3])")
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="wall-clock bound (s) of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
@@ -688,7 +834,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload.startswith("vit_"):
+            run_vit(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             torch.distributed.destroy_process_group()

@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 from .workspace import Arena
-from .ops import A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU, E_GN_BWD, E_SILU_BWD, E_STORE
+from .ops import A_AFF, A_AFF_SILU, A_BNB, A_GN, A_RAW, A_SILU, E_GN_BWD, E_SILU_BWD, E_STORE
 
 BF16 = torch.bfloat16
 
