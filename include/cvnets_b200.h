@@ -331,6 +331,14 @@ CVB_API int cvb_col2im(const void* dA, int lda, int B, int Cin, int H, int W, in
 /* ViT token assembly (vit.py:476-507): out[b,0] = cls (no positional term), out[b,1+n] = patch[b,n] + pos[n]; patch bf16 [B*N, C] (the
  * channels-last output of the last stem conv IS token-major), pos fp32 [N, C], cls fp32 [C] or NULL, out bf16 [B, N(+1), C].
  * bwd: dpatch = dout[:, 1:], dpos += sum_b dout[:, 1:], dcls += sum_b dout[:, 0] (fp32, accumulated into caller-zeroed buffers). */
+/* MobileViT-v1 unfolding / folding (cvnets/modules/mobilevit_block.py:186-267) as a row permutation of the channels-last matrix:
+ * feature-map row (b, h, w) <-> token row (b*P + p, n), p = (h % ph)*pw + (w % pw), n = (h / ph)*(W / pw) + (w / pw), P = ph*pw.
+ * inverse = 0: X is the feature map [B*H*W, C], OUT the token matrix [B*P, N, C]; inverse = 1: the other way (folding).  The permutation
+ * is its own adjoint with the flag flipped.  H, W must be multiples of the patch (the bilinear resize branch, :191-200, is not implemented). */
+CVB_API int cvb_patch_permute(const void* X, void* OUT, int B, int H, int W, int C, int patch_h, int patch_w, int inverse, cvb_stream_t stream);
+/* OUT[m, :] = [A[m, :C1] | B[m, :C2]] (torch.cat((res, fm), dim=1) on channels-last maps, mobilevit_block.py:287) and the adjoint split */
+CVB_API int cvb_concat2(const void* A, const void* B, int C1, int C2, int64_t M, void* OUT, cvb_stream_t stream);
+CVB_API int cvb_split2(const void* G, int C1, int C2, int64_t M, void* DA, void* DB, cvb_stream_t stream);
 CVB_API int cvb_vit_tokens_fwd(const void* patch, const float* pos, const float* cls, void* out, int B, int N, int C, cvb_stream_t stream);
 CVB_API int cvb_vit_tokens_bwd(const void* dout, void* dpatch, float* dpos, float* dcls, int B, int N, int C, cvb_stream_t stream);
 

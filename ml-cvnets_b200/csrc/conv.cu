@@ -145,6 +145,47 @@ __global__ void __launch_bounds__(CNT) vit_tokens_bwd_kernel(const bf16* __restr
   }
 }
 
+// MobileViT-v1 unfolding / folding (cvnets/modules/mobilevit_block.py:186-267) on channels-last rows: the feature map row (b, h, w) and the
+// token row (b*P + p, n) with p = (h % ph) * pw + (w % pw), n = (h / ph) * (W / pw) + (w / pw) hold the same C values: a row permutation.
+__global__ void __launch_bounds__(CNT) patch_permute_kernel(const bf16* __restrict__ X, bf16* __restrict__ OUT, int H, int W, int C, int ph, int pw,
+                                                            int inverse, int64_t npix) {
+  pdl_wait();
+  pdl_trigger();
+  const int cg = C >> 3, nw = W / pw, N = (H / ph) * nw, P = ph * pw;
+  const int64_t total = npix * cg;
+  for (int64_t idx = (int64_t)blockIdx.x * CNT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * CNT) {
+    const int64_t pix = idx / cg;
+    const int c8 = (int)(idx % cg);
+    const int w = (int)(pix % W), h = (int)((pix / W) % H);
+    const int64_t b = pix / ((int64_t)W * H);
+    const int p = (h % ph) * pw + (w % pw), n = (h / ph) * nw + (w / pw);
+    const int64_t tok = (b * P + p) * N + n;
+    if (inverse) stg16(OUT + pix * C + c8 * 8, ldg16(X + tok * C + c8 * 8));
+    else stg16(OUT + tok * C + c8 * 8, ldg16(X + pix * C + c8 * 8));
+  }
+}
+
+// channel concatenation of two channels-last matrices (torch.cat((res, fm), dim=1), mobilevit_block.py:287) and its adjoint
+__global__ void __launch_bounds__(CNT) concat2_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, bf16* __restrict__ OUT, int C1, int C2,
+                                                      int split, int64_t M, bf16* __restrict__ DA, bf16* __restrict__ DB) {
+  pdl_wait();
+  pdl_trigger();
+  const int cg = (C1 + C2) >> 3, cg1 = C1 >> 3;
+  const int64_t total = M * cg;
+  for (int64_t idx = (int64_t)blockIdx.x * CNT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * CNT) {
+    const int64_t m = idx / cg;
+    const int c8 = (int)(idx % cg);
+    if (!split) {
+      const uint4 v = c8 < cg1 ? ldg16(A + m * C1 + c8 * 8) : ldg16(B + m * C2 + (c8 - cg1) * 8);
+      stg16(OUT + m * (C1 + C2) + c8 * 8, v);
+    } else {
+      const uint4 v = ldg16(OUT + m * (C1 + C2) + c8 * 8);
+      if (c8 < cg1) stg16(DA + m * C1 + c8 * 8, v);
+      else stg16(DB + m * C2 + (c8 - cg1) * 8, v);
+    }
+  }
+}
+
 int cgrid(int64_t items) {
   int64_t g = (items + CNT - 1) / CNT;
   const int64_t cap = 16 * (int64_t)cvb_num_sms();
@@ -201,6 +242,34 @@ extern "C" int cvb_vit_tokens_bwd(const void* dout, void* dpatch, float* dpos, f
   const int has_cls = dcls != nullptr;
   CVB_CUDA(cvb_launch(vit_tokens_bwd_kernel, cgrid((int64_t)(N + has_cls) * (C / 8)), CNT, 0, static_cast<cudaStream_t>(stream),
                       static_cast<const bf16*>(dout), static_cast<bf16*>(dpatch), dpos, dcls, B, N, C, has_cls));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_patch_permute(const void* X, void* OUT, int B, int H, int W, int C, int patch_h, int patch_w, int inverse, cvb_stream_t stream) {
+  CVB_CHECK(X && OUT && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && patch_h > 0 && patch_w > 0 && H % patch_h == 0 && W % patch_w == 0,
+            "cvb_patch_permute: bad arguments (C %% 8 == 0, H, W multiples of the patch)");
+  CVB_CHECK(cvb_aligned16(X) && cvb_aligned16(OUT), "cvb_patch_permute: misaligned operand");
+  const int64_t npix = (int64_t)B * H * W;
+  CVB_CUDA(cvb_launch(patch_permute_kernel, cgrid(npix * (C / 8)), CNT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X),
+                      static_cast<bf16*>(OUT), H, W, C, patch_h, patch_w, inverse, npix));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_concat2(const void* A, const void* B, int C1, int C2, int64_t M, void* OUT, cvb_stream_t stream) {
+  CVB_CHECK(A && B && OUT && C1 > 0 && C2 > 0 && C1 % 8 == 0 && C2 % 8 == 0 && M > 0, "cvb_concat2: bad arguments");
+  CVB_CUDA(cvb_launch(concat2_kernel, cgrid(M * ((C1 + C2) / 8)), CNT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(A),
+                      static_cast<const bf16*>(B), static_cast<bf16*>(OUT), C1, C2, 0, M, static_cast<bf16*>(nullptr), static_cast<bf16*>(nullptr)));
+  CVB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int cvb_split2(const void* G, int C1, int C2, int64_t M, void* DA, void* DB, cvb_stream_t stream) {
+  CVB_CHECK(G && DA && DB && C1 > 0 && C2 > 0 && C1 % 8 == 0 && C2 % 8 == 0 && M > 0, "cvb_split2: bad arguments");
+  CVB_CUDA(cvb_launch(concat2_kernel, cgrid(M * ((C1 + C2) / 8)), CNT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(nullptr),
+                      static_cast<const bf16*>(nullptr), const_cast<bf16*>(static_cast<const bf16*>(G)), C1, C2, 1, M, static_cast<bf16*>(DA),
+                      static_cast<bf16*>(DB)));
   CVB_LAUNCH_CHECK();
   return 0;
 }

@@ -211,7 +211,7 @@ __device__ __forceinline__ PixOut load_x(const uint8_t* sX, int pix, int lane, f
     const float2 z = ffma2(xsc, o.xr, xsh);
     if (XMODE == CVB_A_AFF_SILU) {
       // one sigmoid per element serves both uses: a = z*s and silu'(z) = s + a*(1-s)
-      const float sx = 1.0f / (1.0f + __expf(-z.x)), sy = 1.0f / (1.0f + __expf(-z.y));
+      const float sx = sigmoid_f(z.x), sy = sigmoid_f(z.y);
       o.a = make_float2(z.x * sx, z.y * sy);
       o.dact = make_float2(fmaf(o.a.x, 1.0f - sx, sx), fmaf(o.a.y, 1.0f - sy, sy));
     } else {

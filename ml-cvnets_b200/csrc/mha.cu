@@ -26,15 +26,39 @@ struct MhaCfg {
   static constexpr int NT = HD / 8;       // n-tiles over the head dim
 };
 
-// cooperative load of one [S, HD] strided operand into smem rows (zero fill past S)
+// cooperative load of one [S, hd] strided operand into smem rows of HD >= hd columns (zero fill past S and past hd).  hd == HD: 16-byte
+// chunks; otherwise (MobileViT-v1 head dims 20 / 24 / 36 / 48 / 60, hd % 4 == 0) 8-byte chunks -- a head's columns start at h * hd, which
+// is 8- but not 16-byte aligned -- with the pad columns zero-filled, so that the padded tiles contribute nothing to any product.
+__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* gptr, bool pred) {
+  int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_addr), "l"(gptr), "r"(sz));
+}
 template <int HD>
-__device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, int ld, int S, int Sp, int tid, int nthreads) {
+__device__ __forceinline__ void load_rows(bf16* dst, const bf16* src, int ld, int S, int Sp, int hd, int tid, int nthreads) {
   constexpr int LD = MhaCfg<HD>::LD;
-  constexpr int CH = HD / 8;
-  for (int idx = tid; idx < Sp * CH; idx += nthreads) {
-    const int row = idx / CH, ch = idx % CH;
-    const bool ok = row < S;
-    cp_async16(smem_u32(dst + row * LD + ch * 8), src + (ok ? (size_t)row * ld + ch * 8 : 0), ok);
+  if (hd == HD) {
+    constexpr int CH = HD / 8;
+    for (int idx = tid; idx < Sp * CH; idx += nthreads) {
+      const int row = idx / CH, ch = idx % CH;
+      const bool ok = row < S;
+      cp_async16(smem_u32(dst + row * LD + ch * 8), src + (ok ? (size_t)row * ld + ch * 8 : 0), ok);
+    }
+  } else if (hd % 4 == 0) {
+    constexpr int CH = HD / 4;
+    for (int idx = tid; idx < Sp * CH; idx += nthreads) {
+      const int row = idx / CH, ch = idx % CH;
+      const bool ok = row < S && ch * 4 < hd;
+      cp_async8(smem_u32(dst + row * LD + ch * 4), src + (ok ? (size_t)row * ld + ch * 4 : 0), ok);
+    }
+  } else {  // even head dims that are not multiples of 4 (MobileViT-XS: 120 / 4 = 30): 4-byte chunks
+    constexpr int CH = HD / 2;
+    for (int idx = tid; idx < Sp * CH; idx += nthreads) {
+      const int row = idx / CH, ch = idx % CH;
+      const bool ok = row < S && ch * 2 < hd;
+      const int sz = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(dst + row * LD + ch * 2)), "l"(src + (ok ? (size_t)row * ld + ch * 2 : 0)),
+                   "r"(sz));
+    }
   }
 }
 
@@ -103,7 +127,7 @@ __device__ __forceinline__ float mask_term(const float* amask, const uint8_t* kp
 // ------------------------------------------------------------------------------------------------------------- forward
 template <int HD>
 __global__ void __launch_bounds__(128) mha_fwd_kernel(const bf16* __restrict__ QKV, int ldq, int S, int H, float scale, const float* __restrict__ amask,
-                                                      const uint8_t* __restrict__ kpm, bf16* __restrict__ O, int ldo, float* __restrict__ LSE) {
+                                                      const uint8_t* __restrict__ kpm, bf16* __restrict__ O, int ldo, float* __restrict__ LSE, int hd) {
   constexpr int LD = MhaCfg<HD>::LD;
   constexpr int NT = MhaCfg<HD>::NT;
   pdl_wait();
@@ -112,15 +136,15 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const bf16* __restrict__ Q
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int C = H * HD;
+  const int C = H * hd;
   const int Sp = (S + 63) / 64 * 64;
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sK = sQ + Sp * LD;
   bf16* sV = sK + Sp * LD;
-  const bf16* base = QKV + (size_t)b * S * ldq + h * HD;
-  load_rows<HD>(sQ, base, ldq, S, Sp, tid, 128);
-  load_rows<HD>(sK, base + C, ldq, S, Sp, tid, 128);
-  load_rows<HD>(sV, base + 2 * C, ldq, S, Sp, tid, 128);
+  const bf16* base = QKV + (size_t)b * S * ldq + h * hd;
+  load_rows<HD>(sQ, base, ldq, S, Sp, hd, tid, 128);
+  load_rows<HD>(sK, base + C, ldq, S, Sp, hd, tid, 128);
+  load_rows<HD>(sV, base + 2 * C, ldq, S, Sp, hd, tid, 128);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -191,10 +215,10 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const bf16* __restrict__ Q
       const int q = q0 + g + r * 8;
       if (q < S) {
         const float inv = 1.0f / lrow[r];  // a fully masked row gives 0 * inf = NaN, like softmax over an all -inf row in the reference
-        bf16* orow = O + ((size_t)b * S + q) * ldo + h * HD;
+        bf16* orow = O + ((size_t)b * S + q) * ldo + h * hd;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
-          *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t4) = pack_bf162(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+          if (nt * 8 + 2 * t4 < hd) *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t4) = pack_bf162(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
         if (t4 == 0) LSE[((size_t)b * H + h) * S + q] = mrow[r] + log2f(lrow[r]);
       }
     }
@@ -206,7 +230,7 @@ template <int HD>
 __global__ void __launch_bounds__(256) mha_bwd_kernel(const bf16* __restrict__ QKV, int ldq, const bf16* __restrict__ O, const bf16* __restrict__ DO,
                                                       int ldo, const float* __restrict__ LSE, int S, int H, float scale,
                                                       const float* __restrict__ amask, const uint8_t* __restrict__ kpm, bf16* __restrict__ DQKV,
-                                                      int lddq) {
+                                                      int lddq, int hd) {
   constexpr int LD = MhaCfg<HD>::LD;
   constexpr int NT = MhaCfg<HD>::NT;
   constexpr int KS = MhaCfg<HD>::KS;
@@ -216,7 +240,7 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const bf16* __restrict__ Q
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int C = H * HD;
+  const int C = H * hd;
   const int Sp = (S + 63) / 64 * 64;
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sK = sQ + Sp * LD;
@@ -224,25 +248,33 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const bf16* __restrict__ Q
   bf16* sDO = sV + Sp * LD;
   float* sLse = reinterpret_cast<float*>(sDO + Sp * LD);
   float* sD = sLse + Sp;
-  const bf16* base = QKV + (size_t)b * S * ldq + h * HD;
-  const bf16* obase = O + (size_t)b * S * ldo + h * HD;
-  const bf16* dobase = DO + (size_t)b * S * ldo + h * HD;
-  load_rows<HD>(sQ, base, ldq, S, Sp, tid, 256);
-  load_rows<HD>(sK, base + C, ldq, S, Sp, tid, 256);
-  load_rows<HD>(sV, base + 2 * C, ldq, S, Sp, tid, 256);
-  load_rows<HD>(sDO, dobase, ldo, S, Sp, tid, 256);
+  const bf16* base = QKV + (size_t)b * S * ldq + h * hd;
+  const bf16* obase = O + (size_t)b * S * ldo + h * hd;
+  const bf16* dobase = DO + (size_t)b * S * ldo + h * hd;
+  load_rows<HD>(sQ, base, ldq, S, Sp, hd, tid, 256);
+  load_rows<HD>(sK, base + C, ldq, S, Sp, hd, tid, 256);
+  load_rows<HD>(sV, base + 2 * C, ldq, S, Sp, hd, tid, 256);
+  load_rows<HD>(sDO, dobase, ldo, S, Sp, hd, tid, 256);
   cp_async_commit();
   // D[q] = sum_c dO[q,c] * O[q,c]  (softmax backward row term), lse of padded rows = +inf so that their P is exactly 0
   for (int q = tid; q < Sp; q += 256) {
     float d = 0.f;
     if (q < S) {
+      if (hd == HD) {
 #pragma unroll
-      for (int ch = 0; ch < HD / 8; ++ch) {
-        float a[8], c[8];
-        unpack8(ldg16(obase + (size_t)q * ldo + ch * 8), a);
-        unpack8(ldg16(dobase + (size_t)q * ldo + ch * 8), c);
+        for (int ch = 0; ch < HD / 8; ++ch) {
+          float a[8], c[8];
+          unpack8(ldg16(obase + (size_t)q * ldo + ch * 8), a);
+          unpack8(ldg16(dobase + (size_t)q * ldo + ch * 8), c);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d = fmaf(a[e], c[e], d);
+          for (int e = 0; e < 8; ++e) d = fmaf(a[e], c[e], d);
+        }
+      } else {
+        for (int c2 = 0; c2 < hd; c2 += 2) {
+          const float2 a = unpack_bf162(*reinterpret_cast<const uint32_t*>(obase + (size_t)q * ldo + c2));
+          const float2 c = unpack_bf162(*reinterpret_cast<const uint32_t*>(dobase + (size_t)q * ldo + c2));
+          d = fmaf(a.x, c.x, fmaf(a.y, c.y, d));
+        }
       }
     }
     sD[q] = d;
@@ -252,7 +284,7 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const bf16* __restrict__ Q
   __syncthreads();
   const float sc2 = scale * LOG2E;
   const bool masked = (amask != nullptr) || (kpm != nullptr);
-  bf16* dbase = DQKV + (size_t)b * S * lddq + h * HD;
+  bf16* dbase = DQKV + (size_t)b * S * lddq + h * hd;
 
   // ---- pass A: this warp owns 16 query rows -> dQ = scale * sum_t dS[q,t] K[t,:],  dS = P o (dP - D),  dP = dO V^T
   for (int slab = warp; slab * 16 < S; slab += 8) {
@@ -292,7 +324,7 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const bf16* __restrict__ Q
         bf16* row = dbase + (size_t)q * lddq;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
-          *reinterpret_cast<uint32_t*>(row + nt * 8 + 2 * t4) = pack_bf162(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
+          if (nt * 8 + 2 * t4 < hd) *reinterpret_cast<uint32_t*>(row + nt * 8 + 2 * t4) = pack_bf162(dq[nt][2 * r] * scale, dq[nt][2 * r + 1] * scale);
       }
     }
   }
@@ -337,6 +369,7 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const bf16* __restrict__ Q
         bf16* row = dbase + (size_t)t * lddq;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
+          if (nt * 8 + 2 * t4 >= hd) continue;
           *reinterpret_cast<uint32_t*>(row + C + nt * 8 + 2 * t4) = pack_bf162(dk[nt][2 * r] * scale, dk[nt][2 * r + 1] * scale);
           *reinterpret_cast<uint32_t*>(row + 2 * C + nt * 8 + 2 * t4) = pack_bf162(dv[nt][2 * r], dv[nt][2 * r + 1]);
         }
@@ -347,31 +380,31 @@ __global__ void __launch_bounds__(256) mha_bwd_kernel(const bf16* __restrict__ Q
 
 template <int HD>
 int launch_fwd(const void* QKV, int ldq, int B, int S, int H, float scale, const float* amask, const uint8_t* kpm, void* O, int ldo, float* LSE,
-               cudaStream_t st) {
+               cudaStream_t st, int hd) {
   const int Sp = (S + 63) / 64 * 64;
   const size_t smem = (size_t)3 * Sp * MhaCfg<HD>::LD * 2;
   static bool attr = false;
   if (!attr) { CVB_CUDA(cudaFuncSetAttribute(mha_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-  CVB_CUDA(cvb_launch(mha_fwd_kernel<HD>, B * H, 128, smem, st, static_cast<const bf16*>(QKV), ldq, S, H, scale, amask, kpm, static_cast<bf16*>(O), ldo, LSE));
+  CVB_CUDA(cvb_launch(mha_fwd_kernel<HD>, B * H, 128, smem, st, static_cast<const bf16*>(QKV), ldq, S, H, scale, amask, kpm, static_cast<bf16*>(O), ldo, LSE, hd));
   CVB_LAUNCH_CHECK();
   return 0;
 }
 template <int HD>
 int launch_bwd(const void* QKV, int ldq, const void* O, const void* DO, int ldo, const float* LSE, int B, int S, int H, float scale,
-               const float* amask, const uint8_t* kpm, void* DQKV, int lddq, cudaStream_t st) {
+               const float* amask, const uint8_t* kpm, void* DQKV, int lddq, cudaStream_t st, int hd) {
   const int Sp = (S + 63) / 64 * 64;
   const size_t smem = (size_t)4 * Sp * MhaCfg<HD>::LD * 2 + (size_t)2 * Sp * 4;
   static bool attr = false;
   if (!attr) { CVB_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
   CVB_CUDA(cvb_launch(mha_bwd_kernel<HD>, B * H, 256, smem, st, static_cast<const bf16*>(QKV), ldq, static_cast<const bf16*>(O),
-                      static_cast<const bf16*>(DO), ldo, LSE, S, H, scale, amask, kpm, static_cast<bf16*>(DQKV), lddq));
+                      static_cast<const bf16*>(DO), ldo, LSE, S, H, scale, amask, kpm, static_cast<bf16*>(DQKV), lddq, hd));
   CVB_LAUNCH_CHECK();
   return 0;
 }
 
 int check_common(const char* who, const void* QKV, int ldq, int B, int S, int H, int head_dim, int ldo) {
   CVB_CHECK(QKV && B > 0 && S > 0 && H > 0, "%s: bad arguments", who);
-  CVB_CHECK(head_dim == 16 || head_dim == 32 || head_dim == 64, "%s: head_dim %d not supported (16, 32, 64)", who, head_dim);
+  CVB_CHECK(head_dim >= 2 && head_dim <= 64 && head_dim % 2 == 0, "%s: head_dim %d not supported (even values up to 64)", who, head_dim);
   CVB_CHECK(S <= 256, "%s: sequence length %d > 256 is not supported in this round (K/V of one head are shared-memory resident)", who, S);
   CVB_CHECK(ldq % 8 == 0 && ldo % 8 == 0 && ldq >= 3 * H * head_dim && ldo >= H * head_dim && cvb_aligned16(QKV), "%s: bad leading dimensions / alignment", who);
   return 0;
@@ -384,11 +417,9 @@ extern "C" int cvb_mha_fwd(const void* QKV, int ldq, int B, int S, int H, int he
   if (check_common("cvb_mha_fwd", QKV, ldq, B, S, H, head_dim, ldo)) return 1;
   CVB_CHECK(O && LSE && cvb_aligned16(O), "cvb_mha_fwd: null / misaligned output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (head_dim) {
-    case 16: return launch_fwd<16>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st);
-    case 32: return launch_fwd<32>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st);
-    default: return launch_fwd<64>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st);
-  }
+  if (head_dim <= 16) return launch_fwd<16>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st, head_dim);
+  if (head_dim <= 32) return launch_fwd<32>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st, head_dim);
+  return launch_fwd<64>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st, head_dim);
 }
 
 extern "C" int cvb_mha_bwd(const void* QKV, int ldq, const void* O, const void* DO, int ldo, const float* LSE, int B, int S, int H, int head_dim,
@@ -397,9 +428,7 @@ extern "C" int cvb_mha_bwd(const void* QKV, int ldq, const void* O, const void* 
   CVB_CHECK(O && DO && LSE && DQKV && cvb_aligned16(O) && cvb_aligned16(DO) && cvb_aligned16(DQKV) && lddq % 8 == 0 && lddq >= 3 * H * head_dim,
             "cvb_mha_bwd: null / misaligned operand");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (head_dim) {
-    case 16: return launch_bwd<16>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st);
-    case 32: return launch_bwd<32>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st);
-    default: return launch_bwd<64>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st);
-  }
+  if (head_dim <= 16) return launch_bwd<16>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st, head_dim);
+  if (head_dim <= 32) return launch_bwd<32>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st, head_dim);
+  return launch_bwd<64>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st, head_dim);
 }

@@ -838,6 +838,60 @@ class GlobalPoolFn(torch.autograd.Function):
         return to_4d(ops.global_pool_bwd(g, B, H * W), B, H, W), None
 
 
+class UnfoldFn(torch.autograd.Function):
+    """MobileViTBlock.unfolding (cvnets/modules/mobilevit_block.py:186-231): [B, C, H, W] -> [B*P, N, C] tokens (a row permutation)."""
+
+    @staticmethod
+    def forward(ctx, x, ph, pw):
+        B, C, H, W = x.shape
+        if H % ph or W % pw:
+            raise NotImplementedError("H, W must be multiples of the patch size (the bilinear resize branch, mobilevit_block.py:191-200, is not implemented)")
+        ctx.dims = (B, C, H, W, ph, pw)
+        return ops.patch_permute(as_2d(x), B, H, W, ph, pw, False).view(B * ph * pw, (H // ph) * (W // pw), C)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W, ph, pw = ctx.dims
+        g2 = g.reshape(-1, C)
+        if g2.dtype != BF16 or not g2.is_contiguous():
+            g2 = g2.to(BF16).contiguous()
+        return to_4d(ops.patch_permute(g2, B, H, W, ph, pw, True), B, H, W), None, None
+
+
+class FoldFn(torch.autograd.Function):
+    """MobileViTBlock.folding (mobilevit_block.py:233-267): [B*P, N, C] tokens -> [B, C, H, W]."""
+
+    @staticmethod
+    def forward(ctx, t, B, H, W, ph, pw):
+        C = t.shape[-1]
+        t2 = t.reshape(-1, C)
+        if t2.dtype != BF16 or not t2.is_contiguous():
+            t2 = t2.to(BF16).contiguous()
+        ctx.dims = (B, C, H, W, ph, pw, tuple(t.shape))
+        return to_4d(ops.patch_permute(t2, B, H, W, ph, pw, True), B, H, W)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W, ph, pw, shape = ctx.dims
+        return ops.patch_permute(as_2d(to_bf16_cl(g)), B, H, W, ph, pw, False).view(shape), None, None, None, None, None
+
+
+class Concat2Fn(torch.autograd.Function):
+    """torch.cat((a, b), dim=1) on channels-last feature maps (the fusion input of MobileViTBlock, mobilevit_block.py:287)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        B, C1, H, W = a.shape
+        ctx.dims = (B, C1, b.shape[1], H, W)
+        return to_4d(ops.concat2(as_2d(a), as_2d(b)), B, H, W)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C1, C2, H, W = ctx.dims
+        da, db = ops.split2(as_2d(to_bf16_cl(g)), C1, C2)
+        return to_4d(da, B, H, W), to_4d(db, B, H, W)
+
+
 class VitTokensFn(torch.autograd.Function):
     """ViT token assembly (cvnets/models/classification/vit.py:476-507): tokens = cat(cls, patch_embedding + positional_embedding).
     patch: [B, C, nh, nw] channels-last (== token-major [B*N, C]); pos: [1, 1, N, C]; cls: [1, 1, C] or None.  Returns [B, N(+1), C]."""

@@ -77,8 +77,10 @@ class LayerNorm2D_NCHW(nn.GroupNorm):
         _need_cuda(x, "LayerNorm2D_NCHW")
         if x.dim() != 4 or x.shape[1] % 8 or not self.affine:
             raise NotImplementedError("LayerNorm2D_NCHW: expects [B, C, H, W] with C % 8 == 0 and affine=True")
-        cfg = SimpleNamespace(eps=float(self.eps), ws=getattr(self, "_ws", None), plist=[self.weight, self.bias])
-        self._cfg = cfg
+        cfg = getattr(self, "_cfg", None)
+        if cfg is None:  # ONE cfg object per module: its id keys the module's slice of the step workspace
+            cfg = self._cfg = SimpleNamespace()
+        cfg.eps, cfg.ws, cfg.plist = float(self.eps), getattr(self, "_ws", None), [self.weight, self.bias]
         return Fn.GroupNorm1Fn.apply(Fn.to_bf16_cl(x), cfg, self.weight, self.bias)
 
     def __repr__(self):
@@ -102,8 +104,10 @@ class LayerNorm(nn.LayerNorm):
             raise NotImplementedError("LayerNorm: last-dimension normalisation with C % 8 == 0, C <= 1024 and affine weights is implemented")
         if x.dim() > 2 and x.shape[1] == C:
             raise NotImplementedError("LayerNorm on a channel-first tensor (x.shape[1] == C, layer_norm.py:52-65) is not implemented")
-        cfg = SimpleNamespace(eps=float(self.eps), ws=getattr(self, "_ws", None), plist=[self.weight, self.bias])
-        self._cfg = cfg
+        cfg = getattr(self, "_cfg", None)
+        if cfg is None:
+            cfg = self._cfg = SimpleNamespace()
+        cfg.eps, cfg.ws, cfg.plist = float(self.eps), getattr(self, "_ws", None), [self.weight, self.bias]
         return Fn.LayerNormFn.apply(x, cfg, self.weight, self.bias)
 
 
@@ -400,10 +404,10 @@ class MultiHeadAttention(BaseLayer):
         return "{}(head_dim={}, num_heads={}, attn_dropout={})".format(self.__class__.__name__, self.head_dim, self.num_heads, self.attn_dropout.p)
 
     def check_supported(self):
-        if self.attn_dropout.p:
-            raise NotImplementedError("attention dropout > 0 is not implemented")
-        if self.head_dim not in (16, 32, 64):
-            raise NotImplementedError(f"head_dim {self.head_dim} is not implemented (16, 32, 64 are)")
+        if self.attn_dropout.p and self.training:
+            raise NotImplementedError("attention dropout > 0 in training mode is not implemented")
+        if self.head_dim % 2 or not (2 <= self.head_dim <= 64):
+            raise NotImplementedError(f"head_dim {self.head_dim} is not implemented (even values up to 64 are)")
         if self.qkv_proj.bias is None or self.out_proj.bias is None:
             raise NotImplementedError("bias=False is not implemented")
 

@@ -295,6 +295,70 @@ class MobileViTBlockv2(BaseModule):
             raise NotImplementedError
 
 
+# ------------------------------------------------------------------------------------------------------- MobileViTBlock (v1)
+class MobileViTBlock(BaseModule):
+    """cvnets/modules/mobilevit_block.py:19-326: dense 3x3 conv + 1x1 -> unfold to [B*P, N, d] tokens -> n x
+    TransformerEncoder -> LayerNorm -> fold -> 1x1 conv -> cat(input, .) -> dense 3x3 fusion conv.  Same constructor, child tree
+    (``local_rep.{conv_3x3,conv_1x1}``, ``global_rep.{i}``, ``conv_proj``, ``fusion``) and ``state_dict`` keys as the reference.
+
+    Composition of the library's own layer functions (the block is <= 0.4 GMAC at XXS scale and not on the throughput metric): dense convs
+    via im2col + GEMM, unfold / fold as one row-permutation kernel each, the encoders on the fused TransformerEncoderFn."""
+
+    def __init__(self, opts, in_channels: int, transformer_dim: int, ffn_dim: int, n_transformer_blocks: Optional[int] = 2,
+                 head_dim: Optional[int] = 32, attn_dropout: Optional[float] = 0.0, dropout: Optional[float] = 0.0, ffn_dropout: Optional[float] = 0.0,
+                 patch_h: Optional[int] = 8, patch_w: Optional[int] = 8, transformer_norm_layer: Optional[str] = "layer_norm",
+                 conv_ksize: Optional[int] = 3, dilation: Optional[int] = 1, no_fusion: Optional[bool] = False, *args, **kwargs) -> None:
+        conv_3x3_in = ConvLayer2d(opts=opts, in_channels=in_channels, out_channels=in_channels, kernel_size=conv_ksize, stride=1, use_norm=True,
+                                  use_act=True, dilation=dilation)
+        conv_1x1_in = ConvLayer2d(opts=opts, in_channels=in_channels, out_channels=transformer_dim, kernel_size=1, stride=1, use_norm=False,
+                                  use_act=False)
+        conv_1x1_out = ConvLayer2d(opts=opts, in_channels=transformer_dim, out_channels=in_channels, kernel_size=1, stride=1, use_norm=True,
+                                   use_act=True)
+        conv_3x3_out = None
+        if not no_fusion:
+            conv_3x3_out = ConvLayer2d(opts=opts, in_channels=2 * in_channels, out_channels=in_channels, kernel_size=conv_ksize, stride=1,
+                                       use_norm=True, use_act=True)
+        super().__init__()
+        self.local_rep = nn.Sequential()
+        self.local_rep.add_module(name="conv_3x3", module=conv_3x3_in)
+        self.local_rep.add_module(name="conv_1x1", module=conv_1x1_in)
+        assert transformer_dim % head_dim == 0
+        num_heads = transformer_dim // head_dim
+        global_rep = [TransformerEncoder(opts=opts, embed_dim=transformer_dim, ffn_latent_dim=ffn_dim, num_heads=num_heads, attn_dropout=attn_dropout,
+                                         dropout=dropout, ffn_dropout=ffn_dropout, transformer_norm_layer=transformer_norm_layer)
+                      for _ in range(n_transformer_blocks)]
+        global_rep.append(get_normalization_layer(opts=opts, norm_type=transformer_norm_layer, num_features=transformer_dim))
+        self.global_rep = nn.Sequential(*global_rep)
+        self.conv_proj = conv_1x1_out
+        self.fusion = conv_3x3_out
+        self.patch_h, self.patch_w, self.patch_area = patch_h, patch_w, patch_w * patch_h
+        self.cnn_in_dim, self.cnn_out_dim, self.n_heads, self.ffn_dim = in_channels, transformer_dim, num_heads, ffn_dim
+        self.dropout, self.attn_dropout, self.ffn_dropout = dropout, attn_dropout, ffn_dropout
+        self.dilation, self.n_blocks, self.conv_ksize = dilation, n_transformer_blocks, conv_ksize
+
+    def forward_spatial(self, x: Tensor) -> Tensor:
+        _require_cuda(x, "MobileViTBlock")
+        res = Fn.to_bf16_cl(x)
+        fm = self.local_rep(res)
+        B, _, H, W = fm.shape
+        patches = Fn.UnfoldFn.apply(fm, self.patch_h, self.patch_w)           # [B*P, N, d]
+        for layer in self.global_rep:
+            patches = layer(patches)
+        fm = Fn.FoldFn.apply(patches, B, H, W, self.patch_h, self.patch_w)
+        fm = self.conv_proj(fm)
+        if self.fusion is not None:
+            fm = self.fusion(Fn.Concat2Fn.apply(res, fm))
+        return fm
+
+    def forward(self, x: Union[Tensor, Tuple[Tensor]], *args, **kwargs) -> Union[Tensor, Tuple[Tensor, Tensor]]:
+        if isinstance(x, Tuple) and len(x) == 2:
+            raise NotImplementedError("forward_temporal (video cross-attention, mobilevit_block.py:290-311) is out of scope")
+        elif isinstance(x, Tensor):
+            return self.forward_spatial(x)
+        else:
+            raise NotImplementedError
+
+
 class TransformerEncoder(BaseModule):
     """cvnets/modules/transformer.py:26-156: pre-norm encoder, ``x = x + MHA(LN(x)); x = x + FFN(LN(x))``.
 
@@ -335,8 +399,6 @@ class TransformerEncoder(BaseModule):
         from . import ops
         if self.norm_type not in ("layer_norm", "layer_norm_fp32"):
             raise NotImplementedError("transformer_norm_layer must be layer_norm or layer_norm_fp32")
-        if self.std_dropout or self.ffn_dropout:
-            raise NotImplementedError("dropout > 0 is not implemented")
         if self.embed_dim % 8 or self.ffn_dim % 8:
             raise NotImplementedError("embed_dim / ffn_latent_dim must be multiples of 8")
         prep = PW()
@@ -354,6 +416,8 @@ class TransformerEncoder(BaseModule):
         _require_cuda(x, "TransformerEncoder")
         if x_prev is not None:
             raise NotImplementedError("cross-attention (x_prev) is not implemented on the B200 path")
+        if self.training and (self.std_dropout or self.ffn_dropout or self.pre_norm_mha[1].attn_dropout.p):
+            raise NotImplementedError("dropout > 0 in training mode is not implemented (it is the identity in eval mode, which works)")
         if x.dim() != 3 or x.shape[1] > 256:
             raise NotImplementedError("TransformerEncoder expects [N, S, C] with S <= 256")
         if x.shape[1] == x.shape[2]:

@@ -252,6 +252,31 @@ def col2im(dA: Tensor, B: int, Cin: int, H: int, W: int, k: int, stride: int, pa
     return dX
 
 
+def patch_permute(X: Tensor, B: int, H: int, W: int, ph: int, pw: int, inverse: bool) -> Tensor:
+    """MobileViT-v1 unfold (inverse=False: feature-map rows -> token rows [B*P*N, C]) / fold (inverse=True)."""
+    out = torch.empty_like(X)
+    L.check(_lib().cvb_patch_permute(X.data_ptr(), out.data_ptr(), B, H, W, X.shape[1], ph, pw, int(inverse), _stream()), "cvb_patch_permute")
+    _count()
+    return out
+
+
+def concat2(A: Tensor, Bt: Tensor) -> Tensor:
+    M, C1, C2 = A.shape[0], A.shape[1], Bt.shape[1]
+    out = torch.empty((M, C1 + C2), device=A.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_concat2(A.data_ptr(), Bt.data_ptr(), C1, C2, M, out.data_ptr(), _stream()), "cvb_concat2")
+    _count()
+    return out
+
+
+def split2(G: Tensor, C1: int, C2: int) -> Tuple[Tensor, Tensor]:
+    M = G.shape[0]
+    da = torch.empty((M, C1), device=G.device, dtype=torch.bfloat16)
+    db = torch.empty((M, C2), device=G.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_split2(G.data_ptr(), C1, C2, M, da.data_ptr(), db.data_ptr(), _stream()), "cvb_split2")
+    _count()
+    return da, db
+
+
 def vit_tokens_fwd(patch: Tensor, pos: Tensor, cls: Optional[Tensor], B: int, N: int, C: int) -> Tensor:
     S = N + (1 if cls is not None else 0)
     out = torch.empty((B, S, C), device=patch.device, dtype=torch.bfloat16)

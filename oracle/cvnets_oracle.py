@@ -291,6 +291,77 @@ def mobilevit_v2_forward(P: Params, x: Tensor, *, width_multiplier: float = 1.0,
 
 
 # --------------------------------------------------------------------------------------------
+# MobileViT v1 (cvnets/modules/mobilevit_block.py:19-326, cvnets/models/classification/mobilevit.py:19-300, config/mobilevit.py:14-200)
+# --------------------------------------------------------------------------------------------
+MIT_MODES = {  # mode: (mv2 expand, layer1 out, layer2 out, [(out, transformer dim, ffn dim, blocks)] x 3)
+    "xx_small": (2, 16, 24, [(48, 64, 128, 2), (64, 80, 160, 4), (80, 96, 192, 3)]),
+    "x_small": (4, 32, 48, [(64, 96, 192, 2), (80, 120, 240, 4), (96, 144, 288, 3)]),
+    "small": (4, 32, 64, [(96, 144, 288, 2), (128, 192, 384, 4), (160, 240, 480, 3)]),
+}
+
+
+def mobilevit_block_v1_shapes(P: Dict, pre: str, c: int, d: int, ffn: int, n_blocks: int):
+    _conv_bn(P, pre + ".local_rep.conv_3x3", c, c, 3)
+    _conv_bn(P, pre + ".local_rep.conv_1x1", c, d, 1, norm=False)
+    for i in range(n_blocks):
+        transformer_encoder_shapes(P, f"{pre}.global_rep.{i}", d, ffn)
+    _gn(P, f"{pre}.global_rep.{n_blocks}", d)
+    _conv_bn(P, pre + ".conv_proj", d, c, 1)
+    _conv_bn(P, pre + ".fusion", 2 * c, c, 3)
+
+
+def mobilevit_v1_shapes(mode: str = "xx_small", n_classes: int = 1000) -> Dict[str, Tensor]:
+    e, c1, c2, mits = MIT_MODES[mode]
+    P: Dict[str, Tensor] = {}
+    _conv_bn(P, "conv_1", 3, 16, 3)
+    inverted_residual_shapes(P, "layer_1.0", 16, c1, e)
+    c = c1
+    for i in range(3):
+        inverted_residual_shapes(P, f"layer_2.{i}", c, c2, e)
+        c = c2
+    for li, (co, d, f, n) in enumerate(mits):
+        inverted_residual_shapes(P, f"layer_{3 + li}.0", c, co, e)
+        c = co
+        mobilevit_block_v1_shapes(P, f"layer_{3 + li}.1", c, d, f, n)
+    _conv_bn(P, "conv_1x1_exp", c, min(4 * c, 960), 1)
+    _linear(P, "classifier.fc", min(4 * c, 960), n_classes)
+    return P
+
+
+def mobilevit_block_v1(P: Params, pre: str, x: Tensor, *, n_blocks: int, num_heads: int = 4, patch: int = 2, training: bool = True) -> Tensor:
+    """MobileViTBlock.forward_spatial (mobilevit_block.py:269-288), dropout p = 0: dense 3x3 + 1x1 -> unfolding [B*P, N, d] (:186-231) -> n x
+    TransformerEncoder -> LayerNorm -> folding (:233-267) -> 1x1 + BN + act -> cat(res, fm) -> dense 3x3 fusion."""
+    res = x
+    fm = conv_layer_2d(P, pre + ".local_rep.conv_3x3", x, training=training)
+    fm = conv_layer_2d(P, pre + ".local_rep.conv_1x1", fm, use_norm=False, use_act=False)
+    B, d, H, W = fm.shape
+    nh, nw = H // patch, W // patch
+    t = fm.reshape(B * d * nh, patch, nw, patch).transpose(1, 2).reshape(B, d, nh * nw, patch * patch).transpose(1, 3)
+    t = t.reshape(B * patch * patch, nh * nw, d)
+    for i in range(n_blocks):
+        t = transformer_encoder(P, f"{pre}.global_rep.{i}", t, num_heads, act="swish", eps=1e-5)
+    t = layer_norm(P, f"{pre}.global_rep.{n_blocks}", t, eps=1e-5)
+    t = t.contiguous().view(B, patch * patch, nh * nw, d).transpose(1, 3)
+    fm = t.reshape(B * d * nh, nw, patch, patch).transpose(1, 2).reshape(B, d, H, W)
+    fm = conv_layer_2d(P, pre + ".conv_proj", fm, training=training)
+    return conv_layer_2d(P, pre + ".fusion", torch.cat((res, fm), dim=1), training=training)
+
+
+def mobilevit_v1_forward(P: Params, x: Tensor, *, mode: str = "xx_small", training: bool = True) -> Tensor:
+    """MobileViT.forward (mobilevit.py:19-300 + base_image_encoder.py:261-301), every dropout p = 0."""
+    _, _, _, mits = MIT_MODES[mode]
+    x = conv_layer_2d(P, "conv_1", x, stride=2, training=training)
+    x = inverted_residual(P, "layer_1.0", x, stride=1, training=training)
+    for i in range(3):
+        x = inverted_residual(P, f"layer_2.{i}", x, stride=2 if i == 0 else 1, training=training)
+    for li, (_, _, _, n) in enumerate(mits):
+        x = inverted_residual(P, f"layer_{3 + li}.0", x, stride=2, training=training)
+        x = mobilevit_block_v1(P, f"layer_{3 + li}.1", x, n_blocks=n, training=training)
+    x = conv_layer_2d(P, "conv_1x1_exp", x, training=training)
+    return F.linear(x.mean(dim=[-2, -1]), P["classifier.fc.weight"], P["classifier.fc.bias"])
+
+
+# --------------------------------------------------------------------------------------------
 # VisionTransformer (cvnets/models/classification/vit.py:33-649, classification path; config/vit.py:12-116)
 # --------------------------------------------------------------------------------------------
 VIT_MODES = {"tiny": (192, 12, 3), "small": (384, 12, 6), "base": (768, 12, 12)}

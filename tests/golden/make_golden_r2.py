@@ -115,7 +115,31 @@ def main():
                   grad_norms={k: float(g.norm()) for k, g in grads.items()},
                   grads={k: g.clone() for k, g in grads.items() if g.numel() <= 20000})
     torch.save(vit_fx, os.path.join(HERE, "vit_small_fp32.pt"))
-    for fn in ("standalone_fp32.pt", "mobilevit_v2_b16_fp32.pt", "vit_small_fp32.pt"):
+    # ---- MobileViT v1 XXS (BASELINE.json configs[0]): eval forward at 1x3x256x256 + a train-mode fwd/bwd (dropouts 0) at 4x3x128x128
+    opts = make_opts(1.0)
+    for k, v in {"model.classification.name": "mobilevit", "model.classification.mit.mode": "xx_small", "model.classification.mit.dropout": 0.0,
+                 "model.classification.mit.attn_dropout": 0.0, "model.classification.mit.ffn_dropout": 0.0,
+                 "model.classification.classifier_dropout": 0.0, "model.classification.n_classes": 1000}.items():
+        setattr(opts, k, v)
+    model = get_model(opts)
+    P = O.mobilevit_v1_shapes("xx_small")
+    load_seeded(model, P, 61)
+    model.eval()
+    x1 = O.seeded_input((1, 3, 256, 256), 361)
+    with torch.no_grad():
+        eval_logits = model(x1).clone()
+    model.train()
+    x = O.seeded_input((4, 3, 128, 128), 362)
+    labels = torch.tensor([5, 701, 33, 999])
+    logits = model(x)
+    loss = F.cross_entropy(logits, labels, label_smoothing=0.1)
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    mit_fx = dict(mode="xx_small", seed=61, eval_x_seed=361, eval_logits=eval_logits, x_seed=362, labels=labels, logits=logits.detach().clone(),
+                  loss=loss.detach().clone(), keys=[[k, list(v.shape)] for k, v in model.state_dict().items()],
+                  grad_norms={k: float(g.norm()) for k, g in grads.items()}, grads={k: g.clone() for k, g in grads.items() if g.numel() <= 5000})
+    torch.save(mit_fx, os.path.join(HERE, "mobilevit_v1_xxs_fp32.pt"))
+    for fn in ("standalone_fp32.pt", "mobilevit_v2_b16_fp32.pt", "vit_small_fp32.pt", "mobilevit_v1_xxs_fp32.pt"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 
 

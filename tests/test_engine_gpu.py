@@ -103,9 +103,9 @@ def test_lazy_module_boundaries_match_materialised_outputs(pkg):
                                          {k: b.clone() for k, b in model.named_buffers()}))
     (la, ga, ba), (la2, ga2, _) = out[True]
     (lb, gb, bb), = out[False]
-    e_log, e_g, n_g = rel_l2(la, lb), rel_l2(ga, gb), rel_l2(ga2, ga)
-    print(f"lazy vs materialised: logits rel-L2 {e_log:.3g}, whole gradient {e_g:.3g} (run-to-run of the lazy path {n_g:.3g})")
-    assert e_log <= 2e-2 and e_g <= 3.0 * n_g + 1e-2
+    e_log, n_log, e_g, n_g = rel_l2(la, lb), rel_l2(la2, la), rel_l2(ga, gb), rel_l2(ga2, ga)
+    print(f"lazy vs materialised: logits rel-L2 {e_log:.3g} (run-to-run of the lazy path {n_log:.3g}), whole gradient {e_g:.3g} (run-to-run {n_g:.3g})")
+    assert e_log <= 3.0 * n_log + 5e-3 and e_g <= 3.0 * n_g + 1e-2
     for k in ba:
         assert rel_l2(ba[k].float(), bb[k].float()) <= 1e-2 or ba[k].dtype == torch.long, k
 

@@ -231,3 +231,22 @@ def test_vit_small_fixture(golden_dir):
         assert abs(float(P[k].grad.norm()) - n) <= 2e-3 * n + 1e-7, k
     for k, g in fx["grads"].items():
         assert float((P[k].grad - g).norm() / (g.norm() + 1e-12)) <= 5e-4, k
+
+
+def test_mobilevit_v1_xxs_fixture(golden_dir):
+    """MobileViT-v1 XXS (BASELINE.json configs[0]): eval forward at 1x3x256x256 and a train-mode forward/backward == the real reference."""
+    import torch.nn.functional as F
+    fx = torch.load(os.path.join(golden_dir, "mobilevit_v1_xxs_fp32.pt"), weights_only=False)
+    shapes = O.mobilevit_v1_shapes(fx["mode"])
+    assert {k: list(v.shape) for k, v in shapes.items()} == {k: s for k, s in fx["keys"]}
+    P = O.clone_params(O.seeded_fill_(shapes, fx["seed"]))
+    with torch.no_grad():
+        ev = O.mobilevit_v1_forward(P, O.seeded_input((1, 3, 256, 256), fx["eval_x_seed"]), mode=fx["mode"], training=False)
+    assert float((ev - fx["eval_logits"]).norm() / fx["eval_logits"].norm()) <= 2e-5
+    logits = O.mobilevit_v1_forward(P, O.seeded_input((4, 3, 128, 128), fx["x_seed"]), mode=fx["mode"], training=True)
+    loss = F.cross_entropy(logits, fx["labels"], label_smoothing=0.1)
+    loss.backward()
+    assert float((logits - fx["logits"]).norm() / fx["logits"].norm()) <= 5e-5
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5
+    for k, g in fx["grads"].items():
+        assert float((P[k].grad - g).norm() / (g.norm() + 1e-12)) <= 2e-3, k

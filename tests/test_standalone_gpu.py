@@ -175,3 +175,48 @@ def test_vision_transformer_against_reference_fixture(pkg, golden_dir):
         worst = max(worst, eo)
         assert eo <= max(6e-2, 2.0 * eau), (k, eo, eau)
     print(f"[vit small] worst parameter-gradient rel-L2 {worst:.4g}")
+
+
+def test_mobilevit_v1_xxs_against_reference_fixture(pkg, golden_dir):
+    """SURVEY.md 8a row a9 / BASELINE.json configs[0]: MobileViT-v1 XXS -- state_dict contract, eval forward at 1x3x256x256 and a train-mode
+    forward/backward (dropouts 0) against the REAL reference (dense 3x3 convs via im2col + GEMM, unfold / fold permutations, head dims
+    16 / 20 / 24 in the attention core)."""
+    import torch.nn.functional as F
+    fx = torch.load(os.path.join(golden_dir, "mobilevit_v1_xxs_fp32.pt"), weights_only=False)
+    opts = pkg.default_mit_opts(fx["mode"], **{"model.classification.mit.dropout": 0.0, "model.classification.classifier_dropout": 0.0})
+    model = pkg.MobileViT(opts)
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == {k: s for k, s in fx["keys"]}
+    model.load_state_dict(O.seeded_fill_(O.mobilevit_v1_shapes(fx["mode"]), fx["seed"]), strict=True)
+    model = model.cuda().eval()
+    x1 = O.seeded_input((1, 3, 256, 256), fx["eval_x_seed"]).cuda()
+    with torch.no_grad():
+        ev = model(x1)
+        Pa = O.clone_params(O.seeded_fill_(O.mobilevit_v1_shapes(fx["mode"]), fx["seed"]), requires_grad=False, device="cuda")
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            eva = O.mobilevit_v1_forward(Pa, x1, mode=fx["mode"], training=False)
+    e, ea = rel_l2(ev, fx["eval_logits"]), rel_l2(eva, fx["eval_logits"])
+    print(f"[mobilevit v1 xxs] eval logits rel-L2 vs the reference: ours {e:.4g}, torch-autocast {ea:.4g}")
+    assert e <= max(3e-2, 1.5 * ea)
+    assert int(ev.argmax()) == int(fx["eval_logits"].argmax()) or e <= 1e-2
+    model.train()
+    x = O.seeded_input((4, 3, 128, 128), fx["x_seed"]).cuda()
+    logits = model(x)
+    loss = F.cross_entropy(logits.float(), fx["labels"].cuda(), label_smoothing=0.1)
+    loss.backward()
+    Pt = O.clone_params(O.seeded_fill_(O.mobilevit_v1_shapes(fx["mode"]), fx["seed"]), device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lt = O.mobilevit_v1_forward(Pt, x, mode=fx["mode"], training=True)
+        F.cross_entropy(lt, fx["labels"].cuda(), label_smoothing=0.1).backward()
+    et, eta = rel_l2(logits, fx["logits"]), rel_l2(lt, fx["logits"])
+    print(f"[mobilevit v1 xxs] train logits rel-L2 vs the reference: ours {et:.4g}, torch-autocast {eta:.4g}; loss {float(loss):.5f} vs {float(fx['loss']):.5f}")
+    assert et <= max(5e-2, 1.5 * eta)
+    named = dict(model.named_parameters())
+    total = sum(n * n for n in fx["grad_norms"].values()) ** 0.5
+    bad = []
+    for k, g in fx["grads"].items():
+        if fx["grad_norms"][k] < 1e-3 * total:
+            continue
+        eo, eau = rel_l2(named[k].grad, g), rel_l2(Pt[k].grad, g)
+        if eo > max(0.1, 2.0 * eau):
+            bad.append((k, eo, eau))
+    assert not bad, bad[:8]
