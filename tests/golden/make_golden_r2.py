@@ -115,7 +115,7 @@ def main():
                   grad_norms={k: float(g.norm()) for k, g in grads.items()},
                   grads={k: g.clone() for k, g in grads.items() if g.numel() <= 20000})
     torch.save(vit_fx, os.path.join(HERE, "vit_small_fp32.pt"))
-    # ---- MobileViT v1 XXS (BASELINE.json configs[0]): eval forward at 1x3x256x256 + a train-mode fwd/bwd (dropouts 0) at 4x3x128x128
+    # ---- MobileViT v1 XXS (BASELINE.json configs[0]): eval forward at 1x3x256x256 + a train-mode fwd/bwd (dropouts 0) at 4x3x192x192
     opts = make_opts(1.0)
     for k, v in {"model.classification.name": "mobilevit", "model.classification.mit.mode": "xx_small", "model.classification.mit.dropout": 0.0,
                  "model.classification.mit.attn_dropout": 0.0, "model.classification.mit.ffn_dropout": 0.0,
@@ -129,7 +129,7 @@ def main():
     with torch.no_grad():
         eval_logits = model(x1).clone()
     model.train()
-    x = O.seeded_input((4, 3, 128, 128), 362)
+    x = O.seeded_input((4, 3, 192, 192), 362)  # (128x128 would give N == d = 64 at layer 3: the reference LayerNorm then takes its channel-first branch)
     labels = torch.tensor([5, 701, 33, 999])
     logits = model(x)
     loss = F.cross_entropy(logits, labels, label_smoothing=0.1)

@@ -243,7 +243,7 @@ def test_mobilevit_v1_xxs_fixture(golden_dir):
     with torch.no_grad():
         ev = O.mobilevit_v1_forward(P, O.seeded_input((1, 3, 256, 256), fx["eval_x_seed"]), mode=fx["mode"], training=False)
     assert float((ev - fx["eval_logits"]).norm() / fx["eval_logits"].norm()) <= 2e-5
-    logits = O.mobilevit_v1_forward(P, O.seeded_input((4, 3, 128, 128), fx["x_seed"]), mode=fx["mode"], training=True)
+    logits = O.mobilevit_v1_forward(P, O.seeded_input((4, 3, 192, 192), fx["x_seed"]), mode=fx["mode"], training=True)
     loss = F.cross_entropy(logits, fx["labels"], label_smoothing=0.1)
     loss.backward()
     assert float((logits - fx["logits"]).norm() / fx["logits"].norm()) <= 5e-5

@@ -199,7 +199,7 @@ def test_mobilevit_v1_xxs_against_reference_fixture(pkg, golden_dir):
     assert e <= max(3e-2, 1.5 * ea)
     assert int(ev.argmax()) == int(fx["eval_logits"].argmax()) or e <= 1e-2
     model.train()
-    x = O.seeded_input((4, 3, 128, 128), fx["x_seed"]).cuda()
+    x = O.seeded_input((4, 3, 192, 192), fx["x_seed"]).cuda()
     logits = model(x)
     loss = F.cross_entropy(logits.float(), fx["labels"].cuda(), label_smoothing=0.1)
     loss.backward()
