@@ -156,6 +156,13 @@ CVB_API int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream);
  * ------------------------------------------------------------------------------------------------------------- */
 CVB_API int cvb_stem_im2col(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A,
                     cvb_stream_t stream);
+/* The same gather with the reference's batch-mixing input transforms folded in (engine/training_engine.py:236-238,
+ * data/transforms/image_torch.py:99-137 RandomMixup, :290-342 RandomCutmix).  mix: DEVICE float[6] = {mode, lambda, x1, y1, x2, y2} or NULL;
+ * every sample pairs with its predecessor in the batch (image.roll(1, 0)): mode 1 (mixup) x = lambda*x + (1-lambda)*x_prev in fp32;
+ * mode 2 (cutmix) rows [y1,y2) x columns [x1,x2) come from x_prev; mode 0 = off.  The matching target distribution
+ * lambda*onehot(y[b]) + (1-lambda)*onehot(y[b-1]) is what cvb_ce_fwd / cvb_ce_bwd use when given the same `mix`. */
+CVB_API int cvb_stem_im2col_mix(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A, const float* mix,
+                        cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * BatchNorm2d bookkeeping (cvnets/layers/normalization/batch_norm.py:14-49; math SURVEY App. A1)
@@ -279,9 +286,9 @@ CVB_API int cvb_adamw_step(float* params, const float* grads, float* exp_avg, fl
  * GradScaler's loss scale (engine/training_engine.py:287) multiplies here instead of in a separate kernel.
  * ------------------------------------------------------------------------------------------------------------- */
 CVB_API int cvb_ce_fwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, float* lse,
-               float* loss, float* n_valid, cvb_stream_t stream);
+               float* loss, float* n_valid, const float* mix /* see cvb_stem_im2col_mix; NULL = plain targets */, cvb_stream_t stream);
 CVB_API int cvb_ce_bwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, const float* lse,
-               const float* n_valid, const float* grad_out, const float* grad_scale, void* dlogits, int ldd, cvb_stream_t stream);
+               const float* n_valid, const float* grad_out, const float* grad_scale, void* dlogits, int ldd, const float* mix, cvb_stream_t stream);
 
 /* Batched fp64 -> fp32 scatter: dst[i] = (float)src[i] for every descriptor (one launch per module backward: the fp64 statistics
  * accumulators that ARE gradients -- GroupNorm dgamma/dbeta, bias gradients -- go straight into the flat gradient buffer). */

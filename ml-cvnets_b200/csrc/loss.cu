@@ -13,10 +13,13 @@ constexpr int LNT = 1024;
 // one warp per row: max, sum of exp, sum of logits (for the smoothing term), the target logit
 __global__ void __launch_bounds__(LNT) ce_fwd_kernel(const bf16* __restrict__ logits, int ld, int B, int C, const int64_t* __restrict__ target,
                                                      int ignore_index, float smoothing, float* __restrict__ lse, float* __restrict__ loss_out,
-                                                     float* __restrict__ nvalid_out) {
+                                                     float* __restrict__ nvalid_out, const float* __restrict__ mix) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_loss[LNT / 32], s_cnt[LNT / 32];
+  // batch mixing (RandomMixup / RandomCutmix targets, image_torch.py:119-137): target distribution = lam*onehot(y[r]) + (1-lam)*onehot(y[r-1])
+  const bool mixing = mix != nullptr && mix[0] != 0.f;
+  const float lam = mixing ? mix[1] : 1.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float loss = 0.f, cnt = 0.f;
   for (int r = warp; r < B; r += LNT / 32) {
@@ -38,7 +41,11 @@ __global__ void __launch_bounds__(LNT) ce_fwd_kernel(const bf16* __restrict__ lo
       const int64_t t = target[r];
       if (t != (int64_t)ignore_index && t >= 0 && t < C) {
         // label smoothing (torch): (1-eps) * nll(target) + eps/C * sum_c nll(c)
-        const float nll_t = l - __bfloat162float(row[t]);
+        float nll_t = l - __bfloat162float(row[t]);
+        if (mixing) {
+          const int64_t t2 = target[r == 0 ? B - 1 : r - 1];
+          if (t2 >= 0 && t2 < C) nll_t = lam * nll_t + (1.0f - lam) * (l - __bfloat162float(row[t2]));
+        }
         const float nll_all = (float)C * l - sl;
         loss += (1.0f - smoothing) * nll_t + smoothing / (float)C * nll_all;
         cnt += 1.0f;
@@ -58,11 +65,14 @@ __global__ void __launch_bounds__(LNT) ce_fwd_kernel(const bf16* __restrict__ lo
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const bf16* __restrict__ logits, int ld, int B, int C, const int64_t* __restrict__ target,
                                                      int ignore_index, float smoothing, const float* __restrict__ lse,
                                                      const float* __restrict__ nvalid, const float* __restrict__ gout, const float* __restrict__ gscale,
-                                                     bf16* __restrict__ dlogits, int ldd) {
+                                                     bf16* __restrict__ dlogits, int ldd, const float* __restrict__ mix) {
   pdl_wait();
   pdl_trigger();
   const int r = blockIdx.x;
   const int64_t t = target[r];
+  const bool mixing = mix != nullptr && mix[0] != 0.f;
+  const float lam = mixing ? mix[1] : 1.f;
+  const int64_t t2 = mixing ? target[r == 0 ? B - 1 : r - 1] : (int64_t)-1;
   const bool valid = (t != (int64_t)ignore_index && t >= 0 && t < C);
   float g = (gout ? gout[0] : 1.0f) * (gscale ? gscale[0] : 1.0f);
   const float nv = nvalid[0];
@@ -75,7 +85,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const bf16* __restrict__ lo
     float d = 0.f;
     if (c < C) {
       const float p = __expf(__bfloat162float(row[c]) - l);
-      d = g * (p - off - ((int64_t)c == t ? (1.0f - smoothing) : 0.f));
+      d = g * (p - off - (1.0f - smoothing) * (((int64_t)c == t ? lam : 0.f) + ((int64_t)c == t2 ? 1.0f - lam : 0.f)));
     }
     drow[c] = __float2bfloat16_rn(d);
   }
@@ -98,19 +108,20 @@ __global__ void __launch_bounds__(256) cast_f64_f32_kernel(const CastDesc* __res
 }  // namespace
 
 extern "C" int cvb_ce_fwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, float* lse,
-                          float* loss, float* n_valid, cvb_stream_t stream) {
+                          float* loss, float* n_valid, const float* mix, cvb_stream_t stream) {
   CVB_CHECK(logits && target && lse && loss && n_valid && B > 0 && C > 0 && ld >= C, "cvb_ce_fwd: bad arguments");
   CVB_CUDA(cvb_launch(ce_fwd_kernel, 1, LNT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(logits), ld, B, C, target, ignore_index,
-                      label_smoothing, lse, loss, n_valid));
+                      label_smoothing, lse, loss, n_valid, mix));
   CVB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int cvb_ce_bwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, const float* lse,
-                          const float* n_valid, const float* grad_out, const float* grad_scale, void* dlogits, int ldd, cvb_stream_t stream) {
+                          const float* n_valid, const float* grad_out, const float* grad_scale, void* dlogits, int ldd, const float* mix,
+                          cvb_stream_t stream) {
   CVB_CHECK(logits && target && lse && n_valid && dlogits && B > 0 && C > 0 && ld >= C && ldd >= C, "cvb_ce_bwd: bad arguments");
   CVB_CUDA(cvb_launch(ce_bwd_kernel, B, 256, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(logits), ld, B, C, target, ignore_index,
-                      label_smoothing, lse, n_valid, grad_out, grad_scale, static_cast<bf16*>(dlogits), ldd));
+                      label_smoothing, lse, n_valid, grad_out, grad_scale, static_cast<bf16*>(dlogits), ldd, mix));
   CVB_LAUNCH_CHECK();
   return 0;
 }

@@ -627,11 +627,18 @@ __global__ void __launch_bounds__(NT) pool_bwd_kernel(const bf16* __restrict__ D
 
 // ------------------------------------------------------------------------------------------------ stem im2col
 // A[(b,oh,ow), ci*9+u*3+v] = bf16(X[b,ci,2oh+u-1,2ow+v-1]) (zero padded), columns 27..31 = 0
+// mix (device, 6 floats, may be NULL): {mode, lambda, x1, y1, x2, y2} -- the batch-mixing transforms of the reference's input edge
+// (data/transforms/image_torch.py:99-137 RandomMixup, :290-342 RandomCutmix; applied at engine/training_engine.py:236-238) folded into the
+// gather: every sample is paired with its predecessor in the batch (image.roll(1, 0)); mode 1: x = lambda*x + (1-lambda)*x_prev (fp32, as the
+// reference), mode 2: the box [y1,y2) x [x1,x2) is pasted from x_prev.  No extra pass over the images, no mixed copy in HBM.
 __global__ void __launch_bounds__(NT) stem_im2col_kernel(const float* __restrict__ X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H,
-                                                         int W, bf16* __restrict__ A) {
+                                                         int W, bf16* __restrict__ A, const float* __restrict__ mix) {
   pdl_wait();
   pdl_trigger();
   const int Ho = H / 2, Wo = W / 2;
+  const int mode = mix ? (int)mix[0] : 0;
+  const float lam = mix ? mix[1] : 1.f;
+  const int bx1 = mix ? (int)mix[2] : 0, by1 = mix ? (int)mix[3] : 0, bx2 = mix ? (int)mix[4] : 0, by2 = mix ? (int)mix[5] : 0;
   const int64_t total = (int64_t)B * Ho * Wo * 4;  // 4 chunks of 8 columns per output pixel
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
     const int ch = (int)(i & 3);
@@ -647,7 +654,15 @@ __global__ void __launch_bounds__(NT) stem_im2col_kernel(const float* __restrict
       if (col < 27) {
         const int ci = col / 9, u = (col % 9) / 3, vv = col % 3;
         const int h = 2 * oh + u - 1, w = 2 * ow + vv - 1;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(X + b * sxn + ci * sxc + h * sxh + w * sxw);
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          const int64_t off = ci * sxc + h * sxh + w * sxw;
+          v = __ldg(X + b * sxn + off);
+          if (mode != 0) {
+            const int bp = b == 0 ? B - 1 : b - 1;
+            if (mode == 1) v = fmaf(lam, v, (1.0f - lam) * __ldg(X + bp * sxn + off));
+            else if (h >= by1 && h < by2 && w >= bx1 && w < bx2) v = __ldg(X + bp * sxn + off);
+          }
+        }
       }
       f[j] = v;
     }
@@ -907,12 +922,18 @@ extern "C" int cvb_col_sum(const void* X, int x_fp32, int ld, int64_t M, int N, 
   return 0;
 }
 
-extern "C" int cvb_stem_im2col(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A, cvb_stream_t stream) {
+extern "C" int cvb_stem_im2col_mix(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A, const float* mix,
+                                   cvb_stream_t stream) {
   CVB_CHECK(X && A && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "cvb_stem_im2col: bad arguments (H, W must be even)");
   int64_t total = (int64_t)B * (H / 2) * (W / 2) * 4;
-  CVB_CUDA(cvb_launch(stem_im2col_kernel, grid_for(total), NT, 0, static_cast<cudaStream_t>(stream), X, sxn, sxc, sxh, sxw, B, H, W, static_cast<bf16*>(A)));
+  CVB_CUDA(cvb_launch(stem_im2col_kernel, grid_for(total), NT, 0, static_cast<cudaStream_t>(stream), X, sxn, sxc, sxh, sxw, B, H, W, static_cast<bf16*>(A),
+                      mix));
   CVB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int cvb_stem_im2col(const float* X, int64_t sxn, int64_t sxc, int64_t sxh, int64_t sxw, int B, int H, int W, void* A, cvb_stream_t stream) {
+  return cvb_stem_im2col_mix(X, sxn, sxc, sxh, sxw, B, H, W, A, nullptr, stream);
 }
 
 extern "C" int cvb_prep_weights(const cvb_prep_desc* descs_device, int n_desc, int max_elems, cvb_stream_t stream) {

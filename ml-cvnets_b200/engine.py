@@ -61,7 +61,9 @@ class TrainStep:
             if self.opt.ema is not None:
                 self.opt.ema.copy_(self.opt.flat_p)
             self.ws.broadcast_buffers()
-        self.loss_cfg = SimpleNamespace(label_smoothing=float(label_smoothing), ignore_index=int(ignore_index), scale=self.opt.loss_scale())
+        self.loss_cfg = SimpleNamespace(label_smoothing=float(label_smoothing), ignore_index=int(ignore_index), scale=self.opt.loss_scale(),
+                                        mix=self.ws.mix)
+        self._mix_host = torch.tensor([0.0, 1.0, 0.0, 0.0, 0.0, 0.0]).pin_memory()
         self._one = torch.ones((), device=self.ws.device, dtype=torch.float32)
         self._graph = None
         self._static = None
@@ -70,6 +72,18 @@ class TrainStep:
     # ---- scheduler / checkpoint hooks
     def set_lr(self, lr: float) -> None:
         self.opt.set_lr(lr)
+
+    def set_mix(self, kind: Optional[str] = None, lam: float = 1.0, box=(0, 0, 0, 0)) -> None:
+        """Batch mixing for the NEXT steps (reference: apply_mixing_transforms, engine/training_engine.py:236-238).
+        kind None = off; "mixup": x = lam*x + (1-lam)*x.roll(1, 0); "cutmix": the box (x1, y1, x2, y2) is pasted from x.roll(1, 0) and
+        ``lam`` must be 1 - box_area / image_area (image_torch.py:338).  Targets become lam*onehot(y) + (1-lam)*onehot(y.roll(1)).  Both
+        are applied inside the stem's gather kernel and the loss kernels: no mixed image or soft-target tensor exists.  The values live in
+        a device buffer, so a captured step follows per-iteration changes."""
+        mode = {None: 0.0, "mixup": 1.0, "cutmix": 2.0}[kind]
+        h = self._mix_host
+        h[0], h[1] = mode, float(lam)
+        h[2], h[3], h[4], h[5] = [float(v) for v in box]
+        self.ws.mix.copy_(h, non_blocking=True)
 
     def state_dict(self):
         return self.opt.state_dict()
@@ -135,3 +149,31 @@ class TrainStep:
     @property
     def static_inputs(self):
         return None if self._static is None else self._static[:2]
+
+
+class MixingSampler:
+    """Host-side sampling of the mixing parameters exactly as the reference's transforms draw them (data/transforms/image_torch.py:124-137,
+    :315-338; selection between the two as apply_mixing_transforms :446-470): lambda ~ Beta(alpha, alpha) via torch._sample_dirichlet, the
+    cutmix box from two randint draws.  ``sample(H, W)`` returns the arguments of ``TrainStep.set_mix``."""
+
+    def __init__(self, mixup_alpha: Optional[float] = 0.2, mixup_p: float = 1.0, cutmix_alpha: Optional[float] = 1.0, cutmix_p: float = 1.0):
+        self.mixup = (float(mixup_alpha), float(mixup_p)) if mixup_alpha else None
+        self.cutmix = (float(cutmix_alpha), float(cutmix_p)) if cutmix_alpha else None
+
+    def sample(self, H: int, W: int):
+        import math
+        import random
+        choices = [c for c in (("mixup",) + self.mixup if self.mixup else None, ("cutmix",) + self.cutmix if self.cutmix else None) if c]
+        if not choices:
+            return None, 1.0, (0, 0, 0, 0)
+        kind, alpha, p = random.choice(choices)
+        if torch.rand(1).item() >= p:
+            return None, 1.0, (0, 0, 0, 0)
+        lam = float(torch._sample_dirichlet(torch.tensor([alpha, alpha]))[0])
+        if kind == "mixup":
+            return "mixup", lam, (0, 0, 0, 0)
+        r_x, r_y = int(torch.randint(W, (1,))), int(torch.randint(H, (1,)))
+        r = 0.5 * math.sqrt(1.0 - lam)
+        rw, rh = int(r * W), int(r * H)
+        x1, y1, x2, y2 = max(r_x - rw, 0), max(r_y - rh, 0), min(r_x + rw, W), min(r_y + rh, H)
+        return "cutmix", float(1.0 - (x2 - x1) * (y2 - y1) / (W * H)), (x1, y1, x2, y2)

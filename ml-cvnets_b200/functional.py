@@ -167,7 +167,8 @@ class StemFn(torch.autograd.Function):
         Ho, Wo = H // 2, W // 2
         M = B * Ho * Wo
         xin = x if x.dtype == torch.float32 else x.float()
-        A0 = ops.stem_im2col(xin)
+        ws = getattr(cfg, "ws", None)
+        A0 = ops.stem_im2col(xin, mix=ws.mix if (ws is not None and ws.active) else None)  # batch mixing rides in the gather (TrainStep.set_mix)
         Ws = cfg.prep.get(cfg.i_w)
         st = _fwd_arena(cfg, x.device, 2 * C0 + 8).f64(2, C0)
         y = ops.pw_gemm(A0, Ws, C0, col_stats=st if cfg.bn.batch_stats else None)
@@ -489,7 +490,7 @@ class CrossEntropyFn(torch.autograd.Function):
         if target.dtype != torch.int64 or target.dim() != 1 or target.shape[0] != B:
             raise ValueError("cross_entropy: target must be an int64 tensor of shape [batch] (class indices)")
         target = target.contiguous()
-        loss, lse, nv = ops.ce_fwd(lg, C, target, cfg.ignore_index, cfg.label_smoothing)
+        loss, lse, nv = ops.ce_fwd(lg, C, target, cfg.ignore_index, cfg.label_smoothing, mix=getattr(cfg, "mix", None))
         ctx.cfg, ctx.saved, ctx.C = cfg, (lg, target, lse, nv), C
         return loss.view(())
 
@@ -499,7 +500,7 @@ class CrossEntropyFn(torch.autograd.Function):
         cfg, C = ctx.cfg, ctx.C
         g = gout if (gout.dtype == torch.float32 and gout.is_contiguous()) else gout.float().contiguous()
         ldd = lg.stride(0) if lg.stride(0) >= C else (C + 7) // 8 * 8
-        d = ops.ce_bwd(lg, C, target, cfg.ignore_index, cfg.label_smoothing, lse, nv, g, getattr(cfg, "scale", None), ldd)
+        d = ops.ce_bwd(lg, C, target, cfg.ignore_index, cfg.label_smoothing, lse, nv, g, getattr(cfg, "scale", None), ldd, mix=getattr(cfg, "mix", None))
         return d[:, :C], None, None
 
 

@@ -292,14 +292,14 @@ def vit_tokens_bwd(dout: Tensor, dpos: Tensor, dcls: Optional[Tensor], B: int, N
     return dpatch
 
 
-def stem_im2col(x: Tensor) -> Tensor:
-    """fp32 image [B,3,H,W] (any strides) -> bf16 patch matrix [B*(H/2)*(W/2), 32]."""
+def stem_im2col(x: Tensor, mix: Optional[Tensor] = None) -> Tensor:
+    """fp32 image [B,3,H,W] (any strides) -> bf16 patch matrix [B*(H/2)*(W/2), 32]; ``mix`` (device float[6]) folds mixup / cutmix in."""
     lib = _lib()
     B, C, H, W = x.shape
     assert C == 3 and x.dtype == torch.float32
     A = torch.empty((B * (H // 2) * (W // 2), 32), device=x.device, dtype=torch.bfloat16)
     sn, sc, sh, sw = x.stride()
-    L.check(lib.cvb_stem_im2col(x.data_ptr(), sn, sc, sh, sw, B, H, W, A.data_ptr(), _stream()), "cvb_stem_im2col")
+    L.check(lib.cvb_stem_im2col_mix(x.data_ptr(), sn, sc, sh, sw, B, H, W, A.data_ptr(), _p(mix), _stream()), "cvb_stem_im2col")
     _count()
     return A
 
@@ -535,23 +535,23 @@ def col_sum(X: Tensor, N: Optional[int] = None, out: Optional[Tensor] = None) ->
     return out
 
 
-def ce_fwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float):
+def ce_fwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float, mix: Optional[Tensor] = None):
     """logits: bf16 [B, ld] (C valid columns).  Returns (loss fp32 [1], lse fp32 [B], n_valid fp32 [1])."""
     B = logits.shape[0]
     lse = torch.empty(B, device=logits.device, dtype=torch.float32)
     out = torch.empty(2, device=logits.device, dtype=torch.float32)
     L.check(_lib().cvb_ce_fwd(logits.data_ptr(), logits.stride(0), B, C, target.data_ptr(), int(ignore_index), float(smoothing), lse.data_ptr(),
-                              out[0:1].data_ptr(), out[1:2].data_ptr(), _stream()), "cvb_ce_fwd")
+                              out[0:1].data_ptr(), out[1:2].data_ptr(), _p(mix), _stream()), "cvb_ce_fwd")
     _count()
     return out[0:1], lse, out[1:2]
 
 
 def ce_bwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float, lse: Tensor, n_valid: Tensor, gout: Optional[Tensor],
-           gscale: Optional[Tensor], ldd: int) -> Tensor:
+           gscale: Optional[Tensor], ldd: int, mix: Optional[Tensor] = None) -> Tensor:
     B = logits.shape[0]
     d = torch.empty((B, ldd), device=logits.device, dtype=torch.bfloat16)
     L.check(_lib().cvb_ce_bwd(logits.data_ptr(), logits.stride(0), B, C, target.data_ptr(), int(ignore_index), float(smoothing), lse.data_ptr(),
-                              n_valid.data_ptr(), _p(gout), _p(gscale), d.data_ptr(), ldd, _stream()), "cvb_ce_bwd")
+                              n_valid.data_ptr(), _p(gout), _p(gscale), d.data_ptr(), ldd, _p(mix), _stream()), "cvb_ce_bwd")
     _count()
     return d
 

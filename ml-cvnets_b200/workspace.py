@@ -84,6 +84,10 @@ class StepWorkspace:
             self._gviews[id(p)] = v
             p.grad = v
         self.active = False           # True only inside TrainStep's forward/backward: modules then write gradients in place
+        # batch mixing {mode, lambda, x1, y1, x2, y2} read by the stem gather and the loss (mode 0 = off); device-resident so that a captured
+        # step follows per-iteration changes (engine.TrainStep.set_mix)
+        self.mix = torch.zeros(6, device=dev, dtype=torch.float32)
+        self.mix[1] = 1.0
         self._plan: Dict[tuple, Tuple[int, int, int, int]] = {}
         self._requests: Dict[tuple, Tuple[int, int]] = {}
         self._used = set()

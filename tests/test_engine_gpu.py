@@ -202,3 +202,58 @@ def test_eval_after_train_step_sees_new_weights(pkg):
         c = fresh(x).float()
     assert rel_l2(b, c) <= 1e-3, "eval forward used stale bf16 weight copies"
     assert rel_l2(a, b) > 1e-2, "weights did not move?"
+
+
+@pytest.mark.parametrize("kind", ["mixup", "cutmix"])
+def test_batch_mixing_fused_into_stem_gather_and_loss(pkg, kind):
+    """RandomMixup / RandomCutmix (data/transforms/image_torch.py:99-137, :290-342) applied inside the stem's gather and
+    the loss kernels == the reference's formulation (mixed images + soft targets) computed with torch."""
+    from ml_cvnets_b200 import ops
+    B, H, W, C = 6, 32, 48, 1000
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(B, 3, H, W, device="cuda", generator=g)
+    y = torch.randint(0, C, (B,), device="cuda", generator=g)
+    lam, box = (0.3, (0, 0, 0, 0)) if kind == "mixup" else (1.0 - (30 - 10) * (20 - 4) / (W * H), (10, 4, 30, 20))
+    mix = torch.tensor([1.0 if kind == "mixup" else 2.0, lam, *box], device="cuda", dtype=torch.float32)
+    rolled = x.roll(1, 0)
+    if kind == "mixup":
+        xm = x * lam + rolled * (1.0 - lam)
+    else:
+        xm = x.clone()
+        x1, y1, x2, y2 = box
+        xm[:, :, y1:y2, x1:x2] = rolled[:, :, y1:y2, x1:x2]
+    a, b = ops.stem_im2col(x, mix=mix).float(), ops.stem_im2col(xm).float()
+    assert float((a - b).abs().max()) <= 2 ** -7 * float(b.abs().max()) and rel_l2(a, b) <= 1e-3  # at most a bf16 ulp (fma vs mul+add)
+    logits = (3 * torch.randn(B, C, device="cuda", generator=g)).bfloat16()
+    soft = F.one_hot(y, C).float() * lam + F.one_hot(y.roll(1, 0), C).float() * (1.0 - lam)
+    ref_in = logits.float().requires_grad_(True)
+    ref = F.cross_entropy(ref_in, soft, label_smoothing=0.1)
+    ref.backward()
+    ours_in = logits.clone().requires_grad_(True)
+    from types import SimpleNamespace
+    loss = pkg.cross_entropy(ours_in, y, _cfg=SimpleNamespace(label_smoothing=0.1, ignore_index=-1, scale=None, mix=mix))
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref)), (float(loss), float(ref))
+    assert rel_l2(ours_in.grad, ref_in.grad) <= 4e-3
+    # end to end through TrainStep (eval-mode BatchNorm keeps the comparison free of batch-statistics amplification)
+    model = _small_model(pkg).eval()
+    ts = pkg.TrainStep(model, lr=0.0, weight_decay=0.0)
+    xs, ys = O.seeded_input((8, 3, 64, 64), 77).cuda(), torch.arange(8, device="cuda") * 7
+    if kind == "cutmix":
+        lam2, box2 = 1.0 - (40 - 8) * (50 - 20) / (64 * 64), (8, 20, 40, 50)
+    else:
+        lam2, box2 = 0.65, (0, 0, 0, 0)
+    ts.set_mix(kind, lam2, box2)
+    l_mixed = float(ts.step(xs, ys))
+    rolled = xs.roll(1, 0)
+    xm = xs * lam2 + rolled * (1 - lam2) if kind == "mixup" else xs.clone()
+    if kind == "cutmix":
+        xm[:, :, box2[1]:box2[3], box2[0]:box2[2]] = rolled[:, :, box2[1]:box2[3], box2[0]:box2[2]]
+    with torch.no_grad():
+        lg = model(xm).float()
+    softs = F.one_hot(ys, 1000).float() * lam2 + F.one_hot(ys.roll(1, 0), 1000).float() * (1 - lam2)
+    l_ref = float(F.cross_entropy(lg, softs, label_smoothing=0.1))
+    ts.set_mix(None)
+    l_plain = float(ts.step(xs, ys))
+    assert abs(l_mixed - l_ref) <= 3e-3 * abs(l_ref), (l_mixed, l_ref)
+    assert abs(l_plain - l_ref) > 1e-4  # the mixing really changed the step
