@@ -75,8 +75,15 @@ def _worker(rank, world, port, q):
         bdrift = max(float((g - gb[0]).abs().max()) for g in gb)
         torch.cuda.synchronize()
         q.put((rank, errs, n_fire, drift, bdrift))
-    finally:
-        dist.destroy_process_group()
+        q.close()
+        q.join_thread()
+    except BaseException as e:  # the parent must never wait for a result that will not come
+        q.put((rank, repr(e)[:500], -1, -1.0, -1.0))
+        q.close()
+        q.join_thread()
+    # a captured CUDA graph that contains NCCL kernels is still alive here; tearing the process group down under it can block, and the
+    # result is already delivered: leave without the collective shutdown
+    os._exit(0)
 
 
 def test_allreduced_gradients_equal_single_gpu_gradients_of_the_concatenated_batch():
@@ -89,11 +96,13 @@ def test_allreduced_gradients_equal_single_gpu_gradients_of_the_concatenated_bat
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
+    res = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
     for rank, errs, n_fire, drift, bdrift in res:
+        assert not isinstance(errs, str), f"rank {rank} failed: {errs}"
         print(f"rank {rank}: rel-L2 of all-reduced gradients vs single-GPU concatenated-batch gradients per step {errs}; buckets {n_fire}; "
               f"weight drift across ranks {drift:.3g}; buffer drift {bdrift:.3g}")
         assert all(e <= 2e-3 for e in errs), errs  # atomics-order noise of the bf16/fp32 kernels, same on one GPU run twice
