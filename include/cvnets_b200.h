@@ -284,11 +284,16 @@ CVB_API int cvb_adamw_step(float* params, const float* grads, float* exp_avg, fl
  * fwd: lse fp32[B] (saved), loss fp32[1], n_valid fp32[1].   bwd: dlogits bf16 [B, ldd] (columns >= C zeroed) =
  * grad_out * grad_scale * (softmax - smoothed one-hot) / n_valid; grad_out / grad_scale are DEVICE scalars or NULL (= 1): the
  * GradScaler's loss scale (engine/training_engine.py:287) multiplies here instead of in a separate kernel.
+ * logit_scale (DEVICE scalar or NULL): CLIP's learnable temperature (cvnets/models/multi_modal_img_text/clip.py: logit_scale.exp().clamp(0, 100);
+ * loss_fn/multi_modal_img_text/contrastive_loss_clip.py:74-79): the rows are RAW similarities and the loss is taken of s * raw; bwd returns the
+ * gradient w.r.t. the raw similarities and accumulates d loss / d logit_scale into dlogit_scale (fp32, atomically; 0 where the clamp is active).
  * ------------------------------------------------------------------------------------------------------------- */
 CVB_API int cvb_ce_fwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, float* lse,
-               float* loss, float* n_valid, const float* mix /* see cvb_stem_im2col_mix; NULL = plain targets */, cvb_stream_t stream);
+               float* loss, float* n_valid, const float* mix /* see cvb_stem_im2col_mix; NULL = plain targets */, const float* logit_scale,
+               cvb_stream_t stream);
 CVB_API int cvb_ce_bwd(const void* logits, int ld, int B, int C, const int64_t* target, int ignore_index, float label_smoothing, const float* lse,
-               const float* n_valid, const float* grad_out, const float* grad_scale, void* dlogits, int ldd, const float* mix, cvb_stream_t stream);
+               const float* n_valid, const float* grad_out, const float* grad_scale, void* dlogits, int ldd, const float* mix,
+               const float* logit_scale, float* dlogit_scale, cvb_stream_t stream);
 
 /* Batched fp64 -> fp32 scatter: dst[i] = (float)src[i] for every descriptor (one launch per module backward: the fp64 statistics
  * accumulators that ARE gradients -- GroupNorm dgamma/dbeta, bias gradients -- go straight into the flat gradient buffer). */
@@ -296,6 +301,22 @@ typedef struct {
   const double* src; float* dst; int n; int pad;
 } cvb_cast_desc;
 CVB_API int cvb_cast_f64_f32(const cvb_cast_desc* descs_device, int n_desc, int max_n, cvb_stream_t stream);
+/* ---------------------------------------------------------------------------------------------------------------
+ * CLIP text tower edges and feature normalisation (BASELINE.json configs[4]; csrc/clip.cu)
+ *   embedding: out[b,s,:] = bf16(table[tokens[b,s],:] + pos[s,:])  (cvnets/text_encoders/transformer.py:328-341); bwd: dtable[token] += dout
+ *              (fp32 atomics), dpos[s] += sum_b dout[b,s]
+ *   eot gather: out[b,:] = X[b, argmax_s tokens[b,s], :] (transformer.py:413-421); idx[b] saved; bwd scatters into a zero-filled dX
+ *   l2norm: Y = X / max(||X||_2, eps) per row (F.normalize, transformer.py:423-425); inv_norm saved; bwd dx = inv*(dy - y (y.dy))
+ *   transpose / add: Y[c,r] = X[r,c];  OUT = bf16(A + B) (A bf16 or NULL, B fp32) -- glue of the contrastive loss's gradient assembly
+ * ------------------------------------------------------------------------------------------------------------- */
+CVB_API int cvb_embedding_fwd(const int64_t* tokens, const float* table, const float* pos, void* out, int B, int S, int C, int V, cvb_stream_t stream);
+CVB_API int cvb_embedding_bwd(const void* dout, const int64_t* tokens, float* dtable, float* dpos, int B, int S, int C, int V, cvb_stream_t stream);
+CVB_API int cvb_eot_gather_fwd(const void* X, const int64_t* tokens, int B, int S, int C, void* out, int* idx, cvb_stream_t stream);
+CVB_API int cvb_eot_gather_bwd(const void* dout, const int* idx, int B, int S, int C, void* dX, cvb_stream_t stream);
+CVB_API int cvb_l2norm_fwd(const void* X, void* Y, float* inv_norm, int M, int C, float eps, cvb_stream_t stream);
+CVB_API int cvb_l2norm_bwd(const void* DY, const void* Y, const float* inv_norm, void* DX, int M, int C, cvb_stream_t stream);
+CVB_API int cvb_transpose_bf16(const void* X, void* Y, int R, int C, cvb_stream_t stream);
+CVB_API int cvb_add_bf16_f32(const void* A, const float* B, void* OUT, int64_t n, cvb_stream_t stream);
 /* cudaMemsetAsync(ptr, 0, bytes): the step's ONE workspace clear (a memset node under graph capture, not a kernel) */
 CVB_API int cvb_memset_zero(void* ptr, int64_t bytes, cvb_stream_t stream);
 

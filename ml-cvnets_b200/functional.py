@@ -920,6 +920,150 @@ class VitTokensFn(torch.autograd.Function):
 
 
 # ==================================================================================================================
+# CLIP edges (BASELINE.json configs[4]): text embedding, end-of-text gather, projection, feature normalisation, contrastive loss
+# ==================================================================================================================
+class EmbeddingFn(torch.autograd.Function):
+    """token embedding + learnable positional embedding (cvnets/text_encoders/transformer.py:328-341).  params = (table [V, C], pos [1,1,S,C] | None)."""
+
+    @staticmethod
+    def forward(ctx, tokens, cfg, table, pos):
+        out = ops.embedding_fwd(tokens, table, pos)
+        ctx.cfg, ctx.plist, ctx.tokens, ctx.shape, ctx.has_pos = cfg, cfg.plist, tokens, tuple(table.shape), pos is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        V, C = ctx.shape
+        B, S = ctx.tokens.shape
+        g = g if (g.dtype == BF16 and g.is_contiguous()) else g.to(BF16).contiguous()
+        D = _Dst(ctx.cfg, ctx.plist, g.device, V * C + S * C + 64, 8, True)
+        dtable = D.mat(0, V, C)
+        dpos = D.mat(1, S, C) if ctx.has_pos else None
+        ops.embedding_bwd(g, ctx.tokens, dtable, dpos)
+        grads = D.finish()
+        return None, None, grads[0], grads[1] if ctx.has_pos else None
+
+
+class EotGatherFn(torch.autograd.Function):
+    """x[arange(B), tokens.argmax(-1)] (transformer.py:413-421): the end-of-text token carries the sequence feature."""
+
+    @staticmethod
+    def forward(ctx, x, tokens):
+        B, S, C = x.shape
+        x = x if (x.dtype == BF16 and x.is_contiguous()) else x.to(BF16).contiguous()
+        out, idx = ops.eot_gather_fwd(x, tokens)
+        ctx.dims, ctx.idx = (B, S, C), idx
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, S, C = ctx.dims
+        g = g if (g.dtype == BF16 and g.is_contiguous()) else g.to(BF16).contiguous()
+        return ops.eot_gather_bwd(g, ctx.idx, B, S, C), None
+
+
+class ProjectionFn(torch.autograd.Function):
+    """y = x @ P with a parameter stored [in, out] (TextTransformer.projection_layer, transformer.py:159-161, 422; SimpleImageProjectionHead.proj)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, P):
+        x2 = x if (x.dtype == BF16 and x.stride(-1) == 1 and x.stride(0) % 8 == 0) else x.to(BF16).contiguous()
+        y = ops.pw_gemm(x2, cfg.prep.get(cfg.i_pt), P.shape[1])
+        ctx.cfg, ctx.plist, ctx.saved, ctx.shape = cfg, cfg.plist, (x2,), tuple(P.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        din, dout = ctx.shape
+        (x2,) = ctx.saved
+        g = g if (g.dtype == BF16 and g.is_contiguous()) else g.to(BF16).contiguous()
+        D = _Dst(ctx.cfg, ctx.plist, g.device, din * dout + 64, 8, True)
+        ops.pw_wgrad_side(x2, g, din, dout, dW=D.mat(0, din, dout))
+        dx = ops.pw_gemm(g, ctx.cfg.prep.get(ctx.cfg.i_p), din, K=dout)
+        ops.join_side()
+        return (dx, None) + D.finish()
+
+
+class L2NormFn(torch.autograd.Function):
+    """F.normalize(x, dim=-1) (transformer.py:423-425)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x if (x.dtype == BF16 and x.is_contiguous()) else x.to(BF16).contiguous()
+        y, inv = ops.l2norm_fwd(x)
+        ctx.saved = (y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, inv = ctx.saved
+        g = g if (g.dtype == BF16 and g.is_contiguous()) else g.to(BF16).contiguous()
+        return ops.l2norm_bwd(g, y, inv)
+
+
+class ClipLossFn(torch.autograd.Function):
+    """ContrastiveLossClip._forward_clip (loss_fn/multi_modal_img_text/contrastive_loss_clip.py:56-97) with gather_all_features
+    (utils/third_party/ddp_functional_utils.py:334-357): logits_per_image = s * img @ all_text^T, logits_per_text = s * text @ all_img^T,
+    s = clamp(exp(logit_scale), 0, 100); loss = (CE(logits_per_image, arange + N*rank) + CE(logits_per_text, .)) / 2.
+    Data parallel: the features are all-gathered over NCCL in the forward and their gradients reduce-scattered in the backward."""
+
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale, cfg):
+        import torch.distributed as dist
+        N, d = img.shape
+        img = img if (img.dtype == BF16 and img.is_contiguous()) else img.to(BF16).contiguous()
+        txt = txt if (txt.dtype == BF16 and txt.is_contiguous()) else txt.to(BF16).contiguous()
+        world, rank = cfg.world, cfg.rank
+        if world > 1:
+            I_all = torch.empty((world * N, d), device=img.device, dtype=BF16)
+            T_all = torch.empty((world * N, d), device=img.device, dtype=BF16)
+            dist.all_gather_into_tensor(I_all, img, group=cfg.group)
+            dist.all_gather_into_tensor(T_all, txt, group=cfg.group)
+        else:
+            I_all, T_all = img, txt
+        G = world * N
+        if G % 8 or d % 8:
+            raise NotImplementedError("contrastive loss: global batch and feature dim must be multiples of 8")
+        labels = getattr(cfg, "_labels", None)
+        if labels is None or labels.numel() != N:
+            labels = cfg._labels = torch.arange(N, device=img.device, dtype=torch.int64) + N * rank
+        Li = ops.pw_gemm(img, T_all, G)
+        Lt = ops.pw_gemm(txt, I_all, G)
+        li, lse_i, nv_i = ops.ce_fwd(Li, G, labels, -1, 0.0, logit_scale=logit_scale)
+        lt, lse_t, nv_t = ops.ce_fwd(Lt, G, labels, -1, 0.0, logit_scale=logit_scale)
+        ctx.cfg, ctx.plist, ctx.dims = cfg, [logit_scale], (N, d, G)
+        ctx.saved = (img, txt, I_all, T_all, Li, Lt, labels, lse_i, nv_i, lse_t, nv_t, logit_scale)
+        return ((li + lt) * 0.5).view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        import torch.distributed as dist
+        cfg = ctx.cfg
+        N, d, G = ctx.dims
+        img, txt, I_all, T_all, Li, Lt, labels, lse_i, nv_i, lse_t, nv_t, p = ctx.saved
+        g = (gout.float() * 0.5).contiguous()
+        D = _Dst(cfg, ctx.plist, img.device, 64, 8, True)
+        dp = D.mat(0, 1, 1)
+        scale = getattr(cfg, "scale", None)
+        dLi = ops.ce_bwd(Li, G, labels, -1, 0.0, lse_i, nv_i, g, scale, G, logit_scale=p, dlogit_scale=dp)
+        dLt = ops.ce_bwd(Lt, G, labels, -1, 0.0, lse_t, nv_t, g, scale, G, logit_scale=p, dlogit_scale=dp)
+        dI = ops.pw_gemm(dLi, ops.transpose_bf16(T_all), d, K=G)     # through the local rows of logits_per_image
+        dT = ops.pw_gemm(dLt, ops.transpose_bf16(I_all), d, K=G)
+        dT_all = ops.pw_wgrad(dLi, img, G, d)                         # fp32 [G, d]: through the gathered operand of logits_per_image
+        dI_all = ops.pw_wgrad(dLt, txt, G, d)
+        if cfg.world > 1:
+            dT_part = torch.empty((N, d), device=img.device, dtype=torch.float32)
+            dI_part = torch.empty((N, d), device=img.device, dtype=torch.float32)
+            dist.reduce_scatter_tensor(dT_part, dT_all, op=dist.ReduceOp.SUM, group=cfg.group)
+            dist.reduce_scatter_tensor(dI_part, dI_all, op=dist.ReduceOp.SUM, group=cfg.group)
+        else:
+            dT_part, dI_part = dT_all, dI_all
+        dimg, dtxt = ops.add_bf16_f32(dI, dI_part), ops.add_bf16_f32(dT, dT_part)
+        grads = D.finish()
+        return dimg, dtxt, (grads[0].view(()) if grads[0] is not None else None), None
+
+
+# ==================================================================================================================
 # Transformer rows (SURVEY.md 8a a10-a12): MultiHeadAttention (cvnets/layers/multi_head_attention.py:135-239) and the pre-norm
 # TransformerEncoder (cvnets/modules/transformer.py:129-156) on token matrices [M = N*S, C] (bf16).  LayerNorm is the GroupNorm
 # load mode of the consuming GEMM with rows_per_sample = 1 (per-token statistics); its backward is the one-pass

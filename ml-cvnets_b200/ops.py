@@ -252,6 +252,70 @@ def col2im(dA: Tensor, B: int, Cin: int, H: int, W: int, k: int, stride: int, pa
     return dX
 
 
+def embedding_fwd(tokens: Tensor, table: Tensor, pos: Optional[Tensor]) -> Tensor:
+    B, S = tokens.shape
+    V, C = table.shape
+    out = torch.empty((B, S, C), device=table.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_embedding_fwd(tokens.data_ptr(), table.data_ptr(), _p(pos), out.data_ptr(), B, S, C, V, _stream()), "cvb_embedding_fwd")
+    _count()
+    return out
+
+
+def embedding_bwd(dout: Tensor, tokens: Tensor, dtable: Tensor, dpos: Optional[Tensor]) -> None:
+    B, S = tokens.shape
+    V, C = dtable.shape
+    L.check(_lib().cvb_embedding_bwd(dout.data_ptr(), tokens.data_ptr(), dtable.data_ptr(), _p(dpos), B, S, C, V, _stream()), "cvb_embedding_bwd")
+    _count()
+
+
+def eot_gather_fwd(X: Tensor, tokens: Tensor):
+    B, S, C = X.shape
+    out = torch.empty((B, C), device=X.device, dtype=torch.bfloat16)
+    idx = torch.empty((B,), device=X.device, dtype=torch.int32)
+    L.check(_lib().cvb_eot_gather_fwd(X.data_ptr(), tokens.data_ptr(), B, S, C, out.data_ptr(), idx.data_ptr(), _stream()), "cvb_eot_gather_fwd")
+    _count()
+    return out, idx
+
+
+def eot_gather_bwd(dout: Tensor, idx: Tensor, B: int, S: int, C: int) -> Tensor:
+    dX = torch.empty((B, S, C), device=dout.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_eot_gather_bwd(dout.data_ptr(), idx.data_ptr(), B, S, C, dX.data_ptr(), _stream()), "cvb_eot_gather_bwd")
+    _count()
+    return dX
+
+
+def l2norm_fwd(X: Tensor, eps: float = 1e-12):
+    M, C = X.shape
+    Y = torch.empty_like(X)
+    inv = torch.empty((M,), device=X.device, dtype=torch.float32)
+    L.check(_lib().cvb_l2norm_fwd(X.data_ptr(), Y.data_ptr(), inv.data_ptr(), M, C, float(eps), _stream()), "cvb_l2norm_fwd")
+    _count()
+    return Y, inv
+
+
+def l2norm_bwd(DY: Tensor, Y: Tensor, inv: Tensor) -> Tensor:
+    M, C = Y.shape
+    DX = torch.empty_like(Y)
+    L.check(_lib().cvb_l2norm_bwd(DY.data_ptr(), Y.data_ptr(), inv.data_ptr(), DX.data_ptr(), M, C, _stream()), "cvb_l2norm_bwd")
+    _count()
+    return DX
+
+
+def transpose_bf16(X: Tensor) -> Tensor:
+    R, C = X.shape
+    Y = torch.empty((C, R), device=X.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_transpose_bf16(X.data_ptr(), Y.data_ptr(), R, C, _stream()), "cvb_transpose_bf16")
+    _count()
+    return Y
+
+
+def add_bf16_f32(A: Optional[Tensor], Bf: Tensor) -> Tensor:
+    out = torch.empty(Bf.shape, device=Bf.device, dtype=torch.bfloat16)
+    L.check(_lib().cvb_add_bf16_f32(_p(A), Bf.data_ptr(), out.data_ptr(), Bf.numel(), _stream()), "cvb_add_bf16_f32")
+    _count()
+    return out
+
+
 def patch_permute(X: Tensor, B: int, H: int, W: int, ph: int, pw: int, inverse: bool) -> Tensor:
     """MobileViT-v1 unfold (inverse=False: feature-map rows -> token rows [B*P*N, C]) / fold (inverse=True)."""
     out = torch.empty_like(X)
@@ -535,23 +599,26 @@ def col_sum(X: Tensor, N: Optional[int] = None, out: Optional[Tensor] = None) ->
     return out
 
 
-def ce_fwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float, mix: Optional[Tensor] = None):
+def ce_fwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float, mix: Optional[Tensor] = None,
+           logit_scale: Optional[Tensor] = None):
     """logits: bf16 [B, ld] (C valid columns).  Returns (loss fp32 [1], lse fp32 [B], n_valid fp32 [1])."""
     B = logits.shape[0]
     lse = torch.empty(B, device=logits.device, dtype=torch.float32)
     out = torch.empty(2, device=logits.device, dtype=torch.float32)
     L.check(_lib().cvb_ce_fwd(logits.data_ptr(), logits.stride(0), B, C, target.data_ptr(), int(ignore_index), float(smoothing), lse.data_ptr(),
-                              out[0:1].data_ptr(), out[1:2].data_ptr(), _p(mix), _stream()), "cvb_ce_fwd")
+                              out[0:1].data_ptr(), out[1:2].data_ptr(), _p(mix), _p(logit_scale), _stream()), "cvb_ce_fwd")
     _count()
     return out[0:1], lse, out[1:2]
 
 
 def ce_bwd(logits: Tensor, C: int, target: Tensor, ignore_index: int, smoothing: float, lse: Tensor, n_valid: Tensor, gout: Optional[Tensor],
-           gscale: Optional[Tensor], ldd: int, mix: Optional[Tensor] = None) -> Tensor:
+           gscale: Optional[Tensor], ldd: int, mix: Optional[Tensor] = None, logit_scale: Optional[Tensor] = None,
+           dlogit_scale: Optional[Tensor] = None) -> Tensor:
     B = logits.shape[0]
     d = torch.empty((B, ldd), device=logits.device, dtype=torch.bfloat16)
     L.check(_lib().cvb_ce_bwd(logits.data_ptr(), logits.stride(0), B, C, target.data_ptr(), int(ignore_index), float(smoothing), lse.data_ptr(),
-                              n_valid.data_ptr(), _p(gout), _p(gscale), d.data_ptr(), ldd, _p(mix), _stream()), "cvb_ce_bwd")
+                              n_valid.data_ptr(), _p(gout), _p(gscale), d.data_ptr(), ldd, _p(mix), _p(logit_scale), _p(dlogit_scale), _stream()),
+            "cvb_ce_bwd")
     _count()
     return d
 

@@ -401,6 +401,58 @@ def vit_forward(P: Params, x: Tensor, *, mode: str = "base", training: bool = Tr
 
 
 # --------------------------------------------------------------------------------------------
+# CLIP (cvnets/models/multi_modal_img_text/clip.py, cvnets/text_encoders/transformer.py:23-440,
+# image_projection_layers/simple_projection_head.py, loss_fn/multi_modal_img_text/contrastive_loss_clip.py:56-97)
+# --------------------------------------------------------------------------------------------
+def clip_shapes(vit_mode: str = "base", proj: int = 512, text_dim: int = 512, text_layers: int = 12, vocab: int = 49408, ctx: int = 77) -> Dict[str, Tensor]:
+    P: Dict[str, Tensor] = {"logit_scale": torch.empty(())}
+    for k, v in vit_shapes(vit_mode).items():
+        if not k.startswith("classifier."):
+            P["image_encoder." + k] = v
+    P["image_encoder.classifier.proj"] = torch.empty(VIT_MODES[vit_mode][0], proj)
+    P["text_encoder.projection_layer"] = torch.empty(text_dim, proj)
+    P["text_encoder.embedding_layer.weight"] = torch.empty(vocab, text_dim)
+    P["text_encoder.positional_embedding.pos_embed.pos_embed"] = torch.empty(1, 1, ctx, text_dim)
+    for i in range(text_layers):
+        transformer_encoder_shapes(P, f"text_encoder.transformer.{i}", text_dim, int(math.ceil(text_dim * 4.0 / 16.0) * 16.0))
+    _gn(P, "text_encoder.final_layer_norm", text_dim)
+    return P
+
+
+def clip_forward(P: Params, images: Tensor, tokens: Tensor, *, vit_mode: str = "base", text_layers: int = 12, text_heads: int = 8,
+                 training: bool = True) -> Tuple[Tensor, Tensor]:
+    """CLIP.forward (clip.py:144-215): L2-normalised image features (ViT cls embedding @ proj) and text features (embedding + positional
+    embedding -> causal pre-norm encoders with LayerNorm eps 1e-5 and the model-wide activation -> final LayerNorm -> end-of-text token
+    @ projection_layer); transformer.py:328-425."""
+    Pi = {k[len("image_encoder."):]: v for k, v in P.items() if k.startswith("image_encoder.")}
+    d, n, heads = VIT_MODES[vit_mode]
+    h = conv_layer_2d(Pi, "patch_emb.0", images, stride=4, training=training, act="gelu")
+    h = conv_layer_2d(Pi, "patch_emb.1", h, stride=2, training=training, act="gelu")
+    h = conv_layer_2d(Pi, "patch_emb.2", h, stride=2, use_norm=False, use_act=False)
+    tok = h.flatten(2).transpose(1, 2) + Pi["pos_embed.pos_embed.pos_embed"].reshape(1, -1, d)
+    tok = torch.cat((Pi["cls_token"].expand(images.shape[0], -1, -1), tok), dim=1)
+    for i in range(n):
+        tok = transformer_encoder(Pi, f"transformer.{i}", tok, heads, act="gelu", eps=1e-6)
+    cls = layer_norm(Pi, "post_transformer_norm", tok, eps=1e-6)[:, 0]
+    img = F.normalize(cls @ Pi["classifier.proj"], dim=-1)
+    S = tokens.shape[1]
+    t = F.embedding(tokens, P["text_encoder.embedding_layer.weight"]) + P["text_encoder.positional_embedding.pos_embed.pos_embed"].reshape(1, S, -1)
+    mask = torch.full((S, S), float("-inf"), device=t.device).triu_(1).unsqueeze(0).expand(tokens.shape[0], -1, -1)
+    for i in range(text_layers):
+        t = transformer_encoder(P, f"text_encoder.transformer.{i}", t, text_heads, act="gelu", eps=1e-5, attn_mask=mask)
+    t = layer_norm(P, "text_encoder.final_layer_norm", t, eps=1e-5)
+    t = t[torch.arange(tokens.shape[0]), tokens.argmax(dim=-1)] @ P["text_encoder.projection_layer"]
+    return img, F.normalize(t, dim=-1)
+
+
+def clip_loss(img: Tensor, txt: Tensor, logit_scale: Tensor) -> Tensor:
+    """ContrastiveLossClip._forward_clip on one rank (contrastive_loss_clip.py:56-97)."""
+    s = torch.clamp(logit_scale.exp(), 0, 100.0)
+    labels = torch.arange(img.shape[0], device=img.device)
+    return 0.5 * (F.cross_entropy(s * img @ txt.t(), labels) + F.cross_entropy(s * txt @ img.t(), labels))
+
+
+# --------------------------------------------------------------------------------------------
 # parameter construction (shape contract: SURVEY.md App. B) + deterministic seeding used by the golden files
 # --------------------------------------------------------------------------------------------
 def _conv_bn(P: Dict, pre: str, cin: int, cout: int, k: int, groups: int = 1, norm: bool = True, bias: bool = False):
@@ -498,7 +550,9 @@ def seeded_fill_(P: Dict[str, Tensor], seed: int) -> Dict[str, Tensor]:
             t.copy_(0.1 * torch.randn(t.shape, generator=g))
         elif k.endswith("running_var"):
             t.copy_(1.0 + 0.2 * torch.rand(t.shape, generator=g))
-        elif k in ("cls_token", "pos_embed.pos_embed.pos_embed"):
+        elif k == "logit_scale":
+            t.fill_(math.log(1.0 / 0.07))
+        elif k.endswith("cls_token") or k.endswith("pos_embed.pos_embed") or k.endswith("embedding_layer.weight"):
             t.copy_(0.05 * torch.randn(t.shape, generator=g))
         elif t.dim() == 1 and k.endswith(".weight"):  # BN / GN gamma
             t.copy_(1.0 + 0.2 * torch.randn(t.shape, generator=g))

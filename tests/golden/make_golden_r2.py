@@ -139,7 +139,37 @@ def main():
                   loss=loss.detach().clone(), keys=[[k, list(v.shape)] for k, v in model.state_dict().items()],
                   grad_norms={k: float(g.norm()) for k, g in grads.items()}, grads={k: g.clone() for k, g in grads.items() if g.numel() <= 5000})
     torch.save(mit_fx, os.path.join(HERE, "mobilevit_v1_xxs_fp32.pt"))
-    for fn in ("standalone_fp32.pt", "mobilevit_v2_b16_fp32.pt", "vit_small_fp32.pt", "mobilevit_v1_xxs_fp32.pt"):
+    # ---- CLIP (BASELINE.json configs[4]) at a reduced geometry: ViT-small image tower, 4-layer / 256-wide causal text transformer, projection 128
+    from loss_fn.multi_modal_img_text.contrastive_loss_clip import ContrastiveLossClip
+    opts = make_opts(1.0)
+    for k, v in {"dataset.category": "multi_modal_image_text", "model.multi_modal_image_text.name": "clip", "model.multi_modal_image_text.clip.projection_dim": 128,
+                 "model.classification.name": "vit", "model.classification.vit.mode": "small", "model.classification.vit.norm_layer": "layer_norm_fp32",
+                 "model.activation.name": "gelu", "model.classification.activation.name": "gelu", "model.image_projection_head.name": "simple_projection_nc2nc",
+                 "model.text.name": "transformer", "model.text.transformer.model_dim": 256, "model.text.transformer.n_transformer_layers": 4,
+                 "model.text.transformer.n_heads_per_layer": 4, "model.text.transformer.ffn_multiplier_per_layer": 4.0,
+                 "model.text.transformer.causal_masking": True, "model.text.transformer.norm_layer": "layer_norm_fp32", "dataset.text_vocab_size": 1000,
+                 "dataset.text_context_length": 16, "dataset.padding_index": None, "ddp.use_distributed": False, "ddp.rank": 0}.items():
+        setattr(opts, k, v)
+    model = get_model(opts)
+    P = O.clip_shapes("small", proj=128, text_dim=256, text_layers=4, vocab=1000, ctx=16)
+    load_seeded(model, P, 71)
+    model.train()
+    images = O.seeded_input((8, 3, 224, 224), 371)
+    gen = torch.Generator().manual_seed(372)
+    tokens = torch.randint(1, 999, (8, 16), generator=gen)
+    tokens[torch.arange(8), torch.tensor([15, 7, 9, 12, 3, 15, 10, 5])] = 999  # the end-of-text token is the highest id
+    out = model({"image": images, "text": tokens})
+    crit = ContrastiveLossClip(opts)
+    crit.train()
+    img_f, txt_f = out["image"].detach().clone(), out["text"].detach().clone()
+    loss = crit(input_sample=None, prediction=dict(out), target=None)["total_loss"]
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    clip_fx = dict(seed=71, x_seed=371, tokens=tokens, image_features=img_f, text_features=txt_f, loss=loss.detach().clone(),
+                   keys=[[k, list(v.shape)] for k, v in model.state_dict().items()], grad_norms={k: float(g.norm()) for k, g in grads.items()},
+                   grads={k: g.clone() for k, g in grads.items() if g.numel() <= 20000})
+    torch.save(clip_fx, os.path.join(HERE, "clip_small_fp32.pt"))
+    for fn in ("standalone_fp32.pt", "mobilevit_v2_b16_fp32.pt", "vit_small_fp32.pt", "mobilevit_v1_xxs_fp32.pt", "clip_small_fp32.pt"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 
 

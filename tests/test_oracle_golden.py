@@ -250,3 +250,20 @@ def test_mobilevit_v1_xxs_fixture(golden_dir):
     assert abs(float(loss) - float(fx["loss"])) <= 1e-5
     for k, g in fx["grads"].items():
         assert float((P[k].grad - g).norm() / (g.norm() + 1e-12)) <= 2e-3, k
+
+
+def test_clip_small_fixture(golden_dir):
+    """CLIP restatement (ViT image tower + projection head, causal text transformer + EOT gather + projection, contrastive loss with the
+    learnable temperature) == the real reference at a reduced geometry."""
+    fx = torch.load(os.path.join(golden_dir, "clip_small_fp32.pt"), weights_only=False)
+    shapes = O.clip_shapes("small", proj=128, text_dim=256, text_layers=4, vocab=1000, ctx=16)
+    assert {k: list(v.shape) for k, v in shapes.items()} == {k: s for k, s in fx["keys"]}
+    P = O.clone_params(O.seeded_fill_(shapes, fx["seed"]))
+    img, txt = O.clip_forward(P, O.seeded_input((8, 3, 224, 224), fx["x_seed"]), fx["tokens"], vit_mode="small", text_layers=4, text_heads=4)
+    loss = O.clip_loss(img, txt, P["logit_scale"])
+    loss.backward()
+    assert float((img - fx["image_features"]).norm() / fx["image_features"].norm()) <= 2e-5
+    assert float((txt - fx["text_features"]).norm() / fx["text_features"].norm()) <= 2e-5
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5
+    for k, n in fx["grad_norms"].items():
+        assert abs(float(P[k].grad.norm()) - n) <= 3e-3 * n + 1e-7, k

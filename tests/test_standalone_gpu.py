@@ -220,3 +220,41 @@ def test_mobilevit_v1_xxs_against_reference_fixture(pkg, golden_dir):
         if eo > max(0.1, 2.0 * eau):
             bad.append((k, eo, eau))
     assert not bad, bad[:8]
+
+
+def test_clip_against_reference_fixture(pkg, golden_dir):
+    """BASELINE.json configs[4] at a reduced geometry (ViT-small image tower, 4-layer causal text transformer): state_dict contract, image /
+    text features, contrastive loss and gradients against the REAL reference (tests/golden/make_golden_r2.py)."""
+    from ml_cvnets_b200.models_clip import CLIP, clip_contrastive_loss, default_clip_opts
+    fx = torch.load(os.path.join(golden_dir, "clip_small_fp32.pt"), weights_only=False)
+    model = CLIP(default_clip_opts("small", projection_dim=128, text_dim=256, text_layers=4, text_heads=4, vocab_size=1000, context_length=16))
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == {k: s for k, s in fx["keys"]}
+    shapes = O.clip_shapes("small", proj=128, text_dim=256, text_layers=4, vocab=1000, ctx=16)
+    model.load_state_dict(O.seeded_fill_(shapes, fx["seed"]), strict=True)
+    model = model.cuda().train()
+    images, tokens = O.seeded_input((8, 3, 224, 224), fx["x_seed"]).cuda(), fx["tokens"].cuda()
+    img, txt, ls = model(images, tokens)
+    loss = clip_contrastive_loss(img, txt, ls)
+    loss.backward()
+    Pa = O.clone_params(O.seeded_fill_(dict(shapes), fx["seed"]), device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ia, ta = O.clip_forward(Pa, images, tokens, vit_mode="small", text_layers=4, text_heads=4)
+        la = O.clip_loss(ia, ta, Pa["logit_scale"])
+    la.backward()
+    ei, et = rel_l2(img, fx["image_features"]), rel_l2(txt, fx["text_features"])
+    print(f"[clip] feature rel-L2 vs the reference: image {ei:.4g} (autocast {rel_l2(ia, fx['image_features']):.4g}), text {et:.4g} "
+          f"(autocast {rel_l2(ta, fx['text_features']):.4g}); loss {float(loss):.5f} vs {float(fx['loss']):.5f} (autocast {float(la):.5f})")
+    assert ei <= 2e-2 and et <= 2e-2
+    assert abs(float(loss) - float(fx["loss"])) <= max(2e-2 * abs(float(fx["loss"])), 2.0 * abs(float(la) - float(fx["loss"])))
+    named = dict(model.named_parameters())
+    total = sum(n * n for n in fx["grad_norms"].values()) ** 0.5
+    bad = []
+    for k, g in fx["grads"].items():
+        if fx["grad_norms"][k] < 1e-3 * total:
+            continue
+        eo, eau = rel_l2(named[k].grad, g), rel_l2(Pa[k].grad, g)
+        if eo > max(0.1, 2.0 * eau):
+            bad.append((k, eo, eau))
+    assert not bad, bad[:8]
+    g_ls, g_ref = float(named["logit_scale"].grad), float(fx["grads"]["logit_scale"])
+    assert abs(g_ls - g_ref) <= max(0.1 * abs(g_ref), 3.0 * abs(float(Pa["logit_scale"].grad) - g_ref)), (g_ls, g_ref)
