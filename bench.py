@@ -662,6 +662,7 @@ def run_ours(args, rank, world, local_rank):
 
 # ------------------------------------------------------------------------------------- secondary workload: ViT-B/16 (BASELINE configs[2])
 VIT_GFLOP_PER_IMAGE = {"base": 106.2, "small": 27.6, "tiny": 7.5}  # 3 x 2 x forward GMAC (fwd + bwd)
+CLIP_GFLOP_PER_PAIR = {"base": 123.8}  # image tower 17.708 GMAC + text tower (12 x 77 tokens x 3.15 M MAC + attention) 2.92 GMAC, x 6
 
 
 def vit_eager_baseline(dev, B, mode, steps, warmup):
@@ -707,16 +708,26 @@ def run_vit(args, rank, world, local_rank):
     (examples/vit/classification/vit_base.yaml:13-14).  Tensor-bound: the roofline is dense-bf16 TFLOP/s."""
     import ml_cvnets_b200 as m
     from ml_cvnets_b200 import ops
+    clip = args.workload.startswith("clip_")
     mode = args.workload.split("_", 1)[1].replace("b16", "base")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.manual_seed(rank)
     B = args.batch if args.batch != 128 else 256
-    model = m.VisionTransformer(m.default_vit_opts(mode)).to(dev).train()
-    ts = m.TrainStep(model, lr=2e-3, weight_decay=0.2, max_norm=1.0, label_smoothing=0.1, ema_momentum=(0.0005 if args.ema else None), n_buckets=args.buckets)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x_dev = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
-    y_dev = torch.randint(0, NCLS, (B,), device=dev, generator=gen)
+    if clip:
+        # BASELINE.json configs[4]: CLIP ViT-B/16 image + text contrastive step (config/multi_modal_img_text/clip_vit.yaml); synthetic pairs,
+        # tokens uniform in the vocabulary with the end-of-text id (the highest) at a random position
+        model = m.CLIP(m.default_clip_opts(mode)).to(dev).train()
+        y_dev = torch.randint(1, 49406, (B, 77), device=dev, generator=gen)
+        y_dev[torch.arange(B, device=dev), torch.randint(1, 77, (B,), device=dev, generator=gen)] = 49407
+        ts = m.TrainStep(model, lr=5e-4, weight_decay=0.2, max_norm=1.0, n_buckets=args.buckets,
+                         forward_loss=lambda mod, im, tok, cfg: m.clip_contrastive_loss(*mod(im, tok), _cfg=cfg))
+    else:
+        model = m.VisionTransformer(m.default_vit_opts(mode)).to(dev).train()
+        ts = m.TrainStep(model, lr=2e-3, weight_decay=0.2, max_norm=1.0, label_smoothing=0.1, ema_momentum=(0.0005 if args.ema else None), n_buckets=args.buckets)
+        y_dev = torch.randint(0, NCLS, (B,), device=dev, generator=gen)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -755,7 +766,7 @@ def run_vit(args, rank, world, local_rank):
     value = world * B / (ms_step * 1e-3)
     launches = (ts.launches_per_step * args.steps) if not args.no_graph else (ops.launch_count - n0)
     # end to end: pinned host -> device every step, loss read back every step
-    hx, hy = torch.randn(B, 3, 224, 224).pin_memory(), torch.randint(0, NCLS, (B,)).pin_memory()
+    hx, hy = torch.randn(B, 3, 224, 224).pin_memory(), y_dev.cpu().pin_memory()
     dx, dy = torch.empty_like(x_dev), torch.empty_like(y_dev)
     hloss = torch.zeros(1).pin_memory()
     sync_all()
@@ -780,19 +791,22 @@ def run_vit(args, rank, world, local_rank):
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1440.0))
-    gflop = VIT_GFLOP_PER_IMAGE.get(mode)
+    gflop = (CLIP_GFLOP_PER_PAIR if clip else VIT_GFLOP_PER_IMAGE).get(mode)
     ach = (value / world) * gflop / 1e3 if gflop else None
     eager = None
-    if not args.no_eager_baseline and world == 1:
+    if not args.no_eager_baseline and world == 1 and not clip:
         try:
             eager = vit_eager_baseline(dev, B, mode, max(3, args.steps // 2), 3)
             eager["ours_over_eager"] = value / eager["value"]
         except Exception as e:
             eager = {"error": repr(e)[:300]}
     emit({
-        "metric": f"images/sec training step, ViT-{mode}/16 bf16 224x224", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "metric": (f"image-text pairs/sec contrastive training step, CLIP ViT-{mode}/16 bf16 224x224" if clip else
+                   f"images/sec training step, ViT-{mode}/16 bf16 224x224"), "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"ViT-{mode}/16 bf16 forward + loss + backward + clip + AdamW, synthetic 224x224 (BASELINE.json configs[2])", "per_gpu_batch": B,
+        "config": {"workload": (f"CLIP ViT-{mode}/16 image + 12-layer text tower, contrastive loss with feature all-gather, fwd + bwd + clip + AdamW, "
+                                "synthetic pairs (BASELINE.json configs[4])" if clip else
+                                f"ViT-{mode}/16 bf16 forward + loss + backward + clip + AdamW, synthetic 224x224 (BASELINE.json configs[2])"), "per_gpu_batch": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "resolution": 224, "l2": "activations per step (> 10 GB) exceed the 126 MB L2"},
         "step_ms": {"min": per[0], "median": per[len(per) // 2], "max": per[-1]}, "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": world * (hx.numel() * 4 + hy.numel() * 8), "d2h_bytes_per_step": world * 4,
@@ -811,7 +825,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (recipe: 128)")
-    ap.add_argument("--workload", default="mobilevit_v2", help="mobilevit_v2 (the metric) | vit_b16 | vit_small (BASELINE.json configs[2] family)")
+    ap.add_argument("--workload", default="mobilevit_v2", help="mobilevit_v2 (the metric) | vit_b16 | vit_small (BASELINE.json configs[2] family) | clip_b16 (configs[4])")
     ap.add_argument("--width", type=float, default=1.0, help="MobileViTv2 width multiplier (1.0 = the metric config, 2.0 = BASELINE.json configs[3])")
     ap.add_argument("--cpu-budget", type=float, default=120.0, help="wall-clock bound (s) of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU comparator")
@@ -834,7 +848,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        if args.workload.startswith("vit_"):
+        if args.workload.startswith("vit_") or args.workload.startswith("clip_"):
             run_vit(args, rank, world, local_rank)
         else:
             run_ours(args, rank, world, local_rank)

@@ -43,7 +43,10 @@ class TrainStep:
     def __init__(self, model: torch.nn.Module, *, lr: float = 2e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
                  no_decay_bn_filter_bias: bool = True, max_norm: float = 10.0, label_smoothing: float = 0.1, ignore_index: int = -1,
                  ema_momentum: Optional[float] = None, init_scale: float = 65536.0, growth_interval: int = 2000,
-                 process_group=None, data_parallel: Optional[bool] = None, n_buckets: int = 3, broadcast_buffers: bool = True):
+                 process_group=None, data_parallel: Optional[bool] = None, n_buckets: int = 3, broadcast_buffers: bool = True,
+                 forward_loss=None):
+        """``forward_loss(model, *inputs, cfg) -> loss`` replaces the default ``cross_entropy(model(x), y)`` (e.g. CLIP's contrastive step);
+        ``cfg.scale`` is the device-resident loss scale the loss's backward must multiply by, ``cfg.world / rank / group`` the process group."""
         import torch.distributed as dist
         self.model = model
         self.ws = StepWorkspace(model)
@@ -64,6 +67,9 @@ class TrainStep:
         self.loss_cfg = SimpleNamespace(label_smoothing=float(label_smoothing), ignore_index=int(ignore_index), scale=self.opt.loss_scale(),
                                         mix=self.ws.mix)
         self._mix_host = torch.tensor([0.0, 1.0, 0.0, 0.0, 0.0, 0.0]).pin_memory()
+        self.forward_loss = forward_loss
+        self.loss_cfg.group = process_group
+        self.loss_cfg.world, self.loss_cfg.rank = self.world, (dist.get_rank(process_group) if data_parallel else 0)
         self._one = torch.ones((), device=self.ws.device, dtype=torch.float32)
         self._graph = None
         self._static = None
@@ -92,15 +98,18 @@ class TrainStep:
         self.opt.load_state_dict(sd)
 
     # ---- one iteration, eager launches
-    def _step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def _step(self, *inputs: torch.Tensor) -> torch.Tensor:
         ws = self.ws
         ws.begin_step()
         if self.world > 1 and self.broadcast_buffers:
             ws.broadcast_buffers()
         ws.active = True
         try:
-            logits = self.model(x)
-            loss = cross_entropy(logits, y, _cfg=self.loss_cfg)
+            if self.forward_loss is None:
+                x, y = inputs
+                loss = cross_entropy(self.model(x), y, _cfg=self.loss_cfg)
+            else:
+                loss = self.forward_loss(self.model, *inputs, self.loss_cfg)
             torch.autograd.backward(loss, grad_tensors=self._one)
         finally:
             ws.active = False
@@ -108,15 +117,14 @@ class TrainStep:
         self.opt.step(grad_div=float(self.world))
         return loss
 
-    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def step(self, *inputs: torch.Tensor) -> torch.Tensor:
         if self._graph is None:
             self.eager_steps += 1
-            return self._step(x, y)
-        sx, sy, sloss = self._static
-        if x is not sx:
-            sx.copy_(x, non_blocking=True)
-        if y is not sy:
-            sy.copy_(y, non_blocking=True)
+            return self._step(*inputs)
+        *statics, sloss = self._static
+        for s_in, t in zip(statics, inputs):
+            if t is not s_in:
+                s_in.copy_(t, non_blocking=True)
         self._graph.replay()
         ops.invalidate_prepared_weights()
         return sloss
@@ -124,31 +132,31 @@ class TrainStep:
     __call__ = step
 
     # ---- whole step as one CUDA graph
-    def capture(self, x: torch.Tensor, y: torch.Tensor, warmup: int = 3):
+    def capture(self, *inputs: torch.Tensor, warmup: int = 3):
         """Warm up eagerly (workspace planning needs two steps), then capture fwd + loss + bwd (+ all-reduce) + optimizer tail."""
         assert self._graph is None, "already captured"
         dev = self.ws.device
-        sx, sy = x.to(dev).clone(), y.to(dev).clone()
+        statics = [t.to(dev).clone() for t in inputs]
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(0, max(warmup, 3) - self.eager_steps)):
-                self._step(sx, sy)
+                self._step(*statics)
                 self.eager_steps += 1
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count
         with torch.cuda.graph(graph):
-            sloss = self._step(sx, sy)
+            sloss = self._step(*statics)
         self.launches_per_step = ops.launch_count - n0
-        self._graph, self._static = graph, (sx, sy, sloss)
+        self._graph, self._static = graph, (*statics, sloss)
         return self
 
     @property
     def static_inputs(self):
-        return None if self._static is None else self._static[:2]
+        return None if self._static is None else self._static[:-1]
 
 
 class MixingSampler:

@@ -97,10 +97,14 @@ class StepWorkspace:
         self.group = None
         self.world = 1
         self.n_buckets = 1
-        self._unit_order: List[Tuple[int, int]] = []   # (lo, hi) flat ranges in the order their backward finishes (recorded on the 1st step)
-        self._fire_at: Dict[int, Tuple[int, int]] = {}  # unit counter value -> flat range to all-reduce
+        self._unit_bucket: Dict[Tuple[int, int], int] = {}  # module's flat range -> bucket (planned after the first step)
+        self._bucket_range: List[Tuple[int, int]] = []
+        self._bucket_count: List[int] = []
+        self._bucket_left: List[int] = []
+        self._bucket_fired: List[bool] = []
+        self._plan_valid = False
+        self._seen_units: List[Tuple[int, int]] = []
         self._units_done = 0
-        self._reduced_lo = None
         self._works = []
         self.model = model
         for m in model.modules():
@@ -165,8 +169,8 @@ class StepWorkspace:
             L.check(lib.cvb_memset_zero(self._buf32.data_ptr(), self._buf32.numel() * 4, st), "cvb_memset_zero")
             L.check(lib.cvb_memset_zero(self._buf64.data_ptr(), self._buf64.numel() * 8, st), "cvb_memset_zero")
         self._units_done = 0
-        self._reduced_lo = self.n
         self._works = []
+        self._reset_bucket_state()
 
     # ------------------------------------------------------------------------------------------- fp64 statistics -> fp32 gradients
     def scatter64(self, key: tuple, pairs: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
@@ -201,7 +205,7 @@ class StepWorkspace:
 
     def unit_done(self, params: Sequence[torch.Tensor]):
         """Called at the end of a module's backward (after its side-stream weight gradients were joined): its gradients are final.
-        Fires the all-reduce of every bucket whose modules are all done."""
+        Fires the all-reduce of every bucket whose modules are all done (whatever order autograd runs them in)."""
         if self.world == 1 or not self.active:
             return
         offs = [self.offsets[id(p)] for p in params if id(p) in self.offsets]
@@ -209,56 +213,69 @@ class StepWorkspace:
             return
         lo = min(o for o, _ in offs)
         hi = max((o + k + ALIGN - 1) // ALIGN * ALIGN for o, k in offs)
-        idx = self._units_done
         self._units_done += 1
-        if idx >= len(self._unit_order) or self._unit_order[idx] != (lo, hi):
-            # first step (or the module order changed): record; the exchange happens once, at finish_reduce()
-            self._unit_order = self._unit_order[:idx] + [(lo, hi)]
-            self._fire_at = {}
+        self._seen_units.append((lo, hi))
+        b = self._unit_bucket.get((lo, hi))
+        if b is None:
+            self._plan_valid = False  # unknown module (first step, or the set of modules changed): exchange everything at the end, re-plan
             return
-        rng = self._fire_at.get(idx)
-        if rng is not None:
-            self._allreduce(*rng)
+        if not self._plan_valid:
+            return
+        self._bucket_left[b] -= 1
+        if self._bucket_left[b] == 0:
+            self._allreduce(*self._bucket_range[b])
+            self._bucket_fired[b] = True
 
     def _allreduce(self, lo: int, hi: int):
         import torch.distributed as dist
         if hi <= lo:
             return
         self._works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        self._reduced_lo = min(self._reduced_lo, lo)
 
-    def _plan_buckets(self):
-        """Contiguous flat ranges in completion order, cut at module boundaries into ~equal-sized buckets."""
-        self._fire_at = {}
-        if not self._unit_order or sum(hi - lo for lo, hi in self._unit_order) != self.n:
-            return  # some parameters belong to modules that do not report completion: one exchange at the end of backward
-        # completion order runs from the end of the flat buffer to its start (classifier first, stem last)
+    def _plan_buckets(self, units):
+        """Contiguous flat ranges cut at module boundaries into ~equal-sized buckets (from the end of the buffer: the classifier's and the
+        last stages' gradients are final first); a bucket fires when every module inside it has reported."""
+        self._unit_bucket, self._bucket_range, self._bucket_count = {}, [], []
+        units = sorted(set(units))
+        pos = 0
+        for lo, hi in units:  # the reporting modules must tile the whole buffer, else some gradient could arrive after its bucket went out
+            if lo != pos:
+                return
+            pos = hi
+        if pos != self.n:
+            return
         target = self.n / self.n_buckets
-        top = self.n
-        acc_lo = top
-        nb = 0
-        for idx, (lo, hi) in enumerate(self._unit_order):
-            acc_lo = min(acc_lo, lo)
-            last = idx == len(self._unit_order) - 1
-            if last:
-                acc_lo = 0
-            if (top - acc_lo) >= target and nb < self.n_buckets - 1 or last:
-                self._fire_at[idx] = (acc_lo, top)
-                top = acc_lo
-                nb += 1
+        top, members = self.n, []
+        for lo, hi in reversed(units):
+            members.append((lo, hi))
+            if (top - lo) >= target and len(self._bucket_range) < self.n_buckets - 1 or lo == 0:
+                b = len(self._bucket_range)
+                self._bucket_range.append((lo, top))
+                self._bucket_count.append(len(members))
+                for u in members:
+                    self._unit_bucket[u] = b
+                top, members = lo, []
+
+    def _reset_bucket_state(self):
+        self._bucket_left = list(self._bucket_count)
+        self._bucket_fired = [False] * len(self._bucket_count)
+        self._plan_valid = bool(self._bucket_count)
+        self._seen_units = []
 
     def finish_reduce(self):
         """Everything not yet exchanged goes out now; then the current stream waits for all exchanges."""
         if self.world == 1:
             return
-        if self._units_done != len(self._unit_order):
-            self._unit_order = self._unit_order[:self._units_done]
-        if not self._fire_at:
-            if self._reduced_lo > 0:
-                self._allreduce(0, self._reduced_lo)
-            self._plan_buckets()
-        elif self._reduced_lo > 0:
-            self._allreduce(0, self._reduced_lo)
+        if self._plan_valid and all(self._bucket_fired):
+            pass
+        elif not self._works:
+            self._allreduce(0, self.n)
+        else:  # a partially fired plan (should not happen: an unknown unit invalidates the plan before anything fires out of order)
+            for b, fired in enumerate(self._bucket_fired):
+                if not fired:
+                    self._allreduce(*self._bucket_range[b])
+        if not self._plan_valid or not self._bucket_count:
+            self._plan_buckets(self._seen_units)
         for w in self._works:
             w.wait()
         self._works = []

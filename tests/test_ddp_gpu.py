@@ -60,7 +60,7 @@ def _worker(rank, world, port, q):
         for it in range(3):  # plan, descriptor tables, bucketed
             ts.step(x, y)
             errs["eval"].append(rel(ts.ws.flat_g / world, ref))  # flat_g holds the SUM over ranks (cvb_grad_norm divides by world)
-        n_fire = len(ts.ws._fire_at)
+        n_fire = len(ts.ws._bucket_range)
         # (b) train mode (per-GPU batch statistics, the recipe): atomics-order noise is amplified by BatchNorm through ~60 bf16 layers, so the
         # bound is the run-to-run difference of the single-GPU reference itself
         ref_t, ref_t2 = reference(True), reference(True)
