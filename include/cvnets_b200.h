@@ -272,11 +272,15 @@ CVB_API int cvb_ln_stats(const void* X, int ldx, int64_t M, int C, float eps, fl
  * grad_div : gradients are divided by loss_scale * grad_div (DDP's mean over ranks: grad_div = world size, main_train.py:90-96)
  * ema / ema_momentum : optional fp32[n] moving average updated in the same pass, ema = ema*(1-momentum) + momentum*param
  *           (cvnets/misc/averaging_utils.py:43-55; also on skipped steps, like the reference's per-iteration update); NULL = off
+ * partials : fp32[2 * cvb_grad_norm_blocks(n)] scratch: per-block (sum of squares, non-finite count), combined in a fixed order by the step
+ *           kernel so that the norm / clip coefficient / update are bit-identical on every data-parallel rank
  * ------------------------------------------------------------------------------------------------------------- */
-CVB_API int cvb_grad_norm(const float* grads, int64_t n, const float* scale, float grad_div, float* stats, cvb_stream_t stream);
+CVB_API int cvb_grad_norm_blocks(int64_t n);
+CVB_API int cvb_grad_norm(const float* grads, int64_t n, const float* scale, float grad_div, float* stats, float* partials, cvb_stream_t stream);
 CVB_API int cvb_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay, int64_t n,
                    const float* hp, float beta1, float beta2, float eps, float max_norm, float* stats, float* scale, float* step,
-                   float growth_factor, float backoff_factor, int growth_interval, float* ema, float ema_momentum, cvb_stream_t stream);
+                   float growth_factor, float backoff_factor, int growth_interval, float* ema, float ema_momentum, const float* partials,
+                   cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Classification loss of the step: F.cross_entropy(prediction, target, ignore_index, label_smoothing), mean over the non-ignored

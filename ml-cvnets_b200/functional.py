@@ -1017,8 +1017,10 @@ class ClipLossFn(torch.autograd.Function):
         if world > 1:
             I_all = torch.empty((world * N, d), device=img.device, dtype=BF16)
             T_all = torch.empty((world * N, d), device=img.device, dtype=BF16)
-            dist.all_gather_into_tensor(I_all, img, group=cfg.group)
-            dist.all_gather_into_tensor(T_all, txt, group=cfg.group)
+            w1 = dist.all_gather_into_tensor(I_all, img, group=cfg.group, async_op=True)
+            w2 = dist.all_gather_into_tensor(T_all, txt, group=cfg.group, async_op=True)
+            w1.wait()
+            w2.wait()
         else:
             I_all, T_all = img, txt
         G = world * N
@@ -1054,8 +1056,10 @@ class ClipLossFn(torch.autograd.Function):
         if cfg.world > 1:
             dT_part = torch.empty((N, d), device=img.device, dtype=torch.float32)
             dI_part = torch.empty((N, d), device=img.device, dtype=torch.float32)
-            dist.reduce_scatter_tensor(dT_part, dT_all, op=dist.ReduceOp.SUM, group=cfg.group)
-            dist.reduce_scatter_tensor(dI_part, dI_all, op=dist.ReduceOp.SUM, group=cfg.group)
+            w1 = dist.reduce_scatter_tensor(dT_part, dT_all, op=dist.ReduceOp.SUM, group=cfg.group, async_op=True)
+            w2 = dist.reduce_scatter_tensor(dI_part, dI_all, op=dist.ReduceOp.SUM, group=cfg.group, async_op=True)
+            w1.wait()
+            w2.wait()
         else:
             dT_part, dI_part = dT_all, dI_all
         dimg, dtxt = ops.add_bf16_f32(dI, dI_part), ops.add_bf16_f32(dT, dT_part)

@@ -46,6 +46,7 @@ class FlatAdamW:
         self.ema = self.flat_p.clone() if ema_momentum is not None else None
         self.ema_momentum = float(ema_momentum) if ema_momentum is not None else 0.0
         self.stats = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.partials = torch.zeros(2 * int(_lib().cvb_grad_norm_blocks(n)), device=dev, dtype=torch.float32)
         self.scale = torch.tensor([init_scale, 0.0], device=dev, dtype=torch.float32)
         self.step_count = torch.zeros(1, device=dev, dtype=torch.float32)
         self.hp = torch.tensor([float(lr)], device=dev, dtype=torch.float32)
@@ -70,14 +71,15 @@ class FlatAdamW:
         if lr_now != float(self._hp_host[0]) and not torch.cuda.is_current_stream_capturing():
             self.set_lr(lr_now)
         lib = _lib()
-        L.check(lib.cvb_grad_norm(self.flat_g.data_ptr(), self.n, self.scale.data_ptr(), float(grad_div), self.stats.data_ptr(), _stream()), "cvb_grad_norm")
+        L.check(lib.cvb_grad_norm(self.flat_g.data_ptr(), self.n, self.scale.data_ptr(), float(grad_div), self.stats.data_ptr(),
+                                  self.partials.data_ptr(), _stream()), "cvb_grad_norm")
         _count()
         b1, b2, eps, max_norm = self.consts
         gf, bf, gi = self.gs
         L.check(lib.cvb_adamw_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                    self.wd.data_ptr(), self.n, self.hp.data_ptr(), b1, b2, eps, max_norm, self.stats.data_ptr(), self.scale.data_ptr(),
                                    self.step_count.data_ptr(), gf, bf, gi, self.ema.data_ptr() if self.ema is not None else None, self.ema_momentum,
-                                   _stream()), "cvb_adamw_step")
+                                   self.partials.data_ptr(), _stream()), "cvb_adamw_step")
         _count()
         invalidate_prepared_weights()  # raw-pointer update: eval-mode weight caches must refresh (Tensor._version did not move)
 
