@@ -18,6 +18,7 @@ inside the step (zero-fills are memset nodes, the loss is cvb_ce_*).  Semantics 
 """
 from __future__ import annotations
 
+import gc
 from types import SimpleNamespace
 from typing import Optional
 
@@ -146,6 +147,7 @@ class TrainStep:
                 self.eager_steps += 1
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
+        gc.collect()  # no autograd graph of an eager step (leaf accumulators are bound to the stream they were created on) may survive into capture
         graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count
         with torch.cuda.graph(graph):

@@ -991,7 +991,9 @@ class L2NormFn(torch.autograd.Function):
     def forward(ctx, x):
         x = x if (x.dtype == BF16 and x.is_contiguous()) else x.to(BF16).contiguous()
         y, inv = ops.l2norm_fwd(x)
-        ctx.saved = (y, inv)
+        # y is also the OUTPUT: keeping that very object on ctx would close a reference cycle (output -> grad_fn -> ctx -> output) that keeps the
+        # whole step's autograd graph -- and the leaf accumulators with the stream they were created on -- alive into the next step
+        ctx.saved = (y.detach(), inv)
         return y
 
     @staticmethod
