@@ -34,7 +34,7 @@ if which in ("all", "gemm", "prof", "one"):
         ("gemm L2.0.red AFFS K128 N128 @64^2 +stats", 64*64, 128, 128, A_AFF_SILU, True),
         ("gemm L2.1.exp RAW  K128 N256 @64^2 +stats", 64*64, 128, 256, A_RAW, True),
         ("gemm L3.ffn1  GN   K128 N256 @32^2", 32*32, 128, 256, A_GN, False),
-    ] if not prof or c[0].startswith(("gemm L2.0.exp RAW  K64 N128 @128^2 +stats",) + (("gemm L2.0.red AFFS",) if which == "prof" else ()))]:
+    ] if not prof or c[0].startswith(("gemm L2.0.exp RAW  K64 N128 @128^2 +stats",) + (("gemm L2.0.red AFFS", "gemm L3.ffn1") if which == "prof" else ()))]:
         M = B * HW
         A = torch.randn(M, K, device=dev).to(BF); W = (torch.randn(N, K, device=dev) * K**-0.5).to(BF)
         p = (vec(K, 0.2, 1.0), vec(K, 0.3), None)
@@ -67,7 +67,7 @@ if which in ("all", "wgrad", "prof"):
         report(name, ms, 2.0 * M * (2 * N + K))
 
 if which in ("all", "dw", "prof"):
-    for (name, H, C, s) in [("dw L1 s1 C64 @128^2", 128, 64, 1), ("dw L2.0 s2 C128 @128^2", 128, 128, 2), ("dw L2.1 s1 C256 @64^2", 64, 256, 1)][1:2] if prof else [("dw L1 s1 C64 @128^2", 128, 64, 1), ("dw L2.0 s2 C128 @128^2", 128, 128, 2), ("dw L2.1 s1 C256 @64^2", 64, 256, 1)]:
+    for (name, H, C, s) in [("dw L1 s1 C64 @128^2", 128, 64, 1), ("dw L2.0 s2 C128 @128^2", 128, 128, 2), ("dw L2.1 s1 C256 @64^2", 64, 256, 1)][0:2] if prof else [("dw L1 s1 C64 @128^2", 128, 64, 1), ("dw L2.0 s2 C128 @128^2", 128, 128, 2), ("dw L2.1 s1 C256 @64^2", 64, 256, 1)]:
         Ho = (H - 1) // s + 1
         X = torch.randn(B * H * H, C, device=dev).to(BF)
         Wt = torch.randn(9, C, device=dev).to(BF).float() * 0.3
