@@ -31,7 +31,7 @@ typedef void* cvb_stream_t; /* cudaStream_t */
 #define CVB_API
 #endif
 
-#define CVB_ABI_VERSION 7
+#define CVB_ABI_VERSION 8
 
 /* operand "load modes": the normalisation / activation of the PRODUCER layer is applied while the CONSUMER loads it
  * (training-mode BatchNorm cannot be fused into its own conv: SURVEY.md section 7 "hard parts"). */
@@ -120,8 +120,9 @@ CVB_API int cvb_apply_load_mode(const void* A, int lda, const void* A2, int lda2
                                 cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Depthwise 3x3 convolution, pad 1, stride 1|2, NHWC (ConvLayer2d(groups=C): mobilenetv2.py:194-207,
- * mobilevit_block.py:369-379).  The producer's BN(+SiLU) is applied on load (x_mode RAW/AFF/AFF_SILU); zero padding
+ * Depthwise 3x3 convolution, pad = dilation, stride 1|2, NHWC (ConvLayer2d(groups=C): mobilenetv2.py:194-207,
+ * mobilevit_block.py:369-379).  dilation 0 / 1 = dense stencil (TMA walk kernels); dilation > 1 (stride 1 only) = the segmentation
+ * backbones' output_stride 8 / 16 variants (base_image_encoder.py:38-47, mobilevit_v2.py:176-191), a direct-gather kernel.  The producer's BN(+SiLU) is applied on load (x_mode RAW/AFF/AFF_SILU); zero padding
  * is applied AFTER that transform, as in the reference where padding acts on the activated tensor.
  * Output: pre-BN y (bf16) + fp64 per-channel sum / sum of squares of the stored values.
  * ------------------------------------------------------------------------------------------------------------- */
@@ -131,6 +132,7 @@ typedef struct {
   const float* Wt;  /* fp32 [9][C] (tap-major), values already rounded to bf16 (autocast semantics) */
   void* Y;          /* bf16 [B,Ho,Wo,C] */
   double* col_sum; double* col_sq;
+  int dilation;     /* 0 or 1: none */
 } cvb_dw_fwd_args;
 CVB_API int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream);
 
@@ -145,6 +147,7 @@ typedef struct {
   void* DX;         /* bf16 [B,H,W,C] */
   double* col_sum; double* col_sq; /* may be NULL when x_mode == RAW */
   float* dWt;       /* fp32 [9][C], atomically accumulated */
+  int dilation;     /* 0 or 1: none */
 } cvb_dw_bwd_args;
 CVB_API int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream);
 

@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcvnets_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # load modes / epilogue modes (mirror include/cvnets_b200.h)
 A_RAW, A_AFF, A_AFF_SILU, A_SILU, A_GN, A_BNB = 0, 1, 2, 3, 4, 5
@@ -58,7 +58,7 @@ class DwFwdArgs(Structure):
     _fields_ = [
         ("B", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("stride", c_int),
         ("X", c_void_p), ("x_mode", c_int), ("x_p0", c_void_p), ("x_p1", c_void_p),
-        ("Wt", c_void_p), ("Y", c_void_p), ("col_sum", c_void_p), ("col_sq", c_void_p),
+        ("Wt", c_void_p), ("Y", c_void_p), ("col_sum", c_void_p), ("col_sq", c_void_p), ("dilation", c_int),
     ]
 
 
@@ -67,7 +67,7 @@ class DwBwdArgs(Structure):
         ("B", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("stride", c_int),
         ("DZ", c_void_p), ("Y2", c_void_p), ("g_mode", c_int), ("g_p0", c_void_p), ("g_p1", c_void_p), ("g_p2", c_void_p),
         ("X", c_void_p), ("x_mode", c_int), ("x_p0", c_void_p), ("x_p1", c_void_p),
-        ("Wt", c_void_p), ("DX", c_void_p), ("col_sum", c_void_p), ("col_sq", c_void_p), ("dWt", c_void_p),
+        ("Wt", c_void_p), ("DX", c_void_p), ("col_sum", c_void_p), ("col_sq", c_void_p), ("dWt", c_void_p), ("dilation", c_int),
     ]
 
 

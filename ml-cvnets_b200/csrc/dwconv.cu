@@ -476,6 +476,9 @@ int round1k(int v) { return (v + 1023) / 1024 * 1024; }
 
 }  // namespace
 
+int cvb_dw_fwd_dilated(const cvb_dw_fwd_args& a, cudaStream_t st);  // dwconv_dilated.cu
+int cvb_dw_bwd_dilated(const cvb_dw_bwd_args& a, cudaStream_t st);
+
 extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   CVB_CHECK(args != nullptr, "cvb_dw_fwd: null args");
   const cvb_dw_fwd_args& a = *args;
@@ -484,6 +487,8 @@ extern "C" int cvb_dw_fwd(const cvb_dw_fwd_args* args, cvb_stream_t stream) {
   CVB_CHECK(a.X && a.Wt && a.Y && cvb_aligned16(a.X) && cvb_aligned16(a.Y), "cvb_dw_fwd: null / misaligned operand");
   CVB_CHECK(a.x_mode == CVB_A_RAW || ((a.x_mode == CVB_A_AFF || a.x_mode == CVB_A_AFF_SILU) && a.x_p0 && a.x_p1), "cvb_dw_fwd: bad x_mode %d", a.x_mode);
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_dw_fwd: col_sq missing");
+  CVB_CHECK(a.dilation >= 0 && a.dilation <= 64, "cvb_dw_fwd: bad dilation %d", a.dilation);
+  if (a.dilation > 1) return cvb_dw_fwd_dilated(a, static_cast<cudaStream_t>(stream));
   const int s = a.stride;
   const int Ho = (a.H - 1) / s + 1, Wo = (a.W - 1) / s + 1;
   // two CTAs per SM: two input buffers of <= ~42 KB each
@@ -531,6 +536,8 @@ extern "C" int cvb_dw_bwd(const cvb_dw_bwd_args* args, cvb_stream_t stream) {
   CVB_CHECK(a.g_mode == CVB_A_RAW || (a.g_mode == CVB_A_BNB && a.Y2 && a.g_p0 && a.g_p1 && a.g_p2), "cvb_dw_bwd: bad g_mode %d", a.g_mode);
   CVB_CHECK(a.x_mode == CVB_A_RAW || ((a.x_mode == CVB_A_AFF || a.x_mode == CVB_A_AFF_SILU) && a.x_p0 && a.x_p1), "cvb_dw_bwd: bad x_mode %d", a.x_mode);
   if (a.col_sum) CVB_CHECK(a.col_sq != nullptr, "cvb_dw_bwd: col_sq missing");
+  CVB_CHECK(a.dilation >= 0 && a.dilation <= 64, "cvb_dw_bwd: bad dilation %d", a.dilation);
+  if (a.dilation > 1) return cvb_dw_bwd_dilated(a, static_cast<cudaStream_t>(stream));
   if (a.stride == 2) CVB_CHECK(a.H % 2 == 0 && a.W % 2 == 0, "cvb_dw_bwd: stride 2 needs even H, W");
   const int s = a.stride;
   const int Ho = (a.H - 1) / s + 1, Wo = (a.W - 1) / s + 1;

@@ -226,7 +226,8 @@ class InvertedResidualFn(torch.autograd.Function):
         else:
             y1 = ops.pw_gemm(x2, P.get(cfg.i_w1), hid, col_stats=st1 if bs[0] else None)
         bn1 = _bn_forward(st1, M, g1, b1, cfg.bn[0])
-        y2 = ops.dw_fwd(y1, B, H, W, hid, s, P.get(cfg.i_wd), x_mode=A_AFF_SILU, x_p=(bn1[2], bn1[3]), col_stats=st2 if bs[1] else None)
+        y2 = ops.dw_fwd(y1, B, H, W, hid, s, P.get(cfg.i_wd), x_mode=A_AFF_SILU, x_p=(bn1[2], bn1[3]), col_stats=st2 if bs[1] else None,
+                        dilation=cfg.dilation)
         bn2 = _bn_forward(st2, M2, g2, b2, cfg.bn[1])
         y3 = ops.pw_gemm(y2, P.get(cfg.i_w3), cout, a_mode=A_AFF_SILU, a_p=(bn2[2], bn2[3]), col_stats=st3 if bs[2] else None)
         bn3 = _bn_forward(st3, M2, g3, b3, cfg.bn[2])
@@ -269,7 +270,7 @@ class InvertedResidualFn(torch.autograd.Function):
         dgb2, c2 = ops.bn_bwd_finalize(sd2, M2, g2, bn2, ev[1], out=D.pair(4, 5))
         D.set_pair(4, 5, dgb2)
         dz1, dWt = ops.dw_bwd(dz2, y1, B, H, W, hid, s, P.get(cfg.i_wd), g_mode=A_BNB, Y2=y2, g_p=c2, x_mode=A_AFF_SILU,
-                              x_p=(bn1[2], bn1[3]), col_stats=sd1, dWt=ar.f32(9, hid))
+                              x_p=(bn1[2], bn1[3]), col_stats=sd1, dWt=ar.f32(9, hid), dilation=cfg.dilation)
         D.unprep(3, dWt, hid, 9, hid, 2)
         # exp_1x1 + BN1
         dgb1, c1 = ops.bn_bwd_finalize(sd1, M, g1, bn1, ev[0], out=D.pair(1, 2))
@@ -312,9 +313,9 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
         lz = ctx.lz_in = cfg.lazy_in
         if lz is not None:
             am, _, ap = _lazy_modes(lz)
-            y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), x_mode=am, x_p=ap, col_stats=st0 if bs[0] else None)
+            y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), x_mode=am, x_p=ap, col_stats=st0 if bs[0] else None, dilation=cfg.dilation)
         else:
-            y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), col_stats=st0 if bs[0] else None)
+            y0 = ops.dw_fwd(x2, B, H, W, C, 1, P.get(cfg.i_wd0), col_stats=st0 if bs[0] else None, dilation=cfg.dilation)
         bn0 = _bn_forward(st0, M, g0, b0, cfg.bn[0])
         X = ops.pw_gemm(y0, P.get(cfg.i_wl), d, a_mode=A_AFF_SILU, a_p=(bn0[2], bn0[3]), samp_stats=samp[0], rows_per_sample=HW)
         blocks = []
@@ -426,9 +427,10 @@ class MobileViTBlockv2Fn(torch.autograd.Function):
             am, _, ap = _lazy_modes(lz)
             lz.stats = ar.f64(2, C)
             dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=am, x_p=ap, col_stats=lz.stats,
-                                 dWt=ar.f32(9, C))
+                                 dWt=ar.f32(9, C), dilation=cfg.dilation)
         else:
-            dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW, dWt=ar.f32(9, C))
+            dx, dWt = ops.dw_bwd(dz0, x2, B, H, W, C, 1, P.get(cfg.i_wd0), g_mode=A_BNB, Y2=y0, g_p=c0, x_mode=A_RAW, dWt=ar.f32(9, C),
+                                 dilation=cfg.dilation)
         D.unprep(0, dWt, C, 9, C, 2)
         ops.join_side()
         return (to_4d(dx, B, H, W), None) + D.finish()
@@ -615,12 +617,12 @@ class DepthwiseConvFn(torch.autograd.Function):
         x2 = as_2d(x)
         if cfg.bn is not None:
             st = _fwd_arena(cfg, x.device, 2 * C + 8).f64(2, C)
-            y = ops.dw_fwd(x2, B, H, W, C, s, cfg.prep.get(cfg.i_w), col_stats=st if cfg.bn.batch_stats else None)
+            y = ops.dw_fwd(x2, B, H, W, C, s, cfg.prep.get(cfg.i_w), col_stats=st if cfg.bn.batch_stats else None, dilation=cfg.dilation)
             bn = _bn_forward(st, M2, gamma, beta, cfg.bn)
             out = ops.bn_apply(y, bn, act=cfg.act is not None)
             ctx.saved, ctx.ev = (x2, y, bn), (not cfg.bn.batch_stats,)
         else:
-            y = ops.dw_fwd(x2, B, H, W, C, s, cfg.prep.get(cfg.i_w))
+            y = ops.dw_fwd(x2, B, H, W, C, s, cfg.prep.get(cfg.i_w), dilation=cfg.dilation)
             out = ops.act_fwd(y, cfg.act) if cfg.act is not None else y
             ctx.saved = (x2, y)
         ctx.cfg, ctx.dims, ctx.plist = cfg, (B, C, H, W, Ho, Wo), cfg.plist
@@ -644,11 +646,12 @@ class DepthwiseConvFn(torch.autograd.Function):
                 dz = dout
             dgb, c = ops.bn_bwd_finalize(sd, M2, gamma, bn, ctx.ev[0], out=D.pair(1, 2))
             D.set_pair(1, 2, dgb)
-            dx, dWt = ops.dw_bwd(dz, x2, B, H, W, C, cfg.stride, cfg.prep.get(cfg.i_w), g_mode=A_BNB, Y2=y, g_p=c, dWt=D.ar.f32(9, C))
+            dx, dWt = ops.dw_bwd(dz, x2, B, H, W, C, cfg.stride, cfg.prep.get(cfg.i_w), g_mode=A_BNB, Y2=y, g_p=c, dWt=D.ar.f32(9, C),
+                                 dilation=cfg.dilation)
         else:
             x2, y = ctx.saved
             dz = ops.act_bwd(dout, y, cfg.act) if cfg.act is not None else dout
-            dx, dWt = ops.dw_bwd(dz, x2, B, H, W, C, cfg.stride, cfg.prep.get(cfg.i_w), dWt=D.ar.f32(9, C))
+            dx, dWt = ops.dw_bwd(dz, x2, B, H, W, C, cfg.stride, cfg.prep.get(cfg.i_w), dWt=D.ar.f32(9, C), dilation=cfg.dilation)
         D.unprep(0, dWt, C, 9, C, 2)
         grads = D.finish()
         return (to_4d(dx, B, H, W), None, grads[0]) + ((grads[1], grads[2]) if cfg.bn is not None else (None, None))

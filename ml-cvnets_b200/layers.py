@@ -6,7 +6,7 @@ keeps working.  Parameters are ordinary ``nn.Parameter``s inside ordinary ``nn.C
 
 There is deliberately NO PyTorch fallback.  Inside InvertedResidual / MobileViTBlockv2 / TransformerEncoder the layers are parameter
 containers executed by the fused autograd functions; used on their own they run the stand-alone functions of functional.py (same
-kernels, one layer per function).  What has no kernel path (dense k x k convs other than the stem, dilation, dropout p > 0) raises.
+kernels, one layer per function).  What has no kernel path (dilated dense convs, dropout p > 0 in training) raises.
 """
 from __future__ import annotations
 
@@ -220,18 +220,20 @@ class ConvLayer2d(BaseLayer):
         # groups = 1: 1x1 convs are the GEMM itself; square k x k convs run as im2col + GEMM (ViT conv stem, MobileViT-v1 3x3 convs)
         pointwise = (self.groups == 1 and self.dilation == (1, 1) and self.kernel_size[0] == self.kernel_size[1] and self.stride[0] == self.stride[1]
                      and pad is not None and pad[0] == pad[1] and (self.in_channels % 8 == 0 or self.kernel_size[0] > 1))
-        depthwise = (self.kernel_size == (3, 3) and self.groups == self.in_channels == self.out_channels and self.dilation == (1, 1)
-                     and self.stride in ((1, 1), (2, 2)) and conv.bias is None and tuple(conv.padding) == (1, 1))
+        dil = self.dilation[0]
+        depthwise = (self.kernel_size == (3, 3) and self.groups == self.in_channels == self.out_channels and self.dilation[0] == self.dilation[1]
+                     and self.stride in ((1, 1), (2, 2)) and (dil == 1 or self.stride == (1, 1)) and conv.bias is None
+                     and tuple(conv.padding) == (dil, dil))
         if depthwise:
             pointwise = False
         if not (pointwise or depthwise) or self.out_channels % 8 or (depthwise and self.in_channels % 8):
             raise NotImplementedError("stand-alone ConvLayer2d: undilated groups=1 convs with square kernels (out_channels % 8 == 0; in_channels % 8 == 0 "
-                                      "for 1x1) and depthwise 3x3 convs have kernel paths")
+                                      "for 1x1) and depthwise 3x3 convs (dilated: stride 1) have kernel paths")
         if self._stem is None:
             prep = PW()
             k = self.kernel_size[0]
             cfg = SimpleNamespace(prep=prep, cout=self.out_channels, act=act, has_bias=conv.bias is not None, stride=self.stride[0], k=k,
-                                  pad=pad[0] if pad is not None else 0)
+                                  pad=pad[0] if pad is not None else 0, dilation=dil)
             if pointwise and k == 1 and self.stride[0] == 1:
                 cfg.i_w = prep.add(conv.weight, PW.KIND_ROWMAJOR)
                 cfg.i_wt = prep.add(conv.weight, PW.KIND_TRANSPOSED)

@@ -72,7 +72,12 @@ class MobileViTv2(nn.Module):
         pool_type = getattr(opts, "model.layer.global_pool", "mean")
         cfg = get_configuration(opts)
         self.opts = opts
+        # segmentation heads (DeepLabv3 / PSPNet) ask for output_stride 8 / 16: the stride of layer_4 / layer_5 becomes dilation
+        # (base_image_encoder.py:38-47)
         self.dilation = 1
+        output_stride = kwargs.get("output_stride", None)
+        self.dilate_l4, self.dilate_l5 = output_stride == 8, output_stride in (8, 16)
+        self.output_stride = output_stride
         self.model_conf_dict = dict()
         c0 = cfg["layer0"]["out_channels"]
         self.conv_1 = ConvLayer2d(opts=opts, in_channels=cfg["layer0"]["img_channels"], out_channels=c0, kernel_size=3, stride=2,
@@ -80,7 +85,8 @@ class MobileViTv2(nn.Module):
         self.model_conf_dict["conv1"] = {"in": 3, "out": c0}
         in_c = c0
         for li in range(1, 6):
-            layer, out_c = self._make_layer(opts=opts, input_channel=in_c, cfg=cfg[f"layer{li}"])
+            layer, out_c = self._make_layer(opts=opts, input_channel=in_c, cfg=cfg[f"layer{li}"],
+                                            dilate={4: self.dilate_l4, 5: self.dilate_l5}.get(li, False))
             setattr(self, f"layer_{li}", layer)
             self.model_conf_dict[f"layer{li}"] = {"in": in_c, "out": out_c}
             in_c = out_c
@@ -117,10 +123,15 @@ class MobileViTv2(nn.Module):
         return nn.Sequential(*block), input_channel
 
     def _make_mit_layer(self, opts, input_channel, cfg: Dict, dilate: Optional[bool] = False) -> Tuple[nn.Sequential, int]:
+        prev_dilation = self.dilation
         block = []
-        if cfg.get("stride", 1) == 2:
-            block.append(InvertedResidual(opts=opts, in_channels=input_channel, out_channels=cfg.get("out_channels"), stride=2,
-                                          expand_ratio=cfg.get("mv_expand_ratio", 4), dilation=1))
+        stride = cfg.get("stride", 1)
+        if stride == 2:
+            if dilate:  # mobilevit_v2.py:183-186
+                self.dilation *= 2
+                stride = 1
+            block.append(InvertedResidual(opts=opts, in_channels=input_channel, out_channels=cfg.get("out_channels"), stride=stride,
+                                          expand_ratio=cfg.get("mv_expand_ratio", 4), dilation=prev_dilation))
             input_channel = cfg.get("out_channels")
         block.append(MobileViTBlockv2(
             opts=opts, in_channels=input_channel, attn_unit_dim=cfg["attn_unit_dim"], ffn_multiplier=cfg.get("ffn_multiplier"),
@@ -128,7 +139,7 @@ class MobileViTv2(nn.Module):
             dropout=getattr(opts, "model.classification.mitv2.dropout", 0.0),
             ffn_dropout=getattr(opts, "model.classification.mitv2.ffn_dropout", 0.0),
             attn_dropout=getattr(opts, "model.classification.mitv2.attn_dropout", 0.0), conv_ksize=3,
-            attn_norm_layer=getattr(opts, "model.classification.mitv2.attn_norm_layer", "layer_norm_2d"), dilation=1))
+            attn_norm_layer=getattr(opts, "model.classification.mitv2.attn_norm_layer", "layer_norm_2d"), dilation=self.dilation))
         return nn.Sequential(*block), input_channel
 
     @classmethod
@@ -193,6 +204,28 @@ class MobileViTv2(nn.Module):
             for m in self._chain:
                 object.__setattr__(m, "_lazy_active", False)
         return self.conv_1x1_exp(x)
+
+    # ---- feature maps for down-stream heads (base_image_encoder.py:206-276); every returned map is materialised (no lazy boundaries)
+    def extract_end_points_all(self, x: Tensor, use_l5: Optional[bool] = True, use_l5_exp: Optional[bool] = False, *args, **kwargs) -> Dict[str, Tensor]:
+        _require_cuda(x, "MobileViTv2")
+        out_dict = {}
+        x = self.layer_1(self.conv_1(x))
+        out_dict["out_l1"] = x
+        x = self.layer_2(x)
+        out_dict["out_l2"] = x
+        x = self.layer_3(x)
+        out_dict["out_l3"] = x
+        x = self.layer_4(x)
+        out_dict["out_l4"] = x
+        if use_l5:
+            x = self.layer_5(x)
+            out_dict["out_l5"] = x
+            if use_l5_exp:
+                out_dict["out_l5_exp"] = self.conv_1x1_exp(x)
+        return out_dict
+
+    def extract_end_points_l4(self, x: Tensor, *args, **kwargs) -> Dict[str, Tensor]:
+        return self.extract_end_points_all(x, use_l5=False)
 
     def forward_classifier(self, x: Tensor, *args, **kwargs) -> Tensor:
         x = self.extract_features(x)

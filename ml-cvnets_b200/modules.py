@@ -100,13 +100,14 @@ class InvertedResidual(BaseModule):
     def _build_cfg(self):
         if self.exp == 1:
             raise NotImplementedError("InvertedResidual with expand_ratio == 1 (no exp_1x1) is not on the MobileViT hot path")
-        if self.dilation != 1:
-            raise NotImplementedError("dilated depthwise conv (segmentation heads, SURVEY.md 8f row 4) is a 'next' row")
+        if self.dilation != 1 and self.stride != 1:
+            raise NotImplementedError("a dilated depthwise conv must have stride 1 (the reference dilates instead of striding, mobilevit_v2.py:183-186)")
         if self.in_channels % 8 or self.out_channels % 8 or self.hidden_dim % 8:
             raise NotImplementedError("channel counts must be multiples of 8 (16-byte channel vectors)")
         b = self.block
         prep = PW()
-        cfg = SimpleNamespace(prep=prep, hid=self.hidden_dim, cout=self.out_channels, stride=self.stride, residual=self.use_res_connect)
+        cfg = SimpleNamespace(prep=prep, hid=self.hidden_dim, cout=self.out_channels, stride=self.stride, residual=self.use_res_connect,
+                              dilation=int(self.dilation))
         cfg.i_w1 = prep.add(b.exp_1x1.block.conv.weight, PW.KIND_ROWMAJOR)
         cfg.i_w1t = prep.add(b.exp_1x1.block.conv.weight, PW.KIND_TRANSPOSED)
         cfg.i_wd = prep.add(b.conv_3x3.block.conv.weight, PW.KIND_TAPMAJOR_F32)
@@ -219,8 +220,8 @@ class MobileViTBlockv2(BaseModule):
         C, d = self.cnn_in_dim, self.cnn_out_dim
         if self.patch_h != 2 or self.patch_w != 2:
             raise NotImplementedError("only 2x2 patches (every MobileViTv2 config) are implemented")
-        if self.conv_ksize != 3 or self.dilation != 1:
-            raise NotImplementedError("local_rep must be an undilated 3x3 depthwise conv")
+        if self.conv_ksize != 3:
+            raise NotImplementedError("local_rep must be a 3x3 depthwise conv")
         if self.attn_norm_layer not in ("layer_norm_2d", "layer_norm_nchw"):
             raise NotImplementedError("attn_norm_layer must be layer_norm_2d")
         if self.dropout or self.attn_dropout or self.ffn_dropout:
@@ -231,7 +232,7 @@ class MobileViTBlockv2(BaseModule):
         if C % 8 or d % 8:
             raise NotImplementedError("channel counts must be multiples of 8")
         prep = PW()
-        cfg = SimpleNamespace(prep=prep, d=d, ffn=ffns.pop(), n_blocks=self.n_blocks, gn_eps=float(self.global_rep[-1].eps))
+        cfg = SimpleNamespace(prep=prep, d=d, ffn=ffns.pop(), n_blocks=self.n_blocks, gn_eps=float(self.global_rep[-1].eps), dilation=int(self.dilation))
         cfg.i_wd0 = prep.add(self.local_rep[0].block.conv.weight, PW.KIND_TAPMAJOR_F32)
         cfg.i_wl = prep.add(self.local_rep[1].block.conv.weight, PW.KIND_ROWMAJOR)
         cfg.i_wlt = prep.add(self.local_rep[1].block.conv.weight, PW.KIND_TRANSPOSED)

@@ -86,16 +86,16 @@ def batch_norm(P: Params, pre: str, x: Tensor, training: bool, momentum: float =
 
 
 def conv_layer_2d(P: Params, pre: str, x: Tensor, *, stride: int = 1, groups: int = 1, use_norm: bool = True,
-                  use_act: bool = True, training: bool = True, momentum: float = 0.1, act: str = "swish") -> Tensor:
+                  use_act: bool = True, training: bool = True, momentum: float = 0.1, act: str = "swish", dilation: int = 1) -> Tensor:
     """ConvLayer2d = Sequential(conv[, norm][, act]) (cvnets/layers/conv_layer.py:200-226,254-255).
 
-    Auto padding ``(k-1)//2`` (``:182-185``); norm = BatchNorm2d (``model.normalization.name=batch_norm``,
+    Auto padding ``(k-1)//2 * dilation`` (``:182-185``); norm = BatchNorm2d (``model.normalization.name=batch_norm``,
     ``:138-144``); act = Swish == nn.SiLU (cvnets/layers/activation/swish.py:13-20).
     """
     w = P[pre + ".block.conv.weight"]
     b = P.get(pre + ".block.conv.bias")
     k = w.shape[-1]
-    x = F.conv2d(x, w, b, stride=stride, padding=(k - 1) // 2, groups=groups)
+    x = F.conv2d(x, w, b, stride=stride, padding=(k - 1) // 2 * dilation, groups=groups, dilation=dilation)
     if use_norm:
         x = batch_norm(P, pre + ".block.norm", x, training, momentum)
     if use_act:
@@ -207,14 +207,14 @@ def transformer_encoder(P: Params, pre: str, x: Tensor, num_heads: int, act: str
 # modules
 # --------------------------------------------------------------------------------------------
 def inverted_residual(P: Params, pre: str, x: Tensor, *, stride: int, training: bool = True,
-                      momentum: float = 0.1) -> Tensor:
+                      momentum: float = 0.1, dilation: int = 1) -> Tensor:
     """InvertedResidual (cvnets/modules/mobilenetv2.py:141-246): exp_1x1 (if present) -> conv_3x3 depthwise
     (stride) -> red_1x1 (no act); residual iff stride==1 and Cin==Cout (``:227-235``)."""
     y = x
     if (pre + ".block.exp_1x1.block.conv.weight") in P:
         y = conv_layer_2d(P, pre + ".block.exp_1x1", y, training=training, momentum=momentum)
     hid = P[pre + ".block.conv_3x3.block.conv.weight"].shape[0]
-    y = conv_layer_2d(P, pre + ".block.conv_3x3", y, stride=stride, groups=hid, training=training, momentum=momentum)
+    y = conv_layer_2d(P, pre + ".block.conv_3x3", y, stride=stride, groups=hid, training=training, momentum=momentum, dilation=dilation)
     y = conv_layer_2d(P, pre + ".block.red_1x1", y, use_act=False, training=training, momentum=momentum)
     cout = P[pre + ".block.red_1x1.block.conv.weight"].shape[0]
     if stride == 1 and x.shape[1] == cout:
@@ -236,14 +236,14 @@ def folding(patches: Tensor, output_size: Tuple[int, int], ph: int = 2, pw: int 
 
 
 def mobilevit_block_v2(P: Params, pre: str, x: Tensor, *, n_attn_blocks: int, patch_h: int = 2, patch_w: int = 2,
-                       training: bool = True, momentum: float = 0.1) -> Tensor:
+                       training: bool = True, momentum: float = 0.1, dilation: int = 1) -> Tensor:
     """MobileViTBlockv2.forward_spatial (cvnets/modules/mobilevit_block.py:605-626):
     local_rep (dw3x3+BN+SiLU, 1x1) -> unfold -> n x LinearAttnFFN -> layer_norm_2d -> fold -> conv_proj 1x1 + BN.
     Input H, W must be multiples of the patch (the bilinear ``resize_input_if_needed`` ``:595-603`` never fires
     at 256x256 and is out of scope)."""
     C = x.shape[1]
     assert x.shape[2] % patch_h == 0 and x.shape[3] % patch_w == 0
-    fm = conv_layer_2d(P, pre + ".local_rep.0", x, groups=C, training=training, momentum=momentum)
+    fm = conv_layer_2d(P, pre + ".local_rep.0", x, groups=C, training=training, momentum=momentum, dilation=dilation)
     fm = conv_layer_2d(P, pre + ".local_rep.1", fm, use_norm=False, use_act=False)
     patches, out_size = unfolding(fm, patch_h, patch_w)
     for i in range(n_attn_blocks):
@@ -256,34 +256,40 @@ def mobilevit_block_v2(P: Params, pre: str, x: Tensor, *, n_attn_blocks: int, pa
 # --------------------------------------------------------------------------------------------
 # model
 # --------------------------------------------------------------------------------------------
-def mobilevit_v2_layout(width_multiplier: float = 1.0) -> List[Tuple[str, str, Dict]]:
+def mobilevit_v2_layout(width_multiplier: float = 1.0, output_stride: Optional[int] = None) -> List[Tuple[str, str, Dict]]:
     """Stage wiring of MobileViTv2.__init__/_make_layer (cvnets/models/classification/mobilevit_v2.py:25-226),
-    as a flat list of (kind, state_dict prefix, kwargs)."""
+    as a flat list of (kind, state_dict prefix, kwargs).  ``output_stride`` 8 / 16 (segmentation backbones,
+    base_image_encoder.py:38-47): layer_4 and/or layer_5 keep their resolution and dilate instead (mobilevit_v2.py:176-191)."""
     cfg = mobilevit_v2_config(width_multiplier)
     out: List[Tuple[str, str, Dict]] = [("stem", "conv_1", {})]
+    dilation = 1
+    dilate = {4: output_stride == 8, 5: output_stride in (8, 16)}
     for li in range(1, 6):
         c = cfg[f"layer{li}"]
         if c["block_type"] == "mv2":
             for i in range(c["num_blocks"]):
-                out.append(("ir", f"layer_{li}.{i}", {"stride": c["stride"] if i == 0 else 1}))
+                out.append(("ir", f"layer_{li}.{i}", {"stride": c["stride"] if i == 0 else 1, "dilation": 1}))
         else:
-            out.append(("ir", f"layer_{li}.0", {"stride": 2}))
-            out.append(("mvit", f"layer_{li}.1", {"n_attn_blocks": c["attn_blocks"]}))
+            prev, stride = dilation, 2
+            if dilate.get(li, False):
+                dilation, stride = dilation * 2, 1
+            out.append(("ir", f"layer_{li}.0", {"stride": stride, "dilation": prev}))
+            out.append(("mvit", f"layer_{li}.1", {"n_attn_blocks": c["attn_blocks"], "dilation": dilation}))
     return out
 
 
 def mobilevit_v2_forward(P: Params, x: Tensor, *, width_multiplier: float = 1.0, training: bool = True,
-                         momentum: float = 0.1, return_stages: bool = False):
+                         momentum: float = 0.1, return_stages: bool = False, output_stride: Optional[int] = None):
     """BaseImageEncoder.forward -> extract_features -> classifier
     (cvnets/models/classification/base_image_encoder.py:261-301; mobilevit_v2.py:37-45,91-94)."""
     stages = {}
-    for kind, pre, kw in mobilevit_v2_layout(width_multiplier):
+    for kind, pre, kw in mobilevit_v2_layout(width_multiplier, output_stride):
         if kind == "stem":
             x = conv_layer_2d(P, pre, x, stride=2, training=training, momentum=momentum)
         elif kind == "ir":
-            x = inverted_residual(P, pre, x, stride=kw["stride"], training=training, momentum=momentum)
+            x = inverted_residual(P, pre, x, stride=kw["stride"], training=training, momentum=momentum, dilation=kw["dilation"])
         else:
-            x = mobilevit_block_v2(P, pre, x, n_attn_blocks=kw["n_attn_blocks"], training=training, momentum=momentum)
+            x = mobilevit_block_v2(P, pre, x, n_attn_blocks=kw["n_attn_blocks"], training=training, momentum=momentum, dilation=kw["dilation"])
         stages[pre] = x
     x = x.mean(dim=[-2, -1])  # GlobalPool(mean) cvnets/layers/global_pool.py:60-71
     logits = F.linear(x, P["classifier.1.weight"], P["classifier.1.bias"])  # cvnets/layers/linear_layer.py:90

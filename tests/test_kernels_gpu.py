@@ -358,6 +358,51 @@ def test_dw_bwd(ops, B, H, W, C, stride, g_mode, x_mode):
         close_stat(col[1], (o * X.float()).sum(0), "sum dz*x")
 
 
+@pytest.mark.parametrize("B,H,W,C,dil", [(2, 16, 16, 64, 2), (3, 12, 20, 48, 2), (2, 16, 16, 384, 4), (2, 8, 8, 72, 4), (1, 5, 7, 8, 3)])
+@pytest.mark.parametrize("x_mode", [0, 1, 2])
+def test_dw_fwd_dilated(ops, B, H, W, C, dil, x_mode):
+    """Dilated depthwise conv (segmentation backbones, output_stride 8 / 16): pad = dilation, stride 1."""
+    X = bf(rnd(B * H * W, C, seed=41))
+    w = bf(rnd(C, 1, 3, 3, scale=0.3, seed=42)).float()
+    p = (1 + 0.2 * rnd(C, seed=43), 0.3 * rnd(C, seed=44))
+    Wt = w.view(C, 9).t().contiguous()
+    col = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    Y = ops.dw_fwd(X, B, H, W, C, 1, Wt, x_mode=x_mode, x_p=p, col_stats=col, dilation=dil)
+    xa = load_ref(x_mode, X, p + (None,)).view(B, H, W, C).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xa, w, None, stride=1, padding=dil, dilation=dil, groups=C).permute(0, 2, 3, 1).reshape(-1, C)
+    close(Y, ref, what="dilated dw fwd")
+    o = Y.float()
+    close_stat(col[0], o.sum(0), "col_sum")
+    close_stat(col[1], (o * o).sum(0), "col_sq")
+
+
+@pytest.mark.parametrize("B,H,W,C,dil", [(2, 16, 16, 64, 2), (3, 12, 20, 48, 2), (2, 16, 16, 384, 4), (1, 5, 7, 8, 3)])
+@pytest.mark.parametrize("g_mode,x_mode", [(0, 0), (5, 2), (5, 0), (0, 2), (5, 1)])
+def test_dw_bwd_dilated(ops, B, H, W, C, dil, g_mode, x_mode):
+    X = bf(rnd(B * H * W, C, seed=51))
+    DZ, Y2 = bf(rnd(B * H * W, C, seed=52)), bf(rnd(B * H * W, C, seed=53))
+    w = bf(rnd(C, 1, 3, 3, scale=0.3, seed=54)).float()
+    gp = (1 + 0.2 * rnd(C, seed=55), 0.3 * rnd(C, seed=56), 0.1 * rnd(C, seed=57))
+    xp = (1 + 0.2 * rnd(C, seed=58), 0.3 * rnd(C, seed=59))
+    Wt = w.view(C, 9).t().contiguous()
+    col = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+    DX, dWt = ops.dw_bwd(DZ, X, B, H, W, C, 1, Wt, g_mode=g_mode, Y2=Y2 if g_mode == 5 else None, g_p=gp, x_mode=x_mode, x_p=xp,
+                         col_stats=col if x_mode != 0 else None, dilation=dil)
+    dy = load_ref(g_mode, DZ, gp, Y2).view(B, H, W, C).permute(0, 3, 1, 2)
+    xa = load_ref(x_mode, X, xp + (None,)).view(B, H, W, C).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wv = w.clone().requires_grad_(True)
+    torch.nn.functional.conv2d(xa, wv, None, stride=1, padding=dil, dilation=dil, groups=C).backward(dy)
+    da = xa.grad.permute(0, 2, 3, 1).reshape(-1, C)
+    if x_mode == 2:
+        da = da * dsilu(xp[0] * X.float() + xp[1])
+    close(DX, da, what="dilated dX")
+    close(dWt, wv.grad.view(C, 9).t(), rtol=3e-3, atol=3e-3 * float(wv.grad.abs().max()) + 1e-5, what="dilated dW")
+    if x_mode != 0:
+        o = DX.float()
+        close_stat(col[0], o.sum(0), "sum dz")
+        close_stat(col[1], (o * X.float()).sum(0), "sum dz*x")
+
+
 # ----------------------------------------------------------------------------------------------------------- BN / GN / misc
 def test_bn_finalize_and_bwd_finalize(ops):
     C, M = 96, 5000

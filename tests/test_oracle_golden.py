@@ -267,3 +267,25 @@ def test_clip_small_fixture(golden_dir):
     assert abs(float(loss) - float(fx["loss"])) <= 1e-5
     for k, n in fx["grad_norms"].items():
         assert abs(float(P[k].grad.norm()) - n) <= 3e-3 * n + 1e-7, k
+
+
+def test_dilated_backbone_fixture(golden_dir):
+    """MobileViTv2 as a segmentation backbone (output_stride 8 / 16: layer_4 / layer_5 dilate instead of striding).
+    Oracle end points and gradients == the real reference (tests/golden/make_golden_dilated.py)."""
+    fx = torch.load(os.path.join(golden_dir, "mobilevit_v2_dilated_fp32.pt"), weights_only=False)
+    for os_ in (8, 16):
+        rec = fx[f"os{os_}"]
+        P = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(fx["width"]), fx["seed"]))
+        x = O.seeded_input((fx["batch"], 3, fx["res"], fx["res"]), fx["x_seed"])
+        _, st = O.mobilevit_v2_forward(P, x, width_multiplier=fx["width"], training=True, return_stages=True, output_stride=os_)
+        ends = {"out_l3": st["layer_3.1"], "out_l4": st["layer_4.1"], "out_l5": st["layer_5.1"]}
+        for k, v in rec["ends"].items():
+            assert ends[k].shape == v.shape, (os_, k, ends[k].shape, v.shape)
+            assert float((ends[k] - v).norm() / v.norm()) <= 2e-5, (os_, k)
+        if "grads" in rec:
+            gy4, gy5 = (O.seeded_input(tuple(ends[k].shape), sd) for k, sd in zip(("out_l4", "out_l5"), rec["gy_seeds"]))
+            ((ends["out_l4"] * gy4).sum() + (ends["out_l5"] * gy5).sum()).backward()
+            for k, n in rec["grad_norms"].items():
+                assert abs(float(P[k].grad.norm()) - n) <= 2e-3 * n + 1e-6, k
+            for k, g in rec["grads"].items():
+                assert float((P[k].grad - g).norm() / (g.norm() + 1e-12)) <= 5e-4, k

@@ -143,6 +143,48 @@ def test_model_batch16_reference_fixture(pkg, golden_dir):
     assert med[0] <= 0.25 and worst[0] <= 0.6  # train-mode bf16 gradients at batch 16 (torch-autocast sits at the same level)
 
 
+def test_dilated_backbone_against_reference_fixture(pkg, golden_dir):
+    """MobileViTv2 built with output_stride 8 / 16 (segmentation backbones: dilated depthwise convs in layer_4 / layer_5),
+    ``extract_end_points_all`` forward + backward against the REAL reference (tests/golden/make_golden_dilated.py)."""
+    fx = torch.load(os.path.join(golden_dir, "mobilevit_v2_dilated_fp32.pt"), weights_only=False)
+    for os_ in (8, 16):
+        rec = fx[f"os{os_}"]
+        model = pkg.MobileViTv2(pkg.default_opts(width_multiplier=fx["width"]), output_stride=os_)
+        model.load_state_dict(O.seeded_fill_(O.mobilevit_v2_shapes(fx["width"]), fx["seed"]), strict=True)
+        model = model.cuda().train()
+        dil = {n: list(m.dilation) for n, m in model.named_modules() if isinstance(m, torch.nn.Conv2d) and tuple(m.dilation) != (1, 1)}
+        assert dil == rec["dilations"], (dil, rec["dilations"])
+        x = O.seeded_input((fx["batch"], 3, fx["res"], fx["res"]), fx["x_seed"]).cuda()
+        ends = model.extract_end_points_all(x)
+        assert set(ends) == {"out_l1", "out_l2", "out_l3", "out_l4", "out_l5"}
+        Pa = O.clone_params(O.seeded_fill_(O.mobilevit_v2_shapes(fx["width"]), fx["seed"]), device="cuda")
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, st = O.mobilevit_v2_forward(Pa, x, width_multiplier=fx["width"], training=True, return_stages=True, output_stride=os_)
+        auto = {"out_l3": st["layer_3.1"], "out_l4": st["layer_4.1"], "out_l5": st["layer_5.1"]}
+        for k, v in rec["ends"].items():
+            assert tuple(ends[k].shape) == tuple(v.shape), (os_, k)
+            e, ea = rel_l2(ends[k], v), rel_l2(auto[k], v)
+            print(f"[dilated backbone os={os_}] {k} rel-L2 vs the reference: ours {e:.4g}, torch-autocast {ea:.4g}")
+            assert e <= max(3e-2, 1.5 * ea), (os_, k, e, ea)
+        if "grads" in rec:
+            gy4, gy5 = (O.seeded_input(tuple(ends[k].shape), sd).cuda() for k, sd in zip(("out_l4", "out_l5"), rec["gy_seeds"]))
+            ((ends["out_l4"].float() * gy4).sum() + (ends["out_l5"].float() * gy5).sum()).backward()
+            ((auto["out_l4"].float() * gy4).sum() + (auto["out_l5"].float() * gy5).sum()).backward()
+            named = dict(model.named_parameters())
+            total = sum(n * n for n in rec["grad_norms"].values()) ** 0.5
+            errs = []
+            for k, g in rec["grads"].items():
+                if rec["grad_norms"][k] < 1e-3 * total:
+                    continue
+                errs.append((rel_l2(named[k].grad, g), rel_l2(Pa[k].grad, g), k))
+            errs.sort()
+            med, worst = errs[len(errs) // 2], errs[-1]
+            print(f"[dilated backbone os={os_}] parameter-gradient rel-L2: median ours {med[0]:.4g} (autocast {med[1]:.4g}), worst {worst[0]:.4g} "
+                  f"(autocast {worst[1]:.4g}, {worst[2]}), n={len(errs)}")
+            med_auto = sorted(e[1] for e in errs)[len(errs) // 2]
+            assert med[0] <= max(5e-2, 1.5 * med_auto) and worst[0] <= max(0.3, 2.0 * max(e[1] for e in errs))
+
+
 def test_vision_transformer_against_reference_fixture(pkg, golden_dir):
     """VisionTransformer (BASELINE.json configs[2] family; 'small' geometry = the same code path as ViT-B/16: 12 layers, head_dim 64,
     S = 197, layer_norm_fp32, GELU) against logits / loss / gradients of the REAL reference (tests/golden/make_golden_r2.py)."""
