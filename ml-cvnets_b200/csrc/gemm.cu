@@ -425,7 +425,7 @@ int launch_gemm(const cvb_gemm_args& a, cudaStream_t st, bool require_two_ctas) 
   // resident CTAs per SM: registers allow 2 (launch bounds); shared memory: 228 KB per SM, ~5 KB static + reserved per CTA
   const int occ = (2 * (smem + 5 * 1024) <= (size_t)228 * 1024) ? 2 : 1;
   const int n_tiles = (a.N + BN - 1) / BN, m_tiles = (a.M + BM - 1) / BM;
-  int gy = (occ * cvb_num_sms() + n_tiles - 1) / n_tiles;  // all CTAs resident, each streaming over its M tiles
+  int gy = (occ * cvb_num_sms()) / n_tiles;  // all CTAs resident (never more than fit at once), each streaming over its M tiles
   if (gy > m_tiles) gy = m_tiles;
   if (gy < 1) gy = 1;
   CUtensorMap tmA, tmA2, tmW;

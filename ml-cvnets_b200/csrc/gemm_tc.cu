@@ -409,7 +409,9 @@ int launch_tc_impl(const cvb_gemm_args& a, cudaStream_t st, size_t fixed, int st
     attr = true;
   }
   const int n_tiles = (a.N + TC_BN - 1) / TC_BN, m_tiles = (a.M + TC_BM - 1) / TC_BM;
-  int gy = (cvb_num_sms() + n_tiles - 1) / n_tiles;  // one persistent CTA per SM
+  // one persistent CTA per SM, never more CTAs than SMs: rounding UP (3 x 50 = 150 CTAs on 148 SMs) put two CTAs into a second wave and doubled
+  // the time of every N = 264 / 392 / 520 / 768-wide late-stage layer (profiles/r2_step_launches_v2_lazybn_dram.csv)
+  int gy = cvb_num_sms() / n_tiles;
   if (gy > m_tiles) gy = m_tiles;
   if (gy < 1) gy = 1;
   CUtensorMap tmA, tmA2, tmW;

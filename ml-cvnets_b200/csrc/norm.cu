@@ -475,12 +475,34 @@ __global__ void __launch_bounds__(NT) ln_bwd_kernel(const bf16* __restrict__ V, 
 }
 
 // stand-alone activation passes for the transformer FFN when the activation is not SiLU (GELU of the ViT / CLIP recipes; the
-// SiLU FFN keeps the activation fused into the GEMM load / epilogue modes).  kind: 0 = SiLU, 1 = GELU (erf form, nn.GELU default)
-__device__ __forceinline__ float act_fwd_f(float x, int kind) { return kind == 0 ? silu_f(x) : 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// SiLU FFN keeps the activation fused into the GEMM load / epilogue modes).  kind: 0 = SiLU, 1 = GELU (erf form, nn.GELU default),
+// 2 = ReLU, 3 = Hardswish x*relu6(x+3)/6, 4 = Hardsigmoid relu6(x+3)/6 (cvnets/layers/activation/{relu,hard_swish,hard_sigmoid}.py: the
+// MobileNetv3-style InvertedResidualSE block, cvnets/modules/mobilenetv2.py:16-138), 5 = Sigmoid
+__device__ __forceinline__ float act_fwd_f(float x, int kind) {
+  switch (kind) {
+    case 0: return silu_f(x);
+    case 1: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case 2: return fmaxf(x, 0.f);
+    case 3: return x * fminf(fmaxf(x + 3.0f, 0.f), 6.0f) * (1.0f / 6.0f);
+    case 4: return fminf(fmaxf(x + 3.0f, 0.f), 6.0f) * (1.0f / 6.0f);
+    default: return 1.0f / (1.0f + __expf(-x));
+  }
+}
 __device__ __forceinline__ float act_grad_f(float x, int kind) {
-  if (kind == 0) return silu_grad_f(x);
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  switch (kind) {
+    case 0: return silu_grad_f(x);
+    case 1: {
+      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+      return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+    }
+    case 2: return x > 0.f ? 1.f : 0.f;
+    case 3: return x < -3.0f ? 0.f : (x <= 3.0f ? fmaf(x, 1.0f / 3.0f, 0.5f) : 1.0f);  // torch: hardswish_backward
+    case 4: return (x > -3.0f && x < 3.0f) ? (1.0f / 6.0f) : 0.f;
+    default: {
+      const float s = 1.0f / (1.0f + __expf(-x));
+      return s * (1.0f - s);
+    }
+  }
 }
 __global__ void __launch_bounds__(NT) act_fwd_kernel(const bf16* __restrict__ X, bf16* __restrict__ Y, int64_t nvec, int kind) {
   pdl_wait();
@@ -837,13 +859,13 @@ extern "C" int cvb_ln_bwd(const void* V, const void* X, const float* mean, const
 }
 
 extern "C" int cvb_act_fwd(const void* X, void* Y, int64_t n, int kind, cvb_stream_t stream) {
-  CVB_CHECK(X && Y && n > 0 && n % 8 == 0 && cvb_aligned16(X) && cvb_aligned16(Y) && (kind == 0 || kind == 1), "cvb_act_fwd: bad arguments");
+  CVB_CHECK(X && Y && n > 0 && n % 8 == 0 && cvb_aligned16(X) && cvb_aligned16(Y) && kind >= 0 && kind <= 5, "cvb_act_fwd: bad arguments");
   CVB_CUDA(cvb_launch(act_fwd_kernel, grid_for(n / 8), NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(X), static_cast<bf16*>(Y), n / 8, kind));
   CVB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int cvb_act_bwd(const void* DY, const void* X, void* DX, int64_t n, int kind, cvb_stream_t stream) {
-  CVB_CHECK(DY && X && DX && n > 0 && n % 8 == 0 && cvb_aligned16(DY) && cvb_aligned16(X) && cvb_aligned16(DX) && (kind == 0 || kind == 1),
+  CVB_CHECK(DY && X && DX && n > 0 && n % 8 == 0 && cvb_aligned16(DY) && cvb_aligned16(X) && cvb_aligned16(DX) && kind >= 0 && kind <= 5,
             "cvb_act_bwd: bad arguments");
   CVB_CUDA(cvb_launch(act_bwd_kernel, grid_for(n / 8), NT, 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(DY), static_cast<const bf16*>(X),
                       static_cast<bf16*>(DX), n / 8, kind));
