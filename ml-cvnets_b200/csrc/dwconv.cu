@@ -14,6 +14,7 @@
 //   * tiles (+ zero-filled halos = the conv padding) are staged by TMA into two buffer sets with mbarriers, the next image's tiles
 //     are in flight while the current one is processed.
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -41,6 +42,12 @@ __device__ __forceinline__ void transform_tile(uint8_t* tile, int TH_, int TW_, 
   *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(s_par + pch * 8 + 4);
   *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(s_par + CB + pch * 8);
   *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(s_par + CB + pch * 8 + 4);
+#if !CVB_SILU_EXP
+  if (XMODE == CVB_A_AFF_SILU) {  // silu(z) = h + h * tanh(h), h = z / 2: fold the 1/2 into the affine parameters
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] *= 0.5f; sh[j] *= 0.5f; }
+  }
+#endif
   for (int ih = warp; ih < TH_; ih += NTHR / 32) {
     const int h = h_base + ih;
     if (h < 0 || h >= H) continue;
@@ -48,14 +55,22 @@ __device__ __forceinline__ void transform_tile(uint8_t* tile, int TH_, int TW_, 
       const int w = w_base + jw;
       if (w < 0 || w >= W) continue;
       uint4* ptr = reinterpret_cast<uint4*>(tile + (ih * TW_ + jw) * 128 + (pch << 4));
-      float f[8];
-      unpack8(*ptr, f);
+      const uint4 raw = *ptr;
+      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t ow[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(sc[j], f[j], sh[j]);
-        f[j] = (XMODE == CVB_A_AFF_SILU) ? silu_f(z) : z;
+      for (int j = 0; j < 4; ++j) {  // packed fp32 pairs: 2 FFMA2 + 2 MUFU per channel pair
+        float2 z = ffma2(make_float2(sc[2 * j], sc[2 * j + 1]), up2(rw[j]), make_float2(sh[2 * j], sh[2 * j + 1]));
+        if (XMODE == CVB_A_AFF_SILU) {
+#if CVB_SILU_EXP
+          z = make_float2(silu_f(z.x), silu_f(z.y));
+#else
+          z = ffma2(z, make_float2(tanh_approx_f(z.x), tanh_approx_f(z.y)), z);
+#endif
+        }
+        ow[j] = pack_bf162(z.x, z.y);
       }
-      *ptr = pack8(f);
+      *ptr = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
 }
@@ -110,6 +125,7 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
   float2 cs = make_float2(0.f, 0.f), cq = make_float2(0.f, 0.f);
   const int strips_w = TW / SEG;
   const int n_strips = (TH / R) * strips_w;
+  const bool interior = (oh0 + TH <= Ho) && (ow0 + TW <= Wo) && (c0 + CB <= p.C);  // uniform per CTA
   __syncthreads();  // s_xp visible
 
   for (int i = 0; i < n_img; ++i) {
@@ -121,6 +137,10 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
       __syncthreads();
     }
     bf16* __restrict__ Y = static_cast<bf16*>(p.Y) + (size_t)b * Ho * Wo * p.C + cl;
+    // interior tiles (every output pixel and channel of the tile exists): no per-pixel predicates, statistics straight from the fp32
+    // accumulators (the rounding error of the stored bf16 averages out over the >= 10^5 values per channel, as in the tcgen05 GEMM epilogue)
+    auto strips = [&](auto interior_tag) {
+    constexpr bool INTERIOR = decltype(interior_tag)::value;
     for (int st = warp; st < n_strips; st += NT / 32) {
       const int orow = (st / strips_w) * R, ocol = (st % strips_w) * SEG;  // tile-local output origin of the strip
       const int irow = orow * S, icol = ocol * S;                         // tile-local input origin (halo included)
@@ -156,17 +176,26 @@ __global__ void __launch_bounds__(NT, 2) dw_fwd_kernel(const __grid_constant__ C
           for (int u = 0; u < 3; ++u)
 #pragma unroll
             for (int v = 0; v < 3; ++v) acc = ffma2(wv[u * 3 + v], win[r + u][v], acc);
-          const bool ok = (oh0 + orow + r < Ho) && (gw < Wo) && lane_ok;
           const uint32_t pk = pack_bf162(acc.x, acc.y);
-          float2 rv = up2(pk);  // statistics of the stored (rounded) values; branch-free, only the store is predicated
-          rv.x = ok ? rv.x : 0.f;
-          rv.y = ok ? rv.y : 0.f;
-          cs = fadd2(cs, rv);
-          cq = ffma2(rv, rv, cq);
-          if (ok) *reinterpret_cast<uint32_t*>(yrow[r] + (size_t)x * p.C) = pk;
+          if (INTERIOR) {
+            cs = fadd2(cs, acc);
+            cq = ffma2(acc, acc, cq);
+            *reinterpret_cast<uint32_t*>(yrow[r]) = pk;
+          } else {
+            const bool ok = (oh0 + orow + r < Ho) && (gw < Wo) && lane_ok;
+            float2 rv = up2(pk);  // branch-free, only the store is predicated
+            rv.x = ok ? rv.x : 0.f;
+            rv.y = ok ? rv.y : 0.f;
+            cs = fadd2(cs, rv);
+            cq = ffma2(rv, rv, cq);
+            if (ok) *reinterpret_cast<uint32_t*>(yrow[r]) = pk;
+          }
+          yrow[r] += p.C;
         }
       }
     }
+    };
+    if (interior) strips(std::true_type{}); else strips(std::false_type{});
     __syncthreads();  // every thread is done with this buffer
     if (tid == 0 && i + 2 < n_img) {
       fence_proxy_async();  // order the generic-proxy accesses above before the async-proxy overwrite
@@ -222,11 +251,19 @@ __device__ __forceinline__ PixOut load_x(const uint8_t* sX, int pix, int lane, f
   if (!ok) o.a = make_float2(0.f, 0.f);  // pixels past the image edge must not reach dW
   return o;
 }
-template <int XMODE>
+template <int XMODE, bool INTERIOR>
 __device__ __forceinline__ void finish_pixel(float2 d, const PixOut& o, float2& cs, float2& cq, bf16* dst, bool ok) {
-  // branch-free: out-of-image pixels / channels contribute zeros to the statistics and only the store is predicated
   if (XMODE == CVB_A_AFF_SILU) d = fmul2(d, o.dact);
   const uint32_t pk = pack_bf162(d.x, d.y);
+  if (INTERIOR) {  // whole tile inside the image: no predicates; statistics from the fp32 values (rounding averages out over the channel)
+    if (XMODE != CVB_A_RAW) {
+      cs = fadd2(cs, d);
+      cq = ffma2(d, o.xr, cq);
+    }
+    *reinterpret_cast<uint32_t*>(dst) = pk;
+    return;
+  }
+  // branch-free: out-of-image pixels / channels contribute zeros to the statistics and only the store is predicated
   if (XMODE != CVB_A_RAW) {
     float2 rv = up2(pk);
     rv.x = ok ? rv.x : 0.f;
@@ -310,6 +347,7 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
   float2 cs = make_float2(0.f, 0.f), cq = make_float2(0.f, 0.f);
   const int strips_w = TW / SEG;
   const int n_strips = (S == 1 ? TH / 2 : TH) * strips_w;
+  const bool interior = (xh_base + XH <= p.H) && (xw_base + XW <= p.W) && (c0 + CB <= p.C);  // uniform per CTA: the whole input tile exists
   __syncthreads();  // s_gp visible
 
   for (int i = 0; i < n_img; ++i) {
@@ -337,12 +375,16 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
             if (ow < 0 || ow >= Wo) continue;
             const int off = (gi * GW + gj) * 128 + (pch << 4);
             uint4* pz = reinterpret_cast<uint4*>(sG + off);
-            float f[8], y[8];
-            unpack8(*pz, f);
-            unpack8(*reinterpret_cast<const uint4*>(sY2 + off), y);
+            const uint4 zr = *pz, yr = *reinterpret_cast<const uint4*>(sY2 + off);
+            const uint32_t zw[4] = {zr.x, zr.y, zr.z, zr.w}, yw[4] = {yr.x, yr.y, yr.z, yr.w};
+            uint32_t o4[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(g0[j], f[j], fmaf(g1[j], y[j], g2[j]));
-            *pz = pack8(f);
+            for (int j = 0; j < 4; ++j) {  // packed fp32 pairs
+              const float2 t = ffma2(make_float2(g1[2 * j], g1[2 * j + 1]), up2(yw[j]), make_float2(g2[2 * j], g2[2 * j + 1]));
+              const float2 v = ffma2(make_float2(g0[2 * j], g0[2 * j + 1]), up2(zw[j]), t);
+              o4[j] = pack_bf162(v.x, v.y);
+            }
+            *pz = make_uint4(o4[0], o4[1], o4[2], o4[3]);
           }
         }
       }
@@ -354,6 +396,8 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
     }
     // ---- 2. the walk
     bf16* __restrict__ DX = static_cast<bf16*>(p.DX) + (size_t)b * p.H * p.W * p.C + cl;
+    auto strips = [&](auto interior_tag) {
+    constexpr bool INTERIOR = decltype(interior_tag)::value;
     for (int st = warp; st < n_strips; st += NTB / 32) {
       const int scol = (st % strips_w) * SEG;
       if (S == 1) {
@@ -372,7 +416,7 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             const int h = oh0 + r0 + r;
-            const bool ok = (h < p.H) && (w < p.W) && lane_ok;
+            const bool ok = INTERIOR || ((h < p.H) && (w < p.W) && lane_ok);
             const PixOut o = load_x<XMODE>(sX, (r0 + r) * XW + scol + x, lane, xsc, xsh, ok);
             float2 d = make_float2(0.f, 0.f);
             // dyn[u][v] = dy[h+1-u][w+1-v] = win[r+2-u][2-v]
@@ -383,7 +427,8 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
                 d = ffma2(wv[u * 3 + v], win[r + 2 - u][2 - v], d);
                 accw[u * 3 + v] = ffma2(o.a, win[r + 2 - u][2 - v], accw[u * 3 + v]);
               }
-            finish_pixel<XMODE>(d, o, cs, cq, dxrow[r] + (size_t)x * p.C, ok);
+            finish_pixel<XMODE, INTERIOR>(d, o, cs, cq, dxrow[r], ok);
+            dxrow[r] += p.C;
           }
         }
       } else {
@@ -400,34 +445,34 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
           const int xp = (2 * i0) * XW + 2 * (scol + x);
           bf16* dx0 = dxrow0 + (size_t)(2 * x) * p.C;
           bf16* dx1 = dx0 + (size_t)p.W * p.C;
-          const bool ok0 = hh < p.H, ok1 = hh + 1 < p.H, okc0 = ww < p.W, okc1 = ww + 1 < p.W;
+          const bool ok0 = INTERIOR || hh < p.H, ok1 = INTERIOR || hh + 1 < p.H, okc0 = INTERIOR || ww < p.W, okc1 = INTERIOR || ww + 1 < p.W;
           {  // (2i, 2j)
-            const bool ok = ok0 && okc0 && lane_ok;
+            const bool ok = INTERIOR || (ok0 && okc0 && lane_ok);
             const PixOut o = load_x<XMODE>(sX, xp, lane, xsc, xsh, ok);
             float2 d = fmul2(wv[4], win[0][0]);
             accw[4] = ffma2(o.a, win[0][0], accw[4]);
-            finish_pixel<XMODE>(d, o, cs, cq, dx0, ok);
+            finish_pixel<XMODE, INTERIOR>(d, o, cs, cq, dx0, ok);
           }
           {  // (2i, 2j+1)
-            const bool ok = ok0 && okc1 && lane_ok;
+            const bool ok = INTERIOR || (ok0 && okc1 && lane_ok);
             const PixOut o = load_x<XMODE>(sX, xp + 1, lane, xsc, xsh, ok);
             float2 d = fmul2(wv[3], win[0][1]);
             d = ffma2(wv[5], win[0][0], d);
             accw[3] = ffma2(o.a, win[0][1], accw[3]);
             accw[5] = ffma2(o.a, win[0][0], accw[5]);
-            finish_pixel<XMODE>(d, o, cs, cq, dx0 + p.C, ok);
+            finish_pixel<XMODE, INTERIOR>(d, o, cs, cq, dx0 + p.C, ok);
           }
           {  // (2i+1, 2j)
-            const bool ok = ok1 && okc0 && lane_ok;
+            const bool ok = INTERIOR || (ok1 && okc0 && lane_ok);
             const PixOut o = load_x<XMODE>(sX, xp + XW, lane, xsc, xsh, ok);
             float2 d = fmul2(wv[1], win[1][0]);
             d = ffma2(wv[7], win[0][0], d);
             accw[1] = ffma2(o.a, win[1][0], accw[1]);
             accw[7] = ffma2(o.a, win[0][0], accw[7]);
-            finish_pixel<XMODE>(d, o, cs, cq, dx1, ok);
+            finish_pixel<XMODE, INTERIOR>(d, o, cs, cq, dx1, ok);
           }
           {  // (2i+1, 2j+1)
-            const bool ok = ok1 && okc1 && lane_ok;
+            const bool ok = INTERIOR || (ok1 && okc1 && lane_ok);
             const PixOut o = load_x<XMODE>(sX, xp + XW + 1, lane, xsc, xsh, ok);
             float2 d = fmul2(wv[0], win[1][1]);
             d = ffma2(wv[2], win[1][0], d);
@@ -437,11 +482,13 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
             accw[2] = ffma2(o.a, win[1][0], accw[2]);
             accw[6] = ffma2(o.a, win[0][1], accw[6]);
             accw[8] = ffma2(o.a, win[0][0], accw[8]);
-            finish_pixel<XMODE>(d, o, cs, cq, dx1 + p.C, ok);
+            finish_pixel<XMODE, INTERIOR>(d, o, cs, cq, dx1 + p.C, ok);
           }
         }
       }
     }
+    };
+    if (interior) strips(std::true_type{}); else strips(std::false_type{});
     __syncthreads();  // every thread is done with this buffer set
     if (tid == 0 && i + 2 < n_img) {
       fence_proxy_async();
