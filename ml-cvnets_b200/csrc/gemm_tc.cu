@@ -29,7 +29,10 @@ constexpr int TC_EPI_WARPS = 16;            // four warps per TMEM lane quadrant
                                             // epilogue, not HBM, bounded round 1's kernel (2 warps / scheduler, ~3000 cycles per tile)
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
-constexpr int TC_XF_THREADS = 128;          // transform warps (only launched for layers with a prologue)
+constexpr int TC_XF_THREADS = 256;          // transform warps (only launched for layers with a prologue).  Each warp is a latency-bound
+                                            // chain (LDS -> convert -> FMA -> MUFU -> pack -> STS): with 4 warps the MMA issuer spent most of its
+                                            // time waiting for transformed stages (ncu source view, round 2), so the prologue layers run 8
+constexpr int TC_XF_IT = (TC_BM * 4) / TC_XF_THREADS;  // 16-byte chunks of a [128 x 32] bf16 stage per transform thread
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_TMEM_COLS = 256;             // 2 accumulators x 128 fp32 columns
 
@@ -81,7 +84,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // WRES: the weight panel [128 ch, K] stays resident in smem (loaded once); otherwise (large K) its k-blocks stream through the
 // ring next to the activation k-blocks (they are L2 hits: every CTA of an N tile reads the same panel).
 template <int AMODE, int EPI, bool WRES>
-__global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS + (AMODE != CVB_A_RAW ? TC_XF_THREADS : 0), 1)
     pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
                       const cvb_gemm_args p, int NST) {
   constexpr bool XF = (AMODE != CVB_A_RAW);     // has transform warps
@@ -181,7 +184,9 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
         }
         asm volatile("bar.sync 2, %0;" ::"n"(TC_XF_THREADS) : "memory");
       }
-      float tmu[4] = {0.f, 0.f, 0.f, 0.f}, trs[4] = {1.f, 1.f, 1.f, 1.f};
+      float tmu[TC_XF_IT], trs[TC_XF_IT];
+#pragma unroll
+      for (int i = 0; i < TC_XF_IT; ++i) { tmu[i] = 0.f; trs[i] = 1.f; }
       for (int it = 0; it < total; ++it) {
         const int stage = it % NST;
         const int j = it / KT, kt = it - j * KT;
@@ -189,8 +194,8 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
         const int k0 = kt * TC_BK;
         if (AMODE == CVB_A_GN && kt == 0) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int m = m0 + (tt >> 2) + i * 32;
+          for (int i = 0; i < TC_XF_IT; ++i) {
+            const int m = m0 + (tt >> 2) + i * (TC_XF_THREADS / 4);
             const int b = (m < p.M ? m : p.M - 1) / p.rows_per_sample;
             tmu[i] = __ldg(p.row_mean + b);
             trs[i] = __ldg(p.row_rstd + b);
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS + TC_XF_THREADS, 1)
         mbar_wait(&full[stage], (it / NST) & 1);
         uint8_t* st = sA + stage * RING_STAGE;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < TC_XF_IT; ++i) {
           const int c = tt + i * TC_XF_THREADS;
           const int row = c >> 2, ch = c & 3;
           const int k = k0 + ch * 8;
