@@ -48,18 +48,13 @@ __device__ __forceinline__ void transform_tile(uint8_t* tile, int TH_, int TW_, 
     for (int j = 0; j < 8; ++j) { sc[j] *= 0.5f; sh[j] *= 0.5f; }
   }
 #endif
-  // pixels are dealt round-robin over ALL threads (a per-row split of an 18-row tile over 8 warps leaves a third of the pass idle at the
-  // barrier that follows)
-  int jw = (warp << 2) + (lane >> 3), ih = 0;
-  while (jw >= TW_) { jw -= TW_; ++ih; }
-  for (; ih < TH_;) {
-    const int h = h_base + ih, w = w_base + jw;
-    const int ih_c = ih, jw_c = jw;
-    jw += NTHR / 8;
-    while (jw >= TW_) { jw -= TW_; ++ih; }
-    if (h < 0 || h >= H || w < 0 || w >= W) continue;
-    {
-      uint4* ptr = reinterpret_cast<uint4*>(tile + (ih_c * TW_ + jw_c) * 128 + (pch << 4));
+  for (int ih = warp; ih < TH_; ih += NTHR / 32) {
+    const int h = h_base + ih;
+    if (h < 0 || h >= H) continue;
+    for (int jw = lane >> 3; jw < TW_; jw += 4) {
+      const int w = w_base + jw;
+      if (w < 0 || w >= W) continue;
+      uint4* ptr = reinterpret_cast<uint4*>(tile + (ih * TW_ + jw) * 128 + (pch << 4));
       const uint4 raw = *ptr;
       const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
       uint32_t ow[4];
@@ -372,15 +367,12 @@ __global__ void __launch_bounds__(NTB, 1) dw_bwd_kernel(const __grid_constant__ 
           *reinterpret_cast<float4*>(g1 + 4 * q) = *reinterpret_cast<const float4*>(s_gp + CB + pch * 8 + 4 * q);
           *reinterpret_cast<float4*>(g2 + 4 * q) = *reinterpret_cast<const float4*>(s_gp + 2 * CB + pch * 8 + 4 * q);
         }
-        int gj_n = (warp << 2) + (lane >> 3), gi_n = 0;  // pixels round-robin over all threads (see transform_tile)
-        while (gj_n >= GW) { gj_n -= GW; ++gi_n; }
-        for (; gi_n < GH;) {
-          const int gi = gi_n, gj = gj_n;
-          gj_n += NTB / 8;
-          while (gj_n >= GW) { gj_n -= GW; ++gi_n; }
-          const int oh = gh_base + gi, ow = gw_base + gj;
-          if (oh < 0 || oh >= Ho || ow < 0 || ow >= Wo) continue;
-          {
+        for (int gi = warp; gi < GH; gi += NTB / 32) {
+          const int oh = gh_base + gi;
+          if (oh < 0 || oh >= Ho) continue;
+          for (int gj = lane >> 3; gj < GW; gj += 4) {
+            const int ow = gw_base + gj;
+            if (ow < 0 || ow >= Wo) continue;
             const int off = (gi * GW + gj) * 128 + (pch << 4);
             uint4* pz = reinterpret_cast<uint4*>(sG + off);
             const uint4 zr = *pz, yr = *reinterpret_cast<const uint4*>(sY2 + off);

@@ -29,10 +29,16 @@ constexpr int TC_EPI_WARPS = 16;            // four warps per TMEM lane quadrant
                                             // epilogue, not HBM, bounded round 1's kernel (2 warps / scheduler, ~3000 cycles per tile)
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
-constexpr int TC_XF_THREADS = 256;          // transform warps (only launched for layers with a prologue).  Each warp is a latency-bound
+constexpr int TC_XF_THREADS_MAX = 256;      // transform warps (only launched for layers with a prologue).  Each warp is a latency-bound
                                             // chain (LDS -> convert -> FMA -> MUFU -> pack -> STS): with 4 warps the MMA issuer spent most of its
                                             // time waiting for transformed stages (ncu source view, round 2), so the prologue layers run 8
-constexpr int TC_XF_IT = (TC_BM * 4) / TC_XF_THREADS;  // 16-byte chunks of a [128 x 32] bf16 stage per transform thread
+                                            // (same-box A/B: AFF_SILU 100.9 -> 85.9 us, GN 48.3 -> 43.4 us); the BNB prologue (two operand
+                                            // tiles per stage, SiLU-backward epilogue) was 4 % faster with 4 and keeps them
+template <int AMODE>
+struct XfCfg {
+  static constexpr int THREADS = (AMODE == CVB_A_RAW) ? 0 : (AMODE == CVB_A_BNB ? 128 : TC_XF_THREADS_MAX);
+  static constexpr int IT = THREADS ? (TC_BM * 4) / THREADS : 1;  // 16-byte chunks of a [128 x 32] bf16 stage per transform thread
+};
 constexpr int TC_MAX_STAGES = 12;
 constexpr int TC_TMEM_COLS = 256;             // 2 accumulators x 128 fp32 columns
 
@@ -84,7 +90,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // WRES: the weight panel [128 ch, K] stays resident in smem (loaded once); otherwise (large K) its k-blocks stream through the
 // ring next to the activation k-blocks (they are L2 hits: every CTA of an N tile reads the same panel).
 template <int AMODE, int EPI, bool WRES>
-__global__ void __launch_bounds__(TC_THREADS + (AMODE != CVB_A_RAW ? TC_XF_THREADS : 0), 1)
+__global__ void __launch_bounds__(TC_THREADS + XfCfg<AMODE>::THREADS, 1)
     pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW,
                       const cvb_gemm_args p, int NST) {
   constexpr bool XF = (AMODE != CVB_A_RAW);     // has transform warps
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS + (AMODE != CVB_A_RAW ? TC_XF_THREA
   __shared__ double s_samp[2][128];
 
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], TC_XF_THREADS / 32); }
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], XfCfg<AMODE>::THREADS ? XfCfg<AMODE>::THREADS / 32 : 1); }
     mbar_init(&wbar, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_mbar_init();
@@ -173,7 +179,9 @@ __global__ void __launch_bounds__(TC_THREADS + (AMODE != CVB_A_RAW ? TC_XF_THREA
   } else if (warp >= 2 + TC_EPI_WARPS) {
     // ===================================================== transform warps: producer's normalisation / activation, in place
     if (XF) {
-      const int tt = tid - TC_THREADS;  // 0..127
+      constexpr int TC_XF_THREADS = XfCfg<AMODE>::THREADS > 0 ? XfCfg<AMODE>::THREADS : 128;
+      constexpr int TC_XF_IT = XfCfg<AMODE>::IT;
+      const int tt = tid - TC_THREADS;  // 0..TC_XF_THREADS-1
       const int Kpad = KT * TC_BK;
       if (HAS_P) {
         for (int k = tt; k < Kpad; k += TC_XF_THREADS) {
@@ -424,7 +432,7 @@ int launch_tc_impl(const cvb_gemm_args& a, cudaStream_t st, size_t fixed, int st
   if (cvb_make_tmap_2d_k32(&tmA2, AMODE == CVB_A_BNB ? a.A2 : a.A, a.M, a.K, AMODE == CVB_A_BNB ? a.lda2 : a.lda, TC_BM)) return 1;
   if (cvb_make_tmap_2d_k32(&tmW, a.W, a.N, a.K, a.ldw, TC_BN)) return 1;
   dim3 grid(n_tiles, gy);
-  const int threads = TC_THREADS + (AMODE != CVB_A_RAW ? TC_XF_THREADS : 0);
+  const int threads = TC_THREADS + XfCfg<AMODE>::THREADS;
   CVB_CUDA(cvb_launch(pw_gemm_tc_kernel<AMODE, EPI, WRES>, grid, threads, smem, st, tmA, tmA2, tmW, a, nst));
   CVB_LAUNCH_CHECK();
   return 0;

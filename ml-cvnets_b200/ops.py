@@ -98,7 +98,11 @@ def set_pdl_enabled(on: bool) -> bool:
 
 
 # --------------------------------------------------------------------------------------------------------------- GEMM
-WIDE_K = int(os.environ.get("CVB_WIDE_K", "384"))  # wide-layer policy threshold (diagnostics: CVB_WIDE_K=100000 disables the pre-pass)
+# wide-layer policy: when the prologue would be re-applied by MANY N tiles (ViT / CLIP: K = 768 / 3072 under 18-24 N tiles) it is applied once
+# by a pre-pass instead.  With 8 transform warps the in-kernel prologue won on every MobileViTv2 layer (same-box A/B: 12.47 -> 12.23 ms per
+# step without the pre-pass), so the policy now needs N >= WIDE_N as well.  CVB_WIDE_K=100000 disables the pre-pass (diagnostics).
+WIDE_K = int(os.environ.get("CVB_WIDE_K", "384"))
+WIDE_N = int(os.environ.get("CVB_WIDE_N", "1024"))
 
 
 def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: int = A_RAW, A2: Optional[Tensor] = None,
@@ -110,7 +114,7 @@ def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: in
     lib = _lib()
     M = A.shape[0]
     K = A.shape[1] if K is None else K
-    if a_mode != A_RAW and K >= WIDE_K and N > 128:
+    if a_mode != A_RAW and K >= WIDE_K and N >= WIDE_N:
         # wide late-stage layer (small, L2-resident operand): apply the prologue once instead of once per N tile, then run the
         # prologue-free (tcgen05) GEMM
         A = apply_load_mode(A, a_mode, K, A2=A2, a_p=a_p, row_stats=row_stats, rows_per_sample=rows_per_sample)
