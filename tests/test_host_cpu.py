@@ -118,6 +118,23 @@ assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
 ours.load_state_dict(ref.state_dict(), strict=True)
 assert type(ours.layer_3[1]).__module__.startswith("ml_cvnets_b200")
 g, _ = ours.get_trainable_parameters(weight_decay=0.05, no_decay_bn_filter_bias=True)
+import ml_cvnets_b200 as m
+assert type(ours).forward is m.MobileViTv2.forward and type(ours).extract_end_points_all is m.MobileViTv2.extract_end_points_all
+assert len(ours._chain) == 10 and ours.fuse_boundaries and ours._chain[0] is ours.conv_1          # private state of the B200 model travels
+seg = get_model(opts.__class__(**{**vars(opts), "model.classification.name": "mobilevit_v2_b200"}), category="classification", output_stride=8)
+assert seg.layer_5[1].local_rep[0].block.conv.dilation == (4, 4)                                   # segmentation heads: output_stride is honoured
+# the other registered assemblers: same keys / shapes as the reference models they replace
+for ours_name, ref_name, extra in (("mobilevit_b200", "mobilevit", {"model.classification.mit.mode": "xx_small"}),
+                                   ("vit_b200", "vit", {"model.classification.vit.mode": "tiny", "model.classification.vit.norm_layer": "layer_norm_fp32",
+                                                        "model.activation.name": "gelu", "model.classification.activation.name": "gelu"})):
+    for k, v in extra.items():
+        setattr(opts, k, v)
+    setattr(opts, "model.classification.name", ours_name)
+    a = get_model(opts)
+    setattr(opts, "model.classification.name", ref_name)
+    b = get_model(opts)
+    assert {k: tuple(v.shape) for k, v in a.state_dict().items()} == {k: tuple(v.shape) for k, v in b.state_dict().items()}, ours_name
+    a.load_state_dict(b.state_dict(), strict=True)
 print("OK", sum(p.numel() for p in ours.parameters()), [len(x["params"]) for x in g])
 """ % REPO
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
