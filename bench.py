@@ -508,9 +508,12 @@ def run_ours(args, rank, world, local_rank):
         optimer.install()
     sampler = ClockSampler(local_rank)
     # ---------------- timed region 1: inputs resident in HBM
-    sync_all()
+    # The sampler is started BEFORE the barrier: spawning nvidia-smi takes 10-100 ms of host time on rank 0; after the barrier that delay made
+    # every other rank wait at its first all-reduce inside ITS timed region (max over ranks then reported 33.3 ms/step for steps that took
+    # 27.9 ms on every rank -- the N = 8 inconsistency of round 1 as well).
     if rank == 0:
         sampler.start()
+    sync_all()
     timer.enabled = not args.no_kernel_timing and not use_graph
     launches0 = ops.launch_count
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -526,7 +529,9 @@ def run_ours(args, rank, world, local_rank):
     sync_all()
     per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
     step_stats = {"min": per_step[0], "median": per_step[len(per_step) // 2], "p90": per_step[min(len(per_step) - 1, int(0.9 * len(per_step)))],
-                  "max": per_step[-1], "note": "this rank's CUDA-event time of each timed step"}
+                  "max": per_step[-1], "note": "rank 0's CUDA-event time of each timed step"}
+    if world > 1:  # slowest rank's view of the same statistics (a straggler shows up here, not only in the max-over-ranks total)
+        step_stats["max_over_ranks"] = {"median": max_over_ranks(step_stats["median"]), "max": max_over_ranks(step_stats["max"])}
     timer.enabled = False
     launches = (launches_per_graph * args.steps) if use_graph else (ops.launch_count - launches0)
     op_ms = optimer.summary(args.steps) if optimer is not None else None
@@ -765,9 +770,9 @@ def run_vit(args, rank, world, local_rank):
         for _ in range(5):
             ts.step(x_dev, y_dev)
     sampler = ClockSampler(local_rank)
-    sync_all()
     if rank == 0:
-        sampler.start()
+        sampler.start()  # before the barrier (see run_ours)
+    sync_all()
     n0 = ops.launch_count
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     marks[0].record()
