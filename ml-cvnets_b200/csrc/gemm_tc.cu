@@ -16,6 +16,7 @@
 // shuffles, no smem atomics) and are flushed with one fp64 atomic per channel per CTA.  The epilogue of tile j overlaps the
 // MMAs of tile j+1 and the TMA loads of tiles j+2...
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -356,21 +357,6 @@ __global__ void __launch_bounds__(TC_THREADS + XfCfg<AMODE>::THREADS, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);  // one arrival per epilogue warp releases the accumulator
-      if (!has_aux && !want_samp) {
-        // plain store epilogue (every forward conv): the 32 channels x 32 pixels this warp drained sit in a region of the staging tile
-        // that no other warp touches, so the warp copies its own block out -- no CTA-wide barrier on the path (the two barriers per tile
-        // were 11 % of the stall samples of the largest layer).  Quarter-warps read 8 different rows (16-byte bank groups 0..7: conflict
-        // free with the 272-byte row stride) and every row segment is two full 32-byte sectors in global memory.
-#pragma unroll
-        for (int t4 = 0; t4 < 4; ++t4) {
-          const int row = cquart * 32 + (lane & 7) + 8 * t4, cgc = quad * 4 + (lane >> 3);
-          const int m = m0 + row, n = n0 + cgc * 8;
-          const uint4 u = *reinterpret_cast<const uint4*>(sO + row * (TC_LDO * 2) + cgc * 16);
-          if (m < p.M && n < p.N) stg16(Cg + (size_t)m * p.ldc + n, u);
-        }
-        __syncwarp();  // the block is free for this warp's next tile
-        continue;
-      }
       epi_bar_sync();                            // staged tile complete
       const int first_sample = m0 / rps;
       for (int c = et; c < TC_BM * CGS; c += TC_EPI_THREADS) {
@@ -521,7 +507,8 @@ int dispatch_tc_epi(const cvb_gemm_args& a, cudaStream_t st) {
 // Returns -1 when the shape / mode is not handled by the tcgen05 kernel (caller uses the mma.sync kernel), 0 on success, > 0 on error.
 int cvb_pw_gemm_tc(const cvb_gemm_args& a, cudaStream_t st) {
   // every epilogue thread owns one of 128 output channels: narrow layers would idle most of them -> mma.sync kernel
-  if (a.N < 96 || (a.N % 128 != 0 && a.N % 128 < 64 && a.N < 256)) return -1;  // N = 64 on this kernel measured slower than mma.sync
+  static const int min_n = [] { const char* e = getenv("CVB_TC_MIN_N"); return e ? atoi(e) : 96; }();  // diagnostics: route narrower layers here
+  if (a.N < min_n || (a.N >= 96 && a.N % 128 != 0 && a.N % 128 < 64 && a.N < 256)) return -1;  // N = 64 on this kernel measured slower than mma.sync (round 1)
   switch (a.a_mode) {
     case CVB_A_RAW: return dispatch_tc_epi<CVB_A_RAW>(a, st);
     case CVB_A_AFF: return dispatch_tc_epi<CVB_A_AFF>(a, st);
