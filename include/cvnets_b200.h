@@ -31,7 +31,7 @@ typedef void* cvb_stream_t; /* cudaStream_t */
 #define CVB_API
 #endif
 
-#define CVB_ABI_VERSION 8
+#define CVB_ABI_VERSION 9
 
 /* operand "load modes": the normalisation / activation of the PRODUCER layer is applied while the CONSUMER loads it
  * (training-mode BatchNorm cannot be fused into its own conv: SURVEY.md section 7 "hard parts"). */
@@ -239,13 +239,18 @@ CVB_API int cvb_linattn_cross_bwd(const void* QK_prev, int ldq, const void* V_x,
  * QKV: bf16 [B*S, ldq] rows = tokens, columns [q (H*c) | k (H*c) | v (H*c)] exactly as qkv_proj writes them (:148-153);
  * O: bf16 [B*S, ldo] with head h at columns h*c.. (the layout out_proj reads, :236).  scale = head_dim^-0.5 (:70, :187).
  * attn_mask: fp32 [B, S, S] additive (or NULL, :197-208); key_padding_mask: uint8 [B, S], non-zero = masked with -inf (:210-224).
- * Softmax in fp32 (:226-228).  LSE: fp32 [B, H, S] log-sum-exp (base 2) saved for the backward.  S <= 256, c in {16, 32, 64}.
+ * Softmax in fp32 (:226-228).  LSE: fp32 [B, H, S] log-sum-exp (base 2) saved for the backward.  S <= 256, even c <= 64.
+ * head_dim == 64 (ViT-B, CLIP text) runs on tcgen05 tensor cores (mha_tc.cu: TMA-staged operands, scores in TMEM, one thread per query
+ * row); every other head_dim on the mma.sync kernels (mha.cu).
  * ------------------------------------------------------------------------------------------------------------- */
 CVB_API int cvb_mha_fwd(const void* QKV, int ldq, int B, int S, int H, int head_dim, float scale, const float* attn_mask,
                 const unsigned char* key_padding_mask, void* O, int ldo, float* LSE, cvb_stream_t stream);
 /* dQKV (bf16 [B*S, lddq], same column layout as QKV) from dO; recomputes the probabilities from LSE. */
 CVB_API int cvb_mha_bwd(const void* QKV, int ldq, const void* O, const void* DO, int ldo, const float* LSE, int B, int S, int H, int head_dim,
                 float scale, const float* attn_mask, const unsigned char* key_padding_mask, void* DQKV, int lddq, cvb_stream_t stream);
+/* Diagnostics / A-B timing: which head_dim == 64 implementation runs.  bit 0: tcgen05 forward, bit 1: tcgen05 backward (default 3; the
+ * environment variable CVB_MHA_TC sets the initial value).  Returns the previous mask. */
+CVB_API int cvb_set_mha_impl(int mask);
 /* per-token LayerNorm statistics of a bf16 [M, C] matrix: mean[m], rstd[m] = 1/sqrt(var + eps) (biased variance, fp32 math like
  * nn.LayerNorm under autocast).  The normalisation itself is the GN load mode of the consuming GEMM with rows_per_sample = 1. */
 /* LayerNorm backward of a [M, C] token matrix in one pass (autograd of nn.LayerNorm as used at transformer.py:77-95):

@@ -13,7 +13,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CVB_LIB: diagnostics only (A/B of two kernel builds on the same GPU box, tools/build_variant.sh); the product loads the in-tree library
 LIB_PATH = os.environ.get("CVB_LIB") or os.path.join(_HERE, "csrc", "libcvnets_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # load modes / epilogue modes (mirror include/cvnets_b200.h)
 A_RAW, A_AFF, A_AFF_SILU, A_SILU, A_GN, A_BNB = 0, 1, 2, 3, 4, 5
@@ -88,6 +88,7 @@ _SIGS = {
     "cvb_pw_gemm": (c_int, [POINTER(GemmArgs), c_void_p]),
     "cvb_set_tc_enabled": (c_int, [c_int]),
     "cvb_set_pdl_enabled": (c_int, [c_int]),
+    "cvb_set_mha_impl": (c_int, [c_int]),
     "cvb_pw_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
     "cvb_apply_load_mode": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                     c_int, c_int64, c_int, c_void_p]),

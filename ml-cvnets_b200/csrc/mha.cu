@@ -412,11 +412,21 @@ int check_common(const char* who, const void* QKV, int ldq, int B, int S, int H,
 
 }  // namespace
 
+// head_dim == 64: tcgen05 kernels (mha_tc.cu); -1 = not handled there
+int cvb_mha_fwd_tc(const void* QKV, int ldq, int B, int S, int H, int head_dim, float scale, const float* amask, const unsigned char* kpm, void* O,
+                   int ldo, float* LSE, cudaStream_t st);
+int cvb_mha_bwd_tc(const void* QKV, int ldq, const void* O, const void* DO, int ldo, const float* LSE, int B, int S, int H, int head_dim, float scale,
+                   const float* amask, const unsigned char* kpm, void* DQKV, int lddq, cudaStream_t st);
+
 extern "C" int cvb_mha_fwd(const void* QKV, int ldq, int B, int S, int H, int head_dim, float scale, const float* attn_mask,
                            const unsigned char* key_padding_mask, void* O, int ldo, float* LSE, cvb_stream_t stream) {
   if (check_common("cvb_mha_fwd", QKV, ldq, B, S, H, head_dim, ldo)) return 1;
   CVB_CHECK(O && LSE && cvb_aligned16(O), "cvb_mha_fwd: null / misaligned output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const int rc = cvb_mha_fwd_tc(QKV, ldq, B, S, H, head_dim, scale, attn_mask, key_padding_mask, O, ldo, LSE, st);
+    if (rc >= 0) return rc;
+  }
   if (head_dim <= 16) return launch_fwd<16>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st, head_dim);
   if (head_dim <= 32) return launch_fwd<32>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st, head_dim);
   return launch_fwd<64>(QKV, ldq, B, S, H, scale, attn_mask, key_padding_mask, O, ldo, LSE, st, head_dim);
@@ -428,6 +438,10 @@ extern "C" int cvb_mha_bwd(const void* QKV, int ldq, const void* O, const void* 
   CVB_CHECK(O && DO && LSE && DQKV && cvb_aligned16(O) && cvb_aligned16(DO) && cvb_aligned16(DQKV) && lddq % 8 == 0 && lddq >= 3 * H * head_dim,
             "cvb_mha_bwd: null / misaligned operand");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const int rc = cvb_mha_bwd_tc(QKV, ldq, O, DO, ldo, LSE, B, S, H, head_dim, scale, attn_mask, key_padding_mask, DQKV, lddq, st);
+    if (rc >= 0) return rc;
+  }
   if (head_dim <= 16) return launch_bwd<16>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st, head_dim);
   if (head_dim <= 32) return launch_bwd<32>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st, head_dim);
   return launch_bwd<64>(QKV, ldq, O, DO, ldo, LSE, B, S, H, scale, attn_mask, key_padding_mask, DQKV, lddq, st, head_dim);
