@@ -260,11 +260,17 @@ CVB_API int cvb_set_mha_impl(int mask);
 CVB_API int cvb_ln_bwd(const void* V, const void* X, const float* mean, const float* rstd, const float* gamma, const void* DRES, void* DX,
                int64_t M, int C, double* dgamma, double* dbeta, double* col_sum, cvb_stream_t stream);
 /* element-wise activation passes over contiguous bf16 tensors of n elements (n % 8 == 0): Y = act(X);  DX = DY * act'(X).
- * kind 0 = SiLU (cvnets/layers/activation/swish.py), 1 = GELU (cvnets/layers/activation/gelu.py: nn.GELU, erf form).  Used by the
- * TransformerEncoder FFN (cvnets/modules/transformer.py:86-95) when the activation is not the GEMM-fused SiLU. */
+ * kind 0 = SiLU (cvnets/layers/activation/swish.py), 1 = GELU (cvnets/layers/activation/gelu.py: nn.GELU, erf form), 2 = ReLU, 3 = Hardswish,
+ * 4 = Hardsigmoid, 5 = Sigmoid (cvnets/layers/activation/{relu,hard_swish,hard_sigmoid,sigmoid}.py).  Used by the TransformerEncoder FFN
+ * (cvnets/modules/transformer.py:86-95) when the activation is not the GEMM-fused SiLU, and by InvertedResidualSE / SqueezeExcitation. */
 CVB_API int cvb_act_fwd(const void* X, void* Y, int64_t n, int kind, cvb_stream_t stream);
 CVB_API int cvb_act_bwd(const void* DY, const void* X, void* DX, int64_t n, int kind, cvb_stream_t stream);
 CVB_API int cvb_ln_stats(const void* X, int ldx, int64_t M, int C, float eps, float* mean, float* rstd, cvb_stream_t stream);
+/* Squeeze-excitation channel scaling (cvnets/modules/squeeze_excitation.py:82-83, used by InvertedResidualSE, cvnets/modules/mobilenetv2.py:16-138):
+ * Y[b,p,c] = X[b,p,c] * S[b,c] on a channels-last bf16 map [B, HW, C] with the bf16 scale vector S [B, C] (C % 8 == 0, C <= 2048);
+ * backward: DX = DY * S and DS[b,c] += sum_p DY * X (fp32, zero-initialised by the caller). */
+CVB_API int cvb_se_scale_fwd(const void* X, const void* S, void* Y, int B, int HW, int C, cvb_stream_t stream);
+CVB_API int cvb_se_scale_bwd(const void* DY, const void* X, const void* S, void* DX, float* DS, int B, int HW, int C, cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Per-step tail of the training loop (engine/training_engine.py:289-312) on FLAT fp32 buffers of n elements: GradScaler unscale +

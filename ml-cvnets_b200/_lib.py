@@ -89,6 +89,8 @@ _SIGS = {
     "cvb_set_tc_enabled": (c_int, [c_int]),
     "cvb_set_pdl_enabled": (c_int, [c_int]),
     "cvb_set_mha_impl": (c_int, [c_int]),
+    "cvb_se_scale_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cvb_se_scale_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cvb_pw_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),
     "cvb_apply_load_mode": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                     c_int, c_int64, c_int, c_void_p]),

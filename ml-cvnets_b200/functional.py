@@ -842,6 +842,48 @@ class GlobalPoolFn(torch.autograd.Function):
         return to_4d(ops.global_pool_bwd(g, B, H * W), B, H, W), None
 
 
+class ActFn(torch.autograd.Function):
+    """A stand-alone activation module on a channels-last bf16 map (cvnets/layers/activation/*.py): the act_fn_1 / act_fn_2 / scale_act children of
+    InvertedResidualSE and SqueezeExcitation (cvnets/modules/mobilenetv2.py:63-92, squeeze_excitation.py:66-76).  kind: ops.ACT_*."""
+
+    @staticmethod
+    def forward(ctx, x, kind):
+        if x.numel() % 8:
+            raise NotImplementedError("activation: tensors with numel % 8 == 0")
+        ctx.kind, ctx.x = kind, x
+        y = ops.act_fwd(x, kind)
+        return y
+
+    @staticmethod
+    def backward(ctx, gout):
+        x = ctx.x
+        g = gout
+        if g.dtype != BF16 or g.stride() != x.stride():
+            g = torch.empty_like(x).copy_(gout)  # same memory layout as x: the kernel is a flat element-wise pass
+        return ops.act_bwd(g, x, ctx.kind), None
+
+
+class SeScaleFn(torch.autograd.Function):
+    """SqueezeExcitation.forward's ``x * se_layer(x)`` (cvnets/modules/squeeze_excitation.py:82-83): [B, C, H, W] map times a [B, C, 1, 1] scale."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        B, C, H, W = x.shape
+        s2 = s.reshape(B, C)
+        if s2.dtype != BF16 or not s2.is_contiguous():
+            s2 = s2.to(BF16).contiguous()
+        x2 = as_2d(x)
+        ctx.saved, ctx.dims = (x2, s2), (B, C, H, W)
+        return to_4d(ops.se_scale_fwd(x2, s2, B, H * W), B, H, W)
+
+    @staticmethod
+    def backward(ctx, gout):
+        B, C, H, W = ctx.dims
+        x2, s2 = ctx.saved
+        dx, ds = ops.se_scale_bwd(as_2d(to_bf16_cl(gout)), x2, s2, B, H * W)
+        return to_4d(dx, B, H, W), ds.view(B, C, 1, 1)
+
+
 class UnfoldFn(torch.autograd.Function):
     """MobileViTBlock.unfolding (cvnets/modules/mobilevit_block.py:186-231): [B, C, H, W] -> [B*P, N, C] tokens (a row permutation)."""
 

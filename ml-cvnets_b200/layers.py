@@ -127,6 +127,58 @@ class GELU(nn.GELU):
 norm_layers_tuple = (nn.BatchNorm2d, nn.GroupNorm, nn.LayerNorm)
 
 
+class _KernelAct(nn.Module):
+    """Stand-alone activation modules of the MobileNetv3-style blocks (cvnets/layers/activation/{relu,hard_swish,hard_sigmoid,sigmoid}.py): one
+    element-wise pass of the kernel library (cvb_act_fwd / cvb_act_bwd).  ``inplace`` is accepted and ignored (outputs are always new tensors)."""
+    kind = -1
+
+    def __init__(self, inplace: Optional[bool] = False, *args, **kwargs) -> None:
+        super().__init__()
+        self.inplace = inplace
+
+    def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
+        from . import functional as Fn
+        _need_cuda(x, self.__class__.__name__)
+        return Fn.ActFn.apply(Fn.to_bf16_cl(x) if x.dim() == 4 else x.to(torch.bfloat16).contiguous(), self.kind)
+
+
+class ReLU(_KernelAct):
+    kind = 2
+
+
+class Hardswish(_KernelAct):
+    kind = 3
+
+
+class Hardsigmoid(_KernelAct):
+    kind = 4
+
+
+class Sigmoid(_KernelAct):
+    kind = 5
+
+
+class AdaptiveAvgPool2d(nn.Module):
+    """cvnets/layers/pooling.py: nn.AdaptiveAvgPool2d; output_size = 1 (the squeeze of SqueezeExcitation, squeeze_excitation.py:67-69) is the
+    global mean-pool kernel with keep_dim."""
+
+    def __init__(self, output_size=1, *args, **kwargs) -> None:
+        super().__init__()
+        if output_size not in (1, (1, 1)):
+            raise NotImplementedError("AdaptiveAvgPool2d: output_size = 1 is on the B200 hot path")
+        self.output_size = output_size
+
+    def forward(self, x: Tensor) -> Tensor:
+        from . import functional as Fn
+        _need_cuda(x, "AdaptiveAvgPool2d")
+        if x.dim() != 4 or x.shape[1] % 8:
+            raise NotImplementedError("AdaptiveAvgPool2d: expects [B, C, H, W] with C % 8 == 0")
+        return Fn.GlobalPoolFn.apply(Fn.to_bf16_cl(x), True)
+
+
+_ACT_CLASSES = {}
+
+
 def _need_cuda(x: Tensor, who: str):
     if not x.is_cuda:
         raise RuntimeError(f"{who}: ml-cvnets_b200 runs on CUDA (sm_100a) only and has no CPU fallback; got a {x.device} tensor")
@@ -147,13 +199,13 @@ def get_normalization_layer(opts, num_features: int, norm_type: Optional[str] = 
     raise NotImplementedError(f"normalization '{norm_type}' is not on the B200 hot path (batch_norm, layer_norm_2d, layer_norm, layer_norm_fp32 are)")
 
 
-def build_activation_layer(opts, *args, **kwargs) -> nn.Module:
-    name = _opt(opts, "model.activation.name", "swish")
-    if name in ("swish", "silu"):
-        return Swish()
-    if name == "gelu":
-        return GELU()
-    raise NotImplementedError(f"activation '{name}' is not on the B200 hot path (swish and gelu are)")
+def build_activation_layer(opts, act_type: Optional[str] = None, *args, **kwargs) -> nn.Module:
+    """cvnets/layers/activation/__init__.py: ``act_type`` overrides ``model.activation.name``."""
+    name = (act_type or _opt(opts, "model.activation.name", "swish")).lower()
+    table = {"swish": Swish, "silu": Swish, "gelu": GELU, "relu": ReLU, "hard_swish": Hardswish, "hard_sigmoid": Hardsigmoid, "sigmoid": Sigmoid}
+    if name in table:
+        return table[name]()
+    raise NotImplementedError(f"activation '{name}' is not on the B200 hot path ({', '.join(sorted(table))} are)")
 
 
 class Conv2d(nn.Conv2d):
@@ -212,9 +264,11 @@ class ConvLayer2d(BaseLayer):
                 and self.out_channels % 8 == 0):
             from .modules import _stem_forward
             return _stem_forward(self, x)
-        if self.norm_name not in (None, "BatchNorm2d") or self.act_name not in (None, "Swish", "GELU") or conv.padding_mode != "zeros":
+        kinds = {"Swish": ops.ACT_SILU, "GELU": ops.ACT_GELU, "ReLU": ops.ACT_RELU, "Hardswish": ops.ACT_HARDSWISH, "Hardsigmoid": ops.ACT_HARDSIGMOID,
+                 "Sigmoid": ops.ACT_SIGMOID}
+        if self.norm_name not in (None, "BatchNorm2d") or self.act_name not in (None, *kinds) or conv.padding_mode != "zeros":
             raise NotImplementedError(f"stand-alone ConvLayer2d with norm={self.norm_name}, act={self.act_name} has no kernel path")
-        act = None if self.act_name is None else (ops.ACT_SILU if self.act_name == "Swish" else ops.ACT_GELU)
+        act = None if self.act_name is None else kinds[self.act_name]
         norm = self.block.norm if self.norm_name is not None else None
         pad = tuple(conv.padding) if not isinstance(conv.padding, str) else None
         # groups = 1: 1x1 convs are the GEMM itself; square k x k convs run as im2col + GEMM (ViT conv stem, MobileViT-v1 3x3 convs)

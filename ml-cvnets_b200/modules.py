@@ -14,8 +14,8 @@ import torch
 from torch import Tensor, nn
 
 from . import functional as Fn
-from .layers import (ConvLayer2d, Dropout, Identity, LinearLayer, LinearSelfAttention, MultiHeadAttention, build_activation_layer,
-                     get_normalization_layer)
+from .layers import (AdaptiveAvgPool2d, ConvLayer2d, Dropout, Identity, LinearLayer, LinearSelfAttention, MultiHeadAttention,
+                     build_activation_layer, get_normalization_layer)
 from .ops import PreparedWeights as PW
 
 
@@ -132,6 +132,82 @@ class InvertedResidual(BaseModule):
     def __repr__(self) -> str:
         return "{}(in_channels={}, out_channels={}, stride={}, exp={}, dilation={}, skip_conn={})".format(
             self.__class__.__name__, self.in_channels, self.out_channels, self.stride, self.exp, self.dilation, self.use_res_connect)
+
+
+# ------------------------------------------------------------------------------- SqueezeExcitation / InvertedResidualSE
+class SqueezeExcitation(BaseModule):
+    """cvnets/modules/squeeze_excitation.py:16-91: ``x * scale_act(fc2(act(fc1(avg_pool(x)))))`` with the reference child tree
+    ``se_layer.{global_pool, fc1, fc2, scale_act}`` (fc1 / fc2 are 1x1 ConvLayer2d with bias; fc1's activation is the model-wide
+    ``model.activation.name``).  Pool, the two GEMMs, the activations and the channel scaling (cvb_se_scale_*) are library kernels."""
+
+    def __init__(self, opts, in_channels: int, squeeze_factor: Optional[int] = 4, squeeze_channels: Optional[int] = None,
+                 scale_fn_name: Optional[str] = "sigmoid", *args, **kwargs) -> None:
+        if squeeze_channels is None:
+            squeeze_channels = max(make_divisible(in_channels // squeeze_factor, 8), 32)
+        super().__init__()
+        self.se_layer = nn.Sequential()
+        self.se_layer.add_module("global_pool", AdaptiveAvgPool2d(output_size=1))
+        self.se_layer.add_module("fc1", ConvLayer2d(opts=opts, in_channels=in_channels, out_channels=squeeze_channels, kernel_size=1, stride=1, bias=True,
+                                                    use_norm=False, use_act=True))
+        self.se_layer.add_module("fc2", ConvLayer2d(opts=opts, in_channels=squeeze_channels, out_channels=in_channels, kernel_size=1, stride=1, bias=True,
+                                                    use_norm=False, use_act=False))
+        self.se_layer.add_module("scale_act", build_activation_layer(opts, act_type=scale_fn_name, inplace=True))
+        self.in_channels, self.squeeze_factor, self.scale_fn = in_channels, squeeze_factor, scale_fn_name
+
+    def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
+        _require_cuda(x, "SqueezeExcitation")
+        x = Fn.to_bf16_cl(x)
+        return Fn.SeScaleFn.apply(x, self.se_layer(x))
+
+    def __repr__(self) -> str:
+        return "{}(in_channels={}, squeeze_factor={}, scale_fn={})".format(self.__class__.__name__, self.in_channels, self.squeeze_factor, self.scale_fn)
+
+
+class InvertedResidualSE(BaseModule):
+    """cvnets/modules/mobilenetv2.py:16-138 (MobileNetv3-style block): exp_1x1 (1x1 + BN) -> act -> conv_3x3 (depthwise + BN)
+    -> act -> [SqueezeExcitation] -> red_1x1 (1x1 + BN), residual iff stride 1 and Cin == Cout.  Same constructor, child tree and state_dict
+    keys (``block.{exp_1x1, act_fn_1, conv_3x3, act_fn_2, se, red_1x1}``; the two act children are ONE module object, as in the reference).
+    Composition of the stand-alone layer kernels; the residual add rides the red_1x1 BatchNorm-apply pass.  Depthwise kernel size 3."""
+
+    def __init__(self, opts, in_channels: int, out_channels: int, expand_ratio: Union[int, float], dilation: Optional[int] = 1,
+                 stride: Optional[int] = 1, use_se: Optional[bool] = False, act_fn_name: Optional[str] = "relu",
+                 se_scale_fn_name: Optional[str] = "hard_sigmoid", kernel_size: Optional[int] = 3, squeeze_factor: Optional[int] = 4,
+                 *args, **kwargs) -> None:
+        hidden_dim = make_divisible(int(round(in_channels * expand_ratio)), 8)
+        act_fn = build_activation_layer(opts, act_type=act_fn_name, inplace=True)
+        super().__init__()
+        block = nn.Sequential()
+        if expand_ratio != 1:
+            block.add_module("exp_1x1", ConvLayer2d(opts, in_channels=in_channels, out_channels=hidden_dim, kernel_size=1, use_act=False, use_norm=True))
+            block.add_module("act_fn_1", act_fn)
+        block.add_module("conv_3x3", ConvLayer2d(opts, in_channels=hidden_dim, out_channels=hidden_dim, stride=stride, kernel_size=kernel_size,
+                                                 groups=hidden_dim, use_act=False, use_norm=True, dilation=dilation))
+        block.add_module("act_fn_2", act_fn)
+        if use_se:
+            block.add_module("se", SqueezeExcitation(opts=opts, in_channels=hidden_dim, squeeze_factor=squeeze_factor, scale_fn_name=se_scale_fn_name))
+        block.add_module("red_1x1", ConvLayer2d(opts, in_channels=hidden_dim, out_channels=out_channels, kernel_size=1, use_act=False, use_norm=True))
+        self.block = block
+        self.in_channels, self.out_channels, self.exp, self.dilation = in_channels, out_channels, expand_ratio, dilation
+        self.use_se, self.stride, self.act_fn_name, self.kernel_size = use_se, stride, act_fn_name, kernel_size
+        self.use_res_connect = self.stride == 1 and in_channels == out_channels
+
+    def forward(self, x: Tensor, *args, **kwargs) -> Tensor:
+        _require_cuda(x, "InvertedResidualSE")
+        if self.kernel_size != 3:
+            raise NotImplementedError("InvertedResidualSE: depthwise kernel size 3 has a kernel path (5x5 is not implemented)")
+        x = Fn.to_bf16_cl(x)
+        y = x
+        for name, m in self.block._modules.items():  # (named_children() would de-duplicate the shared activation module)
+            if name == "red_1x1" and self.use_res_connect:
+                y = m(y, residual=x)  # x + block(x): the residual is added in red_1x1's BatchNorm-apply pass
+            else:
+                y = m(y)
+        return y
+
+    def __repr__(self) -> str:
+        return "{}(in_channels={}, out_channels={}, stride={}, exp={}, dilation={}, use_se={}, kernel_size={}, act_fn={})".format(
+            self.__class__.__name__, self.in_channels, self.out_channels, self.stride, self.exp, self.dilation, self.use_se, self.kernel_size,
+            self.act_fn_name)
 
 
 # -------------------------------------------------------------------------------------------------------- LinearAttnFFN

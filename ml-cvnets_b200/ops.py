@@ -547,7 +547,7 @@ def ln_bwd(V: Tensor, X: Tensor, ln: Tensor, gamma: Tensor, col_stats: Tensor, D
     return DX
 
 
-ACT_SILU, ACT_GELU = 0, 1
+ACT_SILU, ACT_GELU, ACT_RELU, ACT_HARDSWISH, ACT_HARDSIGMOID, ACT_SIGMOID = 0, 1, 2, 3, 4, 5
 
 
 def act_fwd(X: Tensor, kind: int) -> Tensor:
@@ -562,6 +562,23 @@ def act_bwd(DY: Tensor, X: Tensor, kind: int) -> Tensor:
     L.check(_lib().cvb_act_bwd(DY.data_ptr(), X.data_ptr(), DX.data_ptr(), X.numel(), kind, _stream()), "cvb_act_bwd")
     _count()
     return DX
+
+
+def se_scale_fwd(X: Tensor, S: Tensor, B: int, HW: int) -> Tensor:
+    """Y[b,p,c] = X[b,p,c] * S[b,c]: X bf16 [B*HW, C] channels-last rows, S bf16 [B, C] (squeeze_excitation.py:82-83)."""
+    Y = torch.empty_like(X)
+    L.check(_lib().cvb_se_scale_fwd(X.data_ptr(), S.data_ptr(), Y.data_ptr(), B, HW, X.shape[1], _stream()), "cvb_se_scale_fwd")
+    _count()
+    return Y
+
+
+def se_scale_bwd(DY: Tensor, X: Tensor, S: Tensor, B: int, HW: int):
+    """DX = DY * S (bf16) and DS[b,c] = sum_p DY * X (fp32 [B, C])."""
+    DX = torch.empty_like(DY)
+    DS = torch.zeros((B, X.shape[1]), device=X.device, dtype=torch.float32)
+    L.check(_lib().cvb_se_scale_bwd(DY.data_ptr(), X.data_ptr(), S.data_ptr(), DX.data_ptr(), DS.data_ptr(), B, HW, X.shape[1], _stream()), "cvb_se_scale_bwd")
+    _count()
+    return DX, DS
 
 
 def ln_stats(X: Tensor, eps: float) -> Tensor:

@@ -17,6 +17,8 @@ def rebind_modules() -> None:
     import cvnets.modules as cm
     from . import modules as ours
     cm.InvertedResidual = ours.InvertedResidual
+    cm.InvertedResidualSE = ours.InvertedResidualSE  # mobilenetv3.py / efficientnet.py import it from cvnets.modules
+    cm.SqueezeExcitation = ours.SqueezeExcitation
     cm.MobileViTBlockv2 = ours.MobileViTBlockv2
     cm.TransformerEncoder = ours.TransformerEncoder  # used by vit.py:29, mobilevit_block.py (v1), text_encoders/transformer.py:20
 

@@ -188,6 +188,15 @@ def activation(x: Tensor, name: str) -> Tensor:
         return F.silu(x)
     if name == "gelu":
         return F.gelu(x)
+    # MobileNetv3-style blocks (cvnets/layers/activation/{relu,hard_swish,hard_sigmoid,sigmoid}.py == nn.ReLU / Hardswish / Hardsigmoid / Sigmoid)
+    if name == "relu":
+        return F.relu(x)
+    if name == "hard_swish":
+        return F.hardswish(x)
+    if name == "hard_sigmoid":
+        return F.hardsigmoid(x)
+    if name == "sigmoid":
+        return torch.sigmoid(x)
     raise NotImplementedError(name)
 
 
@@ -215,6 +224,34 @@ def inverted_residual(P: Params, pre: str, x: Tensor, *, stride: int, training: 
         y = conv_layer_2d(P, pre + ".block.exp_1x1", y, training=training, momentum=momentum)
     hid = P[pre + ".block.conv_3x3.block.conv.weight"].shape[0]
     y = conv_layer_2d(P, pre + ".block.conv_3x3", y, stride=stride, groups=hid, training=training, momentum=momentum, dilation=dilation)
+    y = conv_layer_2d(P, pre + ".block.red_1x1", y, use_act=False, training=training, momentum=momentum)
+    cout = P[pre + ".block.red_1x1.block.conv.weight"].shape[0]
+    if stride == 1 and x.shape[1] == cout:
+        y = x + y
+    return y
+
+
+def squeeze_excitation(P: Params, pre: str, x: Tensor, *, act: str = "relu", scale_fn: str = "hard_sigmoid") -> Tensor:
+    """SqueezeExcitation.forward (cvnets/modules/squeeze_excitation.py:45-83): x * scale_fn(fc2(act(fc1(AdaptiveAvgPool2d(1)(x))))); fc1 / fc2 are
+    1x1 convs with bias and no norm; fc1's activation is the model-wide ``model.activation.name`` (ConvLayer2d use_act=True, :46-55)."""
+    s = x.mean(dim=(2, 3), keepdim=True)
+    s = activation(F.conv2d(s, P[pre + ".se_layer.fc1.block.conv.weight"], P[pre + ".se_layer.fc1.block.conv.bias"]), act)
+    s = F.conv2d(s, P[pre + ".se_layer.fc2.block.conv.weight"], P[pre + ".se_layer.fc2.block.conv.bias"])
+    return x * activation(s, scale_fn)
+
+
+def inverted_residual_se(P: Params, pre: str, x: Tensor, *, stride: int = 1, act: str = "relu", se_scale: str = "hard_sigmoid", fc_act: str = "relu",
+                         training: bool = True, momentum: float = 0.1, dilation: int = 1) -> Tensor:
+    """InvertedResidualSE (cvnets/modules/mobilenetv2.py:16-138): exp_1x1 (1x1 + BN, if present) -> act -> conv_3x3 (depthwise k x k + BN) -> act ->
+    se (if present) -> red_1x1 (1x1 + BN); residual iff stride == 1 and Cin == Cout (:124, :126-128)."""
+    y = x
+    if (pre + ".block.exp_1x1.block.conv.weight") in P:
+        y = activation(conv_layer_2d(P, pre + ".block.exp_1x1", y, use_act=False, training=training, momentum=momentum), act)
+    hid = P[pre + ".block.conv_3x3.block.conv.weight"].shape[0]
+    y = conv_layer_2d(P, pre + ".block.conv_3x3", y, stride=stride, groups=hid, use_act=False, training=training, momentum=momentum, dilation=dilation)
+    y = activation(y, act)
+    if (pre + ".block.se.se_layer.fc1.block.conv.weight") in P:
+        y = squeeze_excitation(P, pre + ".block.se", y, act=fc_act, scale_fn=se_scale)
     y = conv_layer_2d(P, pre + ".block.red_1x1", y, use_act=False, training=training, momentum=momentum)
     cout = P[pre + ".block.red_1x1.block.conv.weight"].shape[0]
     if stride == 1 and x.shape[1] == cout:
@@ -478,6 +515,19 @@ def inverted_residual_shapes(P: Dict, pre: str, cin: int, cout: int, expand_rati
     if expand_ratio != 1:
         _conv_bn(P, pre + ".block.exp_1x1", cin, hid, 1)
     _conv_bn(P, pre + ".block.conv_3x3", hid, hid, 3, groups=hid)
+    _conv_bn(P, pre + ".block.red_1x1", hid, cout, 1)
+
+
+def inverted_residual_se_shapes(P: Dict, pre: str, cin: int, cout: int, expand_ratio: float, use_se: bool = True, kernel_size: int = 3,
+                                squeeze_factor: int = 4):
+    hid = make_divisible(int(round(cin * expand_ratio)), 8)  # mobilenetv2.py:56
+    if expand_ratio != 1:
+        _conv_bn(P, pre + ".block.exp_1x1", cin, hid, 1)
+    _conv_bn(P, pre + ".block.conv_3x3", hid, hid, kernel_size, groups=hid)
+    if use_se:
+        sq = max(make_divisible(hid // squeeze_factor, 8), 32)  # squeeze_excitation.py:43-44
+        _conv_bn(P, pre + ".block.se.se_layer.fc1", hid, sq, 1, norm=False, bias=True)
+        _conv_bn(P, pre + ".block.se.se_layer.fc2", sq, hid, 1, norm=False, bias=True)
     _conv_bn(P, pre + ".block.red_1x1", hid, cout, 1)
 
 

@@ -581,7 +581,8 @@ def _mha_ref(qkv, B, S, H, c, scale, amask, kpm):
     return (att @ v).transpose(1, 2).reshape(B * S, H * c)
 
 
-@pytest.mark.parametrize("B,S,H,c", [(2, 197, 12, 64), (3, 77, 8, 64), (2, 256, 4, 16), (2, 64, 4, 32), (5, 16, 2, 16), (1, 130, 3, 32)])
+@pytest.mark.parametrize("B,S,H,c", [(2, 197, 12, 64), (3, 77, 8, 64), (2, 256, 4, 16), (2, 64, 4, 32), (5, 16, 2, 16), (1, 130, 3, 32),
+                                      (1, 16, 1, 64), (2, 128, 2, 64), (1, 129, 1, 64), (2, 256, 2, 64)])
 @pytest.mark.parametrize("mask", ["none", "causal", "padding"])
 def test_mha_fwd_bwd(ops, B, S, H, c, mask):
     C = H * c
@@ -601,6 +602,38 @@ def test_mha_fwd_bwd(ops, B, S, H, c, mask):
     ref.backward(dO.float())
     DQKV = ops.mha_bwd(qkv, O, dO, LSE, B, S, H, c, scale, attn_mask=amask, key_padding_mask=kpm)
     close(DQKV, x.grad, rtol=3e-2, atol=2e-2 * float(x.grad.abs().max()) + 1e-6, what="mha bwd")
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 197, 3), (2, 77, 2), (1, 250, 2)])
+@pytest.mark.parametrize("mask", ["none", "causal", "padding"])
+def test_mha_tc_matches_mma(ops, B, S, H, mask):
+    """head_dim 64 has two implementations: tcgen05 (mha_tc.cu, the default) and mma.sync (mha.cu).  Same inputs -> same O / LSE / dQKV up to the
+    bf16 rounding of P (the tensor-core operand) and the accumulation order."""
+    from ml_cvnets_b200 import _lib as L
+    lib = L.load()
+    C = H * 64
+    qkv = bf(rnd(B * S, 3 * C, seed=73))
+    dO = bf(rnd(B * S, C, seed=74))
+    amask = kpm = None
+    if mask == "causal":
+        amask = torch.full((S, S), float("-inf"), device="cuda").triu(1)[None].repeat(B, 1, 1).contiguous()
+    if mask == "padding":
+        kpm = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+        kpm[:, S - max(1, S // 5):] = 1
+    res = {}
+    old = lib.cvb_set_mha_impl(0)
+    try:
+        for name, m in (("mma", 0), ("tc", 3)):
+            lib.cvb_set_mha_impl(m)
+            O, LSE = ops.mha_fwd(qkv, B, S, H, 64, 0.125, attn_mask=amask, key_padding_mask=kpm)
+            D = ops.mha_bwd(qkv, O, dO, LSE, B, S, H, 64, 0.125, attn_mask=amask, key_padding_mask=kpm)
+            res[name] = (O.float(), LSE.clone(), D.float())
+    finally:
+        lib.cvb_set_mha_impl(old)
+    for i, what in enumerate(("O", "LSE", "dQKV")):
+        a, b = res["tc"][i].double(), res["mma"][i].double()
+        r = float((a - b).norm() / (b.norm() + 1e-30))
+        assert r <= 4e-3, f"{what}: tcgen05 vs mma.sync rel-L2 {r:.3g}"
 
 
 @pytest.mark.parametrize("M,C", [(1000, 768), (333, 64), (50, 1000)])

@@ -53,6 +53,18 @@ def test_inverted_residual(mods, name):
     _check(P, fx, x, y)
 
 
+@pytest.mark.parametrize("name", ["ir_se_hs_res", "ir_se_relu_s2", "ir_nose_relu"])
+def test_inverted_residual_se(golden_dir, name):
+    """InvertedResidualSE / SqueezeExcitation (cvnets/modules/mobilenetv2.py:16-138, squeeze_excitation.py) against the real reference."""
+    fx = torch.load(os.path.join(golden_dir, "inverted_residual_se_fp32.pt"), weights_only=False)[name]
+    c = fx["cfg"]
+    P = {}
+    O.inverted_residual_se_shapes(P, "m", c["cin"], c["cout"], c["expand_ratio"], use_se=c["use_se"])
+    P = O.clone_params(O.seeded_fill_(P, fx["seed"]))
+    x, y = _run(lambda P, x: O.inverted_residual_se(P, "m", x, stride=c["stride"], act=c["act_fn_name"]), P, fx)
+    _check(P, fx, x, y)
+
+
 def test_linear_self_attention(mods):
     fx = mods["lsa"]
     P = {}

@@ -93,6 +93,37 @@ def test_conv_layer_standalone(pkg, mods, name):
     run_and_check(load_seeded(m, shapes, fx["seed"]), fx)
 
 
+@pytest.mark.parametrize("name", ["ir_se_hs_res", "ir_se_relu_s2", "ir_nose_relu"])
+def test_inverted_residual_se(pkg, golden_dir, name):
+    """InvertedResidualSE + SqueezeExcitation (cvnets/modules/mobilenetv2.py:16-138) vs the real reference's outputs, input
+    gradient, every parameter gradient and the BatchNorm running statistics."""
+    import copy
+    fx = torch.load(os.path.join(golden_dir, "inverted_residual_se_fp32.pt"), weights_only=False)[name]
+    c = fx["cfg"]
+    shapes = {}
+    O.inverted_residual_se_shapes(shapes, "m", c["cin"], c["cout"], c["expand_ratio"], use_se=c["use_se"])
+    auto = autocast_errors(lambda P, x: O.inverted_residual_se(P, "m", x, stride=c["stride"], act=c["act_fn_name"]), shapes, fx["seed"], fx)
+    opts = copy.deepcopy(pkg.default_opts())
+    setattr(opts, "model.activation.name", "relu")  # the reference default: fc1 of the SE unit takes the model-wide activation
+    m = pkg.InvertedResidualSE(opts, c["cin"], c["cout"], c["expand_ratio"], stride=c["stride"], use_se=c["use_se"], act_fn_name=c["act_fn_name"])
+    run_and_check(load_seeded(m, shapes, fx["seed"]), fx, auto=auto)
+
+
+@pytest.mark.parametrize("B,HW,C", [(3, 50, 64), (2, 4096, 96), (5, 1, 8)])
+def test_se_scale_kernels(pkg, B, HW, C):
+    from ml_cvnets_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(B * HW, C, device="cuda", generator=g).to(torch.bfloat16)
+    S = torch.rand(B, C, device="cuda", generator=g).to(torch.bfloat16)
+    DY = torch.randn(B * HW, C, device="cuda", generator=g).to(torch.bfloat16)
+    Y = ops.se_scale_fwd(X, S, B, HW)
+    ref = (X.float().view(B, HW, C) * S.float()[:, None]).view(B * HW, C)
+    assert rel_l2(Y, ref) <= 4e-3
+    DX, DS = ops.se_scale_bwd(DY, X, S, B, HW)
+    assert rel_l2(DX, (DY.float().view(B, HW, C) * S.float()[:, None]).view(B * HW, C)) <= 4e-3
+    assert rel_l2(DS, (DY.float() * X.float()).view(B, HW, C).sum(1)) <= 1e-4
+
+
 @pytest.mark.parametrize("name", ["ln2d", "ln", "ln_fp32"])
 def test_norm_layers_standalone(pkg, mods, name):
     fx = mods[name]
