@@ -240,16 +240,17 @@ CVB_API int cvb_linattn_cross_bwd(const void* QK_prev, int ldq, const void* V_x,
  * O: bf16 [B*S, ldo] with head h at columns h*c.. (the layout out_proj reads, :236).  scale = head_dim^-0.5 (:70, :187).
  * attn_mask: fp32 [B, S, S] additive (or NULL, :197-208); key_padding_mask: uint8 [B, S], non-zero = masked with -inf (:210-224).
  * Softmax in fp32 (:226-228).  LSE: fp32 [B, H, S] log-sum-exp (base 2) saved for the backward.  S <= 256, even c <= 64.
- * head_dim == 64 (ViT-B, CLIP text) runs on tcgen05 tensor cores (mha_tc.cu: TMA-staged operands, scores in TMEM, one thread per query
- * row); every other head_dim on the mma.sync kernels (mha.cu).
+ * head_dim == 64 (ViT-B / CLIP image tower, key-padding masks included) runs on tcgen05 tensor cores (mha_tc.cu: TMA-staged operands, scores in
+ * TMEM, one thread per query row); every other head_dim, and heads with an additive mask, on the mma.sync kernels (mha.cu).
  * ------------------------------------------------------------------------------------------------------------- */
 CVB_API int cvb_mha_fwd(const void* QKV, int ldq, int B, int S, int H, int head_dim, float scale, const float* attn_mask,
                 const unsigned char* key_padding_mask, void* O, int ldo, float* LSE, cvb_stream_t stream);
 /* dQKV (bf16 [B*S, lddq], same column layout as QKV) from dO; recomputes the probabilities from LSE. */
 CVB_API int cvb_mha_bwd(const void* QKV, int ldq, const void* O, const void* DO, int ldo, const float* LSE, int B, int S, int H, int head_dim,
                 float scale, const float* attn_mask, const unsigned char* key_padding_mask, void* DQKV, int lddq, cvb_stream_t stream);
-/* Diagnostics / A-B timing: which head_dim == 64 implementation runs.  bit 0: tcgen05 forward, bit 1: tcgen05 backward (default 3; the
- * environment variable CVB_MHA_TC sets the initial value).  Returns the previous mask. */
+/* Diagnostics / A-B timing: which head_dim == 64 implementation runs.  bit 0: tcgen05 forward, bit 1: tcgen05 backward, bit 2: tcgen05 also
+ * for heads with an additive attn_mask (default 3: additive-mask heads -- the causal CLIP text tower, S = 77 -- measured faster on mma.sync;
+ * the environment variable CVB_MHA_TC sets the initial value).  Returns the previous mask. */
 CVB_API int cvb_set_mha_impl(int mask);
 /* per-token LayerNorm statistics of a bf16 [M, C] matrix: mean[m], rstd[m] = 1/sqrt(var + eps) (biased variance, fp32 math like
  * nn.LayerNorm under autocast).  The normalisation itself is the GN load mode of the consuming GEMM with rows_per_sample = 1. */
@@ -271,6 +272,16 @@ CVB_API int cvb_ln_stats(const void* X, int ldx, int64_t M, int C, float eps, fl
  * backward: DX = DY * S and DS[b,c] += sum_p DY * X (fp32, zero-initialised by the caller). */
 CVB_API int cvb_se_scale_fwd(const void* X, const void* S, void* Y, int B, int HW, int C, cvb_stream_t stream);
 CVB_API int cvb_se_scale_bwd(const void* DY, const void* X, const void* S, void* DX, float* DS, int B, int HW, int C, cvb_stream_t stream);
+/* Dropout (cvnets/layers/dropout.py == nn.Dropout) and stochastic depth (torchvision.ops.StochasticDepth(mode="row"), cvnets/modules/transformer.py:97-100)
+ * folded into the residual add of the transformer blocks (transformer.py:139-156) on bf16 [M, C] matrices (C % 8 == 0):
+ *   fwd: Y = R + V * e * r   (R optional),   bwd: DV = DY * e * r;   e ~ Bernoulli(1-p)/(1-p) per element, r ~ Bernoulli(1-p_row)/(1-p_row) per
+ *   sample (rows_per_sample consecutive rows).  The masks are a counter-based hash of the 64-bit key at `key` (device memory) -- never stored; the
+ *   backward passes the forward's key.  cvb_rng_next draws a key from the device-resident state {seed, counter} (2 x uint64) and advances the
+ *   counter on the device, so a captured CUDA graph draws fresh masks at every replay. */
+CVB_API int cvb_rng_next(void* state, void* key_out, cvb_stream_t stream);
+CVB_API int cvb_dropout_fwd(const void* V, const void* R, void* Y, int64_t M, int C, int rows_per_sample, float p, float p_row, const void* key,
+                    cvb_stream_t stream);
+CVB_API int cvb_dropout_bwd(const void* DY, void* DV, int64_t M, int C, int rows_per_sample, float p, float p_row, const void* key, cvb_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Per-step tail of the training loop (engine/training_engine.py:289-312) on FLAT fp32 buffers of n elements: GradScaler unscale +

@@ -89,6 +89,9 @@ _SIGS = {
     "cvb_set_tc_enabled": (c_int, [c_int]),
     "cvb_set_pdl_enabled": (c_int, [c_int]),
     "cvb_set_mha_impl": (c_int, [c_int]),
+    "cvb_rng_next": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "cvb_dropout_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "cvb_dropout_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "cvb_se_scale_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cvb_se_scale_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cvb_pw_wgrad": (c_int, [POINTER(WgradArgs), c_void_p]),

@@ -28,6 +28,7 @@ void cvb_set_error(const char* fmt, ...);
   do {                                                                                   \
     cudaError_t e_ = (call);                                                             \
     if (e_ != cudaSuccess) {                                                             \
+      (void)cudaGetLastError(); /* reported here: do not leave it for the next caller */ \
       cvb_set_error("%s:%d CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
       return 2;                                                                          \
     }                                                                                    \

@@ -81,38 +81,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// issue only (the caller overlaps the TMEM read latency with arithmetic on the previous chunk, then calls tmem_wait_ld)
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-      "%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-        "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-constexpr int MT_LD = 33;  // padded row stride of a warp's mask tile (conflict-free row reads)
-// One warp stages the additive mask terms (exp2 domain) of its 32 query rows x 32 key columns: coalesced row reads (lane = key column), then
-// every thread reads its own row from shared memory.  A thread-per-row global read would touch 32 cache lines per load instruction.
-// -inf for padded and out-of-range keys; rows >= S get 0.
-__device__ __forceinline__ void stage_mask_tile(float* tile, const float* __restrict__ amask, const uint8_t* __restrict__ kpm, int b, int S, int q0, int t0,
-                                                int lane) {
-  __syncwarp();  // the previous tile has been consumed
-  const int t = t0 + lane;
-  const bool t_ok = t < S;
-  const bool padded = t_ok && kpm && kpm[(size_t)b * S + t];
-#pragma unroll 8
-  for (int r = 0; r < 32; ++r) {
-    const int q = q0 + r;
-    float v = 0.f;
-    if (!t_ok || padded) v = -CUDART_INF_F;
-    else if (amask && q < S) v = __ldg(amask + ((size_t)b * S + q) * S + t) * LOG2E;
-    tile[r * MT_LD + lane] = v;
-  }
-  __syncwarp();
-}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -120,6 +88,12 @@ __device__ __forceinline__ float ex2(float x) {
 }
 // byte offset of the 16-byte chunk `ch` (0..7) of row `row` inside a [rows x 64 ch] SWIZZLE_128B image
 __device__ __forceinline__ uint32_t sw128(int row, int ch) { return static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4)); }
+// additive mask term (exp2 domain) of score (q, t), t < S; -inf for padded keys
+__device__ __forceinline__ float mask_add(const float* amask, const uint8_t* kpm, int b, int S, int q, int t) {
+  if (kpm && kpm[(size_t)b * S + t]) return -CUDART_INF_F;
+  if (amask && q < S) return amask[((size_t)b * S + q) * S + t] * LOG2E;
+  return 0.f;
+}
 // write 32 consecutive values of one row (columns c32 * 32 .. + 31 of a 64-column box) as bf16 into a SWIZZLE_128B image
 __device__ __forceinline__ void store_row32(uint8_t* box, int row, int c32, const float* v) {
 #pragma unroll
@@ -225,79 +199,59 @@ __global__ void __launch_bounds__(FW_THREADS, 3)
     const bool masked = (amask != nullptr) || (kpm != nullptr);
     mbar_wait(&s_full, 0);
     fence_after();
-    // ---- pass 1: row maximum (exp2 domain; scale > 0, so unmasked chunks take the maximum of the raw scores).  Four partial maxima / sums
-    // break the serial dependency chains (one thread owns the whole row); the TMEM read of chunk c + 1 is in flight while chunk c is reduced.
-    float* mtile = masked ? reinterpret_cast<float*>(sP + 2 * BOX128) + (warp - 2) * (32 * MT_LD) : nullptr;
-    const int q0w = qt * 128 + quad * 32;
-    float mr[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-    float m = -CUDART_INF_F;
-    {
-      uint32_t ra[32], rb[32];
-      tmem_ld32_issue(taddr, ra);
-      tmem_wait_ld();
-      for (int c0 = 0; c0 < Sp; c0 += 64) {
-        // ---- chunk c0 in ra, prefetch c0 + 32 into rb
-        if (c0 + 32 < Sp) tmem_ld32_issue(taddr + c0 + 32, rb);
-        if (!masked && c0 + 32 <= S) {
+    // ---- pass 1: row maximum (exp2 domain; scale > 0, so the unmasked chunks take the maximum of the raw scores)
+    float mraw = -CUDART_INF_F, m = -CUDART_INF_F;
+    for (int c0 = 0; c0 < Sp; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c0, r);
+      if (!masked && c0 + 32 <= S) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(ra[i]));
-        } else {
-          if (masked) stage_mask_tile(mtile, amask, kpm, b, S, q0w, c0, lane);
+        for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, __uint_as_float(r[i]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < S) m = fmaxf(m, fmaf(__uint_as_float(ra[i]), sc2, masked ? mtile[lane * MT_LD + i] : 0.f));
-        }
-        tmem_wait_ld();
-        // ---- chunk c0 + 32 in rb, prefetch c0 + 64 into ra
-        if (c0 + 32 < Sp) {
-          if (c0 + 64 < Sp) tmem_ld32_issue(taddr + c0 + 64, ra);
-          const int c1 = c0 + 32;
-          if (!masked && c1 + 32 <= S) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mr[i & 3] = fmaxf(mr[i & 3], __uint_as_float(rb[i]));
-          } else {
-            if (masked) stage_mask_tile(mtile, amask, kpm, b, S, q0w, c1, lane);
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c1 + i < S) m = fmaxf(m, fmaf(__uint_as_float(rb[i]), sc2, masked ? mtile[lane * MT_LD + i] : 0.f));
+        for (int i = 0; i < 32; ++i) {
+          const int t = c0 + i;
+          if (t < S) {
+            float v = __uint_as_float(r[i]) * sc2;
+            if (masked) v += mask_add(amask, kpm, b, S, q, t);
+            m = fmaxf(m, v);
           }
-          tmem_wait_ld();
         }
       }
     }
-    m = fmaxf(m, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])) * sc2);
+    m = fmaxf(m, mraw * sc2);
     const float msafe = (m == -CUDART_INF_F) ? 0.f : m;  // a fully masked row must not produce inf - inf
     // ---- pass 2: P = exp2(sc2 * s + mask - m), row sum, bf16 chunks for the tensor core
-    float ls[4] = {0.f, 0.f, 0.f, 0.f};
+    float l = 0.f;
     for (int j = 0; j < nchunks; ++j) {
       const int slot = j & 1;
-      uint8_t* box = sP + slot * BOX128;
-      uint32_t ra[32], rb[32];
-      const int ca = j * 64, cb = j * 64 + 32;
-      tmem_ld32_issue(taddr + ca, ra);
-      if (cb < Sp) tmem_ld32_issue(taddr + cb, rb);
       if (j >= 2) mbar_wait(&p_empty[slot], ((j >> 1) - 1) & 1);
-      tmem_wait_ld();
+      uint8_t* box = sP + slot * BOX128;
 #pragma unroll
       for (int hlf = 0; hlf < 2; ++hlf) {
-        const int c0 = hlf ? cb : ca;
-        const uint32_t* r = hlf ? rb : ra;
+        const int c0 = j * 64 + hlf * 32;
         if (c0 < Sp) {
+          uint32_t r[32];
           float p[32];
+          tmem_ld32(taddr + c0, r);
           if (!masked && c0 + 32 <= S) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               p[i] = ex2(fmaf(__uint_as_float(r[i]), sc2, -msafe));
-              ls[i & 3] += p[i];
+              l += p[i];
             }
           } else {
-            if (masked) stage_mask_tile(mtile, amask, kpm, b, S, q0w, c0, lane);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
+              const int t = c0 + i;
               float pv = 0.f;
-              if (c0 + i < S) pv = ex2(fmaf(__uint_as_float(r[i]), sc2, -msafe) + (masked ? mtile[lane * MT_LD + i] : 0.f));
+              if (t < S) {
+                float v = fmaf(__uint_as_float(r[i]), sc2, -msafe);
+                if (masked) v += mask_add(amask, kpm, b, S, q, t);
+                pv = ex2(v);
+              }
               p[i] = pv;
-              ls[i & 3] += pv;
+              l += pv;
             }
           }
           store_row32(box, row, hlf, p);
@@ -308,7 +262,6 @@ __global__ void __launch_bounds__(FW_THREADS, 3)
       __syncwarp();
       if (lane == 0) arrive(&p_full[slot]);
     }
-    const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
     // ---- epilogue: O / l
     mbar_wait(&o_full, 0);
     fence_after();
@@ -441,7 +394,6 @@ __global__ void __launch_bounds__(BW_THREADS, 1)
       }
     }
     bf16* dbase = DQKV + (size_t)b * S * lddq + h * 64;
-    float* mtile = masked ? reinterpret_cast<float*>(sdS + 2 * BOX128) + (warp - 2) * (32 * MT_LD) : nullptr;
     int i = 0;
     for (int tt = 0; tt < NT; ++tt) {
       const int NB = min(128, Sp - tt * 128);
@@ -452,55 +404,41 @@ __global__ void __launch_bounds__(BW_THREADS, 1)
         mbar_wait(&sdp_full, i & 1);
         fence_after();
         if (i > 0) mbar_wait(&pds_empty, (i - 1) & 1);  // the previous block's output MMAs have read sP / sdS
-        // both 32-column chunks of this thread's half: the TMEM reads of the second are in flight while the first is processed
-        const int ca = half * 64, cb = half * 64 + 32;
-        uint32_t rs0[32], rd0[32], rs1[32], rd1[32];
-        if (ca < NB) {
-          tmem_ld32_issue(taddr + T_S + ca, rs0);
-          tmem_ld32_issue(taddr + T_DP + ca, rd0);
-          tmem_wait_ld();
-        }
-        if (cb < NB) {
-          tmem_ld32_issue(taddr + T_S + cb, rs1);
-          tmem_ld32_issue(taddr + T_DP + cb, rd1);
-        }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          const int c0 = cc ? cb : ca;
-          const uint32_t* rs = cc ? rs1 : rs0;
-          const uint32_t* rd = cc ? rd1 : rd0;
-          if (cc == 1) tmem_wait_ld();
+          const int c0 = half * 64 + cc * 32;
           if (c0 < NB) {
+            uint32_t rs[32], rd[32];
+            float p[32], ds[32];
+            tmem_ld32(taddr + T_S + c0, rs);
+            tmem_ld32(taddr + T_DP + c0, rd);
             const int t0 = tt * 128 + c0;
             const bool fast = !masked && q_ok && (t0 + 32 <= S);
-            if (!fast && masked) stage_mask_tile(mtile, amask, kpm, b, S, qt * 128 + quad * 32, t0, lane);
-            uint8_t* pbox = sP + half * BOX128;
-            uint8_t* dbox = sdS + half * BOX128;
+            if (fast) {
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {  // eight keys at a time: one 16-byte chunk of each image
-              float p[8], ds[8];
-#pragma unroll
-              for (int e8 = 0; e8 < 8; ++e8) {
-                const int e = g8 * 8 + e8;
-                if (fast) {
-                  const float pv = ex2(fmaf(__uint_as_float(rs[e]), sc2, -lse_q));
-                  p[e8] = pv;
-                  ds[e8] = pv * (__uint_as_float(rd[e]) - D_q);
-                } else {
-                  float pv = 0.f, dv = 0.f;
-                  if (q_ok && t0 + e < S) {
-                    pv = ex2(fmaf(__uint_as_float(rs[e]), sc2, -lse_q) + (masked ? mtile[lane * MT_LD + e] : 0.f));
-                    dv = pv * (__uint_as_float(rd[e]) - D_q);
-                    if (pv == 0.f) dv = 0.f;  // masked keys: exactly zero whatever dP holds
-                  }
-                  p[e8] = pv;
-                  ds[e8] = dv;
-                }
+              for (int e = 0; e < 32; ++e) {
+                const float pv = ex2(fmaf(__uint_as_float(rs[e]), sc2, -lse_q));
+                p[e] = pv;
+                ds[e] = pv * (__uint_as_float(rd[e]) - D_q);
               }
-              const uint32_t off = sw128(row, cc * 4 + g8);
-              *reinterpret_cast<uint4*>(pbox + off) = pack8(p);
-              *reinterpret_cast<uint4*>(dbox + off) = pack8(ds);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const int t = t0 + e;
+                float pv = 0.f, dv = 0.f;
+                if (q_ok && t < S) {
+                  float v = fmaf(__uint_as_float(rs[e]), sc2, -lse_q);
+                  if (masked) v += mask_add(amask, kpm, b, S, q, t);
+                  pv = ex2(v);
+                  dv = pv * (__uint_as_float(rd[e]) - D_q);
+                  if (pv == 0.f) dv = 0.f;  // masked keys: exactly zero whatever dP holds
+                }
+                p[e] = pv;
+                ds[e] = dv;
+              }
             }
+            store_row32(sP + half * BOX128, row, cc, p);
+            store_row32(sdS + half * BOX128, row, cc, ds);
           }
         }
         fence_proxy_async();
@@ -536,7 +474,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1)
   }
 }
 
-int g_impl = -1;  // bit 0: tcgen05 forward, bit 1: tcgen05 backward
+// bit 0: tcgen05 forward, bit 1: tcgen05 backward, bit 2: also for heads with an ADDITIVE mask.  Default 3: additive masks (the causal mask of the
+// CLIP text tower, S = 77) stay on the mma.sync kernels -- one thread owns one query row here, so the mask is read row-per-thread (32 cache
+// lines per load instruction) and the short sequences leave too few warps to hide that latency: measured 216 / 407 us (fwd / bwd, B 256, S 77,
+// 8 heads, causal) against 65 / 305 us on mma.sync, while the unmasked ViT-B shape (S 197, 12 heads) runs 156 / 462 us against 213 / 907 us.
+int g_impl = -1;
 int impl() {
   if (g_impl < 0) {
     const char* e = getenv("CVB_MHA_TC");
@@ -549,20 +491,20 @@ int impl() {
 
 extern "C" int cvb_set_mha_impl(int mask) {
   const int old = impl();
-  g_impl = mask & 3;
+  g_impl = mask & 7;
   return old;
 }
 
 // Return -1 when the shape is left to the mma.sync kernels (head_dim != 64), 0 on success, > 0 on error.
 int cvb_mha_fwd_tc(const void* QKV, int ldq, int B, int S, int H, int head_dim, float scale, const float* amask, const unsigned char* kpm, void* O,
                    int ldo, float* LSE, cudaStream_t st) {
-  if (head_dim != 64 || !(impl() & 1) || S > 256) return -1;
+  if (head_dim != 64 || !(impl() & 1) || S > 256 || (amask && !(impl() & 4))) return -1;
   const int Sp = (S + 15) / 16 * 16;
   const int NQT = (S + 127) / 128;
   CUtensorMap tmQ, tmKV;
   if (cvb_make_tmap_2d_c64(&tmQ, QKV, (int64_t)B * S, 3 * H * 64, ldq, 128)) return 1;
   if (cvb_make_tmap_2d_c64(&tmKV, QKV, (int64_t)B * S, 3 * H * 64, ldq, Sp)) return 1;
-  const size_t smem = (size_t)BOX128 + (size_t)2 * Sp * 128 + 2 * BOX128 + 1024 + ((amask || kpm) ? (size_t)4 * 32 * MT_LD * 4 : 0);
+  const size_t smem = (size_t)BOX128 + (size_t)2 * Sp * 128 + 2 * BOX128 + 1024;
   const uint32_t cols = Sp <= 64 ? 64u : (Sp <= 128 ? 128u : 256u);
   static bool attr = false;
   if (!attr) { CVB_CUDA(cudaFuncSetAttribute(mha_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
@@ -573,16 +515,16 @@ int cvb_mha_fwd_tc(const void* QKV, int ldq, int B, int S, int H, int head_dim, 
 
 int cvb_mha_bwd_tc(const void* QKV, int ldq, const void* O, const void* DO, int ldo, const float* LSE, int B, int S, int H, int head_dim, float scale,
                    const float* amask, const unsigned char* kpm, void* DQKV, int lddq, cudaStream_t st) {
-  if (head_dim != 64 || !(impl() & 2) || S > 256) return -1;
+  if (head_dim != 64 || !(impl() & 2) || S > 256 || (amask && !(impl() & 4))) return -1;
   const int Sp = (S + 15) / 16 * 16;
   const int NT = (S + 127) / 128;
   const int R = NT * 128;
   CUtensorMap tmQKV, tmDO;
   if (cvb_make_tmap_2d_c64(&tmQKV, QKV, (int64_t)B * S, 3 * H * 64, ldq, R)) return 1;
   if (cvb_make_tmap_2d_c64(&tmDO, DO, (int64_t)B * S, H * 64, ldo, R)) return 1;
-  const size_t smem = (size_t)4 * R * 128 + 4 * BOX128 + 1024 + ((amask || kpm) ? (size_t)8 * 32 * MT_LD * 4 : 0);
+  const size_t smem = (size_t)4 * R * 128 + 4 * BOX128 + 1024;
   static bool attr = false;
-  if (!attr) { CVB_CUDA(cudaFuncSetAttribute(mha_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256)); attr = true; }
+  if (!attr) { CVB_CUDA(cudaFuncSetAttribute(mha_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
   CVB_CUDA(cvb_launch(mha_tc_bwd_kernel, B * H, BW_THREADS, smem, st, tmQKV, tmDO, static_cast<const bf16*>(O), static_cast<const bf16*>(DO), ldo, LSE, S, Sp,
                       H, NT, scale, amask, kpm, static_cast<bf16*>(DQKV), lddq));
   CVB_LAUNCH_CHECK();

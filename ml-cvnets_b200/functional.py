@@ -863,6 +863,27 @@ class ActFn(torch.autograd.Function):
         return ops.act_bwd(g, x, ctx.kind), None
 
 
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout in training mode on a bf16 tensor whose last dimension is a multiple of 8 (cvnets/layers/dropout.py): the mask is a hash of a
+    device-resident key (ops.rng_next), regenerated -- not stored -- in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.dtype != BF16 or not x2.is_contiguous():
+            x2 = x2.to(BF16).contiguous()
+        key = ops.rng_next(x.device)
+        ctx.p, ctx.key, ctx.shape = p, key, x.shape
+        return ops.dropout_fwd(x2, None, p, key).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = gout.reshape(-1, ctx.shape[-1])
+        if g.dtype != BF16 or not g.is_contiguous():
+            g = g.to(BF16).contiguous()
+        return ops.dropout_bwd(g, ctx.p, ctx.key).view(ctx.shape), None
+
+
 class SeScaleFn(torch.autograd.Function):
     """SqueezeExcitation.forward's ``x * se_layer(x)`` (cvnets/modules/squeeze_excitation.py:82-83): [B, C, H, W] map times a [B, C, 1, 1] scale."""
 
@@ -1181,16 +1202,36 @@ class TransformerEncoderFn(torch.autograd.Function):
         ln1 = ops.ln_stats(x2, cfg.eps)
         qkv = ops.pw_gemm(x2, P.get(cfg.i_wqkv), 3 * C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, bias=bqkv)
         O, LSE = ops.mha_fwd(qkv, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
-        samp = _fwd_arena(cfg, x.device, 2 * M + 8).f64(2, M)
-        X1 = ops.pw_gemm(O, P.get(cfg.i_wo), C, bias=bo, R=x2, samp_stats=samp, rows_per_sample=1)
-        ln2 = ops.gn_finalize(samp, C, cfg.eps)
-        h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
-        if cfg.act == ops.ACT_SILU:
-            ha = None
-            X2 = ops.pw_gemm(h, P.get(cfg.i_w2), C, a_mode=A_SILU, bias=bb2, R=X1)
+        drop = getattr(cfg, "drop", None)  # (p, p_ffn, p_row) in training with dropout / stochastic depth > 0 (transformer.py:97-100, 139-156)
+        keys = None
+        if drop is None:
+            samp = _fwd_arena(cfg, x.device, 2 * M + 8).f64(2, M)
+            X1 = ops.pw_gemm(O, P.get(cfg.i_wo), C, bias=bo, R=x2, samp_stats=samp, rows_per_sample=1)
+            ln2 = ops.gn_finalize(samp, C, cfg.eps)
+            h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
+            if cfg.act == ops.ACT_SILU:
+                ha = None
+                X2 = ops.pw_gemm(h, P.get(cfg.i_w2), C, a_mode=A_SILU, bias=bb2, R=X1)
+            else:
+                ha = ops.act_fwd(h, cfg.act)
+                X2 = ops.pw_gemm(ha, P.get(cfg.i_w2), C, bias=bb2, R=X1)
         else:
+            # the residual adds leave the GEMM epilogues: x + DropPath(Dropout(branch)) is one element-wise pass with hashed masks
+            p, p_ffn, p_row = drop
+            k1, k2 = ops.rng_next(x.device), ops.rng_next(x.device)
+            A = ops.pw_gemm(O, P.get(cfg.i_wo), C, bias=bo)
+            X1 = ops.dropout_fwd(A, x2, p, k1, p_row=p_row, rows_per_sample=S)
+            ln2 = ops.ln_stats(X1, cfg.eps)
+            h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
             ha = ops.act_fwd(h, cfg.act)
-            X2 = ops.pw_gemm(ha, P.get(cfg.i_w2), C, bias=bb2, R=X1)
+            k3 = None
+            if p_ffn > 0:
+                k3 = ops.rng_next(x.device)
+                ha = ops.dropout_fwd(ha, None, p_ffn, k3)
+            Fo = ops.pw_gemm(ha, P.get(cfg.i_w2), C, bias=bb2)
+            X2 = ops.dropout_fwd(Fo, X1, p, k2, p_row=p_row, rows_per_sample=S)
+            keys = (k1, k2, k3)
+        ctx.keys, ctx.drop = keys, drop
         ctx.cfg, ctx.dims, ctx.plist = cfg, (N, S, C), cfg.plist
         ctx.saved = (x2, ln1, qkv, O, LSE, X1, ln2, h, ha, amask, kpm)
         ctx.save_for_backward(g1, b1, g2, b2)
@@ -1212,22 +1253,40 @@ class TransformerEncoderFn(torch.autograd.Function):
         vec = lambda i, n: D.mat(i, 1, n).view(n)  # noqa: E731
         # ---- FFN
         db2, db1 = vec(11, C), vec(9, ffn)
-        if cfg.act == ops.ACT_SILU:
+        drop = ctx.drop
+        if drop is not None:
+            p, p_ffn, p_row = drop
+            k1, k2, k3 = ctx.keys
+            dF = ops.dropout_bwd(dY, p, k2, p_row=p_row, rows_per_sample=S)  # gradient of the FFN branch; the residual path keeps dY
+            ops.pw_wgrad_side(dF, ha, C, ffn, dW=D.mat(10, C, ffn), dbias=db2)
+            dha = ops.pw_gemm(dF, P.get(cfg.i_w2t), ffn, K=C)
+            if k3 is not None:
+                dha = ops.dropout_bwd(dha, p_ffn, k3)
+            dh = ops.act_bwd(dha, h, cfg.act)
+        elif cfg.act == ops.ACT_SILU:
             ops.pw_wgrad_side(dY, h, C, ffn, a_mode=A_SILU, dW=D.mat(10, C, ffn), dbias=db2)
             dh = ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C, e_mode=E_SILU_BWD, Y=h)
         else:
             ops.pw_wgrad_side(dY, ha, C, ffn, dW=D.mat(10, C, ffn), dbias=db2)
             dh = ops.act_bwd(ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C), h, cfg.act)
         ops.pw_wgrad_side(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=D.mat(8, ffn, C), dbias=db1)
-        csf, bsum1 = ar.f64(2, C), ar.f64(C)
+        csf = ar.f64(2, C)
         vF = ops.pw_gemm(dh, P.get(cfg.i_w1t), C, K=ffn)
-        dX1 = ops.ln_bwd(vF, X1, ln2, g2, csf, DRES=dY, col_sum=bsum1)  # bsum1 = column sums of dX1 = d(out_proj bias)
-        D.late64(5, bsum1)
+        if drop is None:
+            bsum1 = ar.f64(C)
+            dX1 = ops.ln_bwd(vF, X1, ln2, g2, csf, DRES=dY, col_sum=bsum1)  # bsum1 = column sums of dX1 = d(out_proj bias)
+            D.late64(5, bsum1)
+            dA = dX1
+            dbo = None
+        else:
+            dX1 = ops.ln_bwd(vF, X1, ln2, g2, csf, DRES=dY)
+            dA = ops.dropout_bwd(dX1, p, k1, p_row=p_row, rows_per_sample=S)  # gradient of the attention branch (out_proj output)
+            dbo = vec(5, C)
         D.late64(6, csf[1])
         D.late64(7, csf[0])
         # ---- attention
-        ops.pw_wgrad_side(dX1, O, C, C, dW=D.mat(4, C, C))
-        dO = ops.pw_gemm(dX1, P.get(cfg.i_wot), C, K=C)
+        ops.pw_wgrad_side(dA, O, C, C, dW=D.mat(4, C, C), dbias=dbo)
+        dO = ops.pw_gemm(dA, P.get(cfg.i_wot), C, K=C)
         dqkv = ops.mha_bwd(qkv, O, dO, LSE, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
         ops.pw_wgrad_side(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=D.mat(2, 3 * C, C),
                           dbias=vec(3, 3 * C))

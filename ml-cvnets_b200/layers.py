@@ -40,10 +40,44 @@ class Identity(BaseLayer):
 
 
 class Dropout(nn.Dropout):
-    """cvnets/layers/dropout.py:11-29.  The MobileViTv2 recipe has p = 0 everywhere (mobilevit_v2.py:105-122)."""
+    """cvnets/layers/dropout.py: nn.Dropout.  Training mode with p > 0 on a CUDA tensor runs the library's hashed-mask kernel (cvb_dropout_fwd);
+    eval mode / p == 0 is the identity.  Inside TransformerEncoder the module is only a parameter-free marker: its p is folded into the
+    block's residual adds."""
 
     def __init__(self, p: Optional[float] = 0.5, inplace: Optional[bool] = False, *args, **kwargs) -> None:
         super().__init__(p=p, inplace=inplace)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not self.training or self.p == 0.0:
+            return x
+        from . import functional as Fn
+        _need_cuda(x, "Dropout")
+        if self.p >= 1.0 or x.shape[-1] % 8:
+            raise NotImplementedError("Dropout: 0 <= p < 1 and a last dimension that is a multiple of 8 have a kernel path")
+        if x.dim() == 4:  # [B, C, H, W] maps live channels-last: the kernel sees the [B*H*W, C] matrix
+            xc = Fn.to_bf16_cl(x)
+            B, C, H, W = xc.shape
+            if C % 8:
+                raise NotImplementedError("Dropout: channel count must be a multiple of 8")
+            return Fn.to_4d(Fn.DropoutFn.apply(Fn.as_2d(xc), float(self.p)), B, H, W)
+        return Fn.DropoutFn.apply(x, float(self.p))
+
+
+class StochasticDepth(nn.Module):
+    """cvnets/layers/stochastic_depth.py == torchvision.ops.StochasticDepth: parameter-free marker child ``drop_path`` of TransformerEncoder; its
+    per-sample mask is folded into the block's residual adds (cvb_dropout_fwd, p_row)."""
+
+    def __init__(self, p: float, mode: str) -> None:
+        super().__init__()
+        if mode != "row":
+            raise NotImplementedError("StochasticDepth: mode='row' is what the reference uses (transformer.py:105)")
+        self.p, self.mode = p, mode
+
+    def forward(self, x: Tensor) -> Tensor:
+        raise NotImplementedError("StochasticDepth runs fused inside TransformerEncoder")
+
+    def __repr__(self) -> str:
+        return "{}(p={}, mode={})".format(self.__class__.__name__, self.p, self.mode)
 
 
 class Swish(nn.SiLU):

@@ -128,6 +128,6 @@ class MobileViT(nn.Module):
         _require_cuda(x, "MobileViT")
         x = self.extract_features(x)
         x = self.classifier.global_pool(x)
-        if hasattr(self.classifier, "dropout") and self.training and self.classifier.dropout.p > 0:
-            raise NotImplementedError("classifier dropout > 0 in training mode is not implemented (eval mode works)")
+        if hasattr(self.classifier, "dropout"):
+            x = self.classifier.dropout(x)  # classifier_dropout 0.1 of the recipe (mobilevit.py:110-113): hashed-mask kernel in training, identity in eval
         return self.classifier.fc(x)

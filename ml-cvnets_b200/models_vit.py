@@ -5,7 +5,7 @@ Host code like the MobileViTv2 assembler: same attribute names / ``state_dict`` 
 ``cls_token``, ``pos_embed.pos_embed.pos_embed``, ``transformer.{i}.*``, ``post_transformer_norm.*``, ``classifier.*``), every forward /
 backward kernel is the library's.  BASELINE.json configs[2]: ViT-B/16, bf16, 224x224 (examples/vit/classification/vit_base.yaml).
 Not implemented (raises): SimpleFPN (detection), sinusoidal / interpolated positional embeddings (inputs other than 224x224 with the
-default 196 embeddings), output_stride, gradient checkpointing, dropout / stochastic depth > 0.
+default 196 embeddings), output_stride, gradient checkpointing, attention-probability dropout > 0 in training.
 """
 from __future__ import annotations
 
@@ -13,6 +13,7 @@ import argparse
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 from torch import Tensor, nn
 
@@ -87,12 +88,11 @@ class VisionTransformer(nn.Module):
             ConvLayer2d(opts=opts, in_channels=stem_dim, out_channels=stem_dim, kernel_size=2, stride=2, bias=False, use_norm=True, use_act=True),
             ConvLayer2d(opts=opts, in_channels=stem_dim, out_channels=d, kernel_size=2, stride=2, bias=True, use_norm=False, use_act=False))
         sd = getattr(opts, "model.classification.vit.stochastic_dropout", 0.0)
-        if sd or cfg["dropout"]:
-            raise NotImplementedError("dropout / stochastic depth > 0 is not implemented (the ViT-B recipe uses 0)")
+        per_layer_sd = [round(float(v), 3) for v in np.linspace(0, sd, n_layers)]  # vit.py:129-132
         self.post_transformer_norm = get_normalization_layer(opts=opts, num_features=d, norm_type=norm_layer)
         self.transformer = nn.Sequential(*[
             TransformerEncoder(opts=opts, embed_dim=d, ffn_latent_dim=ffn, num_heads=heads, attn_dropout=cfg["attn_dropout"], dropout=cfg["dropout"],
-                               ffn_dropout=cfg["ffn_dropout"], transformer_norm_layer=norm_layer, stochastic_dropout=0.0) for _ in range(n_layers)])
+                               ffn_dropout=cfg["ffn_dropout"], transformer_norm_layer=norm_layer, stochastic_dropout=per_layer_sd[i]) for i in range(n_layers)])
         self.classifier = LinearLayer(d, num_classes)
         self.reset_parameters(opts)
         if not getattr(opts, "model.classification.vit.no_cls_token", False):
@@ -149,12 +149,11 @@ class VisionTransformer(nn.Module):
         pe = self.pos_embed.pos_embed.pos_embed
         if n_h * n_w != pe.shape[2]:
             raise NotImplementedError("interpolated positional embeddings (inputs other than 224x224) are not implemented")
-        if self.training and self.emb_dropout.p > 0:
-            raise NotImplementedError("positional-embedding dropout > 0 in training (the 'tiny' config, config/vit.py:44) is not implemented")
         tok = self._tok
         tok.ws = getattr(self, "_ws", None)
         tok.plist = [pe] + ([self.cls_token] if self.cls_token is not None else [])
-        return Fn.VitTokensFn.apply(patch, tok, pe, self.cls_token), (n_h, n_w)
+        # emb_dropout (vit.py: positional-embedding dropout, 0.1 in the 'tiny' config): hashed-mask kernel in training, identity otherwise
+        return self.emb_dropout(Fn.VitTokensFn.apply(patch, tok, pe, self.cls_token)), (n_h, n_w)
 
     def extract_features(self, x: Tensor, *args, **kwargs) -> Tensor:
         x, _ = self.extract_patch_embeddings(x)

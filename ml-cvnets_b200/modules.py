@@ -14,7 +14,7 @@ import torch
 from torch import Tensor, nn
 
 from . import functional as Fn
-from .layers import (AdaptiveAvgPool2d, ConvLayer2d, Dropout, Identity, LinearLayer, LinearSelfAttention, MultiHeadAttention,
+from .layers import (AdaptiveAvgPool2d, ConvLayer2d, Dropout, Identity, LinearLayer, LinearSelfAttention, MultiHeadAttention, StochasticDepth,
                      build_activation_layer, get_normalization_layer)
 from .ops import PreparedWeights as PW
 
@@ -461,7 +461,10 @@ class TransformerEncoder(BaseModule):
                                           LinearLayer(in_features=ffn_latent_dim, out_features=embed_dim, bias=True), Dropout(p=dropout))
         self.drop_path = Identity()
         if stochastic_dropout > 0.0:
-            raise NotImplementedError("stochastic depth > 0 is not implemented")
+            if dropout > 0.0:
+                raise ValueError("Stochastic dropout and dropout are mutually exclusive. Use either of them, but not both. "
+                                 "Got: {} and {}".format(stochastic_dropout, dropout))  # transformer.py:98-104 (logger.error -> exit)
+            self.drop_path = StochasticDepth(p=stochastic_dropout, mode="row")
         self.embed_dim, self.ffn_dim, self.ffn_dropout = embed_dim, ffn_latent_dim, ffn_dropout
         self.stochastic_dropout, self.std_dropout = stochastic_dropout, dropout
         self.attn_fn_name, self.act_fn_name, self.norm_type = attn_unit.__class__.__name__, act_name.__class__.__name__, transformer_norm_layer
@@ -493,8 +496,9 @@ class TransformerEncoder(BaseModule):
         _require_cuda(x, "TransformerEncoder")
         if x_prev is not None:
             raise NotImplementedError("cross-attention (x_prev) is not implemented on the B200 path")
-        if self.training and (self.std_dropout or self.ffn_dropout or self.pre_norm_mha[1].attn_dropout.p):
-            raise NotImplementedError("dropout > 0 in training mode is not implemented (it is the identity in eval mode, which works)")
+        if self.training and self.pre_norm_mha[1].attn_dropout.p:
+            raise NotImplementedError("attention-probability dropout > 0 in training mode is not implemented (every recipe of the reference sets 0; "
+                                      "it is the identity in eval mode, which works)")
         if x.dim() != 3 or x.shape[1] > 256:
             raise NotImplementedError("TransformerEncoder expects [N, S, C] with S <= 256")
         if x.shape[1] == x.shape[2]:
@@ -503,6 +507,10 @@ class TransformerEncoder(BaseModule):
             self._build_cfg()
         cfg = self._cfg
         cfg.masks = (attn_mask, key_padding_mask)
+        # training-mode dropout after the attention / FFN branches, FFN-hidden dropout and stochastic depth (transformer.py:77-100, 139-156): hashed
+        # masks folded into the residual adds (functional.TransformerEncoderFn); all three are the identity in eval mode
+        p, pf, pr = float(self.pre_norm_mha[2].p), float(self.pre_norm_ffn[3].p), float(self.stochastic_dropout)
+        cfg.drop = (p, pf, pr) if (self.training and (p > 0 or pf > 0 or pr > 0)) else None
         cfg.eps = float(self.pre_norm_mha[0].eps)  # VisionTransformer.update_layer_norm_eps rewrites it after construction (vit.py:204-208)
         cfg.prep.prepare(force=self.training)
         n1, mha, n2 = self.pre_norm_mha[0], self.pre_norm_mha[1], self.pre_norm_ffn[0]

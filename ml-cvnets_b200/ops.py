@@ -581,6 +581,47 @@ def se_scale_bwd(DY: Tensor, X: Tensor, S: Tensor, B: int, HW: int):
     return DX, DS
 
 
+# ---------------------------------------------------------------------------------------------------------- dropout
+_RNG = {}
+
+
+def rng_seed(seed: Optional[int] = None, device=None) -> None:
+    """(Re)seed the device-resident dropout generator {seed, counter}; default seed = torch.initial_seed() (utils/common_utils.py:68-71 seeds torch)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    seed = torch.initial_seed() if seed is None else int(seed)
+    _RNG[dev] = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], device=dev, dtype=torch.int64)
+
+
+def rng_next(device) -> Tensor:
+    """Draw a 64-bit mask key on the device (int64 [1]); the counter advances on the device, also when replayed inside a CUDA graph."""
+    dev = torch.device(device)
+    if dev not in _RNG:
+        rng_seed(device=dev)
+    key = torch.empty(1, device=dev, dtype=torch.int64)
+    L.check(_lib().cvb_rng_next(_RNG[dev].data_ptr(), key.data_ptr(), _stream()), "cvb_rng_next")
+    _count()
+    return key
+
+
+def dropout_fwd(V: Tensor, R: Optional[Tensor], p: float, key: Tensor, p_row: float = 0.0, rows_per_sample: int = 0) -> Tensor:
+    """Y = R + V * mask / (1 - p) [* per-sample stochastic-depth factor] on bf16 [M, C] (see cvb_dropout_fwd)."""
+    M, C = V.shape
+    Y = torch.empty_like(V)
+    L.check(_lib().cvb_dropout_fwd(V.data_ptr(), _p(R), Y.data_ptr(), M, C, rows_per_sample, float(p), float(p_row), key.data_ptr(), _stream()),
+            "cvb_dropout_fwd")
+    _count()
+    return Y
+
+
+def dropout_bwd(DY: Tensor, p: float, key: Tensor, p_row: float = 0.0, rows_per_sample: int = 0) -> Tensor:
+    M, C = DY.shape
+    DV = torch.empty_like(DY)
+    L.check(_lib().cvb_dropout_bwd(DY.data_ptr(), DV.data_ptr(), M, C, rows_per_sample, float(p), float(p_row), key.data_ptr(), _stream()),
+            "cvb_dropout_bwd")
+    _count()
+    return DV
+
+
 def ln_stats(X: Tensor, eps: float) -> Tensor:
     """per-token LayerNorm statistics of a bf16 [M, C] matrix -> fp32 [2, M] (mean, rstd)."""
     lib = _lib()

@@ -201,15 +201,23 @@ def activation(x: Tensor, name: str) -> Tensor:
 
 
 def transformer_encoder(P: Params, pre: str, x: Tensor, num_heads: int, act: str = "swish", eps: float = 1e-5,
-                        key_padding_mask: Optional[Tensor] = None, attn_mask: Optional[Tensor] = None) -> Tensor:
-    """TransformerEncoder.forward (cvnets/modules/transformer.py:129-156), pre-norm, dropout / stochastic depth p=0:
-    x = x + MHA(LN(x));  x = x + Linear(act(Linear(LN(x)))).  Child indices pre_norm_mha.{0,1}, pre_norm_ffn.{0,1,4} (:77-95)."""
+                        key_padding_mask: Optional[Tensor] = None, attn_mask: Optional[Tensor] = None,
+                        drop_masks: Optional[Tuple[Optional[Tensor], Optional[Tensor], Optional[Tensor]]] = None) -> Tensor:
+    """TransformerEncoder.forward (cvnets/modules/transformer.py:129-156), pre-norm:
+    x = x + DropPath(Dropout(MHA(LN(x))));  x = x + DropPath(Dropout(Linear(Dropout_ffn(act(Linear(LN(x)))))))  (:77-100, 139-156).
+    Child indices pre_norm_mha.{0,1}, pre_norm_ffn.{0,1,4}.  ``drop_masks`` = (attention-branch, ffn-hidden, ffn-branch) multiplicative masks
+    (already scaled by 1/keep, stochastic-depth factor included) -- None = eval mode / p = 0: dropout and stochastic depth are the identity.
+    The masks are an INPUT because no two generators produce the same Bernoulli draws; the parity tests take them from the kernel under test."""
+    m_attn, m_hid, m_ffn = drop_masks if drop_masks is not None else (None, None, None)
     a = layer_norm(P, pre + ".pre_norm_mha.0", x, eps)
-    x = x + multi_head_attention(P, pre + ".pre_norm_mha.1", a, num_heads, key_padding_mask, attn_mask)
+    a = multi_head_attention(P, pre + ".pre_norm_mha.1", a, num_heads, key_padding_mask, attn_mask)
+    x = x + (a if m_attn is None else a * m_attn)
     f = layer_norm(P, pre + ".pre_norm_ffn.0", x, eps)
     f = activation(F.linear(f, P[pre + ".pre_norm_ffn.1.weight"], P[pre + ".pre_norm_ffn.1.bias"]), act)
+    if m_hid is not None:
+        f = f * m_hid
     f = F.linear(f, P[pre + ".pre_norm_ffn.4.weight"], P[pre + ".pre_norm_ffn.4.bias"])
-    return x + f
+    return x + (f if m_ffn is None else f * m_ffn)
 
 
 # --------------------------------------------------------------------------------------------

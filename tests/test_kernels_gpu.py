@@ -623,7 +623,7 @@ def test_mha_tc_matches_mma(ops, B, S, H, mask):
     res = {}
     old = lib.cvb_set_mha_impl(0)
     try:
-        for name, m in (("mma", 0), ("tc", 3)):
+        for name, m in (("mma", 0), ("tc", 7)):  # 7: tcgen05 forward + backward, also with an additive mask
             lib.cvb_set_mha_impl(m)
             O, LSE = ops.mha_fwd(qkv, B, S, H, 64, 0.125, attn_mask=amask, key_padding_mask=kpm)
             D = ops.mha_bwd(qkv, O, dO, LSE, B, S, H, 64, 0.125, attn_mask=amask, key_padding_mask=kpm)
@@ -634,6 +634,45 @@ def test_mha_tc_matches_mma(ops, B, S, H, mask):
         a, b = res["tc"][i].double(), res["mma"][i].double()
         r = float((a - b).norm() / (b.norm() + 1e-30))
         assert r <= 4e-3, f"{what}: tcgen05 vs mma.sync rel-L2 {r:.3g}"
+
+
+# ------------------------------------------------------------------------------------------ dropout / stochastic depth
+def test_dropout_kernels(ops):
+    """Hashed-mask dropout (csrc/dropout.cu): keep rate, scaling, residual add, key determinism, backward == forward mask, per-sample rows."""
+    M, C, rps = 4000, 256, 40
+    V = bf(rnd(M, C, seed=91))
+    R = bf(rnd(M, C, seed=92))
+    ones = torch.ones(M, C, device="cuda", dtype=BF)
+    ops.rng_seed(1234)
+    k1, k2 = ops.rng_next("cuda"), ops.rng_next("cuda")
+    assert int(k1) != int(k2)
+    ops.rng_seed(1234)
+    assert int(ops.rng_next("cuda")) == int(k1) and int(ops.rng_next("cuda")) == int(k2)  # same seed -> same key sequence
+    for p in (0.1, 0.5):
+        m1 = ops.dropout_fwd(ones, None, p, k1).float()
+        keep = float((m1 != 0).float().mean())
+        sigma = (p * (1 - p) / (M * C)) ** 0.5
+        assert abs(keep - (1 - p)) <= 5 * sigma + 2e-5, (p, keep)
+        scale = float(torch.tensor(1.0 / (1 - p)).to(BF))
+        assert torch.all((m1 == 0) | ((m1 - scale).abs() < 1e-6))
+        assert torch.equal(m1, ops.dropout_fwd(ones, None, p, k1).float())          # deterministic in the key
+        assert not torch.equal(m1, ops.dropout_fwd(ones, None, p, k2).float())      # a new key draws a new mask
+        assert torch.equal(m1, ops.dropout_bwd(ones, p, k1).float())                # the backward regenerates the forward's mask
+        Y = ops.dropout_fwd(V, R, p, k1).float()
+        ref = R.float() + V.float() * (m1 != 0) / (1 - p)
+        assert float((Y - ref).norm() / ref.norm()) <= 4e-3
+        # columns are dropped independently of rows: no structure along either axis
+        assert abs(float((m1 != 0).float().mean(0).std()) - ((p * (1 - p) / M) ** 0.5)) < 3e-3
+    # stochastic depth: one Bernoulli per sample (rps rows), scaled by 1 / keep
+    pr = 0.3
+    mr = ops.dropout_fwd(ones, None, 0.0, k1, p_row=pr, rows_per_sample=rps).float().view(M // rps, rps * C)
+    assert torch.all((mr == mr[:, :1]))
+    vals = mr[:, 0]
+    assert torch.all((vals == 0) | ((vals - float(torch.tensor(1 / (1 - pr)).to(BF))).abs() < 1e-6))
+    assert 0.5 < float((vals != 0).float().mean()) < 0.9
+    both = ops.dropout_fwd(ones, None, 0.2, k1, p_row=pr, rows_per_sample=rps).float().view(M // rps, rps * C)
+    assert torch.all(both[vals == 0] == 0) and float((both[vals != 0] != 0).float().mean()) > 0.7
+    assert torch.equal(ops.dropout_bwd(ones, 0.2, k1, p_row=pr, rows_per_sample=rps).float().view(M // rps, rps * C), both)
 
 
 @pytest.mark.parametrize("M,C", [(1000, 768), (333, 64), (50, 1000)])

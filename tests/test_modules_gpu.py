@@ -265,6 +265,72 @@ def test_transformer_encoder(pkg, tfx, name):
     run_and_check(m, fx, auto=auto)
 
 
+@pytest.mark.parametrize("p,p_ffn,p_row", [(0.1, 0.0, 0.0), (0.1, 0.2, 0.0), (0.0, 0.0, 0.25)])
+def test_transformer_encoder_dropout_training(pkg, p, p_ffn, p_row):
+    """Training-mode dropout / FFN-hidden dropout / stochastic depth (cvnets/modules/transformer.py:77-100, 139-156; the MobileViT-v1 recipe trains
+    with dropout 0.1).  The module's hashed masks are reproduced from the same generator state (same seed -> same key sequence) and handed to the
+    fp32 oracle as inputs, so outputs, the input gradient and every parameter gradient are compared under IDENTICAL masks."""
+    from ml_cvnets_b200 import ops
+    C, F_, H, N, S = 64, 128, 4, 16, 40
+    shapes = {}
+    O.transformer_encoder_shapes(shapes, "m", C, F_)
+    opts = pkg.default_opts(**{"model.activation.name": "swish"})
+    m = load_seeded(pkg.TransformerEncoder(opts, C, F_, num_heads=H, dropout=p, ffn_dropout=p_ffn, stochastic_dropout=p_row), shapes, 78)
+    P = O.clone_params(O.seeded_fill_(dict(shapes), 78), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(N, S, C, device="cuda", generator=g).bfloat16().float()
+    gy = torch.randn(N, S, C, device="cuda", generator=g).bfloat16().float()
+    ops.rng_seed(99)
+    xg = x.clone().requires_grad_(True)
+    y = m(xg)
+    y.backward(gy.to(y.dtype))
+    # the same key sequence: attention branch, ffn branch, then the ffn-hidden key (functional.TransformerEncoderFn.forward)
+    ops.rng_seed(99)
+    k1, k2 = ops.rng_next("cuda"), ops.rng_next("cuda")
+    ones = lambda c: torch.ones(N * S, c, device="cuda", dtype=torch.bfloat16)  # noqa: E731
+    m_attn = ops.dropout_fwd(ones(C), None, p, k1, p_row=p_row, rows_per_sample=S).float().view(N, S, C)
+    m_ffn = ops.dropout_fwd(ones(C), None, p, k2, p_row=p_row, rows_per_sample=S).float().view(N, S, C)
+    m_hid = ops.dropout_fwd(ones(F_), None, p_ffn, ops.rng_next("cuda")).float().view(N, S, F_) if p_ffn > 0 else None
+    # masks carry bf16(1/keep); the oracle must scale by the exact factor
+    fix = lambda mk, keep: (mk != 0).float() / keep  # noqa: E731
+    masks = (fix(m_attn, (1 - p) * (1 - p_row)), None if m_hid is None else fix(m_hid, 1 - p_ffn), fix(m_ffn, (1 - p) * (1 - p_row)))
+    assert 0 < float((masks[0] == 0).float().mean()) < 0.6
+    xo = x.clone().requires_grad_(True)
+    yo = O.transformer_encoder(P, "m", xo, H, act="swish", drop_masks=masks)
+    yo.backward(gy)
+    assert rel_l2(y, yo) <= 2e-2, rel_l2(y, yo)
+    assert rel_l2(xg.grad, xo.grad) <= 5e-2, rel_l2(xg.grad, xo.grad)
+    for k, prm in m.named_parameters():
+        e = rel_l2(prm.grad, P["m." + k].grad)
+        assert e <= 6e-2, f"{k}: {e:.4g}"
+    # eval mode: identity
+    m.eval()
+    ye = m(x.clone())
+    yoe = O.transformer_encoder(P, "m", x.clone(), H, act="swish")
+    assert rel_l2(ye, yoe) <= 2e-2
+
+
+def test_dropout_layer_and_classifier_dropout(pkg):
+    """Stand-alone Dropout module (cvnets/layers/dropout.py): identity in eval, hashed mask + exact gradient in training; the MobileViT-v1
+    classifier head with classifier_dropout = 0.1 (mobilevit.py:110-113) trains."""
+    from ml_cvnets_b200 import ops
+    d = pkg.Dropout(p=0.25).cuda()
+    x = torch.randn(64, 320, device="cuda").bfloat16().requires_grad_(True)
+    d.eval()
+    assert d(x) is x
+    d.train()
+    ops.rng_seed(5)
+    y = d(x)
+    keep = (y != 0).float()
+    assert 0.65 < float(keep.mean()) < 0.85
+    assert rel_l2(y, x.detach().float() * keep / 0.75) <= 4e-3
+    y.float().sum().backward()
+    assert rel_l2(x.grad, keep / 0.75) <= 4e-3
+    x4 = torch.randn(2, 16, 5, 7, device="cuda")
+    y4 = d(x4)
+    assert y4.shape == x4.shape and 0.6 < float((y4 != 0).float().mean()) < 0.9
+
+
 def test_transformer_encoder_vit_base_shape(pkg):
     """ViT-B/16 geometry ([N,197,768], 12 heads, f=3072, GELU) against the fp32 oracle on this GPU."""
     torch.manual_seed(0)

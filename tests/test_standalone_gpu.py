@@ -102,11 +102,21 @@ def test_inverted_residual_se(pkg, golden_dir, name):
     c = fx["cfg"]
     shapes = {}
     O.inverted_residual_se_shapes(shapes, "m", c["cin"], c["cout"], c["expand_ratio"], use_se=c["use_se"])
-    auto = autocast_errors(lambda P, x: O.inverted_residual_se(P, "m", x, stride=c["stride"], act=c["act_fn_name"]), shapes, fx["seed"], fx)
+    fn = lambda P, x: O.inverted_residual_se(P, "m", x, stride=c["stride"], act=c["act_fn_name"])  # noqa: E731
+    auto = autocast_errors(fn, shapes, fx["seed"], fx)
+    # same-precision comparator for the INPUT gradient: batch-4 train-mode BatchNorm followed by ReLU gates (discontinuous derivative) amplifies
+    # bf16 rounding for torch autocast as well; ours must stay within 1.5x of it (or the fixed 4e-2)
+    Pa = O.clone_params(O.seeded_fill_(dict(shapes), fx["seed"]), device="cuda")
+    xa = fx["x"].cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ya = fn(Pa, xa)
+    ya.backward(fx["gy"].cuda().to(ya.dtype))
+    auto_gx, auto_y = rel_l2(xa.grad, fx["gx"]), rel_l2(ya, fx["y"])
     opts = copy.deepcopy(pkg.default_opts())
     setattr(opts, "model.activation.name", "relu")  # the reference default: fc1 of the SE unit takes the model-wide activation
     m = pkg.InvertedResidualSE(opts, c["cin"], c["cout"], c["expand_ratio"], stride=c["stride"], use_se=c["use_se"], act_fn_name=c["act_fn_name"])
-    run_and_check(load_seeded(m, shapes, fx["seed"]), fx, auto=auto)
+    errs = run_and_check(load_seeded(m, shapes, fx["seed"]), fx, auto=auto, out_tol=max(2e-2, 1.5 * auto_y), gx_tol=max(4e-2, 1.5 * auto_gx))
+    print(f"{name}: y {errs['y']:.4f} (autocast {auto_y:.4f})  gx {errs['gx']:.4f} (autocast {auto_gx:.4f})")
 
 
 @pytest.mark.parametrize("B,HW,C", [(3, 50, 64), (2, 4096, 96), (5, 1, 8)])

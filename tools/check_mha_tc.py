@@ -65,7 +65,7 @@ def stage_check(which, out):
             ref = ref_attn(x, B, S, H, scale, amask, kpm)
             rec = {"stage": which, "B": B, "S": S, "H": H, "mask": mk}
             if which == "fwd":
-                lib.cvb_set_mha_impl(1)
+                lib.cvb_set_mha_impl(5)
                 O1, LSE1 = ops.mha_fwd(qkv, B, S, H, 64, scale, attn_mask=amask, key_padding_mask=kpm)
                 torch.cuda.synchronize()
                 rec.update(tc_vs_ref=rel(O1, ref.detach()), old_vs_ref=rel(O0, ref.detach()), lse_maxdiff=float((LSE1 - LSE0).abs().max()),
@@ -74,7 +74,7 @@ def stage_check(which, out):
             else:
                 ref.backward(dO.float())
                 D0 = ops.mha_bwd(qkv, O0, dO, LSE0, B, S, H, 64, scale, attn_mask=amask, key_padding_mask=kpm)
-                lib.cvb_set_mha_impl(2)
+                lib.cvb_set_mha_impl(6)
                 D1 = ops.mha_bwd(qkv, O0, dO, LSE0, B, S, H, 64, scale, attn_mask=amask, key_padding_mask=kpm)
                 torch.cuda.synchronize()
                 C = H * 64
@@ -102,7 +102,7 @@ def stage_time(out):
         scale = 64 ** -0.5
         rec = {"stage": "time", "B": B, "S": S, "H": H, "mask": mk}
         flops_f = 4.0 * B * H * S * S * 64
-        for name, mask in (("old", 0), ("tc", 3)):
+        for name, mask in (("old", 0), ("tc", 7)):
             lib.cvb_set_mha_impl(mask)
             O, LSE = ops.mha_fwd(qkv, B, S, H, 64, scale, attn_mask=amask, key_padding_mask=kpm)
             for fn, key, fl in ((lambda: ops.mha_fwd(qkv, B, S, H, 64, scale, attn_mask=amask, key_padding_mask=kpm), "fwd", flops_f),
