@@ -52,14 +52,16 @@ class Dropout(nn.Dropout):
             return x
         from . import functional as Fn
         _need_cuda(x, "Dropout")
-        if self.p >= 1.0 or x.shape[-1] % 8:
-            raise NotImplementedError("Dropout: 0 <= p < 1 and a last dimension that is a multiple of 8 have a kernel path")
+        if self.p >= 1.0:
+            raise NotImplementedError("Dropout: 0 <= p < 1")
         if x.dim() == 4:  # [B, C, H, W] maps live channels-last: the kernel sees the [B*H*W, C] matrix
             xc = Fn.to_bf16_cl(x)
             B, C, H, W = xc.shape
             if C % 8:
                 raise NotImplementedError("Dropout: channel count must be a multiple of 8")
             return Fn.to_4d(Fn.DropoutFn.apply(Fn.as_2d(xc), float(self.p)), B, H, W)
+        if x.shape[-1] % 8:
+            raise NotImplementedError("Dropout: the last dimension must be a multiple of 8 (16-byte channel vectors)")
         return Fn.DropoutFn.apply(x, float(self.p))
 
 

@@ -585,16 +585,21 @@ def se_scale_bwd(DY: Tensor, X: Tensor, S: Tensor, B: int, HW: int):
 _RNG = {}
 
 
+def _rng_device(device) -> torch.device:
+    dev = torch.device("cuda") if device is None else torch.device(device)
+    return torch.device("cuda", torch.cuda.current_device()) if dev.index is None else dev  # "cuda" and "cuda:0" are ONE generator
+
+
 def rng_seed(seed: Optional[int] = None, device=None) -> None:
     """(Re)seed the device-resident dropout generator {seed, counter}; default seed = torch.initial_seed() (utils/common_utils.py:68-71 seeds torch)."""
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dev = _rng_device(device)
     seed = torch.initial_seed() if seed is None else int(seed)
     _RNG[dev] = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], device=dev, dtype=torch.int64)
 
 
 def rng_next(device) -> Tensor:
     """Draw a 64-bit mask key on the device (int64 [1]); the counter advances on the device, also when replayed inside a CUDA graph."""
-    dev = torch.device(device)
+    dev = _rng_device(device)
     if dev not in _RNG:
         rng_seed(device=dev)
     key = torch.empty(1, device=dev, dtype=torch.int64)

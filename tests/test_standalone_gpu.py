@@ -305,6 +305,40 @@ def test_mobilevit_v1_xxs_against_reference_fixture(pkg, golden_dir):
     assert not bad, bad[:8]
 
 
+def test_mobilevit_v1_trains_with_recipe_dropouts(pkg):
+    """config/classification/imagenet/mobilevit.yaml trains with mit.dropout 0.1 and classifier_dropout 0.1: the training step must run (hashed-mask
+    dropout inside every TransformerEncoder and in the classifier head), be reproducible from the generator seed, differ between steps, and eval
+    mode must be dropout-free and deterministic."""
+    import torch.nn.functional as F
+    from ml_cvnets_b200 import ops
+    torch.manual_seed(0)
+    model = pkg.MobileViT(pkg.default_mit_opts("xx_small")).cuda().train()
+    assert model.classifier.dropout.p == 0.1 and model.layer_3[1].global_rep[0].std_dropout == 0.1
+    x = torch.randn(8, 3, 192, 192, device="cuda")  # (192: no layer sees S == d, every map is a multiple of the 2x2 patch)
+    y = torch.randint(0, 1000, (8,), device="cuda")
+
+    def step(seed):
+        ops.rng_seed(seed)
+        model.zero_grad(set_to_none=True)
+        for m in model.modules():  # identical BatchNorm state for every run
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.reset_running_stats()
+        lg = model(x)
+        F.cross_entropy(lg.float(), y).backward()
+        return lg.detach().float().clone(), model.classifier.fc.weight.grad.detach().clone()
+
+    l1, g1 = step(11)
+    l2, g2 = step(11)
+    l3, _ = step(12)
+    assert torch.isfinite(l1).all() and torch.isfinite(g1).all()
+    assert rel_l2(l2, l1) <= 2e-2 and rel_l2(g2, g1) <= 5e-2           # same seed -> same masks (up to atomics-order noise)
+    assert rel_l2(l3, l1) > 5 * max(rel_l2(l2, l1), 1e-3)              # another seed -> other masks
+    model.eval()
+    with torch.no_grad():
+        e1, e2 = model(x).float(), model(x).float()
+    assert rel_l2(e2, e1) <= 1e-3
+
+
 def test_clip_against_reference_fixture(pkg, golden_dir):
     """BASELINE.json configs[4] at a reduced geometry (ViT-small image tower, 4-layer causal text transformer): state_dict contract, image /
     text features, contrastive loss and gradients against the REAL reference (tests/golden/make_golden_r2.py)."""
