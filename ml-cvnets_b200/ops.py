@@ -103,6 +103,10 @@ def set_pdl_enabled(on: bool) -> bool:
 # step without the pre-pass), so the policy now needs N >= WIDE_N as well.  CVB_WIDE_K=100000 disables the pre-pass (diagnostics).
 WIDE_K = int(os.environ.get("CVB_WIDE_K", "384"))
 WIDE_N = int(os.environ.get("CVB_WIDE_N", "1024"))
+# weight gradients: every 128-row block of dW (N / 128 CTAs per K block) re-applies the prologue to the SAME activation operand inside its transform
+# warps.  ViT-B (ncu launch list, profiles/r2_step_launches_vit_b16.csv): the LayerNorm-fused weight gradients of qkv_proj / ffn.1 (N = 2304 / 3072,
+# 18 / 24 blocks) ran at 234-312 TFLOP/s against 858 TFLOP/s for the prologue-free ones of the same size -> one pre-pass, then the RAW kernel.
+WIDE_N_WGRAD = int(os.environ.get("CVB_WIDE_N_WGRAD", "1536"))
 
 
 def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: int = A_RAW, A2: Optional[Tensor] = None,
@@ -174,23 +178,27 @@ def pw_wgrad(G: Tensor, A: Tensor, N: int, K: int, *, g_mode: int = A_RAW, G2: O
     lib = _lib()
     if dW is None:
         dW = torch.zeros((N, K), device=G.device, dtype=torch.float32)
-    a = L.WgradArgs()
-    a.M, a.N, a.K = G.shape[0], N, K
-    a.G, a.ldg, a.g_mode = G.data_ptr(), G.stride(0), g_mode
-    if G2 is not None:
-        a.G2, a.ldg2 = G2.data_ptr(), G2.stride(0)
-    a.g_p0, a.g_p1, a.g_p2 = _p(g_p[0]), _p(g_p[1]), _p(g_p[2])
-    a.A, a.lda, a.a_mode = A.data_ptr(), A.stride(0), a_mode
-    a.a_p0, a.a_p1 = _p(a_p[0]), _p(a_p[1])
-    if row_stats is not None:
-        a.row_mean, a.row_rstd = row_stats[0].data_ptr(), row_stats[1].data_ptr()
-    a.rows_per_sample = rows_per_sample
-    a.dW, a.lddw = dW.data_ptr(), dW.stride(0)
-    a.dbias = _p(dbias)
     with _SideCtx(side):
+        A0 = A
+        if a_mode != A_RAW and K >= WIDE_K and N >= WIDE_N_WGRAD:
+            A = apply_load_mode(A, a_mode, K, a_p=a_p, row_stats=row_stats, rows_per_sample=rows_per_sample)  # on the stream of the weight gradient
+            a_mode, a_p, row_stats = A_RAW, (None, None), None
+        a = L.WgradArgs()
+        a.M, a.N, a.K = G.shape[0], N, K
+        a.G, a.ldg, a.g_mode = G.data_ptr(), G.stride(0), g_mode
+        if G2 is not None:
+            a.G2, a.ldg2 = G2.data_ptr(), G2.stride(0)
+        a.g_p0, a.g_p1, a.g_p2 = _p(g_p[0]), _p(g_p[1]), _p(g_p[2])
+        a.A, a.lda, a.a_mode = A.data_ptr(), A.stride(0), a_mode
+        a.a_p0, a.a_p1 = _p(a_p[0]), _p(a_p[1])
+        if row_stats is not None:
+            a.row_mean, a.row_rstd = row_stats[0].data_ptr(), row_stats[1].data_ptr()
+        a.rows_per_sample = rows_per_sample
+        a.dW, a.lddw = dW.data_ptr(), dW.stride(0)
+        a.dbias = _p(dbias)
         L.check(lib.cvb_pw_wgrad(ctypes.byref(a), _stream()), "cvb_pw_wgrad")
         if side:
-            _hold(G, G2, A, dW, dbias)
+            _hold(G, G2, A, A0, dW, dbias)
     _count()
     return dW
 
