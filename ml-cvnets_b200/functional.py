@@ -1200,7 +1200,16 @@ class TransformerEncoderFn(torch.autograd.Function):
         x2 = x.reshape(M, C)
         amask, kpm = _masks(cfg.masks, N, S, x.device)
         ln1 = ops.ln_stats(x2, cfg.eps)
-        qkv = ops.pw_gemm(x2, P.get(cfg.i_wqkv), 3 * C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, bias=bqkv)
+        # wide layers (ViT / CLIP: K = 768 under 18-24 N tiles): the LayerNorm prologue is applied ONCE by a pre-pass (ops.WIDE_K / WIDE_N policy, which
+        # pw_gemm would apply internally) and the normalised tokens are KEPT for the weight gradient of the same projection, which would otherwise
+        # re-normalise them (profiles/r2_step_launches_vit_b16.csv: 24 extra passes of 80 us per step)
+        keep_n = ops.KEEP_NORMALISED and C >= ops.WIDE_K and 3 * C >= ops.WIDE_N_WGRAD and ffn >= ops.WIDE_N_WGRAD
+        xn1 = xn2 = None
+        if keep_n:
+            xn1 = ops.apply_load_mode(x2, A_GN, C, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1)
+            qkv = ops.pw_gemm(xn1, P.get(cfg.i_wqkv), 3 * C, bias=bqkv)
+        else:
+            qkv = ops.pw_gemm(x2, P.get(cfg.i_wqkv), 3 * C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, bias=bqkv)
         O, LSE = ops.mha_fwd(qkv, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
         drop = getattr(cfg, "drop", None)  # (p, p_ffn, p_row) in training with dropout / stochastic depth > 0 (transformer.py:97-100, 139-156)
         keys = None
@@ -1208,7 +1217,11 @@ class TransformerEncoderFn(torch.autograd.Function):
             samp = _fwd_arena(cfg, x.device, 2 * M + 8).f64(2, M)
             X1 = ops.pw_gemm(O, P.get(cfg.i_wo), C, bias=bo, R=x2, samp_stats=samp, rows_per_sample=1)
             ln2 = ops.gn_finalize(samp, C, cfg.eps)
-            h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
+            if keep_n:
+                xn2 = ops.apply_load_mode(X1, A_GN, C, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1)
+                h = ops.pw_gemm(xn2, P.get(cfg.i_w1), ffn, bias=bb1)
+            else:
+                h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
             if cfg.act == ops.ACT_SILU:
                 ha = None
                 X2 = ops.pw_gemm(h, P.get(cfg.i_w2), C, a_mode=A_SILU, bias=bb2, R=X1)
@@ -1222,7 +1235,11 @@ class TransformerEncoderFn(torch.autograd.Function):
             A = ops.pw_gemm(O, P.get(cfg.i_wo), C, bias=bo)
             X1 = ops.dropout_fwd(A, x2, p, k1, p_row=p_row, rows_per_sample=S)
             ln2 = ops.ln_stats(X1, cfg.eps)
-            h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
+            if keep_n:
+                xn2 = ops.apply_load_mode(X1, A_GN, C, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1)
+                h = ops.pw_gemm(xn2, P.get(cfg.i_w1), ffn, bias=bb1)
+            else:
+                h = ops.pw_gemm(X1, P.get(cfg.i_w1), ffn, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, bias=bb1)
             ha = ops.act_fwd(h, cfg.act)
             k3 = None
             if p_ffn > 0:
@@ -1231,7 +1248,7 @@ class TransformerEncoderFn(torch.autograd.Function):
             Fo = ops.pw_gemm(ha, P.get(cfg.i_w2), C, bias=bb2)
             X2 = ops.dropout_fwd(Fo, X1, p, k2, p_row=p_row, rows_per_sample=S)
             keys = (k1, k2, k3)
-        ctx.keys, ctx.drop = keys, drop
+        ctx.keys, ctx.drop, ctx.xn = keys, drop, (xn1, xn2)
         ctx.cfg, ctx.dims, ctx.plist = cfg, (N, S, C), cfg.plist
         ctx.saved = (x2, ln1, qkv, O, LSE, X1, ln2, h, ha, amask, kpm)
         ctx.save_for_backward(g1, b1, g2, b2)
@@ -1269,7 +1286,11 @@ class TransformerEncoderFn(torch.autograd.Function):
         else:
             ops.pw_wgrad_side(dY, ha, C, ffn, dW=D.mat(10, C, ffn), dbias=db2)
             dh = ops.act_bwd(ops.pw_gemm(dY, P.get(cfg.i_w2t), ffn, K=C), h, cfg.act)
-        ops.pw_wgrad_side(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=D.mat(8, ffn, C), dbias=db1)
+        xn1, xn2 = ctx.xn
+        if xn2 is not None:
+            ops.pw_wgrad_side(dh, xn2, ffn, C, dW=D.mat(8, ffn, C), dbias=db1)
+        else:
+            ops.pw_wgrad_side(dh, X1, ffn, C, a_mode=A_GN, a_p=(g2, b2), row_stats=(ln2[0], ln2[1]), rows_per_sample=1, dW=D.mat(8, ffn, C), dbias=db1)
         csf = ar.f64(2, C)
         vF = ops.pw_gemm(dh, P.get(cfg.i_w1t), C, K=ffn)
         if drop is None:
@@ -1288,8 +1309,11 @@ class TransformerEncoderFn(torch.autograd.Function):
         ops.pw_wgrad_side(dA, O, C, C, dW=D.mat(4, C, C), dbias=dbo)
         dO = ops.pw_gemm(dA, P.get(cfg.i_wot), C, K=C)
         dqkv = ops.mha_bwd(qkv, O, dO, LSE, N, S, cfg.heads, cfg.head_dim, cfg.scale, amask, kpm)
-        ops.pw_wgrad_side(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=D.mat(2, 3 * C, C),
-                          dbias=vec(3, 3 * C))
+        if xn1 is not None:
+            ops.pw_wgrad_side(dqkv, xn1, 3 * C, C, dW=D.mat(2, 3 * C, C), dbias=vec(3, 3 * C))
+        else:
+            ops.pw_wgrad_side(dqkv, x2, 3 * C, C, a_mode=A_GN, a_p=(g1, b1), row_stats=(ln1[0], ln1[1]), rows_per_sample=1, dW=D.mat(2, 3 * C, C),
+                              dbias=vec(3, 3 * C))
         csa = ar.f64(2, C)
         vA = ops.pw_gemm(dqkv, P.get(cfg.i_wqkvt), C, K=3 * C)
         dx = ops.ln_bwd(vA, x2, ln1, g1, csa, DRES=dX1)

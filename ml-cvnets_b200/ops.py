@@ -107,6 +107,8 @@ WIDE_N = int(os.environ.get("CVB_WIDE_N", "1024"))
 # warps.  ViT-B (ncu launch list, profiles/r2_step_launches_vit_b16.csv): the LayerNorm-fused weight gradients of qkv_proj / ffn.1 (N = 2304 / 3072,
 # 18 / 24 blocks) ran at 234-312 TFLOP/s against 858 TFLOP/s for the prologue-free ones of the same size -> one pre-pass, then the RAW kernel.
 WIDE_N_WGRAD = int(os.environ.get("CVB_WIDE_N_WGRAD", "1536"))
+# TransformerEncoderFn keeps the pre-pass output of its two LayerNorm-fused projections for their weight gradients (2 x [tokens, C] bf16 per layer)
+KEEP_NORMALISED = int(os.environ.get("CVB_KEEP_NORMALISED", "1")) != 0
 
 
 def pw_gemm(A: Tensor, W: Tensor, N: int, *, K: Optional[int] = None, a_mode: int = A_RAW, A2: Optional[Tensor] = None,
