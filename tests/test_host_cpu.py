@@ -186,6 +186,48 @@ print("OK")
     assert "OK" in out.stdout
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cvnets"), reason="reference checkout not present (GPU box)")
+def test_se_block_and_dropout_children_match_reference_contract():
+    """InvertedResidualSE / SqueezeExcitation and the dropout / stochastic-depth children of TransformerEncoder: constructor
+    parameters, child tree, state_dict keys / shapes and repr head against the reference checkout; rebind_modules() swaps the block in."""
+    code = r"""
+import sys, os, argparse, inspect
+sys.path.insert(0, %r); sys.path.insert(0, "/root/reference"); os.chdir("/root/reference")
+import ml_cvnets_b200 as ours
+import ml_cvnets_b200.register as r
+from cvnets import modeling_arguments
+from cvnets.modules import InvertedResidualSE as RefSE, SqueezeExcitation as RefSq, TransformerEncoder as RefEnc
+def params(f): return [p for p in inspect.signature(f).parameters if p not in ("args", "kwargs")]
+assert params(ours.InvertedResidualSE.__init__) == params(RefSE.__init__)
+assert params(ours.SqueezeExcitation.__init__) == params(RefSq.__init__)
+opts = modeling_arguments(argparse.ArgumentParser()).parse_args([])
+for kw in (dict(expand_ratio=4, stride=1, use_se=True, act_fn_name="hard_swish"), dict(expand_ratio=3, stride=2, use_se=True, act_fn_name="relu"),
+           dict(expand_ratio=1, stride=1, use_se=False, act_fn_name="relu"), dict(expand_ratio=2, stride=1, use_se=True, kernel_size=5)):
+    a, b = ours.InvertedResidualSE(opts, 24, 24, **kw), RefSE(opts, 24, 24, **kw)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys()), (list(sa.keys()), list(sb.keys()))
+    assert all(sa[k].shape == sb[k].shape and sa[k].dtype == sb[k].dtype for k in sa)
+    a.load_state_dict(sb, strict=True)
+    assert [n for n, _ in a.block.named_children()] == [n for n, _ in b.block.named_children()]
+    assert list(a.block._modules) == list(b.block._modules)                       # incl. the shared activation registered twice
+    assert repr(a) == repr(b), (repr(a), repr(b))
+    assert a.use_res_connect == b.use_res_connect
+e1, e2 = ours.TransformerEncoder(opts, 64, 128, num_heads=4, dropout=0.1, ffn_dropout=0.2), RefEnc(opts, 64, 128, num_heads=4, dropout=0.1, ffn_dropout=0.2)
+assert [type(m).__name__ for m in e1.pre_norm_ffn] == [type(m).__name__ for m in e2.pre_norm_ffn]
+assert (e1.pre_norm_mha[2].p, e1.pre_norm_ffn[3].p, e1.pre_norm_ffn[5].p) == (e2.pre_norm_mha[2].p, e2.pre_norm_ffn[3].p, e2.pre_norm_ffn[5].p)
+s1, s2 = ours.TransformerEncoder(opts, 64, 128, num_heads=4, stochastic_dropout=0.2), RefEnc(opts, 64, 128, num_heads=4, stochastic_dropout=0.2)
+assert type(s1.drop_path).__name__ == type(s2.drop_path).__name__ == "StochasticDepth" and s1.drop_path.p == s2.drop_path.p
+assert list(s1.state_dict().keys()) == list(s2.state_dict().keys())
+r.rebind_modules()
+import cvnets.modules as cm
+assert cm.InvertedResidualSE is ours.InvertedResidualSE and cm.SqueezeExcitation is ours.SqueezeExcitation
+print("OK")
+""" % REPO
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "OK" in out.stdout
+
+
 def _gloo_worker(rank, world, port, q):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, REPO)
