@@ -636,6 +636,21 @@ def test_mha_tc_matches_mma(ops, B, S, H, mask):
         assert r <= 4e-3, f"{what}: tcgen05 vs mma.sync rel-L2 {r:.3g}"
 
 
+@pytest.mark.parametrize("M,K", [(1000, 768), (333, 64), (70, 3072)])
+@pytest.mark.parametrize("a_mode", [1, 2, 3, 4, 5])
+def test_apply_load_mode_prepass(ops, M, K, a_mode):
+    """The wide-layer pre-pass (ops.WIDE_K / WIDE_N policy): OUT = load(A) materialised once, against the fp32 restatement of every load mode."""
+    rps = 50
+    nb = (M + rps - 1) // rps
+    A, A2 = bf(rnd(M, K, seed=11)), bf(rnd(M, K, seed=12))
+    p = (rnd(K, seed=13) * 0.5 + 1.0, rnd(K, seed=14) * 0.3, rnd(K, seed=15) * 0.2)
+    row = (rnd(nb, seed=16) * 0.1, rnd(nb, seed=17).abs() + 0.5)
+    out = ops.apply_load_mode(A, a_mode, K, A2=A2 if a_mode == 5 else None, a_p=p, row_stats=row if a_mode == 4 else None,
+                              rows_per_sample=rps if a_mode == 4 else 0)
+    ref = load_ref(a_mode, A, p, x2=A2, row=row, rps=rps)
+    close(out, ref, what=f"apply_load_mode mode {a_mode}")
+
+
 # ------------------------------------------------------------------------------------------ dropout / stochastic depth
 def test_dropout_kernels(ops):
     """Hashed-mask dropout (csrc/dropout.cu): keep rate, scaling, residual add, key determinism, backward == forward mask, per-sample rows."""
