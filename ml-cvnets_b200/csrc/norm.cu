@@ -439,25 +439,20 @@ __global__ void __launch_bounds__(NT) ln_bwd_kernel(const bf16* __restrict__ V, 
                                                     bf16* __restrict__ DX, int64_t M, int C, double* dgamma, double* dbeta, double* col_sum) {
   pdl_wait();
   pdl_trigger();
-  extern __shared__ float sred[];  // [3][C]
+  extern __shared__ float sred[];  // [3][C] per-channel sums of the CTA (dbeta, dgamma, column sums of DX) + [C] gamma
+  float* sgam = sred + 3 * C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 3 * C; i += NT) sred[i] = 0.f;
+  for (int i = tid; i < C; i += NT) sgam[i] = gamma[i];
   __syncthreads();
   const int nch = C / 8;
-  float gm[LNB_MAXCH][8], sb[LNB_MAXCH][8], sg[LNB_MAXCH][8], sx[LNB_MAXCH][8];
-#pragma unroll
-  for (int q = 0; q < LNB_MAXCH; ++q) {
-    const int ch = lane + 32 * q;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      gm[q][e] = (ch < nch) ? __ldg(gamma + ch * 8 + e) : 0.f;
-      sb[q][e] = 0.f; sg[q][e] = 0.f; sx[q][e] = 0.f;
-    }
-  }
+  // The per-channel sums go to shared memory with one reduction per (row, channel): keeping them in registers (96 accumulators per lane at C = 768)
+  // cost 246 registers = 8 warps per SM, and the kernel ran at 1.3 TB/s on the ViT-B shape (profiles/r2_step_launches_vit_b16.csv)
   const float invC = 1.0f / (float)C;
   for (int64_t row = (int64_t)blockIdx.x * (NT / 32) + warp; row < M; row += (int64_t)gridDim.x * (NT / 32)) {
     const float mu = mean[row], rs = rstd[row];
     float v[LNB_MAXCH][8], xh[LNB_MAXCH][8];
+    uint4 dres[LNB_MAXCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int q = 0; q < LNB_MAXCH; ++q) {
@@ -465,14 +460,24 @@ __global__ void __launch_bounds__(NT) ln_bwd_kernel(const bf16* __restrict__ V, 
       if (ch < nch) {
         unpack8(ldg16_stream(V + row * C + ch * 8), v[q]);
         unpack8(ldg16_stream(X + row * C + ch * 8), xh[q]);
+        if (DRES) dres[q] = ldg16_stream(DRES + row * C + ch * 8);  // issued with the other loads, consumed after the row reduction
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < LNB_MAXCH; ++q) {
+      const int ch = lane + 32 * q;
+      if (ch < nch) {
+        float gq[8];
+        *reinterpret_cast<float4*>(gq) = *reinterpret_cast<const float4*>(sgam + ch * 8);
+        *reinterpret_cast<float4*>(gq + 4) = *reinterpret_cast<const float4*>(sgam + ch * 8 + 4);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           xh[q][e] = (xh[q][e] - mu) * rs;
-          const float g = v[q][e] * gm[q][e];
-          s1 += g;
-          s2 = fmaf(g, xh[q][e], s2);
-          sb[q][e] += v[q][e];
-          sg[q][e] = fmaf(v[q][e], xh[q][e], sg[q][e]);
+          atomicAdd(&sred[e * nch + ch], v[q][e]);  // [element][chunk] layout: the 32 lanes of a reduction hit 32 different banks
+          atomicAdd(&sred[C + e * nch + ch], v[q][e] * xh[q][e]);
+          v[q][e] *= gq[e];  // from here on v holds g = V * gamma
+          s1 += v[q][e];
+          s2 = fmaf(v[q][e], xh[q][e], s2);
         }
       }
     }
@@ -483,35 +488,24 @@ __global__ void __launch_bounds__(NT) ln_bwd_kernel(const bf16* __restrict__ V, 
       const int ch = lane + 32 * q;
       if (ch < nch) {
         float d[8];
-        if (DRES) unpack8(ldg16_stream(DRES + row * C + ch * 8), d);
+        if (DRES) unpack8(dres[q], d);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float o = rs * (v[q][e] * gm[q][e] - s1 - xh[q][e] * s2);
+          float o = rs * (v[q][e] - s1 - xh[q][e] * s2);
           if (DRES) o += d[e];
           d[e] = o;
-          sx[q][e] += o;
+          if (col_sum) atomicAdd(&sred[2 * C + e * nch + ch], o);
         }
         stg16(DX + row * C + ch * 8, pack8(d));
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < LNB_MAXCH; ++q) {
-    const int ch = lane + 32 * q;
-    if (ch < nch) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&sred[ch * 8 + e], sb[q][e]);
-        atomicAdd(&sred[C + ch * 8 + e], sg[q][e]);
-        atomicAdd(&sred[2 * C + ch * 8 + e], sx[q][e]);
-      }
-    }
-  }
   __syncthreads();
   for (int i = tid; i < C; i += NT) {
-    atomicAdd(dbeta + i, (double)sred[i]);
-    atomicAdd(dgamma + i, (double)sred[C + i]);
-    if (col_sum) atomicAdd(col_sum + i, (double)sred[2 * C + i]);
+    const int t = (i & 7) * (C / 8) + (i >> 3);  // channel i lives at [element i % 8][chunk i / 8]
+    atomicAdd(dbeta + i, (double)sred[t]);
+    atomicAdd(dgamma + i, (double)sred[C + t]);
+    if (col_sum) atomicAdd(col_sum + i, (double)sred[2 * C + t]);
   }
 }
 
@@ -902,7 +896,7 @@ extern "C" int cvb_ln_bwd(const void* V, const void* X, const float* mean, const
   int64_t ctas = (M + NT / 32 - 1) / (NT / 32);
   const int64_t cap = 4 * (int64_t)cvb_num_sms();
   if (ctas > cap) ctas = cap;
-  CVB_CUDA(cvb_launch(ln_bwd_kernel, (unsigned)ctas, NT, (size_t)3 * C * sizeof(float), static_cast<cudaStream_t>(stream), static_cast<const bf16*>(V),
+  CVB_CUDA(cvb_launch(ln_bwd_kernel, (unsigned)ctas, NT, (size_t)4 * C * sizeof(float), static_cast<cudaStream_t>(stream), static_cast<const bf16*>(V),
                       static_cast<const bf16*>(X), mean, rstd, gamma, static_cast<const bf16*>(DRES), static_cast<bf16*>(DX), M, C, dgamma, dbeta,
                       col_sum));
   CVB_LAUNCH_CHECK();
